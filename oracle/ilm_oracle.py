@@ -1,0 +1,702 @@
+"""CPU oracle for the immersed-layer operator hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a from-scratch numpy/scipy restatement of the arithmetic that
+JuliaIBPM/ImmersedLayers.jl v0.5.6 performs on its hot path (regularize! /
+interpolate!, the staggered stencils, the lattice-Green's-function inverse
+Laplacian, the Schur-complement builders and the Dirichlet block-LU solve).
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import it; the product (``immersedlayers.jl_b200``)
+never does.
+
+PARITY PINNING.  The path's inner arithmetic lives in un-vendored Julia
+dependencies of the reference (CartesianGrids.jl, compat "0.1.29, 0.2",
+/root/reference/Project.toml:8,20; no Manifest) and there is no Julia
+toolchain here, so the reference cannot be executed.  The restatement follows
+SURVEY.md Appendix A (published algorithm of CartesianGrids: DDF formulas,
+staggered index ranges, LGF integral, CircularConvolution) and the
+*composition* code that IS in the reference (file:line cited per function).
+It is pinned against everything the reference holds for this path:
+  * the adjoint / partition-of-unity identities of test/tools.jl:107,112,119-120,
+  * the executed-notebook golden values of SURVEY.md Appendix B
+    (examples/caches.ipynb, examples/Layers.ipynb),
+  * exact LGF values G(1,0)=1/4, G(1,1)=1/pi, G(2,0)=1-2/pi and L*G=delta,
+  * physics checks of test/surface_ops.jl (mask integral, operator norms).
+No reference test pins a field to 1e-12, nor the far-field constant c0, the
+LGF table values or the tensor-component order: for those the header says
+"parity unpinned" (see DESIGN.md section 3).
+
+Conventions: size(g)=(NX,NY) dual cells incl. ghosts; arrays
+are indexed a[i-1, j-1] for the 1-based Julia index (i, j), x first; flattening
+with order='F' gives Julia's memory layout.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.fft
+import scipy.linalg
+import scipy.sparse as sp
+
+# --------------------------------------------------------------------------
+# layouts
+# --------------------------------------------------------------------------
+PRIMAL, DUAL, XEDGE, YEDGE = "primal", "dual", "xedge", "yedge"
+KINDS = (PRIMAL, DUAL, XEDGE, YEDGE)
+
+
+def field_shape(kind, NX, NY):
+    """Element counts per layout: Nodes{Primal} (NX-1,NY-1); Nodes{Dual}
+    (NX,NY); Edges{Primal}.u (NX,NY-1); Edges{Primal}.v (NX-1,NY)."""
+    return {PRIMAL: (NX - 1, NY - 1), DUAL: (NX, NY),
+            XEDGE: (NX, NY - 1), YEDGE: (NX - 1, NY)}[kind]
+
+
+def field_shift(kind):
+    """Index-space offset of entry (i,j): position = (i - sx, j - sy)."""
+    return {PRIMAL: (0.0, 0.0), DUAL: (0.5, 0.5),
+            XEDGE: (0.5, 0.0), YEDGE: (0.0, 0.5)}[kind]
+
+
+class Grid:
+    """PhysicalGrid surrogate: (NX, NY, dx, I0) passed explicitly
+    (upstream auto-tunes the size, never re-derive it)."""
+
+    def __init__(self, NX, NY, dx, I0):
+        self.NX, self.NY, self.dx = int(NX), int(NY), float(dx)
+        self.I0 = (int(I0[0]), int(I0[1]))
+
+    def zeros(self, kind):
+        return np.zeros(field_shape(kind, self.NX, self.NY), order="F")
+
+    def coords(self, kind):
+        mx, my = field_shape(kind, self.NX, self.NY)
+        sx, sy = field_shift(kind)
+        x = (np.arange(1, mx + 1) - sx - self.I0[0]) * self.dx
+        y = (np.arange(1, my + 1) - sy - self.I0[1]) * self.dx
+        return x, y
+
+
+# --------------------------------------------------------------------------
+# discrete delta functions.  The operation order below is the
+# contract shared with csrc/ilm_ddf.h so that tables are bit-exact.
+# --------------------------------------------------------------------------
+_C1 = 0.40454998233983938      # 17/48 + sqrt(3) pi/108
+_C2 = 1.0954500176601606       # 55/48 - sqrt(3) pi/108
+_S12 = 0.14433756729740644     # sqrt(3)/12
+_S2 = 0.86602540378443865      # sqrt(3)/2
+_S36 = 0.048112522432468814    # sqrt(3)/36
+_C1312 = 1.0833333333333333    # 13/12
+_C148 = 0.020833333333333332   # 1/48
+
+# fdlibm e_asin.c constants (Sun Microsystems, the algorithm Julia's Base.asin
+# also implements)
+_pio2_hi = 1.57079632679489655800e+00
+_pio2_lo = 6.12323399573676603587e-17
+_pio4_hi = 7.85398163397448278999e-01
+_pS = (1.66666666666666657415e-01, -3.25565818622400915405e-01,
+       2.01212532134862925881e-01, -4.00555345006794114027e-02,
+       7.91534994289814532176e-04, 3.47933107596021167570e-05)
+_qS = (-2.40339491173441421878e+00, 2.02094576023350569471e+00,
+       -6.88283971605453293030e-01, 7.70381505559019352791e-02)
+
+
+def asin_fdlibm(x):
+    """asin restated from the published fdlibm algorithm with a fixed
+    operation order (no FMA), valid for |x| <= 1."""
+    x = np.asarray(x, dtype=np.float64)
+    ax = np.abs(x)
+    out = np.empty_like(x)
+
+    def pq(t):
+        p = t * (_pS[0] + t * (_pS[1] + t * (_pS[2] + t * (_pS[3] + t * (_pS[4] + t * _pS[5])))))
+        q = 1.0 + t * (_qS[0] + t * (_qS[1] + t * (_qS[2] + t * _qS[3])))
+        return p, q
+
+    small = ax < 0.5
+    tiny = ax < 2.0 ** -27
+    xs = x[small]
+    t = xs * xs
+    p, q = pq(t)
+    w = p / q
+    res = xs + xs * w
+    res = np.where(tiny[small], xs, res)
+    out[small] = res
+
+    big = ~small
+    xb = ax[big]
+    w = 1.0 - xb
+    t = w * 0.5
+    p, q = pq(t)
+    s = np.sqrt(t)
+    # |x| >= 0.975
+    w1 = p / q
+    t1 = _pio2_hi - (2.0 * (s + s * w1) - _pio2_lo)
+    # 0.5 <= |x| < 0.975
+    wl = (s.view(np.uint64) & np.uint64(0xFFFFFFFF00000000)).view(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        c = (t - wl * wl) / (s + wl)
+    r = p / q
+    p2 = 2.0 * s * r - (_pio2_lo - 2.0 * c)
+    q2 = _pio4_hi - 2.0 * wl
+    t2 = _pio4_hi - (p2 - q2)
+    # fdlibm tests the high word: ix >= 0x3FEF3333
+    hi = (xb.view(np.uint64) >> np.uint64(32)).astype(np.int64)
+    tb = np.where(hi >= 0x3FEF3333, t1, t2)
+    tb = np.where(xb >= 1.0, xb * _pio2_hi + xb * _pio2_lo, tb)
+    out[big] = np.where(x[big] > 0, tb, -tb)
+    return out
+
+
+def ddf_yang3(r):
+    r = np.abs(np.asarray(r, dtype=np.float64))
+    out = np.zeros_like(r)
+    a = r <= 1.0
+    ra = r[a]
+    rr = ra * ra
+    s = np.sqrt(((-12.0 * rr) + 12.0 * ra) + 1.0)
+    t3 = ((1.0 - 2.0 * ra) * 0.0625) * s
+    t4 = _S12 * asin_fdlibm(_S2 * (2.0 * ra - 1.0))
+    out[a] = (((_C1 + ra * 0.25) - rr * 0.25) + t3) - t4
+    b = (r > 1.0) & (r < 2.0)
+    rb = r[b]
+    rr = rb * rb
+    s = np.sqrt(((-12.0 * rr) + 36.0 * rb) - 23.0)
+    t3 = ((2.0 * rb - 3.0) * _C148) * s
+    t4 = _S36 * asin_fdlibm(_S2 * (2.0 * rb - 3.0))
+    out[b] = (((_C2 - _C1312 * rb) + rr * 0.25) + t3) + t4
+    return out
+
+
+def ddf_m3(r):
+    r = np.abs(np.asarray(r, dtype=np.float64))
+    out = np.zeros_like(r)
+    a = r <= 0.5
+    out[a] = 0.75 - r[a] * r[a]
+    b = (r > 0.5) & (r < 1.5)
+    d = 1.5 - r[b]
+    out[b] = 0.5 * (d * d)
+    return out
+
+
+def ddf_roma(r):
+    r = np.abs(np.asarray(r, dtype=np.float64))
+    out = np.zeros_like(r)
+    a = r <= 0.5
+    out[a] = (1.0 + np.sqrt(1.0 - 3.0 * (r[a] * r[a]))) / 3.0
+    b = (r > 0.5) & (r < 1.5)
+    d = 1.0 - r[b]
+    out[b] = ((5.0 - 3.0 * r[b]) - np.sqrt(1.0 - 3.0 * (d * d))) / 6.0
+    return out
+
+
+def ddf_m4prime(r):
+    r = np.abs(np.asarray(r, dtype=np.float64))
+    out = np.zeros_like(r)
+    a = r <= 1.0
+    rr = r[a] * r[a]
+    out[a] = (1.0 - 2.5 * rr) + 1.5 * (rr * r[a])
+    b = (r > 1.0) & (r < 2.0)
+    d = 2.0 - r[b]
+    out[b] = (0.5 * (d * d)) * (1.0 - r[b])
+    return out
+
+
+def ddf_witchhat(r):
+    r = np.abs(np.asarray(r, dtype=np.float64))
+    return np.where(r < 1.0, 1.0 - r, 0.0)
+
+
+# name -> (function, support radius rho, window width W)
+DDFS = {
+    "yang3": (ddf_yang3, 2.0, 4),
+    "m3": (ddf_m3, 1.5, 3),
+    "roma": (ddf_roma, 1.5, 3),
+    "m4prime": (ddf_m4prime, 2.0, 4),
+    "witchhat": (ddf_witchhat, 1.0, 2),
+}
+
+
+# --------------------------------------------------------------------------
+# Regularize / R / E tables (reference call sites
+# src/cache.jl:305-314 (weights), :328-347 (matrices))
+# --------------------------------------------------------------------------
+GRID_SCALING, INDEX_SCALING = "grid", "index"
+
+
+class Table:
+    """Per-point window table for one target layout.
+    i0,j0: 0-based array index of the first window entry (may be out of range,
+    entries outside the field are masked); wR (N,W,W) regularization weights
+    indexed [k, a(x), b(y)]; wE same for interpolation; valid mask."""
+
+    def __init__(self, kind, shape, i0, j0, wR, wE, valid):
+        self.kind, self.shape = kind, shape
+        self.i0, self.j0, self.wR, self.wE, self.valid = i0, j0, wR, wE, valid
+        self.N, self.W = wR.shape[0], wR.shape[1]
+
+    def linear_index(self):
+        """0-based column-major linear index (N,W,W); -1 where masked."""
+        mx, _ = self.shape
+        a = np.arange(self.W)
+        ii = self.i0[:, None, None] + a[None, :, None]
+        jj = self.j0[:, None, None] + a[None, None, :]
+        lin = ii + mx * jj
+        return np.where(self.valid, lin, -1)
+
+
+def scaled_points(grid, x, y):
+    """xs = x/dx + I0 (A.2)."""
+    return np.asarray(x) / grid.dx + grid.I0[0], np.asarray(y) / grid.dx + grid.I0[1]
+
+
+def point_weights(grid, ds, scaling):
+    """GridScaling: w = ds/dx^2 (src/cache.jl:306-307 passes weights=a.data and
+    upstream divides by dx*dx); IndexScaling: w = 1 (issymmetric, :309-310)."""
+    ds = np.asarray(ds, dtype=np.float64)
+    if scaling == GRID_SCALING:
+        return ds / (grid.dx * grid.dx)
+    return np.ones_like(ds)
+
+
+def build_table(grid, x, y, ds, kind, ddf="yang3", scaling=GRID_SCALING):
+    fn, rho, W = DDFS[ddf]
+    xs, ys = scaled_points(grid, x, y)
+    wgt = point_weights(grid, ds, scaling)
+    sx, sy = field_shift(kind)
+    mx, my = field_shape(kind, grid.NX, grid.NY)
+    N = xs.shape[0]
+    # first 1-based grid index of the window
+    ib = np.floor((xs + sx) - rho).astype(np.int64) + 1
+    jb = np.floor((ys + sy) - rho).astype(np.int64) + 1
+    a = np.arange(W)
+    ri = ((ib[:, None] + a[None, :]) - sx) - xs[:, None]
+    rj = ((jb[:, None] + a[None, :]) - sy) - ys[:, None]
+    px = fn(ri)
+    py = fn(rj)
+    wE = px[:, :, None] * py[:, None, :]
+    wR = wE * wgt[:, None, None]
+    i1 = ib[:, None, None] + a[None, :, None]
+    j1 = jb[:, None, None] + a[None, None, :]
+    valid = (i1 >= 1) & (i1 <= mx) & (j1 >= 1) & (j1 <= my)
+    valid = np.broadcast_to(valid, (N, W, W)).copy()
+    wR = np.where(valid, wR, 0.0)
+    wE = np.where(valid, wE, 0.0)
+    if scaling == INDEX_SCALING:
+        wE = wR.copy()
+    return Table(kind, (mx, my), ib - 1, jb - 1, wR, wE, valid)
+
+
+def regularize(tab, f):
+    """s = R f (src/surface_operators.jl:38-41: fill!(s,0); mul!(s,Rc,f)).
+    CSC mat-vec order: columns (points) ascending, y[row] += a*x[col], the
+    product rounded before the add."""
+    mx, my = tab.shape
+    out = np.zeros(mx * my)
+    lin = tab.linear_index()
+    # order (k, b, a): rows ascending inside a column
+    lin_o = np.transpose(lin, (0, 2, 1)).reshape(-1)
+    val = np.transpose(tab.wR * np.asarray(f)[:, None, None], (0, 2, 1)).reshape(-1)
+    m = lin_o >= 0
+    np.add.at(out, lin_o[m], val[m])
+    return out.reshape((mx, my), order="F")
+
+
+def interpolate(tab, s):
+    """f = E s (src/surface_operators.jl:80-83).  CSC mat-vec over grid
+    columns in ascending linear index: per point the sum runs b (y) outer,
+    a (x) inner."""
+    s = np.asarray(s)
+    N, W = tab.N, tab.W
+    f = np.zeros(N)
+    mx, my = tab.shape
+    for b in range(W):
+        for a in range(W):
+            v = tab.valid[:, a, b]
+            ii = np.clip(tab.i0 + a, 0, mx - 1)
+            jj = np.clip(tab.j0 + b, 0, my - 1)
+            term = tab.wE[:, a, b] * s[ii, jj]
+            f = f + np.where(v, term, 0.0)
+    return f
+
+
+def R_matrix(tab):
+    """scipy CSC regularization matrix (grid x N), the structure upstream uses."""
+    lin = tab.linear_index()
+    k = np.broadcast_to(np.arange(tab.N)[:, None, None], lin.shape)
+    m = lin >= 0
+    mx, my = tab.shape
+    return sp.csc_matrix((tab.wR[m], (lin[m], k[m])), shape=(mx * my, tab.N))
+
+
+def E_matrix(tab):
+    lin = tab.linear_index()
+    k = np.broadcast_to(np.arange(tab.N)[:, None, None], lin.shape)
+    m = lin >= 0
+    mx, my = tab.shape
+    return sp.csc_matrix((tab.wE[m], (k[m], lin[m])), shape=(tab.N, mx * my))
+
+
+# --------------------------------------------------------------------------
+# staggered stencils, unscaled.  Outputs are zero outside the
+# stated ranges (the reference zero-fills first: src/grid_operators.jl:26,46,
+# 62,80,98).  Python slices below are the 1-based ranges shifted by one.
+# --------------------------------------------------------------------------
+def curl_n2e(grid, s):
+    """curl!(Edges{Primal} <- Nodes{Dual})."""
+    NX, NY = grid.NX, grid.NY
+    u = np.zeros((NX, NY - 1), order="F")
+    v = np.zeros((NX - 1, NY), order="F")
+    u[:, :] = s[:, 1:] - s[:, :-1]
+    v[:, :] = s[:-1, :] - s[1:, :]
+    return u, v
+
+
+def curl_e2n(grid, u, v):
+    """curl!(Nodes{Dual} <- Edges{Primal}): w[x,y]=u[x,y-1]-u[x,y]-v[x-1,y]+v[x,y],
+    x in 2:NX-1, y in 2:NY-1."""
+    NX, NY = grid.NX, grid.NY
+    w = np.zeros((NX, NY), order="F")
+    w[1:NX - 1, 1:NY - 1] = ((u[1:NX - 1, 0:NY - 2] - u[1:NX - 1, 1:NY - 1])
+                             - v[0:NX - 2, 1:NY - 1]) + v[1:NX - 1, 1:NY - 1]
+    return w
+
+
+def divergence_e2n(grid, u, v):
+    """divergence!(Nodes{Primal} <- Edges{Primal}): p[x,y]=-u[x,y]+u[x+1,y]-v[x,y]+v[x,y+1]."""
+    NX, NY = grid.NX, grid.NY
+    p = np.zeros((NX - 1, NY - 1), order="F")
+    p[:, :] = ((-u[0:NX - 1, :] + u[1:NX, :]) - v[:, 0:NY - 1]) + v[:, 1:NY]
+    return p
+
+
+def grad_n2e(grid, p):
+    """grad!(Edges{Primal} <- Nodes{Primal}): u[x,y]=p[x,y]-p[x-1,y] (x 2:NX-1),
+    v[x,y]=p[x,y]-p[x,y-1] (y 2:NY-1)."""
+    NX, NY = grid.NX, grid.NY
+    u = np.zeros((NX, NY - 1), order="F")
+    v = np.zeros((NX - 1, NY), order="F")
+    u[1:NX - 1, :] = p[1:NX - 1, :] - p[0:NX - 2, :]
+    v[:, 1:NY - 1] = p[:, 1:NY - 1] - p[:, 0:NY - 2]
+    return u, v
+
+
+def grad_e2t(grid, u, v):
+    """grad!(EdgeGradient{Primal,Dual} <- Edges{Primal}); returns dudx,dudy,dvdx,dvdy."""
+    NX, NY = grid.NX, grid.NY
+    dudx = np.zeros((NX - 1, NY - 1), order="F")
+    dvdy = np.zeros((NX - 1, NY - 1), order="F")
+    dudy = np.zeros((NX, NY), order="F")
+    dvdx = np.zeros((NX, NY), order="F")
+    dudx[:, :] = u[1:NX, :] - u[0:NX - 1, :]
+    dvdy[:, :] = v[:, 1:NY] - v[:, 0:NY - 1]
+    dudy[1:NX - 1, 1:NY - 1] = u[1:NX - 1, 1:NY - 1] - u[1:NX - 1, 0:NY - 2]
+    dvdx[1:NX - 1, 1:NY - 1] = v[1:NX - 1, 1:NY - 1] - v[0:NX - 2, 1:NY - 1]
+    return dudx, dudy, dvdx, dvdy
+
+
+def divergence_t2e(grid, dudx, dudy, dvdx, dvdy):
+    """divergence!(Edges{Primal} <- EdgeGradient)."""
+    NX, NY = grid.NX, grid.NY
+    u = np.zeros((NX, NY - 1), order="F")
+    v = np.zeros((NX - 1, NY), order="F")
+    u[1:NX - 1, :] = ((dudx[1:NX - 1, :] - dudx[0:NX - 2, :])
+                      + dudy[1:NX - 1, 1:NY]) - dudy[1:NX - 1, 0:NY - 1]
+    v[:, 1:NY - 1] = ((dvdx[1:NX, 1:NY - 1] - dvdx[0:NX - 1, 1:NY - 1])
+                      + dvdy[:, 1:NY - 1]) - dvdy[:, 0:NY - 2]
+    return u, v
+
+
+def laplacian(grid, w, kind, factor=1.0):
+    """5-point stencil times L.factor on the layout's interior (A.3)."""
+    mx, my = w.shape
+    out = np.zeros_like(w, order="F")
+    c = w[1:mx - 1, 1:my - 1]
+    out[1:mx - 1, 1:my - 1] = ((((-4.0 * c + w[0:mx - 2, 1:my - 1])
+                                 + w[2:mx, 1:my - 1]) + w[1:mx - 1, 0:my - 2])
+                               + w[1:mx - 1, 2:my]) * factor
+    return out
+
+
+# --------------------------------------------------------------------------
+# lattice Green's function convolution
+# --------------------------------------------------------------------------
+EULER_GAMMA = 0.57721566490153286
+
+
+def lgf_c0(DX=1.0):
+    """Far-field constant of ldiv!: (gamma + 0.5 ln 8 - ln DX)/(2 pi) (A.5)."""
+    return (EULER_GAMMA + 0.5 * np.log(8.0) - np.log(DX)) / (2.0 * np.pi)
+
+
+class ConvPlan:
+    """CircularConvolution of upstream: kernel table G (NX,NY) mirrored to
+    (2NX-1, 2NY-1), multiplier precomputed with rfft2; apply = zero-pad,
+    rfft2, multiply, irfft2, crop at (NX,NY)."""
+
+    def __init__(self, G, workers=1):
+        M, N = G.shape
+        self.M, self.N = M, N
+        A = np.zeros((2 * M - 1, 2 * N - 1))
+        A[M - 1:, N - 1:] = G
+        A[:M - 1, N - 1:] = G[:0:-1, :]
+        A[M - 1:, :N - 1] = G[:, :0:-1]
+        A[:M - 1, :N - 1] = G[:0:-1, :0:-1]
+        self.workers = workers
+        self.Ghat = scipy.fft.rfft2(A, workers=workers)
+
+    def apply(self, w):
+        M, N = self.M, self.N
+        mx, my = w.shape
+        buf = np.zeros((2 * M - 1, 2 * N - 1))
+        buf[:mx, :my] = w
+        out = scipy.fft.irfft2(scipy.fft.rfft2(buf, workers=self.workers) * self.Ghat,
+                               s=buf.shape, workers=self.workers)
+        return np.asfortranarray(out[M - 1:M - 1 + mx, N - 1:N - 1 + my])
+
+
+def inverse_laplacian(plan, w, c0, factor):
+    """L\\w (A.5): out = G*w; out -= c0*sum(w); out *= 1/factor.  The iszero
+    guard of src/grid_operators.jl:155 returns the input unchanged (zeros)."""
+    if not np.any(w):
+        return np.array(w, order="F", copy=True)
+    out = plan.apply(w)
+    out = out - c0 * np.sum(w)
+    return out * (1.0 / factor)
+
+
+def direct_convolution(G, w):
+    """O(P^2) reference for small boxes: out[i,j]=sum G(|i-k|,|j-l|) w[k,l]."""
+    mx, my = w.shape
+    ii = np.arange(mx)
+    jj = np.arange(my)
+    out = np.zeros((mx, my), order="F")
+    di = np.abs(ii[:, None] - ii[None, :])
+    dj = np.abs(jj[:, None] - jj[None, :])
+    for j in range(my):
+        # out[:, j] = sum_l  (G[di, dj[j,l]] @ w[:, l])
+        acc = np.zeros(mx)
+        for l in range(my):
+            acc += G[di, dj[j, l]] @ w[:, l]
+        out[:, j] = acc
+    return out
+
+
+# --------------------------------------------------------------------------
+# the cache ("plan") and the operator API of ImmersedLayers on it
+# --------------------------------------------------------------------------
+class ScalarCache:
+    """SurfaceScalarCache (src/cache.jl:164-182, _surfacecache :232-261):
+    R/E: ScalarData <-> Nodes{Primal}; Rsn/Esn: VectorData <-> Edges{Primal}.
+    GridScaling: L.factor = 1/dx^2 (src/cache.jl:323-324)."""
+
+    def __init__(self, grid, x, y, nx, ny, ds, lgf, ddf="yang3", scaling=GRID_SCALING,
+                 c0=None, workers=1):
+        self.grid = grid
+        self.x, self.y = np.asarray(x, float), np.asarray(y, float)
+        self.nx, self.ny, self.ds = np.asarray(nx, float), np.asarray(ny, float), np.asarray(ds, float)
+        self.N = self.x.shape[0]
+        self.scaling, self.ddf = scaling, ddf
+        self.tabs = {k: build_table(grid, self.x, self.y, self.ds, k, ddf, scaling)
+                     for k in (PRIMAL, XEDGE, YEDGE, DUAL)}
+        self.factor = 1.0 / grid.dx ** 2 if scaling == GRID_SCALING else 1.0
+        # plan_laplacian(g::PhysicalGrid): DX believed to be cellsize(g) (A.5)
+        self.c0 = lgf_c0(grid.dx) if c0 is None else c0
+        self.lgf = np.asarray(lgf)[:grid.NX, :grid.NY]
+        self.conv = ConvPlan(self.lgf, workers=workers)
+
+    # -- scaling helpers (src/grid_operators.jl:8-9)
+    def _scale_derivative(self, w):
+        return w / self.grid.dx if self.scaling == GRID_SCALING else w
+
+    # -- basic surface operators (src/surface_operators.jl:13-88)
+    def regularize(self, f):
+        return regularize(self.tabs[PRIMAL], f)
+
+    def interpolate(self, s):
+        return interpolate(self.tabs[PRIMAL], s)
+
+    def regularize_edges(self, fu, fv):
+        return regularize(self.tabs[XEDGE], fu), regularize(self.tabs[YEDGE], fv)
+
+    def interpolate_edges(self, u, v):
+        return interpolate(self.tabs[XEDGE], u), interpolate(self.tabs[YEDGE], v)
+
+    def regularize_normal(self, f):
+        """q = Rf (n o f) (src/surface_operators.jl:100-103)."""
+        return self.regularize_edges(self.nx * f, self.ny * f)
+
+    def normal_interpolate(self, u, v):
+        """vn = n . Ef q (src/surface_operators.jl:230-233); pointwise_dot =
+        n.u*v.u + n.v*v.v."""
+        su, sv = self.interpolate_edges(u, v)
+        return self.nx * su + self.ny * sv
+
+    def regularize_normal_cross(self, f):
+        """q = Rf (n x f e_z): V.u = n.v f, V.v = -n.u f
+        (src/cartesian_extensions.jl:19-23)."""
+        return self.regularize_edges(self.ny * f, -self.nx * f)
+
+    def normal_cross_interpolate(self, u, v):
+        """wn = e_z . (n x Ef q) = n.u*s.v - n.v*s.u."""
+        su, sv = self.interpolate_edges(u, v)
+        return self.nx * sv - self.ny * su
+
+    # -- grid operators with scaling (src/grid_operators.jl:25-134)
+    def divergence(self, u, v):
+        return self._scale_derivative(divergence_e2n(self.grid, u, v))
+
+    def grad(self, p):
+        u, v = grad_n2e(self.grid, p)
+        return self._scale_derivative(u), self._scale_derivative(v)
+
+    def curl_n2e(self, s):
+        u, v = curl_n2e(self.grid, s)
+        return self._scale_derivative(u), self._scale_derivative(v)
+
+    def curl_e2n(self, u, v):
+        return self._scale_derivative(curl_e2n(self.grid, u, v))
+
+    def laplacian(self, w, kind):
+        return laplacian(self.grid, w, kind, self.factor)
+
+    def inverse_laplacian(self, w):
+        return inverse_laplacian(self.conv, w, self.c0, self.factor)
+
+    # -- composite surface-grid operators (src/surface_operators.jl:357-725)
+    def surface_divergence(self, f):
+        """theta = D Rf (n o f) / dx (src/surface_operators.jl:530-547)."""
+        u, v = self.regularize_normal(f)
+        return self._scale_derivative(divergence_e2n(self.grid, u, v))
+
+    def surface_grad(self, phi):
+        """vn = n . Ef G phi / dx (src/surface_operators.jl:604-620)."""
+        u, v = grad_n2e(self.grid, phi)
+        return self._scale_derivative(self.normal_interpolate(u, v))
+
+    def surface_curl_s2n(self, f):
+        """w = C^T Rf (n o f) / dx (src/surface_operators.jl:357-375)."""
+        u, v = self.regularize_normal(f)
+        return self._scale_derivative(curl_e2n(self.grid, u, v))
+
+    def surface_curl_n2s(self, s):
+        """vn = n . Ef C s / dx (src/surface_operators.jl:412-429)."""
+        u, v = curl_n2e(self.grid, s)
+        return self._scale_derivative(self.normal_interpolate(u, v))
+
+    def surface_divergence_cross(self, f):
+        """theta = D Rf (n x f e_z)/dx -- the documented operator
+        (src/surface_operators.jl:672; the shipped body has a typo, Appendix E)."""
+        u, v = self.regularize_normal_cross(f)
+        return self._scale_derivative(divergence_e2n(self.grid, u, v))
+
+    def surface_grad_cross(self, phi):
+        u, v = grad_n2e(self.grid, phi)
+        return self._scale_derivative(self.normal_cross_interpolate(u, v))
+
+    def surface_curl_cross_s2n(self, f):
+        u, v = self.regularize_normal_cross(f)
+        return self._scale_derivative(curl_e2n(self.grid, u, v))
+
+    def surface_curl_cross_n2s(self, s):
+        u, v = curl_n2e(self.grid, s)
+        return self._scale_derivative(self.normal_cross_interpolate(u, v))
+
+    # -- masks (src/surface_operators.jl:865-871)
+    def mask(self):
+        if self.N == 0:
+            return np.ones(field_shape(PRIMAL, self.grid.NX, self.grid.NY), order="F")
+        m = self.surface_divergence(np.ones(self.N))
+        m = self.inverse_laplacian(m)
+        return m * -1.0
+
+    # -- Schur builders (src/matrix_operators.jl)
+    def _probe(self, pre, post, sign, scale, cols=None):
+        N = self.N
+        cols = range(N) if cols is None else cols
+        A = np.zeros((N, len(cols)), order="F")
+        for jc, col in enumerate(cols):
+            e = np.zeros(N)
+            e[col] = 1.0
+            g = pre(e)
+            g = self.inverse_laplacian(g)
+            A[:, jc] = sign * scale * post(g)
+        return A
+
+    def create_RTLinvR(self, scale=1.0, cols=None):
+        """src/matrix_operators.jl:9-30: A[:,c] = -scale*E L^-1 R e_c."""
+        return self._probe(self.regularize, self.interpolate, -1.0, scale, cols)
+
+    def create_CLinvCT(self, scale=1.0, cols=None):
+        """src/matrix_operators.jl:40-61."""
+        return self._probe(self.surface_curl_s2n, self.surface_curl_n2s, -1.0, scale, cols)
+
+    def create_GLinvD(self, scale=1.0, cols=None):
+        """src/matrix_operators.jl:135-155."""
+        return self._probe(self.surface_divergence, self.surface_grad, -1.0, scale, cols)
+
+    def create_GLinvD_cross(self, scale=1.0, cols=None):
+        """src/matrix_operators.jl:195-215 (documented operator, Appendix E)."""
+        return self._probe(self.surface_divergence_cross, self.surface_grad_cross, -1.0, scale, cols)
+
+    def create_nRTRn(self, scale=1.0):
+        """src/matrix_operators.jl:225-244: A[:,c] = scale * n.Ef Rf (n o e_c)."""
+        N = self.N
+        A = np.zeros((N, N), order="F")
+        for col in range(N):
+            e = np.zeros(N)
+            e[col] = 1.0
+            u, v = self.regularize_normal(e)
+            A[:, col] = scale * self.normal_interpolate(u, v)
+        return A
+
+    def create_surface_filter(self):
+        """C = Etilde R (src/matrix_operators.jl:254-268); filtered
+        interpolation Etilde[k,cell] = R[cell,k]/sum_m R[cell,m] (A.2, medium
+        confidence: parity unpinned)."""
+        R = R_matrix(self.tabs[PRIMAL])
+        rowsum = np.asarray(R.sum(axis=1)).ravel()
+        rowsum[rowsum == 0.0] = 1.0
+        Ef = sp.diags(1.0 / rowsum) @ R
+        return np.asarray((Ef.T @ R).todense(), order="F")
+
+
+def dirichlet_solve(cache, fplus, fminus=None, S=None):
+    """Block-LU Dirichlet Poisson (test/literate/dirichlet.jl:71-107).
+    Returns (f, s, S)."""
+    fminus = np.zeros_like(fplus) if fminus is None else fminus
+    d = fplus - fminus
+    fb = 0.5 * (fplus + fminus)
+    fstar = cache.surface_divergence(d)
+    fstar = cache.inverse_laplacian(fstar)
+    if S is None:
+        S = cache.create_RTLinvR()
+    s = cache.interpolate(fstar)
+    s = fb - s
+    s = -scipy.linalg.lu_solve(scipy.linalg.lu_factor(S), s)
+    f = cache.regularize(s)
+    f = cache.inverse_laplacian(f)
+    f = f + fstar
+    return f, s, S
+
+
+# --------------------------------------------------------------------------
+# inner products of the reference used by the pinning tests
+# --------------------------------------------------------------------------
+def dot_grid(grid, a, b, kind):
+    """Grid inner product weighted by dx^2 (src/tools.jl:101-104).  Upstream's
+    dot is a trapezoid rule over the physical domain: along a primal direction
+    the first/last entries weigh 1/2 (Appendix B `integrate(ones_grid)` =
+    404^2 dx^2 on 405^2 primal nodes), along a dual direction the ghost entries
+    weigh 0 (test/tools.jl:37: norm(1,g)^2 = domain area on dual nodes)."""
+    sx, sy = field_shift(kind)
+    mx, my = a.shape
+
+    def w1(m, dual):
+        w = np.ones(m)
+        w[0] = w[-1] = 0.0 if dual else 0.5
+        return w
+    w = w1(mx, sx != 0.0)[:, None] * w1(my, sy != 0.0)[None, :]
+    return float(np.sum(w * a * b) * grid.dx ** 2)
+
+
+def dot_surface(a, b, ds):
+    return float(np.sum(a * b * ds))

@@ -1,0 +1,272 @@
+"""Pin the CPU oracle against everything the reference holds for the hot path
+(SURVEY.md section 4 identity table and Appendix B golden values).  CPU only."""
+import numpy as np
+import pytest
+
+import ilm_b200
+import ilm_oracle as o
+
+bodies = ilm_b200.bodies
+lgfmod = ilm_b200.lgf
+
+
+def layers_setup():
+    """examples/Layers.ipynb cells 5,19: 600^2 grid, dx=0.02, circle R=1, ds=1.5dx."""
+    g = o.Grid(600, 600, 0.02, (300, 300))
+    x, y, nx, ny, ds = bodies.circle(1.0, 1.5 * 0.02)
+    return g, x, y, nx, ny, ds
+
+
+# ---------------------------------------------------------------- DDFs
+@pytest.mark.parametrize("name", list(o.DDFS))
+def test_ddf_moments(name):
+    """Partition of unity and first moment (SURVEY.md A.2 verification)."""
+    fn, rho, W = o.DDFS[name]
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 1, 200)
+    j = np.arange(-4, 6)
+    phi = fn(x[:, None] - j[None, :])
+    assert np.abs(phi.sum(axis=1) - 1).max() < 4e-15
+    if name != "witchhat":
+        assert np.abs(((x[:, None] - j[None, :]) * phi).sum(axis=1)).max() < 4e-15
+
+
+def test_yang3_center_value():
+    """phi(0) of Yang3."""
+    assert abs(o.ddf_yang3(np.array([0.0]))[0] - 0.6181999293593575) < 2e-16
+
+
+def test_asin_fdlibm_matches_libm():
+    x = np.concatenate([np.linspace(-1, 1, 20001), np.random.default_rng(1).uniform(-1, 1, 20000)])
+    ref = np.arcsin(x)
+    got = o.asin_fdlibm(x)
+    ulp = np.spacing(np.abs(ref)) + 1e-300
+    assert np.max(np.abs(got - ref) / ulp) <= 1.0
+
+
+# ---------------------------------------------------------------- golden values
+def test_golden_circle_sum_ds():
+    """examples/caches.ipynb:1380: dot(1,1,cache) = 6.283288300933757 for
+    Circle(1.0, 0.014) (448 points); our midpoint-rule circle reproduces it to
+    4e-12 (Appendix B)."""
+    x, y, nx, ny, ds = bodies.circle(1.0, 1.4 * 0.01)
+    assert x.shape[0] == 448
+    assert abs(ds.sum() - 6.283288300933757) < 1e-11
+    assert abs(nx[1] - 0.9999016728287639) < 1e-7      # caches.ipynb:1177
+    x2 = bodies.circle(0.5, 0.014)[0]
+    assert x2.shape[0] == 224                             # multbodies.ipynb:77
+
+
+def test_golden_layers_dot_x_Rf_n():
+    """examples/Layers.ipynb cell 64: dot(qx, Rf*nrm, g) = 3.141119452036813 with
+    regop weights = dlengthmid(body) (cell 19) and Yang3 on the u-edges."""
+    g, x, y, nx, ny, ds = layers_setup()
+    N = x.shape[0]
+    assert N == 209                                       # cell 62 output
+    dlmid = np.full(N, np.sin(2 * np.pi / N))            # 0.5*|x[k+1]-x[k-1]|
+    tab = o.build_table(g, x, y, dlmid, o.XEDGE, "yang3", o.GRID_SCALING)
+    q = o.regularize(tab, nx)
+    xc, _ = g.coords(o.XEDGE)
+    qx = np.broadcast_to(xc[:, None], q.shape)
+    assert abs(o.dot_grid(g, qx, q, o.XEDGE) - 3.141119452036813) < 2e-14
+
+
+def test_golden_layers_grid_coordinates():
+    """Layers.ipynb cells 54-55: v-edge coords -5.98:0.02:5.98 x -5.99:0.02:5.99, xv[300]=0."""
+    g = o.Grid(600, 600, 0.02, (300, 300))
+    xv, yv = g.coords(o.YEDGE)
+    assert xv.shape[0] == 599 and yv.shape[0] == 600
+    assert abs(xv[0] + 5.98) < 1e-12 and abs(yv[0] + 5.99) < 1e-12 and xv[299] == 0.0
+
+
+def test_golden_integrate_ones():
+    """caches.ipynb:1432: integrate(ones) on the 406^2 grid = 16.3216."""
+    g = o.Grid(406, 406, 0.01, (203, 203))
+    one = np.ones(o.field_shape(o.PRIMAL, 406, 406))
+    assert abs(o.dot_grid(g, one, one, o.PRIMAL) - 16.3216) < 1e-10
+
+
+# ---------------------------------------------------------------- reference test identities
+def test_tools_jl_regularization_identities():
+    """test/tools.jl:96-122 on its fixture (600^2, dx=0.02, Circle(1,1.5dx))."""
+    g, x, y, nx, ny, ds = layers_setup()
+    N = x.shape[0]
+    tab = o.build_table(g, x, y, ds, o.DUAL, "yang3", o.GRID_SCALING)
+    oc = np.ones(o.field_shape(o.DUAL, 600, 600))
+    os_ = np.ones(N)
+    # :107  dot(oc, Rc*os, g) == dot(os, os, ds)
+    assert abs(o.dot_grid(g, oc, o.regularize(tab, os_), o.DUAL) - o.dot_surface(os_, os_, ds)) < 1e-14 * 10
+    # :112 adjointness with random data
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal(oc.shape)
+    u[0, :] = u[-1, :] = 0
+    u[:, 0] = u[:, -1] = 0
+    phi = rng.standard_normal(N)
+    lhs = o.dot_grid(g, u, o.regularize(tab, phi), o.DUAL)
+    rhs = o.dot_surface(o.interpolate(tab, u), phi, ds)
+    assert abs(lhs - rhs) < 1e-13
+    # :119-120 Rf on the u component
+    tu = o.build_table(g, x, y, ds, o.XEDGE, "yang3", o.GRID_SCALING)
+    qu = np.ones(o.field_shape(o.XEDGE, 600, 600))
+    val = o.dot_grid(g, qu, o.regularize(tu, os_), o.XEDGE)
+    assert abs(val - ds.sum()) < 1e-12
+    assert abs(val - 2 * np.pi) < 1e-3
+
+
+def test_regularize_matches_csc_matvec():
+    """The add.at restatement equals scipy's CSC mat-vec (the structure upstream uses)."""
+    g = o.Grid(64, 48, 0.05, (32, 24))
+    x, y, nx, ny, ds = bodies.circle(0.7, 1.4 * 0.05)
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal(x.shape[0])
+    for kind in o.KINDS:
+        tab = o.build_table(g, x, y, ds, kind)
+        a = o.regularize(tab, f)
+        b = (o.R_matrix(tab) @ f).reshape(tab.shape, order="F")
+        assert np.array_equal(a, b)
+        s = rng.standard_normal(tab.shape)
+        fa = o.interpolate(tab, s)
+        fb = o.E_matrix(tab) @ s.ravel(order="F")
+        assert np.abs(fa - fb).max() < 1e-14
+
+
+def test_index_scaling_symmetric():
+    g = o.Grid(64, 64, 0.05, (32, 32))
+    x, y, nx, ny, ds = bodies.circle(0.7, 0.07)
+    tab = o.build_table(g, x, y, ds, o.PRIMAL, "yang3", o.INDEX_SCALING)
+    assert np.array_equal(tab.wR, tab.wE)
+
+
+# ---------------------------------------------------------------- stencil identities
+def test_stencil_identities():
+    """D=-G^T, C^T=transpose(C), DC=0, C^T G=0."""
+    g = o.Grid(20, 17, 1.0, (10, 8))
+    rng = np.random.default_rng(5)
+    NX, NY = g.NX, g.NY
+    p = rng.standard_normal(o.field_shape(o.PRIMAL, NX, NY))
+    s = rng.standard_normal(o.field_shape(o.DUAL, NX, NY))
+    u = rng.standard_normal(o.field_shape(o.XEDGE, NX, NY))
+    v = rng.standard_normal(o.field_shape(o.YEDGE, NX, NY))
+    # interior-supported data so boundary truncation plays no role
+    for a in (p, s, u, v):
+        a[:2, :] = 0; a[-2:, :] = 0; a[:, :2] = 0; a[:, -2:] = 0
+    gu, gv = o.grad_n2e(g, p)
+    lhs = np.sum(gu * u) + np.sum(gv * v)
+    rhs = -np.sum(p * o.divergence_e2n(g, u, v))
+    assert abs(lhs - rhs) < 1e-12
+    cu, cv = o.curl_n2e(g, s)
+    assert abs(np.sum(cu * u) + np.sum(cv * v) - np.sum(s * o.curl_e2n(g, u, v))) < 1e-12
+    assert np.abs(o.divergence_e2n(g, cu, cv)).max() < 1e-13
+    assert np.abs(o.curl_e2n(g, gu, gv)).max() < 1e-13
+    # L_F = G D - C C^T on edges (test/literate/matrices.jl:40-45)
+    gdu, gdv = o.grad_n2e(g, o.divergence_e2n(g, u, v))
+    ccu, ccv = o.curl_n2e(g, o.curl_e2n(g, u, v))
+    lu = o.laplacian(g, u, o.XEDGE)
+    assert np.abs((gdu - ccu) - lu)[3:-3, 3:-3].max() < 1e-12
+    # tensor pair: D_t = -G_t^T
+    t = o.grad_e2t(g, u, v)
+    tt = [rng.standard_normal(a.shape) for a in t]
+    for a in tt:
+        a[:2, :] = 0; a[-2:, :] = 0; a[:, :2] = 0; a[:, -2:] = 0
+    du, dv = o.divergence_t2e(g, *tt)
+    assert abs(sum(np.sum(a * b) for a, b in zip(t, tt)) + np.sum(du * u) + np.sum(dv * v)) < 1e-12
+
+
+# ---------------------------------------------------------------- LGF
+def test_lgf_exact_values_and_delta():
+    G = lgfmod.lgf_table(300)
+    assert abs(G[1, 0] - 0.25) < 1e-15
+    assert abs(G[1, 1] - 1 / np.pi) < 1e-15
+    assert abs(G[2, 0] - (1 - 2 / np.pi)) < 1e-15
+    L = G[2:, 1:-1] + G[:-2, 1:-1] + G[1:-1, 2:] + G[1:-1, :-2] - 4 * G[1:-1, 1:-1]
+    assert np.abs(L).max() < 5e-14
+    assert abs(4 * G[1, 0] - 4 * G[0, 0] - 1) < 1e-15        # L G = +delta at the origin
+    n = np.arange(1, 300)
+    assert np.abs(np.diag(G)[1:] - np.cumsum(1 / (2 * n - 1)) / np.pi).max() < 5e-15
+    Gr = lgfmod.lgf_table(120, rule="gl100")
+    assert np.abs(Gr - G[:120, :120]).max() < 1e-12
+
+
+def test_fft_convolution_matches_direct():
+    G = lgfmod.lgf_table(40)
+    rng = np.random.default_rng(2)
+    plan = o.ConvPlan(G[:24, :20])
+    for shape in [(24, 20), (23, 19), (24, 19), (23, 20)]:
+        w = rng.standard_normal(shape)
+        a = plan.apply(w)
+        b = o.direct_convolution(G, w)
+        assert np.abs(a - b).max() < 1e-12 * np.abs(b).max()
+
+
+def test_inverse_laplacian_inverts_laplacian():
+    """L (L^-1 w) = w for compactly supported w away from the boundary."""
+    g = o.Grid(64, 64, 0.1, (32, 32))
+    G = lgfmod.lgf_table(64)
+    plan = o.ConvPlan(G)
+    w = np.zeros(o.field_shape(o.DUAL, 64, 64), order="F")
+    w[20:40, 22:41] = np.random.default_rng(0).standard_normal((20, 19))
+    factor = 1 / g.dx ** 2
+    sol = o.inverse_laplacian(plan, w, o.lgf_c0(g.dx), factor)
+    back = o.laplacian(g, sol, o.DUAL, factor)
+    assert np.abs(back - w)[1:-1, 1:-1].max() < 1e-11 * np.abs(w).max()
+
+
+# ---------------------------------------------------------------- physics checks (test/surface_ops.jl)
+@pytest.fixture(scope="module")
+def small_cache():
+    """test/surface_ops.jl:4-22 fixture scaled down: 4x4 domain dx=0.04, R=1, ds=1.4dx."""
+    dx = 0.04
+    NX = 104
+    g = o.Grid(NX, NX, dx, (NX // 2, NX // 2))
+    x, y, nx, ny, ds = bodies.circle(1.0, 1.4 * dx)
+    G = lgfmod.lgf_table(NX)
+    return o.ScalarCache(g, x, y, nx, ny, ds, G)
+
+
+def test_mask_integral(small_cache):
+    """test/surface_ops.jl:180-186: integral of the mask = pi R^2 (2e-3)."""
+    c = small_cache
+    m = c.mask()
+    area = o.dot_grid(c.grid, m, np.ones_like(m), o.PRIMAL)
+    assert abs(area - np.pi) < 2e-2        # coarser grid than the reference fixture
+    assert abs(m[52, 52] - 1.0) < 1e-3 and abs(m[2, 2]) < 1e-3
+
+
+def test_schur_operator_norms(small_cache):
+    """test/surface_ops.jl:63-77: nRTRn max singular value ~ 11, CLinvCT(scale=dx)
+    max eigenvalue ~ 0.2, GLinvD max eigenvalue ~ 0.45."""
+    c = small_cache
+    A = c.create_nRTRn()
+    assert abs(np.linalg.svd(A, compute_uv=False).max() - 11) < 1.5
+    cols = range(0, c.N, 1)
+    Cm = c.create_CLinvCT(scale=c.grid.dx, cols=cols)
+    assert abs(np.abs(np.linalg.eigvals(Cm)).max() - 0.2) < 0.1
+    Gm = c.create_GLinvD(scale=c.grid.dx, cols=cols)
+    th = 2 * np.pi * np.arange(c.N) / c.N
+    fn = c.normal_interpolate(*c.regularize_normal(np.sin(th - np.pi / 4)))
+    assert abs(fn.max() - 11) < 1.5 and abs(fn.min() + 11) < 1.5
+    assert abs(np.abs(np.linalg.eigvals(Gm)).max() - 0.45) < 0.1
+
+
+def test_dirichlet_solution(small_cache):
+    """test/literate/dirichlet.jl: phi+ = x outside, 0 inside."""
+    c = small_cache
+    f, s, S = o.dirichlet_solve(c, c.x.copy())
+    # interior is blank, exterior matches the analytic exterior solution x/r^2 near the body
+    assert np.abs(f[52, 52]) < 5e-3
+    xg, yg = c.grid.coords(o.PRIMAL)
+    i, j = 52 + 35, 52          # (1.4, 0)
+    assert abs(f[i, j] - xg[i] / (xg[i] ** 2 + yg[j] ** 2)) < 3e-2
+    C = c.create_surface_filter()
+    assert np.abs(C.sum(axis=1) - 1).max() < 1e-12       # filter preserves constants
+
+
+def test_zero_body_cache():
+    """test/surface_ops.jl:356-371: N = 0 caches work and give zeros."""
+    g = o.Grid(32, 32, 0.1, (16, 16))
+    z = np.zeros(0)
+    c = o.ScalarCache(g, z, z, z, z, z, lgfmod.lgf_table(32))
+    assert np.all(c.regularize(z) == 0)
+    assert c.interpolate(g.zeros(o.PRIMAL)).shape == (0,)
+    assert np.all(c.mask() == 1.0)
+    assert c.create_RTLinvR().shape == (0, 0)
