@@ -649,14 +649,16 @@ class ScalarCache:
         return A
 
     def create_surface_filter(self):
-        """C = Etilde R (src/matrix_operators.jl:254-268); filtered
-        interpolation Etilde[k,cell] = R[cell,k]/sum_m R[cell,m] (A.2, medium
-        confidence: parity unpinned)."""
-        R = R_matrix(self.tabs[PRIMAL])
+        """C = Etilde R (src/matrix_operators.jl:254-268).  Filtered
+        interpolation (filter=true upstream): Etilde[k,cell] = E[k,cell] /
+        sum_m R[cell,m], zero denominators -> 1, so that C preserves constants
+        (medium confidence on upstream's exact form: parity unpinned)."""
+        tab = self.tabs[PRIMAL]
+        R = R_matrix(tab)
         rowsum = np.asarray(R.sum(axis=1)).ravel()
         rowsum[rowsum == 0.0] = 1.0
-        Ef = sp.diags(1.0 / rowsum) @ R
-        return np.asarray((Ef.T @ R).todense(), order="F")
+        Ef = E_matrix(tab) @ sp.diags(1.0 / rowsum)
+        return np.asarray((Ef @ R).todense(), order="F")
 
 
 def dirichlet_solve(cache, fplus, fminus=None, S=None):
