@@ -1,0 +1,200 @@
+// CPU emulation harness for the FFT-convolution kernel bodies (no GPU in the
+// build container): runs the *same* __host__ __device__ bodies that the CUDA
+// kernels call, with 512 std::threads per emulated CTA and condition-variable
+// barriers, and checks them against a long-double DFT / direct convolution.
+//   nvcc -std=c++17 -O1 -o test_fft_host test_fft_host.cu && ./test_fft_host
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <random>
+#include <thread>
+#include <vector>
+
+#include "ilm_conv.cuh"
+
+using namespace ilm;
+
+struct Barrier {
+    std::mutex m; std::condition_variable cv; int n, count = 0, gen = 0;
+    explicit Barrier(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        int g = gen;
+        if (++count == n) { count = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+struct HostCtx {
+    int tid, grp; Barrier* gb; Barrier* cb;
+    void sync() { gb->wait(); }
+    void sync_cta() { cb->wait(); }
+};
+
+static double2 expm2pii(long long num, long long den) {
+    num %= den;
+    long double a = -2.0L * acosl(-1.0L) * (long double)num / (long double)den;
+    return cmk((double)cosl(a), (double)sinl(a));
+}
+
+template <class Body> static void run_cta(size_t smem_bytes, Body body) {
+    std::vector<double2> smem(smem_bytes / sizeof(double2) + 1);
+    Barrier g0(256), g1(256), cb(512);
+    std::vector<std::thread> th;
+    for (int t = 0; t < 512; ++t)
+        th.emplace_back([&, t] {
+            HostCtx c{t & 255, t >> 8, (t >> 8) ? &g1 : &g0, &cb};
+            body(c, smem.data());
+        });
+    for (auto& x : th) x.join();
+}
+
+// ---------------------------------------------------------------- single FFT
+template <int L, bool INV> static double test_fft() {
+    using C = FftCfg<L>;
+    std::vector<double2> tw(C::TW_TOTAL + 1);
+    fft_fill_twiddles<L>(tw.data(), expm2pii);
+    std::mt19937_64 rng(L + INV);
+    std::normal_distribution<double> nd;
+    const int nf = 2 * C::F;
+    std::vector<double2> in((size_t)nf * L), out((size_t)nf * L);
+    for (auto& z : in) z = cmk(nd(rng), nd(rng));
+    run_cta(C::SMEM_BYTES, [&](HostCtx& c, double2* smem) {
+        double2* tws = smem + 2 * C::GROUP_XBUF;
+        load_twiddles<L>(c, tws, tw.data());
+        const int f = c.tid / C::T, j = c.tid % C::T;
+        double2* xb = smem + c.grp * C::GROUP_XBUF + f * C::XBUF;
+        const double2* src = in.data() + (size_t)(c.grp * C::F + f) * L;
+        double2* dst = out.data() + (size_t)(c.grp * C::F + f) * L;
+        double2 v[16];
+        for (int e = 0; e < 16; ++e) v[e] = src[j + e * C::T];
+        fft_regs<L, INV>(v, c, xb, tws, j);
+        for (int e = 0; e < 16; ++e) dst[j + e * C::T] = v[e];
+    });
+    // reference DFT in long double for the first and last transform
+    double err = 0, nrm = 0;
+    const long double tp = 2.0L * acosl(-1.0L);
+    for (int q : {0, nf - 1}) {
+        for (int k = 0; k < L; k += (L > 256 ? 37 : 1)) {
+            long double sr = 0, si = 0;
+            for (int n = 0; n < L; ++n) {
+                long double ang = (INV ? tp : -tp) * (long double)(((long long)k * n) % L) / L;
+                long double c = cosl(ang), s = sinl(ang);
+                sr += in[(size_t)q * L + n].x * c - in[(size_t)q * L + n].y * s;
+                si += in[(size_t)q * L + n].x * s + in[(size_t)q * L + n].y * c;
+            }
+            err = fmax(err, fmax(fabs((double)sr - out[(size_t)q * L + k].x), fabs((double)si - out[(size_t)q * L + k].y)));
+            nrm = fmax(nrm, hypot((double)sr, (double)si));
+        }
+    }
+    printf("  fft L=%4d %s  max err %.3e (|X|max %.3e)\n", L, INV ? "inv" : "fwd", err, nrm);
+    return err / nrm;
+}
+
+// ---------------------------------------------------------------- convolution
+
+
+template <int LX, int LY>
+static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool second) {
+    // kernel table g(i,j), 0<=i<NX, 0<=j<NY : something LGF-like
+    std::vector<double> G((size_t)NX * NY);
+    for (int j = 0; j < NY; ++j)
+        for (int i = 0; i < NX; ++i) G[(size_t)j * NX + i] = 0.3 * log(1.0 + i * i + 2.0 * j * j) + 0.1 * cos(0.3 * i) - 0.05 * j;
+    std::vector<double2> twx(FftCfg<LX>::TW_TOTAL + 1), twy(FftCfg<LY>::TW_TOTAL + 1);
+    fft_fill_twiddles<LX>(twx.data(), expm2pii);
+    fft_fill_twiddles<LY>(twy.data(), expm2pii);
+    ConvArgs a{};
+    a.twx = twx.data(); a.twy = twy.data();
+    // ---- Ghat build: h = eps_i eps_j g
+    std::vector<double> h((size_t)NX * NY);
+    for (int j = 0; j < NY; ++j)
+        for (int i = 0; i < NX; ++i) h[(size_t)j * NX + i] = G[(size_t)j * NX + i] * (i ? 2.0 : 1.0) * (j ? 2.0 : 1.0);
+    ConvGeom gg{LX, LY, NY, (NY + 1) & ~1};
+    std::vector<double2> S(s_elems(gg)), S2;
+    std::vector<double> Ghat(ghat_elems(gg), 0.0);
+    a.g = gg; a.f1 = FieldRef{h.data(), NX, NY}; a.f2 = FieldRef{nullptr, 0, 0};
+    a.S = S.data(); a.GhatOut = Ghat.data(); a.gscale = 1.0 / (4.0 * LX * LY);
+    {
+        int nwork = (gg.MYp + 2 * FftCfg<LX>::F - 1) / (2 * FftCfg<LX>::F);
+        int nb = nwork > 3 ? 3 : nwork;     // exercise the persistent loop
+        for (int b = 0; b < nb; ++b)
+            run_cta(FftCfg<LX>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passA_body<LX>(c, a, sm, b, nb); });
+        nwork = (gg.Lx + FftCfg<LY>::F - 1) / FftCfg<LY>::F;
+        nb = nwork > 3 ? 3 : nwork;
+        for (int b = 0; b < nb; ++b)
+            run_cta(FftCfg<LY>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passB_body<LY, 1>(c, a, sm, b, nb); });
+    }
+    // ---- fields
+    std::mt19937_64 rng(NX * 131 + NY);
+    std::normal_distribution<double> nd;
+    std::vector<double> w1((size_t)mx1 * my1), w2((size_t)mx2 * my2);
+    for (auto& x : w1) x = nd(rng);
+    for (auto& x : w2) x = nd(rng);
+    std::vector<double> o1 = w1, o2 = w2;
+    int MY = second ? (my1 > my2 ? my1 : my2) : my1;
+    ConvGeom g2{LX, LY, MY, (MY + 1) & ~1};
+    S.assign(s_elems(g2), cmk(NAN, NAN));
+    S2.assign(s_elems(g2), cmk(NAN, NAN));
+    a.g = g2; a.f1 = FieldRef{o1.data(), mx1, my1};
+    a.f2 = second ? FieldRef{o2.data(), mx2, my2} : FieldRef{nullptr, 0, 0};
+    a.S = S.data(); a.S2 = S2.data(); a.Ghat = Ghat.data();
+    {
+        int nwork = (g2.MYp + 2 * FftCfg<LX>::F - 1) / (2 * FftCfg<LX>::F);
+        int nb = nwork > 2 ? 2 : nwork;
+        for (int b = 0; b < nb; ++b)
+            run_cta(FftCfg<LX>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passA_body<LX>(c, a, sm, b, nb); });
+        int nworkB = (g2.Lx + FftCfg<LY>::F - 1) / FftCfg<LY>::F;
+        int nbB = nworkB > 3 ? 3 : nworkB;
+        for (int b = 0; b < nbB; ++b)
+            run_cta(FftCfg<LY>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passB_body<LY, 0>(c, a, sm, b, nbB); });
+        for (int b = 0; b < nb; ++b)
+            run_cta(FftCfg<LX>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passC_body<LX>(c, a, sm, b, nb); });
+    }
+    // ---- direct check (sampled)
+    double err = 0, nrm = 0;
+    auto check = [&](const std::vector<double>& w, const std::vector<double>& o, int mx, int my) {
+        int step = (mx * my > 4000) ? 97 : 1;
+        for (int idx = 0; idx < mx * my; idx += step) {
+            int i = idx % mx, j = idx / mx;
+            long double s = 0;
+            for (int l = 0; l < my; ++l)
+                for (int k = 0; k < mx; ++k) s += (long double)G[(size_t)abs(j - l) * NX + abs(i - k)] * w[(size_t)l * mx + k];
+            err = fmax(err, fabs((double)s - o[idx]));
+            nrm = fmax(nrm, fabs((double)s));
+        }
+    };
+    check(w1, o1, mx1, my1);
+    if (second) check(w2, o2, mx2, my2);
+    printf("  conv NX=%d NY=%d Lx=%d Ly=%d fields (%dx%d)%s  max err %.3e (max |out| %.3e)\n", NX, NY, LX, LY, mx1, my1,
+           second ? "+2nd" : "", err, nrm);
+    return err / nrm;
+}
+
+int main() {
+    double worst = 0;
+    printf("single FFTs\n");
+    worst = fmax(worst, test_fft<16, false>());
+    worst = fmax(worst, test_fft<32, false>());
+    worst = fmax(worst, test_fft<64, true>());
+    worst = fmax(worst, test_fft<128, false>());
+    worst = fmax(worst, test_fft<256, true>());
+    worst = fmax(worst, test_fft<512, false>());
+    worst = fmax(worst, test_fft<1024, true>());
+    worst = fmax(worst, test_fft<2048, false>());
+    worst = fmax(worst, test_fft<4096, false>());
+    worst = fmax(worst, test_fft<4096, true>());
+    printf("convolutions\n");
+    worst = fmax(worst, test_conv<16, 16>(8, 7, 8, 7, 7, 6, true));
+    worst = fmax(worst, test_conv<32, 16>(14, 8, 13, 7, 14, 8, true));
+    worst = fmax(worst, test_conv<16, 32>(8, 15, 8, 15, 0, 0, false));
+    worst = fmax(worst, test_conv<64, 32>(24, 13, 24, 12, 23, 13, true));
+    worst = fmax(worst, test_conv<32, 128>(16, 64, 15, 63, 16, 64, true));
+    worst = fmax(worst, test_conv<256, 16>(100, 8, 100, 8, 99, 7, true));
+    worst = fmax(worst, test_conv<512, 16>(200, 5, 199, 5, 200, 4, true));
+    worst = fmax(worst, test_conv<16, 1024>(6, 400, 6, 400, 5, 399, true));
+    worst = fmax(worst, test_conv<4096, 16>(1100, 3, 1100, 3, 1099, 2, true));
+    printf("worst relative error %.3e -> %s\n", worst, worst < 1e-12 ? "PASS" : "FAIL");
+    return worst < 1e-12 ? 0 : 1;
+}
