@@ -1,3 +1,17 @@
-"""ilm-b200: B200-native immersed-layer operator hot path (host-side mirror of
-the ImmersedLayers.jl operator API over the C-ABI library libilm_b200.so)."""
-from . import bodies, lgf  # noqa: F401
+"""ilm-b200: B200-native immersed-layer operator hot path.
+
+Host-side mirror of the ImmersedLayers.jl operator API on `BasicILMCache`
+(regularize!/interpolate!, staggered stencils, LGF inverse Laplacian, Schur
+builders, surface-point solve) over the C ABI of libilm_b200.so
+(include/ilm_b200.h).  Import as `import ilm_b200` (see ../ilm_b200.py).
+"""
+from . import _lib, bodies, lgf  # noqa: F401
+from ._lib import DimensionMismatch, IlmError, MethodError  # noqa: F401
+from .api import (  # noqa: F401
+    Dual, Edges, GridScaling, IndexScaling, LU, Nodes, PhysicalGrid, Primal, ScalarData,
+    SurfaceScalarCache, VectorData, complementary_mask, create_CLinvCT, create_GLinvD,
+    create_GLinvD_cross, create_RTLinvR, create_nRTRn, create_surface_filter, curl,
+    dirichlet_poisson, divergence, grad, interpolate, inverse_laplacian, laplacian, mask,
+    matvec_pow, normal_cross_interpolate, normal_interpolate, regularize, regularize_normal,
+    regularize_normal_cross, surface_curl, surface_curl_cross, surface_divergence,
+    surface_divergence_cross, surface_grad, surface_grad_cross)

@@ -1,0 +1,647 @@
+"""Host-side mirror of the ImmersedLayers.jl operator API on `BasicILMCache`
+for the hot path, over the C ABI of libilm_b200.so.
+
+Names follow the reference (the trailing `!` is dropped, the output comes
+first as in Julia): `regularize(s, f, cache)` is `regularize!(s,f,cache)`
+(src/surface_operators.jl:13), etc.  Data containers are thin typed wrappers
+around a flat fp64 buffer in the reference's memory order (x fastest) that is
+either a numpy array (host mode: the library stages H2D/D2H inside the call)
+or a CUDA torch tensor (device-resident mode: zero copies).
+
+Error behaviour mirrors the reference: a call with the wrong container type
+raises `MethodError` (Julia MethodError, test/tools.jl:34), a size mismatch
+raises `DimensionMismatch` (AssertionError / DimensionMismatch, test/tools.jl:35).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from . import lgf as _lgf
+from ._lib import DimensionMismatch, IlmError, MethodError  # noqa: F401
+
+Primal, Dual = "primal", "dual"
+GridScaling, IndexScaling = "grid", "index"
+
+
+# --------------------------------------------------------------------------
+# grid
+# --------------------------------------------------------------------------
+class PhysicalGrid:
+    """size(g) = (NX, NY) dual cells incl. ghosts, cellsize dx, origin I0
+    (1-based index of the primal node at the physical origin).  Dimensions are
+    explicit: upstream's PhysicalGrid auto-tunes them."""
+
+    def __init__(self, NX, NY, dx, I0):
+        self.NX, self.NY, self.dx = int(NX), int(NY), float(dx)
+        self.I0 = (int(I0[0]), int(I0[1]))
+
+    @classmethod
+    def centered(cls, N, half_width=2.0):
+        """Square domain (-h, h)^2 with N x N dual cells incl. ghosts
+        (SURVEY.md section 8d synthetic grids)."""
+        return cls(N, N, 2.0 * half_width / (N - 2), (N // 2, N // 2))
+
+    def size(self):
+        return self.NX, self.NY
+
+    def cellsize(self):
+        return self.dx
+
+    def layout_shape(self, layout):
+        NX, NY = self.NX, self.NY
+        return {L.NODES_PRIMAL: (NX - 1, NY - 1), L.NODES_DUAL: (NX, NY),
+                L.XEDGES: (NX, NY - 1), L.YEDGES: (NX - 1, NY)}[layout]
+
+    def coordinates(self, layout):
+        mx, my = self.layout_shape(layout)
+        sx, sy = {L.NODES_PRIMAL: (0.0, 0.0), L.NODES_DUAL: (0.5, 0.5),
+                  L.XEDGES: (0.5, 0.0), L.YEDGES: (0.0, 0.5)}[layout]
+        x = (np.arange(1, mx + 1) - sx - self.I0[0]) * self.dx
+        y = (np.arange(1, my + 1) - sy - self.I0[1]) * self.dx
+        return x, y
+
+
+# --------------------------------------------------------------------------
+# data containers
+# --------------------------------------------------------------------------
+def _is_torch(buf):
+    return type(buf).__module__.startswith("torch")
+
+
+def _ptr(buf):
+    if _is_torch(buf):
+        return C.c_void_p(buf.data_ptr())
+    return C.c_void_p(buf.ctypes.data)
+
+
+def _alloc(n, device):
+    if device:
+        import torch
+        return torch.zeros(int(n), dtype=torch.float64, device="cuda")
+    return np.zeros(int(n), dtype=np.float64)
+
+
+class _Data:
+    """Flat fp64 buffer + layout tag."""
+    layout = None
+
+    def __init__(self, data):
+        self.data = data
+
+    def __len__(self):
+        return int(self.data.shape[0]) if self.data.ndim == 1 else int(np.prod(self.data.shape))
+
+    def numpy(self):
+        if _is_torch(self.data):
+            return self.data.detach().cpu().numpy()
+        return self.data
+
+    def fill(self, value):
+        if _is_torch(self.data):
+            self.data.fill_(value)
+        else:
+            self.data[...] = value
+        return self
+
+    def set(self, arr):
+        arr = np.asarray(arr, dtype=np.float64).ravel(order="F")
+        if arr.shape[0] != len(self):
+            raise DimensionMismatch(f"expected {len(self)} values, got {arr.shape[0]}")
+        if _is_torch(self.data):
+            import torch
+            self.data.copy_(torch.from_numpy(np.ascontiguousarray(arr)))
+        else:
+            self.data[...] = arr
+        return self
+
+
+class Nodes(_Data):
+    """Nodes{Primal} ((NX-1) x (NY-1)) or Nodes{Dual} (NX x NY)."""
+
+    def __init__(self, celltype, grid, data=None, device=False):
+        self.celltype = celltype
+        self.layout = L.NODES_PRIMAL if celltype == Primal else L.NODES_DUAL
+        self.shape = grid.layout_shape(self.layout)
+        super().__init__(_alloc(self.shape[0] * self.shape[1], device) if data is None else data)
+
+    def array(self):
+        """(mx, my) Fortran-ordered view/copy for inspection."""
+        return self.numpy().reshape(self.shape, order="F")
+
+
+class Edges(_Data):
+    """Edges{Primal}: data = [vec(u); vec(v)], u NX x (NY-1), v (NX-1) x NY."""
+    layout = L.EDGES
+
+    def __init__(self, grid, data=None, device=False):
+        self.ushape = grid.layout_shape(L.XEDGES)
+        self.vshape = grid.layout_shape(L.YEDGES)
+        self.nu = self.ushape[0] * self.ushape[1]
+        self.nv = self.vshape[0] * self.vshape[1]
+        super().__init__(_alloc(self.nu + self.nv, device) if data is None else data)
+
+    @property
+    def u(self):
+        return self.numpy()[: self.nu].reshape(self.ushape, order="F")
+
+    @property
+    def v(self):
+        return self.numpy()[self.nu:].reshape(self.vshape, order="F")
+
+
+class ScalarData(_Data):
+    def __init__(self, n, data=None, device=False):
+        super().__init__(_alloc(n, device) if data is None else data)
+
+
+class VectorData(_Data):
+    """data = [u; v]."""
+
+    def __init__(self, n, data=None, device=False):
+        self.n = int(n)
+        super().__init__(_alloc(2 * self.n, device) if data is None else data)
+
+    @property
+    def u(self):
+        return self.numpy()[: self.n]
+
+    @property
+    def v(self):
+        return self.numpy()[self.n:]
+
+
+def _expect(obj, cls, what):
+    if not isinstance(obj, cls):
+        names = "/".join(c.__name__ for c in (cls if isinstance(cls, tuple) else (cls,)))
+        raise MethodError(f"{what}: expected {names}, got {type(obj).__name__}")
+    return obj
+
+
+def _expect_nodes(obj, celltype, what):
+    _expect(obj, Nodes, what)
+    if obj.celltype != celltype:
+        raise MethodError(f"{what}: expected Nodes{{{celltype}}}, got Nodes{{{obj.celltype}}}")
+    return obj
+
+
+# --------------------------------------------------------------------------
+# the cache (plan)
+# --------------------------------------------------------------------------
+class SurfaceScalarCache:
+    """`SurfaceScalarCache(body, g; scaling, ddftype)` (src/cache.jl:164-182,
+    205-224): body = (x, y, nx, ny, ds) arrays of the surface points, unit
+    normals and arc weights (`points`, `normals`, `areas`)."""
+
+    def __init__(self, body, g, scaling=GridScaling, ddftype="yang3", lgf_table=None, c0=None,
+                 device=False, stream=None):
+        self.g = g
+        x, y, nx, ny, ds = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)) for a in body[:5]]
+        N = x.shape[0]
+        for a in (y, nx, ny, ds):
+            if a.shape[0] != N:
+                raise DimensionMismatch("points, normals and areas must have equal length")
+        self.pts = (x, y)
+        self.nrm = (nx, ny)
+        self.areas_ = ds
+        self.N = N
+        self.scaling = scaling
+        self.ddftype = ddftype
+        self.device = bool(device)
+        if lgf_table is None:
+            lgf_table = _lgf.lgf_table(max(g.NX, g.NY))
+        lgf_table = np.asfortranarray(lgf_table, dtype=np.float64)
+        if lgf_table.shape[0] != lgf_table.shape[1] or lgf_table.shape[0] < max(g.NX, g.NY):
+            raise DimensionMismatch("LGF table must be square and at least max(NX,NY)")
+        # _get_laplacian (src/cache.jl:321-324): factor = 1/dx^2 for GridScaling;
+        # far-field constant with DX = cellsize
+        self.lap_factor = 1.0 / g.dx ** 2 if scaling == GridScaling else 1.0
+        self.c0 = _lgf.lgf_c0(g.dx) if c0 is None else float(c0)
+        lib = L.load()
+        gs = L.ilm_grid(g.NX, g.NY, g.dx, g.I0[0], g.I0[1])
+        plan = C.c_void_p()
+        if ddftype not in L.DDF:
+            raise MethodError(f"unknown ddftype {ddftype!r}")
+        st = lib.ilm_plan_create(C.byref(gs), N, _ptr(x), _ptr(y), _ptr(nx), _ptr(ny), _ptr(ds),
+                                 L.DDF[ddftype], L.GRID_SCALING if scaling == GridScaling else L.INDEX_SCALING,
+                                 _ptr(lgf_table), lgf_table.shape[0], self.c0, self.lap_factor,
+                                 C.c_void_p(stream or 0), C.byref(plan))
+        L.check(st)
+        self._plan = plan
+        self._lib = lib
+
+    def __del__(self):
+        plan = getattr(self, "_plan", None)
+        if plan:
+            self._lib.ilm_plan_destroy(plan)
+            self._plan = None
+
+    close = __del__
+
+    # -- convenience (src/cache.jl:351-775, src/tools.jl:16-46)
+    def __len__(self):
+        return self.N
+
+    def points(self):
+        return self.pts
+
+    def normals(self):
+        return self.nrm
+
+    def areas(self):
+        return self.areas_
+
+    def cellsize(self):
+        return self.g.dx
+
+    def zeros_grid(self):
+        return Nodes(Primal, self.g, device=self.device)
+
+    def zeros_gridcurl(self):
+        return Nodes(Dual, self.g, device=self.device)
+
+    def zeros_gridgrad(self):
+        return Edges(self.g, device=self.device)
+
+    def zeros_surface(self):
+        return ScalarData(self.N, device=self.device)
+
+    def zeros_surfacevec(self):
+        return VectorData(self.N, device=self.device)
+
+    def update_points(self, body):
+        """update_system (src/system.jl:26-50): new body, same L."""
+        x, y, nx, ny, ds = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)) for a in body[:5]]
+        L.check(self._lib.ilm_plan_update_points(self._plan, x.shape[0], _ptr(x), _ptr(y), _ptr(nx), _ptr(ny), _ptr(ds)))
+        self.pts, self.nrm, self.areas_, self.N = (x, y), (nx, ny), ds, x.shape[0]
+
+    def sync(self):
+        L.check(self._lib.ilm_plan_sync(self._plan))
+
+    def launch_count(self):
+        return int(self._lib.ilm_plan_launch_count(self._plan))
+
+    def table(self, layout):
+        """(idx, wR, wE) of the DDF window table, each (N, W, W) in [k][b][a] order."""
+        W = C.c_int()
+        L.check(self._lib.ilm_get_table(self._plan, layout, C.byref(W), None, None, None))
+        W = W.value
+        idx = np.zeros((self.N, W, W), dtype=np.int64)
+        wR = np.zeros((self.N, W, W))
+        wE = np.zeros((self.N, W, W))
+        L.check(self._lib.ilm_get_table(self._plan, layout, None, _ptr(idx), _ptr(wR), _ptr(wE)))
+        return idx, wR, wE
+
+    def add_kernel(self, table, c0=0.0, factor=1.0):
+        table = np.asfortranarray(table, dtype=np.float64)
+        kid = C.c_int()
+        L.check(self._lib.ilm_add_kernel(self._plan, _ptr(table), table.shape[0], c0, factor, C.byref(kid)))
+        return kid.value
+
+    def _check_n(self, d, n, what):
+        if len(d) != n:
+            raise DimensionMismatch(f"{what}: expected length {n}, got {len(d)}")
+
+
+def _grid_len(cache, layout):
+    return int(cache._lib.ilm_layout_size(cache._plan, layout))
+
+
+# --------------------------------------------------------------------------
+# operators (reference names, `!` dropped)
+# --------------------------------------------------------------------------
+def regularize(s, f, cache):
+    """regularize!(s::Nodes{Primal}, f::ScalarData, cache)  (src/surface_operators.jl:13)
+    regularize!(v::Edges, vb::VectorData, cache)           (:36)"""
+    if isinstance(s, Edges):
+        _expect(f, VectorData, "regularize")
+        cache._check_n(f, 2 * cache.N, "regularize")
+        L.check(cache._lib.ilm_regularize(cache._plan, L.EDGES, _ptr(f.data), _ptr(s.data)))
+        return s
+    _expect(s, Nodes, "regularize")
+    _expect(f, ScalarData, "regularize")
+    cache._check_n(f, cache.N, "regularize")
+    cache._check_n(s, _grid_len(cache, s.layout), "regularize")
+    L.check(cache._lib.ilm_regularize(cache._plan, s.layout, _ptr(f.data), _ptr(s.data)))
+    return s
+
+
+def interpolate(f, s, cache):
+    """interpolate!(f::ScalarData, s::Nodes, cache) (:56), (vb::VectorData, v::Edges) (:78)"""
+    if isinstance(s, Edges):
+        _expect(f, VectorData, "interpolate")
+        cache._check_n(f, 2 * cache.N, "interpolate")
+        L.check(cache._lib.ilm_interpolate(cache._plan, L.EDGES, _ptr(s.data), _ptr(f.data)))
+        return f
+    _expect(s, Nodes, "interpolate")
+    _expect(f, ScalarData, "interpolate")
+    cache._check_n(f, cache.N, "interpolate")
+    cache._check_n(s, _grid_len(cache, s.layout), "interpolate")
+    L.check(cache._lib.ilm_interpolate(cache._plan, s.layout, _ptr(s.data), _ptr(f.data)))
+    return f
+
+
+def _s2e(fn_mode, q, f, cache, what):
+    _expect(q, Edges, what)
+    _expect(f, ScalarData, what)
+    cache._check_n(f, cache.N, what)
+    L.check(cache._lib.ilm_regularize_normal(cache._plan, fn_mode, _ptr(f.data), _ptr(q.data)))
+    return q
+
+
+def _e2s(fn_mode, vn, q, cache, what):
+    _expect(q, Edges, what)
+    _expect(vn, ScalarData, what)
+    cache._check_n(vn, cache.N, what)
+    L.check(cache._lib.ilm_normal_interpolate(cache._plan, fn_mode, _ptr(q.data), _ptr(vn.data)))
+    return vn
+
+
+def regularize_normal(q, f, cache):
+    """regularize_normal!(q::Edges, f::ScalarData, cache) (:98)"""
+    return _s2e(L.NORMAL, q, f, cache, "regularize_normal")
+
+
+def regularize_normal_cross(q, f, cache):
+    """regularize_normal_cross!(q::Edges, f::ScalarData, cache) (:150)"""
+    return _s2e(L.CROSS, q, f, cache, "regularize_normal_cross")
+
+
+def normal_interpolate(vn, q, cache):
+    """normal_interpolate!(vn::ScalarData, q::Edges, cache) (:228)"""
+    return _e2s(L.NORMAL, vn, q, cache, "normal_interpolate")
+
+
+def normal_cross_interpolate(vn, q, cache):
+    """normal_cross_interpolate!(vn::ScalarData, q::Edges, cache) (:270)"""
+    return _e2s(L.CROSS, vn, q, cache, "normal_cross_interpolate")
+
+
+def divergence(p, q, cache):
+    """divergence!(p::Nodes{Primal}, q::Edges, cache) (src/grid_operators.jl:25)"""
+    _expect_nodes(p, Primal, "divergence")
+    _expect(q, Edges, "divergence")
+    L.check(cache._lib.ilm_divergence(cache._plan, _ptr(q.data), _ptr(p.data)))
+    return p
+
+
+def grad(q, p, cache):
+    """grad!(q::Edges, p::Nodes{Primal}, cache) (src/grid_operators.jl:45)"""
+    _expect(q, Edges, "grad")
+    _expect_nodes(p, Primal, "grad")
+    L.check(cache._lib.ilm_grad(cache._plan, _ptr(p.data), _ptr(q.data)))
+    return q
+
+
+def curl(a, b, cache):
+    """curl!(q::Edges, s::Nodes{Dual}, cache) / curl!(w::Nodes{Dual}, q::Edges, cache)
+    (src/grid_operators.jl:79,97)"""
+    if isinstance(a, Edges):
+        _expect_nodes(b, Dual, "curl")
+        L.check(cache._lib.ilm_curl_n2e(cache._plan, _ptr(b.data), _ptr(a.data)))
+    else:
+        _expect_nodes(a, Dual, "curl")
+        _expect(b, Edges, "curl")
+        L.check(cache._lib.ilm_curl_e2n(cache._plan, _ptr(b.data), _ptr(a.data)))
+    return a
+
+
+def laplacian(w, s, cache):
+    """laplacian!(w, s, cache) (src/grid_operators.jl:123)"""
+    if type(w) is not type(s) or w.layout != s.layout:
+        raise MethodError("laplacian: input and output must have the same type")
+    L.check(cache._lib.ilm_laplacian(cache._plan, w.layout, _ptr(s.data), _ptr(w.data)))
+    return w
+
+
+def inverse_laplacian(w, cache):
+    """inverse_laplacian!(w, cache) in place (src/grid_operators.jl:153)"""
+    _expect(w, (Nodes, Edges), "inverse_laplacian")
+    cache._check_n(w, _grid_len(cache, w.layout), "inverse_laplacian")
+    L.check(cache._lib.ilm_inverse_laplacian(cache._plan, w.layout, _ptr(w.data)))
+    return w
+
+
+def surface_divergence(theta, f, cache):
+    """surface_divergence!(theta::Nodes{Primal}, f::ScalarData, cache) (src/surface_operators.jl:530)"""
+    _expect_nodes(theta, Primal, "surface_divergence")
+    _expect(f, ScalarData, "surface_divergence")
+    cache._check_n(f, cache.N, "surface_divergence")
+    L.check(cache._lib.ilm_surface_divergence(cache._plan, L.NORMAL, _ptr(f.data), _ptr(theta.data)))
+    return theta
+
+
+def surface_divergence_cross(theta, f, cache):
+    """surface_divergence_cross! (:679; documented operator)"""
+    _expect_nodes(theta, Primal, "surface_divergence_cross")
+    _expect(f, ScalarData, "surface_divergence_cross")
+    L.check(cache._lib.ilm_surface_divergence(cache._plan, L.CROSS, _ptr(f.data), _ptr(theta.data)))
+    return theta
+
+
+def surface_grad(vn, phi, cache):
+    """surface_grad!(vn::ScalarData, phi::Nodes{Primal}, cache) (:604)"""
+    _expect(vn, ScalarData, "surface_grad")
+    _expect_nodes(phi, Primal, "surface_grad")
+    L.check(cache._lib.ilm_surface_grad(cache._plan, L.NORMAL, _ptr(phi.data), _ptr(vn.data)))
+    return vn
+
+
+def surface_grad_cross(vn, phi, cache):
+    """surface_grad_cross! (:712)"""
+    _expect(vn, ScalarData, "surface_grad_cross")
+    _expect_nodes(phi, Primal, "surface_grad_cross")
+    L.check(cache._lib.ilm_surface_grad(cache._plan, L.CROSS, _ptr(phi.data), _ptr(vn.data)))
+    return vn
+
+
+def _surface_curl(mode, a, b, cache, what):
+    if isinstance(a, Nodes):
+        _expect_nodes(a, Dual, what)
+        _expect(b, ScalarData, what)
+        L.check(cache._lib.ilm_surface_curl_s2n(cache._plan, mode, _ptr(b.data), _ptr(a.data)))
+    else:
+        _expect(a, ScalarData, what)
+        _expect_nodes(b, Dual, what)
+        L.check(cache._lib.ilm_surface_curl_n2s(cache._plan, mode, _ptr(b.data), _ptr(a.data)))
+    return a
+
+
+def surface_curl(a, b, cache):
+    """surface_curl!(w::Nodes{Dual}, f::ScalarData, cache) (:357) /
+    surface_curl!(vn::ScalarData, s::Nodes{Dual}, cache) (:412)"""
+    return _surface_curl(L.NORMAL, a, b, cache, "surface_curl")
+
+
+def surface_curl_cross(a, b, cache):
+    """surface_curl_cross! (:467, :493)"""
+    return _surface_curl(L.CROSS, a, b, cache, "surface_curl_cross")
+
+
+def mask(cache):
+    """mask(cache) (src/surface_operators.jl:737): 1 inside, 0 outside, on Nodes{Primal}."""
+    if cache.scaling != GridScaling:
+        raise MethodError("mask is only defined for GridScaling caches")
+    m = cache.zeros_grid()
+    L.check(cache._lib.ilm_mask(cache._plan, _ptr(m.data)))
+    return m
+
+
+def complementary_mask(cache):
+    m = mask(cache)
+    if _is_torch(m.data):
+        m.data.neg_().add_(1.0)
+    else:
+        m.data[...] = 1.0 - m.data
+    return m
+
+
+# --------------------------------------------------------------------------
+# matrix operators (src/matrix_operators.jl) and the surface-point solve
+# --------------------------------------------------------------------------
+def _matrix(cache, ncols):
+    if cache.device:
+        import torch
+        return torch.zeros(int(ncols) * cache.N, dtype=torch.float64, device="cuda")
+    return np.zeros(int(ncols) * cache.N, dtype=np.float64)
+
+
+def _as_matrix(buf, N, ncols):
+    if _is_torch(buf):
+        return buf.view(ncols, N).t()          # column-major N x ncols view
+    return buf.reshape((N, ncols), order="F")
+
+
+def _schur(which, cache, scale, cols):
+    c0, c1 = (0, cache.N) if cols is None else cols
+    buf = _matrix(cache, c1 - c0)
+    L.check(cache._lib.ilm_create_schur(cache._plan, which, float(scale), int(c0), int(c1), _ptr(buf)))
+    return _as_matrix(buf, cache.N, c1 - c0)
+
+
+def create_RTLinvR(cache, scale=1.0, cols=None):
+    """create_RTLinvR(cache; scale) (src/matrix_operators.jl:9-30).  `cols=(c0,c1)`
+    builds a column block (the multi-GPU shard)."""
+    return _schur(L.RTLINVR, cache, scale, cols)
+
+
+def create_CLinvCT(cache, scale=1.0, cols=None):
+    """create_CLinvCT (src/matrix_operators.jl:40-61)"""
+    return _schur(L.CLINVCT, cache, scale, cols)
+
+
+def create_GLinvD(cache, scale=1.0, cols=None):
+    """create_GLinvD (src/matrix_operators.jl:135-155)"""
+    return _schur(L.GLINVD, cache, scale, cols)
+
+
+def create_GLinvD_cross(cache, scale=1.0, cols=None):
+    """create_GLinvD_cross (src/matrix_operators.jl:195-215)"""
+    return _schur(L.GLINVD_CROSS, cache, scale, cols)
+
+
+def create_nRTRn(cache, scale=1.0):
+    """create_nRTRn (src/matrix_operators.jl:225-244)"""
+    buf = _matrix(cache, cache.N)
+    L.check(cache._lib.ilm_create_nRTRn(cache._plan, float(scale), _ptr(buf)))
+    return _as_matrix(buf, cache.N, cache.N)
+
+
+def create_surface_filter(cache):
+    """create_surface_filter (src/matrix_operators.jl:254-268)"""
+    buf = _matrix(cache, cache.N)
+    L.check(cache._lib.ilm_create_surface_filter(cache._plan, _ptr(buf)))
+    return _as_matrix(buf, cache.N, cache.N)
+
+
+def _colmajor_buffer(A):
+    """Return (flat column-major buffer, n) for a square matrix given as numpy
+    (any order) or as the torch column-major view produced by _as_matrix."""
+    if _is_torch(A):
+        n = A.shape[0]
+        At = A.t()
+        if not At.is_contiguous():
+            At = At.contiguous()
+        return At.reshape(-1), n
+    Af = np.asfortranarray(A, dtype=np.float64)
+    return Af.reshape(-1, order="F"), Af.shape[0]
+
+
+class LU:
+    """lu(S): dense LU with partial pivoting on the GPU (LAPACK getrf semantics)."""
+
+    def __init__(self, A, stream=None):
+        buf, n = _colmajor_buffer(A)
+        if _is_torch(buf):
+            import torch
+            self.lu = buf.clone()
+            self.ipiv = torch.zeros(n, dtype=torch.int32, device="cuda")
+        else:
+            self.lu = buf.copy()
+            self.ipiv = np.zeros(n, dtype=np.int32)
+        self.n = n
+        self.stream = stream
+        L.check(L.load().ilm_dense_factor(n, _ptr(self.lu), _ptr(self.ipiv), C.c_void_p(stream or 0)))
+
+    def solve(self, b):
+        """S \\ b, in place on a copy; b is ScalarData or a flat buffer."""
+        data = b.data if isinstance(b, _Data) else b
+        if int(np.prod(data.shape)) != self.n:
+            raise DimensionMismatch(f"solve: expected length {self.n}")
+        out = data.clone() if _is_torch(data) else np.array(data, dtype=np.float64, copy=True)
+        if _is_torch(out) != _is_torch(self.lu):
+            raise MethodError("solve: right-hand side and factorisation must live on the same side (host/device)")
+        L.check(L.load().ilm_dense_solve(self.n, _ptr(self.lu), _ptr(self.ipiv), 1, _ptr(out), C.c_void_p(self.stream or 0)))
+        return ScalarData(self.n, data=out) if isinstance(b, _Data) else out
+
+
+def matvec_pow(Cm, k, s, stream=None):
+    """s <- C^k s  (`s .= C^5*s`, test/literate/dirichlet.jl:124)."""
+    buf, n = _colmajor_buffer(Cm)
+    data = s.data if isinstance(s, _Data) else s
+    if int(np.prod(data.shape)) != n:
+        raise DimensionMismatch(f"matvec_pow: expected length {n}")
+    L.check(L.load().ilm_dense_matvec_pow(n, _ptr(buf), int(k), _ptr(data), C.c_void_p(stream or 0)))
+    return s
+
+
+# --------------------------------------------------------------------------
+# the north-star algorithm: Dirichlet Poisson by block LU
+# --------------------------------------------------------------------------
+def dirichlet_poisson(cache, fplus, fminus=None, S=None, filter_passes=0):
+    """test/literate/dirichlet.jl:71-107 on the B200 path.  fplus/fminus: surface
+    values of the exterior/interior Dirichlet data.  Returns (f, s, S)."""
+    N = cache.N
+    fplus = np.asarray(fplus, dtype=np.float64)
+    fminus = np.zeros(N) if fminus is None else np.asarray(fminus, dtype=np.float64)
+    d = cache.zeros_surface().set(fplus - fminus)
+    fb = 0.5 * (fplus + fminus)
+    fstar = cache.zeros_grid()
+    surface_divergence(fstar, d, cache)
+    inverse_laplacian(fstar, cache)
+    if S is None:
+        S = create_RTLinvR(cache)
+    s = cache.zeros_surface()
+    interpolate(s, fstar, cache)
+    if cache.device:
+        import torch
+        rhs = torch.from_numpy(fb).cuda() - s.data
+        sol = LU(S).solve(rhs)
+        s.data.copy_(-sol)
+    else:
+        rhs = fb - s.data
+        sol = LU(S).solve(rhs)
+        s.data[...] = -sol
+    f = cache.zeros_grid()
+    regularize(f, s, cache)
+    inverse_laplacian(f, cache)
+    if cache.device:
+        f.data.add_(fstar.data)
+    else:
+        f.data += fstar.data
+    if filter_passes:
+        Cm = create_surface_filter(cache)
+        matvec_pow(Cm, filter_passes, s)
+    return f, s, S

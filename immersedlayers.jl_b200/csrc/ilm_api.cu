@@ -1,0 +1,549 @@
+// ilm_api.cu -- the C ABI of libilm_b200.so (include/ilm_b200.h): plan life
+// cycle, host/device pointer plumbing and the operator entry points that mirror
+// ImmersedLayers' methods on BasicILMCache.
+#include <cstdio>
+#include <cstring>
+
+#include "ilm_internal.h"
+
+namespace ilm {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+    g_err = buf;
+    return ILM_ECUDA;
+}
+
+bool is_device_ptr(const void* ptr) {
+    if (!ptr) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+void* Io::stage(size_t bytes) {
+    if (slot >= (int)p->staging.size()) { p->staging.push_back(nullptr); p->staging_cap.push_back(0); }
+    if (p->staging_cap[slot] < bytes) {
+        cudaFree(p->staging[slot]);
+        p->staging[slot] = nullptr;
+        if (cudaMalloc(&p->staging[slot], bytes) != cudaSuccess) { status = ILM_ENOMEM; set_error("staging allocation failed"); return nullptr; }
+        p->staging_cap[slot] = bytes;
+    }
+    return p->staging[slot++];
+}
+const double* Io::in(const double* user, size_t n) {
+    if (n == 0 || is_device_ptr(user)) return user;
+    void* d = stage(n * sizeof(double));
+    if (!d) return nullptr;
+    if (cudaMemcpyAsync(d, user, n * sizeof(double), cudaMemcpyHostToDevice, p->stream) != cudaSuccess) status = ILM_ECUDA;
+    return (const double*)d;
+}
+double* Io::out(double* user, size_t n) {
+    if (n == 0 || is_device_ptr(user)) return user;
+    void* d = stage(n * sizeof(double));
+    if (!d) return nullptr;
+    back.push_back({user, d, n * sizeof(double)});
+    return (double*)d;
+}
+double* Io::inout(double* user, size_t n) {
+    if (n == 0 || is_device_ptr(user)) return user;
+    void* d = stage(n * sizeof(double));
+    if (!d) return nullptr;
+    if (cudaMemcpyAsync(d, user, n * sizeof(double), cudaMemcpyHostToDevice, p->stream) != cudaSuccess) status = ILM_ECUDA;
+    back.push_back({user, d, n * sizeof(double)});
+    return (double*)d;
+}
+int Io::finish() {
+    if (status != ILM_OK) return status;
+    for (auto& b : back) ILM_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, p->stream));
+    if (!back.empty()) ILM_CUDA(cudaStreamSynchronize(p->stream));
+    return ILM_OK;
+}
+
+static int upload_points(ilm_plan* p, int N, const double* x, const double* y, const double* nx, const double* ny,
+                         const double* ds) {
+    if (N > p->ncap) {
+        cudaFree(p->x); cudaFree(p->y); cudaFree(p->nx); cudaFree(p->ny); cudaFree(p->ds); cudaFree(p->s_a);
+        const size_t b = (size_t)N * sizeof(double);
+        ILM_CUDA(cudaMalloc(&p->x, b)); ILM_CUDA(cudaMalloc(&p->y, b)); ILM_CUDA(cudaMalloc(&p->nx, b));
+        ILM_CUDA(cudaMalloc(&p->ny, b)); ILM_CUDA(cudaMalloc(&p->ds, b)); ILM_CUDA(cudaMalloc(&p->s_a, 4 * b));
+        p->ncap = N;
+    }
+    p->N = N;
+    if (N > 0) {
+        const size_t b = (size_t)N * sizeof(double);
+        const cudaMemcpyKind kd = cudaMemcpyDefault;
+        ILM_CUDA(cudaMemcpyAsync(p->x, x, b, kd, p->stream)); ILM_CUDA(cudaMemcpyAsync(p->y, y, b, kd, p->stream));
+        ILM_CUDA(cudaMemcpyAsync(p->nx, nx, b, kd, p->stream)); ILM_CUDA(cudaMemcpyAsync(p->ny, ny, b, kd, p->stream));
+        ILM_CUDA(cudaMemcpyAsync(p->ds, ds, b, kd, p->stream));
+    }
+    return build_tables(p);
+}
+
+static bool layout_ok(int layout) { return layout >= ILM_NODES_PRIMAL && layout <= ILM_YEDGES; }
+static double deriv_div(const ilm_plan* p) { return p->scaling == ILM_GRID_SCALING ? p->g.dx : 1.0; }
+static size_t n_edges_u(const ilm_plan* p) { return (size_t)p->g.NX * (p->g.NY - 1); }
+static size_t n_edges_v(const ilm_plan* p) { return (size_t)(p->g.NX - 1) * p->g.NY; }
+static size_t n_edges(const ilm_plan* p) { return n_edges_u(p) + n_edges_v(p); }
+static size_t n_layout(const ilm_plan* p, int layout) {
+    if (layout == ILM_EDGES) return n_edges(p);
+    return layout_info(layout, p->g.NX, p->g.NY).n();
+}
+
+// q = Rf (n o f) or Rf (n x f e_z) into an Edges buffer (src/surface_operators.jl:100-103,159-162)
+static int regularize_normal_dev(ilm_plan* p, int mode, const double* f, double* edges) {
+    double* u = edges;
+    double* v = edges + n_edges_u(p);
+    if (mode == ILM_NORMAL) {
+        ILM_TRY(launch_regularize(p, p->tab[ILM_XEDGES], f, p->nx, 1.0, u, true));
+        ILM_TRY(launch_regularize(p, p->tab[ILM_YEDGES], f, p->ny, 1.0, v, true));
+    } else {
+        ILM_TRY(launch_regularize(p, p->tab[ILM_XEDGES], f, p->ny, 1.0, u, true));
+        ILM_TRY(launch_regularize(p, p->tab[ILM_YEDGES], f, p->nx, -1.0, v, true));
+    }
+    return ILM_OK;
+}
+
+static FieldRef fref(const ilm_plan* p, int layout, double* w) {
+    const LayoutInfo li = layout_info(layout, p->g.NX, p->g.NY);
+    return FieldRef{w, li.mx, li.my};
+}
+
+// device-side composites used by the public entry points and the Schur builders
+static int surface_divergence_dev(ilm_plan* p, int mode, const double* f, double* out) {
+    ILM_TRY(regularize_normal_dev(p, mode, f, p->g_edges));
+    return launch_divergence(p, p->g_edges, p->g_edges + n_edges_u(p), out, deriv_div(p));
+}
+static int surface_grad_dev(ilm_plan* p, int mode, const double* phi, double* f) {
+    ILM_TRY(launch_grad(p, phi, p->g_edges, p->g_edges + n_edges_u(p), 1.0));
+    return launch_normal_interpolate(p, mode, p->g_edges, p->g_edges + n_edges_u(p), f, deriv_div(p));
+}
+static int surface_curl_s2n_dev(ilm_plan* p, int mode, const double* f, double* out) {
+    ILM_TRY(regularize_normal_dev(p, mode, f, p->g_edges));
+    return launch_curl_e2n(p, p->g_edges, p->g_edges + n_edges_u(p), out, deriv_div(p));
+}
+static int surface_curl_n2s_dev(ilm_plan* p, int mode, const double* s, double* f) {
+    ILM_TRY(launch_curl_n2e(p, s, p->g_edges, p->g_edges + n_edges_u(p), 1.0));
+    return launch_normal_interpolate(p, mode, p->g_edges, p->g_edges + n_edges_u(p), f, deriv_div(p));
+}
+
+__global__ void k_unit(double* __restrict__ s, int n, int col) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) s[i] = (i == col) ? 1.0 : 0.0;
+}
+static int set_unit(ilm_plan* p, double* s, int col) {
+    k_unit<<<(p->N + 127) / 128, 128, 0, p->stream>>>(s, p->N, col);
+    ILM_CUDA(cudaGetLastError());
+    p->launches++;
+    return ILM_OK;
+}
+
+}  // namespace ilm
+
+using namespace ilm;
+
+#define ILM_CHECK_PLAN(p)                                   \
+    do {                                                    \
+        if (!(p)) { set_error("null plan"); return ILM_EINVAL; } \
+        cudaSetDevice((p)->device);                         \
+    } while (0)
+
+extern "C" const char* ilm_last_error(void) { return g_err.c_str(); }
+
+extern "C" int ilm_plan_create(const ilm_grid* grid, int N, const double* x, const double* y, const double* nx,
+                               const double* ny, const double* ds, int ddf, int scaling, const double* lgf, int nlgf,
+                               double c0, double lap_factor, void* stream, ilm_plan** out) {
+    if (!grid || !out || N < 0 || (N > 0 && (!x || !y || !nx || !ny || !ds)) || !lgf) {
+        set_error("ilm_plan_create: null argument");
+        return ILM_EINVAL;
+    }
+    if (ddf < 0 || ddf > ILM_DDF_WITCHHAT || (scaling != ILM_GRID_SCALING && scaling != ILM_INDEX_SCALING)) {
+        set_error("ilm_plan_create: unknown ddf or scaling");
+        return ILM_EINVAL;
+    }
+    if (grid->NX < 4 || grid->NY < 4 || !(grid->dx > 0) || lap_factor == 0.0) {
+        set_error("ilm_plan_create: bad grid");
+        return ILM_ESIZE;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("ilm_plan_create: no CUDA device (this library has no CPU fallback)");
+        return ILM_ECUDA;
+    }
+    ilm_plan* p = new ilm_plan();
+    p->g = *grid; p->ddf = ddf; p->scaling = scaling; p->c0 = c0; p->lap_factor = lap_factor;
+    p->stream = (cudaStream_t)stream;
+    int st = ILM_OK;
+    auto fail = [&](int s) { ilm_plan_destroy(p); return s; };
+    if (cudaGetDevice(&p->device) != cudaSuccess) return fail(ILM_ECUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) return fail(ILM_ECUDA);
+    p->nsm = prop.multiProcessorCount;
+    const size_t nfull = (size_t)grid->NX * grid->NY;
+    if (cudaMalloc(&p->g_a, nfull * sizeof(double)) != cudaSuccess || cudaMalloc(&p->g_b, nfull * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&p->g_edges, 2 * nfull * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("ilm_plan_create: out of device memory");
+        return fail(ILM_ENOMEM);
+    }
+    if ((st = conv_setup(p)) != ILM_OK) return fail(st);
+    if ((st = conv_add_kernel(p, lgf, nlgf, c0, lap_factor, nullptr)) != ILM_OK) return fail(st);
+    if ((st = upload_points(p, N, x, y, nx, ny, ds)) != ILM_OK) return fail(st);
+    if (cudaStreamSynchronize(p->stream) != cudaSuccess) return fail(ILM_ECUDA);
+    *out = p;
+    return ILM_OK;
+}
+
+extern "C" int ilm_plan_update_points(ilm_plan* p, int N, const double* x, const double* y, const double* nx,
+                                      const double* ny, const double* ds) {
+    ILM_CHECK_PLAN(p);
+    if (N < 0 || (N > 0 && (!x || !y || !nx || !ny || !ds))) { set_error("ilm_plan_update_points: bad arguments"); return ILM_EINVAL; }
+    return upload_points(p, N, x, y, nx, ny, ds);
+}
+
+extern "C" void ilm_plan_destroy(ilm_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    for (auto& t : p->tab) free_table(t);
+    conv_free(p);
+    cudaFree(p->x); cudaFree(p->y); cudaFree(p->nx); cudaFree(p->ny); cudaFree(p->ds);
+    cudaFree(p->g_edges); cudaFree(p->g_a); cudaFree(p->g_b); cudaFree(p->s_a);
+    for (void* s : p->staging) cudaFree(s);
+    delete p;
+}
+
+extern "C" int ilm_plan_sync(ilm_plan* p) {
+    ILM_CHECK_PLAN(p);
+    ILM_CUDA(cudaStreamSynchronize(p->stream));
+    return ILM_OK;
+}
+extern "C" int ilm_plan_npoints(const ilm_plan* p) { return p ? p->N : -1; }
+extern "C" int64_t ilm_layout_size(const ilm_plan* p, int layout) {
+    if (!p || layout < 0 || layout > ILM_EDGES) return -1;
+    return (int64_t)n_layout(p, layout);
+}
+extern "C" int64_t ilm_plan_launch_count(const ilm_plan* p) { return p ? p->launches : -1; }
+
+extern "C" int ilm_get_table(ilm_plan* p, int layout, int* W, int64_t* idx, double* wR, double* wE) {
+    ILM_CHECK_PLAN(p);
+    if (!layout_ok(layout)) { set_error("ilm_get_table: bad layout"); return ILM_EINVAL; }
+    const DevTable& t = p->tab[layout];
+    const int W2 = t.W * t.W, N = p->N;
+    if (W) *W = t.W;
+    if (N == 0) return ILM_OK;
+    ILM_CUDA(cudaStreamSynchronize(p->stream));
+    if (wR) ILM_CUDA(cudaMemcpy(wR, t.wR, (size_t)N * W2 * sizeof(double), cudaMemcpyDefault));
+    if (wE) ILM_CUDA(cudaMemcpy(wE, t.wE, (size_t)N * W2 * sizeof(double), cudaMemcpyDefault));
+    if (idx) {
+        std::vector<int> hi(N), hj(N);
+        ILM_CUDA(cudaMemcpy(hi.data(), t.i0, N * sizeof(int), cudaMemcpyDeviceToHost));
+        ILM_CUDA(cudaMemcpy(hj.data(), t.j0, N * sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<int64_t> h((size_t)N * W2);
+        for (int k = 0; k < N; ++k)
+            for (int b = 0; b < t.W; ++b)
+                for (int a = 0; a < t.W; ++a) {
+                    const int i = hi[k] + a, j = hj[k] + b;
+                    h[(size_t)k * W2 + b * t.W + a] = (i >= 0 && i < t.mx && j >= 0 && j < t.my) ? (int64_t)i + (int64_t)t.mx * j : -1;
+                }
+        ILM_CUDA(cudaMemcpy(idx, h.data(), h.size() * sizeof(int64_t), cudaMemcpyDefault));
+    }
+    return ILM_OK;
+}
+
+// ---------------------------------------------------------------- regularize / interpolate
+extern "C" int ilm_regularize(ilm_plan* p, int layout, const double* f, double* grid) {
+    ILM_CHECK_PLAN(p);
+    if (layout == ILM_EDGES) {   // Edges <- VectorData [u; v]
+        Io io(p);
+        const double* df = io.in(f, 2 * (size_t)p->N);
+        double* dg = io.out(grid, n_edges(p));
+        if (io.status) return io.status;
+        ILM_TRY(launch_regularize(p, p->tab[ILM_XEDGES], df, nullptr, 1.0, dg, true));
+        ILM_TRY(launch_regularize(p, p->tab[ILM_YEDGES], df + p->N, nullptr, 1.0, dg + n_edges_u(p), true));
+        return io.finish();
+    }
+    if (!layout_ok(layout)) { set_error("ilm_regularize: bad layout"); return ILM_EINVAL; }
+    Io io(p);
+    const double* df = io.in(f, p->N);
+    double* dg = io.out(grid, n_layout(p, layout));
+    if (io.status) return io.status;
+    ILM_TRY(launch_regularize(p, p->tab[layout], df, nullptr, 1.0, dg, true));
+    return io.finish();
+}
+
+extern "C" int ilm_interpolate(ilm_plan* p, int layout, const double* grid, double* f) {
+    ILM_CHECK_PLAN(p);
+    if (layout == ILM_EDGES) {
+        Io io(p);
+        const double* dg = io.in(grid, n_edges(p));
+        double* df = io.out(f, 2 * (size_t)p->N);
+        if (io.status) return io.status;
+        ILM_TRY(launch_interpolate(p, p->tab[ILM_XEDGES], dg, df));
+        ILM_TRY(launch_interpolate(p, p->tab[ILM_YEDGES], dg + n_edges_u(p), df + p->N));
+        return io.finish();
+    }
+    if (!layout_ok(layout)) { set_error("ilm_interpolate: bad layout"); return ILM_EINVAL; }
+    Io io(p);
+    const double* dg = io.in(grid, n_layout(p, layout));
+    double* df = io.out(f, p->N);
+    if (io.status) return io.status;
+    ILM_TRY(launch_interpolate(p, p->tab[layout], dg, df));
+    return io.finish();
+}
+
+extern "C" int ilm_regularize_normal(ilm_plan* p, int mode, const double* f, double* edges) {
+    ILM_CHECK_PLAN(p);
+    if (mode != ILM_NORMAL && mode != ILM_CROSS) { set_error("bad normal mode"); return ILM_EINVAL; }
+    Io io(p);
+    const double* df = io.in(f, p->N);
+    double* de = io.out(edges, n_edges(p));
+    if (io.status) return io.status;
+    ILM_TRY(regularize_normal_dev(p, mode, df, de));
+    return io.finish();
+}
+
+extern "C" int ilm_normal_interpolate(ilm_plan* p, int mode, const double* edges, double* f) {
+    ILM_CHECK_PLAN(p);
+    if (mode != ILM_NORMAL && mode != ILM_CROSS) { set_error("bad normal mode"); return ILM_EINVAL; }
+    Io io(p);
+    const double* de = io.in(edges, n_edges(p));
+    double* df = io.out(f, p->N);
+    if (io.status) return io.status;
+    ILM_TRY(launch_normal_interpolate(p, mode, de, de + n_edges_u(p), df, 1.0));
+    return io.finish();
+}
+
+// ---------------------------------------------------------------- stencils
+extern "C" int ilm_divergence(ilm_plan* p, const double* edges, double* nodes) {
+    ILM_CHECK_PLAN(p);
+    Io io(p);
+    const double* de = io.in(edges, n_edges(p));
+    double* dn = io.out(nodes, n_layout(p, ILM_NODES_PRIMAL));
+    if (io.status) return io.status;
+    ILM_TRY(launch_divergence(p, de, de + n_edges_u(p), dn, deriv_div(p)));
+    return io.finish();
+}
+extern "C" int ilm_grad(ilm_plan* p, const double* nodes, double* edges) {
+    ILM_CHECK_PLAN(p);
+    Io io(p);
+    const double* dn = io.in(nodes, n_layout(p, ILM_NODES_PRIMAL));
+    double* de = io.out(edges, n_edges(p));
+    if (io.status) return io.status;
+    ILM_TRY(launch_grad(p, dn, de, de + n_edges_u(p), deriv_div(p)));
+    return io.finish();
+}
+extern "C" int ilm_curl_n2e(ilm_plan* p, const double* nodes, double* edges) {
+    ILM_CHECK_PLAN(p);
+    Io io(p);
+    const double* dn = io.in(nodes, n_layout(p, ILM_NODES_DUAL));
+    double* de = io.out(edges, n_edges(p));
+    if (io.status) return io.status;
+    ILM_TRY(launch_curl_n2e(p, dn, de, de + n_edges_u(p), deriv_div(p)));
+    return io.finish();
+}
+extern "C" int ilm_curl_e2n(ilm_plan* p, const double* edges, double* nodes) {
+    ILM_CHECK_PLAN(p);
+    Io io(p);
+    const double* de = io.in(edges, n_edges(p));
+    double* dn = io.out(nodes, n_layout(p, ILM_NODES_DUAL));
+    if (io.status) return io.status;
+    ILM_TRY(launch_curl_e2n(p, de, de + n_edges_u(p), dn, deriv_div(p)));
+    return io.finish();
+}
+extern "C" int ilm_laplacian(ilm_plan* p, int layout, const double* in, double* out) {
+    ILM_CHECK_PLAN(p);
+    if (layout < 0 || layout > ILM_EDGES) { set_error("ilm_laplacian: bad layout"); return ILM_EINVAL; }
+    if (in == out) { set_error("ilm_laplacian: in-place not supported"); return ILM_EINVAL; }
+    Io io(p);
+    const double* di = io.in(in, n_layout(p, layout));
+    double* dout = io.out(out, n_layout(p, layout));
+    if (io.status) return io.status;
+    if (layout == ILM_EDGES) {
+        const LayoutInfo lu = layout_info(ILM_XEDGES, p->g.NX, p->g.NY), lv = layout_info(ILM_YEDGES, p->g.NX, p->g.NY);
+        ILM_TRY(launch_laplacian(p, di, dout, lu.mx, lu.my, p->lap_factor));
+        ILM_TRY(launch_laplacian(p, di + lu.n(), dout + lu.n(), lv.mx, lv.my, p->lap_factor));
+    } else {
+        const LayoutInfo li = layout_info(layout, p->g.NX, p->g.NY);
+        ILM_TRY(launch_laplacian(p, di, dout, li.mx, li.my, p->lap_factor));
+    }
+    return io.finish();
+}
+
+// ---------------------------------------------------------------- convolutions
+extern "C" int ilm_convolve(ilm_plan* p, int kernel_id, int layout, double* w) {
+    ILM_CHECK_PLAN(p);
+    if (layout < 0 || layout > ILM_EDGES) { set_error("ilm_convolve: bad layout"); return ILM_EINVAL; }
+    Io io(p);
+    double* dw = io.inout(w, n_layout(p, layout));
+    if (io.status) return io.status;
+    if (layout == ILM_EDGES)
+        ILM_TRY(conv_apply(p, kernel_id, fref(p, ILM_XEDGES, dw), fref(p, ILM_YEDGES, dw + n_edges_u(p))));
+    else
+        ILM_TRY(conv_apply(p, kernel_id, fref(p, layout, dw), FieldRef{nullptr, 0, 0}));
+    return io.finish();
+}
+extern "C" int ilm_inverse_laplacian(ilm_plan* p, int layout, double* w) { return ilm_convolve(p, 0, layout, w); }
+
+extern "C" int ilm_inverse_laplacian_pair(ilm_plan* p, int layout1, double* w1, int layout2, double* w2) {
+    ILM_CHECK_PLAN(p);
+    if (!layout_ok(layout1) || !layout_ok(layout2)) { set_error("ilm_inverse_laplacian_pair: bad layout"); return ILM_EINVAL; }
+    Io io(p);
+    double* d1 = io.inout(w1, n_layout(p, layout1));
+    double* d2 = io.inout(w2, n_layout(p, layout2));
+    if (io.status) return io.status;
+    ILM_TRY(conv_apply(p, 0, fref(p, layout1, d1), fref(p, layout2, d2)));
+    return io.finish();
+}
+
+extern "C" int ilm_add_kernel(ilm_plan* p, const double* table, int n, double c0, double factor, int* id) {
+    ILM_CHECK_PLAN(p);
+    if (!table || factor == 0.0) { set_error("ilm_add_kernel: bad arguments"); return ILM_EINVAL; }
+    return conv_add_kernel(p, table, n, c0, factor, id);
+}
+
+// ---------------------------------------------------------------- composites
+#define ILM_MODE_CHECK(mode) \
+    if ((mode) != ILM_NORMAL && (mode) != ILM_CROSS) { set_error("bad normal mode"); return ILM_EINVAL; }
+
+extern "C" int ilm_surface_divergence(ilm_plan* p, int mode, const double* f, double* nodes) {
+    ILM_CHECK_PLAN(p);
+    ILM_MODE_CHECK(mode);
+    Io io(p);
+    const double* df = io.in(f, p->N);
+    double* dn = io.out(nodes, n_layout(p, ILM_NODES_PRIMAL));
+    if (io.status) return io.status;
+    ILM_TRY(surface_divergence_dev(p, mode, df, dn));
+    return io.finish();
+}
+extern "C" int ilm_surface_grad(ilm_plan* p, int mode, const double* nodes, double* f) {
+    ILM_CHECK_PLAN(p);
+    ILM_MODE_CHECK(mode);
+    Io io(p);
+    const double* dn = io.in(nodes, n_layout(p, ILM_NODES_PRIMAL));
+    double* df = io.out(f, p->N);
+    if (io.status) return io.status;
+    ILM_TRY(surface_grad_dev(p, mode, dn, df));
+    return io.finish();
+}
+extern "C" int ilm_surface_curl_s2n(ilm_plan* p, int mode, const double* f, double* nodes) {
+    ILM_CHECK_PLAN(p);
+    ILM_MODE_CHECK(mode);
+    Io io(p);
+    const double* df = io.in(f, p->N);
+    double* dn = io.out(nodes, n_layout(p, ILM_NODES_DUAL));
+    if (io.status) return io.status;
+    ILM_TRY(surface_curl_s2n_dev(p, mode, df, dn));
+    return io.finish();
+}
+extern "C" int ilm_surface_curl_n2s(ilm_plan* p, int mode, const double* nodes, double* f) {
+    ILM_CHECK_PLAN(p);
+    ILM_MODE_CHECK(mode);
+    Io io(p);
+    const double* dn = io.in(nodes, n_layout(p, ILM_NODES_DUAL));
+    double* df = io.out(f, p->N);
+    if (io.status) return io.status;
+    ILM_TRY(surface_curl_n2s_dev(p, mode, dn, df));
+    return io.finish();
+}
+
+extern "C" int ilm_mask(ilm_plan* p, double* nodes) {
+    ILM_CHECK_PLAN(p);
+    Io io(p);
+    const size_t n = n_layout(p, ILM_NODES_PRIMAL);
+    double* dn = io.out(nodes, n);
+    if (io.status) return io.status;
+    if (p->N == 0) {       // _get_mask!(msk, cache::BasicILMCache{0}) : ones
+        ILM_TRY(launch_fill(p, dn, n, 1.0));
+        return io.finish();
+    }
+    ILM_TRY(launch_fill(p, p->s_a, p->N, 1.0));
+    ILM_TRY(surface_divergence_dev(p, ILM_NORMAL, p->s_a, dn));
+    ILM_TRY(conv_apply(p, 0, fref(p, ILM_NODES_PRIMAL, dn), FieldRef{nullptr, 0, 0}));
+    ILM_TRY(launch_scale(p, dn, n, -1.0));
+    return io.finish();
+}
+
+// ---------------------------------------------------------------- Schur builders
+extern "C" int ilm_create_schur(ilm_plan* p, int which, double scale, int col_begin, int col_end, double* A) {
+    ILM_CHECK_PLAN(p);
+    const int N = p->N;
+    if (which < ILM_RTLINVR || which > ILM_GLINVD_CROSS) { set_error("ilm_create_schur: unknown matrix"); return ILM_EINVAL; }
+    if (col_begin < 0 || col_end > N || col_begin > col_end) { set_error("ilm_create_schur: bad column range"); return ILM_ESIZE; }
+    const int ncols = col_end - col_begin;
+    if (N == 0 || ncols == 0) return ILM_OK;
+    Io io(p);
+    double* dA = io.out(A, (size_t)N * ncols);
+    if (io.status) return io.status;
+    const int glayout = (which == ILM_CLINVCT) ? ILM_NODES_DUAL : ILM_NODES_PRIMAL;
+    const int mode = (which == ILM_GLINVD_CROSS) ? ILM_CROSS : ILM_NORMAL;
+    double* unit = p->s_a;            // N
+    double* sout = p->s_a + N;        // N
+    double* gf[2] = {p->g_a, p->g_b};
+    auto pre = [&](int col, double* g) -> int {
+        ILM_TRY(set_unit(p, unit, col));
+        switch (which) {
+        case ILM_RTLINVR: return launch_regularize(p, p->tab[ILM_NODES_PRIMAL], unit, nullptr, 1.0, g, true);
+        case ILM_CLINVCT: return surface_curl_s2n_dev(p, mode, unit, g);
+        default: return surface_divergence_dev(p, mode, unit, g);
+        }
+    };
+    auto post = [&](double* g, double* dst) -> int {
+        switch (which) {
+        case ILM_RTLINVR: ILM_TRY(launch_interpolate(p, p->tab[ILM_NODES_PRIMAL], g, sout)); break;
+        case ILM_CLINVCT: ILM_TRY(surface_curl_n2s_dev(p, mode, g, sout)); break;
+        default: ILM_TRY(surface_grad_dev(p, mode, g, sout)); break;
+        }
+        return launch_scale_store_column(p, sout, dst, N, -scale);
+    };
+    // two columns per complex transform (src/matrix_operators.jl:16-26 probes one at a time)
+    for (int c = col_begin; c < col_end; c += 2) {
+        const bool two = c + 1 < col_end;
+        ILM_TRY(pre(c, gf[0]));
+        if (two) ILM_TRY(pre(c + 1, gf[1]));
+        ILM_TRY(conv_apply(p, 0, fref(p, glayout, gf[0]), two ? fref(p, glayout, gf[1]) : FieldRef{nullptr, 0, 0}));
+        ILM_TRY(post(gf[0], dA + (size_t)(c - col_begin) * N));
+        if (two) ILM_TRY(post(gf[1], dA + (size_t)(c + 1 - col_begin) * N));
+    }
+    return io.finish();
+}
+
+extern "C" int ilm_create_nRTRn(ilm_plan* p, double scale, double* A) {
+    ILM_CHECK_PLAN(p);
+    const int N = p->N;
+    if (N == 0) return ILM_OK;
+    Io io(p);
+    double* dA = io.out(A, (size_t)N * N);
+    if (io.status) return io.status;
+    double* unit = p->s_a;
+    double* sout = p->s_a + N;
+    for (int c = 0; c < N; ++c) {
+        ILM_TRY(set_unit(p, unit, c));
+        ILM_TRY(regularize_normal_dev(p, ILM_NORMAL, unit, p->g_edges));
+        ILM_TRY(launch_normal_interpolate(p, ILM_NORMAL, p->g_edges, p->g_edges + n_edges_u(p), sout, 1.0));
+        ILM_TRY(launch_scale_store_column(p, sout, dA + (size_t)c * N, N, scale));
+    }
+    return io.finish();
+}
+
+extern "C" int ilm_create_surface_filter(ilm_plan* p, double* C) {
+    ILM_CHECK_PLAN(p);
+    if (p->N == 0) return ILM_OK;
+    Io io(p);
+    double* dC = io.out(C, (size_t)p->N * p->N);
+    if (io.status) return io.status;
+    ILM_TRY(launch_surface_filter(p, p->tab[ILM_NODES_PRIMAL], dC));
+    return io.finish();
+}
+
+extern "C" int ilm_profile_conv(ilm_plan* p, int layout, int reps, double ms[3]) {
+    ILM_CHECK_PLAN(p);
+    if (!layout_ok(layout) || reps < 1 || !ms) { set_error("ilm_profile_conv: bad arguments"); return ILM_EINVAL; }
+    ILM_TRY(launch_fill(p, p->g_a, n_layout(p, layout), 1.0));
+    ILM_TRY(launch_fill(p, p->g_b, n_layout(p, layout), -0.5));
+    return conv_profile(p, fref(p, layout, p->g_a), fref(p, layout, p->g_b), reps, ms);
+}

@@ -1,0 +1,331 @@
+// ilm_dense.cu -- dense surface-point solve: LU with partial pivoting, getrs,
+// and the mat-vec power C^k s.  Replaces the LAPACK getrf/getrs behind `S\s`
+// and `C^5*s` in the reference's user-level algorithm
+// (test/literate/dirichlet.jl:99,124; neumann.jl:123,133).
+//
+// Right-looking blocked LU (NB = 32): panel factorisation by one CTA, row
+// interchanges, a triangular solve for the block row, and the trailing update
+// A22 -= A21 * A12 on the FP64 tensor pipe (mma.sync.m8n8k4.f64, "DMMA").
+#include <vector>
+
+#include "ilm_internal.h"
+
+namespace ilm {
+
+constexpr int NB = 32;
+long long g_dense_launches = 0;
+
+// ---- panel: columns [k0, k0+nb), rows [k0, n); one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_lu_panel(int n, int k0, int nb, double* __restrict__ A, int* __restrict__ ipiv) {
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_piv;
+    __shared__ double s_row[NB];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int jj = 0; jj < nb; ++jj) {
+        const int col = k0 + jj;
+        double* a_col = A + (size_t)col * n;
+        // pivot search: first maximum of |a| (idamax semantics)
+        double best = -1.0;
+        int bi = n;
+        for (int r = col + tid; r < n; r += 1024) {
+            const double v = fabs(a_col[r]);
+            if (v > best) { best = v; bi = r; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, off);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[wid] = best; s_idx[wid] = bi; }
+        __syncthreads();
+        if (wid == 0) {
+            best = s_val[lane]; bi = s_idx[lane];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, best, off);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) { s_piv = bi; ipiv[col] = bi + 1; }
+        }
+        __syncthreads();
+        const int piv = s_piv;
+        // swap rows col <-> piv inside the panel, keep the pivot row in smem
+        if (tid < nb) {
+            double* c = A + (size_t)(k0 + tid) * n;
+            const double top = c[piv];
+            if (piv != col) { c[piv] = c[col]; c[col] = top; }
+            s_row[tid] = top;
+        }
+        __syncthreads();
+        const double pivot = s_row[jj];
+        // scale the column and rank-1 update of the remaining panel columns
+        const int ncols = nb - jj - 1;
+        for (int r = col + 1 + tid; r < n; r += 1024) {
+            const double l = a_col[r] / pivot;
+            a_col[r] = l;
+            for (int c = 0; c < ncols; ++c) {
+                double* q = A + (size_t)(col + 1 + c) * n + r;
+                *q = *q - l * s_row[jj + 1 + c];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// apply the panel's row interchanges to the columns outside the panel
+__global__ void k_lu_swap(int n, int k0, int nb, double* __restrict__ A, const int* __restrict__ ipiv) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n - nb) return;
+    if (c >= k0) c += nb;
+    double* col = A + (size_t)c * n;
+    for (int jj = 0; jj < nb; ++jj) {
+        const int r = k0 + jj, pv = ipiv[r] - 1;
+        if (pv != r) { const double t = col[r]; col[r] = col[pv]; col[pv] = t; }
+    }
+}
+
+// block row: A12 <- L11^-1 A12 (unit lower triangular nb x nb)
+__global__ void k_lu_trsm(int n, int k0, int nb, double* __restrict__ A) {
+    __shared__ double L11[NB][NB + 1];
+    for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) L11[i % nb][i / nb] = A[(size_t)(k0 + i / nb) * n + k0 + i % nb];
+    __syncthreads();
+    const int c = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double* col = A + (size_t)c * n + k0;
+    double x[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) x[i] = i < nb ? col[i] : 0.0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+#pragma unroll
+        for (int j = 0; j < i; ++j) x[i] -= L11[i][j] * x[j];
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+        if (i < nb) col[i] = x[i];
+}
+
+// trailing update C -= A * B, K = kk (<= 32); 64x64 tile per CTA, 4 warps of 32x32, DMMA m8n8k4
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128) k_lu_gemm(int M, int Nc, int kk, const double* __restrict__ A,
+                                                 const double* __restrict__ B, double* __restrict__ C, int ld) {
+    constexpr int LDA = 68, LDB = 36;
+    __shared__ double As[NB * LDA];      // As[k][m]
+    __shared__ double Bs[64 * LDB];      // Bs[n][k]
+    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 64 * NB; i += 128) {
+        const int m = i & 63, k = i >> 6;
+        As[k * LDA + m] = (m0 + m < M && k < kk) ? A[(size_t)k * ld + m0 + m] : 0.0;
+    }
+    for (int i = tid; i < 64 * NB; i += 128) {
+        const int k = i & (NB - 1), nn = i >> 5;
+        Bs[nn * LDB + k] = (n0 + nn < Nc && k < kk) ? B[(size_t)(n0 + nn) * ld + k] : 0.0;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NB; k += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[(k + t) * LDA + wm + 8 * i + g];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[(wn + 8 * j + g) * LDB + k + t];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = m0 + wm + 8 * i + g;
+            const int c = n0 + wn + 8 * j + 2 * t;
+            if (r < M) {
+                if (c < Nc) C[(size_t)c * ld + r] -= acc[i][j][0];
+                if (c + 1 < Nc) C[(size_t)(c + 1) * ld + r] -= acc[i][j][1];
+            }
+        }
+}
+
+struct DenseIo {      // host/device staging without a plan
+    cudaStream_t st;
+    std::vector<void*> owned;
+    struct Back { void* host; const void* dev; size_t bytes; };
+    std::vector<Back> back;
+    explicit DenseIo(void* stream) : st((cudaStream_t)stream) {}
+    ~DenseIo() { for (void* q : owned) cudaFree(q); }
+    template <class T> int map(T* user, size_t n, bool copy_in, bool copy_out, T** dev) {
+        if (is_device_ptr(user)) { *dev = user; return ILM_OK; }
+        void* d = nullptr;
+        ILM_CUDA(cudaMalloc(&d, (n ? n : 1) * sizeof(T)));
+        owned.push_back(d);
+        if (copy_in) ILM_CUDA(cudaMemcpyAsync(d, user, n * sizeof(T), cudaMemcpyHostToDevice, st));
+        if (copy_out) back.push_back({(void*)user, d, n * sizeof(T)});
+        *dev = (T*)d;
+        return ILM_OK;
+    }
+    int finish() {
+        for (auto& b : back) ILM_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, st));
+        if (!back.empty()) ILM_CUDA(cudaStreamSynchronize(st));
+        return ILM_OK;
+    }
+};
+
+// ---- getrs pieces: single CTA, right-hand side in shared memory
+__global__ void __launch_bounds__(1024) k_getrs(int n, const double* __restrict__ LU, const int* __restrict__ ipiv,
+                                                double* __restrict__ b) {
+    extern __shared__ double sb[];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n; i += 1024) sb[i] = b[i];
+    __syncthreads();
+    if (tid == 0)
+        for (int i = 0; i < n; ++i) {
+            const int pv = ipiv[i] - 1;
+            if (pv != i) { const double t = sb[i]; sb[i] = sb[pv]; sb[pv] = t; }
+        }
+    __syncthreads();
+    // forward: unit lower
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        const int nb = min(NB, n - k0);
+        if (tid < 32) {
+            double x = tid < nb ? sb[k0 + tid] : 0.0;
+            for (int j = 0; j < nb; ++j) {
+                const double xj = __shfl_sync(0xffffffffu, x, j);
+                if (tid > j && tid < nb) x -= LU[(size_t)(k0 + j) * n + k0 + tid] * xj;
+            }
+            if (tid < nb) sb[k0 + tid] = x;
+        }
+        __syncthreads();
+        for (int r = k0 + nb + tid; r < n; r += 1024) {
+            double acc = 0.0;
+            for (int c = 0; c < nb; ++c) acc += LU[(size_t)(k0 + c) * n + r] * sb[k0 + c];
+            sb[r] -= acc;
+        }
+        __syncthreads();
+    }
+    // backward: upper
+    for (int k1 = n; k1 > 0; k1 -= NB) {
+        const int k0 = max(0, k1 - NB), nb = k1 - k0;
+        if (tid < 32) {
+            double x = tid < nb ? sb[k0 + tid] : 0.0;
+            for (int j = nb - 1; j >= 0; --j) {
+                if (tid == j) x = x / LU[(size_t)(k0 + j) * n + k0 + j];
+                const double xj = __shfl_sync(0xffffffffu, x, j);
+                if (tid < j) x -= LU[(size_t)(k0 + j) * n + k0 + tid] * xj;
+            }
+            if (tid < nb) sb[k0 + tid] = x;
+        }
+        __syncthreads();
+        for (int r = tid; r < k0; r += 1024) {
+            double acc = 0.0;
+            for (int c = 0; c < nb; ++c) acc += LU[(size_t)(k0 + c) * n + r] * sb[k0 + c];
+            sb[r] -= acc;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += 1024) b[i] = sb[i];
+}
+
+// ---- y = C x in two deterministic stages
+constexpr int MV_CH = 16;
+__global__ void k_gemv_part(int n, const double* __restrict__ C, const double* __restrict__ x, double* __restrict__ part) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y;
+    const int per = (n + MV_CH - 1) / MV_CH;
+    const int c0 = ch * per, c1 = min(n, c0 + per);
+    if (r >= n) return;
+    double acc = 0.0;
+    for (int c = c0; c < c1; ++c) acc += C[(size_t)c * n + r] * x[c];
+    part[(size_t)ch * n + r] = acc;
+}
+__global__ void k_gemv_sum(int n, const double* __restrict__ part, double* __restrict__ y) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double acc = 0.0;
+    for (int ch = 0; ch < MV_CH; ++ch) acc += part[(size_t)ch * n + r];
+    y[r] = acc;
+}
+
+}  // namespace ilm
+
+using namespace ilm;
+
+extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
+    if (n < 0 || (n > 0 && (!A || !ipiv))) { set_error("ilm_dense_factor: bad arguments"); return ILM_EINVAL; }
+    if (n == 0) return ILM_OK;
+    DenseIo io(stream);
+    double* dA = nullptr; int* dP = nullptr;
+    ILM_TRY(io.map(A, (size_t)n * n, true, true, &dA));
+    ILM_TRY(io.map(ipiv, (size_t)n, false, true, &dP));
+    cudaStream_t st = io.st;
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        const int nb = n - k0 < NB ? n - k0 : NB;
+        k_lu_panel<<<1, 1024, 0, st>>>(n, k0, nb, dA, dP);
+        if (n - nb > 0) k_lu_swap<<<(n - nb + 127) / 128, 128, 0, st>>>(n, k0, nb, dA, dP);
+        const int rem = n - k0 - nb;
+        if (rem > 0) {
+            k_lu_trsm<<<(rem + 63) / 64, 64, 0, st>>>(n, k0, nb, dA);
+            dim3 grid((rem + 63) / 64, (rem + 63) / 64);
+            k_lu_gemm<<<grid, 128, 0, st>>>(rem, rem, nb, dA + (size_t)k0 * n + k0 + nb, dA + (size_t)(k0 + nb) * n + k0,
+                                            dA + (size_t)(k0 + nb) * n + k0 + nb, n);
+            g_dense_launches += 2;
+        }
+        g_dense_launches += 2;
+    }
+    ILM_CUDA(cudaGetLastError());
+    return io.finish();
+}
+
+extern "C" int ilm_dense_solve(int n, const double* LU, const int* ipiv, int nrhs, double* B, void* stream) {
+    if (n < 0 || nrhs < 0 || (n > 0 && nrhs > 0 && (!LU || !ipiv || !B))) { set_error("ilm_dense_solve: bad arguments"); return ILM_EINVAL; }
+    if (n == 0 || nrhs == 0) return ILM_OK;
+    if ((size_t)n * sizeof(double) > 200 * 1024) { set_error("ilm_dense_solve: n too large for the shared-memory solve"); return ILM_ESIZE; }
+    DenseIo io(stream);
+    double* dLU = nullptr; int* dP = nullptr; double* dB = nullptr;
+    ILM_TRY(io.map(const_cast<double*>(LU), (size_t)n * n, true, false, &dLU));
+    ILM_TRY(io.map(const_cast<int*>(ipiv), (size_t)n, true, false, &dP));
+    ILM_TRY(io.map(B, (size_t)n * nrhs, true, true, &dB));
+    const size_t smem = (size_t)n * sizeof(double);
+    ILM_CUDA(cudaFuncSetAttribute(k_getrs, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int r = 0; r < nrhs; ++r) k_getrs<<<1, 1024, smem, io.st>>>(n, dLU, dP, dB + (size_t)r * n);
+    g_dense_launches += nrhs;
+    ILM_CUDA(cudaGetLastError());
+    return io.finish();
+}
+
+extern "C" int ilm_dense_matvec_pow(int n, const double* C, int k, double* s, void* stream) {
+    if (n < 0 || k < 0 || (n > 0 && (!C || !s))) { set_error("ilm_dense_matvec_pow: bad arguments"); return ILM_EINVAL; }
+    if (n == 0 || k == 0) return ILM_OK;
+    DenseIo io(stream);
+    double* dC = nullptr; double* ds = nullptr; double* part = nullptr;
+    ILM_TRY(io.map(const_cast<double*>(C), (size_t)n * n, true, false, &dC));
+    ILM_TRY(io.map(s, (size_t)n, true, true, &ds));
+    ILM_CUDA(cudaMalloc(&part, (size_t)MV_CH * n * sizeof(double)));
+    io.owned.push_back(part);
+    for (int it = 0; it < k; ++it) {
+        k_gemv_part<<<dim3((n + 127) / 128, MV_CH), 128, 0, io.st>>>(n, dC, ds, part);
+        k_gemv_sum<<<(n + 127) / 128, 128, 0, io.st>>>(n, part, ds);
+        g_dense_launches += 2;
+    }
+    ILM_CUDA(cudaGetLastError());
+    int s_ = io.finish();
+    ILM_CUDA(cudaStreamSynchronize(io.st));     // `part` is freed by ~DenseIo
+    return s_;
+}
+
+extern "C" int64_t ilm_dense_launch_count(void) { return (int64_t)ilm::g_dense_launches; }

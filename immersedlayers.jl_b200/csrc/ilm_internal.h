@@ -1,0 +1,143 @@
+// ilm_internal.h -- plan object and kernel-launcher prototypes shared by the
+// translation units of libilm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ilm_b200.h"
+#include "ilm_conv.cuh"
+
+namespace ilm {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define ILM_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) return ::ilm::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define ILM_TRY(call)                   \
+    do {                                \
+        int s__ = (call);               \
+        if (s__ != ILM_OK) return s__;  \
+    } while (0)
+
+struct LayoutInfo {
+    int mx, my;
+    double sx, sy;
+    size_t n() const { return (size_t)mx * my; }
+};
+inline LayoutInfo layout_info(int layout, int NX, int NY) {
+    switch (layout) {
+    case ILM_NODES_PRIMAL: return {NX - 1, NY - 1, 0.0, 0.0};
+    case ILM_NODES_DUAL: return {NX, NY, 0.5, 0.5};
+    case ILM_XEDGES: return {NX, NY - 1, 0.5, 0.0};
+    default: return {NX - 1, NY, 0.0, 0.5};      // ILM_YEDGES
+    }
+}
+
+// DDF window table + cell-bucketed gather list of one layout
+struct DevTable {
+    int W = 0, mx = 0, my = 0;
+    int* i0 = nullptr;          // N
+    int* j0 = nullptr;          // N
+    double* wR = nullptr;       // N*W*W, [k][b][a]
+    double* wE = nullptr;
+    int ncell = 0, nent = 0;
+    int* cell_idx = nullptr;    // ncell   linear index of each active cell (ascending)
+    int* cell_off = nullptr;    // ncell+1 offsets into ent
+    int* ent = nullptr;         // nent    k*W*W + slot, ascending k inside a cell
+    double* rowsum = nullptr;   // ncell   sum_k R[cell,k] (surface filter)
+};
+
+struct ConvKernel {     // one multiplier (LGF inverse, integrating factor, ...)
+    double* ghat = nullptr;
+};
+
+}  // namespace ilm
+
+struct ilm_plan {
+    ilm_grid g{};
+    int N = 0, ddf = 0, scaling = 0;
+    double c0 = 0, lap_factor = 1;
+    cudaStream_t stream = nullptr;
+    int device = 0, nsm = 0;
+    long long launches = 0;
+    // surface points (device)
+    double *x = nullptr, *y = nullptr, *nx = nullptr, *ny = nullptr, *ds = nullptr;
+    int ncap = 0;
+    ilm::DevTable tab[4];
+    // convolution engine
+    int Lx = 0, Ly = 0;
+    double2 *twx = nullptr, *twy = nullptr;
+    double2 *S = nullptr, *S2 = nullptr;
+    size_t s_cap = 0;
+    std::vector<ilm::ConvKernel> kernels;
+    // scratch (device)
+    double* g_edges = nullptr;      // Edges scratch (gsnorm_cache)
+    double* g_a = nullptr;          // NX*NY scratch field (gdata/gcurl cache)
+    double* g_b = nullptr;          // NX*NY scratch field (second Schur column)
+    double* s_a = nullptr;          // 4N surface scratch
+    std::vector<void*> staging;     // device staging for host pointers
+    std::vector<size_t> staging_cap;
+};
+
+namespace ilm {
+
+// host/device pointer plumbing for one API call
+struct Io {
+    ilm_plan* p;
+    int slot = 0;
+    struct Back { void* host; const void* dev; size_t bytes; };
+    std::vector<Back> back;
+    int status = ILM_OK;
+    explicit Io(ilm_plan* plan) : p(plan) {}
+    const double* in(const double* user, size_t n);
+    double* out(double* user, size_t n);
+    double* inout(double* user, size_t n);
+    int finish();
+private:
+    void* stage(size_t bytes);
+};
+bool is_device_ptr(const void* p);
+
+// ---- launchers (ilm_ops.cu) -------------------------------------------------
+int launch_fill(ilm_plan* p, double* dst, size_t n, double value);
+// out = sum_k wR[cell,k] * (mul ? mul[k] : 1) * sign * f[k]  on active cells (out pre-zeroed unless !zero)
+int launch_regularize(ilm_plan* p, const DevTable& t, const double* f, const double* mul, double sign, double* out,
+                      bool zero);
+int launch_interpolate(ilm_plan* p, const DevTable& t, const double* field, double* f);
+// f = a_u*(E_u u) + a_v*(E_v v) with per-point factors (normal / cross products), then / div
+int launch_normal_interpolate(ilm_plan* p, int mode, const double* u, const double* v, double* f, double div);
+int launch_unit_columns(ilm_plan* p, const DevTable& t, int col, double* out);   // out += R e_col (pre-zeroed)
+int launch_divergence(ilm_plan* p, const double* u, const double* v, double* out, double div);
+int launch_grad(ilm_plan* p, const double* in, double* u, double* v, double div);
+int launch_curl_n2e(ilm_plan* p, const double* s, double* u, double* v, double div);
+int launch_curl_e2n(ilm_plan* p, const double* u, const double* v, double* w, double div);
+int launch_laplacian(ilm_plan* p, const double* in, double* out, int mx, int my, double factor);
+int launch_scale_store_column(ilm_plan* p, const double* src, double* dst, int n, double scale);
+int launch_scale(ilm_plan* p, double* w, size_t n, double scale);
+int launch_lgf_prep(ilm_plan* p, const double* table, int ld, int NX, int NY, double c0, double* h);
+int launch_filter_rowsum(ilm_plan* p, DevTable& t);
+int launch_surface_filter(ilm_plan* p, const DevTable& t, double* C);
+
+// ---- tables (ilm_tables.cu, compiled without FMA contraction) -----------------
+int build_tables(ilm_plan* p);
+void free_table(DevTable& t);
+
+// ---- convolution engine (ilm_lgf.cu + ilm_conv_inst.cu) -------------------------
+int conv_setup(ilm_plan* p);
+int conv_add_kernel(ilm_plan* p, const double* table_host_or_dev, int n, double c0, double factor, int* id);
+int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2);
+void conv_free(ilm_plan* p);
+int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3]);
+extern long long g_dense_launches;
+// per-length launchers, which = 0: pass A, 1: pass B, 2: pass C, 3: pass G
+typedef int (*conv_launch_fn)(int which, const ConvArgs& a, int nsm, cudaStream_t st);
+conv_launch_fn conv_launcher(int L);
+const double2* conv_twiddles_host(int L, size_t* count);
+
+}  // namespace ilm

@@ -1,0 +1,167 @@
+// ilm_lgf.cu -- host side of the FFT convolution engine: transform sizes,
+// twiddle upload, spectrum buffers, multiplier (Ghat) construction and the
+// three-pass apply.  Replaces plan_laplacian / CircularConvolution set-up
+// reached from _get_laplacian (src/cache.jl:321-324) and the `L\w` apply
+// reached from inverse_laplacian! (src/grid_operators.jl:153-179).
+#include "ilm_internal.h"
+
+namespace ilm {
+
+#define ILM_DECL_L(L)                                                                  \
+    int conv_launch_L##L(int which, const ConvArgs& a, int nsm, cudaStream_t st);      \
+    const double2* conv_twiddles_L##L(size_t* count);
+ILM_DECL_L(16) ILM_DECL_L(32) ILM_DECL_L(64) ILM_DECL_L(128) ILM_DECL_L(256)
+ILM_DECL_L(512) ILM_DECL_L(1024) ILM_DECL_L(2048) ILM_DECL_L(4096)
+
+conv_launch_fn conv_launcher(int L) {
+    switch (L) {
+    case 16: return conv_launch_L16;
+    case 32: return conv_launch_L32;
+    case 64: return conv_launch_L64;
+    case 128: return conv_launch_L128;
+    case 256: return conv_launch_L256;
+    case 512: return conv_launch_L512;
+    case 1024: return conv_launch_L1024;
+    case 2048: return conv_launch_L2048;
+    case 4096: return conv_launch_L4096;
+    default: return nullptr;
+    }
+}
+
+const double2* conv_twiddles_host(int L, size_t* count) {
+    switch (L) {
+    case 16: return conv_twiddles_L16(count);
+    case 32: return conv_twiddles_L32(count);
+    case 64: return conv_twiddles_L64(count);
+    case 128: return conv_twiddles_L128(count);
+    case 256: return conv_twiddles_L256(count);
+    case 512: return conv_twiddles_L512(count);
+    case 1024: return conv_twiddles_L1024(count);
+    case 2048: return conv_twiddles_L2048(count);
+    case 4096: return conv_twiddles_L4096(count);
+    default: *count = 0; return nullptr;
+    }
+}
+
+// half padded length: smallest power of two L >= 16 with 2L >= 2n-1
+static int half_len(int n) {
+    int L = 16;
+    while (2 * L < 2 * n - 1) L <<= 1;
+    return L;
+}
+
+int conv_setup(ilm_plan* p) {
+    p->Lx = half_len(p->g.NX);
+    p->Ly = half_len(p->g.NY);
+    if (p->Lx > 4096 || p->Ly > 4096) {
+        set_error("grid larger than 4096 cells per direction is not supported by the single-GPU FFT engine yet");
+        return ILM_ESIZE;
+    }
+    size_t nx = 0, ny = 0;
+    const double2* hx = conv_twiddles_host(p->Lx, &nx);
+    const double2* hy = conv_twiddles_host(p->Ly, &ny);
+    ILM_CUDA(cudaMalloc(&p->twx, nx * sizeof(double2)));
+    ILM_CUDA(cudaMalloc(&p->twy, ny * sizeof(double2)));
+    ILM_CUDA(cudaMemcpyAsync(p->twx, hx, nx * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
+    ILM_CUDA(cudaMemcpyAsync(p->twy, hy, ny * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
+    ConvGeom g{p->Lx, p->Ly, p->g.NY, (p->g.NY + 1) & ~1};
+    p->s_cap = s_elems(g);
+    ILM_CUDA(cudaMalloc(&p->S, p->s_cap * sizeof(double2)));
+    ILM_CUDA(cudaMalloc(&p->S2, p->s_cap * sizeof(double2)));
+    ILM_CUDA(cudaStreamSynchronize(p->stream));
+    return ILM_OK;
+}
+
+void conv_free(ilm_plan* p) {
+    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->S); cudaFree(p->S2);
+    for (auto& k : p->kernels) cudaFree(k.ghat);
+    p->kernels.clear();
+}
+
+// table: n x n column-major (host or device), n >= max(NX, NY)
+int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double factor, int* id) {
+    const int NX = p->g.NX, NY = p->g.NY;
+    if (n < NX || n < NY) {
+        set_error("kernel table smaller than the grid");
+        return ILM_ESIZE;
+    }
+    double* dtab = nullptr;
+    const double* src = table;
+    if (!is_device_ptr(table)) {
+        ILM_CUDA(cudaMalloc(&dtab, (size_t)n * NY * sizeof(double)));
+        ILM_CUDA(cudaMemcpyAsync(dtab, table, (size_t)n * NY * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        src = dtab;
+    }
+    // h = eps_i eps_j (G - c0) into scratch field g_a (NX x NY)
+    ILM_TRY(launch_lgf_prep(p, src, n, NX, NY, c0, p->g_a));
+    ConvKernel k;
+    ConvArgs a{};
+    a.g = ConvGeom{p->Lx, p->Ly, NY, (NY + 1) & ~1};
+    ILM_CUDA(cudaMalloc(&k.ghat, ghat_elems(a.g) * sizeof(double)));
+    a.f1 = FieldRef{p->g_a, NX, NY};
+    a.f2 = FieldRef{nullptr, 0, 0};
+    a.S = p->S; a.S2 = p->S2;
+    a.GhatOut = k.ghat;
+    a.gscale = 1.0 / (4.0 * (double)p->Lx * (double)p->Ly * factor);
+    a.twx = p->twx; a.twy = p->twy;
+    ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream));
+    ILM_TRY(conv_launcher(p->Ly)(3, a, p->nsm, p->stream));
+    p->launches += 2;
+    ILM_CUDA(cudaStreamSynchronize(p->stream));
+    if (dtab) cudaFree(dtab);
+    p->kernels.push_back(k);
+    if (id) *id = (int)p->kernels.size() - 1;
+    return ILM_OK;
+}
+
+int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2) {
+    if (kernel_id < 0 || kernel_id >= (int)p->kernels.size()) {
+        set_error("unknown convolution kernel id");
+        return ILM_EINVAL;
+    }
+    ConvArgs a{};
+    int MY = f1.p ? f1.my : 0;
+    if (f2.p && f2.my > MY) MY = f2.my;
+    if (MY == 0) return ILM_OK;
+    a.g = ConvGeom{p->Lx, p->Ly, MY, (MY + 1) & ~1};
+    a.f1 = f1; a.f2 = f2;
+    a.S = p->S; a.S2 = p->S2;
+    a.Ghat = p->kernels[kernel_id].ghat;
+    a.twx = p->twx; a.twy = p->twy;
+    ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream));
+    ILM_TRY(conv_launcher(p->Ly)(1, a, p->nsm, p->stream));
+    ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, p->stream));
+    p->launches += 3;
+    return ILM_OK;
+}
+
+// per-pass timing for the roofline report (ilm_profile_conv)
+int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3]) {
+    ConvArgs a{};
+    int MY = f1.my > f2.my ? f1.my : f2.my;
+    a.g = ConvGeom{p->Lx, p->Ly, MY, (MY + 1) & ~1};
+    a.f1 = f1; a.f2 = f2;
+    a.S = p->S; a.S2 = p->S2;
+    a.Ghat = p->kernels[0].ghat;
+    a.twx = p->twx; a.twy = p->twy;
+    cudaEvent_t e0, e1;
+    ILM_CUDA(cudaEventCreate(&e0));
+    ILM_CUDA(cudaEventCreate(&e1));
+    const int Ls[3] = {p->Lx, p->Ly, p->Lx};
+    for (int which = 0; which < 3; ++which) {
+        ILM_TRY(conv_launcher(Ls[which])(which, a, p->nsm, p->stream));      // warm-up
+        ILM_CUDA(cudaEventRecord(e0, p->stream));
+        for (int r = 0; r < reps; ++r) ILM_TRY(conv_launcher(Ls[which])(which, a, p->nsm, p->stream));
+        ILM_CUDA(cudaEventRecord(e1, p->stream));
+        ILM_CUDA(cudaEventSynchronize(e1));
+        float t = 0;
+        ILM_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        ms[which] = (double)t / reps;
+        p->launches += reps + 1;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ILM_OK;
+}
+
+}  // namespace ilm

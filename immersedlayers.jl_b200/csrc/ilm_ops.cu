@@ -1,0 +1,382 @@
+// ilm_ops.cu -- surface <-> grid transfer kernels and staggered-grid stencils.
+//
+// regularize! / interpolate! and their normal-weighted variants
+// (src/surface_operators.jl:13-343) and divergence!/grad!/curl!/laplacian!
+// (src/grid_operators.jl:25-134 over CartesianGrids' stencils).
+//   * regularization is a deterministic gather over the active cells (no
+//     atomics): each cell adds its bucketed points in ascending point order
+//     with separately rounded multiply and add -- the summation order of the
+//     reference's CSC mat-vec -- so the field is bit-reproducible;
+//   * interpolation uses one half-warp per surface point: 16 gathers and a
+//     fixed shuffle tree;
+//   * stencils are coalesced sweeps, x fastest, 8 rows per thread, with the
+//     zero-fill, the difference and the 1/dx scaling fused into one pass
+//     (the reference does fill!, stencil, ./= dx as three sweeps).
+#include "ilm_internal.h"
+
+namespace ilm {
+
+#define ILM_LAUNCHED(p)               \
+    do {                              \
+        ILM_CUDA(cudaGetLastError()); \
+        (p)->launches++;              \
+    } while (0)
+
+// ------------------------------------------------------------------ fill / scale
+__global__ void k_fill(double* __restrict__ dst, size_t n, double value) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n2 = n >> 1;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        double2* d2 = reinterpret_cast<double2*>(dst);
+        const double2 v2 = make_double2(value, value);
+        for (size_t q = i; q < n2; q += stride) d2[q] = v2;
+        if (i == 0 && (n & 1)) dst[n - 1] = value;
+    } else {
+        for (size_t q = i; q < n; q += stride) dst[q] = value;
+    }
+}
+
+int launch_fill(ilm_plan* p, double* dst, size_t n, double value) {
+    if (n == 0) return ILM_OK;
+    size_t blocks = (n / 2 + 255) / 256;
+    const size_t cap = (size_t)p->nsm * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_fill<<<(unsigned)blocks, 256, 0, p->stream>>>(dst, n, value);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+__global__ void k_scale(double* __restrict__ w, size_t n, double s) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) w[i] = w[i] * s;
+}
+int launch_scale(ilm_plan* p, double* w, size_t n, double s) {
+    if (n == 0) return ILM_OK;
+    size_t blocks = (n + 255) / 256;
+    const size_t cap = (size_t)p->nsm * 16;
+    if (blocks > cap) blocks = cap;
+    k_scale<<<(unsigned)blocks, 256, 0, p->stream>>>(w, n, s);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+__global__ void k_scale_store(const double* __restrict__ src, double* __restrict__ dst, int n, double scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = scale * src[i];
+}
+int launch_scale_store_column(ilm_plan* p, const double* src, double* dst, int n, double scale) {
+    if (n == 0) return ILM_OK;
+    k_scale_store<<<(n + 127) / 128, 128, 0, p->stream>>>(src, dst, n, scale);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// ------------------------------------------------------------------ regularize
+__global__ void k_regularize(int ncell, int W2, const int* __restrict__ cell_idx, const int* __restrict__ cell_off,
+                             const int* __restrict__ ent, const double* __restrict__ wR,
+                             const double* __restrict__ f, const double* __restrict__ mul, double sign,
+                             double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    double sum = 0.0;
+    const int q1 = cell_off[c + 1];
+    for (int q = cell_off[c]; q < q1; ++q) {
+        const int id = ent[q];
+        const int k = id / W2;
+        double v = f[k];
+        if (mul) v = __dmul_rn(mul[k], v);
+        v = sign < 0 ? -v : v;
+        sum = __dadd_rn(sum, __dmul_rn(wR[id], v));
+    }
+    out[cell_idx[c]] = sum;
+}
+
+int launch_regularize(ilm_plan* p, const DevTable& t, const double* f, const double* mul, double sign, double* out,
+                      bool zero) {
+    if (zero) ILM_TRY(launch_fill(p, out, (size_t)t.mx * t.my, 0.0));
+    if (t.ncell == 0) return ILM_OK;
+    k_regularize<<<(t.ncell + 127) / 128, 128, 0, p->stream>>>(t.ncell, t.W * t.W, t.cell_idx, t.cell_off, t.ent,
+                                                               t.wR, f, mul, sign, out);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+__global__ void k_rowsum(int ncell, const int* __restrict__ cell_off, const int* __restrict__ ent,
+                         const double* __restrict__ wR, double* __restrict__ rowsum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    double sum = 0.0;
+    for (int q = cell_off[c]; q < cell_off[c + 1]; ++q) sum += wR[ent[q]];
+    rowsum[c] = sum == 0.0 ? 1.0 : sum;
+}
+int launch_filter_rowsum(ilm_plan* p, DevTable& t) {
+    if (t.ncell == 0) return ILM_OK;
+    k_rowsum<<<(t.ncell + 127) / 128, 128, 0, p->stream>>>(t.ncell, t.cell_off, t.ent, t.wR, t.rowsum);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// C = Etilde R, one thread per row k (rows are independent -> no atomics)
+__global__ void k_surface_filter(int N, int W, int mx, int my, const int* __restrict__ i0, const int* __restrict__ j0,
+                                 const double* __restrict__ wE, const double* __restrict__ wR, int ncell,
+                                 const int* __restrict__ cell_idx, const int* __restrict__ cell_off,
+                                 const int* __restrict__ ent, const double* __restrict__ rowsum,
+                                 double* __restrict__ C) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const int W2 = W * W;
+    for (int b = 0; b < W; ++b)
+        for (int a = 0; a < W; ++a) {
+            const int i = i0[k] + a, j = j0[k] + b;
+            if (i < 0 || i >= mx || j < 0 || j >= my) continue;
+            const int lin = i + mx * j;
+            int lo = 0, hi = ncell - 1, c = -1;
+            while (lo <= hi) {
+                const int mid = (lo + hi) >> 1;
+                const int v = cell_idx[mid];
+                if (v == lin) { c = mid; break; }
+                if (v < lin) lo = mid + 1; else hi = mid - 1;
+            }
+            if (c < 0) continue;
+            const double ef = wE[(size_t)k * W2 + b * W + a] / rowsum[c];
+            for (int q = cell_off[c]; q < cell_off[c + 1]; ++q) {
+                const int id = ent[q];
+                const int l = id / W2;
+                C[(size_t)l * N + k] += ef * wR[id];
+            }
+        }
+}
+int launch_surface_filter(ilm_plan* p, const DevTable& t, double* C) {
+    const int N = p->N;
+    ILM_TRY(launch_fill(p, C, (size_t)N * N, 0.0));
+    if (N == 0) return ILM_OK;
+    k_surface_filter<<<(N + 63) / 64, 64, 0, p->stream>>>(N, t.W, t.mx, t.my, t.i0, t.j0, t.wE, t.wR, t.ncell,
+                                                           t.cell_idx, t.cell_off, t.ent, t.rowsum, C);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// ------------------------------------------------------------------ interpolate
+struct TabView {
+    int W, mx, my;
+    const int *i0, *j0;
+    const double* wE;
+};
+__device__ __forceinline__ double gather16(const TabView& t, const double* __restrict__ field, int k, int slot,
+                                           bool live) {
+    double val = 0.0;
+    const int W2 = t.W * t.W;
+    if (live && slot < W2) {
+        const int a = slot % t.W, b = slot / t.W;
+        const int i = t.i0[k] + a, j = t.j0[k] + b;
+        if (i >= 0 && i < t.mx && j >= 0 && j < t.my)
+            val = __dmul_rn(t.wE[(size_t)k * W2 + slot], field[(size_t)j * t.mx + i]);
+    }
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) val += __shfl_down_sync(0xffffffffu, val, off, 16);
+    return val;
+}
+
+__global__ void k_interpolate(int N, TabView t, const double* __restrict__ field, double* __restrict__ f) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = gid >> 4, slot = gid & 15;
+    const double v = gather16(t, field, k, slot, k < N);
+    if (slot == 0 && k < N) f[k] = v;
+}
+
+static TabView view(const DevTable& t) { return TabView{t.W, t.mx, t.my, t.i0, t.j0, t.wE}; }
+
+int launch_interpolate(ilm_plan* p, const DevTable& t, const double* field, double* f) {
+    if (p->N == 0) return ILM_OK;
+    const int threads = p->N * 16;
+    k_interpolate<<<(threads + 127) / 128, 128, 0, p->stream>>>(p->N, view(t), field, f);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+__global__ void k_normal_interpolate(int N, TabView tu, TabView tv, const double* __restrict__ u,
+                                     const double* __restrict__ v, const double* __restrict__ nx,
+                                     const double* __restrict__ ny, int mode, double div, double* __restrict__ f) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = gid >> 4, slot = gid & 15;
+    const double su = gather16(tu, u, k, slot, k < N);
+    const double sv = gather16(tv, v, k, slot, k < N);
+    if (slot == 0 && k < N) {
+        double r;
+        if (mode == ILM_NORMAL) r = __dadd_rn(__dmul_rn(nx[k], su), __dmul_rn(ny[k], sv));
+        else r = __dsub_rn(__dmul_rn(nx[k], sv), __dmul_rn(ny[k], su));
+        f[k] = r / div;
+    }
+}
+
+int launch_normal_interpolate(ilm_plan* p, int mode, const double* u, const double* v, double* f, double div) {
+    if (p->N == 0) return ILM_OK;
+    const int threads = p->N * 16;
+    k_normal_interpolate<<<(threads + 127) / 128, 128, 0, p->stream>>>(p->N, view(p->tab[ILM_XEDGES]),
+                                                                       view(p->tab[ILM_YEDGES]), u, v, p->nx, p->ny,
+                                                                       mode, div, f);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// ------------------------------------------------------------------ stencils
+// thread = one x, ROWS consecutive y; grid covers the NX x NY superset.
+constexpr int ST_BX = 128, ST_ROWS = 8;
+static dim3 st_grid(int NX, int NY) { return dim3((NX + ST_BX - 1) / ST_BX, (NY + ST_ROWS - 1) / ST_ROWS); }
+
+// p[x,y] = -u[x,y] + u[x+1,y] - v[x,y] + v[x,y+1]          (A.3)
+__global__ void k_divergence(int NX, int NY, const double* __restrict__ u, const double* __restrict__ v,
+                             double* __restrict__ out, double div) {
+    const int x = blockIdx.x * ST_BX + threadIdx.x;
+    const int y0 = blockIdx.y * ST_ROWS;
+    if (x >= NX - 1) return;
+    const int mxv = NX - 1;
+    double vprev = (y0 < NY) ? v[(size_t)y0 * mxv + x] : 0.0;
+#pragma unroll
+    for (int r = 0; r < ST_ROWS; ++r) {
+        const int y = y0 + r;
+        if (y >= NY - 1) break;
+        const double vn = v[(size_t)(y + 1) * mxv + x];
+        const double ul = u[(size_t)y * NX + x], ur = u[(size_t)y * NX + x + 1];
+        out[(size_t)y * mxv + x] = (((-ul + ur) - vprev) + vn) / div;
+        vprev = vn;
+    }
+}
+int launch_divergence(ilm_plan* p, const double* u, const double* v, double* out, double div) {
+    k_divergence<<<st_grid(p->g.NX, p->g.NY), ST_BX, 0, p->stream>>>(p->g.NX, p->g.NY, u, v, out, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// u[x,y] = p[x,y]-p[x-1,y] (x in 2:NX-1), v[x,y] = p[x,y]-p[x,y-1] (y in 2:NY-1), zero elsewhere
+__global__ void k_grad(int NX, int NY, const double* __restrict__ pn, double* __restrict__ u, double* __restrict__ v,
+                       double div) {
+    const int x = blockIdx.x * ST_BX + threadIdx.x;
+    const int y0 = blockIdx.y * ST_ROWS;
+    if (x >= NX) return;
+    const int mp = NX - 1;
+    double pprev = (y0 >= 1 && y0 - 1 < NY - 1 && x < mp) ? pn[(size_t)(y0 - 1) * mp + x] : 0.0;
+#pragma unroll
+    for (int r = 0; r < ST_ROWS; ++r) {
+        const int y = y0 + r;
+        if (y >= NY) break;
+        const bool prow = y < NY - 1;
+        const double pc = (prow && x < mp) ? pn[(size_t)y * mp + x] : 0.0;
+        if (prow) {   // u row
+            double val = 0.0;
+            if (x >= 1 && x <= NX - 2) val = (pc - pn[(size_t)y * mp + x - 1]) / div;
+            u[(size_t)y * NX + x] = val;
+        }
+        if (x < mp) {  // v row
+            double val = 0.0;
+            if (y >= 1 && y <= NY - 2) val = (pc - pprev) / div;
+            v[(size_t)y * mp + x] = val;
+        }
+        pprev = pc;
+    }
+}
+int launch_grad(ilm_plan* p, const double* in, double* u, double* v, double div) {
+    k_grad<<<st_grid(p->g.NX, p->g.NY), ST_BX, 0, p->stream>>>(p->g.NX, p->g.NY, in, u, v, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// u[x,y] = s[x,y+1]-s[x,y] ; v[x,y] = s[x,y]-s[x+1,y]
+__global__ void k_curl_n2e(int NX, int NY, const double* __restrict__ s, double* __restrict__ u,
+                           double* __restrict__ v, double div) {
+    const int x = blockIdx.x * ST_BX + threadIdx.x;
+    const int y0 = blockIdx.y * ST_ROWS;
+    if (x >= NX) return;
+    const int mxv = NX - 1;
+    double sc = (y0 < NY) ? s[(size_t)y0 * NX + x] : 0.0;
+#pragma unroll
+    for (int r = 0; r < ST_ROWS; ++r) {
+        const int y = y0 + r;
+        if (y >= NY) break;
+        if (x < mxv) v[(size_t)y * mxv + x] = (sc - s[(size_t)y * NX + x + 1]) / div;
+        if (y < NY - 1) {
+            const double sn = s[(size_t)(y + 1) * NX + x];
+            u[(size_t)y * NX + x] = (sn - sc) / div;
+            sc = sn;
+        }
+    }
+}
+int launch_curl_n2e(ilm_plan* p, const double* s, double* u, double* v, double div) {
+    k_curl_n2e<<<st_grid(p->g.NX, p->g.NY), ST_BX, 0, p->stream>>>(p->g.NX, p->g.NY, s, u, v, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// w[x,y] = u[x,y-1]-u[x,y]-v[x-1,y]+v[x,y], x in 2:NX-1, y in 2:NY-1, zero elsewhere
+__global__ void k_curl_e2n(int NX, int NY, const double* __restrict__ u, const double* __restrict__ v,
+                           double* __restrict__ w, double div) {
+    const int x = blockIdx.x * ST_BX + threadIdx.x;
+    const int y0 = blockIdx.y * ST_ROWS;
+    if (x >= NX) return;
+    const int mxv = NX - 1;
+    double uprev = (y0 >= 1 && y0 - 1 < NY - 1) ? u[(size_t)(y0 - 1) * NX + x] : 0.0;
+#pragma unroll
+    for (int r = 0; r < ST_ROWS; ++r) {
+        const int y = y0 + r;
+        if (y >= NY) break;
+        const double uc = (y < NY - 1) ? u[(size_t)y * NX + x] : 0.0;
+        double val = 0.0;
+        if (x >= 1 && x <= NX - 2 && y >= 1 && y <= NY - 2)
+            val = (((uprev - uc) - v[(size_t)y * mxv + x - 1]) + v[(size_t)y * mxv + x]) / div;
+        w[(size_t)y * NX + x] = val;
+        uprev = uc;
+    }
+}
+int launch_curl_e2n(ilm_plan* p, const double* u, const double* v, double* w, double div) {
+    k_curl_e2n<<<st_grid(p->g.NX, p->g.NY), ST_BX, 0, p->stream>>>(p->g.NX, p->g.NY, u, v, w, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// 5-point Laplacian times factor on the interior of an mx x my field, zero on its border
+__global__ void k_laplacian(int mx, int my, const double* __restrict__ in, double* __restrict__ out, double factor) {
+    const int x = blockIdx.x * ST_BX + threadIdx.x;
+    const int y0 = blockIdx.y * ST_ROWS;
+    if (x >= mx) return;
+    double below = (y0 >= 1) ? in[(size_t)(y0 - 1) * mx + x] : 0.0;
+    double cur = (y0 < my) ? in[(size_t)y0 * mx + x] : 0.0;
+#pragma unroll
+    for (int r = 0; r < ST_ROWS; ++r) {
+        const int y = y0 + r;
+        if (y >= my) break;
+        const double above = (y + 1 < my) ? in[(size_t)(y + 1) * mx + x] : 0.0;
+        double val = 0.0;
+        if (x >= 1 && x <= mx - 2 && y >= 1 && y <= my - 2) {
+            const double l = in[(size_t)y * mx + x - 1], rr = in[(size_t)y * mx + x + 1];
+            val = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(-4.0, cur), l), rr), below), above), factor);
+        }
+        out[(size_t)y * mx + x] = val;
+        below = cur;
+        cur = above;
+    }
+}
+int launch_laplacian(ilm_plan* p, const double* in, double* out, int mx, int my, double factor) {
+    k_laplacian<<<st_grid(mx, my), ST_BX, 0, p->stream>>>(mx, my, in, out, factor);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// ------------------------------------------------------------------ LGF multiplier source
+// h[i,j] = eps_i eps_j (G[i,j] - c0), eps_0 = 1, eps_{>0} = 2   (see ilm_conv.cuh)
+__global__ void k_lgf_prep(const double* __restrict__ table, int ld, int NX, int NY, double c0,
+                           double* __restrict__ h) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= NX || j >= NY) return;
+    const double e = (i ? 2.0 : 1.0) * (j ? 2.0 : 1.0);
+    h[(size_t)j * NX + i] = e * (table[(size_t)j * ld + i] - c0);
+}
+int launch_lgf_prep(ilm_plan* p, const double* table, int ld, int NX, int NY, double c0, double* h) {
+    k_lgf_prep<<<dim3((NX + 127) / 128, NY), 128, 0, p->stream>>>(table, ld, NX, NY, c0, h);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+}  // namespace ilm

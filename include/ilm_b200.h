@@ -1,0 +1,164 @@
+/* ilm_b200.h -- C ABI of libilm_b200.so, the B200 (sm_100a) implementation of
+ * the ImmersedLayers.jl immersed-layer operator hot path.
+ *
+ * The reference (JuliaIBPM/ImmersedLayers.jl v0.5.6) has no FFI: its seam is
+ * Julia dispatch on `BasicILMCache` (src/cache.jl:16-88).  Each entry point
+ * below names the reference method whose body a Julia `ccall` shim replaces
+ * (see INTEGRATION.md).  Conventions:
+ *   - all arrays are fp64, column-major with x (first index) fastest, exactly
+ *     the memory layout of CartesianGrids' Nodes/Edges/ScalarData/VectorData;
+ *     Edges = [vec(u); vec(v)], VectorData = [u; v];
+ *   - every data pointer may be a device pointer (zero-copy, asynchronous on
+ *     the plan's stream) or a host pointer (staged H2D/D2H inside the call,
+ *     the call returns after the result is in host memory);
+ *   - a plan is bound to one CUDA stream and is not re-entrant (the
+ *     reference's caches are shared mutable scratch, src/matrix_operators.jl:10-25);
+ *   - functions return ILM_OK or an error code; ilm_last_error() gives text.
+ *     The Julia shim maps ILM_ESIZE -> DimensionMismatch/AssertionError and
+ *     ILM_EINVAL -> ArgumentError/MethodError (test/tools.jl:34-35,86).
+ * There is no CPU fallback: without a CUDA device ilm_plan_create fails with
+ * ILM_ECUDA.
+ */
+#ifndef ILM_B200_H
+#define ILM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ilm_plan ilm_plan;
+
+enum ilm_status { ILM_OK = 0, ILM_EINVAL = 1, ILM_ESIZE = 2, ILM_ECUDA = 3, ILM_ENCCL = 4, ILM_ENOMEM = 5 };
+
+/* CartesianGrids DDF types listed at src/cache.jl:305 (Goza is not provided) */
+enum ilm_ddf { ILM_DDF_YANG3 = 0, ILM_DDF_M3 = 1, ILM_DDF_ROMA = 2, ILM_DDF_M4PRIME = 3, ILM_DDF_WITCHHAT = 4 };
+/* GridScaling / IndexScaling (src/ImmersedLayers.jl:81, src/cache.jl:305-324) */
+enum ilm_scaling { ILM_GRID_SCALING = 0, ILM_INDEX_SCALING = 1 };
+/* staggered layouts */
+enum ilm_layout {
+    ILM_NODES_PRIMAL = 0, /* (NX-1) x (NY-1) at (i, j)         */
+    ILM_NODES_DUAL = 1,   /* NX x NY         at (i-1/2, j-1/2) */
+    ILM_XEDGES = 2,       /* Edges{Primal}.u NX x (NY-1) at (i-1/2, j) */
+    ILM_YEDGES = 3,       /* Edges{Primal}.v (NX-1) x NY at (i, j-1/2) */
+    ILM_EDGES = 4         /* [u; v] */
+};
+/* pointwise normal products fused into regularize / interpolate
+ * (src/surface_operators.jl:98-343) */
+enum ilm_normal_mode {
+    ILM_NORMAL = 0, /* product!(V,n,f) / pointwise_dot!(f,n,V)                  */
+    ILM_CROSS = 1   /* pointwise_cross!: V.u = n.v f, V.v = -n.u f / n.u V.v - n.v V.u */
+};
+/* Schur-complement builders of src/matrix_operators.jl */
+enum ilm_schur {
+    ILM_RTLINVR = 0,     /* create_RTLinvR      :9-30    */
+    ILM_CLINVCT = 1,     /* create_CLinvCT      :40-61   */
+    ILM_GLINVD = 2,      /* create_GLinvD       :135-155 */
+    ILM_GLINVD_CROSS = 3 /* create_GLinvD_cross :195-215 */
+};
+
+/* PhysicalGrid as data: size(g), cellsize(g), origin(g) */
+typedef struct {
+    int NX, NY;   /* dual cells incl. ghosts */
+    double dx;
+    int I0x, I0y; /* 1-based index of the primal node at the physical origin */
+} ilm_grid;
+
+/* ---- plan = BasicILMCache -------------------------------------------------
+ * ilm_plan_create replaces SurfaceScalarCache(...) -> _surfacecache,
+ * _get_regularization, _get_laplacian (src/cache.jl:164-182, 232-261, 305-324):
+ * scaled point coordinates, DDF window tables for the primal-node, dual-node,
+ * u-edge and v-edge layouts, their cell-bucketed gather lists, the LGF
+ * multiplier Ghat and all scratch fields, resident in HBM.
+ *   x,y,nx,ny,ds : N surface points, unit normals, arc weights (host pointers)
+ *   lgf          : nlgf x nlgf table G(i,j), column-major, nlgf >= max(NX,NY)
+ *                  (CartesianGrids' LGF_TABLE or lgf.lgf_table(); host pointer)
+ *   c0           : far-field constant subtracted by `L\w`
+ *   lap_factor   : L.factor (1/dx^2 for GridScaling, src/cache.jl:323-324)
+ *   stream       : cudaStream_t or NULL (default stream)                     */
+int ilm_plan_create(const ilm_grid* grid, int N, const double* x, const double* y, const double* nx,
+                    const double* ny, const double* ds, int ddf, int scaling, const double* lgf, int nlgf,
+                    double c0, double lap_factor, void* stream, ilm_plan** plan);
+/* update_system (src/system.jl:26-50): new body positions, Ghat is kept */
+int ilm_plan_update_points(ilm_plan* plan, int N, const double* x, const double* y, const double* nx,
+                           const double* ny, const double* ds);
+void ilm_plan_destroy(ilm_plan* plan);
+int ilm_plan_sync(ilm_plan* plan);
+const char* ilm_last_error(void);
+int ilm_plan_npoints(const ilm_plan* plan);
+/* number of elements of a layout on this plan's grid */
+int64_t ilm_layout_size(const ilm_plan* plan, int layout);
+/* kernels of this library launched on the plan so far (bench bookkeeping) */
+int64_t ilm_plan_launch_count(const ilm_plan* plan);
+
+/* DDF table inspection (bit-exact parity tests).  W*W entries per point in
+ * [k][b][a] order (a = x offset fastest); idx = 0-based column-major linear
+ * index or -1 if the entry lies outside the field. */
+int ilm_get_table(ilm_plan* plan, int layout, int* W, int64_t* idx, double* wR, double* wE);
+
+/* ---- regularize! / interpolate! (src/surface_operators.jl:13-88) ---------- */
+int ilm_regularize(ilm_plan* plan, int layout, const double* f, double* grid);
+int ilm_interpolate(ilm_plan* plan, int layout, const double* grid, double* f);
+/* regularize_normal!, regularize_normal_cross! (:98-103, :150-162) : Edges <- ScalarData */
+int ilm_regularize_normal(ilm_plan* plan, int mode, const double* f, double* edges);
+/* normal_interpolate!, normal_cross_interpolate! (:228-233, :270-291) : ScalarData <- Edges */
+int ilm_normal_interpolate(ilm_plan* plan, int mode, const double* edges, double* f);
+
+/* ---- staggered stencils with scaling (src/grid_operators.jl:25-134) ------- */
+int ilm_divergence(ilm_plan* plan, const double* edges, double* nodes_primal);
+int ilm_grad(ilm_plan* plan, const double* nodes_primal, double* edges);
+int ilm_curl_n2e(ilm_plan* plan, const double* nodes_dual, double* edges);
+int ilm_curl_e2n(ilm_plan* plan, const double* edges, double* nodes_dual);
+int ilm_laplacian(ilm_plan* plan, int layout, const double* in, double* out);
+
+/* ---- inverse_laplacian! (src/grid_operators.jl:153-179) -------------------
+ * in place: w <- (G * w - c0 sum(w)) / L.factor on the layout's own index box.
+ * ILM_EDGES solves u and v together (one complex transform).                */
+int ilm_inverse_laplacian(ilm_plan* plan, int layout, double* w);
+/* two independent fields of the given layouts in one complex transform */
+int ilm_inverse_laplacian_pair(ilm_plan* plan, int layout1, double* w1, int layout2, double* w2);
+/* extra convolution kernels on the same engine: exp(L,a) -> plan_intfact
+ * (src/timemarching.jl:93,104 via ConstrainedSystems).  table: n x n, kernel id
+ * returned in *id (id 0 is the inverse Laplacian). */
+int ilm_add_kernel(ilm_plan* plan, const double* table, int n, double c0, double factor, int* id);
+int ilm_convolve(ilm_plan* plan, int kernel_id, int layout, double* w);
+
+/* ---- composite surface-grid operators (src/surface_operators.jl:357-725) -- */
+int ilm_surface_divergence(ilm_plan* plan, int mode, const double* f, double* nodes_primal);
+int ilm_surface_grad(ilm_plan* plan, int mode, const double* nodes_primal, double* f);
+int ilm_surface_curl_s2n(ilm_plan* plan, int mode, const double* f, double* nodes_dual);
+int ilm_surface_curl_n2s(ilm_plan* plan, int mode, const double* nodes_dual, double* f);
+/* _get_mask! (src/surface_operators.jl:865-876): mask = -L^-1 D_s 1 on primal nodes */
+int ilm_mask(ilm_plan* plan, double* nodes_primal);
+
+/* ---- Schur-complement builders (src/matrix_operators.jl) ------------------
+ * Columns [col_begin, col_end) of the N x N matrix, written column-major with
+ * leading dimension N into A (N x (col_end-col_begin)).  Column ranges are the
+ * multi-GPU shard.                                                          */
+int ilm_create_schur(ilm_plan* plan, int which, double scale, int col_begin, int col_end, double* A);
+int ilm_create_nRTRn(ilm_plan* plan, double scale, double* A);   /* :225-244 */
+int ilm_create_surface_filter(ilm_plan* plan, double* C);        /* :254-268 */
+
+/* ---- surface-point solve (user level: test/literate/dirichlet.jl:99,124) --
+ * LU with partial pivoting (LAPACK getrf/getrs semantics, ipiv 1-based),
+ * dense mat-vec power s <- C^k s.  `stream` as in ilm_plan_create.           */
+int ilm_dense_factor(int n, double* A, int* ipiv, void* stream);
+int ilm_dense_solve(int n, const double* LU, const int* ipiv, int nrhs, double* B, void* stream);
+int ilm_dense_matvec_pow(int n, const double* C, int k, double* s, void* stream);
+
+/* kernels launched by the three ilm_dense_* entry points since load (bench bookkeeping) */
+int64_t ilm_dense_launch_count(void);
+
+/* ---- measurement hook ------------------------------------------------------
+ * Times each pass of the convolution (A: rows forward, B: columns, C: rows
+ * inverse) on the plan's stream with CUDA events: `reps` back-to-back launches
+ * per pass on a two-field (complex) problem of the given layout; ms[i] is the
+ * average launch duration of pass i.  The spectrum buffers (hundreds of MB at
+ * 4096^2) exceed the L2, so no flush is needed between launches.            */
+int ilm_profile_conv(ilm_plan* plan, int layout, int reps, double ms[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ILM_B200_H */

@@ -1,0 +1,410 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on
+identical seeded inputs.  Bit-exact for index/weight tables, regularization
+and the difference stencils; 1e-12 (norm-wise, relative to the field's max
+magnitude -- SURVEY.md section 7 "hard parts") for every floating-point field
+that goes through a reduction tree or the FFT."""
+import numpy as np
+import pytest
+
+import ilm_b200 as ilm
+import ilm_oracle as o
+from ilm_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+KIND = {L.NODES_PRIMAL: o.PRIMAL, L.NODES_DUAL: o.DUAL, L.XEDGES: o.XEDGE, L.YEDGES: o.YEDGE}
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    d = np.abs(a - b).max() if a.size else 0.0
+    s = np.abs(b).max() if b.size else 1.0
+    return d / (s if s > 0 else 1.0)
+
+
+def make_case(NX, NY, dx, I0, body, ddf="yang3", scaling=ilm.GridScaling, device=False, lgf_rule="accurate"):
+    g = ilm.PhysicalGrid(NX, NY, dx, I0)
+    G = ilm.lgf.lgf_table(max(NX, NY), rule=lgf_rule)
+    cache = ilm.SurfaceScalarCache(body, g, scaling=scaling, ddftype=ddf, lgf_table=G, device=device)
+    og = o.Grid(NX, NY, dx, I0)
+    oc = o.ScalarCache(og, *body[:5], G, ddf=ddf, scaling=o.GRID_SCALING if scaling == ilm.GridScaling else o.INDEX_SCALING)
+    return cache, oc
+
+
+@pytest.fixture(scope="module")
+def c1():
+    """BASELINE config C1: Dirichlet Poisson on a circle, 128x128, Yang3."""
+    g = ilm.PhysicalGrid.centered(128)
+    body = ilm.bodies.circle(1.0, 1.4 * g.dx)
+    return make_case(g.NX, g.NY, g.dx, g.I0, body)
+
+
+@pytest.fixture(scope="module")
+def odd():
+    """Non-square, odd-sized grid with an off-centre ellipse (ragged rows, misaligned layouts)."""
+    body = ilm.bodies.ellipse(0.9, 0.45, 0.07, center=(0.13, -0.21))
+    return make_case(91, 67, 0.05, (44, 35), body)
+
+
+# ---------------------------------------------------------------- tables
+@pytest.mark.parametrize("ddf", ["yang3", "m3", "roma", "m4prime", "witchhat"])
+@pytest.mark.parametrize("scaling", [ilm.GridScaling, ilm.IndexScaling])
+def test_tables_bit_exact(ddf, scaling):
+    body = ilm.bodies.ellipse(0.9, 0.45, 0.07, center=(0.13, -0.21))
+    cache, oc = make_case(91, 67, 0.05, (44, 35), body, ddf=ddf, scaling=scaling)
+    for layout, kind in KIND.items():
+        idx, wR, wE = cache.table(layout)
+        tab = oc.tabs[kind]
+        lin = np.transpose(tab.linear_index(), (0, 2, 1))        # oracle [k][a][b] -> [k][b][a]
+        assert np.array_equal(idx, lin)
+        assert np.array_equal(wR, np.transpose(tab.wR, (0, 2, 1)))
+        assert np.array_equal(wE, np.transpose(tab.wE, (0, 2, 1)))
+
+
+def test_tables_clipped_at_boundary():
+    """Points next to the grid edge: window entries outside the field are dropped."""
+    g = ilm.PhysicalGrid(40, 36, 0.1, (3, 4))
+    body = ilm.bodies.circle(0.25, 0.14)
+    cache, oc = make_case(g.NX, g.NY, g.dx, g.I0, body)
+    for layout, kind in KIND.items():
+        idx, wR, wE = cache.table(layout)
+        lin = np.transpose(oc.tabs[kind].linear_index(), (0, 2, 1))
+        assert (lin < 0).any()
+        assert np.array_equal(idx, lin)
+        assert np.array_equal(wR, np.transpose(oc.tabs[kind].wR, (0, 2, 1)))
+    f = np.random.default_rng(0).standard_normal(cache.N)
+    s = cache.zeros_grid()
+    ilm.regularize(s, ilm.ScalarData(cache.N, data=f), cache)
+    assert np.array_equal(s.array(), oc.regularize(f))
+
+
+# ---------------------------------------------------------------- regularize / interpolate
+@pytest.mark.parametrize("case", ["c1", "odd"])
+def test_regularize_interpolate(case, request):
+    cache, oc = request.getfixturevalue(case)
+    rng = np.random.default_rng(1)
+    f = rng.standard_normal(cache.N)
+    fd = ilm.ScalarData(cache.N, data=f.copy())
+    for celltype, kind in ((ilm.Primal, o.PRIMAL), (ilm.Dual, o.DUAL)):
+        s = ilm.Nodes(celltype, cache.g)
+        ilm.regularize(s, fd, cache)
+        ref = o.regularize(oc.tabs[kind], f)
+        assert np.array_equal(s.array(), ref)                       # deterministic gather: bit-exact
+        w = rng.standard_normal(ref.shape)
+        sw = ilm.Nodes(celltype, cache.g).set(w)
+        out = cache.zeros_surface()
+        ilm.interpolate(out, sw, cache)
+        assert relerr(out.data, o.interpolate(oc.tabs[kind], w)) < RTOL
+    # Edges <-> VectorData
+    fv = rng.standard_normal(2 * cache.N)
+    q = cache.zeros_gridgrad()
+    ilm.regularize(q, ilm.VectorData(cache.N, data=fv.copy()), cache)
+    ru, rv = oc.regularize_edges(fv[:cache.N], fv[cache.N:])
+    assert np.array_equal(q.u, ru) and np.array_equal(q.v, rv)
+    q.set(np.concatenate([rng.standard_normal(ru.shape).ravel(order="F"), rng.standard_normal(rv.shape).ravel(order="F")]))
+    vb = cache.zeros_surfacevec()
+    ilm.interpolate(vb, q, cache)
+    su, sv = oc.interpolate_edges(q.u, q.v)
+    assert relerr(vb.u, su) < RTOL and relerr(vb.v, sv) < RTOL
+
+
+@pytest.mark.parametrize("case", ["c1", "odd"])
+def test_normal_variants(case, request):
+    cache, oc = request.getfixturevalue(case)
+    rng = np.random.default_rng(2)
+    f = rng.standard_normal(cache.N)
+    fd = ilm.ScalarData(cache.N, data=f.copy())
+    q = cache.zeros_gridgrad()
+    ilm.regularize_normal(q, fd, cache)
+    ru, rv = oc.regularize_normal(f)
+    assert np.array_equal(q.u, ru) and np.array_equal(q.v, rv)
+    ilm.regularize_normal_cross(q, fd, cache)
+    cu, cv = oc.regularize_normal_cross(f)
+    assert np.array_equal(q.u, cu) and np.array_equal(q.v, cv)
+    u = rng.standard_normal(ru.shape)
+    v = rng.standard_normal(rv.shape)
+    q.set(np.concatenate([u.ravel(order="F"), v.ravel(order="F")]))
+    vn = cache.zeros_surface()
+    ilm.normal_interpolate(vn, q, cache)
+    assert relerr(vn.data, oc.normal_interpolate(u, v)) < RTOL
+    ilm.normal_cross_interpolate(vn, q, cache)
+    assert relerr(vn.data, oc.normal_cross_interpolate(u, v)) < RTOL
+
+
+# ---------------------------------------------------------------- stencils
+@pytest.mark.parametrize("case", ["c1", "odd"])
+def test_stencils_bit_exact(case, request):
+    cache, oc = request.getfixturevalue(case)
+    g, og = cache.g, oc.grid
+    rng = np.random.default_rng(3)
+    u = rng.standard_normal(g.layout_shape(L.XEDGES))
+    v = rng.standard_normal(g.layout_shape(L.YEDGES))
+    p = rng.standard_normal(g.layout_shape(L.NODES_PRIMAL))
+    s = rng.standard_normal(g.layout_shape(L.NODES_DUAL))
+    q = ilm.Edges(g).set(np.concatenate([u.ravel(order="F"), v.ravel(order="F")]))
+    pn = ilm.Nodes(ilm.Primal, g).set(p)
+    sn = ilm.Nodes(ilm.Dual, g).set(s)
+    out_p = ilm.Nodes(ilm.Primal, g).fill(7.0)        # outputs are fully overwritten
+    ilm.divergence(out_p, q, cache)
+    assert np.array_equal(out_p.array(), oc.divergence(u, v))
+    out_q = ilm.Edges(g).fill(7.0)
+    ilm.grad(out_q, pn, cache)
+    gu, gv = oc.grad(p)
+    assert np.array_equal(out_q.u, gu) and np.array_equal(out_q.v, gv)
+    ilm.curl(out_q, sn, cache)
+    cu, cv = oc.curl_n2e(s)
+    assert np.array_equal(out_q.u, cu) and np.array_equal(out_q.v, cv)
+    out_s = ilm.Nodes(ilm.Dual, g).fill(7.0)
+    ilm.curl(out_s, q, cache)
+    assert np.array_equal(out_s.array(), oc.curl_e2n(u, v))
+    ilm.laplacian(out_s, sn, cache)
+    assert np.array_equal(out_s.array(), oc.laplacian(s, o.DUAL))
+    ilm.laplacian(out_p, pn, cache)
+    assert np.array_equal(out_p.array(), oc.laplacian(p, o.PRIMAL))
+    ilm.laplacian(out_q, q, cache)
+    assert np.array_equal(out_q.u, oc.laplacian(u, o.XEDGE)) and np.array_equal(out_q.v, oc.laplacian(v, o.YEDGE))
+
+
+# ---------------------------------------------------------------- inverse Laplacian
+@pytest.mark.parametrize("case", ["c1", "odd"])
+def test_inverse_laplacian(case, request):
+    cache, oc = request.getfixturevalue(case)
+    g = cache.g
+    rng = np.random.default_rng(4)
+    for celltype, kind in ((ilm.Primal, o.PRIMAL), (ilm.Dual, o.DUAL)):
+        w = rng.standard_normal(g.layout_shape(L.NODES_PRIMAL if celltype == ilm.Primal else L.NODES_DUAL))
+        wn = ilm.Nodes(celltype, g).set(w)
+        ilm.inverse_laplacian(wn, cache)
+        assert relerr(wn.array(), oc.inverse_laplacian(w)) < RTOL
+    u = rng.standard_normal(g.layout_shape(L.XEDGES))
+    v = rng.standard_normal(g.layout_shape(L.YEDGES))
+    q = ilm.Edges(g).set(np.concatenate([u.ravel(order="F"), v.ravel(order="F")]))
+    ilm.inverse_laplacian(q, cache)        # u and v ride one complex transform
+    assert relerr(q.u, oc.inverse_laplacian(u)) < RTOL and relerr(q.v, oc.inverse_laplacian(v)) < RTOL
+    z = ilm.Nodes(ilm.Primal, g)
+    ilm.inverse_laplacian(z, cache)        # iszero short-circuit of the reference: zeros stay zeros
+    assert not np.any(z.array())
+
+
+def test_inverse_laplacian_unit_impulses(c1):
+    """A unit impulse returns the LGF table itself: (G - c0)/factor."""
+    cache, oc = c1
+    g = cache.g
+    w = np.zeros(g.layout_shape(L.NODES_DUAL))
+    w[5, 9] = 1.0
+    wn = ilm.Nodes(ilm.Dual, g).set(w)
+    ilm.inverse_laplacian(wn, cache)
+    ii = np.abs(np.arange(g.NX) - 5)
+    jj = np.abs(np.arange(g.NY) - 9)
+    ref = (oc.lgf[np.ix_(ii, jj)] - oc.c0) / oc.factor
+    assert relerr(wn.array(), ref) < RTOL
+
+
+def test_intfact_kernel(c1):
+    """plan_intfact on the same engine: E_a convolution, a = 0.5."""
+    cache, oc = c1
+    g = cache.g
+    E = ilm.lgf.intfact_table(0.5, g.NX)
+    kid = cache.add_kernel(E)
+    assert kid == 1
+    w = np.random.default_rng(5).standard_normal(g.layout_shape(L.NODES_DUAL))
+    wn = ilm.Nodes(ilm.Dual, g).set(w)
+    L.check(cache._lib.ilm_convolve(cache._plan, kid, L.NODES_DUAL, wn.data.ctypes.data))
+    ref = o.ConvPlan(E[:g.NX, :g.NY]).apply(w)
+    assert relerr(wn.array(), ref) < RTOL
+    # a = 0 is the identity
+    kid0 = cache.add_kernel(ilm.lgf.intfact_table(0.0, g.NX))
+    wn.set(w)
+    L.check(cache._lib.ilm_convolve(cache._plan, kid0, L.NODES_DUAL, wn.data.ctypes.data))
+    assert relerr(wn.array(), w) < RTOL
+
+
+# ---------------------------------------------------------------- composites, mask
+@pytest.mark.parametrize("case", ["c1", "odd"])
+def test_surface_grid_composites(case, request):
+    cache, oc = request.getfixturevalue(case)
+    g = cache.g
+    rng = np.random.default_rng(6)
+    f = rng.standard_normal(cache.N)
+    fd = ilm.ScalarData(cache.N, data=f.copy())
+    th = cache.zeros_grid()
+    ilm.surface_divergence(th, fd, cache)
+    assert np.array_equal(th.array(), oc.surface_divergence(f))
+    ilm.surface_divergence_cross(th, fd, cache)
+    assert np.array_equal(th.array(), oc.surface_divergence_cross(f))
+    w = cache.zeros_gridcurl()
+    ilm.surface_curl(w, fd, cache)
+    assert np.array_equal(w.array(), oc.surface_curl_s2n(f))
+    ilm.surface_curl_cross(w, fd, cache)
+    assert np.array_equal(w.array(), oc.surface_curl_cross_s2n(f))
+    phi = rng.standard_normal(g.layout_shape(L.NODES_PRIMAL))
+    psi = rng.standard_normal(g.layout_shape(L.NODES_DUAL))
+    vn = cache.zeros_surface()
+    ilm.surface_grad(vn, ilm.Nodes(ilm.Primal, g).set(phi), cache)
+    assert relerr(vn.data, oc.surface_grad(phi)) < RTOL
+    ilm.surface_grad_cross(vn, ilm.Nodes(ilm.Primal, g).set(phi), cache)
+    assert relerr(vn.data, oc.surface_grad_cross(phi)) < RTOL
+    ilm.surface_curl(vn, ilm.Nodes(ilm.Dual, g).set(psi), cache)
+    assert relerr(vn.data, oc.surface_curl_n2s(psi)) < RTOL
+    ilm.surface_curl_cross(vn, ilm.Nodes(ilm.Dual, g).set(psi), cache)
+    assert relerr(vn.data, oc.surface_curl_cross_n2s(psi)) < RTOL
+
+
+def test_mask(c1):
+    cache, oc = c1
+    m = ilm.mask(cache)
+    assert relerr(m.array(), oc.mask()) < RTOL
+    cm = ilm.complementary_mask(cache)
+    assert relerr(cm.array(), 1.0 - oc.mask()) < RTOL
+
+
+# ---------------------------------------------------------------- Schur builders, dense solve
+def test_schur_matrices(c1):
+    cache, oc = c1
+    S = ilm.create_RTLinvR(cache)
+    Sref = oc.create_RTLinvR()
+    assert S.shape == Sref.shape
+    assert relerr(S, Sref) < RTOL
+    assert relerr(ilm.create_RTLinvR(cache, scale=2.5, cols=(3, 10)), 2.5 * Sref[:, 3:10]) < RTOL   # odd-sized block
+    dx = cache.g.dx
+    assert relerr(ilm.create_CLinvCT(cache, scale=dx), oc.create_CLinvCT(scale=dx)) < RTOL
+    assert relerr(ilm.create_GLinvD(cache, scale=dx), oc.create_GLinvD(scale=dx)) < RTOL
+    assert relerr(ilm.create_GLinvD_cross(cache, scale=dx, cols=(0, 16)), oc.create_GLinvD_cross(scale=dx, cols=range(16))) < RTOL
+    assert relerr(ilm.create_nRTRn(cache), oc.create_nRTRn()) < RTOL
+    assert relerr(ilm.create_surface_filter(cache), oc.create_surface_filter()) < RTOL
+
+
+def test_schur_reference_physics(c1):
+    """The reference's own checks (test/surface_ops.jl:69-77) on the GPU matrices."""
+    cache, _ = c1
+    dx = cache.g.dx
+    assert abs(np.abs(np.linalg.eigvals(ilm.create_CLinvCT(cache, scale=dx))).max() - 0.2) < 0.1
+    assert abs(np.abs(np.linalg.eigvals(ilm.create_GLinvD(cache, scale=dx))).max() - 0.45) < 0.1
+    assert abs(np.linalg.svd(ilm.create_nRTRn(cache), compute_uv=False).max() - 11) < 1.5
+
+
+@pytest.mark.parametrize("n", [1, 7, 32, 33, 141, 500])
+def test_dense_lu_solve(n):
+    import scipy.linalg
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)) + 0.1 * n * np.eye(n) * (rng.random(n) - 0.5)[:, None]
+    b = rng.standard_normal(n)
+    lu = ilm.LU(A)
+    x = lu.solve(b)
+    lu_ref, piv_ref = scipy.linalg.lu_factor(A)
+    assert np.array_equal(lu.ipiv - 1, piv_ref)                     # same pivot sequence as LAPACK
+    assert relerr(lu.lu.reshape((n, n), order="F"), lu_ref) < 1e-11
+    xref = scipy.linalg.lu_solve((lu_ref, piv_ref), b)
+    assert relerr(x, xref) < 1e-10 * max(1.0, np.linalg.cond(A) * 1e-3)
+    assert np.abs(A @ x - b).max() < 1e-10 * np.abs(b).max() * n
+
+
+def test_matvec_pow():
+    rng = np.random.default_rng(8)
+    n = 141
+    Cm = rng.standard_normal((n, n)) / n
+    s = rng.standard_normal(n)
+    out = s.copy()
+    ilm.matvec_pow(Cm, 5, out)
+    assert relerr(out, np.linalg.matrix_power(Cm, 5) @ s) < RTOL
+
+
+# ---------------------------------------------------------------- the north-star algorithm
+def test_dirichlet_poisson_c1(c1):
+    """test/literate/dirichlet.jl on config C1, GPU vs oracle, every field."""
+    cache, oc = c1
+    fplus = cache.points()[0].copy()
+    f, s, S = ilm.dirichlet_poisson(cache, fplus)
+    fr, sr, Sr = o.dirichlet_solve(oc, fplus)
+    assert relerr(S, Sr) < RTOL
+    # the multiplier s solves an ill-conditioned system: compare the residuals of
+    # both solutions in the oracle's system and the solutions up to cond(S)*eps
+    cond = np.linalg.cond(Sr)
+    assert relerr(s.data, sr) < 50 * cond * np.finfo(float).eps
+    assert relerr(f.array(), fr) < 1e-10
+    # same S (the oracle's) -> the rest of the chain matches tightly
+    f2, s2, _ = ilm.dirichlet_poisson(cache, fplus, S=Sr)
+    assert relerr(s2.data, sr) < 50 * cond * np.finfo(float).eps
+    # physics: zero inside, x/r^2 outside
+    fa = f.array()
+    i0 = cache.g.I0[0] - 1
+    assert abs(fa[i0, i0]) < 1e-2
+
+
+def test_device_resident_mode():
+    """Torch CUDA tensors in, CUDA tensors out: no host staging."""
+    import torch
+    g = ilm.PhysicalGrid.centered(64)
+    body = ilm.bodies.circle(1.0, 1.4 * g.dx)
+    cache, oc = make_case(g.NX, g.NY, g.dx, g.I0, body, device=True)
+    f = np.random.default_rng(9).standard_normal(cache.N)
+    fd = cache.zeros_surface().set(f)
+    assert fd.data.is_cuda
+    s = cache.zeros_grid()
+    ilm.regularize(s, fd, cache)
+    ilm.inverse_laplacian(s, cache)
+    out = cache.zeros_surface()
+    ilm.interpolate(out, s, cache)
+    cache.sync()
+    ref = oc.interpolate(oc.inverse_laplacian(oc.regularize(f)))
+    assert relerr(out.numpy(), ref) < RTOL
+    S = ilm.create_RTLinvR(cache)
+    assert S.is_cuda
+    assert relerr(S.cpu().numpy(), oc.create_RTLinvR()) < RTOL
+    fsol, ssol, _ = ilm.dirichlet_poisson(cache, cache.points()[0].copy(), S=S)
+    fr, sr, _ = o.dirichlet_solve(oc, oc.x.copy())
+    assert relerr(fsol.numpy().reshape(fr.shape, order="F"), fr) < 1e-10
+    assert cache.launch_count() > 0
+
+
+def test_update_points_moving_body():
+    """update_system (src/system.jl:26-50): new points, same Ghat."""
+    g = ilm.PhysicalGrid.centered(64)
+    body = ilm.bodies.circle(0.8, 1.4 * g.dx, center=(-0.3, 0.0))
+    cache, _ = make_case(g.NX, g.NY, g.dx, g.I0, body)
+    body2 = ilm.bodies.circle(0.8, 1.4 * g.dx, center=(0.25, 0.1))
+    cache.update_points(body2)
+    _, oc2 = make_case(g.NX, g.NY, g.dx, g.I0, body2)
+    idx, wR, _ = cache.table(L.NODES_PRIMAL)
+    assert np.array_equal(wR, np.transpose(oc2.tabs[o.PRIMAL].wR, (0, 2, 1)))
+    assert relerr(ilm.create_RTLinvR(cache, cols=(0, 8)), oc2.create_RTLinvR(cols=range(8))) < RTOL
+
+
+def test_zero_body_cache():
+    """test/surface_ops.jl:356-371."""
+    g = ilm.PhysicalGrid.centered(32)
+    z = np.zeros(0)
+    cache = ilm.SurfaceScalarCache((z, z, z, z, z), g)
+    s = cache.zeros_grid().fill(3.0)
+    ilm.regularize(s, cache.zeros_surface(), cache)
+    assert not np.any(s.array())
+    assert np.all(ilm.mask(cache).array() == 1.0)
+    assert ilm.create_RTLinvR(cache).shape == (0, 0)
+
+
+def test_error_behaviour(c1):
+    """MethodError on container-type mismatch, DimensionMismatch on sizes (test/tools.jl:34-35,86)."""
+    cache, _ = c1
+    with pytest.raises(ilm.MethodError):
+        ilm.regularize(cache.zeros_grid(), cache.zeros_surfacevec(), cache)
+    with pytest.raises(ilm.MethodError):
+        ilm.divergence(cache.zeros_gridcurl(), cache.zeros_gridgrad(), cache)
+    with pytest.raises(ilm.DimensionMismatch):
+        ilm.regularize(cache.zeros_grid(), ilm.ScalarData(cache.N + 1), cache)
+    with pytest.raises(ilm.DimensionMismatch):
+        ilm.create_RTLinvR(cache, cols=(0, cache.N + 1))
+    with pytest.raises(ilm.DimensionMismatch):
+        small = ilm.PhysicalGrid.centered(64)
+        ilm.interpolate(cache.zeros_surface(), ilm.Nodes(ilm.Primal, small), cache)
+    with pytest.raises(ilm.DimensionMismatch):
+        ilm.SurfaceScalarCache(ilm.bodies.circle(1.0, 0.1), ilm.PhysicalGrid.centered(64),
+                               lgf_table=ilm.lgf.lgf_table(16))
+
+
+def test_reference_lgf_rule(c1):
+    """The reference-compatible 100-node table runs through the same path."""
+    g = ilm.PhysicalGrid.centered(64)
+    body = ilm.bodies.circle(1.0, 1.4 * g.dx)
+    cache, oc = make_case(g.NX, g.NY, g.dx, g.I0, body, lgf_rule="gl100")
+    assert relerr(ilm.create_RTLinvR(cache), oc.create_RTLinvR()) < RTOL

@@ -270,3 +270,27 @@ def test_zero_body_cache():
     assert c.interpolate(g.zeros(o.PRIMAL)).shape == (0,)
     assert np.all(c.mask() == 1.0)
     assert c.create_RTLinvR().shape == (0, 0)
+
+
+def test_c_direct_convolution_matches_fft_oracle():
+    """oracle/direct_conv.c (long-double O(P^2)) vs the FFT restatement, incl. c0 and factor."""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    so = os.path.join(here, "libilm_oracle_c.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", here])
+    lib = ctypes.CDLL(so)
+    G = np.asfortranarray(lgfmod.lgf_table(40))
+    plan = o.ConvPlan(G[:33, :29])
+    rng = np.random.default_rng(11)
+    dp = ctypes.c_void_p
+    for shape in [(33, 29), (32, 28), (33, 28)]:
+        w = np.asfortranarray(rng.standard_normal(shape))
+        out = np.zeros(shape, order="F")
+        c0, factor = o.lgf_c0(0.05), 400.0
+        lib.ilm_oracle_inverse_laplacian(dp(G.ctypes.data), 40, dp(w.ctypes.data), shape[0], shape[1],
+                                         ctypes.c_double(c0), ctypes.c_double(factor), dp(out.ctypes.data))
+        ref = o.inverse_laplacian(plan, w, c0, factor)
+        assert np.abs(out - ref).max() < 1e-12 * np.abs(ref).max()
