@@ -25,6 +25,11 @@ struct DevCtx {
         __syncthreads();
 #endif
     }
+    ILM_HD void prefetch_l2(const void* p) {
+#ifdef __CUDA_ARCH__
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+    }
 };
 
 #define ILM_CAT2(a, b) a##b
@@ -62,8 +67,8 @@ int ILM_CAT(conv_launch_L, ILM_L)(int which, const ConvArgs& a, int nsm, cudaStr
         attr_done = true;
     }
     int nwork;
-    if (which == 0 || which == 2) nwork = (a.g.MYp + 2 * C::F - 1) / (2 * C::F);
-    else nwork = (a.g.Lx + C::F - 1) / C::F;
+    if (which == 0 || which == 2) nwork = (a.g.MYp + C::F - 1) / C::F;
+    else { const int cpw = C::F == 1 ? 2 : C::F; nwork = (2 * a.g.Lx + cpw - 1) / cpw; }
     int grid = nwork < nsm ? nwork : nsm;
     if (grid < 1) grid = 1;
     switch (which) {

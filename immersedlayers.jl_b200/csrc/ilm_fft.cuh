@@ -139,12 +139,12 @@ ILM_HD int xpad(int i) { return i + (i >> 4); }
 
 // w_32^e, e = 0..15
 ILM_HD double2 w32(int e) {
-    const double c[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+    static constexpr double c[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
                           0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
                           0.19509032201612826785, 0.0, -0.19509032201612826785, -0.38268343236508977173,
                           -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
                           -0.92387953251128675613, -0.98078528040323044913};
-    const double s[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
+    static constexpr double s[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
                           0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613,
                           0.98078528040323044913, 1.0, 0.98078528040323044913, 0.92387953251128675613,
                           0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
