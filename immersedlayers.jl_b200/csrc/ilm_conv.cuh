@@ -72,7 +72,12 @@ struct ConvArgs {
     double gscale;         // pass G scale
     const double2* twx;    // twiddle table for Lx (global)
     const double2* twy;    // twiddle table for Ly (global)
+    int skew_ns;           // start-up delay of one group (de-phases FP64 and shared-memory phases)
 };
+
+// named barriers 1,2 are the per-group barriers (Ctx::sync); these two carry the
+// producer (odd half, group 1) -> consumer (even half, group 0) hand-off
+constexpr int BAR_READY = 3, BAR_FREE = 4;
 
 // copy the twiddle table into shared memory (whole CTA, 512 threads)
 template <int L, class Ctx>
@@ -91,25 +96,42 @@ template <class Ctx> ILM_HD void prefetch_range(Ctx& ctx, const void* base, size
     for (size_t off = (size_t)(ctx.grp * 256 + ctx.tid) * 128; off < bytes; off += 512 * 128) ctx.prefetch_l2(b + off);
 }
 
+// spectrum index of element e of thread j when the transform runs along x (rows):
+// m = j + e*T at fixed row; constant stride T*MYp for even T
+template <int T> ILM_HD size_t row_elem(const ConvGeom& g, int px, int row, int j, int e, size_t i0) {
+    if constexpr (T >= 2) return i0 + (size_t)e * T * (size_t)g.MYp;
+    else return s_index(g, px, j + e * T, row);
+}
+// ... and along y (columns): n = j + e*T at fixed m; constant stride 2T for even T
+template <int T> ILM_HD size_t col_elem(const ConvGeom& g, int px, int m, int j, int e, size_t i0) {
+    if constexpr (T >= 2) return i0 + (size_t)e * (2 * T);
+    else return s_index(g, px, m, j + e * T);
+}
+
 // ---------------------------------------------------------------- pass A
 // work item = F rows; group g computes output parity px = g of those rows
 template <int L, class Ctx>
 ILM_HD void passA_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, int nblocks) {
     using C = FftCfg<L>;
     constexpr int T = C::T, F = C::F;
-    double2* tw = smem + 2 * C::GROUP_XBUF;
+    double2* tw = smem + C::TW_BASE;
     load_twiddles<L>(ctx, tw, a.twx);
     const int f = ctx.tid / T, j = ctx.tid % T, px = ctx.grp;
     double2* xb = smem + ctx.grp * C::GROUP_XBUF + f * C::XBUF;
-    const int nwork = (a.g.MYp + F - 1) / F;
+    // work item = F rows (measured: pairing consecutive rows per CTA is slower here)
+    constexpr int SUB = 1, RPW = F * SUB;
+    const int nwork = (a.g.MYp + RPW - 1) / RPW;
+    if (px) ctx.delay(a.skew_ns);
     for (int w = block; w < nwork; w += nblocks) {
-        const int row = w * F + f;
-        const bool r1 = a.f1.p && row < a.f1.my, r2 = a.f2.p && row < a.f2.my;
         const int wn = w + nblocks;                       // next work item of this CTA
         if (wn < nwork) {
-            if (a.f1.p && wn * F < a.f1.my) prefetch_range(ctx, a.f1.p + (size_t)wn * F * a.f1.mx, (size_t)F * a.f1.mx * 8);
-            if (a.f2.p && wn * F < a.f2.my) prefetch_range(ctx, a.f2.p + (size_t)wn * F * a.f2.mx, (size_t)F * a.f2.mx * 8);
+            if (a.f1.p && wn * RPW < a.f1.my) prefetch_range(ctx, a.f1.p + (size_t)wn * RPW * a.f1.mx, (size_t)RPW * a.f1.mx * 8);
+            if (a.f2.p && wn * RPW < a.f2.my) prefetch_range(ctx, a.f2.p + (size_t)wn * RPW * a.f2.mx, (size_t)RPW * a.f2.mx * 8);
         }
+#pragma unroll 1
+      for (int sub = 0; sub < SUB; ++sub) {
+        const int row = w * RPW + sub * F + f;
+        const bool r1 = a.f1.p && row < a.f1.my, r2 = a.f2.p && row < a.f2.my;
         double2 v[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
@@ -121,9 +143,11 @@ ILM_HD void passA_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
         }
         fft_regs<L, false>(v, ctx, xb, tw, j);
         if (row < a.g.MYp) {
+            const size_t i0 = s_index(a.g, px, j, row);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) a.S[s_index(a.g, px, j + e * T, row)] = v[e];
+            for (int e = 0; e < 16; ++e) a.S[row_elem<T>(a.g, px, row, j, e, i0)] = v[e];
         }
+      }
     }
 }
 
@@ -136,14 +160,17 @@ ILM_HD void passB_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
     constexpr int T = C::T, F = C::F;
     constexpr int SUB = (F == 1) ? 2 : 1;        // a 2-column tile is never split between CTAs
     constexpr int CPW = F * SUB;
-    double2* tw = smem + 2 * C::GROUP_XBUF;
+    double2* tw = smem + C::TW_BASE;
     load_twiddles<L>(ctx, tw, a.twy);
     const int f = ctx.tid / T, j = ctx.tid % T, py = ctx.grp;
     double2* xb = smem + ctx.grp * C::GROUP_XBUF + f * C::XBUF;
-    double2* xb_odd = smem + C::GROUP_XBUF + f * C::XBUF;      // group 1's buffer of the same FFT slot
+    double2* comb = smem + 2 * C::GROUP_XBUF + f * L;           // odd -> even hand-off of this FFT slot
     const int ncols = 2 * a.g.Lx;
     const int nwork = (ncols + CPW - 1) / CPW;
     const size_t col_elems = (size_t)a.g.MYp;                   // complex elements per column
+    if (MODE == 0) {
+        if (!py) { ctx.arrive(BAR_FREE); ctx.delay(a.skew_ns); }
+    }
     for (int w = block; w < nwork; w += nblocks) {
         const int wn = w + nblocks;
         if (wn < nwork) {
@@ -159,12 +186,13 @@ ILM_HD void passB_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
             const int px = live ? c / a.g.Lx : 0;
             const int m = live ? c % a.g.Lx : 0;
             const size_t gbase = ((size_t)ghat_col(a.g, px, m) * 2 + py) * a.g.Ly;
+            const size_t i0 = s_index(a.g, px, m, j);
             if (MODE == 0 && live) ctx.prefetch_l2(a.Ghat + gbase + (size_t)j * 16);    // T lines of 16 doubles
             double2 v[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
                 const int n = j + e * T;
-                v[e] = (live && n < a.g.MYp) ? a.S[s_index(a.g, px, m, n)] : cmk(0.0, 0.0);
+                v[e] = (live && n < a.g.MYp) ? a.S[col_elem<T>(a.g, px, m, j, e, i0)] : cmk(0.0, 0.0);
                 if (MODE == 1) v[e].y = 0.0;
                 if (py) v[e] = cmul(v[e], mod_fwd<L>(tw, j, e));
             }
@@ -183,19 +211,21 @@ ILM_HD void passB_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
                 fft_regs<L, true>(v, ctx, xb, tw, j);
                 // combine the two half transforms: y[n] = E[n] + conj(w^n) O[n]
                 if (py) {
-                    ctx.sync();                               // group 1 finished reading its exchange buffer
+                    ctx.wait(BAR_FREE);                       // consumer has drained the previous column
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) xb[xpad(j + e * T)] = cmulc(v[e], mod_fwd<L>(tw, j, e));
-                }
-                ctx.sync_cta();
-                if (!py && live) {
+                    for (int e = 0; e < 16; ++e) comb[j + e * T] = cmulc(v[e], mod_fwd<L>(tw, j, e));
+                    ctx.arrive(BAR_READY);
+                } else {
+                    ctx.wait(BAR_READY);
+                    if (live) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int n = j + e * T;
-                        if (n < a.g.MYp) a.S2[s_index(a.g, px, m, n)] = cadd(v[e], xb_odd[xpad(n)]);
+                        for (int e = 0; e < 16; ++e) {
+                            const int n = j + e * T;
+                            if (n < a.g.MYp) a.S2[col_elem<T>(a.g, px, m, j, e, i0)] = cadd(v[e], comb[n]);
+                        }
                     }
+                    ctx.arrive(BAR_FREE);
                 }
-                ctx.sync_cta();                               // group 1 may reuse its buffer
             }
         }
     }
@@ -207,42 +237,44 @@ template <int L, class Ctx>
 ILM_HD void passC_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, int nblocks) {
     using C = FftCfg<L>;
     constexpr int T = C::T, F = C::F;
-    double2* tw = smem + 2 * C::GROUP_XBUF;
+    double2* tw = smem + C::TW_BASE;
     load_twiddles<L>(ctx, tw, a.twx);
     const int f = ctx.tid / T, j = ctx.tid % T, px = ctx.grp;
     double2* xb = smem + ctx.grp * C::GROUP_XBUF + f * C::XBUF;
-    double2* xb_odd = smem + C::GROUP_XBUF + f * C::XBUF;
-    const int nwork = (a.g.MYp + F - 1) / F;
+    double2* comb = smem + 2 * C::GROUP_XBUF + f * L;
+    // RPW consecutive rows per work item: the second row of each 2x2 tile is an
+    // L2 hit (its sector came in with the first row's 64-byte DRAM access)
+    constexpr int SUB = (F == 1) ? 2 : 1, RPW = F * SUB;
+    const int nwork = (a.g.MYp + RPW - 1) / RPW;
+    if (!px) { ctx.arrive(BAR_FREE); ctx.delay(a.skew_ns); }
     for (int w = block; w < nwork; w += nblocks) {
-        const int row = w * F + f;
+#pragma unroll 1
+      for (int sub = 0; sub < SUB; ++sub) {
+        const int row = w * RPW + sub * F + f;
         const bool live = row < a.g.MYp;
         const bool r1 = a.f1.p && row < a.f1.my, r2 = a.f2.p && row < a.f2.my;
+        const size_t i0 = s_index(a.g, px, j, row);
         double2 v[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = live ? a.S2[s_index(a.g, px, j + e * T, row)] : cmk(0.0, 0.0);
-        // next row of this CTA: the 32-byte sectors this thread will read
-        const int rown = row + nblocks * F;
-        if (rown < a.g.MYp) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) ctx.prefetch_l2(&a.S2[s_index(a.g, px, j + e * T, rown)]);
-        }
+        for (int e = 0; e < 16; ++e) v[e] = live ? a.S2[row_elem<T>(a.g, px, row, j, e, i0)] : cmk(0.0, 0.0);
         fft_regs<L, true>(v, ctx, xb, tw, j);
         if (px) {
-            ctx.sync();
+            ctx.wait(BAR_FREE);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) xb[xpad(j + e * T)] = cmulc(v[e], mod_fwd<L>(tw, j, e));
-        }
-        ctx.sync_cta();
-        if (!px) {
+            for (int e = 0; e < 16; ++e) comb[j + e * T] = cmulc(v[e], mod_fwd<L>(tw, j, e));
+            ctx.arrive(BAR_READY);
+        } else {
+            ctx.wait(BAR_READY);
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
                 const int n = j + e * T;
-                const double2 y = cadd(v[e], xb_odd[xpad(n)]);
+                const double2 y = cadd(v[e], comb[n]);
                 if (r1 && n < a.f1.mx) a.f1.p[(size_t)row * a.f1.mx + n] = y.x;
                 if (r2 && n < a.f2.mx) a.f2.p[(size_t)row * a.f2.mx + n] = y.y;
             }
+            ctx.arrive(BAR_FREE);
         }
-        ctx.sync_cta();
+      }
     }
 }
 

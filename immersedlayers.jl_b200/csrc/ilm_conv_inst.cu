@@ -25,6 +25,23 @@ struct DevCtx {
         __syncthreads();
 #endif
     }
+    // producer/consumer hand-off between the two groups (512 = both groups)
+    ILM_HD void arrive(int id) {
+#ifdef __CUDA_ARCH__
+        __threadfence_block();
+        asm volatile("bar.arrive %0, 512;" ::"r"(id) : "memory");
+#endif
+    }
+    ILM_HD void wait(int id) {
+#ifdef __CUDA_ARCH__
+        asm volatile("bar.sync %0, 512;" ::"r"(id) : "memory");
+#endif
+    }
+    ILM_HD void delay(int ns) {
+#ifdef __CUDA_ARCH__
+        if (ns > 0) __nanosleep((unsigned)ns);
+#endif
+    }
     ILM_HD void prefetch_l2(const void* p) {
 #ifdef __CUDA_ARCH__
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -67,8 +84,10 @@ int ILM_CAT(conv_launch_L, ILM_L)(int which, const ConvArgs& a, int nsm, cudaStr
         attr_done = true;
     }
     int nwork;
-    if (which == 0 || which == 2) nwork = (a.g.MYp + C::F - 1) / C::F;
-    else { const int cpw = C::F == 1 ? 2 : C::F; nwork = (2 * a.g.Lx + cpw - 1) / cpw; }
+    const int cpw = C::F == 1 ? 2 : C::F;          // rows / columns per work item
+    if (which == 0) nwork = (a.g.MYp + C::F - 1) / C::F;
+    else if (which == 2) nwork = (a.g.MYp + cpw - 1) / cpw;
+    else nwork = (2 * a.g.Lx + cpw - 1) / cpw;
     int grid = nwork < nsm ? nwork : nsm;
     if (grid < 1) grid = 1;
     switch (which) {

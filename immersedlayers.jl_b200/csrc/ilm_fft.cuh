@@ -116,6 +116,8 @@ template <bool INV> ILM_HD void fft16(double2* v) {
 }
 
 // ---- compile-time plan for length L ---------------------------------------
+constexpr int ilm_log2(int n) { return n <= 1 ? 0 : 1 + ilm_log2(n / 2); }
+
 template <int L> struct FftCfg {
     static_assert(L >= 16 && L <= 4096 && (L & (L - 1)) == 0, "L must be a power of two in [16,4096]");
     static constexpr int T = L / 16;            // threads per FFT
@@ -123,16 +125,20 @@ template <int L> struct FftCfg {
     static constexpr int P = (L == 16) ? 1 : (L <= 256 ? 2 : 3);
     static constexpr int RL = (P == 1) ? 16 : (P == 2 ? L / 16 : L / 256);   // tail radix
     static constexpr int NS_LAST = L / RL;
+    // twiddle tables hold only the power-of-two exponents w^(k 2^i); the other
+    // powers are formed by products in registers (4 loads instead of 15)
     static constexpr int TW1_OFF = 0;
-    static constexpr int TW1_N = (P == 3) ? 15 * 16 : 0;
+    static constexpr int TW1_N = (P == 3) ? 4 * 16 : 0;          // middle pass: radix 16, Ns = 16
     static constexpr int TWL_OFF = TW1_OFF + TW1_N;
-    static constexpr int TWL_N = (P >= 2) ? (RL - 1) * NS_LAST : 0;
+    static constexpr int TWL_N = (P >= 2) ? ilm_log2(RL) * NS_LAST : 0;
     static constexpr int MOD_OFF = TWL_OFF + TWL_N;     // w_{2L}^j, j < T
     static constexpr int MOD_N = T;
     static constexpr int TW_TOTAL = MOD_OFF + MOD_N;
     static constexpr int XBUF = L + L / 16;             // padded exchange entries per FFT
     static constexpr int GROUP_XBUF = F * XBUF;         // = 4352 for every L
-    static constexpr size_t SMEM_BYTES = (size_t)(2 * GROUP_XBUF + TW_TOTAL) * sizeof(double2);
+    static constexpr int COMB = F * L;                  // combine buffer (unpadded), = 4096
+    static constexpr int TW_BASE = 2 * GROUP_XBUF + COMB;
+    static constexpr size_t SMEM_BYTES = (size_t)(TW_BASE + TW_TOTAL) * sizeof(double2);
 };
 
 ILM_HD int xpad(int i) { return i + (i >> 4); }
@@ -159,6 +165,26 @@ template <int R, bool INV, int S> ILM_HD void fft_tail(double2* v) {
     else fft2s<S>(v);
 }
 
+// v[t*S] *= w^(k t), t = 1..R-1, from the table of power-of-two exponents
+// tw[i*ns + k] = w^(k 2^i); conjugated for the inverse transform.
+template <int R, bool INV, int S> ILM_HD void twiddle_powers(double2* v, const double2* tw, int ns, int k) {
+    double2 b[R];
+    b[1] = tw[k];
+    if constexpr (R >= 4) { b[2] = tw[ns + k]; b[3] = cmul(b[1], b[2]); }
+    if constexpr (R >= 8) {
+        b[4] = tw[2 * ns + k];
+#pragma unroll
+        for (int t = 1; t < 4; ++t) b[4 + t] = cmul(b[4], b[t]);
+    }
+    if constexpr (R >= 16) {
+        b[8] = tw[3 * ns + k];
+#pragma unroll
+        for (int t = 1; t < 8; ++t) b[8 + t] = cmul(b[8], b[t]);
+    }
+#pragma unroll
+    for (int t = 1; t < R; ++t) v[t * S] = ctw<INV>(v[t * S], b[t]);
+}
+
 // One complex FFT of length L on the 16 registers of each of its T threads.
 //   v[e] holds x[j + e*T] on entry and X[j + e*T] on exit (unnormalised).
 //   xb: this FFT's padded exchange buffer (XBUF entries), tw: twiddle table.
@@ -177,8 +203,7 @@ ILM_HD void fft_regs(double2* v, Ctx& ctx, double2* xb, const double2* tw, int j
     for (int e = 0; e < 16; ++e) v[e] = xb[xpad(j + e * T)];
     if (C::P == 3) {
         const int k = j & 15;
-#pragma unroll
-        for (int t = 1; t < 16; ++t) v[t] = ctw<INV>(v[t], tw[C::TW1_OFF + (t - 1) * 16 + k]);
+        twiddle_powers<16, INV, 1>(v, tw + C::TW1_OFF, 16, k);
         fft16<INV>(v);
         ctx.sync();
 #pragma unroll
@@ -191,10 +216,7 @@ ILM_HD void fft_regs(double2* v, Ctx& ctx, double2* xb, const double2* tw, int j
     constexpr int RL = C::RL, S = 16 / RL, NS = C::NS_LAST;
 #pragma unroll
     for (int q = 0; q < S; ++q) {
-        const int k = j + q * T;
-#pragma unroll
-        for (int t = 1; t < RL; ++t)
-            v[q + t * S] = ctw<INV>(v[q + t * S], tw[C::TWL_OFF + (t - 1) * NS + k]);
+        twiddle_powers<RL, INV, S>(v + q, tw + C::TWL_OFF, NS, j + q * T);
         fft_tail<RL, INV, S>(v + q);
     }
 }
@@ -204,12 +226,12 @@ template <int L, class TrigFn>
 inline void fft_fill_twiddles(double2* tw, TrigFn expm2pii /* (num, den) -> exp(-2 pi i num/den) */) {
     using C = FftCfg<L>;
     if (C::P == 3)
-        for (int t = 1; t < 16; ++t)
-            for (int k = 0; k < 16; ++k) tw[C::TW1_OFF + (t - 1) * 16 + k] = expm2pii((long long)k * t, 256);
+        for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 16; ++k) tw[C::TW1_OFF + i * 16 + k] = expm2pii((long long)k << i, 256);
     if (C::P >= 2)
-        for (int t = 1; t < C::RL; ++t)
+        for (int i = 0; i < ilm_log2(C::RL); ++i)
             for (int k = 0; k < C::NS_LAST; ++k)
-                tw[C::TWL_OFF + (t - 1) * C::NS_LAST + k] = expm2pii((long long)k * t, (long long)L);
+                tw[C::TWL_OFF + i * C::NS_LAST + k] = expm2pii((long long)k << i, (long long)L);
     for (int j = 0; j < C::T; ++j) tw[C::MOD_OFF + j] = expm2pii(j, 2LL * L);
 }
 

@@ -75,6 +75,7 @@ struct ilm_plan {
     double2 *twx = nullptr, *twy = nullptr;
     double2 *S = nullptr, *S2 = nullptr;
     size_t s_cap = 0;
+    int skew_ns = 500;              // ILM_CONV_SKEW_NS: start-up skew between the two groups of a CTA
     std::vector<ilm::ConvKernel> kernels;
     // scratch (device)
     double* g_edges = nullptr;      // Edges scratch (gsnorm_cache)

@@ -3,6 +3,8 @@
 // three-pass apply.  Replaces plan_laplacian / CircularConvolution set-up
 // reached from _get_laplacian (src/cache.jl:321-324) and the `L\w` apply
 // reached from inverse_laplacian! (src/grid_operators.jl:153-179).
+#include <cstdlib>
+
 #include "ilm_internal.h"
 
 namespace ilm {
@@ -51,6 +53,7 @@ static int half_len(int n) {
 }
 
 int conv_setup(ilm_plan* p) {
+    if (const char* e = getenv("ILM_CONV_SKEW_NS")) p->skew_ns = atoi(e);
     p->Lx = half_len(p->g.NX);
     p->Ly = half_len(p->g.NY);
     if (p->Lx > 4096 || p->Ly > 4096) {
@@ -104,6 +107,7 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     a.GhatOut = k.ghat;
     a.gscale = 1.0 / (4.0 * (double)p->Lx * (double)p->Ly * factor);
     a.twx = p->twx; a.twy = p->twy;
+    a.skew_ns = p->skew_ns;
     ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream));
     ILM_TRY(conv_launcher(p->Ly)(3, a, p->nsm, p->stream));
     p->launches += 2;
@@ -128,6 +132,7 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2) {
     a.S = p->S; a.S2 = p->S2;
     a.Ghat = p->kernels[kernel_id].ghat;
     a.twx = p->twx; a.twy = p->twy;
+    a.skew_ns = p->skew_ns;
     ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream));
     ILM_TRY(conv_launcher(p->Ly)(1, a, p->nsm, p->stream));
     ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, p->stream));
@@ -144,6 +149,7 @@ int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3]) 
     a.S = p->S; a.S2 = p->S2;
     a.Ghat = p->kernels[0].ghat;
     a.twx = p->twx; a.twy = p->twy;
+    a.skew_ns = p->skew_ns;
     cudaEvent_t e0, e1;
     ILM_CUDA(cudaEventCreate(&e0));
     ILM_CUDA(cudaEventCreate(&e1));

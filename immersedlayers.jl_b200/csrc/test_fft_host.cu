@@ -25,12 +25,19 @@ struct Barrier {
         if (++count == n) { count = 0; ++gen; cv.notify_all(); }
         else cv.wait(lk, [&] { return gen != g; });
     }
+    void arrive() {          // bar.arrive: count in, do not wait
+        std::unique_lock<std::mutex> lk(m);
+        if (++count == n) { count = 0; ++gen; cv.notify_all(); }
+    }
 };
 
 struct HostCtx {
-    int tid, grp; Barrier* gb; Barrier* cb;
+    int tid, grp; Barrier* gb; Barrier* cb; Barrier* named;   // named[id] for id = BAR_READY, BAR_FREE
     void sync() { gb->wait(); }
     void sync_cta() { cb->wait(); }
+    void arrive(int id) { named[id].arrive(); }
+    void wait(int id) { named[id].wait(); }
+    void delay(int) {}
     void prefetch_l2(const void*) {}
 };
 
@@ -43,10 +50,11 @@ static double2 expm2pii(long long num, long long den) {
 template <class Body> static void run_cta(size_t smem_bytes, Body body) {
     std::vector<double2> smem(smem_bytes / sizeof(double2) + 1);
     Barrier g0(256), g1(256), cb(512);
+    Barrier named[5] = {Barrier(512), Barrier(512), Barrier(512), Barrier(512), Barrier(512)};
     std::vector<std::thread> th;
     for (int t = 0; t < 512; ++t)
         th.emplace_back([&, t] {
-            HostCtx c{t & 255, t >> 8, (t >> 8) ? &g1 : &g0, &cb};
+            HostCtx c{t & 255, t >> 8, (t >> 8) ? &g1 : &g0, &cb, named};
             body(c, smem.data());
         });
     for (auto& x : th) x.join();
@@ -63,7 +71,7 @@ template <int L, bool INV> static double test_fft() {
     std::vector<double2> in((size_t)nf * L), out((size_t)nf * L);
     for (auto& z : in) z = cmk(nd(rng), nd(rng));
     run_cta(C::SMEM_BYTES, [&](HostCtx& c, double2* smem) {
-        double2* tws = smem + 2 * C::GROUP_XBUF;
+        double2* tws = smem + C::TW_BASE;
         load_twiddles<L>(c, tws, tw.data());
         const int f = c.tid / C::T, j = c.tid % C::T;
         double2* xb = smem + c.grp * C::GROUP_XBUF + f * C::XBUF;
@@ -142,10 +150,12 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
     a.f2 = second ? FieldRef{o2.data(), mx2, my2} : FieldRef{nullptr, 0, 0};
     a.S = S.data(); a.S2 = S2.data(); a.Ghat = Ghat.data();
     {
-        int nwork = (g2.MYp + FftCfg<LX>::F - 1) / FftCfg<LX>::F;
+        int nwork = (g2.MYp + (FftCfg<LX>::F == 1 ? 2 : FftCfg<LX>::F) - 1) / (FftCfg<LX>::F == 1 ? 2 : FftCfg<LX>::F);
         int nb = nwork > 2 ? 2 : nwork;
-        for (int b = 0; b < nb; ++b)
-            run_cta(FftCfg<LX>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passA_body<LX>(c, a, sm, b, nb); });
+        int nworkA = (g2.MYp + FftCfg<LX>::F - 1) / FftCfg<LX>::F;
+        int nbA = nworkA > 2 ? 2 : nworkA;
+        for (int b = 0; b < nbA; ++b)
+            run_cta(FftCfg<LX>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passA_body<LX>(c, a, sm, b, nbA); });
         int nworkB = (2 * g2.Lx + (FftCfg<LY>::F == 1 ? 2 : FftCfg<LY>::F) - 1) / (FftCfg<LY>::F == 1 ? 2 : FftCfg<LY>::F);
         int nbB = nworkB > 3 ? 3 : nworkB;
         for (int b = 0; b < nbB; ++b)
