@@ -248,6 +248,42 @@ def main():
                 "solve_frac_of_hbm": sum(bytes_pass.values()) / (conv_ms * 1e-3) / 1e9 / peak,
                 "frac_of_nominal_8TBps": achieved / 8000.0}
 
+    # ---- the other stages of the path (stencils, regularize, interpolate), device resident,
+    #      20 back-to-back launches between CUDA events on the plan's stream (= torch's default stream)
+    def time_op(fn, reps=20):
+        fn()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record()
+        a1.synchronize()
+        return a0.elapsed_time(a1) / reps
+
+    Pn = (g.NX - 1) * (g.NY - 1)
+    Pd, Pe = g.NX * g.NY, g.NX * (g.NY - 1) + (g.NX - 1) * g.NY
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    qe, pn_, sd = cache.zeros_gridgrad(), cache.zeros_grid(), cache.zeros_gridcurl()
+    qe.data.normal_(generator=gen); pn_.data.normal_(generator=gen); sd.data.normal_(generator=gen)
+    oq, op_, os_ = cache.zeros_gridgrad(), cache.zeros_grid(), cache.zeros_gridcurl()
+    fs, fo = cache.zeros_surface(), cache.zeros_surface()
+    fs.data.normal_(generator=gen)
+    stage_defs = {
+        "divergence": (lambda: ilm.divergence(op_, qe, cache), 8 * (Pe + Pn)),
+        "grad": (lambda: ilm.grad(oq, pn_, cache), 8 * (Pe + Pn)),
+        "curl_nodes_to_edges": (lambda: ilm.curl(oq, sd, cache), 8 * (Pe + Pd)),
+        "curl_edges_to_nodes": (lambda: ilm.curl(os_, qe, cache), 8 * (Pe + Pd)),
+        "laplacian": (lambda: ilm.laplacian(os_, sd, cache), 16 * Pd),
+        "regularize": (lambda: ilm.regularize(op_, fs, cache), 8 * Pn + N * (16 * 12 + 8)),
+        "interpolate": (lambda: ilm.interpolate(fo, pn_, cache), N * (16 * 20 + 8)),
+    }
+    stages = {}
+    for name, (fn, nbytes) in stage_defs.items():
+        tms = time_op(fn)
+        stages[name] = {"ms": tms, "bytes": nbytes, "GBps": nbytes / (tms * 1e-3) / 1e9,
+                        "frac_of_hbm_peak": nbytes / (tms * 1e-3) / 1e9 / peak}
+    roofline["stages"] = stages
+
     # ---- end to end through the public API with host buffers
     e2e = None
     if rank == 0 or world > 1:
