@@ -1,6 +1,7 @@
 // ilm_api.cu -- the C ABI of libilm_b200.so (include/ilm_b200.h): plan life
 // cycle, host/device pointer plumbing and the operator entry points that mirror
 // ImmersedLayers' methods on BasicILMCache.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
@@ -501,11 +502,23 @@ extern "C" int ilm_create_schur(ilm_plan* p, int which, double scale, int col_be
         return launch_scale_store_column(p, sout, dst, N, -scale);
     };
     // two columns per complex transform (src/matrix_operators.jl:16-26 probes one at a time)
+    const DevTable& tp = p->tab[ILM_NODES_PRIMAL];
     for (int c = col_begin; c < col_end; c += 2) {
         const bool two = c + 1 < col_end;
-        ILM_TRY(pre(c, gf[0]));
-        if (two) ILM_TRY(pre(c + 1, gf[1]));
-        ILM_TRY(conv_apply(p, 0, fref(p, glayout, gf[0]), two ? fref(p, glayout, gf[1]) : FieldRef{nullptr, 0, 0}));
+        int rlo = -1, rhi = -1;
+        if (which == ILM_RTLINVR) {
+            // R e_c is a WxW patch: only its rows are non-zero -> sparse-row input of the transform
+            rlo = tp.h_j0[c]; rhi = tp.h_j0[c] + tp.W;
+            if (two) { rlo = std::min(rlo, tp.h_j0[c + 1]); rhi = std::max(rhi, tp.h_j0[c + 1] + tp.W); }
+            rlo = std::max(rlo, 0); rhi = std::min(rhi, tp.my);
+            if (rhi <= rlo) { rlo = 0; rhi = 1; }
+            ILM_TRY(launch_regularize_unit(p, tp, c, gf[0], rlo, rhi));
+            if (two) ILM_TRY(launch_regularize_unit(p, tp, c + 1, gf[1], rlo, rhi));
+        } else {
+            ILM_TRY(pre(c, gf[0]));
+            if (two) ILM_TRY(pre(c + 1, gf[1]));
+        }
+        ILM_TRY(conv_apply(p, 0, fref(p, glayout, gf[0]), two ? fref(p, glayout, gf[1]) : FieldRef{nullptr, 0, 0}, rlo, rhi));
         ILM_TRY(post(gf[0], dA + (size_t)(c - col_begin) * N));
         if (two) ILM_TRY(post(gf[1], dA + (size_t)(c + 1 - col_begin) * N));
     }

@@ -73,6 +73,8 @@ struct ConvArgs {
     const double2* twx;    // twiddle table for Lx (global)
     const double2* twy;    // twiddle table for Ly (global)
     int skew_ns;           // start-up delay of one group (de-phases FP64 and shared-memory phases)
+    int rlo, rhi;          // input rows outside [rlo, rhi) are known to be zero in both fields
+                           // (Schur probes: a 4x4 patch); pass A skips them, pass B reads zeros
 };
 
 // named barriers 1,2 are the per-group barriers (Ctx::sync); these two carry the
@@ -120,17 +122,18 @@ ILM_HD void passA_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
     double2* xb = smem + ctx.grp * C::GROUP_XBUF + f * C::XBUF;
     // work item = F rows (measured: pairing consecutive rows per CTA is slower here)
     constexpr int SUB = 1, RPW = F * SUB;
-    const int nwork = (a.g.MYp + RPW - 1) / RPW;
+    const int nwork = (a.rhi - a.rlo + RPW - 1) / RPW;
     if (px) ctx.delay(a.skew_ns);
     for (int w = block; w < nwork; w += nblocks) {
         const int wn = w + nblocks;                       // next work item of this CTA
         if (wn < nwork) {
-            if (a.f1.p && wn * RPW < a.f1.my) prefetch_range(ctx, a.f1.p + (size_t)wn * RPW * a.f1.mx, (size_t)RPW * a.f1.mx * 8);
-            if (a.f2.p && wn * RPW < a.f2.my) prefetch_range(ctx, a.f2.p + (size_t)wn * RPW * a.f2.mx, (size_t)RPW * a.f2.mx * 8);
+            const int rn = a.rlo + wn * RPW;
+            if (a.f1.p && rn < a.f1.my) prefetch_range(ctx, a.f1.p + (size_t)rn * a.f1.mx, (size_t)RPW * a.f1.mx * 8);
+            if (a.f2.p && rn < a.f2.my) prefetch_range(ctx, a.f2.p + (size_t)rn * a.f2.mx, (size_t)RPW * a.f2.mx * 8);
         }
 #pragma unroll 1
       for (int sub = 0; sub < SUB; ++sub) {
-        const int row = w * RPW + sub * F + f;
+        const int row = a.rlo + w * RPW + sub * F + f;
         const bool r1 = a.f1.p && row < a.f1.my, r2 = a.f2.p && row < a.f2.my;
         double2 v[16];
 #pragma unroll
@@ -142,7 +145,7 @@ ILM_HD void passA_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
             if (px) v[e] = cmul(v[e], mod_fwd<L>(tw, j, e));
         }
         fft_regs<L, false>(v, ctx, xb, tw, j);
-        if (row < a.g.MYp) {
+        if (row < a.rhi) {
             const size_t i0 = s_index(a.g, px, j, row);
 #pragma unroll
             for (int e = 0; e < 16; ++e) a.S[row_elem<T>(a.g, px, row, j, e, i0)] = v[e];
@@ -173,7 +176,7 @@ ILM_HD void passB_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
     }
     for (int w = block; w < nwork; w += nblocks) {
         const int wn = w + nblocks;
-        if (wn < nwork) {
+        if (wn < nwork && a.rhi - a.rlo == a.g.MYp) {
             const size_t e0 = (size_t)wn * CPW * col_elems;
             size_t ne = (size_t)CPW * col_elems;
             if (e0 + ne > s_elems(a.g)) ne = s_elems(a.g) - e0;
@@ -192,7 +195,7 @@ ILM_HD void passB_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
                 const int n = j + e * T;
-                v[e] = (live && n < a.g.MYp) ? a.S[col_elem<T>(a.g, px, m, j, e, i0)] : cmk(0.0, 0.0);
+                v[e] = (live && n >= a.rlo && n < a.rhi) ? a.S[col_elem<T>(a.g, px, m, j, e, i0)] : cmk(0.0, 0.0);
                 if (MODE == 1) v[e].y = 0.0;
                 if (py) v[e] = cmul(v[e], mod_fwd<L>(tw, j, e));
             }

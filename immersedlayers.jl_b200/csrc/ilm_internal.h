@@ -51,6 +51,7 @@ struct DevTable {
     int* cell_off = nullptr;    // ncell+1 offsets into ent
     int* ent = nullptr;         // nent    k*W*W + slot, ascending k inside a cell
     double* rowsum = nullptr;   // ncell   sum_k R[cell,k] (surface filter)
+    std::vector<int> h_j0;      // host mirror of j0 (row range of each point's window)
 };
 
 struct ConvKernel {     // one multiplier (LGF inverse, integrating factor, ...)
@@ -113,7 +114,8 @@ int launch_regularize(ilm_plan* p, const DevTable& t, const double* f, const dou
 int launch_interpolate(ilm_plan* p, const DevTable& t, const double* field, double* f);
 // f = a_u*(E_u u) + a_v*(E_v v) with per-point factors (normal / cross products), then / div
 int launch_normal_interpolate(ilm_plan* p, int mode, const double* u, const double* v, double* f, double div);
-int launch_unit_columns(ilm_plan* p, const DevTable& t, int col, double* out);   // out += R e_col (pre-zeroed)
+// out rows [rlo, rhi) = R e_col (zero elsewhere in that row range); other rows untouched
+int launch_regularize_unit(ilm_plan* p, const DevTable& t, int col, double* out, int rlo, int rhi);
 int launch_divergence(ilm_plan* p, const double* u, const double* v, double* out, double div);
 int launch_grad(ilm_plan* p, const double* in, double* u, double* v, double div);
 int launch_curl_n2e(ilm_plan* p, const double* s, double* u, double* v, double div);
@@ -132,7 +134,8 @@ void free_table(DevTable& t);
 // ---- convolution engine (ilm_lgf.cu + ilm_conv_inst.cu) -------------------------
 int conv_setup(ilm_plan* p);
 int conv_add_kernel(ilm_plan* p, const double* table_host_or_dev, int n, double c0, double factor, int* id);
-int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2);
+// rows outside [rlo, rhi) of both inputs are known zeros (-1, -1 = dense input)
+int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo = -1, int rhi = -1);
 void conv_free(ilm_plan* p);
 int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3]);
 extern long long g_dense_launches;

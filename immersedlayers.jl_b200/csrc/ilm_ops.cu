@@ -103,6 +103,22 @@ int launch_regularize(ilm_plan* p, const DevTable& t, const double* f, const dou
     return ILM_OK;
 }
 
+// unit-vector probe of the Schur builders: out = R e_col restricted to rows [rlo, rhi)
+__global__ void k_regularize_unit(int W, int mx, int my, const int* __restrict__ i0, const int* __restrict__ j0,
+                                  const double* __restrict__ wR, int col, double* __restrict__ out) {
+    const int slot = threadIdx.x;
+    if (slot >= W * W) return;
+    const int a = slot % W, b = slot / W;
+    const int i = i0[col] + a, j = j0[col] + b;
+    if (i >= 0 && i < mx && j >= 0 && j < my) out[(size_t)j * mx + i] = wR[(size_t)col * W * W + slot];
+}
+int launch_regularize_unit(ilm_plan* p, const DevTable& t, int col, double* out, int rlo, int rhi) {
+    ILM_TRY(launch_fill(p, out + (size_t)rlo * t.mx, (size_t)(rhi - rlo) * t.mx, 0.0));
+    k_regularize_unit<<<1, 32, 0, p->stream>>>(t.W, t.mx, t.my, t.i0, t.j0, t.wR, col, out);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
 __global__ void k_rowsum(int ncell, const int* __restrict__ cell_off, const int* __restrict__ ent,
                          const double* __restrict__ wR, double* __restrict__ rowsum) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;

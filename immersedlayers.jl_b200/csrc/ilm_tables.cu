@@ -66,6 +66,7 @@ int build_tables(ilm_plan* p) {
             ILM_CUDA(cudaMemcpyAsync(hj.data(), t.j0, N * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
             ILM_CUDA(cudaStreamSynchronize(p->stream));
         }
+        t.h_j0 = hj;
         // gather list: (cell, k, slot) for every in-range window entry, sorted by cell then k
         struct Ent { int cell, id; };
         std::vector<Ent> ents;

@@ -106,7 +106,7 @@ template <int L, bool INV> static double test_fft() {
 
 
 template <int LX, int LY>
-static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool second) {
+static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool second, int rlo = -1, int rhi = -1) {
     // kernel table g(i,j), 0<=i<NX, 0<=j<NY : something LGF-like
     std::vector<double> G((size_t)NX * NY);
     for (int j = 0; j < NY; ++j)
@@ -124,6 +124,7 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
     std::vector<double2> S(s_elems(gg)), S2;
     std::vector<double> Ghat(ghat_elems(gg), 0.0);
     a.g = gg; a.f1 = FieldRef{h.data(), NX, NY}; a.f2 = FieldRef{nullptr, 0, 0};
+    a.rlo = 0; a.rhi = gg.MYp;
     a.S = S.data(); a.GhatOut = Ghat.data(); a.gscale = 1.0 / (4.0 * LX * LY);
     {
         int nwork = (gg.MYp + FftCfg<LX>::F - 1) / FftCfg<LX>::F;
@@ -141,18 +142,27 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
     std::vector<double> w1((size_t)mx1 * my1), w2((size_t)mx2 * my2);
     for (auto& x : w1) x = nd(rng);
     for (auto& x : w2) x = nd(rng);
+    if (rlo >= 0) {     // sparse-row input (Schur probe): zero outside [rlo, rhi)
+        for (int l = 0; l < my1; ++l) if (l < rlo || l >= rhi) for (int k = 0; k < mx1; ++k) w1[(size_t)l * mx1 + k] = 0;
+        for (int l = 0; l < my2; ++l) if (l < rlo || l >= rhi) for (int k = 0; k < mx2; ++k) w2[(size_t)l * mx2 + k] = 0;
+    }
     std::vector<double> o1 = w1, o2 = w2;
+    if (rlo >= 0) {     // rows outside the range hold garbage that must never be read
+        for (int l = 0; l < my1; ++l) if (l < rlo || l >= rhi) for (int k = 0; k < mx1; ++k) o1[(size_t)l * mx1 + k] = NAN;
+        for (int l = 0; l < my2; ++l) if (l < rlo || l >= rhi) for (int k = 0; k < mx2; ++k) o2[(size_t)l * mx2 + k] = NAN;
+    }
     int MY = second ? (my1 > my2 ? my1 : my2) : my1;
     ConvGeom g2{LX, LY, MY, (MY + 1) & ~1};
     S.assign(s_elems(g2), cmk(NAN, NAN));
     S2.assign(s_elems(g2), cmk(NAN, NAN));
     a.g = g2; a.f1 = FieldRef{o1.data(), mx1, my1};
+    a.rlo = rlo >= 0 ? rlo : 0; a.rhi = rlo >= 0 ? rhi : g2.MYp;
     a.f2 = second ? FieldRef{o2.data(), mx2, my2} : FieldRef{nullptr, 0, 0};
     a.S = S.data(); a.S2 = S2.data(); a.Ghat = Ghat.data();
     {
         int nwork = (g2.MYp + (FftCfg<LX>::F == 1 ? 2 : FftCfg<LX>::F) - 1) / (FftCfg<LX>::F == 1 ? 2 : FftCfg<LX>::F);
         int nb = nwork > 2 ? 2 : nwork;
-        int nworkA = (g2.MYp + FftCfg<LX>::F - 1) / FftCfg<LX>::F;
+        int nworkA = (a.rhi - a.rlo + FftCfg<LX>::F - 1) / FftCfg<LX>::F;
         int nbA = nworkA > 2 ? 2 : nworkA;
         for (int b = 0; b < nbA; ++b)
             run_cta(FftCfg<LX>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passA_body<LX>(c, a, sm, b, nbA); });
@@ -207,6 +217,8 @@ int main() {
     worst = fmax(worst, test_conv<16, 1024>(6, 400, 6, 400, 5, 399, true));
     worst = fmax(worst, test_conv<4096, 16>(1100, 3, 1100, 3, 1099, 2, true));
     worst = fmax(worst, test_conv<16, 4096>(5, 1100, 4, 1100, 5, 1099, true));
+    worst = fmax(worst, test_conv<64, 32>(24, 13, 24, 12, 23, 13, true, 5, 9));
+    worst = fmax(worst, test_conv<16, 1024>(6, 400, 6, 400, 5, 399, true, 201, 206));
     printf("worst relative error %.3e -> %s\n", worst, worst < 1e-12 ? "PASS" : "FAIL");
     return worst < 1e-12 ? 0 : 1;
 }
