@@ -57,9 +57,11 @@ int main() {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4352 * 16);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const int iters = 2000, ncomp = 8;      // 8 x 32 DFMA = 256 FP64 instr per compute phase
+    const int iters = 2000;
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
-    for (int mode = 0; mode < 7; ++mode) {
+    for (int ncomp : {2, 4, 8, 16})
+    for (int mode : {5, 6, 2}) {
+        printf("ncomp %2d ", ncomp);
         k<<<148, 512, 2 * 4352 * 16>>>(mode, 10, ncomp, out);
         cudaEventRecord(e0);
         k<<<148, 512, 2 * 4352 * 16>>>(mode, iters, ncomp, out);
