@@ -70,6 +70,21 @@ SIGNATURES = {
     "ilm_dense_factor": (_i, [_i, _dp, _ip, _vp]),
     "ilm_dense_solve": (_i, [_i, _dp, _ip, _i, _dp, _vp]),
     "ilm_dense_matvec_pow": (_i, [_i, _dp, _i, _dp, _vp]),
+    "ilm_regularize_normal_tensor": (_i, [_vp, _i, _dp, _dp]),
+    "ilm_normal_interpolate_tensor": (_i, [_vp, _i, _dp, _dp]),
+    "ilm_regularize_normal_vs": (_i, [_vp, _i, _dp, _dp]),
+    "ilm_normal_interpolate_vs": (_i, [_vp, _i, _dp, _dp]),
+    "ilm_regularize_normal_dot_tensor": (_i, [_vp, _dp, _dp]),
+    "ilm_normal_dot_interpolate_tensor": (_i, [_vp, _dp, _dp]),
+    "ilm_grad_tensor": (_i, [_vp, _dp, _dp]),
+    "ilm_divergence_tensor": (_i, [_vp, _dp, _dp]),
+    "ilm_vsurface_divergence": (_i, [_vp, _i, _dp, _dp]),
+    "ilm_vsurface_grad": (_i, [_vp, _i, _dp, _dp]),
+    "ilm_vsurface_curl_s2n": (_i, [_vp, _dp, _dp]),
+    "ilm_vsurface_curl_n2s": (_i, [_vp, _dp, _dp]),
+    "ilm_mask_edges": (_i, [_vp, _dp]),
+    "ilm_create_schur_vector": (_i, [_vp, _i, _d, _i, _i, _dp]),
+    "ilm_create_nRTRn_vector": (_i, [_vp, _d, _dp]),
     "ilm_dense_launch_count": (C.c_int64, []),
     "ilm_profile_conv": (_i, [_vp, _i, _i, C.POINTER(C.c_double * 3)]),
 }

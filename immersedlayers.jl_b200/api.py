@@ -645,3 +645,312 @@ def dirichlet_poisson(cache, fplus, fminus=None, S=None, filter_passes=0):
         Cm = create_surface_filter(cache)
         matvec_pow(Cm, filter_passes, s)
     return f, s, S
+
+
+# ==========================================================================
+# vector-data cache: SurfaceVectorCache (src/cache.jl:184-202) and the
+# VectorData / TensorData / EdgeGradient methods of the operator API.  The
+# functions below re-dispatch on the argument types the way Julia's methods do.
+# ==========================================================================
+EDGEGRAD = 5
+
+
+class TensorData(_Data):
+    """data = [dudx; dudy; dvdx; dvdy] (4N)."""
+
+    def __init__(self, n, data=None, device=False):
+        self.n = int(n)
+        super().__init__(_alloc(4 * self.n, device) if data is None else data)
+
+    def component(self, i):
+        return self.numpy()[i * self.n:(i + 1) * self.n]
+
+
+class EdgeGradient(_Data):
+    """EdgeGradient{Primal,Dual}: [dudx; dudy; dvdx; dvdy], dudx/dvdy on primal
+    nodes, dudy/dvdx on dual nodes (src/cache.jl:682-690)."""
+    layout = EDGEGRAD
+
+    def __init__(self, grid, data=None, device=False):
+        ps, ds_ = grid.layout_shape(L.NODES_PRIMAL), grid.layout_shape(L.NODES_DUAL)
+        self.shapes = (ps, ds_, ds_, ps)
+        sizes = [s[0] * s[1] for s in self.shapes]
+        self.offsets = np.concatenate([[0], np.cumsum(sizes)])
+        super().__init__(_alloc(int(self.offsets[-1]), device) if data is None else data)
+
+    def component(self, i):
+        return self.numpy()[self.offsets[i]:self.offsets[i + 1]].reshape(self.shapes[i], order="F")
+
+    def set_components(self, comps):
+        return self.set(np.concatenate([np.asarray(c).ravel(order="F") for c in comps]))
+
+
+class SurfaceVectorCache(SurfaceScalarCache):
+    """`SurfaceVectorCache(body, g; ...)`: surface data are VectorData, grid data
+    Edges{Primal}; the plan (tables of all four layouts, Ghat) is the same object
+    kind as for the scalar cache."""
+    kind = "vector"
+
+    def zeros_grid(self):
+        return Edges(self.g, device=self.device)
+
+    def zeros_gridgrad(self):
+        return EdgeGradient(self.g, device=self.device)
+
+    def zeros_griddiv(self):
+        return Nodes(Primal, self.g, device=self.device)
+
+    def zeros_surface(self):
+        return VectorData(self.N, device=self.device)
+
+    def zeros_surfacescalar(self):
+        return ScalarData(self.N, device=self.device)
+
+    def zeros_surfacetensor(self):
+        return TensorData(self.N, device=self.device)
+
+
+SurfaceScalarCache.kind = "scalar"
+
+
+def _is_vector(cache):
+    return getattr(cache, "kind", "scalar") == "vector"
+
+
+def _need_vector(cache, what):
+    if not _is_vector(cache):
+        raise MethodError(f"{what}: only defined for a SurfaceVectorCache")
+
+
+_s_regularize_normal, _s_normal_interpolate = regularize_normal, normal_interpolate
+_s_regularize_normal_cross, _s_normal_cross_interpolate = regularize_normal_cross, normal_cross_interpolate
+_s_divergence, _s_grad = divergence, grad
+_s_surface_divergence, _s_surface_grad, _s_surface_curl = surface_divergence, surface_grad, surface_curl
+_s_mask = mask
+_s_create_RTLinvR, _s_create_CLinvCT, _s_create_GLinvD, _s_create_nRTRn = (
+    create_RTLinvR, create_CLinvCT, create_GLinvD, create_nRTRn)
+
+
+def _tensor_s2g(mode, q, f, cache, what):
+    _need_vector(cache, what)
+    _expect(q, EdgeGradient, what)
+    _expect(f, VectorData, what)
+    cache._check_n(f, 2 * cache.N, what)
+    L.check(cache._lib.ilm_regularize_normal_tensor(cache._plan, mode, _ptr(f.data), _ptr(q.data)))
+    return q
+
+
+def _tensor_g2s(mode, vn, q, cache, what):
+    _need_vector(cache, what)
+    _expect(q, EdgeGradient, what)
+    _expect(vn, VectorData, what)
+    L.check(cache._lib.ilm_normal_interpolate_tensor(cache._plan, mode, _ptr(q.data), _ptr(vn.data)))
+    return vn
+
+
+def regularize_normal(q, f, cache):
+    """regularize_normal!(q::Edges, f::ScalarData) (:98) / (qt::EdgeGradient, v::VectorData) (:113)"""
+    if isinstance(q, EdgeGradient):
+        return _tensor_s2g(0, q, f, cache, "regularize_normal")
+    return _s_regularize_normal(q, f, cache)
+
+
+def regularize_normal_symm(q, f, cache):
+    """regularize_normal_symm!(qt::EdgeGradient, v::VectorData) (:123)"""
+    return _tensor_s2g(1, q, f, cache, "regularize_normal_symm")
+
+
+def normal_interpolate(vn, q, cache):
+    """normal_interpolate!(vn::ScalarData, q::Edges) (:228) / (tau::VectorData, A::EdgeGradient) (:242)"""
+    if isinstance(q, EdgeGradient):
+        return _tensor_g2s(0, vn, q, cache, "normal_interpolate")
+    return _s_normal_interpolate(vn, q, cache)
+
+
+def normal_interpolate_symm(vn, q, cache):
+    """normal_interpolate_symm!(tau::VectorData, A::EdgeGradient) (:252)"""
+    return _tensor_g2s(1, vn, q, cache, "normal_interpolate_symm")
+
+
+def regularize_normal_cross(q, f, cache):
+    """regularize_normal_cross!(q::Edges, f::ScalarData) (:150) / (w::Nodes{Dual}, vs::VectorData) (:172)"""
+    if isinstance(q, Nodes):
+        _need_vector(cache, "regularize_normal_cross")
+        _expect_nodes(q, Dual, "regularize_normal_cross")
+        _expect(f, VectorData, "regularize_normal_cross")
+        L.check(cache._lib.ilm_regularize_normal_vs(cache._plan, 0, _ptr(f.data), _ptr(q.data)))
+        return q
+    return _s_regularize_normal_cross(q, f, cache)
+
+
+def regularize_normal_dot(a, b, cache):
+    """regularize_normal_dot!(f::Nodes{Primal}, vs::VectorData) (:188) / (v::Edges, taus::TensorData) (:209)"""
+    if isinstance(a, Edges):
+        _need_vector(cache, "regularize_normal_dot")
+        _expect(b, TensorData, "regularize_normal_dot")
+        L.check(cache._lib.ilm_regularize_normal_dot_tensor(cache._plan, _ptr(b.data), _ptr(a.data)))
+        return a
+    _expect_nodes(a, Primal, "regularize_normal_dot")
+    _expect(b, VectorData, "regularize_normal_dot")
+    L.check(cache._lib.ilm_regularize_normal_vs(cache._plan, 1, _ptr(b.data), _ptr(a.data)))
+    return a
+
+
+def normal_cross_interpolate(a, b, cache):
+    """normal_cross_interpolate!(wn::ScalarData, v::Edges) (:270) / (vs::VectorData, s::Nodes{Dual}) (:303)"""
+    if isinstance(a, VectorData):
+        _need_vector(cache, "normal_cross_interpolate")
+        _expect_nodes(b, Dual, "normal_cross_interpolate")
+        L.check(cache._lib.ilm_normal_interpolate_vs(cache._plan, 0, _ptr(b.data), _ptr(a.data)))
+        return a
+    return _s_normal_cross_interpolate(a, b, cache)
+
+
+def normal_dot_interpolate(a, b, cache):
+    """normal_dot_interpolate!(vs::VectorData, f::Nodes{Primal}) (:320) / (taus::TensorData, v::Edges) (:335)"""
+    if isinstance(a, TensorData):
+        _need_vector(cache, "normal_dot_interpolate")
+        _expect(b, Edges, "normal_dot_interpolate")
+        L.check(cache._lib.ilm_normal_dot_interpolate_tensor(cache._plan, _ptr(b.data), _ptr(a.data)))
+        return a
+    _expect(a, VectorData, "normal_dot_interpolate")
+    _expect_nodes(b, Primal, "normal_dot_interpolate")
+    L.check(cache._lib.ilm_normal_interpolate_vs(cache._plan, 1, _ptr(b.data), _ptr(a.data)))
+    return a
+
+
+def divergence(p, q, cache):
+    """divergence!(p::Nodes{Primal}, q::Edges) / divergence!(p::Edges, q::EdgeGradient)"""
+    if isinstance(q, EdgeGradient):
+        _expect(p, Edges, "divergence")
+        L.check(cache._lib.ilm_divergence_tensor(cache._plan, _ptr(q.data), _ptr(p.data)))
+        return p
+    return _s_divergence(p, q, cache)
+
+
+def grad(q, p, cache):
+    """grad!(q::Edges, p::Nodes{Primal}) (src/grid_operators.jl:45) / grad!(q::EdgeGradient, p::Edges) (:61)"""
+    if isinstance(q, EdgeGradient):
+        _expect(p, Edges, "grad")
+        L.check(cache._lib.ilm_grad_tensor(cache._plan, _ptr(p.data), _ptr(q.data)))
+        return q
+    return _s_grad(q, p, cache)
+
+
+def surface_divergence(theta, f, cache):
+    """surface_divergence!(theta::Nodes{Primal}, f::ScalarData) (:530) / (v::Edges, dv::VectorData) (:559)"""
+    if isinstance(theta, Edges):
+        _need_vector(cache, "surface_divergence")
+        _expect(f, VectorData, "surface_divergence")
+        L.check(cache._lib.ilm_vsurface_divergence(cache._plan, 0, _ptr(f.data), _ptr(theta.data)))
+        return theta
+    return _s_surface_divergence(theta, f, cache)
+
+
+def surface_divergence_symm(theta, f, cache):
+    """surface_divergence_symm!(v::Edges, dv::VectorData) (:570)"""
+    _need_vector(cache, "surface_divergence_symm")
+    _expect(theta, Edges, "surface_divergence_symm")
+    _expect(f, VectorData, "surface_divergence_symm")
+    L.check(cache._lib.ilm_vsurface_divergence(cache._plan, 1, _ptr(f.data), _ptr(theta.data)))
+    return theta
+
+
+def surface_grad(vn, phi, cache):
+    """surface_grad!(vn::ScalarData, phi::Nodes{Primal}) (:604) / (tau::VectorData, v::Edges) (:632)"""
+    if isinstance(phi, Edges):
+        _need_vector(cache, "surface_grad")
+        _expect(vn, VectorData, "surface_grad")
+        L.check(cache._lib.ilm_vsurface_grad(cache._plan, 0, _ptr(phi.data), _ptr(vn.data)))
+        return vn
+    return _s_surface_grad(vn, phi, cache)
+
+
+def surface_grad_symm(vn, phi, cache):
+    """surface_grad_symm!(tau::VectorData, v::Edges) (:643)"""
+    _need_vector(cache, "surface_grad_symm")
+    _expect(vn, VectorData, "surface_grad_symm")
+    _expect(phi, Edges, "surface_grad_symm")
+    L.check(cache._lib.ilm_vsurface_grad(cache._plan, 1, _ptr(phi.data), _ptr(vn.data)))
+    return vn
+
+
+def surface_curl(a, b, cache):
+    """surface_curl! in its four forms (:357, :388, :412, :443)"""
+    if isinstance(b, VectorData):
+        _need_vector(cache, "surface_curl")
+        _expect_nodes(a, Dual, "surface_curl")
+        L.check(cache._lib.ilm_vsurface_curl_s2n(cache._plan, _ptr(b.data), _ptr(a.data)))
+        return a
+    if isinstance(a, VectorData):
+        _need_vector(cache, "surface_curl")
+        _expect_nodes(b, Dual, "surface_curl")
+        L.check(cache._lib.ilm_vsurface_curl_n2s(cache._plan, _ptr(b.data), _ptr(a.data)))
+        return a
+    return _s_surface_curl(a, b, cache)
+
+
+def mask(cache):
+    """mask(cache): Nodes{Primal} for a scalar cache, Edges for a vector cache (:737)."""
+    if _is_vector(cache):
+        if cache.scaling != GridScaling:
+            raise MethodError("mask is only defined for GridScaling caches")
+        m = cache.zeros_grid()
+        L.check(cache._lib.ilm_mask_edges(cache._plan, _ptr(m.data)))
+        return m
+    return _s_mask(cache)
+
+
+def _vmatrix(cache, which, scale, cols):
+    M = 2 * cache.N
+    c0, c1 = (0, M) if cols is None else cols
+    if cache.device:
+        import torch
+        buf = torch.zeros(M * (c1 - c0), dtype=torch.float64, device="cuda")
+    else:
+        buf = np.zeros(M * (c1 - c0), dtype=np.float64)
+    L.check(cache._lib.ilm_create_schur_vector(cache._plan, which, float(scale), int(c0), int(c1), _ptr(buf)))
+    return _as_matrix(buf, M, c1 - c0)
+
+
+def create_RTLinvR(cache, scale=1.0, cols=None):
+    """create_RTLinvR (src/matrix_operators.jl:9-30): N x N (scalar cache) or 2N x 2N (vector cache)."""
+    return _vmatrix(cache, 0, scale, cols) if _is_vector(cache) else _s_create_RTLinvR(cache, scale, cols)
+
+
+def create_CLinvCT(cache, scale=1.0, cols=None):
+    """create_CLinvCT (:40-61) on the cache's primary point data type."""
+    return _vmatrix(cache, 1, scale, cols) if _is_vector(cache) else _s_create_CLinvCT(cache, scale, cols)
+
+
+def create_CLinvCT_scalar(cache, scale=1.0, cols=None):
+    """create_CLinvCT_scalar (:71-92): ScalarData form, vector caches only."""
+    _need_vector(cache, "create_CLinvCT_scalar")
+    return _s_create_CLinvCT(cache, scale, cols)
+
+
+def create_CL2invCT(cache, scale=1.0, cols=None):
+    """create_CL2invCT (:102-125): -C_s L^-2 C_s^T."""
+    _need_vector(cache, "create_CL2invCT")
+    return _vmatrix(cache, 2, scale, cols)
+
+
+def create_GLinvD(cache, scale=1.0, cols=None):
+    """create_GLinvD (:135-155)."""
+    return _vmatrix(cache, 3, scale, cols) if _is_vector(cache) else _s_create_GLinvD(cache, scale, cols)
+
+
+def create_GLinvD_symm(cache, scale=1.0, cols=None):
+    """create_GLinvD_symm (:165-185)."""
+    _need_vector(cache, "create_GLinvD_symm")
+    return _vmatrix(cache, 4, scale, cols)
+
+
+def create_nRTRn(cache, scale=1.0):
+    """create_nRTRn (:225-244)."""
+    if not _is_vector(cache):
+        return _s_create_nRTRn(cache, scale)
+    M = 2 * cache.N
+    buf = _matrix(cache, 4 * cache.N) if cache.N else _matrix(cache, 0)
+    L.check(cache._lib.ilm_create_nRTRn_vector(cache._plan, float(scale), _ptr(buf)))
+    return _as_matrix(buf, M, M)

@@ -67,10 +67,11 @@ int Io::finish() {
 static int upload_points(ilm_plan* p, int N, const double* x, const double* y, const double* nx, const double* ny,
                          const double* ds) {
     if (N > p->ncap) {
-        cudaFree(p->x); cudaFree(p->y); cudaFree(p->nx); cudaFree(p->ny); cudaFree(p->ds); cudaFree(p->s_a);
+        cudaFree(p->x); cudaFree(p->y); cudaFree(p->nx); cudaFree(p->ny); cudaFree(p->ds); cudaFree(p->s_a); cudaFree(p->s_b);
         const size_t b = (size_t)N * sizeof(double);
         ILM_CUDA(cudaMalloc(&p->x, b)); ILM_CUDA(cudaMalloc(&p->y, b)); ILM_CUDA(cudaMalloc(&p->nx, b));
         ILM_CUDA(cudaMalloc(&p->ny, b)); ILM_CUDA(cudaMalloc(&p->ds, b)); ILM_CUDA(cudaMalloc(&p->s_a, 4 * b));
+        ILM_CUDA(cudaMalloc(&p->s_b, 4 * b));
         p->ncap = N;
     }
     p->N = N;
@@ -213,7 +214,7 @@ extern "C" void ilm_plan_destroy(ilm_plan* p) {
     for (auto& t : p->tab) free_table(t);
     conv_free(p);
     cudaFree(p->x); cudaFree(p->y); cudaFree(p->nx); cudaFree(p->ny); cudaFree(p->ds);
-    cudaFree(p->g_edges); cudaFree(p->g_a); cudaFree(p->g_b); cudaFree(p->s_a);
+    cudaFree(p->g_edges); cudaFree(p->g_a); cudaFree(p->g_b); cudaFree(p->s_a); cudaFree(p->s_b); cudaFree(p->g_tensor);
     for (void* s : p->staging) cudaFree(s);
     delete p;
 }
@@ -225,6 +226,8 @@ extern "C" int ilm_plan_sync(ilm_plan* p) {
 }
 extern "C" int ilm_plan_npoints(const ilm_plan* p) { return p ? p->N : -1; }
 extern "C" int64_t ilm_layout_size(const ilm_plan* p, int layout) {
+    if (p && layout == ILM_EDGEGRAD)
+        return 2 * (int64_t)layout_info(ILM_NODES_PRIMAL, p->g.NX, p->g.NY).n() + 2 * (int64_t)p->g.NX * p->g.NY;
     if (!p || layout < 0 || layout > ILM_EDGES) return -1;
     return (int64_t)n_layout(p, layout);
 }

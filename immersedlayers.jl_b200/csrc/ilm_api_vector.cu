@@ -1,0 +1,329 @@
+// ilm_api_vector.cu -- C ABI of the vector-data cache (SurfaceVectorCache,
+// src/cache.jl:184-202): TensorData / EdgeGradient operators, the vector forms
+// of the surface-grid composites and the 2N x 2N Schur builders
+// (src/surface_operators.jl:113-138,172-215,242-343,388-398,443-452,559-664;
+// src/matrix_operators.jl:9-30,40-61,102-185,225-244).
+#include <algorithm>
+
+#include "ilm_internal.h"
+
+using namespace ilm;
+
+namespace {
+
+struct Sizes {
+    size_t Pn, Pd, nu, nv, ne, ng;
+    explicit Sizes(const ilm_plan* p) {
+        const int NX = p->g.NX, NY = p->g.NY;
+        Pn = (size_t)(NX - 1) * (NY - 1); Pd = (size_t)NX * NY;
+        nu = (size_t)NX * (NY - 1); nv = (size_t)(NX - 1) * NY;
+        ne = nu + nv; ng = 2 * Pn + 2 * Pd;
+    }
+};
+
+double deriv_div(const ilm_plan* p) { return p->scaling == ILM_GRID_SCALING ? p->g.dx : 1.0; }
+
+int need_tensor_scratch(ilm_plan* p) {
+    if (!p->g_tensor) ILM_CUDA(cudaMalloc(&p->g_tensor, Sizes(p).ng * sizeof(double)));
+    return ILM_OK;
+}
+
+// EdgeGradient <- TensorData (4 tables: primal, dual, dual, primal)
+int regularize_tensor(ilm_plan* p, const double* T, double* eg) {
+    const Sizes z(p);
+    const int N = p->N;
+    ILM_TRY(launch_regularize(p, p->tab[ILM_NODES_PRIMAL], T, nullptr, 1.0, eg, true));
+    ILM_TRY(launch_regularize(p, p->tab[ILM_NODES_DUAL], T + N, nullptr, 1.0, eg + z.Pn, true));
+    ILM_TRY(launch_regularize(p, p->tab[ILM_NODES_DUAL], T + 2 * (size_t)N, nullptr, 1.0, eg + z.Pn + z.Pd, true));
+    ILM_TRY(launch_regularize(p, p->tab[ILM_NODES_PRIMAL], T + 3 * (size_t)N, nullptr, 1.0, eg + z.Pn + 2 * z.Pd, true));
+    return ILM_OK;
+}
+int interpolate_tensor(ilm_plan* p, const double* eg, double* T) {
+    const Sizes z(p);
+    const int N = p->N;
+    ILM_TRY(launch_interpolate(p, p->tab[ILM_NODES_PRIMAL], eg, T));
+    ILM_TRY(launch_interpolate(p, p->tab[ILM_NODES_DUAL], eg + z.Pn, T + N));
+    ILM_TRY(launch_interpolate(p, p->tab[ILM_NODES_DUAL], eg + z.Pn + z.Pd, T + 2 * (size_t)N));
+    ILM_TRY(launch_interpolate(p, p->tab[ILM_NODES_PRIMAL], eg + z.Pn + 2 * z.Pd, T + 3 * (size_t)N));
+    return ILM_OK;
+}
+int regularize_edges(ilm_plan* p, const double* v, double* edges) {
+    ILM_TRY(launch_regularize(p, p->tab[ILM_XEDGES], v, nullptr, 1.0, edges, true));
+    return launch_regularize(p, p->tab[ILM_YEDGES], v + p->N, nullptr, 1.0, edges + Sizes(p).nu, true);
+}
+int interpolate_edges(ilm_plan* p, const double* edges, double* v) {
+    ILM_TRY(launch_interpolate(p, p->tab[ILM_XEDGES], edges, v));
+    return launch_interpolate(p, p->tab[ILM_YEDGES], edges + Sizes(p).nu, v + p->N);
+}
+
+// device composites (inputs/outputs are device pointers)
+int regularize_normal_tensor_dev(ilm_plan* p, int mode, const double* v, double* eg) {
+    ILM_TRY(launch_tensor_from_vector(p, mode, v, p->s_b));
+    return regularize_tensor(p, p->s_b, eg);
+}
+int normal_interpolate_tensor_dev(ilm_plan* p, int mode, const double* eg, double* v, double div) {
+    ILM_TRY(interpolate_tensor(p, eg, p->s_b));
+    return launch_tensor_dot(p, mode, p->s_b, div, v);
+}
+int vsurface_divergence_dev(ilm_plan* p, int mode, const double* v, double* edges) {
+    ILM_TRY(need_tensor_scratch(p));
+    ILM_TRY(regularize_normal_tensor_dev(p, mode, v, p->g_tensor));
+    return launch_div_tensor(p, p->g_tensor, edges, deriv_div(p));
+}
+int vsurface_grad_dev(ilm_plan* p, int mode, const double* edges, double* v) {
+    ILM_TRY(need_tensor_scratch(p));
+    ILM_TRY(launch_grad_tensor(p, edges, p->g_tensor, 1.0));
+    return normal_interpolate_tensor_dev(p, mode, p->g_tensor, v, deriv_div(p));
+}
+int vsurface_curl_s2n_dev(ilm_plan* p, const double* v, double* dual) {
+    ILM_TRY(regularize_edges(p, v, p->g_edges));
+    return launch_curl_e2n(p, p->g_edges, p->g_edges + Sizes(p).nu, dual, deriv_div(p));
+}
+__global__ void k_div_scalar(double* __restrict__ w, int n, double div) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = w[i] / div;
+}
+int vsurface_curl_n2s_dev(ilm_plan* p, const double* dual, double* v) {
+    ILM_TRY(launch_curl_n2e(p, dual, p->g_edges, p->g_edges + Sizes(p).nu, 1.0));
+    ILM_TRY(interpolate_edges(p, p->g_edges, v));
+    if (p->N && deriv_div(p) != 1.0) {
+        k_div_scalar<<<(2 * p->N + 127) / 128, 128, 0, p->stream>>>(v, 2 * p->N, deriv_div(p));
+        ILM_CUDA(cudaGetLastError());
+        p->launches++;
+    }
+    return ILM_OK;
+}
+
+__global__ void k_unit2(double* __restrict__ s, int n, int col) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) s[i] = (i == col) ? 1.0 : 0.0;
+}
+
+}  // namespace
+
+#define ILM_VPLAN(p)                                           \
+    do {                                                       \
+        if (!(p)) { set_error("null plan"); return ILM_EINVAL; } \
+        cudaSetDevice((p)->device);                            \
+    } while (0)
+#define ILM_TMODE(m) \
+    if ((m) != ILM_TENSOR_NORMAL && (m) != ILM_TENSOR_SYMM) { set_error("bad tensor mode"); return ILM_EINVAL; }
+
+extern "C" int ilm_regularize_normal_tensor(ilm_plan* p, int mode, const double* v, double* eg) {
+    ILM_VPLAN(p);
+    ILM_TMODE(mode);
+    Io io(p);
+    const double* dv = io.in(v, 2 * (size_t)p->N);
+    double* de = io.out(eg, Sizes(p).ng);
+    if (io.status) return io.status;
+    ILM_TRY(regularize_normal_tensor_dev(p, mode, dv, de));
+    return io.finish();
+}
+
+extern "C" int ilm_normal_interpolate_tensor(ilm_plan* p, int mode, const double* eg, double* v) {
+    ILM_VPLAN(p);
+    ILM_TMODE(mode);
+    Io io(p);
+    const double* de = io.in(eg, Sizes(p).ng);
+    double* dv = io.out(v, 2 * (size_t)p->N);
+    if (io.status) return io.status;
+    ILM_TRY(normal_interpolate_tensor_dev(p, mode, de, dv, 1.0));
+    return io.finish();
+}
+
+extern "C" int ilm_regularize_normal_vs(ilm_plan* p, int op, const double* v, double* nodes) {
+    ILM_VPLAN(p);
+    if (op != ILM_VS_CROSS && op != ILM_VS_DOT) { set_error("bad op"); return ILM_EINVAL; }
+    const Sizes z(p);
+    Io io(p);
+    const double* dv = io.in(v, 2 * (size_t)p->N);
+    double* dn = io.out(nodes, op == ILM_VS_CROSS ? z.Pd : z.Pn);
+    if (io.status) return io.status;
+    ILM_TRY(launch_vec_pointwise(p, op == ILM_VS_CROSS ? 0 : 1, dv, p->s_b));
+    ILM_TRY(launch_regularize(p, p->tab[op == ILM_VS_CROSS ? ILM_NODES_DUAL : ILM_NODES_PRIMAL], p->s_b, nullptr, 1.0, dn, true));
+    return io.finish();
+}
+
+extern "C" int ilm_normal_interpolate_vs(ilm_plan* p, int op, const double* nodes, double* v) {
+    ILM_VPLAN(p);
+    if (op != ILM_VS_CROSS && op != ILM_VS_DOT) { set_error("bad op"); return ILM_EINVAL; }
+    const Sizes z(p);
+    Io io(p);
+    const double* dn = io.in(nodes, op == ILM_VS_CROSS ? z.Pd : z.Pn);
+    double* dv = io.out(v, 2 * (size_t)p->N);
+    if (io.status) return io.status;
+    ILM_TRY(launch_interpolate(p, p->tab[op == ILM_VS_CROSS ? ILM_NODES_DUAL : ILM_NODES_PRIMAL], dn, p->s_b));
+    ILM_TRY(launch_vec_pointwise(p, op == ILM_VS_CROSS ? 2 : 3, p->s_b, dv));
+    return io.finish();
+}
+
+extern "C" int ilm_regularize_normal_dot_tensor(ilm_plan* p, const double* tau, double* edges) {
+    ILM_VPLAN(p);
+    Io io(p);
+    const double* dt = io.in(tau, 4 * (size_t)p->N);
+    double* de = io.out(edges, Sizes(p).ne);
+    if (io.status) return io.status;
+    ILM_TRY(launch_tensor_dot(p, ILM_TENSOR_NORMAL, dt, 1.0, p->s_b));
+    ILM_TRY(regularize_edges(p, p->s_b, de));
+    return io.finish();
+}
+
+extern "C" int ilm_normal_dot_interpolate_tensor(ilm_plan* p, const double* edges, double* tau) {
+    ILM_VPLAN(p);
+    Io io(p);
+    const double* de = io.in(edges, Sizes(p).ne);
+    double* dt = io.out(tau, 4 * (size_t)p->N);
+    if (io.status) return io.status;
+    ILM_TRY(interpolate_edges(p, de, p->s_b));
+    ILM_TRY(launch_tensor_from_vector(p, ILM_TENSOR_NORMAL, p->s_b, dt));
+    return io.finish();
+}
+
+extern "C" int ilm_grad_tensor(ilm_plan* p, const double* edges, double* eg) {
+    ILM_VPLAN(p);
+    Io io(p);
+    const double* de = io.in(edges, Sizes(p).ne);
+    double* dg = io.out(eg, Sizes(p).ng);
+    if (io.status) return io.status;
+    ILM_TRY(launch_grad_tensor(p, de, dg, deriv_div(p)));
+    return io.finish();
+}
+
+extern "C" int ilm_divergence_tensor(ilm_plan* p, const double* eg, double* edges) {
+    ILM_VPLAN(p);
+    Io io(p);
+    const double* dg = io.in(eg, Sizes(p).ng);
+    double* de = io.out(edges, Sizes(p).ne);
+    if (io.status) return io.status;
+    ILM_TRY(launch_div_tensor(p, dg, de, deriv_div(p)));
+    return io.finish();
+}
+
+extern "C" int ilm_vsurface_divergence(ilm_plan* p, int mode, const double* v, double* edges) {
+    ILM_VPLAN(p);
+    ILM_TMODE(mode);
+    Io io(p);
+    const double* dv = io.in(v, 2 * (size_t)p->N);
+    double* de = io.out(edges, Sizes(p).ne);
+    if (io.status) return io.status;
+    ILM_TRY(vsurface_divergence_dev(p, mode, dv, de));
+    return io.finish();
+}
+
+extern "C" int ilm_vsurface_grad(ilm_plan* p, int mode, const double* edges, double* v) {
+    ILM_VPLAN(p);
+    ILM_TMODE(mode);
+    Io io(p);
+    const double* de = io.in(edges, Sizes(p).ne);
+    double* dv = io.out(v, 2 * (size_t)p->N);
+    if (io.status) return io.status;
+    ILM_TRY(vsurface_grad_dev(p, mode, de, dv));
+    return io.finish();
+}
+
+extern "C" int ilm_vsurface_curl_s2n(ilm_plan* p, const double* v, double* dual) {
+    ILM_VPLAN(p);
+    Io io(p);
+    const double* dv = io.in(v, 2 * (size_t)p->N);
+    double* dn = io.out(dual, Sizes(p).Pd);
+    if (io.status) return io.status;
+    ILM_TRY(vsurface_curl_s2n_dev(p, dv, dn));
+    return io.finish();
+}
+
+extern "C" int ilm_vsurface_curl_n2s(ilm_plan* p, const double* dual, double* v) {
+    ILM_VPLAN(p);
+    Io io(p);
+    const double* dn = io.in(dual, Sizes(p).Pd);
+    double* dv = io.out(v, 2 * (size_t)p->N);
+    if (io.status) return io.status;
+    ILM_TRY(vsurface_curl_n2s_dev(p, dn, dv));
+    return io.finish();
+}
+
+extern "C" int ilm_mask_edges(ilm_plan* p, double* edges) {
+    ILM_VPLAN(p);
+    const Sizes z(p);
+    Io io(p);
+    double* de = io.out(edges, z.ne);
+    if (io.status) return io.status;
+    if (p->N == 0) {
+        ILM_TRY(launch_fill(p, de, z.ne, 1.0));
+        return io.finish();
+    }
+    ILM_TRY(launch_fill(p, p->s_a, 2 * (size_t)p->N, 1.0));
+    ILM_TRY(vsurface_divergence_dev(p, ILM_TENSOR_NORMAL, p->s_a, de));
+    ILM_TRY(conv_apply(p, 0, FieldRef{de, p->g.NX, p->g.NY - 1}, FieldRef{de + z.nu, p->g.NX - 1, p->g.NY}));
+    ILM_TRY(launch_scale(p, de, z.ne, -1.0));
+    return io.finish();
+}
+
+extern "C" int ilm_create_schur_vector(ilm_plan* p, int which, double scale, int col_begin, int col_end, double* A) {
+    ILM_VPLAN(p);
+    const int N = p->N, M = 2 * N;
+    if (which < ILM_V_RTLINVR || which > ILM_V_GLINVD_SYMM) { set_error("ilm_create_schur_vector: unknown matrix"); return ILM_EINVAL; }
+    if (col_begin < 0 || col_end > M || col_begin > col_end) { set_error("ilm_create_schur_vector: bad column range"); return ILM_ESIZE; }
+    const int ncols = col_end - col_begin;
+    if (N == 0 || ncols == 0) return ILM_OK;
+    const Sizes z(p);
+    Io io(p);
+    double* dA = io.out(A, (size_t)M * ncols);
+    if (io.status) return io.status;
+    double* unit = p->s_a;            // 2N
+    double* sout = p->s_a + M;        // 2N
+    const int mode = which == ILM_V_GLINVD_SYMM ? ILM_TENSOR_SYMM : ILM_TENSOR_NORMAL;
+    const bool curl = which == ILM_V_CLINVCT || which == ILM_V_CL2INVCT;
+    // grid scratch: Nodes{Dual} right-hand sides (curl builders) live in g_a; Edges-valued ones in g_edges,
+    // whose u and v components ride one complex transform
+    double* fu = p->g_a;
+    for (int c = col_begin; c < col_end; ++c) {
+        k_unit2<<<(M + 127) / 128, 128, 0, p->stream>>>(unit, M, c);
+        ILM_CUDA(cudaGetLastError());
+        p->launches++;
+        if (curl) {
+            // C_s^T v = C^T R_f v / dx -> Nodes{Dual} in g_a
+            ILM_TRY(vsurface_curl_s2n_dev(p, unit, fu));
+            const int reps = which == ILM_V_CL2INVCT ? 2 : 1;
+            for (int r = 0; r < reps; ++r)
+                ILM_TRY(conv_apply(p, 0, FieldRef{fu, p->g.NX, p->g.NY}, FieldRef{nullptr, 0, 0}));
+            ILM_TRY(vsurface_curl_n2s_dev(p, fu, sout));
+        } else {
+            // Edges-valued field: stage through g_edges, then split into (fu, fv) for the pair transform
+            if (which == ILM_V_RTLINVR) ILM_TRY(regularize_edges(p, unit, p->g_edges));
+            else ILM_TRY(vsurface_divergence_dev(p, mode, unit, p->g_edges));
+            ILM_TRY(conv_apply(p, 0, FieldRef{p->g_edges, p->g.NX, p->g.NY - 1},
+                               FieldRef{p->g_edges + z.nu, p->g.NX - 1, p->g.NY}));
+            if (which == ILM_V_RTLINVR) {
+                ILM_TRY(interpolate_edges(p, p->g_edges, sout));
+            } else {
+                // surface_grad reads Edges and uses g_tensor as scratch; g_edges is the input here
+                ILM_TRY(need_tensor_scratch(p));
+                ILM_TRY(launch_grad_tensor(p, p->g_edges, p->g_tensor, 1.0));
+                ILM_TRY(normal_interpolate_tensor_dev(p, mode, p->g_tensor, sout, deriv_div(p)));
+            }
+        }
+        ILM_TRY(launch_scale_store_column(p, sout, dA + (size_t)(c - col_begin) * M, M, -scale));
+    }
+    return io.finish();
+}
+
+extern "C" int ilm_create_nRTRn_vector(ilm_plan* p, double scale, double* A) {
+    ILM_VPLAN(p);
+    const int N = p->N, M = 2 * N;
+    if (N == 0) return ILM_OK;
+    Io io(p);
+    double* dA = io.out(A, (size_t)M * M);
+    if (io.status) return io.status;
+    ILM_TRY(need_tensor_scratch(p));
+    double* unit = p->s_a;
+    double* sout = p->s_a + M;
+    for (int c = 0; c < M; ++c) {
+        k_unit2<<<(M + 127) / 128, 128, 0, p->stream>>>(unit, M, c);
+        ILM_CUDA(cudaGetLastError());
+        p->launches++;
+        ILM_TRY(regularize_normal_tensor_dev(p, ILM_TENSOR_NORMAL, unit, p->g_tensor));
+        ILM_TRY(normal_interpolate_tensor_dev(p, ILM_TENSOR_NORMAL, p->g_tensor, sout, 1.0));
+        ILM_TRY(launch_scale_store_column(p, sout, dA + (size_t)c * M, M, scale));
+    }
+    return io.finish();
+}

@@ -83,6 +83,8 @@ struct ilm_plan {
     double* g_a = nullptr;          // NX*NY scratch field (gdata/gcurl cache)
     double* g_b = nullptr;          // NX*NY scratch field (second Schur column)
     double* s_a = nullptr;          // 4N surface scratch
+    double* s_b = nullptr;          // 4N surface scratch (TensorData temporaries)
+    double* g_tensor = nullptr;     // EdgeGradient scratch (allocated on first vector-cache use)
     std::vector<void*> staging;     // device staging for host pointers
     std::vector<size_t> staging_cap;
 };
@@ -126,6 +128,12 @@ int launch_scale(ilm_plan* p, double* w, size_t n, double scale);
 int launch_lgf_prep(ilm_plan* p, const double* table, int ld, int NX, int NY, double c0, double* h);
 int launch_filter_rowsum(ilm_plan* p, DevTable& t);
 int launch_surface_filter(ilm_plan* p, const DevTable& t, double* C);
+// vector-cache pieces (TensorData = [dudx; dudy; dvdx; dvdy], EdgeGradient likewise)
+int launch_tensor_from_vector(ilm_plan* p, int mode, const double* v, double* T);
+int launch_tensor_dot(ilm_plan* p, int mode, const double* S, double div, double* out);
+int launch_vec_pointwise(ilm_plan* p, int op, const double* in, double* out);
+int launch_grad_tensor(ilm_plan* p, const double* edges, double* eg, double div);
+int launch_div_tensor(ilm_plan* p, const double* eg, double* edges, double div);
 
 // ---- tables (ilm_tables.cu, compiled without FMA contraction) -----------------
 int build_tables(ilm_plan* p);

@@ -396,3 +396,137 @@ int launch_lgf_prep(ilm_plan* p, const double* table, int ld, int NX, int NY, do
 }
 
 }  // namespace ilm
+
+// =====================================================================================
+// vector-cache operators: TensorData / EdgeGradient forms (src/surface_operators.jl:113-138,
+// 172-215, 242-343) and the Edges <-> EdgeGradient stencils (src/grid_operators.jl:61-71).
+// Tensor convention (parity unpinned): component (i,j) = (velocity
+// component, derivative direction): [dudx, dudy, dvdx, dvdy]; n (x) v -> v_i n_j; n . T -> sum_j n_j T_ij.
+// =====================================================================================
+namespace ilm {
+
+// T = n (x) v (mode 0) or n (x) v + (n (x) v)^T - (n.v) I (mode 1)
+__global__ void k_tensor_from_vector(int N, const double* __restrict__ nx, const double* __restrict__ ny,
+                                     const double* __restrict__ v, int mode, double* __restrict__ T) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const double n1 = nx[k], n2 = ny[k], vu = v[k], vv = v[N + k];
+    const double t0 = __dmul_rn(n1, vu), t1 = __dmul_rn(n2, vu), t2 = __dmul_rn(n1, vv), t3 = __dmul_rn(n2, vv);
+    if (mode == 0) {
+        T[k] = t0; T[N + k] = t1; T[2 * N + k] = t2; T[3 * N + k] = t3;
+    } else {
+        const double dot = __dadd_rn(t0, t3);
+        T[k] = __dsub_rn(__dadd_rn(t0, t0), dot);
+        T[N + k] = __dadd_rn(t1, t2);
+        T[2 * N + k] = __dadd_rn(t2, t1);
+        T[3 * N + k] = __dsub_rn(__dadd_rn(t3, t3), dot);
+    }
+}
+int launch_tensor_from_vector(ilm_plan* p, int mode, const double* v, double* T) {
+    if (p->N == 0) return ILM_OK;
+    k_tensor_from_vector<<<(p->N + 127) / 128, 128, 0, p->stream>>>(p->N, p->nx, p->ny, v, mode, T);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// t = n . S (mode 0) or n . (S + S^T - tr(S) I) (mode 1), then / div
+__global__ void k_tensor_dot(int N, const double* __restrict__ nx, const double* __restrict__ ny,
+                             const double* __restrict__ S, int mode, double div, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    double s0 = S[k], s1 = S[N + k], s2 = S[2 * N + k], s3 = S[3 * N + k];
+    if (mode == 1) {
+        const double tr = __dadd_rn(s0, s3), o = __dadd_rn(s2, s1);
+        s0 = __dsub_rn(__dadd_rn(s0, s0), tr);
+        s3 = __dsub_rn(__dadd_rn(s3, s3), tr);
+        s1 = o; s2 = o;
+    }
+    const double n1 = nx[k], n2 = ny[k];
+    out[k] = __dadd_rn(__dmul_rn(n1, s0), __dmul_rn(n2, s1)) / div;
+    out[N + k] = __dadd_rn(__dmul_rn(n1, s2), __dmul_rn(n2, s3)) / div;
+}
+int launch_tensor_dot(ilm_plan* p, int mode, const double* S, double div, double* out) {
+    if (p->N == 0) return ILM_OK;
+    k_tensor_dot<<<(p->N + 127) / 128, 128, 0, p->stream>>>(p->N, p->nx, p->ny, S, mode, div, out);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// op 0: s = n.u v.v - n.v v.u ; 1: s = n.u v.u + n.v v.v ; 2: v = (n.v s, -n.u s) ; 3: v = (n.u s, n.v s)
+__global__ void k_vec_pointwise(int N, const double* __restrict__ nx, const double* __restrict__ ny,
+                                const double* __restrict__ in, int op, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const double n1 = nx[k], n2 = ny[k];
+    if (op == 0) out[k] = __dsub_rn(__dmul_rn(n1, in[N + k]), __dmul_rn(n2, in[k]));
+    else if (op == 1) out[k] = __dadd_rn(__dmul_rn(n1, in[k]), __dmul_rn(n2, in[N + k]));
+    else if (op == 2) { out[k] = __dmul_rn(n2, in[k]); out[N + k] = -__dmul_rn(n1, in[k]); }
+    else { out[k] = __dmul_rn(n1, in[k]); out[N + k] = __dmul_rn(n2, in[k]); }
+}
+int launch_vec_pointwise(ilm_plan* p, int op, const double* in, double* out) {
+    if (p->N == 0) return ILM_OK;
+    k_vec_pointwise<<<(p->N + 127) / 128, 128, 0, p->stream>>>(p->N, p->nx, p->ny, in, op, out);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// grad!(EdgeGradient <- Edges): A.3
+__global__ void k_grad_tensor(int NX, int NY, const double* __restrict__ u, const double* __restrict__ v,
+                              double* __restrict__ dudx, double* __restrict__ dudy, double* __restrict__ dvdx,
+                              double* __restrict__ dvdy, double div) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= NX || y >= NY) return;
+    const int mp = NX - 1;
+    if (x < NX - 1 && y < NY - 1) {
+        dudx[(size_t)y * mp + x] = (u[(size_t)y * NX + x + 1] - u[(size_t)y * NX + x]) / div;
+        dvdy[(size_t)y * mp + x] = (v[(size_t)(y + 1) * mp + x] - v[(size_t)y * mp + x]) / div;
+    }
+    double a = 0.0, b = 0.0;
+    if (x >= 1 && x <= NX - 2 && y >= 1 && y <= NY - 2) {
+        a = (u[(size_t)y * NX + x] - u[(size_t)(y - 1) * NX + x]) / div;
+        b = (v[(size_t)y * mp + x] - v[(size_t)y * mp + x - 1]) / div;
+    }
+    dudy[(size_t)y * NX + x] = a;
+    dvdx[(size_t)y * NX + x] = b;
+}
+int launch_grad_tensor(ilm_plan* p, const double* edges, double* eg, double div) {
+    const int NX = p->g.NX, NY = p->g.NY;
+    const size_t Pn = (size_t)(NX - 1) * (NY - 1), Pd = (size_t)NX * NY, nu = (size_t)NX * (NY - 1);
+    k_grad_tensor<<<dim3((NX + 127) / 128, NY), 128, 0, p->stream>>>(NX, NY, edges, edges + nu, eg, eg + Pn, eg + Pn + Pd,
+                                                                     eg + Pn + 2 * Pd, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// divergence!(Edges <- EdgeGradient): A.3
+__global__ void k_div_tensor(int NX, int NY, const double* __restrict__ dudx, const double* __restrict__ dudy,
+                             const double* __restrict__ dvdx, const double* __restrict__ dvdy,
+                             double* __restrict__ u, double* __restrict__ v, double div) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= NX || y >= NY) return;
+    const int mp = NX - 1;
+    if (y < NY - 1) {
+        double val = 0.0;
+        if (x >= 1 && x <= NX - 2)
+            val = (((dudx[(size_t)y * mp + x] - dudx[(size_t)y * mp + x - 1]) + dudy[(size_t)(y + 1) * NX + x]) -
+                   dudy[(size_t)y * NX + x]) / div;
+        u[(size_t)y * NX + x] = val;
+    }
+    if (x < NX - 1) {
+        double val = 0.0;
+        if (y >= 1 && y <= NY - 2)
+            val = (((dvdx[(size_t)y * NX + x + 1] - dvdx[(size_t)y * NX + x]) + dvdy[(size_t)y * mp + x]) -
+                   dvdy[(size_t)(y - 1) * mp + x]) / div;
+        v[(size_t)y * mp + x] = val;
+    }
+}
+int launch_div_tensor(ilm_plan* p, const double* eg, double* edges, double div) {
+    const int NX = p->g.NX, NY = p->g.NY;
+    const size_t Pn = (size_t)(NX - 1) * (NY - 1), Pd = (size_t)NX * NY, nu = (size_t)NX * (NY - 1);
+    k_div_tensor<<<dim3((NX + 127) / 128, NY), 128, 0, p->stream>>>(NX, NY, eg, eg + Pn, eg + Pn + Pd, eg + Pn + 2 * Pd,
+                                                                    edges, edges + nu, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+}  // namespace ilm

@@ -147,6 +147,50 @@ int ilm_dense_factor(int n, double* A, int* ipiv, void* stream);
 int ilm_dense_solve(int n, const double* LU, const int* ipiv, int nrhs, double* B, void* stream);
 int ilm_dense_matvec_pow(int n, const double* C, int k, double* s, void* stream);
 
+/* ---- vector-data cache: SurfaceVectorCache (src/cache.jl:184-202) ----------
+ * The same plan serves both cache kinds (it holds the tables of all four
+ * layouts).  VectorData = [u; v] (2N); TensorData = [dudx; dudy; dvdx; dvdy]
+ * (4N); EdgeGradient{Primal,Dual} = [dudx; dudy; dvdx; dvdy] with dudx, dvdy on
+ * primal nodes and dudy, dvdx on dual nodes (layout ILM_EDGEGRAD).  Tensor
+ * component (i,j) = (velocity component, derivative direction); see DESIGN.md
+ * section 3 for the (unpinned) pointwise tensor conventions.                   */
+#define ILM_EDGEGRAD 5
+enum ilm_tensor_mode { ILM_TENSOR_NORMAL = 0, ILM_TENSOR_SYMM = 1 };
+/* regularize_normal!(EdgeGradient<-VectorData), regularize_normal_symm! (src/surface_operators.jl:113-138) */
+int ilm_regularize_normal_tensor(ilm_plan* plan, int mode, const double* v, double* edgegrad);
+/* normal_interpolate!(VectorData<-EdgeGradient), normal_interpolate_symm! (:242-267) */
+int ilm_normal_interpolate_tensor(ilm_plan* plan, int mode, const double* edgegrad, double* v);
+enum ilm_vs_op {
+    ILM_VS_CROSS = 0, /* Nodes{Dual}:   n x v  /  n x (psi e_z)   (:172-178, :303-310) */
+    ILM_VS_DOT = 1    /* Nodes{Primal}: n . v  /  n phi           (:188-200, :320-332) */
+};
+int ilm_regularize_normal_vs(ilm_plan* plan, int op, const double* v, double* nodes);
+int ilm_normal_interpolate_vs(ilm_plan* plan, int op, const double* nodes, double* v);
+/* regularize_normal_dot!(Edges<-TensorData) (:209-215), normal_dot_interpolate!(TensorData<-Edges) (:335-343) */
+int ilm_regularize_normal_dot_tensor(ilm_plan* plan, const double* tau, double* edges);
+int ilm_normal_dot_interpolate_tensor(ilm_plan* plan, const double* edges, double* tau);
+/* grad!(EdgeGradient<-Edges), divergence!(Edges<-EdgeGradient) (src/grid_operators.jl:61-71) */
+int ilm_grad_tensor(ilm_plan* plan, const double* edges, double* edgegrad);
+int ilm_divergence_tensor(ilm_plan* plan, const double* edgegrad, double* edges);
+/* surface_divergence!(Edges<-VectorData) / _symm (:559-591), surface_grad!(VectorData<-Edges) / _symm (:632-664) */
+int ilm_vsurface_divergence(ilm_plan* plan, int mode, const double* v, double* edges);
+int ilm_vsurface_grad(ilm_plan* plan, int mode, const double* edges, double* v);
+/* surface_curl!(Nodes{Dual}<-VectorData) (:388-398), surface_curl!(VectorData<-Nodes{Dual}) (:443-452) */
+int ilm_vsurface_curl_s2n(ilm_plan* plan, const double* v, double* nodes_dual);
+int ilm_vsurface_curl_n2s(ilm_plan* plan, const double* nodes_dual, double* v);
+/* _get_mask! with Edges grid data (vector cache) */
+int ilm_mask_edges(ilm_plan* plan, double* edges);
+/* Schur builders on VectorData: 2N x 2N, columns [col_begin, col_end) */
+enum ilm_schur_vector {
+    ILM_V_RTLINVR = 0,    /* create_RTLinvR      (src/matrix_operators.jl:9-30)    */
+    ILM_V_CLINVCT = 1,    /* create_CLinvCT      (:40-61)                          */
+    ILM_V_CL2INVCT = 2,   /* create_CL2invCT     (:102-125), two inverse Laplacians */
+    ILM_V_GLINVD = 3,     /* create_GLinvD       (:135-155)                        */
+    ILM_V_GLINVD_SYMM = 4 /* create_GLinvD_symm  (:165-185)                        */
+};
+int ilm_create_schur_vector(ilm_plan* plan, int which, double scale, int col_begin, int col_end, double* A);
+int ilm_create_nRTRn_vector(ilm_plan* plan, double scale, double* A);
+
 /* kernels launched by the three ilm_dense_* entry points since load (bench bookkeeping) */
 int64_t ilm_dense_launch_count(void);
 

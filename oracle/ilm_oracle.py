@@ -661,6 +661,156 @@ class ScalarCache:
         return np.asarray((Ef @ R).todense(), order="F")
 
 
+class VectorCache(ScalarCache):
+    """SurfaceVectorCache (src/cache.jl:184-202): R/E: VectorData <-> Edges{Primal};
+    Rsn/Esn: TensorData <-> EdgeGradient{Primal,Dual}; Rcurl/Ecurl: ScalarData <->
+    Nodes{Dual}; Rdiv/Ediv: ScalarData <-> Nodes{Primal}.  VectorData is (u, v);
+    TensorData / EdgeGradient are (dudx, dudy, dvdx, dvdy) with dudx, dvdy on primal
+    nodes and dudy, dvdx on dual nodes (src/cache.jl:682-690).
+
+    Tensor component convention (PARITY UNPINNED): component (i, j)
+    = (velocity component i, derivative direction j); pointwise_tensorproduct!(T, n, v)
+    gives T.d(v_i)/d(x_j) = v_i n_j and pointwise_dot!(t, n, T) gives t_i = sum_j n_j T_ij,
+    the pair that makes regularize_normal!/normal_interpolate! adjoint and D R_t (n o v)
+    a double layer."""
+
+    # -- pointwise tensor algebra
+    def tensorproduct(self, vu, vv):
+        n1, n2 = self.nx, self.ny
+        return n1 * vu, n2 * vu, n1 * vv, n2 * vv
+
+    def tensordot(self, T):
+        n1, n2 = self.nx, self.ny
+        return n1 * T[0] + n2 * T[1], n1 * T[2] + n2 * T[3]
+
+    # -- TensorData <-> EdgeGradient tables
+    def regularize_tensor(self, T):
+        return (regularize(self.tabs[PRIMAL], T[0]), regularize(self.tabs[DUAL], T[1]),
+                regularize(self.tabs[DUAL], T[2]), regularize(self.tabs[PRIMAL], T[3]))
+
+    def interpolate_tensor(self, A):
+        return (interpolate(self.tabs[PRIMAL], A[0]), interpolate(self.tabs[DUAL], A[1]),
+                interpolate(self.tabs[DUAL], A[2]), interpolate(self.tabs[PRIMAL], A[3]))
+
+    # -- src/surface_operators.jl:113-138
+    def regularize_normal_v(self, vu, vv):
+        return self.regularize_tensor(self.tensorproduct(vu, vv))
+
+    def symm_tensor(self, vu, vv):
+        t = self.tensorproduct(vu, vv)
+        dot = self.nx * vu + self.ny * vv
+        return (t[0] + t[0]) - dot, t[1] + t[2], t[2] + t[1], (t[3] + t[3]) - dot
+
+    def regularize_normal_symm(self, vu, vv):
+        return self.regularize_tensor(self.symm_tensor(vu, vv))
+
+    # -- src/surface_operators.jl:242-267
+    def normal_interpolate_v(self, A):
+        return self.tensordot(self.interpolate_tensor(A))
+
+    def normal_interpolate_symm(self, A):
+        tr = A[0] + A[3]
+        Gs = ((A[0] + A[0]) - tr, A[2] + A[1], A[1] + A[2], (A[3] + A[3]) - tr)
+        return self.tensordot(self.interpolate_tensor(Gs))
+
+    # -- src/surface_operators.jl:172-215, 303-343
+    def regularize_normal_cross_v(self, vu, vv):
+        """w = Rcurl (n x v), pointwise_cross!(s,n,v) = n.u v.v - n.v v.u."""
+        return regularize(self.tabs[DUAL], self.nx * vv - self.ny * vu)
+
+    def regularize_normal_dot_v(self, vu, vv):
+        return regularize(self.tabs[PRIMAL], self.nx * vu + self.ny * vv)
+
+    def regularize_normal_dot_t(self, T):
+        tu, tv = self.tensordot(T)
+        return self.regularize_edges(tu, tv)
+
+    def normal_cross_interpolate_v(self, s):
+        f = interpolate(self.tabs[DUAL], s)
+        return self.ny * f, -self.nx * f
+
+    def normal_dot_interpolate_v(self, phi):
+        f = interpolate(self.tabs[PRIMAL], phi)
+        return self.nx * f, self.ny * f
+
+    def normal_dot_interpolate_t(self, u, v):
+        su, sv = self.interpolate_edges(u, v)
+        return self.tensorproduct(su, sv)
+
+    # -- composites (src/surface_operators.jl:388-398, 443-452, 559-591, 632-664)
+    def surface_divergence_v(self, vu, vv, symm=False):
+        T = self.regularize_normal_symm(vu, vv) if symm else self.regularize_normal_v(vu, vv)
+        u, v = divergence_t2e(self.grid, *T)
+        return self._scale_derivative(u), self._scale_derivative(v)
+
+    def surface_grad_v(self, u, v, symm=False):
+        A = grad_e2t(self.grid, u, v)
+        tu, tv = self.normal_interpolate_symm(A) if symm else self.normal_interpolate_v(A)
+        return self._scale_derivative(tu), self._scale_derivative(tv)
+
+    def surface_curl_v2n(self, vu, vv):
+        u, v = self.regularize_edges(vu, vv)
+        return self._scale_derivative(curl_e2n(self.grid, u, v))
+
+    def surface_curl_n2v(self, s):
+        u, v = curl_n2e(self.grid, s)
+        fu, fv = self.interpolate_edges(u, v)
+        return self._scale_derivative(fu), self._scale_derivative(fv)
+
+    def inverse_laplacian_edges(self, u, v):
+        return self.inverse_laplacian(u), self.inverse_laplacian(v)
+
+    def mask_edges(self):
+        """_get_mask! with Edges grid data (src/surface_operators.jl:865-871)."""
+        one = np.ones(self.N)
+        u, v = self.surface_divergence_v(one, one)
+        u, v = self.inverse_laplacian_edges(u, v)
+        return u * -1.0, v * -1.0
+
+    # -- Schur builders on VectorData (2N x 2N), src/matrix_operators.jl
+    def _probe_v(self, pre, post, sign, scale, nsolve=1, cols=None):
+        N = self.N
+        cols = range(2 * N) if cols is None else cols
+        A = np.zeros((2 * N, len(cols)), order="F")
+        for jc, col in enumerate(cols):
+            e = np.zeros(2 * N)
+            e[col] = 1.0
+            g = pre(e[:N], e[N:])
+            for _ in range(nsolve):
+                g = tuple(self.inverse_laplacian(c) for c in g) if isinstance(g, tuple) else self.inverse_laplacian(g)
+            out = post(*g) if isinstance(g, tuple) else post(g)
+            A[:, jc] = sign * scale * np.concatenate(out)
+        return A
+
+    def create_RTLinvR_v(self, scale=1.0, cols=None):
+        return self._probe_v(self.regularize_edges, self.interpolate_edges, -1.0, scale, cols=cols)
+
+    def create_CLinvCT_v(self, scale=1.0, cols=None):
+        """create_CLinvCT on a vector cache (src/matrix_operators.jl:40-61)."""
+        return self._probe_v(self.surface_curl_v2n, self.surface_curl_n2v, -1.0, scale, cols=cols)
+
+    def create_CL2invCT(self, scale=1.0, cols=None):
+        """src/matrix_operators.jl:102-125: two inverse Laplacians."""
+        return self._probe_v(self.surface_curl_v2n, self.surface_curl_n2v, -1.0, scale, nsolve=2, cols=cols)
+
+    def create_GLinvD_v(self, scale=1.0, symm=False, cols=None):
+        """create_GLinvD / create_GLinvD_symm on a vector cache (:135-185)."""
+        return self._probe_v(lambda a, b: self.surface_divergence_v(a, b, symm),
+                             lambda u, v: self.surface_grad_v(u, v, symm), -1.0, scale, cols=cols)
+
+    def create_nRTRn_v(self, scale=1.0):
+        N = self.N
+        A = np.zeros((2 * N, 2 * N), order="F")
+        for col in range(2 * N):
+            e = np.zeros(2 * N)
+            e[col] = 1.0
+            A[:, col] = scale * np.concatenate(self.normal_interpolate_v(self.regularize_normal_v(e[:N], e[N:])))
+        return A
+
+    # create_CLinvCT_scalar (:71-92) on a vector cache is the scalar-cache create_CLinvCT
+    create_CLinvCT_scalar = ScalarCache.create_CLinvCT
+
+
 def dirichlet_solve(cache, fplus, fminus=None, S=None):
     """Block-LU Dirichlet Poisson (test/literate/dirichlet.jl:71-107).
     Returns (f, s, S)."""

@@ -294,3 +294,59 @@ def test_c_direct_convolution_matches_fft_oracle():
                                          ctypes.c_double(c0), ctypes.c_double(factor), dp(out.ctypes.data))
         ref = o.inverse_laplacian(plan, w, c0, factor)
         assert np.abs(out - ref).max() < 1e-12 * np.abs(ref).max()
+
+
+# ---------------------------------------------------------------- vector cache (test/surface_ops.jl:121-146)
+@pytest.fixture(scope="module")
+def small_vcache():
+    dx = 0.04
+    NX = 104
+    g = o.Grid(NX, NX, dx, (NX // 2, NX // 2))
+    x, y, nx, ny, ds = bodies.circle(1.0, 1.4 * dx)
+    return o.VectorCache(g, x, y, nx, ny, ds, lgfmod.lgf_table(NX))
+
+
+def test_vector_surface_ops_reference_values(small_vcache):
+    """regularize_normal_symm! / normal_interpolate_symm! round trip: extrema of vs.u ~ +-22.5
+    (test/surface_ops.jl:124-137, same sequence of calls)."""
+    c = small_vcache
+    th = 2 * np.pi * np.arange(c.N) / c.N
+    vu, vv = np.sin(th - np.pi / 4), np.zeros(c.N)
+    vu, vv = c.normal_interpolate_v(c.regularize_normal_v(vu, vv))
+    vu = np.sin(th - np.pi / 4)
+    vu, vv = c.normal_interpolate_symm(c.regularize_normal_symm(vu, vv))
+    assert abs(vu.max() - 22.5) < 1.0 and abs(vu.min() + 22.5) < 1.0
+
+
+def test_vector_schur_and_adjoints(small_vcache):
+    c = small_vcache
+    g = c.grid
+    rng = np.random.default_rng(21)
+    vu, vv = rng.standard_normal(c.N), rng.standard_normal(c.N)
+    A = [rng.standard_normal(o.field_shape(k, g.NX, g.NY)) for k in (o.PRIMAL, o.DUAL, o.DUAL, o.PRIMAL)]
+    for a in A:
+        a[:2, :] = 0; a[-2:, :] = 0; a[:, :2] = 0; a[:, -2:] = 0
+    # <A, Rt (n o v)>_grid dx^2 = <n . Et A, v>_ds   (regularize_normal! / normal_interpolate! adjoint pair)
+    T = c.regularize_normal_v(vu, vv)
+    lhs = sum(np.sum(a * t) for a, t in zip(A, T)) * g.dx ** 2
+    tu, tv = c.normal_interpolate_v(A)
+    assert abs(lhs - np.sum((tu * vu + tv * vv) * c.ds)) < 1e-10 * abs(lhs)
+    Ts = c.regularize_normal_symm(vu, vv)
+    lhs = sum(np.sum(a * t) for a, t in zip(A, Ts)) * g.dx ** 2
+    tu, tv = c.normal_interpolate_symm(A)
+    assert abs(lhs - np.sum((tu * vu + tv * vv) * c.ds)) < 1e-10 * abs(lhs)
+    # surface_grad is the negative adjoint of surface_divergence (src/surface_operators.jl:557)
+    qu = rng.standard_normal(o.field_shape(o.XEDGE, g.NX, g.NY)); qv = rng.standard_normal(o.field_shape(o.YEDGE, g.NX, g.NY))
+    for a in (qu, qv):
+        a[:3, :] = 0; a[-3:, :] = 0; a[:, :3] = 0; a[:, -3:] = 0
+    du, dv = c.surface_divergence_v(vu, vv)
+    gu, gv = c.surface_grad_v(qu, qv)
+    lhs = (np.sum(du * qu) + np.sum(dv * qv)) * g.dx ** 2
+    assert abs(lhs + np.sum((gu * vu + gv * vv) * c.ds)) < 1e-10 * abs(lhs)
+    # create_GLinvD(vcache, scale=dx): max |eig| ~ 0.45 (test/surface_ops.jl:145-146), sampled columns keep it quick
+    cols = list(range(0, 2 * c.N, 1))
+    Gm = c.create_GLinvD_v(scale=g.dx, cols=cols)
+    assert abs(np.abs(np.linalg.eigvals(Gm)).max() - 0.45) < 0.1
+    # mask on Edges integrates to the body area
+    mu, mv = c.mask_edges()
+    assert abs(o.dot_grid(g, mu, np.ones_like(mu), o.XEDGE) - np.pi) < 3e-2
