@@ -283,6 +283,13 @@ def main():
         stages[name] = {"ms": tms, "bytes": nbytes, "GBps": nbytes / (tms * 1e-3) / 1e9,
                         "frac_of_hbm_peak": nbytes / (tms * 1e-3) / 1e9 / peak}
     roofline["stages"] = stages
+    # transform-free direct-table Schur builder: reported beside, never part of `value` / `e2e`
+    t_direct = time_op(lambda: ilm.create_RTLinvR_direct(cache), reps=3)
+    S_fft = ilm.create_RTLinvR(cache, cols=(0, 64))
+    S_dir = ilm.create_RTLinvR_direct(cache, cols=(0, 64))
+    roofline["schur_direct_table"] = {
+        "ms": t_direct, "note": "optional O(N^2 W^4) table form of S (SURVEY fact 8); not used by the metric path",
+        "rel_diff_vs_column_solves": float(((S_dir - S_fft).abs().max() / S_fft.abs().max()).item())}
 
     # ---- end to end through the public API with host buffers
     e2e = None

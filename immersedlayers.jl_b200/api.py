@@ -954,3 +954,14 @@ def create_nRTRn(cache, scale=1.0):
     buf = _matrix(cache, 4 * cache.N) if cache.N else _matrix(cache, 0)
     L.check(cache._lib.ilm_create_nRTRn_vector(cache._plan, float(scale), _ptr(buf)))
     return _as_matrix(buf, M, M)
+
+
+def create_RTLinvR_direct(cache, scale=1.0, cols=None):
+    """The matrix of create_RTLinvR from the direct LGF-table identity:
+    no transform is applied.  Cross-check and optional fast builder for scalar caches."""
+    if _is_vector(cache):
+        raise MethodError("create_RTLinvR_direct: scalar caches only")
+    c0, c1 = (0, cache.N) if cols is None else cols
+    buf = _matrix(cache, c1 - c0)
+    L.check(cache._lib.ilm_create_RTLinvR_direct(cache._plan, float(scale), int(c0), int(c1), _ptr(buf)))
+    return _as_matrix(buf, cache.N, c1 - c0)

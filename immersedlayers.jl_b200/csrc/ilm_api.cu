@@ -563,3 +563,17 @@ extern "C" int ilm_profile_conv(ilm_plan* p, int layout, int reps, double ms[3])
     ILM_TRY(launch_fill(p, p->g_b, n_layout(p, layout), -0.5));
     return conv_profile(p, fref(p, layout, p->g_a), fref(p, layout, p->g_b), reps, ms);
 }
+
+// Direct-table builder of -scale * E L^-1 R (cross-check / optional fast path, see ilm_ops.cu)
+extern "C" int ilm_create_RTLinvR_direct(ilm_plan* p, double scale, int col_begin, int col_end, double* A) {
+    ILM_CHECK_PLAN(p);
+    const int N = p->N;
+    if (col_begin < 0 || col_end > N || col_begin > col_end) { set_error("ilm_create_RTLinvR_direct: bad column range"); return ILM_ESIZE; }
+    if (!p->lgf_dev) { set_error("ilm_create_RTLinvR_direct: the plan was created from a device-resident table"); return ILM_EINVAL; }
+    if (N == 0 || col_end == col_begin) return ILM_OK;
+    Io io(p);
+    double* dA = io.out(A, (size_t)N * (col_end - col_begin));
+    if (io.status) return io.status;
+    ILM_TRY(launch_schur_direct(p, p->lgf_dev, p->lgf_ld, scale, col_begin, col_end, dA));
+    return io.finish();
+}

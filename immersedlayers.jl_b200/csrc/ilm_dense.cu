@@ -6,9 +6,13 @@
 // Right-looking blocked LU (NB = 32): panel factorisation by one CTA, row
 // interchanges, a triangular solve for the block row, and the trailing update
 // A22 -= A21 * A12 on the FP64 tensor pipe (mma.sync.m8n8k4.f64, "DMMA").
+#include <cooperative_groups.h>
+
 #include <vector>
 
 #include "ilm_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace ilm {
 
@@ -73,6 +77,95 @@ __global__ void __launch_bounds__(1024) k_lu_panel(int n, int k0, int nb, double
         }
         __syncthreads();
     }
+}
+
+// ---- panel on a thread-block cluster: 8 CTAs (8 SMs) share one panel, each owning a fixed slice
+// of the rows below the diagonal block; the pivot candidates are exchanged through distributed
+// shared memory, two cluster barriers per column.
+constexpr int PANEL_CTAS = 8;
+__global__ void __cluster_dims__(PANEL_CTAS, 1, 1) __launch_bounds__(1024)
+k_lu_panel_cluster(int n, int k0, int nb, double* __restrict__ A, int* __restrict__ ipiv) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ double c_val;          // this CTA's pivot candidate (read by the peers through DSMEM)
+    __shared__ int c_idx;
+    __shared__ int s_piv;
+    __shared__ double s_row[NB];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // fixed row slices of [k0, n)
+    const int len = n - k0, chunk = (len + PANEL_CTAS - 1) / PANEL_CTAS;
+    const int sl0 = k0 + rank * chunk, sl1 = min(n, sl0 + chunk);
+    for (int jj = 0; jj < nb; ++jj) {
+        const int col = k0 + jj;
+        double* a_col = A + (size_t)col * n;
+        double best = -1.0;
+        int bi = n;
+        for (int r = max(sl0, col) + tid; r < sl1; r += 1024) {
+            const double v = fabs(a_col[r]);
+            if (v > best) { best = v; bi = r; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, off);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[wid] = best; s_idx[wid] = bi; }
+        __syncthreads();
+        if (wid == 0) {
+            best = s_val[lane]; bi = s_idx[lane];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, best, off);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) { c_val = best; c_idx = bi; }
+        }
+        cl.sync();                                   // candidates of all CTAs are in place
+        if (wid == 0) {
+            best = -1.0; bi = n;
+            if (lane < PANEL_CTAS) {
+                best = *cl.map_shared_rank(&c_val, lane);
+                bi = *cl.map_shared_rank(&c_idx, lane);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, best, off);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) s_piv = bi;
+        }
+        __syncthreads();
+        const int piv = s_piv;
+        if (rank == 0) {                             // row interchange inside the panel
+            if (tid < nb) {
+                double* c = A + (size_t)(k0 + tid) * n;
+                const double top = c[piv];
+                if (piv != col) { c[piv] = c[col]; c[col] = top; }
+            }
+            if (tid == 0) ipiv[col] = piv + 1;
+            __threadfence();
+        }
+        cl.sync();                                   // the swapped pivot row is visible to every CTA
+        if (tid < nb) s_row[tid] = A[(size_t)(k0 + tid) * n + col];
+        __syncthreads();
+        const double pivot = s_row[jj];
+        const int ncols = nb - jj - 1;
+        for (int r = max(sl0, col + 1) + tid; r < sl1; r += 1024) {
+            const double l = a_col[r] / pivot;
+            a_col[r] = l;
+            for (int c = 0; c < ncols; ++c) {
+                double* q = A + (size_t)(col + 1 + c) * n + r;
+                *q = *q - l * s_row[jj + 1 + c];
+            }
+        }
+        __syncthreads();
+    }
+    cl.sync();                                       // no CTA leaves while a peer may still read its smem
 }
 
 // apply the panel's row interchanges to the columns outside the panel
@@ -275,7 +368,8 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
     cudaStream_t st = io.st;
     for (int k0 = 0; k0 < n; k0 += NB) {
         const int nb = n - k0 < NB ? n - k0 : NB;
-        k_lu_panel<<<1, 1024, 0, st>>>(n, k0, nb, dA, dP);
+        if (n - k0 >= 2048) k_lu_panel_cluster<<<PANEL_CTAS, 1024, 0, st>>>(n, k0, nb, dA, dP);
+        else k_lu_panel<<<1, 1024, 0, st>>>(n, k0, nb, dA, dP);
         if (n - nb > 0) k_lu_swap<<<(n - nb + 127) / 128, 128, 0, st>>>(n, k0, nb, dA, dP);
         const int rem = n - k0 - nb;
         if (rem > 0) {

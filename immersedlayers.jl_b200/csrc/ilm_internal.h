@@ -78,6 +78,8 @@ struct ilm_plan {
     size_t s_cap = 0;
     int skew_ns = 500;              // ILM_CONV_SKEW_NS: start-up skew between the two groups of a CTA
     std::vector<ilm::ConvKernel> kernels;
+    double* lgf_dev = nullptr;      // device copy of the LGF table (ld = lgf_ld), kept for the direct Schur form
+    int lgf_ld = 0;
     // scratch (device)
     double* g_edges = nullptr;      // Edges scratch (gsnorm_cache)
     double* g_a = nullptr;          // NX*NY scratch field (gdata/gcurl cache)
@@ -128,6 +130,7 @@ int launch_scale(ilm_plan* p, double* w, size_t n, double scale);
 int launch_lgf_prep(ilm_plan* p, const double* table, int ld, int NX, int NY, double c0, double* h);
 int launch_filter_rowsum(ilm_plan* p, DevTable& t);
 int launch_surface_filter(ilm_plan* p, const DevTable& t, double* C);
+int launch_schur_direct(ilm_plan* p, const double* G, int ldg, double scale, int col_begin, int col_end, double* A);
 // vector-cache pieces (TensorData = [dudx; dudy; dvdx; dvdy], EdgeGradient likewise)
 int launch_tensor_from_vector(ilm_plan* p, int mode, const double* v, double* T);
 int launch_tensor_dot(ilm_plan* p, int mode, const double* S, double div, double* out);

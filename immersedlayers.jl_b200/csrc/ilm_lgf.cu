@@ -78,6 +78,7 @@ int conv_setup(ilm_plan* p) {
 void conv_free(ilm_plan* p) {
     cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->S); cudaFree(p->S2);
     for (auto& k : p->kernels) cudaFree(k.ghat);
+    cudaFree(p->lgf_dev); p->lgf_dev = nullptr;
     p->kernels.clear();
 }
 
@@ -113,7 +114,10 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     ILM_TRY(conv_launcher(p->Ly)(3, a, p->nsm, p->stream));
     p->launches += 2;
     ILM_CUDA(cudaStreamSynchronize(p->stream));
-    if (dtab) cudaFree(dtab);
+    if (dtab) {
+        if (p->kernels.empty() && !p->lgf_dev) { p->lgf_dev = dtab; p->lgf_ld = n; }   // kernel 0 = LGF: keep the table
+        else cudaFree(dtab);
+    }
     p->kernels.push_back(k);
     if (id) *id = (int)p->kernels.size() - 1;
     return ILM_OK;

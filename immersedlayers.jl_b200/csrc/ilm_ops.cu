@@ -530,3 +530,58 @@ int launch_div_tensor(ilm_plan* p, const double* eg, double* edges, double div) 
 }
 
 }  // namespace ilm
+
+// =====================================================================================
+// Direct-table form of S = -scale * E L^-1 R: the response of L^-1 to a
+// unit impulse is the (shifted) LGF table itself, so
+//   S[k,l] = -(scale/factor) * sum_p E[k,p] * sum_q (G(|p-q|) - c0) * R[q,l]
+// needs no transform at all (O(N^2 W^4) table look-ups).  Cross-check of the column-solve path
+// and an optional fast builder; bench.py's metric path always uses the column solves.
+// =====================================================================================
+namespace ilm {
+
+__global__ void __launch_bounds__(256)
+k_schur_direct(int N, int W, int mx, const int* __restrict__ i0, const int* __restrict__ j0,
+               const double* __restrict__ wE, const double* __restrict__ wR, const double* __restrict__ G, int ldg,
+               int my, double c0, double coef, int col_begin, double* __restrict__ A) {
+    const int l = col_begin + blockIdx.y;
+    __shared__ double rw[16];
+    __shared__ int ri[16], rj[16];
+    const int W2 = W * W;
+    if (threadIdx.x < W2) {
+        const int a = threadIdx.x % W, b = threadIdx.x / W;
+        const int i = i0[l] + a, j = j0[l] + b;
+        const bool ok = i >= 0 && i < mx && j >= 0 && j < my;
+        rw[threadIdx.x] = ok ? wR[(size_t)l * W2 + threadIdx.x] : 0.0;
+        ri[threadIdx.x] = i; rj[threadIdx.x] = j;
+    }
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    double sum = 0.0;
+    for (int b = 0; b < W; ++b)
+        for (int a = 0; a < W; ++a) {
+            const int pi = i0[k] + a, pj = j0[k] + b;
+            if (pi < 0 || pi >= mx || pj < 0 || pj >= my) continue;
+            double inner = 0.0;
+            for (int q = 0; q < W2; ++q) {
+                const int di = abs(pi - ri[q]), dj = abs(pj - rj[q]);
+                inner += (G[(size_t)dj * ldg + di] - c0) * rw[q];
+            }
+            sum += wE[(size_t)k * W2 + b * W + a] * inner;
+        }
+    A[(size_t)blockIdx.y * N + k] = coef * sum;
+}
+
+int launch_schur_direct(ilm_plan* p, const double* G, int ldg, double scale, int col_begin, int col_end, double* A) {
+    const DevTable& t = p->tab[ILM_NODES_PRIMAL];
+    const int N = p->N, ncols = col_end - col_begin;
+    if (N == 0 || ncols == 0) return ILM_OK;
+    dim3 grid((N + 255) / 256, ncols);
+    k_schur_direct<<<grid, 256, 0, p->stream>>>(N, t.W, t.mx, t.i0, t.j0, t.wE, t.wR, G, ldg, t.my, p->c0,
+                                                -scale / p->lap_factor, col_begin, A);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+}  // namespace ilm

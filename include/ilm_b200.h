@@ -137,6 +137,11 @@ int ilm_mask(ilm_plan* plan, double* nodes_primal);
  * leading dimension N into A (N x (col_end-col_begin)).  Column ranges are the
  * multi-GPU shard.                                                          */
 int ilm_create_schur(ilm_plan* plan, int which, double scale, int col_begin, int col_end, double* A);
+/* Same matrix as ilm_create_schur(ILM_RTLINVR) from the direct-table identity
+ * S[k,l] = -(scale/factor) sum_p sum_q E[k,p] (G(|p-q|) - c0) R[q,l]: no
+ * transform, O(N^2 W^4) look-ups.  Cross-check of the column-solve path and an optional fast
+ * builder; it is NOT what bench.py's grid-point*solves/s metric times.                      */
+int ilm_create_RTLinvR_direct(ilm_plan* plan, double scale, int col_begin, int col_end, double* A);
 int ilm_create_nRTRn(ilm_plan* plan, double scale, double* A);   /* :225-244 */
 int ilm_create_surface_filter(ilm_plan* plan, double* C);        /* :254-268 */
 

@@ -275,6 +275,14 @@ def test_schur_matrices(c1):
     assert relerr(ilm.create_surface_filter(cache), oc.create_surface_filter()) < RTOL
 
 
+def test_schur_direct_table_form(c1):
+    """the transform-free table form equals the column-solve path."""
+    cache, oc = c1
+    Sd = ilm.create_RTLinvR_direct(cache, scale=1.5)
+    assert relerr(Sd, 1.5 * oc.create_RTLinvR()) < RTOL
+    assert relerr(ilm.create_RTLinvR_direct(cache, cols=(5, 12)), ilm.create_RTLinvR(cache, cols=(5, 12))) < RTOL
+
+
 def test_schur_reference_physics(c1):
     """The reference's own checks (test/surface_ops.jl:69-77) on the GPU matrices."""
     cache, _ = c1
@@ -285,7 +293,7 @@ def test_schur_reference_physics(c1):
     assert abs(np.linalg.svd(ilm.create_nRTRn(cache), compute_uv=False).max() * dx / 0.04 - 11) < 1.5
 
 
-@pytest.mark.parametrize("n", [1, 7, 32, 33, 141, 500])
+@pytest.mark.parametrize("n", [1, 7, 32, 33, 141, 500, 2500])
 def test_dense_lu_solve(n):
     import scipy.linalg
     rng = np.random.default_rng(n)

@@ -21,6 +21,8 @@ def timed(name, fn, reps=1):
     return out
 
 S = timed("create_RTLinvR", lambda: ilm.create_RTLinvR(cache))
+Sd = timed("create_RTLinvR_direct", lambda: ilm.create_RTLinvR_direct(cache))
+print("direct vs column-solve rel diff", ((Sd - S).abs().max() / S.abs().max()).item())
 lu = timed("LU factor", lambda: ilm.LU(S))
 b = torch.randn(cache.N, dtype=torch.float64, device="cuda")
 x = timed("LU solve", lambda: lu.solve(b), reps=3)
