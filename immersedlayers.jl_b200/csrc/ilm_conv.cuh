@@ -235,7 +235,12 @@ ILM_HD void passB_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
 }
 
 // ---------------------------------------------------------------- pass C
-// work item = F rows; group g inverts parity px = g; group 0 combines and stores
+// work item = RPW rows; group g inverts parity px = g; group 0 combines and stores.
+// For L >= 512 the spectrum rows are fetched with bulk-tensor (TMA) copies straight
+// into the group's exchange buffer, one step ahead: the copy of step s+1 is issued
+// as soon as step s has read the buffer for the last time, and lands while the last
+// butterfly pass, the combine and the stores of step s run.  The 2x2-tile gather
+// (32-byte pieces) is done by the copy engine instead of 16 scattered loads per thread.
 template <int L, class Ctx>
 ILM_HD void passC_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, int nblocks) {
     using C = FftCfg<L>;
@@ -243,24 +248,44 @@ ILM_HD void passC_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
     double2* tw = smem + C::TW_BASE;
     load_twiddles<L>(ctx, tw, a.twx);
     const int f = ctx.tid / T, j = ctx.tid % T, px = ctx.grp;
-    double2* xb = smem + ctx.grp * C::GROUP_XBUF + f * C::XBUF;
+    double2* xgrp = smem + ctx.grp * C::GROUP_XBUF;
+    double2* xb = xgrp + f * C::XBUF;
     double2* comb = smem + 2 * C::GROUP_XBUF + f * L;
+    double2* mbar = smem + C::MBAR_OFF + ctx.grp;
     // RPW consecutive rows per work item: the second row of each 2x2 tile is an
     // L2 hit (its sector came in with the first row's 64-byte DRAM access)
     constexpr int SUB = (F == 1) ? 2 : 1, RPW = F * SUB;
     const int nwork = (a.g.MYp + RPW - 1) / RPW;
+    const int nsteps = (block < nwork) ? ((nwork - block + nblocks - 1) / nblocks) * SUB : 0;
+    // rows of step s for FFT slot ff
+    auto step_row0 = [&](int s) { return (block + (s / SUB) * nblocks) * RPW + (s % SUB) * F; };
+    if constexpr (C::USE_TMA) {
+        ctx.tma_init(mbar);
+        if (nsteps > 0) ctx.tma_load_rows(a, px, step_row0(0), F, L, C::XBUF, xgrp, mbar);
+    }
     if (!px) { ctx.arrive(BAR_FREE); ctx.delay(a.skew_ns); }
-    for (int w = block; w < nwork; w += nblocks) {
-#pragma unroll 1
-      for (int sub = 0; sub < SUB; ++sub) {
-        const int row = w * RPW + sub * F + f;
+    for (int s = 0; s < nsteps; ++s) {
+        const int row = step_row0(s) + f;
         const bool live = row < a.g.MYp;
         const bool r1 = a.f1.p && row < a.f1.my, r2 = a.f2.p && row < a.f2.my;
-        const size_t i0 = s_index(a.g, px, j, row);
         double2 v[16];
+        if constexpr (C::USE_TMA) {
+            ctx.tma_wait(mbar, s & 1);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = live ? a.S2[row_elem<T>(a.g, px, row, j, e, i0)] : cmk(0.0, 0.0);
-        fft_regs<L, true>(v, ctx, xb, tw, j);
+            for (int e = 0; e < 16; ++e) v[e] = xb[j + e * T];
+        } else {
+            const size_t i0 = s_index(a.g, px, j, row);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = live ? a.S2[row_elem<T>(a.g, px, row, j, e, i0)] : cmk(0.0, 0.0);
+        }
+        fft_head<L, true>(v, ctx, xb, tw, j);
+        if constexpr (C::USE_TMA) {
+            if (s + 1 < nsteps) {
+                ctx.sync();                                   // every thread has left the exchange buffer
+                ctx.tma_load_rows(a, px, step_row0(s + 1), F, L, C::XBUF, xgrp, mbar);
+            }
+        }
+        fft_last_pass<L, true>(v, tw, j);
         if (px) {
             ctx.wait(BAR_FREE);
 #pragma unroll
@@ -277,7 +302,6 @@ ILM_HD void passC_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
             }
             ctx.arrive(BAR_FREE);
         }
-      }
     }
 }
 

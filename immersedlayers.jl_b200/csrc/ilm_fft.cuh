@@ -138,7 +138,10 @@ template <int L> struct FftCfg {
     static constexpr int GROUP_XBUF = F * XBUF;         // = 4352 for every L
     static constexpr int COMB = F * L;                  // combine buffer (unpadded), = 4096
     static constexpr int TW_BASE = 2 * GROUP_XBUF + COMB;
-    static constexpr size_t SMEM_BYTES = (size_t)(TW_BASE + TW_TOTAL) * sizeof(double2);
+    static constexpr int MBAR_OFF = TW_BASE + TW_TOTAL;      // two 8-byte mbarriers (one per group)
+    static constexpr size_t SMEM_BYTES = (size_t)(MBAR_OFF + 2) * sizeof(double2);
+    static constexpr bool USE_TMA = L >= 512;               // bulk-tensor loads of spectrum rows (pass C)
+    static constexpr int TMA_BOX = 256;                     // tile columns (a) per bulk-tensor box
 };
 
 ILM_HD int xpad(int i) { return i + (i >> 4); }
@@ -189,12 +192,15 @@ template <int R, bool INV, int S> ILM_HD void twiddle_powers(double2* v, const d
 //   v[e] holds x[j + e*T] on entry and X[j + e*T] on exit (unnormalised).
 //   xb: this FFT's padded exchange buffer (XBUF entries), tw: twiddle table.
 //   ctx.sync() is a barrier over the 256-thread group.
+// fft_head runs every pass but the last and ends right after the last read of the
+// exchange buffer (callers may then hand the buffer to an asynchronous copy);
+// fft_last_pass is the last butterfly pass on registers only.
 template <int L, bool INV, class Ctx>
-ILM_HD void fft_regs(double2* v, Ctx& ctx, double2* xb, const double2* tw, int j) {
+ILM_HD void fft_head(double2* v, Ctx& ctx, double2* xb, const double2* tw, int j) {
     using C = FftCfg<L>;
     constexpr int T = C::T;
-    fft16<INV>(v);
     if (C::P == 1) return;
+    fft16<INV>(v);
     ctx.sync();                                   // previous readers of xb are done
 #pragma unroll
     for (int t = 0; t < 16; ++t) xb[xpad(j * 16 + t)] = v[t];
@@ -212,13 +218,24 @@ ILM_HD void fft_regs(double2* v, Ctx& ctx, double2* xb, const double2* tw, int j
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] = xb[xpad(j + e * T)];
     }
+}
+
+template <int L, bool INV> ILM_HD void fft_last_pass(double2* v, const double2* tw, int j) {
+    using C = FftCfg<L>;
+    if (C::P == 1) { fft16<INV>(v); return; }
     // tail pass: radix RL, Ns = L/RL, butterflies q = 0..S-1 on registers q + t*S
-    constexpr int RL = C::RL, S = 16 / RL, NS = C::NS_LAST;
+    constexpr int T = C::T, RL = C::RL, S = 16 / RL, NS = C::NS_LAST;
 #pragma unroll
     for (int q = 0; q < S; ++q) {
         twiddle_powers<RL, INV, S>(v + q, tw + C::TWL_OFF, NS, j + q * T);
         fft_tail<RL, INV, S>(v + q);
     }
+}
+
+template <int L, bool INV, class Ctx>
+ILM_HD void fft_regs(double2* v, Ctx& ctx, double2* xb, const double2* tw, int j) {
+    fft_head<L, INV>(v, ctx, xb, tw, j);
+    fft_last_pass<L, INV>(v, tw, j);
 }
 
 // host-side generation of the twiddle table for length L (long double -> double)

@@ -76,6 +76,8 @@ struct ilm_plan {
     double2 *twx = nullptr, *twy = nullptr;
     double2 *S = nullptr, *S2 = nullptr;
     size_t s_cap = 0;
+    alignas(64) unsigned char tmap_s2[128] = {};   // CUtensorMap of S2 for the current row count (pass C)
+    int tmap_myp = -1;
     int skew_ns = 500;              // ILM_CONV_SKEW_NS: start-up skew between the two groups of a CTA
     std::vector<ilm::ConvKernel> kernels;
     double* lgf_dev = nullptr;      // device copy of the LGF table (ld = lgf_ld), kept for the direct Schur form
@@ -151,7 +153,7 @@ void conv_free(ilm_plan* p);
 int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3]);
 extern long long g_dense_launches;
 // per-length launchers, which = 0: pass A, 1: pass B, 2: pass C, 3: pass G
-typedef int (*conv_launch_fn)(int which, const ConvArgs& a, int nsm, cudaStream_t st);
+typedef int (*conv_launch_fn)(int which, const ConvArgs& a, int nsm, cudaStream_t st, const void* tmap);
 conv_launch_fn conv_launcher(int L);
 const double2* conv_twiddles_host(int L, size_t* count);
 

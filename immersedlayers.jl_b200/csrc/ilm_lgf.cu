@@ -3,6 +3,8 @@
 // three-pass apply.  Replaces plan_laplacian / CircularConvolution set-up
 // reached from _get_laplacian (src/cache.jl:321-324) and the `L\w` apply
 // reached from inverse_laplacian! (src/grid_operators.jl:153-179).
+#include <cuda.h>
+
 #include <cstdlib>
 
 #include "ilm_internal.h"
@@ -10,7 +12,7 @@
 namespace ilm {
 
 #define ILM_DECL_L(L)                                                                  \
-    int conv_launch_L##L(int which, const ConvArgs& a, int nsm, cudaStream_t st);      \
+    int conv_launch_L##L(int which, const ConvArgs& a, int nsm, cudaStream_t st, const void* tmap); \
     const double2* conv_twiddles_L##L(size_t* count);
 ILM_DECL_L(16) ILM_DECL_L(32) ILM_DECL_L(64) ILM_DECL_L(128) ILM_DECL_L(256)
 ILM_DECL_L(512) ILM_DECL_L(1024) ILM_DECL_L(2048) ILM_DECL_L(4096)
@@ -43,6 +45,35 @@ const double2* conv_twiddles_host(int L, size_t* count) {
     case 4096: return conv_twiddles_L4096(count);
     default: *count = 0; return nullptr;
     }
+}
+
+// 3-D tensor map over the S2 spectrum in units of doubles: (8 per 2x2 tile, MYp/2 row pairs,
+// Lx tile columns incl. both parities); a box = (4 doubles = one row's two m, 1, <=256 tile
+// columns), i.e. the 32-byte pieces of one row gathered into m order (pass C).
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_s2_tensor_map(ilm_plan* p, int MYp) {
+    if (p->tmap_myp == MYp) return ILM_OK;
+    static encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        ILM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return ILM_ECUDA; }
+        encode = (encode_tiled_fn)fn;
+    }
+    const int na = p->Lx >> 1;
+    cuuint64_t dims[3] = {8, (cuuint64_t)(MYp >> 1), (cuuint64_t)p->Lx};
+    cuuint64_t strides[2] = {64, (cuuint64_t)(MYp >> 1) * 64};             // bytes, dims 1 and 2
+    cuuint32_t box[3] = {4, 1, (cuuint32_t)(na < 256 ? na : 256)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(reinterpret_cast<CUtensorMap*>(p->tmap_s2), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p->S2, dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed"); return ILM_ECUDA; }
+    p->tmap_myp = MYp;
+    return ILM_OK;
 }
 
 // half padded length: smallest power of two L >= 16 with 2L >= 2n-1
@@ -110,8 +141,8 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     a.gscale = 1.0 / (4.0 * (double)p->Lx * (double)p->Ly * factor);
     a.twx = p->twx; a.twy = p->twy;
     a.skew_ns = p->skew_ns;
-    ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream));
-    ILM_TRY(conv_launcher(p->Ly)(3, a, p->nsm, p->stream));
+    ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream, nullptr));
+    ILM_TRY(conv_launcher(p->Ly)(3, a, p->nsm, p->stream, nullptr));
     p->launches += 2;
     ILM_CUDA(cudaStreamSynchronize(p->stream));
     if (dtab) {
@@ -140,9 +171,10 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
     a.Ghat = p->kernels[kernel_id].ghat;
     a.twx = p->twx; a.twy = p->twy;
     a.skew_ns = p->skew_ns;
-    ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream));
-    ILM_TRY(conv_launcher(p->Ly)(1, a, p->nsm, p->stream));
-    ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, p->stream));
+    if (p->Lx >= 512) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
+    ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream, nullptr));
+    ILM_TRY(conv_launcher(p->Ly)(1, a, p->nsm, p->stream, nullptr));
+    ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, p->stream, p->tmap_s2));
     p->launches += 3;
     return ILM_OK;
 }
@@ -162,10 +194,11 @@ int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3]) 
     ILM_CUDA(cudaEventCreate(&e0));
     ILM_CUDA(cudaEventCreate(&e1));
     const int Ls[3] = {p->Lx, p->Ly, p->Lx};
+    if (p->Lx >= 512) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
     for (int which = 0; which < 3; ++which) {
-        ILM_TRY(conv_launcher(Ls[which])(which, a, p->nsm, p->stream));      // warm-up
+        ILM_TRY(conv_launcher(Ls[which])(which, a, p->nsm, p->stream, p->tmap_s2));      // warm-up
         ILM_CUDA(cudaEventRecord(e0, p->stream));
-        for (int r = 0; r < reps; ++r) ILM_TRY(conv_launcher(Ls[which])(which, a, p->nsm, p->stream));
+        for (int r = 0; r < reps; ++r) ILM_TRY(conv_launcher(Ls[which])(which, a, p->nsm, p->stream, p->tmap_s2));
         ILM_CUDA(cudaEventRecord(e1, p->stream));
         ILM_CUDA(cudaEventSynchronize(e1));
         float t = 0;

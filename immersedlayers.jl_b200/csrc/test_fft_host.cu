@@ -38,6 +38,17 @@ struct HostCtx {
     void arrive(int id) { named[id].arrive(); }
     void wait(int id) { named[id].wait(); }
     void delay(int) {}
+    // bulk-tensor copies emulated synchronously by thread 0; the wait is a group barrier
+    void tma_init(double2*) { gb->wait(); }
+    void tma_load_rows(const ConvArgs& a, int px, int row0, int nrows, int L, int slot_stride, double2* dst, double2*) {
+        if (tid != 0) return;
+        for (int r = 0; r < nrows; ++r)
+            for (int m = 0; m < L; ++m) {
+                const int row = row0 + r;
+                dst[(size_t)r * slot_stride + m] = row < a.g.MYp ? a.S2[s_index(a.g, px, m, row)] : cmk(0.0, 0.0);
+            }
+    }
+    void tma_wait(double2*, int) { gb->wait(); }
     void prefetch_l2(const void*) {}
 };
 
