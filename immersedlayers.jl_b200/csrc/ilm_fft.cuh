@@ -161,6 +161,12 @@ ILM_HD double2 w32(int e) {
     return cmk(c[e], -s[e]);
 }
 
+// w_16^q, q = 0..15
+ILM_HD double2 w16(int q) {
+    const double2 h = w32((2 * q) & 15);          // w_32^(2q mod 16); w_32^16 = -1
+    return (q & 8) ? cmk(-h.x, -h.y) : h;
+}
+
 template <int R, bool INV, int S> ILM_HD void fft_tail(double2* v) {
     if constexpr (R == 16) fft16<INV>(v);
     else if constexpr (R == 8) fft8s<INV, S>(v);

@@ -74,6 +74,7 @@ struct ilm_plan {
     // convolution engine
     int Lx = 0, Ly = 0;
     double2 *twx = nullptr, *twy = nullptr;
+    double2* wl2y = nullptr;        // exp(-2 pi i n / (2 Ly)) table for the sparse forward transform
     double2 *S = nullptr, *S2 = nullptr;
     size_t s_cap = 0;
     alignas(64) unsigned char tmap_s2[128] = {};   // CUtensorMap of S2 for the current row count (pass C)

@@ -5,7 +5,9 @@
 // reached from inverse_laplacian! (src/grid_operators.jl:153-179).
 #include <cuda.h>
 
+#include <cmath>
 #include <cstdlib>
+#include <vector>
 
 #include "ilm_internal.h"
 
@@ -98,6 +100,13 @@ int conv_setup(ilm_plan* p) {
     ILM_CUDA(cudaMalloc(&p->twy, ny * sizeof(double2)));
     ILM_CUDA(cudaMemcpyAsync(p->twx, hx, nx * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
     ILM_CUDA(cudaMemcpyAsync(p->twy, hy, ny * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
+    {
+        std::vector<double2> w(2 * (size_t)p->Ly);
+        const long double tp = -2.0L * acosl(-1.0L) / (2.0L * p->Ly);
+        for (size_t n = 0; n < w.size(); ++n) w[n] = cmk((double)cosl(tp * n), (double)sinl(tp * n));
+        ILM_CUDA(cudaMalloc(&p->wl2y, w.size() * sizeof(double2)));
+        ILM_CUDA(cudaMemcpy(p->wl2y, w.data(), w.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    }
     ConvGeom g{p->Lx, p->Ly, p->g.NY, (p->g.NY + 1) & ~1};
     p->s_cap = s_elems(g);
     ILM_CUDA(cudaMalloc(&p->S, p->s_cap * sizeof(double2)));
@@ -107,7 +116,7 @@ int conv_setup(ilm_plan* p) {
 }
 
 void conv_free(ilm_plan* p) {
-    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->S); cudaFree(p->S2);
+    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->wl2y); cudaFree(p->S); cudaFree(p->S2);
     for (auto& k : p->kernels) cudaFree(k.ghat);
     cudaFree(p->lgf_dev); p->lgf_dev = nullptr;
     p->kernels.clear();
@@ -141,6 +150,7 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     a.gscale = 1.0 / (4.0 * (double)p->Lx * (double)p->Ly * factor);
     a.twx = p->twx; a.twy = p->twy;
     a.skew_ns = p->skew_ns;
+    a.wl2y = p->wl2y;
     ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream, nullptr));
     ILM_TRY(conv_launcher(p->Ly)(3, a, p->nsm, p->stream, nullptr));
     p->launches += 2;
@@ -171,6 +181,7 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
     a.Ghat = p->kernels[kernel_id].ghat;
     a.twx = p->twx; a.twy = p->twy;
     a.skew_ns = p->skew_ns;
+    a.wl2y = p->wl2y;
     if (p->Lx >= 512) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
     ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream, nullptr));
     ILM_TRY(conv_launcher(p->Ly)(1, a, p->nsm, p->stream, nullptr));
@@ -190,6 +201,7 @@ int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3]) 
     a.Ghat = p->kernels[0].ghat;
     a.twx = p->twx; a.twy = p->twy;
     a.skew_ns = p->skew_ns;
+    a.wl2y = p->wl2y;
     cudaEvent_t e0, e1;
     ILM_CUDA(cudaEventCreate(&e0));
     ILM_CUDA(cudaEventCreate(&e1));

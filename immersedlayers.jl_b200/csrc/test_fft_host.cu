@@ -127,6 +127,9 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
     fft_fill_twiddles<LY>(twy.data(), expm2pii);
     ConvArgs a{};
     a.twx = twx.data(); a.twy = twy.data();
+    std::vector<double2> wl2(2 * LY);
+    for (int n = 0; n < 2 * LY; ++n) wl2[n] = expm2pii(n, 2LL * LY);
+    a.wl2y = wl2.data();
     // ---- Ghat build: h = eps_i eps_j g
     std::vector<double> h((size_t)NX * NY);
     for (int j = 0; j < NY; ++j)
