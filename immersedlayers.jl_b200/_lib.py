@@ -88,6 +88,7 @@ SIGNATURES = {
     "ilm_create_nRTRn_vector": (_i, [_vp, _d, _dp]),
     "ilm_dense_launch_count": (C.c_int64, []),
     "ilm_profile_conv": (_i, [_vp, _i, _i, C.POINTER(C.c_double * 3)]),
+    "ilm_profile_conv_probe": (_i, [_vp, _i, _i, C.POINTER(C.c_double * 3)]),
 }
 
 _lib = None

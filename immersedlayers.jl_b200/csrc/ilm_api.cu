@@ -577,3 +577,16 @@ extern "C" int ilm_create_RTLinvR_direct(ilm_plan* p, double scale, int col_begi
     ILM_TRY(launch_schur_direct(p, p->lgf_dev, p->lgf_ld, scale, col_begin, col_end, dA));
     return io.finish();
 }
+
+// same as ilm_profile_conv but in Schur-probe mode: the input is R e_c (+ R e_{c+1}), so pass A only
+// transforms the patch rows and pass B uses the sparse forward transform (what the S build launches)
+extern "C" int ilm_profile_conv_probe(ilm_plan* p, int col, int reps, double ms[3]) {
+    ILM_CHECK_PLAN(p);
+    if (reps < 1 || !ms || col < 0 || col + 1 >= p->N) { set_error("ilm_profile_conv_probe: bad arguments"); return ILM_EINVAL; }
+    const DevTable& tp = p->tab[ILM_NODES_PRIMAL];
+    int rlo = std::min(tp.h_j0[col], tp.h_j0[col + 1]), rhi = std::max(tp.h_j0[col], tp.h_j0[col + 1]) + tp.W;
+    rlo = std::max(rlo, 0); rhi = std::min(rhi, tp.my);
+    ILM_TRY(launch_regularize_unit(p, tp, col, p->g_a, rlo, rhi));
+    ILM_TRY(launch_regularize_unit(p, tp, col + 1, p->g_b, rlo, rhi));
+    return conv_profile(p, fref(p, ILM_NODES_PRIMAL, p->g_a), fref(p, ILM_NODES_PRIMAL, p->g_b), reps, ms, rlo, rhi);
+}

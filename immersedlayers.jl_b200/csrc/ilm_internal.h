@@ -151,7 +151,7 @@ int conv_add_kernel(ilm_plan* p, const double* table_host_or_dev, int n, double 
 // rows outside [rlo, rhi) of both inputs are known zeros (-1, -1 = dense input)
 int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo = -1, int rhi = -1);
 void conv_free(ilm_plan* p);
-int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3]);
+int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo = -1, int rhi = -1);
 extern long long g_dense_launches;
 // per-length launchers, which = 0: pass A, 1: pass B, 2: pass C, 3: pass G
 typedef int (*conv_launch_fn)(int which, const ConvArgs& a, int nsm, cudaStream_t st, const void* tmap);

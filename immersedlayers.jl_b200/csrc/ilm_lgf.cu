@@ -191,12 +191,13 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
 }
 
 // per-pass timing for the roofline report (ilm_profile_conv)
-int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3]) {
+int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo, int rhi) {
     ConvArgs a{};
     int MY = f1.my > f2.my ? f1.my : f2.my;
     a.g = ConvGeom{p->Lx, p->Ly, MY, (MY + 1) & ~1};
     a.f1 = f1; a.f2 = f2;
-    a.rlo = 0; a.rhi = a.g.MYp;
+    a.rlo = rlo < 0 ? 0 : rlo;
+    a.rhi = (rhi < 0 || rhi > a.g.MYp) ? a.g.MYp : rhi;
     a.S = p->S; a.S2 = p->S2;
     a.Ghat = p->kernels[0].ghat;
     a.twx = p->twx; a.twy = p->twy;

@@ -206,6 +206,10 @@ int64_t ilm_dense_launch_count(void);
  * average launch duration of pass i.  The spectrum buffers (hundreds of MB at
  * 4096^2) exceed the L2, so no flush is needed between launches.            */
 int ilm_profile_conv(ilm_plan* plan, int layout, int reps, double ms[3]);
+/* Same, in Schur-probe mode: the right-hand sides are R e_col and R e_{col+1} (W x W patches), i.e. the
+ * launches ilm_create_schur(ILM_RTLINVR) issues: pass A transforms only the patch rows, pass B uses the
+ * sparse forward half transform.                                                                     */
+int ilm_profile_conv_probe(ilm_plan* plan, int col, int reps, double ms[3]);
 
 #ifdef __cplusplus
 }
