@@ -77,11 +77,28 @@ def _ptr(buf):
     return C.c_void_p(buf.ctypes.data)
 
 
+_PIN_MIN = 1 << 16          # host buffers of at least this many doubles are page-locked
+
+
+def _host_zeros(n):
+    """Host buffer for host mode.  Large buffers are page-locked (through torch) so that the
+    library's H2D/D2H staging runs at DMA speed instead of through the driver's bounce buffer."""
+    n = int(n)
+    if n >= _PIN_MIN:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.zeros(n, dtype=torch.float64).pin_memory().numpy()
+        except Exception:
+            pass
+    return np.zeros(n, dtype=np.float64)
+
+
 def _alloc(n, device):
     if device:
         import torch
         return torch.zeros(int(n), dtype=torch.float64, device="cuda")
-    return np.zeros(int(n), dtype=np.float64)
+    return _host_zeros(n)
 
 
 class _Data:
@@ -505,7 +522,7 @@ def _matrix(cache, ncols):
     if cache.device:
         import torch
         return torch.zeros(int(ncols) * cache.N, dtype=torch.float64, device="cuda")
-    return np.zeros(int(ncols) * cache.N, dtype=np.float64)
+    return _host_zeros(int(ncols) * cache.N)
 
 
 def _as_matrix(buf, N, ncols):
@@ -579,7 +596,8 @@ class LU:
             self.lu = buf.clone()
             self.ipiv = torch.zeros(n, dtype=torch.int32, device="cuda")
         else:
-            self.lu = buf.copy()
+            self.lu = _host_zeros(buf.shape[0])
+            self.lu[...] = buf
             self.ipiv = np.zeros(n, dtype=np.int32)
         self.n = n
         self.stream = stream
@@ -908,7 +926,7 @@ def _vmatrix(cache, which, scale, cols):
         import torch
         buf = torch.zeros(M * (c1 - c0), dtype=torch.float64, device="cuda")
     else:
-        buf = np.zeros(M * (c1 - c0), dtype=np.float64)
+        buf = _host_zeros(M * (c1 - c0))
     L.check(cache._lib.ilm_create_schur_vector(cache._plan, which, float(scale), int(c0), int(c1), _ptr(buf)))
     return _as_matrix(buf, M, c1 - c0)
 

@@ -120,16 +120,14 @@ static int surface_divergence_dev(ilm_plan* p, int mode, const double* f, double
     return launch_divergence(p, p->g_edges, p->g_edges + n_edges_u(p), out, deriv_div(p));
 }
 static int surface_grad_dev(ilm_plan* p, int mode, const double* phi, double* f) {
-    ILM_TRY(launch_grad(p, phi, p->g_edges, p->g_edges + n_edges_u(p), 1.0));
-    return launch_normal_interpolate(p, mode, p->g_edges, p->g_edges + n_edges_u(p), f, deriv_div(p));
+    return launch_normal_interpolate_fused(p, 0, mode, phi, f, deriv_div(p));     // grad fused into the gather
 }
 static int surface_curl_s2n_dev(ilm_plan* p, int mode, const double* f, double* out) {
     ILM_TRY(regularize_normal_dev(p, mode, f, p->g_edges));
     return launch_curl_e2n(p, p->g_edges, p->g_edges + n_edges_u(p), out, deriv_div(p));
 }
 static int surface_curl_n2s_dev(ilm_plan* p, int mode, const double* s, double* f) {
-    ILM_TRY(launch_curl_n2e(p, s, p->g_edges, p->g_edges + n_edges_u(p), 1.0));
-    return launch_normal_interpolate(p, mode, p->g_edges, p->g_edges + n_edges_u(p), f, deriv_div(p));
+    return launch_normal_interpolate_fused(p, 1, mode, s, f, deriv_div(p));       // curl fused into the gather
 }
 
 __global__ void k_unit(double* __restrict__ s, int n, int col) {
@@ -485,17 +483,8 @@ extern "C" int ilm_create_schur(ilm_plan* p, int which, double scale, int col_be
     if (io.status) return io.status;
     const int glayout = (which == ILM_CLINVCT) ? ILM_NODES_DUAL : ILM_NODES_PRIMAL;
     const int mode = (which == ILM_GLINVD_CROSS) ? ILM_CROSS : ILM_NORMAL;
-    double* unit = p->s_a;            // N
     double* sout = p->s_a + N;        // N
     double* gf[2] = {p->g_a, p->g_b};
-    auto pre = [&](int col, double* g) -> int {
-        ILM_TRY(set_unit(p, unit, col));
-        switch (which) {
-        case ILM_RTLINVR: return launch_regularize(p, p->tab[ILM_NODES_PRIMAL], unit, nullptr, 1.0, g, true);
-        case ILM_CLINVCT: return surface_curl_s2n_dev(p, mode, unit, g);
-        default: return surface_divergence_dev(p, mode, unit, g);
-        }
-    };
     auto post = [&](double* g, double* dst) -> int {
         switch (which) {
         case ILM_RTLINVR: ILM_TRY(launch_interpolate(p, p->tab[ILM_NODES_PRIMAL], g, sout)); break;
@@ -518,8 +507,24 @@ extern "C" int ilm_create_schur(ilm_plan* p, int which, double scale, int col_be
             ILM_TRY(launch_regularize_unit(p, tp, c, gf[0], rlo, rhi));
             if (two) ILM_TRY(launch_regularize_unit(p, tp, c + 1, gf[1], rlo, rhi));
         } else {
-            ILM_TRY(pre(c, gf[0]));
-            if (two) ILM_TRY(pre(c + 1, gf[1]));
+            // D_s e_c / C_s^T e_c: two WxW edge patches, then a stencil -> non-zero rows known in advance
+            const DevTable& tu = p->tab[ILM_XEDGES];
+            const DevTable& tv = p->tab[ILM_YEDGES];
+            int lo = std::min(tu.h_j0[c], tv.h_j0[c]), hi = std::max(tu.h_j0[c], tv.h_j0[c]) + tu.W;
+            if (two) {
+                lo = std::min(lo, std::min(tu.h_j0[c + 1], tv.h_j0[c + 1]));
+                hi = std::max(hi, std::max(tu.h_j0[c + 1], tv.h_j0[c + 1]) + tu.W);
+            }
+            const LayoutInfo lg = layout_info(glayout, p->g.NX, p->g.NY);
+            rlo = std::max(lo - 1, 0); rhi = std::min(hi + 1, lg.my);
+            if (rhi <= rlo) { rlo = 0; rhi = 1; }
+            double* eu = p->g_edges;
+            double* ev = p->g_edges + n_edges_u(p);
+            for (int q = 0; q < (two ? 2 : 1); ++q) {
+                ILM_TRY(launch_regularize_normal_unit(p, mode, c + q, eu, ev, rlo - 1, rhi + 1, true));
+                if (which == ILM_CLINVCT) ILM_TRY(launch_curl_e2n(p, eu, ev, gf[q], deriv_div(p), rlo, rhi));
+                else ILM_TRY(launch_divergence(p, eu, ev, gf[q], deriv_div(p), rlo, rhi));
+            }
         }
         ILM_TRY(conv_apply(p, 0, fref(p, glayout, gf[0]), two ? fref(p, glayout, gf[1]) : FieldRef{nullptr, 0, 0}, rlo, rhi));
         ILM_TRY(post(gf[0], dA + (size_t)(c - col_begin) * N));

@@ -159,7 +159,7 @@ ILM_HD void passA_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
 // a WxW patch): X_py[k] = sum_r x_r w_{2L}^{r (2k + py)} summed directly, k = j + e*T.
 // About 300 FP64 instructions and no shared-memory exchange, against ~780 and two exchanges
 // for the full transform; used when the row range is short.
-constexpr int SPARSE_MAX_ROWS = 10;
+constexpr int SPARSE_MAX_ROWS = 16;
 template <int L, class Ctx>
 ILM_HD void sparse_forward(double2* v, Ctx& ctx, const ConvArgs& a, double2* xb, int px, int m, int py, int j, bool live) {
     const int nrows = a.rhi - a.rlo;

@@ -123,10 +123,13 @@ int launch_interpolate(ilm_plan* p, const DevTable& t, const double* field, doub
 int launch_normal_interpolate(ilm_plan* p, int mode, const double* u, const double* v, double* f, double div);
 // out rows [rlo, rhi) = R e_col (zero elsewhere in that row range); other rows untouched
 int launch_regularize_unit(ilm_plan* p, const DevTable& t, int col, double* out, int rlo, int rhi);
-int launch_divergence(ilm_plan* p, const double* u, const double* v, double* out, double div);
+// ybeg/yend: only output rows [ybeg, yend) are written (-1: all rows)
+int launch_divergence(ilm_plan* p, const double* u, const double* v, double* out, double div, int ybeg = -1, int yend = -1);
+int launch_normal_interpolate_fused(ilm_plan* p, int op, int mode, const double* nodes, double* f, double div);
+int launch_regularize_normal_unit(ilm_plan* p, int mode, int col, double* u, double* v, int flo, int fhi, bool fill);
 int launch_grad(ilm_plan* p, const double* in, double* u, double* v, double div);
 int launch_curl_n2e(ilm_plan* p, const double* s, double* u, double* v, double div);
-int launch_curl_e2n(ilm_plan* p, const double* u, const double* v, double* w, double div);
+int launch_curl_e2n(ilm_plan* p, const double* u, const double* v, double* w, double div, int ybeg = -1, int yend = -1);
 int launch_laplacian(ilm_plan* p, const double* in, double* out, int mx, int my, double factor);
 int launch_scale_store_column(ilm_plan* p, const double* src, double* dst, int n, double scale);
 int launch_scale(ilm_plan* p, double* w, size_t n, double scale);

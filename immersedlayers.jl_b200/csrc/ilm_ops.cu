@@ -227,6 +227,99 @@ __global__ void k_normal_interpolate(int N, TabView tu, TabView tv, const double
     }
 }
 
+// Fused  n . E_f (G phi)  /  n . E_f (C s): the edge value is formed on the fly from the node field
+// (same difference, same multiply as stencil-then-gather: bit-identical, one full-field sweep less).
+// OP 0: grad of Nodes{Primal}; OP 1: curl of Nodes{Dual}.  COMP 0: u entries, 1: v entries.
+template <int OP, int COMP>
+__device__ __forceinline__ double gather16_edge(const TabView& t, const double* __restrict__ nf, int NX, int NY, int k,
+                                                int slot, bool live) {
+    double val = 0.0;
+    const int W2 = t.W * t.W;
+    if (live && slot < W2) {
+        const int a = slot % t.W, b = slot / t.W;
+        const int i = t.i0[k] + a, j = t.j0[k] + b;
+        if (i >= 0 && i < t.mx && j >= 0 && j < t.my) {
+            double ev = 0.0;
+            const int mp = NX - 1;
+            if (OP == 0) {
+                if (COMP == 0) { if (i >= 1 && i <= NX - 2) ev = nf[(size_t)j * mp + i] - nf[(size_t)j * mp + i - 1]; }
+                else { if (j >= 1 && j <= NY - 2) ev = nf[(size_t)j * mp + i] - nf[(size_t)(j - 1) * mp + i]; }
+            } else {
+                if (COMP == 0) ev = nf[(size_t)(j + 1) * NX + i] - nf[(size_t)j * NX + i];
+                else ev = nf[(size_t)j * NX + i] - nf[(size_t)j * NX + i + 1];
+            }
+            val = __dmul_rn(t.wE[(size_t)k * W2 + slot], ev);
+        }
+    }
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) val += __shfl_down_sync(0xffffffffu, val, off, 16);
+    return val;
+}
+
+template <int OP>
+__global__ void k_normal_interpolate_fused(int N, TabView tu, TabView tv, const double* __restrict__ nf, int NX, int NY,
+                                           const double* __restrict__ nx, const double* __restrict__ ny, int mode,
+                                           double div, double* __restrict__ f) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = gid >> 4, slot = gid & 15;
+    const double su = gather16_edge<OP, 0>(tu, nf, NX, NY, k, slot, k < N);
+    const double sv = gather16_edge<OP, 1>(tv, nf, NX, NY, k, slot, k < N);
+    if (slot == 0 && k < N) {
+        double r;
+        if (mode == ILM_NORMAL) r = __dadd_rn(__dmul_rn(nx[k], su), __dmul_rn(ny[k], sv));
+        else r = __dsub_rn(__dmul_rn(nx[k], sv), __dmul_rn(ny[k], su));
+        f[k] = r / div;
+    }
+}
+
+// op 0: f = n . E_f G phi / div (phi: Nodes{Primal}); op 1: f = n . E_f C s / div (s: Nodes{Dual})
+int launch_normal_interpolate_fused(ilm_plan* p, int op, int mode, const double* nodes, double* f, double div) {
+    if (p->N == 0) return ILM_OK;
+    const int threads = p->N * 16, blocks = (threads + 127) / 128;
+    if (op == 0)
+        k_normal_interpolate_fused<0><<<blocks, 128, 0, p->stream>>>(p->N, view(p->tab[ILM_XEDGES]), view(p->tab[ILM_YEDGES]),
+                                                                    nodes, p->g.NX, p->g.NY, p->nx, p->ny, mode, div, f);
+    else
+        k_normal_interpolate_fused<1><<<blocks, 128, 0, p->stream>>>(p->N, view(p->tab[ILM_XEDGES]), view(p->tab[ILM_YEDGES]),
+                                                                    nodes, p->g.NX, p->g.NY, p->nx, p->ny, mode, div, f);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// unit-vector probe of regularize_normal!: rows [flo, fhi) of both Edges components are zeroed and the
+// two WxW patches n_u R_u e_col, n_v R_v e_col written (mode NORMAL: (n.u, n.v); CROSS: (n.v, -n.u))
+__global__ void k_regularize_normal_unit(int W, int NX, int NY, const int* __restrict__ iu, const int* __restrict__ ju,
+                                         const double* __restrict__ wu, const int* __restrict__ iv,
+                                         const int* __restrict__ jv, const double* __restrict__ wv,
+                                         const double* __restrict__ nx, const double* __restrict__ ny, int mode, int col,
+                                         double* __restrict__ u, double* __restrict__ v) {
+    const int slot = threadIdx.x & 15, comp = threadIdx.x >> 4;
+    if (slot >= W * W || comp > 1) return;
+    const int a = slot % W, b = slot / W;
+    const double fu = mode == ILM_NORMAL ? nx[col] : ny[col];
+    const double fv = mode == ILM_NORMAL ? ny[col] : -nx[col];
+    if (comp == 0) {
+        const int i = iu[col] + a, j = ju[col] + b;
+        if (i >= 0 && i < NX && j >= 0 && j < NY - 1) u[(size_t)j * NX + i] = __dmul_rn(wu[(size_t)col * W * W + slot], fu);
+    } else {
+        const int i = iv[col] + a, j = jv[col] + b;
+        if (i >= 0 && i < NX - 1 && j >= 0 && j < NY) v[(size_t)j * (NX - 1) + i] = __dmul_rn(wv[(size_t)col * W * W + slot], fv);
+    }
+}
+int launch_regularize_normal_unit(ilm_plan* p, int mode, int col, double* u, double* v, int flo, int fhi, bool fill) {
+    const DevTable& tu = p->tab[ILM_XEDGES];
+    const DevTable& tv = p->tab[ILM_YEDGES];
+    if (fill) {
+        const int ulo = max(flo, 0), uhi = min(fhi, tu.my), vlo = max(flo, 0), vhi = min(fhi, tv.my);
+        if (uhi > ulo) ILM_TRY(launch_fill(p, u + (size_t)ulo * tu.mx, (size_t)(uhi - ulo) * tu.mx, 0.0));
+        if (vhi > vlo) ILM_TRY(launch_fill(p, v + (size_t)vlo * tv.mx, (size_t)(vhi - vlo) * tv.mx, 0.0));
+    }
+    k_regularize_normal_unit<<<1, 32, 0, p->stream>>>(tu.W, p->g.NX, p->g.NY, tu.i0, tu.j0, tu.wR, tv.i0, tv.j0, tv.wR, p->nx,
+                                                      p->ny, mode, col, u, v);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
 int launch_normal_interpolate(ilm_plan* p, int mode, const double* u, const double* v, double* f, double div) {
     if (p->N == 0) return ILM_OK;
     const int threads = p->N * 16;
@@ -244,24 +337,25 @@ static dim3 st_grid(int NX, int NY) { return dim3((NX + ST_BX - 1) / ST_BX, (NY 
 
 // p[x,y] = -u[x,y] + u[x+1,y] - v[x,y] + v[x,y+1]          (A.3)
 __global__ void k_divergence(int NX, int NY, const double* __restrict__ u, const double* __restrict__ v,
-                             double* __restrict__ out, double div) {
+                             double* __restrict__ out, double div, int ybeg, int yend) {
     const int x = blockIdx.x * ST_BX + threadIdx.x;
-    const int y0 = blockIdx.y * ST_ROWS;
+    const int y0 = ybeg + blockIdx.y * ST_ROWS;
     if (x >= NX - 1) return;
     const int mxv = NX - 1;
     double vprev = (y0 < NY) ? v[(size_t)y0 * mxv + x] : 0.0;
 #pragma unroll
     for (int r = 0; r < ST_ROWS; ++r) {
         const int y = y0 + r;
-        if (y >= NY - 1) break;
+        if (y >= NY - 1 || y >= yend) break;
         const double vn = v[(size_t)(y + 1) * mxv + x];
         const double ul = u[(size_t)y * NX + x], ur = u[(size_t)y * NX + x + 1];
         out[(size_t)y * mxv + x] = (((-ul + ur) - vprev) + vn) / div;
         vprev = vn;
     }
 }
-int launch_divergence(ilm_plan* p, const double* u, const double* v, double* out, double div) {
-    k_divergence<<<st_grid(p->g.NX, p->g.NY), ST_BX, 0, p->stream>>>(p->g.NX, p->g.NY, u, v, out, div);
+int launch_divergence(ilm_plan* p, const double* u, const double* v, double* out, double div, int ybeg, int yend) {
+    if (ybeg < 0) { ybeg = 0; yend = p->g.NY; }
+    k_divergence<<<st_grid(p->g.NX, yend - ybeg), ST_BX, 0, p->stream>>>(p->g.NX, p->g.NY, u, v, out, div, ybeg, yend);
     ILM_LAUNCHED(p);
     return ILM_OK;
 }
@@ -327,16 +421,16 @@ int launch_curl_n2e(ilm_plan* p, const double* s, double* u, double* v, double d
 
 // w[x,y] = u[x,y-1]-u[x,y]-v[x-1,y]+v[x,y], x in 2:NX-1, y in 2:NY-1, zero elsewhere
 __global__ void k_curl_e2n(int NX, int NY, const double* __restrict__ u, const double* __restrict__ v,
-                           double* __restrict__ w, double div) {
+                           double* __restrict__ w, double div, int ybeg, int yend) {
     const int x = blockIdx.x * ST_BX + threadIdx.x;
-    const int y0 = blockIdx.y * ST_ROWS;
+    const int y0 = ybeg + blockIdx.y * ST_ROWS;
     if (x >= NX) return;
     const int mxv = NX - 1;
     double uprev = (y0 >= 1 && y0 - 1 < NY - 1) ? u[(size_t)(y0 - 1) * NX + x] : 0.0;
 #pragma unroll
     for (int r = 0; r < ST_ROWS; ++r) {
         const int y = y0 + r;
-        if (y >= NY) break;
+        if (y >= NY || y >= yend) break;
         const double uc = (y < NY - 1) ? u[(size_t)y * NX + x] : 0.0;
         double val = 0.0;
         if (x >= 1 && x <= NX - 2 && y >= 1 && y <= NY - 2)
@@ -345,8 +439,9 @@ __global__ void k_curl_e2n(int NX, int NY, const double* __restrict__ u, const d
         uprev = uc;
     }
 }
-int launch_curl_e2n(ilm_plan* p, const double* u, const double* v, double* w, double div) {
-    k_curl_e2n<<<st_grid(p->g.NX, p->g.NY), ST_BX, 0, p->stream>>>(p->g.NX, p->g.NY, u, v, w, div);
+int launch_curl_e2n(ilm_plan* p, const double* u, const double* v, double* w, double div, int ybeg, int yend) {
+    if (ybeg < 0) { ybeg = 0; yend = p->g.NY; }
+    k_curl_e2n<<<st_grid(p->g.NX, yend - ybeg), ST_BX, 0, p->stream>>>(p->g.NX, p->g.NY, u, v, w, div, ybeg, yend);
     ILM_LAUNCHED(p);
     return ILM_OK;
 }
