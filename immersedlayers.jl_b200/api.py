@@ -983,3 +983,83 @@ def create_RTLinvR_direct(cache, scale=1.0, cols=None):
     buf = _matrix(cache, c1 - c0)
     L.check(cache._lib.ilm_create_RTLinvR_direct(cache._plan, float(scale), int(c0), int(c1), _ptr(buf)))
     return _as_matrix(buf, cache.N, c1 - c0)
+
+
+def neumann_poisson(cache, vnplus, vnminus=None, S=None):
+    """The Neumann Poisson solve of test/literate/neumann.jl:101-142 on the B200 path (config C2):
+    S = create_CLinvCT(cache); returns (f, df, s, ds) = potential, its surface jump, streamfunction
+    and its jump.  Host-mode or device-mode containers follow the cache."""
+    N = cache.N
+    vnplus = np.asarray(vnplus, dtype=np.float64)
+    vnminus = np.zeros(N) if vnminus is None else np.asarray(vnminus, dtype=np.float64)
+    if S is None:
+        S = create_CLinvCT(cache)
+    lu = LU(S)
+    dvn = cache.zeros_surface().set(vnplus - vnminus)
+    vn = 0.5 * (vnplus + vnminus)
+    fstar = cache.zeros_grid()
+    regularize(fstar, dvn, cache)
+    inverse_laplacian(fstar, cache)
+    df = cache.zeros_surface()
+    surface_grad(df, fstar, cache)
+    df.set(_neg_solve(lu, vn, df, cache))
+    f = cache.zeros_grid()
+    surface_divergence(f, df, cache)
+    inverse_laplacian(f, cache)
+    _iadd(f, fstar)
+    # streamfunction
+    sstar = cache.zeros_gridcurl()
+    surface_curl(sstar, df, cache)
+    ds = cache.zeros_surface()
+    surface_grad_cross(ds, fstar, cache)
+    sol = lu.solve(ds.data)
+    _assign(ds, sol)
+    s = cache.zeros_gridcurl()
+    surface_curl_cross(s, ds, cache)
+    _isub(s, sstar)
+    _iscale(s, -1.0)
+    inverse_laplacian(s, cache)
+    return f, df, s, ds
+
+
+def _to_host(x):
+    return x.detach().cpu().numpy() if _is_torch(x) else np.asarray(x)
+
+
+def _dev(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _neg_solve(lu, vn, df, cache):
+    """-(S \\ (vn - df)) as a host array."""
+    rhs = (_dev(vn) - df.data) if cache.device else (vn - df.data)
+    return -_to_host(lu.solve(rhs))
+
+
+def _assign(d, values):
+    if _is_torch(d.data):
+        d.data.copy_(values if _is_torch(values) else _dev(values))
+    else:
+        d.data[...] = _to_host(values)
+
+
+def _iadd(a, b):
+    if _is_torch(a.data):
+        a.data.add_(b.data)
+    else:
+        a.data += b.data
+
+
+def _isub(a, b):
+    if _is_torch(a.data):
+        a.data.sub_(b.data)
+    else:
+        a.data -= b.data
+
+
+def _iscale(a, c):
+    if _is_torch(a.data):
+        a.data.mul_(c)
+    else:
+        a.data *= c

@@ -830,6 +830,28 @@ def dirichlet_solve(cache, fplus, fminus=None, S=None):
     return f, s, S
 
 
+def neumann_solve(cache, vnplus, vnminus=None, S=None):
+    """Block-LU Neumann Poisson with streamfunction (test/literate/neumann.jl:101-142).
+    Returns (f, df, s, ds, S)."""
+    vnminus = np.zeros_like(vnplus) if vnminus is None else vnminus
+    dvn = vnplus - vnminus
+    vn = 0.5 * (vnplus + vnminus)
+    if S is None:
+        S = cache.create_CLinvCT()
+    lu = scipy.linalg.lu_factor(S)
+    fstar = cache.inverse_laplacian(cache.regularize(dvn))
+    df = cache.surface_grad(fstar)
+    df = vn - df
+    df = -scipy.linalg.lu_solve(lu, df)
+    f = cache.inverse_laplacian(cache.surface_divergence(df)) + fstar
+    sstar = cache.surface_curl_s2n(df)
+    ds = scipy.linalg.lu_solve(lu, cache.surface_grad_cross(fstar))
+    s = cache.surface_curl_cross_s2n(ds)
+    s = (s - sstar) * -1.0
+    s = cache.inverse_laplacian(s)
+    return f, df, s, ds, S
+
+
 # --------------------------------------------------------------------------
 # inner products of the reference used by the pinning tests
 # --------------------------------------------------------------------------

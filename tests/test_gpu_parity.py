@@ -417,3 +417,16 @@ def test_reference_lgf_rule(c1):
     body = ilm.bodies.circle(1.0, 1.4 * g.dx)
     cache, oc = make_case(g.NX, g.NY, g.dx, g.I0, body, lgf_rule="gl100")
     assert relerr(ilm.create_RTLinvR(cache), oc.create_RTLinvR()) < RTOL
+
+
+def test_neumann_poisson_c1(c1):
+    """test/literate/neumann.jl:101-142 (BASELINE config C2 algorithm) GPU vs oracle, every output."""
+    cache, oc = c1
+    vnp = cache.normals()[0].copy()
+    fr, dfr, sr, dsr, Sr = o.neumann_solve(oc, vnp)
+    f, df, s, ds = ilm.neumann_poisson(cache, vnp, S=Sr)
+    tol = 200 * np.linalg.cond(Sr) * np.finfo(float).eps
+    assert relerr(df.data, dfr) < tol and relerr(ds.data, dsr) < tol
+    assert relerr(f.array(), fr) < 1e-9 and relerr(s.array(), sr) < 1e-9
+    f2, df2, _, _ = ilm.neumann_poisson(cache, vnp)          # S built on the GPU
+    assert relerr(df2.data, dfr) < tol

@@ -350,3 +350,11 @@ def test_vector_schur_and_adjoints(small_vcache):
     # mask on Edges integrates to the body area
     mu, mv = c.mask_edges()
     assert abs(o.dot_grid(g, mu, np.ones_like(mu), o.XEDGE) - np.pi) < 3e-2
+
+
+def test_neumann_added_mass(small_cache):
+    """test/literate/neumann.jl: v_n+ = n_x on the unit circle; the potential jump df ~ -2 x and the
+    added mass  -int df n_x ds  -> pi (examples/neumann.ipynb reports the coefficient of a small circle)."""
+    c = small_cache
+    f, df, s, ds, S = o.neumann_solve(c, c.nx.copy())
+    assert abs(np.sum(df * c.nx * c.ds) + np.pi) < 0.15
