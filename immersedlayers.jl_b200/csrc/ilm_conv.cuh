@@ -209,10 +209,20 @@ ILM_HD void passB_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
     if (MODE == 0) {
         if (!py) { ctx.arrive(BAR_FREE); ctx.delay(a.skew_ns); }
     }
-    for (int w = block; w < nwork; w += nblocks) {
-        const int wn = w + nblocks;
-        if (wn < nwork && a.rhi - a.rlo == a.g.MYp) {
-            const size_t e0 = (size_t)wn * CPW * col_elems;
+    // Work order: inside each parity block the tile columns are visited from both ends
+    // (0, last, 1, last-1, ...) so that a column and its mirror kx <-> PX-kx, which share one
+    // Ghat column, are processed at about the same time by neighbouring CTAs: Ghat is read from
+    // DRAM once and hit in L2 the second time (F == 1 only; smaller transforms keep the identity).
+    auto tile_of = [&](int w) {
+        if (F != 1) return w;
+        const int half = a.g.Lx >> 1, blk = w / half, t = w % half;
+        return blk * half + ((t & 1) ? half - 1 - (t >> 1) : (t >> 1));
+    };
+    for (int w0 = block; w0 < nwork; w0 += nblocks) {
+        const int w = tile_of(w0);
+        const int wn0 = w0 + nblocks;
+        if (wn0 < nwork && a.rhi - a.rlo == a.g.MYp) {
+            const size_t e0 = (size_t)tile_of(wn0) * CPW * col_elems;
             size_t ne = (size_t)CPW * col_elems;
             if (e0 + ne > s_elems(a.g)) ne = s_elems(a.g) - e0;
             prefetch_range(ctx, a.S + e0, ne * sizeof(double2));
