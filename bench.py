@@ -250,7 +250,10 @@ def main():
     fp64_winst_B = 2 * Lx * 2 * (782 + 300) * 8
     roofline = {"bound": "hbm",
                 "kernel": f"ilm_passB_L{Ly} in Schur-probe mode (column pass: sparse forward DFT_y * Ghat * IFFT_y, 2 columns of S per launch)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu capture at 4096^2
+                # (profiles/r1_passB_probe_dram.txt); null for other grids
+                "traffic": 957.5e6 if args.grid == 4096 else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_probe_B,
                 "launch_ms": float(msq[1]),
                 "dense_equivalent_frac": bytes_pass["B_columns"] / (float(msq[1]) * 1e-3) / 1e9 / peak,
