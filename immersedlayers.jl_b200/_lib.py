@@ -65,6 +65,7 @@ SIGNATURES = {
     "ilm_surface_curl_n2s": (_i, [_vp, _i, _dp, _dp]),
     "ilm_mask": (_i, [_vp, _dp]),
     "ilm_create_schur": (_i, [_vp, _i, _d, _i, _i, _dp]),
+    "ilm_create_schur_kernel": (_i, [_vp, _i, _i, _d, _i, _i, _dp]),
     "ilm_create_RTLinvR_direct": (_i, [_vp, _d, _i, _i, _dp]),
     "ilm_create_nRTRn": (_i, [_vp, _d, _dp]),
     "ilm_create_surface_filter": (_i, [_vp, _dp]),

@@ -1063,3 +1063,16 @@ def _iscale(a, c):
         a.data.mul_(c)
     else:
         a.data *= c
+
+
+def create_RTHR(cache, kernel_id, scale=1.0, cols=None):
+    """-scale * E H R with H the convolution kernel `kernel_id` registered with
+    `cache.add_kernel` (e.g. the integrating factor exp(L a), `lgf.intfact_table`): the Schur
+    complement `S_i = -B2 H_i B1^T` of an IF-HERK stage (src/timemarching.jl:86-107 through
+    ConstrainedSystems).  kernel_id = 0 is create_RTLinvR."""
+    if _is_vector(cache):
+        raise MethodError("create_RTHR: scalar caches only")
+    c0, c1 = (0, cache.N) if cols is None else cols
+    buf = _matrix(cache, c1 - c0)
+    L.check(cache._lib.ilm_create_schur_kernel(cache._plan, L.RTLINVR, int(kernel_id), float(scale), int(c0), int(c1), _ptr(buf)))
+    return _as_matrix(buf, cache.N, c1 - c0)

@@ -471,8 +471,13 @@ extern "C" int ilm_mask(ilm_plan* p, double* nodes) {
 }
 
 // ---------------------------------------------------------------- Schur builders
-extern "C" int ilm_create_schur(ilm_plan* p, int which, double scale, int col_begin, int col_end, double* A) {
+// `kernel_id` selects the convolution kernel between the pre- and post-operator: 0 = L^-1 (the
+// reference's builders), any id returned by ilm_add_kernel gives e.g. -E exp(L a) R, the Schur
+// complement of an IF-HERK stage (src/timemarching.jl:86-107 via ConstrainedSystems)
+extern "C" int ilm_create_schur_kernel(ilm_plan* p, int which, int kernel_id, double scale, int col_begin, int col_end,
+                                       double* A) {
     ILM_CHECK_PLAN(p);
+    if (kernel_id < 0 || kernel_id >= (int)p->kernels.size()) { set_error("ilm_create_schur_kernel: unknown kernel id"); return ILM_EINVAL; }
     const int N = p->N;
     if (which < ILM_RTLINVR || which > ILM_GLINVD_CROSS) { set_error("ilm_create_schur: unknown matrix"); return ILM_EINVAL; }
     if (col_begin < 0 || col_end > N || col_begin > col_end) { set_error("ilm_create_schur: bad column range"); return ILM_ESIZE; }
@@ -504,8 +509,7 @@ extern "C" int ilm_create_schur(ilm_plan* p, int which, double scale, int col_be
             if (two) { rlo = std::min(rlo, tp.h_j0[c + 1]); rhi = std::max(rhi, tp.h_j0[c + 1] + tp.W); }
             rlo = std::max(rlo, 0); rhi = std::min(rhi, tp.my);
             if (rhi <= rlo) { rlo = 0; rhi = 1; }
-            ILM_TRY(launch_regularize_unit(p, tp, c, gf[0], rlo, rhi));
-            if (two) ILM_TRY(launch_regularize_unit(p, tp, c + 1, gf[1], rlo, rhi));
+            ILM_TRY(launch_probe_pre(p, tp, c, two ? 2 : 1, gf[0], gf[1], rlo, rhi));
         } else {
             // D_s e_c / C_s^T e_c: two WxW edge patches, then a stencil -> non-zero rows known in advance
             const DevTable& tu = p->tab[ILM_XEDGES];
@@ -526,11 +530,20 @@ extern "C" int ilm_create_schur(ilm_plan* p, int which, double scale, int col_be
                 else ILM_TRY(launch_divergence(p, eu, ev, gf[q], deriv_div(p), rlo, rhi));
             }
         }
-        ILM_TRY(conv_apply(p, 0, fref(p, glayout, gf[0]), two ? fref(p, glayout, gf[1]) : FieldRef{nullptr, 0, 0}, rlo, rhi));
-        ILM_TRY(post(gf[0], dA + (size_t)(c - col_begin) * N));
-        if (two) ILM_TRY(post(gf[1], dA + (size_t)(c + 1 - col_begin) * N));
+        ILM_TRY(conv_apply(p, kernel_id, fref(p, glayout, gf[0]), two ? fref(p, glayout, gf[1]) : FieldRef{nullptr, 0, 0}, rlo, rhi));
+        if (which == ILM_RTLINVR && kernel_id >= 0) {
+            ILM_TRY(launch_probe_post(p, tp, two ? 2 : 1, gf[0], gf[1], -scale, dA + (size_t)(c - col_begin) * N,
+                                      dA + (size_t)(c + 1 - col_begin) * N));
+        } else {
+            ILM_TRY(post(gf[0], dA + (size_t)(c - col_begin) * N));
+            if (two) ILM_TRY(post(gf[1], dA + (size_t)(c + 1 - col_begin) * N));
+        }
     }
     return io.finish();
+}
+
+extern "C" int ilm_create_schur(ilm_plan* p, int which, double scale, int col_begin, int col_end, double* A) {
+    return ilm_create_schur_kernel(p, which, 0, scale, col_begin, col_end, A);
 }
 
 extern "C" int ilm_create_nRTRn(ilm_plan* p, double scale, double* A) {

@@ -136,6 +136,9 @@ int launch_scale(ilm_plan* p, double* w, size_t n, double scale);
 int launch_lgf_prep(ilm_plan* p, const double* table, int ld, int NX, int NY, double c0, double* h);
 int launch_filter_rowsum(ilm_plan* p, DevTable& t);
 int launch_surface_filter(ilm_plan* p, const DevTable& t, double* C);
+int launch_probe_pre(ilm_plan* p, const DevTable& t, int col0, int ncol, double* g0, double* g1, int rlo, int rhi);
+int launch_probe_post(ilm_plan* p, const DevTable& t, int ncol, const double* g0, const double* g1, double coef, double* d0,
+                      double* d1);
 int launch_schur_direct(ilm_plan* p, const double* G, int ldg, double scale, int col_begin, int col_end, double* A);
 // vector-cache pieces (TensorData = [dudx; dudy; dvdx; dvdy], EdgeGradient likewise)
 int launch_tensor_from_vector(ilm_plan* p, int mode, const double* v, double* T);

@@ -680,3 +680,57 @@ int launch_schur_direct(ilm_plan* p, const double* G, int ldg, double scale, int
 }
 
 }  // namespace ilm
+
+// =====================================================================================
+// Fused pre/post kernels of the create_RTLinvR probe (two columns per launch):
+//   pre : rows [rlo, rhi) of the two right-hand sides = R e_c0, R e_c1 (zero elsewhere in the rows)
+//   post: A[:, c] = coef * E field_c   for both fields
+// (replace 2 fills + 2 scatters and 2 interpolations + 2 scale-stores per column pair)
+// =====================================================================================
+namespace ilm {
+
+__global__ void k_probe_pre(int W, int mx, int my, const int* __restrict__ i0, const int* __restrict__ j0,
+                            const double* __restrict__ wR, int col0, int ncol, double* __restrict__ g0,
+                            double* __restrict__ g1, int rlo, int rhi) {
+    const int q = blockIdx.y;                   // which column / field
+    if (q >= ncol) return;
+    const int col = col0 + q;
+    double* out = q ? g1 : g0;
+    const int ci = i0[col], cj = j0[col];
+    const size_t n = (size_t)(rhi - rlo) * mx;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t % mx), j = rlo + (int)(t / mx);
+        const int a = i - ci, b = j - cj;
+        double v = 0.0;
+        if (a >= 0 && a < W && b >= 0 && b < W) v = wR[(size_t)col * W * W + b * W + a];
+        out[(size_t)j * mx + i] = v;
+    }
+}
+int launch_probe_pre(ilm_plan* p, const DevTable& t, int col0, int ncol, double* g0, double* g1, int rlo, int rhi) {
+    const size_t n = (size_t)(rhi - rlo) * t.mx;
+    int bx = (int)((n + 255) / 256);
+    if (bx > 2 * p->nsm) bx = 2 * p->nsm;
+    k_probe_pre<<<dim3(bx, ncol), 256, 0, p->stream>>>(t.W, t.mx, t.my, t.i0, t.j0, t.wR, col0, ncol, g0, g1, rlo, rhi);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+__global__ void k_probe_post(int N, TabView t, const double* __restrict__ g0, const double* __restrict__ g1, double coef,
+                             double* __restrict__ d0, double* __restrict__ d1) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = gid >> 4, slot = gid & 15;
+    const double* field = blockIdx.y ? g1 : g0;
+    double* dst = blockIdx.y ? d1 : d0;
+    const double v = gather16(t, field, k, slot, k < N);
+    if (slot == 0 && k < N) dst[k] = coef * v;
+}
+int launch_probe_post(ilm_plan* p, const DevTable& t, int ncol, const double* g0, const double* g1, double coef, double* d0,
+                      double* d1) {
+    if (p->N == 0) return ILM_OK;
+    const int threads = p->N * 16;
+    k_probe_post<<<dim3((threads + 127) / 128, ncol), 128, 0, p->stream>>>(p->N, view(t), g0, g1, coef, d0, d1);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+}  // namespace ilm

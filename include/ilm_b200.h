@@ -137,6 +137,11 @@ int ilm_mask(ilm_plan* plan, double* nodes_primal);
  * leading dimension N into A (N x (col_end-col_begin)).  Column ranges are the
  * multi-GPU shard.                                                          */
 int ilm_create_schur(ilm_plan* plan, int which, double scale, int col_begin, int col_end, double* A);
+/* Same probing with another convolution kernel between the pre- and post-operator (ids from
+ * ilm_add_kernel; 0 = L^-1): -scale * E exp(L a) R is the Schur complement of an IF-HERK stage
+ * (`S_i = -B2 H_i B1^T`, src/timemarching.jl:86-107 via ConstrainedSystems). */
+int ilm_create_schur_kernel(ilm_plan* plan, int which, int kernel_id, double scale, int col_begin, int col_end,
+                            double* A);
 /* Same matrix as ilm_create_schur(ILM_RTLINVR) from the direct-table identity
  * S[k,l] = -(scale/factor) sum_p sum_q E[k,p] (G(|p-q|) - c0) R[q,l]: no
  * transform, O(N^2 W^4) look-ups.  Cross-check of the column-solve path and an optional fast

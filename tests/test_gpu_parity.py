@@ -430,3 +430,24 @@ def test_neumann_poisson_c1(c1):
     assert relerr(f.array(), fr) < 1e-9 and relerr(s.array(), sr) < 1e-9
     f2, df2, _, _ = ilm.neumann_poisson(cache, vnp)          # S built on the GPU
     assert relerr(df2.data, dfr) < tol
+
+
+def test_ifherk_stage_schur_complement(c1):
+    """S_i = -E exp(L a) R, a = Fo/2 = 0.5: the integrating-factor
+    kernel on the same engine, probed like create_RTLinvR."""
+    cache, oc = c1
+    g = cache.g
+    E = ilm.lgf.intfact_table(0.5, g.NX)
+    kid = cache.add_kernel(E)
+    S = ilm.create_RTHR(cache, kid)
+    plan = o.ConvPlan(E[:g.NX, :g.NY])
+    Sref = np.zeros((cache.N, cache.N))
+    for c in range(cache.N):
+        e = np.zeros(cache.N); e[c] = 1.0
+        Sref[:, c] = -oc.interpolate(plan.apply(oc.regularize(e)))
+    assert relerr(S, Sref) < RTOL
+    # a = 0: H = I, S_3 = -E R (stage 3 of LiskaIFHERK)
+    kid0 = cache.add_kernel(ilm.lgf.intfact_table(0.0, g.NX))
+    S3 = ilm.create_RTHR(cache, kid0)
+    ER = -(o.E_matrix(oc.tabs[o.PRIMAL]) @ o.R_matrix(oc.tabs[o.PRIMAL])).toarray()
+    assert relerr(S3, ER) < RTOL
