@@ -129,3 +129,24 @@ def test_schur_columns_match_direct_table_form(big):
         dj = np.abs(pj[rows][:, :, None] - qj[None, None, :])
         val = -np.einsum("kp,kpq,q->k", E[rows], G[di, dj] - c0, R) / factor
         assert relerr(S[rows, c - c_lo], val) < 1e-11
+
+
+def test_multibody_c4_schur_block_fullsize():
+    """BASELINE config C4: 8 cylinders + a flat plate (~4400 points incl. an open body) on 4096^2.
+    Column-solve blocks of S against the transform-free table form, plus the moving-body refresh
+    (update_points keeps Ghat)."""
+    g = ilm.PhysicalGrid.centered(NG)
+    body = ilm.bodies.multibody_c4(g.dx)
+    G = ilm.lgf.lgf_table(NG, cache_dir="/tmp/ilm_lgf_cache")
+    cache = ilm.SurfaceScalarCache(body[:5], g, lgf_table=G)
+    N = cache.N
+    assert 4300 < N < 4500 and body[5].shape[0] == 10
+    for c0 in (0, N // 2 - 7, N - 12):            # first circle, across a body boundary, the plate
+        blk = ilm.create_RTLinvR(cache, cols=(c0, c0 + 12))
+        ref = ilm.create_RTLinvR_direct(cache, cols=(c0, c0 + 12))
+        assert relerr(blk, ref) < 1e-12
+    # C3-style refresh: translate every body, same plan
+    moved = (body[0] + 0.137, body[1] - 0.059, body[2], body[3], body[4])
+    cache.update_points(moved)
+    blk = ilm.create_RTLinvR(cache, cols=(100, 108))
+    assert relerr(blk, ilm.create_RTLinvR_direct(cache, cols=(100, 108))) < 1e-12
