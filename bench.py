@@ -154,6 +154,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # Libraries (NCCL prints its version banner on stdout) must not pollute the one JSON line:
+    # everything written to fd 1 goes to stderr until the final print.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import ilm_b200 as ilm
@@ -369,7 +375,8 @@ def main():
                        "checksum_f": checksum},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(lc2 - lc1), "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -168,6 +168,105 @@ k_lu_panel_cluster(int n, int k0, int nb, double* __restrict__ A, int* __restric
     cl.sync();                                       // no CTA leaves while a peer may still read its smem
 }
 
+// ---- panel held in shared memory: each of the 8 CTAs of the cluster keeps its slice of the panel
+// (rows x nb) in its shared memory for all nb column steps; pivot candidates, the pivot row and the
+// row that is swapped out travel through distributed shared memory.  Per column: one block reduction,
+// two cluster barriers, no global memory traffic.
+__global__ void __cluster_dims__(PANEL_CTAS, 1, 1) __launch_bounds__(1024)
+k_lu_panel_smem(int n, int k0, int nb, int ldp, double* __restrict__ A, int* __restrict__ ipiv) {
+    extern __shared__ double P[];                    // [ldp][nb] column-major slice
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ double c_val;
+    __shared__ int c_idx;
+    __shared__ int s_piv;
+    __shared__ double s_row[NB], s_old[NB];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int len = n - k0, chunk = (len + PANEL_CTAS - 1) / PANEL_CTAS;
+    const int sl0 = k0 + rank * chunk, sl1 = min(n, sl0 + chunk);
+    const int nrow = max(sl1 - sl0, 0);
+    for (int c = 0; c < nb; ++c)
+        for (int r = tid; r < nrow; r += 1024) P[r + ldp * c] = A[(size_t)(k0 + c) * n + sl0 + r];
+    __syncthreads();
+    for (int jj = 0; jj < nb; ++jj) {
+        const int col = k0 + jj;
+        const double* pc = P + ldp * jj;
+        double best = -1.0;
+        int bi = n;
+        for (int r = max(col - sl0, 0) + tid; r < nrow; r += 1024) {
+            const double v = fabs(pc[r]);
+            if (v > best) { best = v; bi = sl0 + r; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, off);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[wid] = best; s_idx[wid] = bi; }
+        __syncthreads();
+        if (wid == 0) {
+            best = s_val[lane]; bi = s_idx[lane];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, best, off);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) { c_val = best; c_idx = bi; }
+        }
+        cl.sync();                                   // (A) candidates in place, previous updates finished
+        if (wid == 0) {
+            best = -1.0; bi = n;
+            if (lane < PANEL_CTAS) {
+                best = *cl.map_shared_rank(&c_val, lane);
+                bi = *cl.map_shared_rank(&c_idx, lane);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, best, off);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) s_piv = bi;
+        }
+        __syncthreads();
+        const int piv = s_piv;
+        const int rp = (piv - k0) / chunk, rc = (col - k0) / chunk;      // owners of the two rows
+        if (tid < nb) {
+            const double* Pp = cl.map_shared_rank(P, rp);
+            s_row[tid] = Pp[(piv - (k0 + rp * chunk)) + ldp * tid];
+        } else if (tid >= 32 && tid < 32 + nb) {
+            const double* Pc = cl.map_shared_rank(P, rc);
+            s_old[tid - 32] = Pc[(col - (k0 + rc * chunk)) + ldp * (tid - 32)];
+        }
+        cl.sync();                                   // (B) every CTA holds both rows; owners may overwrite
+        if (piv != col && tid < nb) {
+            if (rank == rc) P[(col - sl0) + ldp * tid] = s_row[tid];
+            if (rank == rp) P[(piv - sl0) + ldp * tid] = s_old[tid];
+        }
+        if (rank == 0 && tid == 0) ipiv[col] = piv + 1;
+        __syncthreads();
+        const double pivot = s_row[jj];
+        const int ncols = nb - jj - 1;
+        double* pcw = P + ldp * jj;
+        for (int r = max(col + 1 - sl0, 0) + tid; r < nrow; r += 1024) {
+            const double l = pcw[r] / pivot;
+            pcw[r] = l;
+            for (int c = 0; c < ncols; ++c) {
+                double* q = P + ldp * (jj + 1 + c) + r;
+                *q = *q - l * s_row[jj + 1 + c];
+            }
+        }
+        __syncthreads();
+    }
+    for (int c = 0; c < nb; ++c)
+        for (int r = tid; r < nrow; r += 1024) A[(size_t)(k0 + c) * n + sl0 + r] = P[r + ldp * c];
+    cl.sync();                                       // no CTA leaves while a peer may still read its smem
+}
+
 // apply the panel's row interchanges to the columns outside the panel
 __global__ void k_lu_swap(int n, int k0, int nb, double* __restrict__ A, const int* __restrict__ ipiv) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -366,10 +465,21 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
     ILM_TRY(io.map(A, (size_t)n * n, true, true, &dA));
     ILM_TRY(io.map(ipiv, (size_t)n, false, true, &dP));
     cudaStream_t st = io.st;
+    ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     for (int k0 = 0; k0 < n; k0 += NB) {
         const int nb = n - k0 < NB ? n - k0 : NB;
-        if (n - k0 >= 2048) k_lu_panel_cluster<<<PANEL_CTAS, 1024, 0, st>>>(n, k0, nb, dA, dP);
-        else k_lu_panel<<<1, 1024, 0, st>>>(n, k0, nb, dA, dP);
+        {
+            const int chunk = (n - k0 + PANEL_CTAS - 1) / PANEL_CTAS;
+            const int ldp = chunk | 1;
+            const size_t smem = (size_t)ldp * NB * sizeof(double);
+            if (smem <= 200 * 1024) {
+                k_lu_panel_smem<<<PANEL_CTAS, 1024, smem, st>>>(n, k0, nb, ldp, dA, dP);
+            } else if (n - k0 >= 2048) {
+                k_lu_panel_cluster<<<PANEL_CTAS, 1024, 0, st>>>(n, k0, nb, dA, dP);
+            } else {
+                k_lu_panel<<<1, 1024, 0, st>>>(n, k0, nb, dA, dP);
+            }
+        }
         if (n - nb > 0) k_lu_swap<<<(n - nb + 127) / 128, 128, 0, st>>>(n, k0, nb, dA, dP);
         const int rem = n - k0 - nb;
         if (rem > 0) {
