@@ -128,7 +128,10 @@ __global__ void __launch_bounds__(512, 1) ILM_CAT(ilm_passG_L, ILM_L)(ConvArgs a
 
 int ILM_CAT(conv_launch_L, ILM_L)(int which, const ConvArgs& a, int nsm, cudaStream_t st, const void* tmap) {
     using C = FftCfg<ILM_L>;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};           // per device: the attribute belongs to the device's function
+    int dev = 0;
+    ILM_CUDA(cudaGetDevice(&dev));
+    bool& attr_done = attr_done_dev[dev & 63];
     if (!attr_done) {
         ILM_CUDA(cudaFuncSetAttribute(ILM_CAT(ilm_passA_L, ILM_L), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         ILM_CUDA(cudaFuncSetAttribute(ILM_CAT(ilm_passB_L, ILM_L), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));

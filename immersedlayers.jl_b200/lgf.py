@@ -128,3 +128,33 @@ def intfact_table(a, n):
         E[nmax + 1:, :] = 0.0
         E[:, nmax + 1:] = 0.0
     return E
+
+
+def implicit_diffusion_table(a, n):
+    """plan_implicit_diffusion kernel: impulse response of (I - a L)^-1 on the infinite lattice
+    (L = unscaled 5-point Laplacian), `implicit_operator(L, a)` of src/grid_operators.jl:182-184.
+    K(m,n) = (1/pi) int_0^pi cos(m k) rho(k)^|n| / sqrt(A(k)^2 - 4 a^2) dk with A = 1 + 4a - 2a cos k,
+    rho = (A - sqrt(A^2 - 4a^2)) / (2a)  (the y-sum done in closed form); the periodic integrand is
+    analytic, so the trapezoid rule (an FFT) converges geometrically.  Entries below eps*K(0,0) are
+    zeroed like plan_intfact does.  Upstream's table is not recalled: parity unpinned."""
+    n = int(n)
+    if a == 0:
+        K = np.zeros((n, n))
+        K[0, 0] = 1.0
+        return K
+    M = 8 * max(n, 64)
+    k = 2.0 * np.pi * np.arange(M) / M
+    A = 1.0 + 4.0 * a - 2.0 * a * np.cos(k)
+    root = np.sqrt(A * A - 4.0 * a * a)
+    rho = (A - root) / (2.0 * a)
+    K = np.zeros((n, n))
+    p = 1.0 / root
+    for j in range(n):
+        col = np.fft.ifft(p).real[:n]
+        K[:, j] = col
+        p = p * rho
+        if np.abs(col).max() < np.finfo(np.float64).eps * 1e-3:
+            break
+    K = 0.5 * (K + K.T)
+    K[np.abs(K) < np.finfo(np.float64).eps * K[0, 0]] = 0.0
+    return K

@@ -451,3 +451,22 @@ def test_ifherk_stage_schur_complement(c1):
     S3 = ilm.create_RTHR(cache, kid0)
     ER = -(o.E_matrix(oc.tabs[o.PRIMAL]) @ o.R_matrix(oc.tabs[o.PRIMAL])).toarray()
     assert relerr(S3, ER) < RTOL
+
+
+def test_implicit_diffusion_kernel(c1):
+    """implicit_operator(L, a) -> plan_implicit_diffusion(a L.factor) (src/grid_operators.jl:182-184):
+    (I - a L)^-1 as a convolution on the same engine; (I - a L) applied to the result gives the input back."""
+    cache, oc = c1
+    g = cache.g
+    a_tab = 0.5                                        # = a * L.factor
+    K = ilm.lgf.implicit_diffusion_table(a_tab, g.NX)
+    kid = cache.add_kernel(K)
+    w = np.zeros(g.layout_shape(L.NODES_DUAL))
+    w[40:90, 35:80] = np.random.default_rng(12).standard_normal((50, 45))
+    u = ilm.Nodes(ilm.Dual, g).set(w)
+    L.check(cache._lib.ilm_convolve(cache._plan, kid, L.NODES_DUAL, u.data.ctypes.data))
+    assert relerr(u.array(), o.ConvPlan(K[:g.NX, :g.NY]).apply(w)) < RTOL
+    lap = ilm.Nodes(ilm.Dual, g)
+    ilm.laplacian(lap, u, cache)                       # scaled by L.factor = 1/dx^2
+    back = u.array() - a_tab * g.dx ** 2 * lap.array()
+    assert np.abs(back - w)[1:-1, 1:-1].max() < 1e-12 * np.abs(w).max()

@@ -358,3 +358,14 @@ def test_neumann_added_mass(small_cache):
     c = small_cache
     f, df, s, ds, S = o.neumann_solve(c, c.nx.copy())
     assert abs(np.sum(df * c.nx * c.ds) + np.pi) < 0.15
+
+
+def test_implicit_diffusion_table():
+    """(I - aL) K = delta on the lattice and sum K = 1 (the symbol at k = 0)."""
+    for a in (0.05, 0.5, 2.0):
+        K = lgfmod.implicit_diffusion_table(a, 96)
+        LK = K[2:, 1:-1] + K[:-2, 1:-1] + K[1:-1, 2:] + K[1:-1, :-2] - 4 * K[1:-1, 1:-1]
+        assert np.abs(K[1:-1, 1:-1] - a * LK).max() < 1e-15
+        assert abs(K[0, 0] - a * (2 * K[1, 0] + 2 * K[0, 1] - 4 * K[0, 0]) - 1) < 1e-15
+        tot = 4 * K.sum() - 2 * K[0, :].sum() - 2 * K[:, 0].sum() + K[0, 0]
+        assert abs(tot - 1) < 1e-13
