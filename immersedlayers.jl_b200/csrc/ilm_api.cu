@@ -474,6 +474,20 @@ extern "C" int ilm_mask(ilm_plan* p, double* nodes) {
 // `kernel_id` selects the convolution kernel between the pre- and post-operator: 0 = L^-1 (the
 // reference's builders), any id returned by ilm_add_kernel gives e.g. -E exp(L a) R, the Schur
 // complement of an IF-HERK stage (src/timemarching.jl:86-107 via ConstrainedSystems)
+// rows of the probed grid field that the post-operator (E, or a stencil followed by E on the edge
+// tables) can read: the union of the points' window rows, widened by the stencil reach
+static void probe_output_rows(const ilm_plan* p, int which, int* olo, int* ohi) {
+    int lo = 1 << 30, hi = -1;
+    auto span = [&](const DevTable& t, int margin) {
+        for (int j : t.h_j0) { lo = std::min(lo, j - margin); hi = std::max(hi, j + t.W + margin); }
+    };
+    if (which == ILM_RTLINVR) span(p->tab[ILM_NODES_PRIMAL], 0);
+    else { span(p->tab[ILM_XEDGES], 2); span(p->tab[ILM_YEDGES], 2); }
+    *olo = std::max(lo, 0);
+    *ohi = hi;                       // clamped to the field by conv_apply
+    if (hi <= *olo) { *olo = -1; *ohi = -1; }
+}
+
 extern "C" int ilm_create_schur_kernel(ilm_plan* p, int which, int kernel_id, double scale, int col_begin, int col_end,
                                        double* A) {
     ILM_CHECK_PLAN(p);
@@ -500,6 +514,11 @@ extern "C" int ilm_create_schur_kernel(ilm_plan* p, int which, int kernel_id, do
     };
     // two columns per complex transform (src/matrix_operators.jl:16-26 probes one at a time)
     const DevTable& tp = p->tab[ILM_NODES_PRIMAL];
+    // The post-operator only reads the rows under the interpolation windows (plus the stencil
+    // reach): the inverse transforms are restricted to that row range, the rest of the scratch
+    // field is never read.
+    int olo, ohi;
+    probe_output_rows(p, which, &olo, &ohi);
     for (int c = col_begin; c < col_end; c += 2) {
         const bool two = c + 1 < col_end;
         int rlo = -1, rhi = -1;
@@ -530,7 +549,7 @@ extern "C" int ilm_create_schur_kernel(ilm_plan* p, int which, int kernel_id, do
                 else ILM_TRY(launch_divergence(p, eu, ev, gf[q], deriv_div(p), rlo, rhi));
             }
         }
-        ILM_TRY(conv_apply(p, kernel_id, fref(p, glayout, gf[0]), two ? fref(p, glayout, gf[1]) : FieldRef{nullptr, 0, 0}, rlo, rhi));
+        ILM_TRY(conv_apply(p, kernel_id, fref(p, glayout, gf[0]), two ? fref(p, glayout, gf[1]) : FieldRef{nullptr, 0, 0}, rlo, rhi, olo, ohi));
         if (which == ILM_RTLINVR && kernel_id >= 0) {
             ILM_TRY(launch_probe_post(p, tp, two ? 2 : 1, gf[0], gf[1], -scale, dA + (size_t)(c - col_begin) * N,
                                       dA + (size_t)(c + 1 - col_begin) * N));
@@ -606,5 +625,7 @@ extern "C" int ilm_profile_conv_probe(ilm_plan* p, int col, int reps, double ms[
     rlo = std::max(rlo, 0); rhi = std::min(rhi, tp.my);
     ILM_TRY(launch_regularize_unit(p, tp, col, p->g_a, rlo, rhi));
     ILM_TRY(launch_regularize_unit(p, tp, col + 1, p->g_b, rlo, rhi));
-    return conv_profile(p, fref(p, ILM_NODES_PRIMAL, p->g_a), fref(p, ILM_NODES_PRIMAL, p->g_b), reps, ms, rlo, rhi);
+    int olo, ohi;
+    probe_output_rows(p, ILM_RTLINVR, &olo, &ohi);
+    return conv_profile(p, fref(p, ILM_NODES_PRIMAL, p->g_a), fref(p, ILM_NODES_PRIMAL, p->g_b), reps, ms, rlo, rhi, olo, ohi);
 }

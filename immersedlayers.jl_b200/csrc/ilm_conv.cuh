@@ -76,6 +76,9 @@ struct ConvArgs {
     const double2* wl2y;   // exp(-2 pi i n / (2 Ly)), n < 2 Ly (global; sparse forward transform of pass B)
     int rlo, rhi;          // input rows outside [rlo, rhi) are known to be zero in both fields
                            // (Schur probes: a 4x4 patch); pass A skips them, pass B reads zeros
+    int olo, ohi;          // only output rows [olo, ohi) are needed (Schur probes: the rows under the
+                           // interpolation windows); pass B stores and pass C inverts only those rows,
+                           // the other rows of the output fields are left untouched.  olo is even.
 };
 
 // named barriers 1,2 are the per-group barriers (Ctx::sync); these two carry the
@@ -273,7 +276,7 @@ ILM_HD void passB_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
                             const int n = j + e * T;
-                            if (n < a.g.MYp) a.S2[col_elem<T>(a.g, px, m, j, e, i0)] = cadd(v[e], comb[n]);
+                            if (n >= a.olo && n < a.ohi) a.S2[col_elem<T>(a.g, px, m, j, e, i0)] = cadd(v[e], comb[n]);
                         }
                     }
                     ctx.arrive(BAR_FREE);
@@ -304,10 +307,10 @@ ILM_HD void passC_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
     // RPW consecutive rows per work item: the second row of each 2x2 tile is an
     // L2 hit (its sector came in with the first row's 64-byte DRAM access)
     constexpr int SUB = (F == 1) ? 2 : 1, RPW = F * SUB;
-    const int nwork = (a.g.MYp + RPW - 1) / RPW;
+    const int nwork = (a.ohi - a.olo + RPW - 1) / RPW;
     const int nsteps = (block < nwork) ? ((nwork - block + nblocks - 1) / nblocks) * SUB : 0;
     // rows of step s for FFT slot ff
-    auto step_row0 = [&](int s) { return (block + (s / SUB) * nblocks) * RPW + (s % SUB) * F; };
+    auto step_row0 = [&](int s) { return a.olo + (block + (s / SUB) * nblocks) * RPW + (s % SUB) * F; };
     if constexpr (C::USE_TMA) {
         ctx.tma_init(mbar);
         if (nsteps > 0) ctx.tma_load_rows(a, px, step_row0(0), F, L, C::XBUF, xgrp, mbar);
@@ -315,8 +318,8 @@ ILM_HD void passC_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
     if (!px) { ctx.arrive(BAR_FREE); ctx.delay(a.skew_ns); }
     for (int s = 0; s < nsteps; ++s) {
         const int row = step_row0(s) + f;
-        const bool live = row < a.g.MYp;
-        const bool r1 = a.f1.p && row < a.f1.my, r2 = a.f2.p && row < a.f2.my;
+        const bool live = row < a.ohi;
+        const bool r1 = live && a.f1.p && row < a.f1.my, r2 = live && a.f2.p && row < a.f2.my;
         double2 v[16];
         if constexpr (C::USE_TMA) {
             ctx.tma_wait(mbar, s & 1);

@@ -154,10 +154,11 @@ void free_table(DevTable& t);
 // ---- convolution engine (ilm_lgf.cu + ilm_conv_inst.cu) -------------------------
 int conv_setup(ilm_plan* p);
 int conv_add_kernel(ilm_plan* p, const double* table_host_or_dev, int n, double c0, double factor, int* id);
-// rows outside [rlo, rhi) of both inputs are known zeros (-1, -1 = dense input)
-int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo = -1, int rhi = -1);
+// rows outside [rlo, rhi) of both inputs are known zeros (-1, -1 = dense input); only output rows
+// [olo, ohi) are needed by the caller (-1, -1 = all), the others are left untouched
+int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1);
 void conv_free(ilm_plan* p);
-int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo = -1, int rhi = -1);
+int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1);
 extern long long g_dense_launches;
 // per-length launchers, which = 0: pass A, 1: pass B, 2: pass C, 3: pass G
 typedef int (*conv_launch_fn)(int which, const ConvArgs& a, int nsm, cudaStream_t st, const void* tmap);

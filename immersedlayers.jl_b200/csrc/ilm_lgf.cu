@@ -145,6 +145,7 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     a.f1 = FieldRef{p->g_a, NX, NY};
     a.f2 = FieldRef{nullptr, 0, 0};
     a.rlo = 0; a.rhi = a.g.MYp;
+    a.olo = 0; a.ohi = a.g.MYp;
     a.S = p->S; a.S2 = p->S2;
     a.GhatOut = k.ghat;
     a.gscale = 1.0 / (4.0 * (double)p->Lx * (double)p->Ly * factor);
@@ -164,7 +165,7 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     return ILM_OK;
 }
 
-int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, int rhi) {
+int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, int rhi, int olo, int ohi) {
     if (kernel_id < 0 || kernel_id >= (int)p->kernels.size()) {
         set_error("unknown convolution kernel id");
         return ILM_EINVAL;
@@ -177,6 +178,9 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
     a.f1 = f1; a.f2 = f2;
     a.rlo = rlo < 0 ? 0 : rlo;
     a.rhi = (rhi < 0 || rhi > a.g.MYp) ? a.g.MYp : rhi;
+    a.olo = olo < 0 ? 0 : (olo & ~1);
+    a.ohi = (ohi < 0 || ohi > a.g.MYp) ? a.g.MYp : ohi;
+    if (a.ohi <= a.olo) { a.olo = 0; a.ohi = a.g.MYp < 2 ? a.g.MYp : 2; }
     a.S = p->S; a.S2 = p->S2;
     a.Ghat = p->kernels[kernel_id].ghat;
     a.twx = p->twx; a.twy = p->twy;
@@ -191,13 +195,16 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
 }
 
 // per-pass timing for the roofline report (ilm_profile_conv)
-int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo, int rhi) {
+int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo, int rhi, int olo, int ohi) {
     ConvArgs a{};
     int MY = f1.my > f2.my ? f1.my : f2.my;
     a.g = ConvGeom{p->Lx, p->Ly, MY, (MY + 1) & ~1};
     a.f1 = f1; a.f2 = f2;
     a.rlo = rlo < 0 ? 0 : rlo;
     a.rhi = (rhi < 0 || rhi > a.g.MYp) ? a.g.MYp : rhi;
+    a.olo = olo < 0 ? 0 : (olo & ~1);
+    a.ohi = (ohi < 0 || ohi > a.g.MYp) ? a.g.MYp : ohi;
+    if (a.ohi <= a.olo) { a.olo = 0; a.ohi = a.g.MYp < 2 ? a.g.MYp : 2; }
     a.S = p->S; a.S2 = p->S2;
     a.Ghat = p->kernels[0].ghat;
     a.twx = p->twx; a.twy = p->twy;

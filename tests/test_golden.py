@@ -1,0 +1,135 @@
+"""Committed golden fixtures (tests/golden/):
+
+* reference_notebook_values.json -- numbers printed by the reference's own executed notebooks
+  (extract_reference_goldens.py); the oracle must reproduce them (CPU).
+* c1_dirichlet_128.npz -- oracle outputs on BASELINE config C1 (make_oracle_fixtures.py); the
+  oracle must still reproduce the file (CPU) and the CUDA path must match it (-m gpu): bit-exact
+  for tables / regularization / stencils, 1e-12 norm-wise for everything through the FFT."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import ilm_b200 as ilm
+import ilm_oracle as o
+from ilm_b200 import _lib as L
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def nbvals():
+    return json.load(open(os.path.join(HERE, "reference_notebook_values.json")))
+
+
+@pytest.fixture(scope="module")
+def c1file():
+    return np.load(os.path.join(HERE, "c1_dirichlet_128.npz"))
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ---------------------------------------------------------------- reference notebook values (CPU)
+def test_notebook_circle_and_normals(nbvals):
+    """examples/caches.ipynb: Circle(1.0, 1.4*0.01) has 448 points, sum(ds) and the first/last
+    printed normal components."""
+    npts = int(nbvals["caches_circle"]["numbers"][0])
+    x, y, nx, ny, ds = ilm.bodies.circle(1.0, 1.4 * 0.01)[:5]
+    assert len(x) == npts == 448
+    assert abs(ds.sum() - nbvals["caches_dot_ones_surface"]["values"][0]) < 1e-11
+    assert abs(ds.sum() - nbvals["caches_integrate_ones_surface"]["values"][0]) < 1e-11
+    vals = nbvals["caches_normals_head"]["values"]          # 10 leading nx, then the trailing ny (after the ellipsis)
+    # RigidBodyTools (un-vendored; bodies are INPUTS of the hot path) derives its normals from the
+    # discretised shape: they deviate by an alternating +-1.5e-6 rad from the exact midpoint normals
+    # (its first normal is cos(1.5e-6), not 1)
+    assert np.abs(nx[:10] - np.array(vals[:10])).max() < 2e-6
+    tail = np.array(vals[10:])
+    assert np.abs(ny[-len(tail):] - tail).max() < 2e-6
+    assert len(ilm.bodies.circle(0.5, 1.4 * 0.01)[0]) == int(nbvals["multbodies_circle"]["numbers"][0])
+
+
+def test_notebook_grid_integrals(nbvals):
+    """examples/caches.ipynb: PhysicalGrid((406,406),(203,203),0.01,...); integrate(ones_grid) = 16.3216."""
+    nums = nbvals["caches_grid"]["numbers"]
+    NX, NY, I0x, I0y, dx = int(nums[1]), int(nums[2]), int(nums[3]), int(nums[4]), nums[5]
+    g = o.Grid(NX, NY, dx, (I0x, I0y))
+    ones = np.ones(o.field_shape(o.PRIMAL, NX, NY))
+    val = o.dot_grid(g, ones, ones, o.PRIMAL)
+    assert abs(val - nbvals["caches_integrate_ones_grid"]["values"][0]) < 1e-10
+    xs, ys = g.coords(o.PRIMAL)
+    assert abs(xs[0] - nums[6]) < 1e-12 and abs(xs[-1] - nums[7]) < 1e-12
+
+
+def test_notebook_layers_dot(nbvals):
+    """examples/Layers.ipynb cell 64: dot(qx, Rf*nrm, g) on the 600^2 grid, dx = 0.02, circle R = 1,
+    ds = 1.5 dx (cells 5, 19); the regularization weights are dlengthmid(body) (cell 19)."""
+    dx = 0.02
+    g = o.Grid(600, 600, dx, (300, 300))
+    x, y, nx, ny, ds = ilm.bodies.circle(1.0, 1.5 * dx)[:5]
+    N = len(x)
+    dlmid = np.full(N, np.sin(2 * np.pi / N))            # 0.5*|x[k+1]-x[k-1]| on the unit circle
+    q = o.regularize(o.build_table(g, x, y, dlmid, o.XEDGE), nx)
+    xu = g.coords(o.XEDGE)[0]
+    got = o.dot_grid(g, np.broadcast_to(xu[:, None], q.shape), q, o.XEDGE)
+    ref = nbvals["layers_dot_x_Rf_n"]["values"][0]
+    assert abs(got - ref) < 1e-13 * abs(ref)
+
+
+# ---------------------------------------------------------------- oracle vs the committed C1 file (CPU)
+def test_oracle_reproduces_c1_fixture(c1file):
+    d = c1file
+    g = o.Grid(int(d["NX"]), int(d["NY"]), float(d["dx"]), tuple(int(v) for v in d["I0"]))
+    oc = o.ScalarCache(g, d["x"], d["y"], d["nx"], d["ny"], d["ds"], d["lgf"])
+    tab = oc.tabs[o.PRIMAL]
+    assert np.array_equal(np.transpose(tab.linear_index(), (0, 2, 1)), d["table_idx"])
+    assert np.array_equal(np.transpose(tab.wR, (0, 2, 1)), d["table_wR"])
+    assert np.array_equal(o.regularize(tab, d["f"]), d["regularize_f"])
+    assert relerr(o.interpolate(tab, d["w"]), d["interpolate_w"]) < 1e-14
+    assert relerr(oc.inverse_laplacian(d["w"].copy()), d["inverse_laplacian_w"]) < 1e-13
+    assert relerr(oc.mask(), d["mask"]) < 1e-13
+    f, s, S = o.dirichlet_solve(oc, np.asarray(d["x"]).copy())
+    assert relerr(S, d["S"]) < 1e-13
+    assert relerr(f, d["dirichlet_f"]) < 1e-11
+    assert np.array_equal(ilm.lgf.lgf_table(128), d["lgf"])
+
+
+# ---------------------------------------------------------------- CUDA path vs the committed C1 file
+@pytest.mark.gpu
+def test_gpu_matches_c1_fixture(c1file):
+    d = c1file
+    g = ilm.PhysicalGrid(int(d["NX"]), int(d["NY"]), float(d["dx"]), tuple(int(v) for v in d["I0"]))
+    body = (d["x"], d["y"], d["nx"], d["ny"], d["ds"])
+    cache = ilm.SurfaceScalarCache(body, g, lgf_table=d["lgf"])
+    idx, wR, wE = cache.table(L.NODES_PRIMAL)
+    assert np.array_equal(idx, d["table_idx"])
+    assert np.array_equal(wR, d["table_wR"]) and np.array_equal(wE, d["table_wE"])
+    fd = ilm.ScalarData(cache.N, data=d["f"].copy())
+    s = cache.zeros_grid()
+    ilm.regularize(s, fd, cache)
+    assert np.array_equal(s.array(), d["regularize_f"])
+    w = cache.zeros_grid().set(d["w"])
+    out = cache.zeros_surface()
+    ilm.interpolate(out, w, cache)
+    assert relerr(out.data, d["interpolate_w"]) < RTOL
+    q = cache.zeros_gridgrad()
+    ilm.grad(q, w, cache)
+    p = cache.zeros_grid()
+    ilm.divergence(p, q, cache)
+    assert np.array_equal(p.array(), d["divergence_grad_w"])
+    ilm.inverse_laplacian(w, cache)
+    assert relerr(w.array(), d["inverse_laplacian_w"]) < RTOL
+    assert relerr(ilm.mask(cache).array(), d["mask"]) < RTOL
+    S = ilm.create_RTLinvR(cache)
+    assert relerr(S, d["S"]) < RTOL
+    assert relerr(ilm.create_CLinvCT(cache), d["CLinvCT"]) < RTOL
+    assert relerr(ilm.create_nRTRn(cache), d["nRTRn"]) < RTOL
+    assert relerr(ilm.create_surface_filter(cache), d["surface_filter"]) < RTOL
+    f, sm, _ = ilm.dirichlet_poisson(cache, np.asarray(d["x"]).copy())
+    cond = np.linalg.cond(d["S"])
+    assert relerr(sm.data, d["dirichlet_s"]) < 50 * cond * np.finfo(float).eps
+    assert relerr(f.array(), d["dirichlet_f"]) < 1e-10
