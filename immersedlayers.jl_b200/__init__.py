@@ -11,7 +11,7 @@ from .api import (  # noqa: F401
     EdgeGradient, SurfaceVectorCache, TensorData, create_CL2invCT, create_RTHR, create_RTLinvR_direct, neumann_poisson, create_CLinvCT_scalar, create_GLinvD_symm,
     normal_dot_interpolate, normal_interpolate_symm, regularize_normal_dot, regularize_normal_symm,
     surface_divergence_symm, surface_grad_symm,
-    Dual, Edges, GridScaling, IndexScaling, LU, Nodes, PhysicalGrid, Primal, ScalarData,
+    XEdges, YEdges, Dual, Edges, GridScaling, IndexScaling, LU, Nodes, PhysicalGrid, Primal, ScalarData,
     SurfaceScalarCache, VectorData, complementary_mask, create_CLinvCT, create_GLinvD,
     create_GLinvD_cross, create_RTLinvR, create_nRTRn, create_surface_filter, curl,
     dirichlet_poisson, divergence, grad, interpolate, inverse_laplacian, laplacian, mask,

@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libilm_b200.so")
 
 OK, EINVAL, ESIZE, ECUDA, ENCCL, ENOMEM = range(6)
 
-NODES_PRIMAL, NODES_DUAL, XEDGES, YEDGES, EDGES = range(5)
+NODES_PRIMAL, NODES_DUAL, XEDGES, YEDGES, EDGES, EDGEGRAD = range(6)
+SCALAR_CACHE, VECTOR_CACHE = 0, 1
 NORMAL, CROSS = 0, 1
 RTLINVR, CLINVCT, GLINVD, GLINVD_CROSS = range(4)
 DDF = {"yang3": 0, "m3": 1, "roma": 2, "m4prime": 3, "witchhat": 4}
@@ -85,6 +86,7 @@ SIGNATURES = {
     "ilm_vsurface_curl_s2n": (_i, [_vp, _dp, _dp]),
     "ilm_vsurface_curl_n2s": (_i, [_vp, _dp, _dp]),
     "ilm_mask_edges": (_i, [_vp, _dp]),
+    "ilm_mask_product": (_i, [_vp, _i, _i, _i, _dp]),
     "ilm_create_schur_vector": (_i, [_vp, _i, _d, _i, _i, _dp]),
     "ilm_create_nRTRn_vector": (_i, [_vp, _d, _dp]),
     "ilm_dense_launch_count": (C.c_int64, []),

@@ -169,6 +169,25 @@ class Edges(_Data):
         return self.numpy()[self.nu:].reshape(self.vshape, order="F")
 
 
+class _EdgeComponent(_Data):
+    def __init__(self, grid, data=None, device=False):
+        self.shape = grid.layout_shape(self.layout)
+        super().__init__(_alloc(self.shape[0] * self.shape[1], device) if data is None else data)
+
+    def array(self):
+        return self.numpy().reshape(self.shape, order="F")
+
+
+class XEdges(_EdgeComponent):
+    """XEdges{Primal}: one u component, NX x (NY-1)."""
+    layout = L.XEDGES
+
+
+class YEdges(_EdgeComponent):
+    """YEdges{Primal}: one v component, (NX-1) x NY."""
+    layout = L.YEDGES
+
+
 class ScalarData(_Data):
     def __init__(self, n, data=None, device=False):
         super().__init__(_alloc(n, device) if data is None else data)
@@ -908,8 +927,43 @@ def surface_curl(a, b, cache):
     return _s_surface_curl(a, b, cache)
 
 
-def mask(cache):
-    """mask(cache): Nodes{Primal} for a scalar cache, Edges for a vector cache (:737)."""
+def _mask_layout(w, cache):
+    """Layout code of grid data `w` for mask!/complementary_mask! (the methods of
+    _scalar_mask_product! / _vector_mask_product!, src/surface_operators.jl:880-923)."""
+    if isinstance(w, Nodes):
+        return L.NODES_PRIMAL if w.celltype == Primal else L.NODES_DUAL
+    if isinstance(w, XEdges):
+        return L.XEDGES
+    if isinstance(w, YEdges):
+        return L.YEDGES
+    if isinstance(w, Edges):
+        return L.EDGES
+    if isinstance(w, EdgeGradient):
+        return L.EDGEGRAD
+    raise MethodError(f"mask!: no method for {type(w).__name__}")
+
+
+def _mask_inplace(w, cache, complementary):
+    if cache.scaling != GridScaling:
+        raise MethodError("mask! is only defined for GridScaling caches")
+    layout = _mask_layout(w, cache)
+    vec = _is_vector(cache)
+    if vec and layout in (L.XEDGES, L.YEDGES):
+        raise MethodError("mask!: no method for a single edge component on a vector cache")
+    if not vec and layout == L.EDGEGRAD:
+        raise MethodError("mask!: no method for EdgeGradient on a scalar cache")
+    L.check(cache._lib.ilm_mask_product(cache._plan, L.VECTOR_CACHE if vec else L.SCALAR_CACHE, layout,
+                                        1 if complementary else 0, _ptr(w.data)))
+    return w
+
+
+def mask(*args):
+    """mask(cache) -> new grid data with 1 inside / 0 outside (src/surface_operators.jl:737): Nodes{Primal}
+    for a scalar cache, Edges for a vector cache.  mask(w, cache) = mask!(w, cache) (:788-800): w is
+    multiplied in place by the mask, averaged onto w's layout where needed."""
+    if len(args) == 2:
+        return _mask_inplace(args[0], args[1], False)
+    (cache,) = args
     if _is_vector(cache):
         if cache.scaling != GridScaling:
             raise MethodError("mask is only defined for GridScaling caches")
@@ -917,6 +971,19 @@ def mask(cache):
         L.check(cache._lib.ilm_mask_edges(cache._plan, _ptr(m.data)))
         return m
     return _s_mask(cache)
+
+
+def complementary_mask(*args):
+    """complementary_mask(cache) (:749) / complementary_mask!(w, cache) (:811-823)."""
+    if len(args) == 2:
+        return _mask_inplace(args[0], args[1], True)
+    (cache,) = args
+    m = mask(cache)
+    if _is_torch(m.data):
+        m.data.neg_().add_(1.0)
+    else:
+        m.data[...] = 1.0 - m.data
+    return m
 
 
 def _vmatrix(cache, which, scale, cols):

@@ -453,20 +453,24 @@ extern "C" int ilm_surface_curl_n2s(ilm_plan* p, int mode, const double* nodes, 
     return io.finish();
 }
 
-extern "C" int ilm_mask(ilm_plan* p, double* nodes) {
-    ILM_CHECK_PLAN(p);
-    Io io(p);
+namespace ilm {
+// _get_mask!(msk, cache) (src/surface_operators.jl:865-876) on device buffers
+int mask_primal_dev(ilm_plan* p, double* dn) {
     const size_t n = n_layout(p, ILM_NODES_PRIMAL);
-    double* dn = io.out(nodes, n);
-    if (io.status) return io.status;
-    if (p->N == 0) {       // _get_mask!(msk, cache::BasicILMCache{0}) : ones
-        ILM_TRY(launch_fill(p, dn, n, 1.0));
-        return io.finish();
-    }
+    if (p->N == 0) return launch_fill(p, dn, n, 1.0);       // _get_mask!(msk, cache::BasicILMCache{0}) : ones
     ILM_TRY(launch_fill(p, p->s_a, p->N, 1.0));
     ILM_TRY(surface_divergence_dev(p, ILM_NORMAL, p->s_a, dn));
     ILM_TRY(conv_apply(p, 0, fref(p, ILM_NODES_PRIMAL, dn), FieldRef{nullptr, 0, 0}));
-    ILM_TRY(launch_scale(p, dn, n, -1.0));
+    return launch_scale(p, dn, n, -1.0);
+}
+}  // namespace ilm
+
+extern "C" int ilm_mask(ilm_plan* p, double* nodes) {
+    ILM_CHECK_PLAN(p);
+    Io io(p);
+    double* dn = io.out(nodes, n_layout(p, ILM_NODES_PRIMAL));
+    if (io.status) return io.status;
+    ILM_TRY(mask_primal_dev(p, dn));
     return io.finish();
 }
 

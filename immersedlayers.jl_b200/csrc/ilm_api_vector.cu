@@ -241,20 +241,67 @@ extern "C" int ilm_vsurface_curl_n2s(ilm_plan* p, const double* dual, double* v)
     return io.finish();
 }
 
-extern "C" int ilm_mask_edges(ilm_plan* p, double* edges) {
-    ILM_VPLAN(p);
+namespace ilm {
+int mask_edges_dev(ilm_plan* p, double* de) {
     const Sizes z(p);
-    Io io(p);
-    double* de = io.out(edges, z.ne);
-    if (io.status) return io.status;
-    if (p->N == 0) {
-        ILM_TRY(launch_fill(p, de, z.ne, 1.0));
-        return io.finish();
-    }
+    if (p->N == 0) return launch_fill(p, de, z.ne, 1.0);
     ILM_TRY(launch_fill(p, p->s_a, 2 * (size_t)p->N, 1.0));
     ILM_TRY(vsurface_divergence_dev(p, ILM_TENSOR_NORMAL, p->s_a, de));
     ILM_TRY(conv_apply(p, 0, FieldRef{de, p->g.NX, p->g.NY - 1}, FieldRef{de + z.nu, p->g.NX - 1, p->g.NY}));
-    ILM_TRY(launch_scale(p, de, z.ne, -1.0));
+    return launch_scale(p, de, z.ne, -1.0);
+}
+}  // namespace ilm
+
+extern "C" int ilm_mask_edges(ilm_plan* p, double* edges) {
+    ILM_VPLAN(p);
+    Io io(p);
+    double* de = io.out(edges, Sizes(p).ne);
+    if (io.status) return io.status;
+    ILM_TRY(mask_edges_dev(p, de));
+    return io.finish();
+}
+
+// mask!(w, cache) / complementary_mask!(w, cache) (src/surface_operators.jl:788-823, 880-923): the
+// mask is recomputed (one inverse Laplacian, as the reference does) and multiplied into w, averaged
+// onto w's layout where that differs from the cache's own grid-data layout.
+extern "C" int ilm_mask_product(ilm_plan* p, int cache_kind, int layout, int complementary, double* w) {
+    ILM_VPLAN(p);
+    if (p->scaling != ILM_GRID_SCALING) { set_error("mask!: only defined for GridScaling caches"); return ILM_EINVAL; }
+    if (cache_kind != ILM_SCALAR_CACHE && cache_kind != ILM_VECTOR_CACHE) { set_error("mask!: bad cache kind"); return ILM_EINVAL; }
+    const bool vec = cache_kind == ILM_VECTOR_CACHE;
+    const bool ok = layout >= ILM_NODES_PRIMAL && (vec ? (layout == ILM_NODES_PRIMAL || layout == ILM_NODES_DUAL || layout == ILM_EDGES || layout == ILM_EDGEGRAD)
+                                                       : layout <= ILM_EDGES);
+    if (!ok) { set_error("mask!: no method for this grid data type on this cache"); return ILM_EINVAL; }
+    const Sizes z(p);
+    const size_t n = layout == ILM_EDGES ? z.ne : layout == ILM_EDGEGRAD ? z.ng : layout_info(layout, p->g.NX, p->g.NY).n();
+    Io io(p);
+    double* dw = io.inout(w, n);
+    if (io.status) return io.status;
+    const int c = complementary ? 1 : 0;
+    if (!vec) {
+        double* m = p->g_b;                                   // Nodes{Primal} mask (gdata_cache)
+        ILM_TRY(mask_primal_dev(p, m));
+        if (layout == ILM_EDGES) {
+            ILM_TRY(launch_mask_product(p, dw, ILM_XEDGES, m, ILM_NODES_PRIMAL, c));
+            ILM_TRY(launch_mask_product(p, dw + z.nu, ILM_YEDGES, m, ILM_NODES_PRIMAL, c));
+        } else {
+            ILM_TRY(launch_mask_product(p, dw, layout, m, ILM_NODES_PRIMAL, c));
+        }
+    } else {
+        double* m = p->g_edges;                               // Edges mask (gdata_cache of the vector cache)
+        ILM_TRY(mask_edges_dev(p, m));
+        if (layout == ILM_EDGES) {                            // product!(w, gdata_cache, w)
+            ILM_TRY(launch_mask_product(p, dw, ILM_XEDGES, m, ILM_XEDGES, c));
+            ILM_TRY(launch_mask_product(p, dw + z.nu, ILM_YEDGES, m + z.nu, ILM_YEDGES, c));
+        } else if (layout == ILM_EDGEGRAD) {                  // every component uses gdata_cache.u (:908-923)
+            ILM_TRY(launch_mask_product(p, dw, ILM_NODES_PRIMAL, m, ILM_XEDGES, c));
+            ILM_TRY(launch_mask_product(p, dw + z.Pn, ILM_NODES_DUAL, m, ILM_XEDGES, c));
+            ILM_TRY(launch_mask_product(p, dw + z.Pn + z.Pd, ILM_NODES_DUAL, m, ILM_XEDGES, c));
+            ILM_TRY(launch_mask_product(p, dw + z.Pn + 2 * z.Pd, ILM_NODES_PRIMAL, m, ILM_XEDGES, c));
+        } else {
+            ILM_TRY(launch_mask_product(p, dw, layout, m, ILM_XEDGES, c));
+        }
+    }
     return io.finish();
 }
 

@@ -79,6 +79,8 @@ struct ConvArgs {
     int olo, ohi;          // only output rows [olo, ohi) are needed (Schur probes: the rows under the
                            // interpolation windows); pass B stores and pass C inverts only those rows,
                            // the other rows of the output fields are left untouched.  olo is even.
+    int wlo, whi;          // pass B visits the work items [wlo, whi) only (slab decomposition: the x-frequency
+                           // columns this GPU owns); whi <= 0 = all of them
 };
 
 // named barriers 1,2 are the per-group barriers (Ctx::sync); these two carry the
@@ -216,15 +218,17 @@ ILM_HD void passB_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
     // (0, last, 1, last-1, ...) so that a column and its mirror kx <-> PX-kx, which share one
     // Ghat column, are processed at about the same time by neighbouring CTAs: Ghat is read from
     // DRAM once and hit in L2 the second time (F == 1 only; smaller transforms keep the identity).
+    const bool ranged = a.whi > 0;                              // a slab owns a contiguous column range: identity order
     auto tile_of = [&](int w) {
-        if (F != 1) return w;
+        if (F != 1 || ranged) return w;
         const int half = a.g.Lx >> 1, blk = w / half, t = w % half;
         return blk * half + ((t & 1) ? half - 1 - (t >> 1) : (t >> 1));
     };
-    for (int w0 = block; w0 < nwork; w0 += nblocks) {
+    const int wbeg = ranged ? a.wlo : 0, wend = ranged ? (a.whi < nwork ? a.whi : nwork) : nwork;
+    for (int w0 = wbeg + block; w0 < wend; w0 += nblocks) {
         const int w = tile_of(w0);
         const int wn0 = w0 + nblocks;
-        if (wn0 < nwork && a.rhi - a.rlo == a.g.MYp) {
+        if (wn0 < wend && a.rhi - a.rlo == a.g.MYp) {
             const size_t e0 = (size_t)tile_of(wn0) * CPW * col_elems;
             size_t ne = (size_t)CPW * col_elems;
             if (e0 + ne > s_elems(a.g)) ne = s_elems(a.g) - e0;

@@ -143,7 +143,10 @@ int ILM_CAT(conv_launch_L, ILM_L)(int which, const ConvArgs& a, int nsm, cudaStr
     const int cpw = C::F == 1 ? 2 : C::F;          // rows / columns per work item
     if (which == 0) nwork = (a.rhi - a.rlo + C::F - 1) / C::F;
     else if (which == 2) nwork = (a.ohi - a.olo + cpw - 1) / cpw;
-    else nwork = (2 * a.g.Lx + cpw - 1) / cpw;
+    else {
+        nwork = (2 * a.g.Lx + cpw - 1) / cpw;
+        if (a.whi > 0) nwork = (a.whi < nwork ? a.whi : nwork) - a.wlo;
+    }
     int grid = nwork < nsm ? nwork : nsm;
     if (grid < 1) grid = 1;
     switch (which) {

@@ -133,6 +133,8 @@ int launch_curl_e2n(ilm_plan* p, const double* u, const double* v, double* w, do
 int launch_laplacian(ilm_plan* p, const double* in, double* out, int mx, int my, double factor);
 int launch_scale_store_column(ilm_plan* p, const double* src, double* dst, int n, double scale);
 int launch_scale(ilm_plan* p, double* w, size_t n, double scale);
+// w *= mean of the (complementary) mask m over the nearest entries of its layout (grid_interpolate!)
+int launch_mask_product(ilm_plan* p, double* w, int wlayout, const double* m, int mlayout, int complementary);
 int launch_lgf_prep(ilm_plan* p, const double* table, int ld, int NX, int NY, double c0, double* h);
 int launch_filter_rowsum(ilm_plan* p, DevTable& t);
 int launch_surface_filter(ilm_plan* p, const DevTable& t, double* C);
@@ -147,6 +149,10 @@ int launch_vec_pointwise(ilm_plan* p, int op, const double* in, double* out);
 int launch_grad_tensor(ilm_plan* p, const double* edges, double* eg, double div);
 int launch_div_tensor(ilm_plan* p, const double* eg, double* edges, double div);
 
+// mask = -L^-1 D_s 1 on Nodes{Primal} (scalar cache, ilm_api.cu) / on Edges (vector cache, ilm_api_vector.cu)
+int mask_primal_dev(ilm_plan* p, double* dn);
+int mask_edges_dev(ilm_plan* p, double* de);
+
 // ---- tables (ilm_tables.cu, compiled without FMA contraction) -----------------
 int build_tables(ilm_plan* p);
 void free_table(DevTable& t);
@@ -158,6 +164,8 @@ int conv_add_kernel(ilm_plan* p, const double* table_host_or_dev, int n, double 
 // [olo, ohi) are needed by the caller (-1, -1 = all), the others are left untouched
 int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1);
 void conv_free(ilm_plan* p);
+int conv_half_len(int n);                       // half padded transform length of an n-cell direction
+int make_s2_tensor_map(ilm_plan* p, int MYp);    // bulk-tensor map of S2 for pass C
 int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1);
 extern long long g_dense_launches;
 // per-length launchers, which = 0: pass A, 1: pass B, 2: pass C, 3: pass G

@@ -55,7 +55,7 @@ const double2* conv_twiddles_host(int L, size_t* count) {
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_s2_tensor_map(ilm_plan* p, int MYp) {
+int make_s2_tensor_map(ilm_plan* p, int MYp) {
     if (p->tmap_myp == MYp) return ILM_OK;
     static encode_tiled_fn encode = nullptr;
     if (!encode) {
@@ -79,7 +79,7 @@ static int make_s2_tensor_map(ilm_plan* p, int MYp) {
 }
 
 // half padded length: smallest power of two L >= 16 with 2L >= 2n-1
-static int half_len(int n) {
+int conv_half_len(int n) {
     int L = 16;
     while (2 * L < 2 * n - 1) L <<= 1;
     return L;
@@ -87,8 +87,8 @@ static int half_len(int n) {
 
 int conv_setup(ilm_plan* p) {
     if (const char* e = getenv("ILM_CONV_SKEW_NS")) p->skew_ns = atoi(e);
-    p->Lx = half_len(p->g.NX);
-    p->Ly = half_len(p->g.NY);
+    p->Lx = conv_half_len(p->g.NX);
+    p->Ly = conv_half_len(p->g.NY);
     if (p->Lx > 4096 || p->Ly > 4096) {
         set_error("grid larger than 4096 cells per direction is not supported by the single-GPU FFT engine yet");
         return ILM_ESIZE;

@@ -733,4 +733,51 @@ int launch_probe_post(ilm_plan* p, const DevTable& t, int ncol, const double* g0
     return ILM_OK;
 }
 
+// ------------------------------------------------------------------ mask products
+// w *= grid_interpolate(mask -> layout of w), the body of _scalar_mask_product! / _vector_mask_product!
+// (src/surface_operators.jl:880-923): product!(w, mask, w) on the mask's own layout, otherwise the
+// mask is first averaged onto w's staggered positions (CartesianGrids grid_interpolate!: 2-point
+// mean along a direction in which the two layouts are offset by half a cell, 4-point mean
+// primal<->dual nodes).  Entries of w whose stencil leaves the mask field get the factor 0 (upstream
+// leaves its zero-initialised scratch untouched there).  hx, hy = twice the layout shift.
+__global__ void k_mask_product(double* __restrict__ w, int mx, int my, int hxw, int hyw, const double* __restrict__ m,
+                               int mmx, int mmy, int hxm, int hym, int complementary) {
+    const size_t n = (size_t)mx * my;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int dxo = hxm - hxw, dyo = hym - hyw;          // -1, 0, +1
+    const int a0 = dxo < 0 ? -1 : 0, a1 = dxo > 0 ? 1 : 0;
+    const int b0 = dyo < 0 ? -1 : 0, b1 = dyo > 0 ? 1 : 0;
+    const double scale = 1.0 / (double)((a1 - a0 + 1) * (b1 - b0 + 1));
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+        const int i = (int)(idx % mx), j = (int)(idx / mx);          // 0-based
+        double fac = 0.0;
+        if (i + a0 >= 0 && i + a1 < mmx && j + b0 >= 0 && j + b1 < mmy) {
+            double row[2] = {0.0, 0.0};
+            for (int b = b0; b <= b1; ++b) {
+                double acc = 0.0;
+                for (int a = a0; a <= a1; ++a) {
+                    double v = m[(size_t)(j + b) * mmx + (i + a)];
+                    if (complementary) v = __dsub_rn(1.0, v);
+                    acc = (a == a0) ? v : __dadd_rn(acc, v);
+                }
+                row[b - b0] = acc;
+            }
+            fac = __dmul_rn(scale, (b1 > b0) ? __dadd_rn(row[0], row[1]) : row[0]);
+        }
+        w[idx] = __dmul_rn(fac, w[idx]);
+    }
+}
+int launch_mask_product(ilm_plan* p, double* w, int wlayout, const double* m, int mlayout, int complementary) {
+    const LayoutInfo lw = layout_info(wlayout, p->g.NX, p->g.NY), lm = layout_info(mlayout, p->g.NX, p->g.NY);
+    const size_t n = lw.n();
+    if (n == 0) return ILM_OK;
+    size_t blocks = (n + 255) / 256;
+    const size_t cap = (size_t)p->nsm * 16;
+    if (blocks > cap) blocks = cap;
+    k_mask_product<<<(unsigned)blocks, 256, 0, p->stream>>>(w, lw.mx, lw.my, (int)(2 * lw.sx), (int)(2 * lw.sy), m, lm.mx, lm.my,
+                                                           (int)(2 * lm.sx), (int)(2 * lm.sy), complementary);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
 }  // namespace ilm

@@ -190,6 +190,13 @@ int ilm_vsurface_curl_s2n(ilm_plan* plan, const double* v, double* nodes_dual);
 int ilm_vsurface_curl_n2s(ilm_plan* plan, const double* nodes_dual, double* v);
 /* _get_mask! with Edges grid data (vector cache) */
 int ilm_mask_edges(ilm_plan* plan, double* edges);
+/* mask!(w, cache) / complementary_mask!(w, cache) (src/surface_operators.jl:788-823) with
+ * _scalar_mask_product! / _vector_mask_product! (:880-923): w (in place) is multiplied by the mask,
+ * averaged onto w's layout (grid_interpolate!) when that is not the cache's own grid-data layout.
+ *   scalar cache: ILM_NODES_PRIMAL, ILM_NODES_DUAL, ILM_XEDGES, ILM_YEDGES, ILM_EDGES
+ *   vector cache: ILM_EDGES, ILM_NODES_DUAL, ILM_NODES_PRIMAL, ILM_EDGEGRAD                      */
+enum ilm_cache_kind { ILM_SCALAR_CACHE = 0, ILM_VECTOR_CACHE = 1 };
+int ilm_mask_product(ilm_plan* plan, int cache_kind, int layout, int complementary, double* w);
 /* Schur builders on VectorData: 2N x 2N, columns [col_begin, col_end) */
 enum ilm_schur_vector {
     ILM_V_RTLINVR = 0,    /* create_RTLinvR      (src/matrix_operators.jl:9-30)    */

@@ -405,6 +405,36 @@ def divergence_t2e(grid, dudx, dudy, dvdx, dvdy):
     return u, v
 
 
+def grid_interpolate(grid, m, src, dst):
+    """CartesianGrids grid_interpolate!(dst <- src) [UPSTREAM-RECALL, SURVEY.md A.3]: the mean of the
+    nearest source entries -- 2 points along a direction in which the layouts are offset by half a
+    cell, 4 points primal<->dual nodes; destination entries whose stencil leaves the source field
+    stay 0 (upstream leaves its zero-initialised scratch untouched there).  Parity unpinned: the exact
+    index ranges and the summation order of the 4-point mean are not fixed by any reference test."""
+    NX, NY = grid.NX, grid.NY
+    out = np.zeros(field_shape(dst, NX, NY))
+    (sxs, sys_), (sxd, syd) = field_shift(src), field_shift(dst)
+
+    def offs(ss, sd):                                       # source index offsets relative to the target index
+        d = int(round(2 * (ss - sd)))
+        return (0,) if d == 0 else ((-1, 0) if d < 0 else (0, 1))
+    ox, oy = offs(sxs, sxd), offs(sys_, syd)
+    mx, my = out.shape
+    i = np.arange(mx)[:, None]
+    j = np.arange(my)[None, :]
+    ok = (i + ox[0] >= 0) & (i + ox[-1] < m.shape[0]) & (j + oy[0] >= 0) & (j + oy[-1] < m.shape[1])
+    rows = []
+    for b in oy:
+        acc = None
+        for a in ox:
+            v = m[np.clip(i + a, 0, m.shape[0] - 1), np.clip(j + b, 0, m.shape[1] - 1)]
+            acc = v if acc is None else acc + v
+        rows.append(acc)
+    tot = rows[0] if len(rows) == 1 else rows[0] + rows[1]
+    out[...] = np.where(ok, (1.0 / (len(ox) * len(oy))) * tot, 0.0)
+    return out
+
+
 def laplacian(grid, w, kind, factor=1.0):
     """5-point stencil times L.factor on the layout's interior (A.3)."""
     mx, my = w.shape
@@ -609,6 +639,14 @@ class ScalarCache:
         return m * -1.0
 
     # -- Schur builders (src/matrix_operators.jl)
+    def mask_product(self, w, kind, complementary=False):
+        """mask!(w, cache) / complementary_mask!(w, cache) on a scalar cache
+        (src/surface_operators.jl:791-795, 814-818, 880-902): w .*= grid_interpolate(mask)."""
+        m = self.mask()
+        if complementary:
+            m = 1.0 - m                                     # _get_complementary_mask! (:856-859)
+        return grid_interpolate(self.grid, m, PRIMAL, kind) * w
+
     def _probe(self, pre, post, sign, scale, cols=None):
         N = self.N
         cols = range(N) if cols is None else cols
@@ -768,6 +806,19 @@ class VectorCache(ScalarCache):
         return u * -1.0, v * -1.0
 
     # -- Schur builders on VectorData (2N x 2N), src/matrix_operators.jl
+    def mask_product_v(self, w, kind, complementary=False):
+        """mask!/complementary_mask! on a vector cache (:796-800, 819-823, 904-923).  `w` is a tuple
+        (u, v) for kind 'edges', 4 components for 'edgegrad', one array for PRIMAL / DUAL."""
+        mu, mv = self.mask_edges()
+        if complementary:
+            mu, mv = 1.0 - mu, 1.0 - mv
+        if kind == "edges":
+            return mu * w[0], mv * w[1]
+        if kind == "edgegrad":                               # dudx, dvdy primal; dudy, dvdx dual; all from mask.u
+            kinds = (PRIMAL, DUAL, DUAL, PRIMAL)
+            return tuple(grid_interpolate(self.grid, mu, XEDGE, k) * c for k, c in zip(kinds, w))
+        return grid_interpolate(self.grid, mu, XEDGE, kind) * w
+
     def _probe_v(self, pre, post, sign, scale, nsolve=1, cols=None):
         N = self.N
         cols = range(2 * N) if cols is None else cols

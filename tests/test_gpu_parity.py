@@ -259,6 +259,38 @@ def test_mask(c1):
     assert relerr(cm.array(), 1.0 - oc.mask()) < RTOL
 
 
+@pytest.mark.parametrize("case", ["c1", "odd"])
+@pytest.mark.parametrize("complementary", [False, True])
+def test_mask_products(case, complementary, request):
+    """mask!(w, cache) / complementary_mask!(w, cache) on every layout of a scalar cache
+    (src/surface_operators.jl:788-823, 880-902; test/surface_ops.jl:190-210)."""
+    cache, oc = request.getfixturevalue(case)
+    rng = np.random.default_rng(5)
+    fn = ilm.complementary_mask if complementary else ilm.mask
+    mk = {o.PRIMAL: lambda: ilm.Nodes(ilm.Primal, cache.g), o.DUAL: lambda: ilm.Nodes(ilm.Dual, cache.g),
+          o.XEDGE: lambda: ilm.XEdges(cache.g), o.YEDGE: lambda: ilm.YEdges(cache.g)}
+    for kind, make in mk.items():
+        w = make()
+        a = rng.standard_normal(w.shape)
+        w.set(a)
+        assert fn(w, cache) is w
+        assert relerr(w.array(), oc.mask_product(a, kind, complementary)) < RTOL
+    q = cache.zeros_gridgrad()
+    au, av = rng.standard_normal(q.ushape), rng.standard_normal(q.vshape)
+    q.set(np.concatenate([au.ravel(order="F"), av.ravel(order="F")]))
+    fn(q, cache)
+    assert relerr(q.u, oc.mask_product(au, o.XEDGE, complementary)) < RTOL
+    assert relerr(q.v, oc.mask_product(av, o.YEDGE, complementary)) < RTOL
+    # ones -> area of the body (test/surface_ops.jl:193-207, 1e-3 on the reference's finer grid)
+    if case == "c1" and not complementary:
+        one = ilm.Nodes(ilm.Dual, cache.g).fill(1.0)
+        ilm.mask(one, cache)
+        area = o.dot_grid(oc.grid, one.array(), np.ones(one.shape), o.DUAL)
+        assert abs(area - np.pi) < 2e-2
+    with pytest.raises(ilm.MethodError):
+        ilm.mask(ilm.EdgeGradient(cache.g), cache)
+
+
 # ---------------------------------------------------------------- Schur builders, dense solve
 def test_schur_matrices(c1):
     cache, oc = c1

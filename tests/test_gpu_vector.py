@@ -187,3 +187,32 @@ def test_vector_schur_matrices():
         ilm.create_CL2invCT(sc)
     with pytest.raises(ilm.MethodError):
         ilm.surface_divergence(sc.zeros_gridgrad(), ilm.VectorData(sc.N), sc)
+
+
+@pytest.mark.parametrize("complementary", [False, True])
+def test_vector_mask_products(vc, complementary):
+    """mask!/complementary_mask! on a vector cache: Edges, Nodes{Dual}, Nodes{Primal}, EdgeGradient
+    (src/surface_operators.jl:796-800, 819-823, 904-923; test/surface_ops.jl:212-232)."""
+    cache, oc = vc
+    rng = np.random.default_rng(17)
+    fn = ilm.complementary_mask if complementary else ilm.mask
+    q = cache.zeros_grid()
+    au, av = rng.standard_normal(q.ushape), rng.standard_normal(q.vshape)
+    q.set(np.concatenate([au.ravel(order="F"), av.ravel(order="F")]))
+    fn(q, cache)
+    ru, rv = oc.mask_product_v((au, av), "edges", complementary)
+    assert relerr(q.u, ru) < RTOL and relerr(q.v, rv) < RTOL
+    for celltype, kind in ((ilm.Primal, o.PRIMAL), (ilm.Dual, o.DUAL)):
+        w = ilm.Nodes(celltype, cache.g)
+        a = rng.standard_normal(w.shape)
+        w.set(a)
+        fn(w, cache)
+        assert relerr(w.array(), oc.mask_product_v(a, kind, complementary)) < RTOL
+    t = cache.zeros_gridgrad()
+    A = [rng.standard_normal(s) for s in t.shapes]
+    t.set_components(A)
+    fn(t, cache)
+    for got, ref in zip(eg_arrays(t), oc.mask_product_v(tuple(A), "edgegrad", complementary)):
+        assert relerr(got, ref) < RTOL
+    with pytest.raises(ilm.MethodError):
+        fn(ilm.XEdges(cache.g), cache)

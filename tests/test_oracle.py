@@ -369,3 +369,37 @@ def test_implicit_diffusion_table():
         assert abs(K[0, 0] - a * (2 * K[1, 0] + 2 * K[0, 1] - 4 * K[0, 0]) - 1) < 1e-15
         tot = 4 * K.sum() - 2 * K[0, :].sum() - 2 * K[:, 0].sum() + K[0, 0]
         assert abs(tot - 1) < 1e-13
+
+
+# ---------------------------------------------------------------- mask products (test/surface_ops.jl:190-232)
+def test_mask_products_integrate_to_area(small_cache, small_vcache):
+    """mask!(ones) on every layout integrates to pi R^2 (the reference asserts 1e-3 on its dx=0.02 grid;
+    this fixture is coarser), and mask + complementary mask reproduce the field away from the ghosts."""
+    c, g = small_cache, small_cache.grid
+    for kind in (o.PRIMAL, o.DUAL, o.XEDGE, o.YEDGE):
+        one = np.ones(o.field_shape(kind, g.NX, g.NY))
+        inner = c.mask_product(one, kind)
+        assert abs(o.dot_grid(g, inner, one, kind) - np.pi) < 2e-2
+        outer = c.mask_product(one, kind, complementary=True)
+        assert np.abs((inner + outer)[2:-2, 2:-2] - 1.0).max() < 1e-12
+    v = small_vcache
+    ones_e = tuple(np.ones(o.field_shape(k, g.NX, g.NY)) for k in (o.XEDGE, o.YEDGE))
+    mu, mv = v.mask_product_v(ones_e, "edges")
+    assert abs(o.dot_grid(g, mu, ones_e[0], o.XEDGE) - np.pi) < 2e-2
+    assert abs(o.dot_grid(g, mv, ones_e[1], o.YEDGE) - np.pi) < 2e-2
+    kinds = (o.PRIMAL, o.DUAL, o.DUAL, o.PRIMAL)
+    ones_t = tuple(np.ones(o.field_shape(k, g.NX, g.NY)) for k in kinds)
+    for comp, k, one in zip(v.mask_product_v(ones_t, "edgegrad"), kinds, ones_t):
+        assert abs(o.dot_grid(g, comp, one, k) - np.pi) < 2e-2
+
+
+def test_grid_interpolate_is_exact_for_linear_fields():
+    g = o.Grid(12, 9, 0.5, (3, 2))
+    for src in o.KINDS:
+        xs, ys = g.coords(src)
+        m = 2.0 * xs[:, None] - 3.0 * ys[None, :] + 0.25
+        for dst in o.KINDS:
+            xd, yd = g.coords(dst)
+            ref = 2.0 * xd[:, None] - 3.0 * yd[None, :] + 0.25
+            got = o.grid_interpolate(g, m, src, dst)
+            assert np.abs(got - ref)[2:-2, 2:-2].max() < 1e-13      # the outer ring may be left at 0
