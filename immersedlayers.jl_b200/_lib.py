@@ -22,6 +22,10 @@ class ilm_grid(C.Structure):
     _fields_ = [("NX", C.c_int), ("NY", C.c_int), ("dx", C.c_double), ("I0x", C.c_int), ("I0y", C.c_int)]
 
 
+class ilm_slab_info(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nranks", "rank", "Lx", "Ly", "MYp", "row0", "row1", "ntc", "tc0", "tc1", "cpw", "wlo", "whi")]
+
+
 class IlmError(RuntimeError):
     """Generic library failure (ILM_ECUDA / ILM_ENOMEM / ILM_ENCCL)."""
 
@@ -90,6 +94,12 @@ SIGNATURES = {
     "ilm_create_schur_vector": (_i, [_vp, _i, _d, _i, _i, _dp]),
     "ilm_create_nRTRn_vector": (_i, [_vp, _d, _dp]),
     "ilm_dense_launch_count": (C.c_int64, []),
+    "ilm_slab_partition": (_i, [_i, _i, _i, _i, _i, C.POINTER(ilm_slab_info)]),
+    "ilm_slab_counts": (_i, [_i, _i, C.POINTER(ilm_slab_info), _i, _vp, _vp]),
+    "ilm_slab_buffer_doubles": (C.c_int64, [C.POINTER(ilm_slab_info)]),
+    "ilm_slab_forward": (_i, [_vp, C.POINTER(ilm_slab_info), _i, _dp, _i, _dp, _dp]),
+    "ilm_slab_columns": (_i, [_vp, C.POINTER(ilm_slab_info), _i, _dp, _dp]),
+    "ilm_slab_inverse": (_i, [_vp, C.POINTER(ilm_slab_info), _dp, _i, _dp, _i, _dp]),
     "ilm_profile_conv": (_i, [_vp, _i, _i, C.POINTER(C.c_double * 3)]),
     "ilm_profile_conv_probe": (_i, [_vp, _i, _i, C.POINTER(C.c_double * 3)]),
 }

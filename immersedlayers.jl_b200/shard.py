@@ -46,3 +46,105 @@ def create_schur_sharded(builder, cache, scale=1.0, group=None):
     flat = blk.t().contiguous().reshape(-1) if blk.numel() else blk.reshape(-1)
     full = allgather_columns(flat, cache.N, ranges, group)
     return full.view(cache.N, cache.N).t()
+
+
+# --------------------------------------------------------------------------
+# slab decomposition of ONE convolution
+# --------------------------------------------------------------------------
+def slab_info(NX, NY, rows, world_size, rank):
+    """Partition of one L^-1 solve over `world_size` GPUs (ilm_slab_partition; pure host
+    arithmetic, no GPU needed): field rows [row0,row1) and x-frequency tile columns [tc0,tc1)."""
+    from . import _lib as L
+    import ctypes as C
+    info = L.ilm_slab_info()
+    L.check(L.load().ilm_slab_partition(NX, NY, rows, world_size, rank, C.byref(info)))
+    return info
+
+
+def slab_counts(NX, NY, info, phase):
+    """(send_counts, recv_counts) in doubles of all-to-all #1 (phase 0) / #2 (phase 1)."""
+    from . import _lib as L
+    import ctypes as C
+    send = (C.c_int64 * info.nranks)()
+    recv = (C.c_int64 * info.nranks)()
+    L.check(L.load().ilm_slab_counts(NX, NY, C.byref(info), phase, send, recv))
+    return list(send), list(recv)
+
+
+class SlabLaplacian:
+    """inverse_laplacian! (src/grid_operators.jl:153-179) of ONE grid whose rows are spread over
+    the ranks of a torch.distributed group, one process per GPU.  Every rank holds a replica of the
+    plan (tables, Ghat) and a slab of rows of the field; the two transposes of the 2-D transform are
+    variable-count all-to-alls (NCCL over NVLink/NVSwitch), everything else runs in libilm_b200.
+
+        slab = SlabLaplacian(cache, L.NODES_PRIMAL)
+        mine = slab.scatter(full_field)            # torch tensor with this rank's rows
+        slab.inverse_laplacian(mine)               # in place
+    """
+
+    def __init__(self, cache, layout1, layout2=None, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib as L
+        self.cache, self.group = cache, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.layouts = (layout1, layout2)
+        g = cache.g
+        shapes = [g.layout_shape(l) for l in self.layouts if l is not None]
+        rows = max(s[1] for s in shapes)
+        self.info = slab_info(g.NX, g.NY, rows, self.world, self.rank)
+        self.counts = [slab_counts(g.NX, g.NY, self.info, ph) for ph in (0, 1)]
+        n = int(L.load().ilm_slab_buffer_doubles(C.byref(self.info)))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.send = torch.empty(n, dtype=torch.float64, device=dev)
+        self.recv = torch.empty(n, dtype=torch.float64, device=dev)
+        self._L, self._C = L, C
+
+    def rows(self, layout):
+        """Rows [r0, r1) of a field of this layout owned by this rank."""
+        my = self.cache.g.layout_shape(layout)[1]
+        return min(self.info.row0, my), min(self.info.row1, my)
+
+    def scatter(self, full, layout=None):
+        """This rank's rows of a full (mx, my) array as a flat device tensor (x fastest)."""
+        import numpy as np
+        import torch
+        layout = self.layouts[0] if layout is None else layout
+        r0, r1 = self.rows(layout)
+        part = np.ascontiguousarray(np.asarray(full, dtype=np.float64)[:, r0:r1].T).reshape(-1)
+        return torch.from_numpy(part).to(self.send.device)
+
+    def gather(self, mine, layout=None):
+        """Full (mx, my) numpy array on every rank (test / inspection helper)."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        layout = self.layouts[0] if layout is None else layout
+        mx, my = self.cache.g.layout_shape(layout)
+        parts = [None] * self.world
+        dist.all_gather_object(parts, mine.cpu().numpy(), group=self.group)
+        return np.concatenate([p.reshape(-1, mx) for p in parts], axis=0).T.copy()
+
+    def _exchange(self, phase):
+        import torch.distributed as dist
+        send, recv = self.counts[phase]
+        dist.all_to_all_single(self.recv[: sum(recv)], self.send[: sum(send)], output_split_sizes=recv,
+                               input_split_sizes=send, group=self.group)
+
+    def inverse_laplacian(self, w1, w2=None, kernel_id=0):
+        """w1 (and w2, the second layout) hold this rank's rows and are overwritten with L^-1 w
+        (kernel_id selects another convolution kernel, e.g. an integrating factor)."""
+        L, C = self._L, self._C
+        lib, plan, info = self.cache._lib, self.cache._plan, C.byref(self.info)
+        l1, l2 = self.layouts
+        if (w2 is None) != (l2 is None):
+            raise L.MethodError("SlabLaplacian: second field does not match the configured layouts")
+        p1 = C.c_void_p(w1.data_ptr())
+        p2 = C.c_void_p(w2.data_ptr()) if w2 is not None else None
+        L.check(lib.ilm_slab_forward(plan, info, l1, p1, -1 if l2 is None else l2, p2, C.c_void_p(self.send.data_ptr())))
+        self._exchange(0)
+        L.check(lib.ilm_slab_columns(plan, info, kernel_id, C.c_void_p(self.recv.data_ptr()), C.c_void_p(self.send.data_ptr())))
+        self._exchange(1)
+        L.check(lib.ilm_slab_inverse(plan, info, C.c_void_p(self.recv.data_ptr()), l1, p1, -1 if l2 is None else l2, p2))
+        return w1 if w2 is None else (w1, w2)

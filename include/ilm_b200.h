@@ -211,6 +211,39 @@ int ilm_create_nRTRn_vector(ilm_plan* plan, double scale, double* A);
 /* kernels launched by the three ilm_dense_* entry points since load (bench bookkeeping) */
 int64_t ilm_dense_launch_count(void);
 
+/* ---- slab decomposition of one convolution over several GPUs ---------------------------------
+ * Multi-GPU form of inverse_laplacian! (src/grid_operators.jl:153-179; the reference itself is
+ * single-process) for ONE grid whose rows are spread over `nranks` GPUs, one process per GPU
+ * (BASELINE config C5b).  Rank r owns the field rows [row0,row1) and, for the
+ * column pass, the x-frequency tile columns [tc0,tc1).  A solve is
+ *     ilm_slab_forward -> all-to-all #1 -> ilm_slab_columns -> all-to-all #2 -> ilm_slab_inverse
+ * where the library computes and packs / unpacks the exchange buffers and the host language issues
+ * the two variable-count all-to-alls (counts from ilm_slab_counts, in doubles, peer-major buffers).
+ * ilm_slab_partition / _counts / _buffer_doubles are pure host arithmetic (no GPU needed).
+ * Every data pointer of the three compute calls is a DEVICE pointer; w*_rows address this rank's first
+ * row (row0) of the field, mx * (min(row1, my) - row0) doubles.                                    */
+typedef struct {
+    int nranks, rank;
+    int Lx, Ly;     /* half padded transform lengths                                   */
+    int MYp;        /* rows carried through the spectrum (even)                        */
+    int row0, row1; /* field rows of this rank (even boundaries; row1 may exceed my by the pad row) */
+    int ntc;        /* tile columns (pairs of x-frequency columns) in total            */
+    int tc0, tc1;   /* tile columns of this rank                                       */
+    int cpw;        /* x-frequency columns per work item of the column pass            */
+    int wlo, whi;   /* work items of the column pass owned by this rank                */
+} ilm_slab_info;
+/* rows = number of rows (my) of the widest field carried by the solve */
+int ilm_slab_partition(int NX, int NY, int rows, int nranks, int rank, ilm_slab_info* out);
+/* phase 0: exchange #1 (rows -> columns), phase 1: exchange #2 (columns -> rows); send[q], recv[q] in doubles */
+int ilm_slab_counts(int NX, int NY, const ilm_slab_info* me, int phase, int64_t* send, int64_t* recv);
+/* capacity (doubles) that each of the send and receive buffers needs */
+int64_t ilm_slab_buffer_doubles(const ilm_slab_info* me);
+int ilm_slab_forward(ilm_plan* plan, const ilm_slab_info* me, int layout1, const double* w1_rows, int layout2,
+                     const double* w2_rows /* NULL: one field */, double* sendbuf);
+int ilm_slab_columns(ilm_plan* plan, const ilm_slab_info* me, int kernel_id, const double* recvbuf, double* sendbuf);
+int ilm_slab_inverse(ilm_plan* plan, const ilm_slab_info* me, const double* recvbuf, int layout1, double* w1_rows, int layout2,
+                     double* w2_rows /* NULL: one field */);
+
 /* ---- measurement hook ------------------------------------------------------
  * Times each pass of the convolution (A: rows forward, B: columns, C: rows
  * inverse) on the plan's stream with CUDA events: `reps` back-to-back launches

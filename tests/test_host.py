@@ -157,3 +157,126 @@ def test_fft_kernel_bodies_on_cpu():
                            "-o", exe, os.path.join(CSRC, "test_fft_host.cu")])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "PASS" in out.stdout, out.stdout[-2000:]
+
+
+# ---------------------------------------------------------------- slab decomposition (section 8e, config C5b)
+def test_slab_partition_is_consistent():
+    """ilm_slab_partition / ilm_slab_counts (pure host arithmetic): the ranks tile the rows and the
+    tile columns, row boundaries are even, and what p sends to q is what q expects from p."""
+    from ilm_b200 import shard
+    for NX, NY in ((24, 20), (24, 600), (600, 24), (130, 129), (4096, 4096)):
+        rows = NY - 1
+        for world in (1, 2, 3, 8):
+            infos = [shard.slab_info(NX, NY, rows, world, r) for r in range(world)]
+            assert infos[0].row0 == 0 and infos[-1].row1 == infos[0].MYp >= rows
+            assert infos[0].tc0 == 0 and infos[-1].tc1 == infos[0].ntc == infos[0].Lx
+            for a, b in zip(infos, infos[1:]):
+                assert a.row1 == b.row0 and a.tc1 == b.tc0 and a.whi == b.wlo
+            assert all(i.row0 % 2 == 0 and i.row1 % 2 == 0 for i in infos)
+            for phase in (0, 1):
+                cnt = [shard.slab_counts(NX, NY, i, phase) for i in infos]
+                for p in range(world):
+                    for q in range(world):
+                        assert cnt[p][0][q] == cnt[q][1][p]
+                total = sum(sum(c[0]) for c in cnt)
+                assert total == 4 * infos[0].ntc * infos[0].MYp          # the whole spectrum, in doubles
+
+
+def _slab_worker(rank, world, port, NX, NY, q):
+    """numpy emulation of the three slab stages around REAL all_to_all_single calls (gloo), with the
+    partition, the counts and the block order of csrc/ilm_slab.cu; result vs the oracle."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ilm_oracle as o
+    from ilm_b200 import lgf, shard
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mx, my = NX - 1, NY - 1
+    info = shard.slab_info(NX, NY, my, world, rank)
+    peers = [shard.slab_info(NX, NY, my, world, r) for r in range(world)]
+    Lx, Ly, MYp = info.Lx, info.Ly, info.MYp
+    G = lgf.lgf_table(max(NX, NY))
+    c0, factor = 0.37, 2.5
+    w = np.random.default_rng(3).standard_normal((mx, my))
+    ref = o.inverse_laplacian(o.ConvPlan(G[:NX, :NY]), w, c0, factor)
+    # multiplier on the (2Lx, 2Ly) pad: even extension of (G - c0) / factor
+    K = np.zeros((2 * Lx, 2 * Ly))
+    ii = np.minimum(np.arange(2 * Lx), 2 * Lx - np.arange(2 * Lx))
+    jj = np.minimum(np.arange(2 * Ly), 2 * Ly - np.arange(2 * Ly))
+    okx, oky = ii < NX, jj < NY
+    K[np.ix_(okx, oky)] = (G[np.ix_(ii[okx], jj[oky])] - c0) / factor
+    Ghat = np.fft.fft2(K).real
+
+    def kx_of(tc, ms):                      # tile column -> x frequency (ilm_conv.cuh layout)
+        px, a = divmod(tc, Lx // 2)
+        return 2 * (2 * a + ms) + px
+
+    # stage 1: FFT_x of my rows, spectrum in tile layout S[tc, row, ms]
+    mine = np.zeros((MYp, mx))
+    r0, r1 = info.row0, min(info.row1, my)
+    mine[r0:r1] = w[:, r0:r1].T
+    X = np.fft.fft(mine[info.row0:info.row1], n=2 * Lx, axis=1)          # (my rows, kx)
+    S = np.zeros((info.ntc, MYp, 2), dtype=complex)
+    for tc in range(info.ntc):
+        for ms in (0, 1):
+            S[tc, info.row0:info.row1, ms] = X[:, kx_of(tc, ms)]
+
+    def pack(A, blocks):                   # blocks: (tc0, tc1, row0, row1) per peer, peer-major
+        out = [A[t0:t1, a:b].reshape(-1) for (t0, t1, a, b) in blocks]
+        return np.concatenate(out) if out else np.zeros(0, dtype=complex)
+
+    def exchange(buf, phase):
+        send, recv = shard.slab_counts(NX, NY, info, phase)
+        sb = torch.from_numpy(buf.view(np.float64).copy())
+        assert sb.numel() == sum(send)
+        rb = torch.empty(sum(recv), dtype=torch.float64)
+        dist.all_to_all_single(rb, sb, output_split_sizes=recv, input_split_sizes=send)
+        return rb.numpy().view(complex)
+
+    got = exchange(pack(S, [(p.tc0, p.tc1, info.row0, info.row1) for p in peers]), 0)
+    # stage 2: my tile columns, all rows
+    C = np.zeros((info.tc1 - info.tc0, MYp, 2), dtype=complex)
+    off = 0
+    for p in peers:
+        n = (info.tc1 - info.tc0) * (p.row1 - p.row0) * 2
+        C[:, p.row0:p.row1] = got[off:off + n].reshape(info.tc1 - info.tc0, p.row1 - p.row0, 2)
+        off += n
+    for t in range(info.tc1 - info.tc0):
+        for ms in (0, 1):
+            col = np.fft.fft(C[t, :, ms], n=2 * Ly) * Ghat[kx_of(info.tc0 + t, ms)]
+            C[t, :, ms] = np.fft.ifft(col)[:MYp]
+    got = exchange(pack(C, [(0, info.tc1 - info.tc0, p.row0, p.row1) for p in peers]), 1)
+    # stage 3: every tile column, my rows
+    S2 = np.zeros((info.ntc, info.row1 - info.row0, 2), dtype=complex)
+    off = 0
+    for p in peers:
+        n = (p.tc1 - p.tc0) * (info.row1 - info.row0) * 2
+        S2[p.tc0:p.tc1] = got[off:off + n].reshape(p.tc1 - p.tc0, info.row1 - info.row0, 2)
+        off += n
+    X2 = np.zeros((info.row1 - info.row0, 2 * Lx), dtype=complex)
+    for tc in range(info.ntc):
+        for ms in (0, 1):
+            X2[:, kx_of(tc, ms)] = S2[tc, :, ms]
+    out = np.fft.ifft(X2, axis=1)[:, :mx].real                          # (my rows, mx)
+    err = np.abs(out[: r1 - r0] - ref[:, r0:r1].T).max() / np.abs(ref).max() if r1 > r0 else 0.0
+    q.put((rank, float(err)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("NX,NY", [(24, 20), (24, 600), (300, 24)])
+def test_slab_exchange_gloo_world2(NX, NY):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + NX + NY) % 2000
+    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, NX, NY, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r for r, _ in res] == [0, 1]
+    assert all(e < 1e-12 for _, e in res), res
