@@ -79,6 +79,8 @@ struct ConvArgs {
     int olo, ohi;          // only output rows [olo, ohi) are needed (Schur probes: the rows under the
                            // interpolation windows); pass B stores and pass C inverts only those rows,
                            // the other rows of the output fields are left untouched.  olo is even.
+    const double2* wl2x;   // exp(-2 pi i n / (2 Lx)), n < 2 Lx (only for Lx > 4096, ilm_conv_big.cuh)
+    double2* scratch;      // per-CTA hand-off lines of the big column pass (2 groups x Ly complex per CTA)
     int wlo, whi;          // pass B visits the work items [wlo, whi) only (slab decomposition: the x-frequency
                            // columns this GPU owns); whi <= 0 = all of them
 };

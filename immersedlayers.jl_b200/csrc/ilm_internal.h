@@ -75,6 +75,8 @@ struct ilm_plan {
     int Lx = 0, Ly = 0;
     double2 *twx = nullptr, *twy = nullptr;
     double2* wl2y = nullptr;        // exp(-2 pi i n / (2 Ly)) table for the sparse forward transform
+    double2* wl2x = nullptr;        // same for x, only when Lx > 4096 (ilm_conv_big.cuh)
+    double2* conv_scratch = nullptr; // per-CTA hand-off lines of the big column pass (Ly > 4096)
     double2 *S = nullptr, *S2 = nullptr;
     size_t s_cap = 0;
     alignas(64) unsigned char tmap_s2[128] = {};   // CUtensorMap of S2 for the current row count (pass C)
@@ -164,6 +166,7 @@ int conv_add_kernel(ilm_plan* p, const double* table_host_or_dev, int n, double 
 // [olo, ohi) are needed by the caller (-1, -1 = all), the others are left untouched
 int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1);
 void conv_free(ilm_plan* p);
+ConvArgs conv_base_args(const ilm_plan* p);      // plan-constant kernel arguments (buffers, twiddle tables)
 int conv_half_len(int n);                       // half padded transform length of an n-cell direction
 int make_s2_tensor_map(ilm_plan* p, int MYp);    // bulk-tensor map of S2 for pass C
 int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1);

@@ -18,6 +18,8 @@ namespace ilm {
     const double2* conv_twiddles_L##L(size_t* count);
 ILM_DECL_L(16) ILM_DECL_L(32) ILM_DECL_L(64) ILM_DECL_L(128) ILM_DECL_L(256)
 ILM_DECL_L(512) ILM_DECL_L(1024) ILM_DECL_L(2048) ILM_DECL_L(4096)
+int conv_launch_big_Q2(int which, const ConvArgs& a, int nsm, cudaStream_t st, const void* tmap);
+int conv_launch_big_Q4(int which, const ConvArgs& a, int nsm, cudaStream_t st, const void* tmap);
 
 conv_launch_fn conv_launcher(int L) {
     switch (L) {
@@ -30,11 +32,14 @@ conv_launch_fn conv_launcher(int L) {
     case 1024: return conv_launch_L1024;
     case 2048: return conv_launch_L2048;
     case 4096: return conv_launch_L4096;
+    case 8192: return conv_launch_big_Q2;          // radix-2Q step over the 4096-point transform
+    case 16384: return conv_launch_big_Q4;
     default: return nullptr;
     }
 }
 
 const double2* conv_twiddles_host(int L, size_t* count) {
+    if (L > 4096) L = 4096;                        // big lengths run 4096-point sub-transforms
     switch (L) {
     case 16: return conv_twiddles_L16(count);
     case 32: return conv_twiddles_L32(count);
@@ -89,8 +94,8 @@ int conv_setup(ilm_plan* p) {
     if (const char* e = getenv("ILM_CONV_SKEW_NS")) p->skew_ns = atoi(e);
     p->Lx = conv_half_len(p->g.NX);
     p->Ly = conv_half_len(p->g.NY);
-    if (p->Lx > 4096 || p->Ly > 4096) {
-        set_error("grid larger than 4096 cells per direction is not supported by the single-GPU FFT engine yet");
+    if (p->Lx > 16384 || p->Ly > 16384) {
+        set_error("grid larger than 16384 cells per direction is not supported by the FFT engine");
         return ILM_ESIZE;
     }
     size_t nx = 0, ny = 0;
@@ -100,13 +105,17 @@ int conv_setup(ilm_plan* p) {
     ILM_CUDA(cudaMalloc(&p->twy, ny * sizeof(double2)));
     ILM_CUDA(cudaMemcpyAsync(p->twx, hx, nx * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
     ILM_CUDA(cudaMemcpyAsync(p->twy, hy, ny * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
-    {
-        std::vector<double2> w(2 * (size_t)p->Ly);
-        const long double tp = -2.0L * acosl(-1.0L) / (2.0L * p->Ly);
+    auto upload_wl2 = [&](int L, double2** dst) -> int {           // exp(-2 pi i n / 2L), n < 2L
+        std::vector<double2> w(2 * (size_t)L);
+        const long double tp = -2.0L * acosl(-1.0L) / (2.0L * L);
         for (size_t n = 0; n < w.size(); ++n) w[n] = cmk((double)cosl(tp * n), (double)sinl(tp * n));
-        ILM_CUDA(cudaMalloc(&p->wl2y, w.size() * sizeof(double2)));
-        ILM_CUDA(cudaMemcpy(p->wl2y, w.data(), w.size() * sizeof(double2), cudaMemcpyHostToDevice));
-    }
+        ILM_CUDA(cudaMalloc(dst, w.size() * sizeof(double2)));
+        ILM_CUDA(cudaMemcpy(*dst, w.data(), w.size() * sizeof(double2), cudaMemcpyHostToDevice));
+        return ILM_OK;
+    };
+    ILM_TRY(upload_wl2(p->Ly, &p->wl2y));
+    if (p->Lx > 4096) ILM_TRY(upload_wl2(p->Lx, &p->wl2x));
+    if (p->Ly > 4096) ILM_CUDA(cudaMalloc(&p->conv_scratch, (size_t)p->nsm * 2 * p->Ly * sizeof(double2)));
     ConvGeom g{p->Lx, p->Ly, p->g.NY, (p->g.NY + 1) & ~1};
     p->s_cap = s_elems(g);
     ILM_CUDA(cudaMalloc(&p->S, p->s_cap * sizeof(double2)));
@@ -116,11 +125,23 @@ int conv_setup(ilm_plan* p) {
 }
 
 void conv_free(ilm_plan* p) {
-    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->wl2y); cudaFree(p->S); cudaFree(p->S2);
+    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->wl2y); cudaFree(p->wl2x); cudaFree(p->conv_scratch); cudaFree(p->S); cudaFree(p->S2);
     for (auto& k : p->kernels) cudaFree(k.ghat);
     cudaFree(p->lgf_dev); p->lgf_dev = nullptr;
     p->kernels.clear();
 }
+
+// the plan-constant part of the kernel arguments
+ConvArgs conv_base_args(const ilm_plan* p) {
+    ConvArgs a{};
+    a.S = p->S; a.S2 = p->S2;
+    a.twx = p->twx; a.twy = p->twy;
+    a.skew_ns = p->skew_ns;
+    a.wl2y = p->wl2y; a.wl2x = p->wl2x;
+    a.scratch = p->conv_scratch;
+    return a;
+}
+static bool use_tma(const ilm_plan* p) { return p->Lx >= 512 && p->Lx <= 4096; }
 
 // table: n x n column-major (host or device), n >= max(NX, NY)
 int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double factor, int* id) {
@@ -139,19 +160,15 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     // h = eps_i eps_j (G - c0) into scratch field g_a (NX x NY)
     ILM_TRY(launch_lgf_prep(p, src, n, NX, NY, c0, p->g_a));
     ConvKernel k;
-    ConvArgs a{};
+    ConvArgs a = conv_base_args(p);
     a.g = ConvGeom{p->Lx, p->Ly, NY, (NY + 1) & ~1};
     ILM_CUDA(cudaMalloc(&k.ghat, ghat_elems(a.g) * sizeof(double)));
     a.f1 = FieldRef{p->g_a, NX, NY};
     a.f2 = FieldRef{nullptr, 0, 0};
     a.rlo = 0; a.rhi = a.g.MYp;
     a.olo = 0; a.ohi = a.g.MYp;
-    a.S = p->S; a.S2 = p->S2;
     a.GhatOut = k.ghat;
     a.gscale = 1.0 / (4.0 * (double)p->Lx * (double)p->Ly * factor);
-    a.twx = p->twx; a.twy = p->twy;
-    a.skew_ns = p->skew_ns;
-    a.wl2y = p->wl2y;
     ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream, nullptr));
     ILM_TRY(conv_launcher(p->Ly)(3, a, p->nsm, p->stream, nullptr));
     p->launches += 2;
@@ -170,7 +187,7 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
         set_error("unknown convolution kernel id");
         return ILM_EINVAL;
     }
-    ConvArgs a{};
+    ConvArgs a = conv_base_args(p);
     int MY = f1.p ? f1.my : 0;
     if (f2.p && f2.my > MY) MY = f2.my;
     if (MY == 0) return ILM_OK;
@@ -181,12 +198,8 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
     a.olo = olo < 0 ? 0 : (olo & ~1);
     a.ohi = (ohi < 0 || ohi > a.g.MYp) ? a.g.MYp : ohi;
     if (a.ohi <= a.olo) { a.olo = 0; a.ohi = a.g.MYp < 2 ? a.g.MYp : 2; }
-    a.S = p->S; a.S2 = p->S2;
     a.Ghat = p->kernels[kernel_id].ghat;
-    a.twx = p->twx; a.twy = p->twy;
-    a.skew_ns = p->skew_ns;
-    a.wl2y = p->wl2y;
-    if (p->Lx >= 512) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
+    if (use_tma(p)) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
     ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream, nullptr));
     ILM_TRY(conv_launcher(p->Ly)(1, a, p->nsm, p->stream, nullptr));
     ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, p->stream, p->tmap_s2));
@@ -196,7 +209,7 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
 
 // per-pass timing for the roofline report (ilm_profile_conv)
 int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo, int rhi, int olo, int ohi) {
-    ConvArgs a{};
+    ConvArgs a = conv_base_args(p);
     int MY = f1.my > f2.my ? f1.my : f2.my;
     a.g = ConvGeom{p->Lx, p->Ly, MY, (MY + 1) & ~1};
     a.f1 = f1; a.f2 = f2;
@@ -205,16 +218,12 @@ int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], 
     a.olo = olo < 0 ? 0 : (olo & ~1);
     a.ohi = (ohi < 0 || ohi > a.g.MYp) ? a.g.MYp : ohi;
     if (a.ohi <= a.olo) { a.olo = 0; a.ohi = a.g.MYp < 2 ? a.g.MYp : 2; }
-    a.S = p->S; a.S2 = p->S2;
     a.Ghat = p->kernels[0].ghat;
-    a.twx = p->twx; a.twy = p->twy;
-    a.skew_ns = p->skew_ns;
-    a.wl2y = p->wl2y;
     cudaEvent_t e0, e1;
     ILM_CUDA(cudaEventCreate(&e0));
     ILM_CUDA(cudaEventCreate(&e1));
     const int Ls[3] = {p->Lx, p->Ly, p->Lx};
-    if (p->Lx >= 512) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
+    if (use_tma(p)) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
     for (int which = 0; which < 3; ++which) {
         ILM_TRY(conv_launcher(Ls[which])(which, a, p->nsm, p->stream, p->tmap_s2));      // warm-up
         ILM_CUDA(cudaEventRecord(e0, p->stream));

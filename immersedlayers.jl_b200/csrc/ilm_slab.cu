@@ -86,13 +86,9 @@ int check_info(const ilm_plan* p, const ilm_slab_info* s, int my1, int my2) {
 }
 
 ConvArgs base_args(ilm_plan* p, const ilm_slab_info* s, int kernel_id) {
-    ConvArgs a{};
+    ConvArgs a = conv_base_args(p);
     a.g = ConvGeom{p->Lx, p->Ly, s->MYp, s->MYp};
-    a.S = p->S; a.S2 = p->S2;
     a.Ghat = p->kernels[kernel_id].ghat;
-    a.twx = p->twx; a.twy = p->twy;
-    a.skew_ns = p->skew_ns;
-    a.wl2y = p->wl2y;
     a.rlo = 0; a.rhi = s->MYp; a.olo = 0; a.ohi = s->MYp;
     return a;
 }
@@ -211,7 +207,7 @@ extern "C" int ilm_slab_inverse(ilm_plan* p, const ilm_slab_info* s, const doubl
     a.f1 = slab_ref(p, layout1, w1_rows, s->row0);
     a.f2 = slab_ref(p, layout2, w2_rows, s->row0);
     a.olo = s->row0; a.ohi = s->row1;
-    if (p->Lx >= 512) ILM_TRY(make_s2_tensor_map(p, s->MYp));
+    if (p->Lx >= 512 && p->Lx <= 4096) ILM_TRY(make_s2_tensor_map(p, s->MYp));
     ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, p->stream, p->tmap_s2));
     p->launches++;
     return ILM_OK;

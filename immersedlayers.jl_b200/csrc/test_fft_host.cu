@@ -12,7 +12,7 @@
 #include <thread>
 #include <vector>
 
-#include "ilm_conv.cuh"
+#include "ilm_conv_big.cuh"
 
 using namespace ilm;
 
@@ -114,6 +114,25 @@ template <int L, bool INV> static double test_fft() {
 }
 
 // ---------------------------------------------------------------- convolution
+// lengths above 4096 go through the radix-2Q bodies of ilm_conv_big.cuh
+template <int L> struct Len {
+    static constexpr bool big = L > 4096;
+    static constexpr int base = big ? 4096 : L;
+    static constexpr int Q = big ? L / 4096 : 1;
+    using Cfg = FftCfg<base>;
+    static constexpr int cpw = big ? 2 : (Cfg::F == 1 ? 2 : Cfg::F);        // pass B / C work item width
+    static int rowsA(int nrows) { return big ? nrows * Q : (nrows + Cfg::F - 1) / Cfg::F; }
+    static int rowsC(int nrows) { return big ? nrows * Q : (nrows + cpw - 1) / cpw; }
+};
+template <int L> static void runA(HostCtx& c, const ConvArgs& a, double2* sm, int b, int nb) {
+    if constexpr (Len<L>::big) passA_big_body<Len<L>::Q>(c, a, sm, b, nb); else passA_body<L>(c, a, sm, b, nb);
+}
+template <int L, int MODE> static void runB(HostCtx& c, const ConvArgs& a, double2* sm, int b, int nb) {
+    if constexpr (Len<L>::big) passB_big_body<Len<L>::Q, MODE>(c, a, sm, b, nb); else passB_body<L, MODE>(c, a, sm, b, nb);
+}
+template <int L> static void runC(HostCtx& c, const ConvArgs& a, double2* sm, int b, int nb) {
+    if constexpr (Len<L>::big) passC_big_body<Len<L>::Q>(c, a, sm, b, nb); else passC_body<L>(c, a, sm, b, nb);
+}
 
 
 template <int LX, int LY>
@@ -123,14 +142,19 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
     std::vector<double> G((size_t)NX * NY);
     for (int j = 0; j < NY; ++j)
         for (int i = 0; i < NX; ++i) G[(size_t)j * NX + i] = 0.3 * log(1.0 + i * i + 2.0 * j * j) + 0.1 * cos(0.3 * i) - 0.05 * j;
-    std::vector<double2> twx(FftCfg<LX>::TW_TOTAL + 1), twy(FftCfg<LY>::TW_TOTAL + 1);
-    fft_fill_twiddles<LX>(twx.data(), expm2pii);
-    fft_fill_twiddles<LY>(twy.data(), expm2pii);
+    using CX = typename Len<LX>::Cfg;
+    using CY = typename Len<LY>::Cfg;
+    std::vector<double2> twx(CX::TW_TOTAL + 1), twy(CY::TW_TOTAL + 1);
+    fft_fill_twiddles<Len<LX>::base>(twx.data(), expm2pii);
+    fft_fill_twiddles<Len<LY>::base>(twy.data(), expm2pii);
     ConvArgs a{};
     a.twx = twx.data(); a.twy = twy.data();
-    std::vector<double2> wl2(2 * LY);
+    std::vector<double2> wl2(2 * LY), wl2x(2 * LX);
     for (int n = 0; n < 2 * LY; ++n) wl2[n] = expm2pii(n, 2LL * LY);
-    a.wl2y = wl2.data();
+    for (int n = 0; n < 2 * LX; ++n) wl2x[n] = expm2pii(n, 2LL * LX);
+    a.wl2y = wl2.data(); a.wl2x = wl2x.data();
+    std::vector<double2> scratch((size_t)3 * 2 * LY, cmk(NAN, NAN));        // up to 3 emulated CTAs
+    a.scratch = scratch.data();
     // ---- Ghat build: h = eps_i eps_j g
     std::vector<double> h((size_t)NX * NY);
     for (int j = 0; j < NY; ++j)
@@ -143,14 +167,14 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
     a.olo = 0; a.ohi = gg.MYp;
     a.S = S.data(); a.GhatOut = Ghat.data(); a.gscale = 1.0 / (4.0 * LX * LY);
     {
-        int nwork = (gg.MYp + FftCfg<LX>::F - 1) / FftCfg<LX>::F;
+        int nwork = Len<LX>::rowsA(gg.MYp);
         int nb = nwork > 3 ? 3 : nwork;     // exercise the persistent loop
         for (int b = 0; b < nb; ++b)
-            run_cta(FftCfg<LX>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passA_body<LX>(c, a, sm, b, nb); });
-        nwork = (2 * gg.Lx + (FftCfg<LY>::F == 1 ? 2 : FftCfg<LY>::F) - 1) / (FftCfg<LY>::F == 1 ? 2 : FftCfg<LY>::F);
+            run_cta(CX::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runA<LX>(c, a, sm, b, nb); });
+        nwork = (2 * gg.Lx + Len<LY>::cpw - 1) / Len<LY>::cpw;
         nb = nwork > 3 ? 3 : nwork;
         for (int b = 0; b < nb; ++b)
-            run_cta(FftCfg<LY>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passB_body<LY, 1>(c, a, sm, b, nb); });
+            run_cta(CY::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runB<LY, 1>(c, a, sm, b, nb); });
     }
     // ---- fields
     std::mt19937_64 rng(NX * 131 + NY);
@@ -178,18 +202,18 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
     a.f2 = second ? FieldRef{o2.data(), mx2, my2} : FieldRef{nullptr, 0, 0};
     a.S = S.data(); a.S2 = S2.data(); a.Ghat = Ghat.data();
     {
-        int nwork = (a.ohi - a.olo + (FftCfg<LX>::F == 1 ? 2 : FftCfg<LX>::F) - 1) / (FftCfg<LX>::F == 1 ? 2 : FftCfg<LX>::F);
+        int nwork = Len<LX>::rowsC(a.ohi - a.olo);
         int nb = nwork > 2 ? 2 : nwork;
-        int nworkA = (a.rhi - a.rlo + FftCfg<LX>::F - 1) / FftCfg<LX>::F;
+        int nworkA = Len<LX>::rowsA(a.rhi - a.rlo);
         int nbA = nworkA > 2 ? 2 : nworkA;
         for (int b = 0; b < nbA; ++b)
-            run_cta(FftCfg<LX>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passA_body<LX>(c, a, sm, b, nbA); });
-        int nworkB = (2 * g2.Lx + (FftCfg<LY>::F == 1 ? 2 : FftCfg<LY>::F) - 1) / (FftCfg<LY>::F == 1 ? 2 : FftCfg<LY>::F);
+            run_cta(CX::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runA<LX>(c, a, sm, b, nbA); });
+        int nworkB = (2 * g2.Lx + Len<LY>::cpw - 1) / Len<LY>::cpw;
         int nbB = nworkB > 3 ? 3 : nworkB;
         for (int b = 0; b < nbB; ++b)
-            run_cta(FftCfg<LY>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passB_body<LY, 0>(c, a, sm, b, nbB); });
+            run_cta(CY::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runB<LY, 0>(c, a, sm, b, nbB); });
         for (int b = 0; b < nb; ++b)
-            run_cta(FftCfg<LX>::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passC_body<LX>(c, a, sm, b, nb); });
+            run_cta(CX::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runC<LX>(c, a, sm, b, nb); });
     }
     // ---- direct check (sampled)
     double err = 0, nrm = 0;
@@ -245,6 +269,12 @@ int main() {
     worst = fmax(worst, test_conv<64, 32>(24, 13, 24, 12, 23, 13, true, 5, 9, 3, 11));      // pruned output rows
     worst = fmax(worst, test_conv<16, 1024>(6, 400, 6, 400, 5, 399, true, 201, 206, 101, 333));
     worst = fmax(worst, test_conv<512, 16>(200, 5, 199, 5, 200, 4, true, 1, 3, 2, 4));
+    if (getenv("ILM_TEST_BIG")) {          // lengths above 4096 (radix-2Q step, ilm_conv_big.cuh); slower
+        worst = fmax(worst, test_conv<8192, 16>(4500, 3, 4500, 3, 4499, 2, true));
+        worst = fmax(worst, test_conv<16, 8192>(3, 4500, 2, 4500, 3, 4499, true));
+        worst = fmax(worst, test_conv<16384, 16>(9000, 2, 9000, 2, 8999, 2, true));
+        worst = fmax(worst, test_conv<16, 16384>(2, 9000, 2, 9000, 1, 8999, true, 4000, 4007, 3000, 6001));
+    }
     printf("worst relative error %.3e -> %s\n", worst, worst < 1e-12 ? "PASS" : "FAIL");
     return worst < 1e-12 ? 0 : 1;
 }

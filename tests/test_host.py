@@ -153,10 +153,12 @@ def test_fft_kernel_bodies_on_cpu():
     emulated threads per CTA vs long-double DFT / direct convolution."""
     exe = os.path.join(CSRC, "build", "test_fft_host")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-x", "c++", "-I/usr/local/cuda/include", "-pthread",
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-x", "c++", "-I/usr/local/cuda/include", "-pthread",
                            "-o", exe, os.path.join(CSRC, "test_fft_host.cu")])
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    # ILM_TEST_BIG: also the radix-2Q bodies for lengths 8192 / 16384 (csrc/ilm_conv_big.cuh)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=dict(os.environ, ILM_TEST_BIG="1"))
     assert out.returncode == 0 and "PASS" in out.stdout, out.stdout[-2000:]
+    assert "Lx=16384" in out.stdout and "Ly=16384" in out.stdout
 
 
 # ---------------------------------------------------------------- slab decomposition (section 8e, config C5b)
