@@ -41,7 +41,7 @@ template <int Q> ILM_HD double2 rotq(double2 z, int t) {
 }
 
 // ---------------------------------------------------------------- pass A (rows, forward)
-// work item = (row, k1); group p computes the class c = p + 2 k1
+// work item = row (its Q classes k1 in sequence); group p computes the class c = p + 2 k1
 template <int Q, class Ctx>
 ILM_HD void passA_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, int nblocks) {
     using C = FftCfg<BIG_M>;
@@ -51,8 +51,11 @@ ILM_HD void passA_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block
     const int j = ctx.tid, px = ctx.grp;
     double2* xb = smem + ctx.grp * C::GROUP_XBUF;
     const unsigned mask = 2u * (unsigned)a.g.Lx - 1u;
+    // work item = one row, its Q classes back to back on the same CTA: the row is re-read from L1/L2
+    // and the 16-byte halves of a spectrum sector (m even / odd = k1 even / odd) are written within
+    // microseconds of each other, so that L2 merges them into full-sector DRAM writes
     const int nwork = (a.rhi - a.rlo) * Q;
-    for (int w = block; w < nwork; w += nblocks) {
+    for (int w = block * Q; w < nwork; w = ((w + 1) % Q) ? w + 1 : w + 1 + (nblocks - 1) * Q) {
         const int row = a.rlo + w / Q, k1 = w % Q;
         const unsigned cls = (unsigned)(px + 2 * k1);
         const bool r1 = a.f1.p && row < a.f1.my, r2 = a.f2.p && row < a.f2.my;
@@ -191,6 +194,8 @@ ILM_HD void passC_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block
     const unsigned mask = 2u * (unsigned)a.g.Lx - 1u;
     const int nwork = (a.ohi - a.olo) * Q;
     if (!px) ctx.arrive(BAR_FREE);
+    // the Q residues of a row run on Q neighbouring CTAs at the same time (measured faster than back
+    // to back on one CTA: the spectrum row is fetched once and hit in L2 by the other three)
     for (int w = block; w < nwork; w += nblocks) {
         const int row = a.olo + w / Q, n1 = w % Q;
         const bool r1 = a.f1.p && row < a.f1.my, r2 = a.f2.p && row < a.f2.my;

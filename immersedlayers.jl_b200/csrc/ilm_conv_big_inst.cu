@@ -48,7 +48,7 @@ int ILM_CAT(conv_launch_big_Q, ILM_Q)(int which, const ConvArgs& a, int nsm, cud
         attr_done = true;
     }
     int nwork;
-    if (which == 0) nwork = (a.rhi - a.rlo) * ILM_Q;
+    if (which == 0) nwork = a.rhi - a.rlo;              // one row (all of its classes) per work item
     else if (which == 2) nwork = (a.ohi - a.olo) * ILM_Q;
     else {
         nwork = a.g.Lx;                                   // 2-column tiles

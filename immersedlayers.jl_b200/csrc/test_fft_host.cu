@@ -121,7 +121,7 @@ template <int L> struct Len {
     static constexpr int Q = big ? L / 4096 : 1;
     using Cfg = FftCfg<base>;
     static constexpr int cpw = big ? 2 : (Cfg::F == 1 ? 2 : Cfg::F);        // pass B / C work item width
-    static int rowsA(int nrows) { return big ? nrows * Q : (nrows + Cfg::F - 1) / Cfg::F; }
+    static int rowsA(int nrows) { return big ? nrows : (nrows + Cfg::F - 1) / Cfg::F; }
     static int rowsC(int nrows) { return big ? nrows * Q : (nrows + cpw - 1) / cpw; }
 };
 template <int L> static void runA(HostCtx& c, const ConvArgs& a, double2* sm, int b, int nb) {
