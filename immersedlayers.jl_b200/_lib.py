@@ -72,6 +72,7 @@ SIGNATURES = {
     "ilm_create_schur": (_i, [_vp, _i, _d, _i, _i, _dp]),
     "ilm_create_schur_kernel": (_i, [_vp, _i, _i, _d, _i, _i, _dp]),
     "ilm_create_RTLinvR_direct": (_i, [_vp, _d, _i, _i, _dp]),
+    "ilm_create_schur_direct_kernel": (_i, [_vp, _dp, _i, _d, _d, _d, _i, _i, _dp]),
     "ilm_create_nRTRn": (_i, [_vp, _d, _dp]),
     "ilm_create_surface_filter": (_i, [_vp, _dp]),
     "ilm_dense_factor": (_i, [_i, _dp, _ip, _vp]),

@@ -1143,3 +1143,34 @@ def create_RTHR(cache, kernel_id, scale=1.0, cols=None):
     buf = _matrix(cache, c1 - c0)
     L.check(cache._lib.ilm_create_schur_kernel(cache._plan, L.RTLINVR, int(kernel_id), float(scale), int(c0), int(c1), _ptr(buf)))
     return _as_matrix(buf, cache.N, c1 - c0)
+
+
+def create_RTHR_direct(cache, table, c0=0.0, factor=1.0, scale=1.0, cols=None):
+    """-scale/factor * E (T - c0) R from the kernel table T itself (no transform): the fast builder
+    of an IF-HERK stage complement for a compact table such as `lgf.intfact_table(a, 32)`; what makes
+    the per-step operator refresh of a moving body affordable."""
+    if _is_vector(cache):
+        raise MethodError("create_RTHR_direct: scalar caches only")
+    table = np.asfortranarray(table, dtype=np.float64)
+    if table.ndim != 2 or table.shape[0] != table.shape[1]:
+        raise DimensionMismatch("create_RTHR_direct: square kernel table expected")
+    c0_, c1_ = (0, cache.N) if cols is None else cols
+    buf = _matrix(cache, c1_ - c0_)
+    L.check(cache._lib.ilm_create_schur_direct_kernel(cache._plan, _ptr(table), table.shape[0], float(c0), float(factor),
+                                                      float(scale), int(c0_), int(c1_), _ptr(buf)))
+    return _as_matrix(buf, cache.N, c1_ - c0_)
+
+
+def convolve(w, cache, kernel_id):
+    """w <- K * w for a kernel registered with `cache.add_kernel`: `exp(L, a) * w` (plan_intfact, the
+    integrating factor of src/timemarching.jl:93,104) or `implicit_operator(L, a) \\ w`
+    (src/grid_operators.jl:182-184).  In place; Nodes, XEdges / YEdges or Edges."""
+    if isinstance(w, Edges):
+        layout = L.EDGES
+    elif isinstance(w, (Nodes, XEdges, YEdges)):
+        layout = w.layout
+    else:
+        raise MethodError(f"convolve: no method for {type(w).__name__}")
+    L.check(cache._lib.ilm_convolve(cache._plan, int(kernel_id), layout, _ptr(w.data)))
+    return w
+

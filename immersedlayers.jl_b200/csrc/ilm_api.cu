@@ -615,7 +615,25 @@ extern "C" int ilm_create_RTLinvR_direct(ilm_plan* p, double scale, int col_begi
     Io io(p);
     double* dA = io.out(A, (size_t)N * (col_end - col_begin));
     if (io.status) return io.status;
-    ILM_TRY(launch_schur_direct(p, p->lgf_dev, p->lgf_ld, scale, col_begin, col_end, dA));
+    ILM_TRY(launch_schur_direct(p, p->lgf_dev, p->lgf_ld, p->lgf_ld, p->c0, p->lap_factor, scale, col_begin, col_end, dA));
+    return io.finish();
+}
+
+// Direct-table form with an arbitrary kernel table: -scale/factor * E (T - c0) R, e.g. the Schur
+// complement S_i = -E exp(L a) R of an IF-HERK stage from the compact plan_intfact table.  This is
+// what makes a plan refresh per time step affordable for moving bodies.
+extern "C" int ilm_create_schur_direct_kernel(ilm_plan* p, const double* table, int n, double c0, double factor, double scale,
+                                              int col_begin, int col_end, double* A) {
+    ILM_CHECK_PLAN(p);
+    const int N = p->N;
+    if (!table || n < 1 || factor == 0.0) { set_error("ilm_create_schur_direct_kernel: bad table"); return ILM_EINVAL; }
+    if (col_begin < 0 || col_end > N || col_begin > col_end) { set_error("ilm_create_schur_direct_kernel: bad column range"); return ILM_ESIZE; }
+    if (N == 0 || col_end == col_begin) return ILM_OK;
+    Io io(p);
+    const double* dT = io.in(table, (size_t)n * n);
+    double* dA = io.out(A, (size_t)N * (col_end - col_begin));
+    if (io.status) return io.status;
+    ILM_TRY(launch_schur_direct(p, dT, n, n, c0, factor, scale, col_begin, col_end, dA));
     return io.finish();
 }
 

@@ -143,7 +143,9 @@ int launch_surface_filter(ilm_plan* p, const DevTable& t, double* C);
 int launch_probe_pre(ilm_plan* p, const DevTable& t, int col0, int ncol, double* g0, double* g1, int rlo, int rhi);
 int launch_probe_post(ilm_plan* p, const DevTable& t, int ncol, const double* g0, const double* g1, double coef, double* d0,
                       double* d1);
-int launch_schur_direct(ilm_plan* p, const double* G, int ldg, double scale, int col_begin, int col_end, double* A);
+// A[:, c] = -scale/factor * E (T - c0) R e_c with T an ng x ng table (leading dimension ldg), zero beyond ng
+int launch_schur_direct(ilm_plan* p, const double* G, int ldg, int ng, double c0, double factor, double scale, int col_begin,
+                        int col_end, double* A);
 // vector-cache pieces (TensorData = [dudx; dudy; dvdx; dvdy], EdgeGradient likewise)
 int launch_tensor_from_vector(ilm_plan* p, int mode, const double* v, double* T);
 int launch_tensor_dot(ilm_plan* p, int mode, const double* S, double div, double* out);

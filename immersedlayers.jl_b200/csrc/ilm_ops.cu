@@ -638,7 +638,7 @@ namespace ilm {
 __global__ void __launch_bounds__(256)
 k_schur_direct(int N, int W, int mx, const int* __restrict__ i0, const int* __restrict__ j0,
                const double* __restrict__ wE, const double* __restrict__ wR, const double* __restrict__ G, int ldg,
-               int my, double c0, double coef, int col_begin, double* __restrict__ A) {
+               int ng, int my, double c0, double coef, int col_begin, double* __restrict__ A) {
     const int l = col_begin + blockIdx.y;
     __shared__ double rw[16];
     __shared__ int ri[16], rj[16];
@@ -661,20 +661,22 @@ k_schur_direct(int N, int W, int mx, const int* __restrict__ i0, const int* __re
             double inner = 0.0;
             for (int q = 0; q < W2; ++q) {
                 const int di = abs(pi - ri[q]), dj = abs(pj - rj[q]);
-                inner += (G[(size_t)dj * ldg + di] - c0) * rw[q];
+                const double gv = (di < ng && dj < ng) ? G[(size_t)dj * ldg + di] : 0.0;     // compact tables: 0 beyond
+                inner += (gv - c0) * rw[q];
             }
             sum += wE[(size_t)k * W2 + b * W + a] * inner;
         }
     A[(size_t)blockIdx.y * N + k] = coef * sum;
 }
 
-int launch_schur_direct(ilm_plan* p, const double* G, int ldg, double scale, int col_begin, int col_end, double* A) {
+int launch_schur_direct(ilm_plan* p, const double* G, int ldg, int ng, double c0, double factor, double scale, int col_begin,
+                        int col_end, double* A) {
     const DevTable& t = p->tab[ILM_NODES_PRIMAL];
     const int N = p->N, ncols = col_end - col_begin;
     if (N == 0 || ncols == 0) return ILM_OK;
     dim3 grid((N + 255) / 256, ncols);
-    k_schur_direct<<<grid, 256, 0, p->stream>>>(N, t.W, t.mx, t.i0, t.j0, t.wE, t.wR, G, ldg, t.my, p->c0,
-                                                -scale / p->lap_factor, col_begin, A);
+    k_schur_direct<<<grid, 256, 0, p->stream>>>(N, t.W, t.mx, t.i0, t.j0, t.wE, t.wR, G, ldg, ng, t.my, c0, -scale / factor,
+                                                col_begin, A);
     ILM_LAUNCHED(p);
     return ILM_OK;
 }

@@ -147,6 +147,10 @@ int ilm_create_schur_kernel(ilm_plan* plan, int which, int kernel_id, double sca
  * transform, O(N^2 W^4) look-ups.  Cross-check of the column-solve path and an optional fast
  * builder; it is NOT what bench.py's grid-point*solves/s metric times.                      */
 int ilm_create_RTLinvR_direct(ilm_plan* plan, double scale, int col_begin, int col_end, double* A);
+/* same direct form for an arbitrary n x n kernel table T (column-major, zero beyond n):
+ * A = -scale/factor * E (T - c0) R, e.g. S_i = -E exp(L a) R of an IF-HERK stage from plan_intfact's table */
+int ilm_create_schur_direct_kernel(ilm_plan* plan, const double* table, int n, double c0, double factor, double scale,
+                                   int col_begin, int col_end, double* A);
 int ilm_create_nRTRn(ilm_plan* plan, double scale, double* A);   /* :225-244 */
 int ilm_create_surface_filter(ilm_plan* plan, double* C);        /* :254-268 */
 

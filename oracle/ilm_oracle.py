@@ -925,3 +925,58 @@ def dot_grid(grid, a, b, kind):
 
 def dot_surface(a, b, ds):
     return float(np.sum(a * b * ds))
+
+
+# --------------------------------------------------------------------------
+# IF-HERK step of the constrained heat equation (config C3)
+# --------------------------------------------------------------------------
+def heat_ifherk_step(cache, T, t, dt, kappa, tab_a, tab_c, tables, Tplus, Tminus):
+    """One step of the half-explicit Runge-Kutta scheme with integrating factor that the reference
+    reaches through ConstrainedSystems.jl's LiskaIFHERK (src/timemarching.jl:86-107,254-260;
+    problem functions of test/literate/heatconduction.jl:87-129):
+        dT/dt = kappa L T + D_s(-kappa [T]) - R sigma,   E T = (T+ + T-)/2.
+    `tables[a]` is the plan_intfact table for the argument a = kappa/dx^2 (c_i - c_{i-1}) dt (a = 0:
+    identity).  PARITY UNPINNED (un-vendored integrator): recursion as in timemarching.py."""
+    g = cache.grid
+    N = cache.N
+    tp = cache.tabs[PRIMAL]
+
+    def sval(f, tt):
+        return np.asarray(f(cache.x, cache.y, tt), dtype=float) if callable(f) else np.full(N, float(f))
+
+    def H(wf, a):
+        return wf if a == 0.0 else ConvPlan(tables[a][:g.NX, :g.NY]).apply(wf)
+
+    def rhs(tt):
+        return cache.surface_divergence(-kappa * (sval(Tplus, tt) - sval(Tminus, tt)))
+
+    Emat, Rmat = E_matrix(tp), R_matrix(tp)
+    q = T.copy()
+    w = []
+    c_prev = 0.0
+    U = None
+    sig = None
+    for i, c in enumerate(tab_c):
+        a = kappa / g.dx ** 2 * (c - c_prev) * dt
+        w = [H(wj, a) for wj in w]
+        q = H(q, a)
+        w.append(H(rhs(t + c_prev * dt), a))
+        U = q.copy()
+        for j in range(i + 1):
+            if tab_a[i][j] != 0.0:
+                U = U + (dt * tab_a[i][j]) * w[j]
+        # S_i = -E H_i R, column by column like create_RTLinvR (src/matrix_operators.jl:9-30)
+        S = np.zeros((N, N))
+        for col in range(N):
+            e = np.zeros(N)
+            e[col] = 1.0
+            S[:, col] = -interpolate(tp, H(regularize(tp, e), a))
+        b = 0.5 * (sval(Tplus, t + c * dt) + sval(Tminus, t + c * dt))
+        sig = np.linalg.solve(S, b - interpolate(tp, U))
+        corr = H(regularize(tp, sig), a)
+        U = U - corr
+        w[i] = w[i] - corr * (1.0 / (dt * tab_a[i][i]))
+        c_prev = c
+    del Emat, Rmat
+    return U, sig
+
