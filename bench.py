@@ -246,10 +246,14 @@ def main():
               for i, (k, b) in enumerate(bytes_pass.items())}
     conv_ms = sum(float(msp[i]) for i in range(3))
     # the launches the Schur build actually issues (4593 of the 4595 solves of a step): sparse-row probes.
-    # Pass B then reads no spectrum (the input rows are summed directly) -> Ghat in, S2 out.
+    # Pass B then reads no spectrum (the input rows are summed directly) -> Ghat in, S2 out
     msq = (L.C.c_double * 3)()
     L.check(cache._lib.ilm_profile_conv_probe(cache._plan, N // 3, 10, L.C.byref(msq)))
-    bytes_probe_B = spec + (Lx + 1) * 2 * Ly * 8
+    # ... and only for the rows under the interpolation windows (ilm_probe_output_rows)
+    r0, r1 = L.C.c_int(), L.C.c_int()
+    L.check(cache._lib.ilm_probe_output_rows(cache._plan, L.RTLINVR, L.C.byref(r0), L.C.byref(r1)))
+    rows_out = r1.value - r0.value
+    bytes_probe_B = 2 * Lx * rows_out * 16 + (Lx + 1) * 2 * Ly * 8
     achieved = bytes_probe_B / (float(msq[1]) * 1e-3) / 1e9
     # FP64 pipe: warp instructions per launch (ncu-verified static counts: inverse FFT 782/thread,
     # sparse forward ~300/thread) x 2 issue cycles / (148 SMs x 4 SMSPs x elapsed cycles at 1.965 GHz)
@@ -258,14 +262,15 @@ def main():
                 "kernel": f"ilm_passB_L{Ly} in Schur-probe mode (column pass: sparse forward DFT_y * Ghat * IFFT_y, 2 columns of S per launch)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu capture at 4096^2
-                # (profiles/r1_passB_probe_dram.txt); null for other grids
-                "traffic": 957.5e6 if args.grid == 4096 else None,
+                # (profiles/r1_passB_probe_dram_v6.txt: 286.6 MB read + 233.7 MB written); null for other grids
+                "traffic": 520.3e6 if args.grid == 4096 else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_probe_B,
                 "launch_ms": float(msq[1]),
                 "dense_equivalent_frac": bytes_pass["B_columns"] / (float(msq[1]) * 1e-3) / 1e9 / peak,
                 "fp64_pipe_frac_est": fp64_winst_B * 2 / (148 * 4 * float(msq[1]) * 1e-3 * 1.965e9),
                 "probe_passes_ms": {"A_rows_fwd": float(msq[0]), "B_columns": float(msq[1]), "C_rows_inv": float(msq[2])},
                 "probe_pair_ms": sum(float(msq[i]) for i in range(3)),
+                "probe_output_rows": [r0.value, r1.value],
                 "dense_passes": passes,
                 "dense_solve_pair_ms": conv_ms,
                 "dense_solve_frac_of_hbm": sum(bytes_pass.values()) / (conv_ms * 1e-3) / 1e9 / peak,

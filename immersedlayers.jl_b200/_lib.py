@@ -103,6 +103,7 @@ SIGNATURES = {
     "ilm_slab_inverse": (_i, [_vp, C.POINTER(ilm_slab_info), _dp, _i, _dp, _i, _dp]),
     "ilm_profile_conv": (_i, [_vp, _i, _i, C.POINTER(C.c_double * 3)]),
     "ilm_profile_conv_probe": (_i, [_vp, _i, _i, C.POINTER(C.c_double * 3)]),
+    "ilm_probe_output_rows": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
 }
 
 _lib = None

@@ -637,6 +637,20 @@ extern "C" int ilm_create_schur_direct_kernel(ilm_plan* p, const double* table, 
     return io.finish();
 }
 
+// rows of the probed field that the Schur builder `which` keeps through the inverse transforms
+extern "C" int ilm_probe_output_rows(ilm_plan* p, int which, int* row_begin, int* row_end) {
+    ILM_CHECK_PLAN(p);
+    if (which < ILM_RTLINVR || which > ILM_GLINVD_CROSS || !row_begin || !row_end) { set_error("ilm_probe_output_rows: bad arguments"); return ILM_EINVAL; }
+    int olo, ohi;
+    probe_output_rows(p, which, &olo, &ohi);
+    const LayoutInfo lg = layout_info(which == ILM_CLINVCT ? ILM_NODES_DUAL : ILM_NODES_PRIMAL, p->g.NX, p->g.NY);
+    const int MYp = (lg.my + 1) & ~1;
+    if (olo < 0) { olo = 0; ohi = MYp; }
+    *row_begin = olo & ~1;
+    *row_end = ohi > MYp ? MYp : ohi;
+    return ILM_OK;
+}
+
 // same as ilm_profile_conv but in Schur-probe mode: the input is R e_c (+ R e_{c+1}), so pass A only
 // transforms the patch rows and pass B uses the sparse forward transform (what the S build launches)
 extern "C" int ilm_profile_conv_probe(ilm_plan* p, int col, int reps, double ms[3]) {

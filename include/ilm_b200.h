@@ -259,6 +259,10 @@ int ilm_profile_conv(ilm_plan* plan, int layout, int reps, double ms[3]);
  * launches ilm_create_schur(ILM_RTLINVR) issues: pass A transforms only the patch rows, pass B uses the
  * sparse forward half transform.                                                                     */
 int ilm_profile_conv_probe(ilm_plan* plan, int col, int reps, double ms[3]);
+/* Row range [row_begin, row_end) of the probed grid field that ilm_create_schur(which) carries through
+ * the inverse transforms (the rows under the interpolation windows, widened by the stencil reach); the
+ * other rows are neither stored by the column pass nor inverted by the last row pass.             */
+int ilm_probe_output_rows(ilm_plan* plan, int which, int* row_begin, int* row_end);
 
 #ifdef __cplusplus
 }
