@@ -1174,3 +1174,61 @@ def convolve(w, cache, kernel_id):
     L.check(cache._lib.ilm_convolve(cache._plan, int(kernel_id), layout, _ptr(w.data)))
     return w
 
+
+def stokes_flow(cache, vplus, vminus=None, S=None, Ss=None):
+    """Stokes flow past a body with prescribed surface velocities, `solve(prob::StokesFlowProblem, sys)` of
+    test/literate/stokes.jl:98-166 on the B200 path (BASELINE config C5a: vector-data / Rf problems).
+    vplus, vminus: (2N,) exterior / interior surface velocities [u; v].  Returns (v, s, sigma, S, Ss):
+    velocity (Edges), streamfunction (Nodes{Dual}), traction (VectorData) and the two factored-once
+    matrices S = create_CL2invCT, Ss = create_CLinvCT_scalar (reusable for other boundary data).
+    The final traction filter `C^2 * sigma` (:163) is left to the caller (create_surface_filter)."""
+    _need_vector(cache, "stokes_flow")
+    N = cache.N
+    vplus = np.asarray(vplus, dtype=np.float64)
+    vminus = np.zeros(2 * N) if vminus is None else np.asarray(vminus, dtype=np.float64)
+    nx, ny = cache.normals()
+    dv_h = vplus - vminus                                       # prescribed_surface_jump!
+    dv = cache.zeros_surface().set(dv_h)
+    v = cache.zeros_grid()
+    sstar = cache.zeros_gridcurl()
+    surface_divergence_symm(v, dv, cache)                       # psi*: -L^-2 curl(D_s^symm dv)
+    curl(sstar, v, cache)
+    _iscale(sstar, -1.0)
+    inverse_laplacian(sstar, cache)
+    inverse_laplacian(sstar, cache)
+    dvn = cache.zeros_surfacescalar().set(nx * dv_h[:N] + ny * dv_h[N:])      # pointwise_dot!(dvn, nrm, dv)
+    phi = cache.zeros_griddiv()
+    regularize(phi, dvn, cache)
+    inverse_laplacian(phi, cache)
+    vphi = cache.zeros_grid()
+    grad(vphi, phi, cache)
+    vb = cache.zeros_surface()
+    interpolate(vb, vphi, cache)
+    vprime = cache.zeros_surface().set(0.5 * (vplus + vminus))  # prescribed_surface_average!
+    _isub(vprime, vb)
+    curl(v, sstar, cache)
+    interpolate(vb, v, cache)
+    _isub(vprime, vb)                                           # spurious slip
+    if S is None:
+        S = LU(create_CL2invCT(cache))
+    sigma = cache.zeros_surface()
+    _assign(sigma, S.solve(vprime.data))
+    s = cache.zeros_gridcurl()
+    surface_curl(s, sigma, cache)                               # correction streamfunction
+    _iscale(s, -1.0)
+    inverse_laplacian(s, cache)
+    inverse_laplacian(s, cache)
+    _iadd(s, sstar)
+    curl(v, s, cache)
+    _iadd(v, vphi)
+    ds = cache.zeros_surfacescalar()                            # streamfunction equivalent of the potential
+    surface_grad_cross(ds, phi, cache)
+    if Ss is None:
+        Ss = LU(create_CLinvCT_scalar(cache))
+    _assign(ds, Ss.solve(ds.data))
+    surface_curl_cross(sstar, ds, cache)
+    _iscale(sstar, -1.0)
+    inverse_laplacian(sstar, cache)
+    _iadd(s, sstar)
+    return v, s, sigma, S, Ss
+

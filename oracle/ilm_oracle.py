@@ -980,3 +980,33 @@ def heat_ifherk_step(cache, T, t, dt, kappa, tab_a, tab_c, tables, Tplus, Tminus
     del Emat, Rmat
     return U, sig
 
+
+def stokes_solve(cache, vplus, vminus=None):
+    """`solve(prob::StokesFlowProblem, sys)` of test/literate/stokes.jl:98-166 on a VectorCache (without the
+    final `C^2 * sigma` traction filter).  vplus / vminus: (2N,) [u; v].  Returns (vu, vv, s, sigma)."""
+    N = cache.N
+    vplus = np.asarray(vplus, float)
+    vminus = np.zeros(2 * N) if vminus is None else np.asarray(vminus, float)
+    dv = vplus - vminus
+    vu, vv = cache.surface_divergence_v(dv[:N], dv[N:], symm=True)
+    sstar = -1.0 * cache.curl_e2n(vu, vv)
+    sstar = cache.inverse_laplacian(cache.inverse_laplacian(sstar))
+    dvn = cache.nx * dv[:N] + cache.ny * dv[N:]
+    phi = cache.inverse_laplacian(cache.regularize(dvn))
+    pu, pv = cache.grad(phi)
+    eu, ev = cache.interpolate_edges(pu, pv)
+    vprime = 0.5 * (vplus + vminus) - np.concatenate([eu, ev])
+    cu, cv = cache.curl_n2e(sstar)
+    eu, ev = cache.interpolate_edges(cu, cv)
+    vprime = vprime - np.concatenate([eu, ev])
+    S = cache.create_CL2invCT()
+    sigma = np.linalg.solve(S, vprime)
+    s = -1.0 * cache.surface_curl_v2n(sigma[:N], sigma[N:])
+    s = cache.inverse_laplacian(cache.inverse_laplacian(s)) + sstar
+    cu, cv = cache.curl_n2e(s)
+    vu, vv = cu + pu, cv + pv
+    ds = cache.surface_grad_cross(phi)
+    ds = np.linalg.solve(cache.create_CLinvCT(), ds)
+    s = s + cache.inverse_laplacian(-1.0 * cache.surface_curl_cross_s2n(ds))
+    return vu, vv, s, sigma
+

@@ -216,3 +216,28 @@ def test_vector_mask_products(vc, complementary):
         assert relerr(got, ref) < RTOL
     with pytest.raises(ilm.MethodError):
         fn(ilm.XEdges(cache.g), cache)
+
+
+def test_stokes_flow_matches_oracle():
+    """test/literate/stokes.jl:98-166 (config C5a scaled down): rectangle translating at unit speed."""
+    g = ilm.PhysicalGrid.centered(128)
+    body = ilm.bodies.rectangle(0.5, 0.25, 1.4 * g.dx)
+    G = ilm.lgf.lgf_table(128)
+    cache = ilm.SurfaceVectorCache(body, g, lgf_table=G)
+    oc = o.VectorCache(o.Grid(g.NX, g.NY, g.dx, g.I0), *body[:5], G)
+    N = cache.N
+    vplus = np.concatenate([np.ones(N), np.zeros(N)])          # stokes.jl:186-191
+    v, s, sigma, S, Ss = ilm.stokes_flow(cache, vplus)
+    vu, vv, sr, sigr = o.stokes_solve(oc, vplus)
+    assert relerr(v.u, vu) < 1e-9 and relerr(v.v, vv) < 1e-9
+    assert relerr(s.array(), sr) < 1e-9
+    assert relerr(sigma.data, sigr) < 1e-5                      # solution of an ill-conditioned system
+    # the factorisations are reusable for other boundary data
+    vplus2 = np.concatenate([np.zeros(N), np.ones(N)])
+    v2 = ilm.stokes_flow(cache, vplus2, S=S, Ss=Ss)[0]
+    vu2, vv2, _, _ = o.stokes_solve(oc, vplus2)
+    assert relerr(v2.u, vu2) < 1e-9 and relerr(v2.v, vv2) < 1e-9
+    # the constraint: the velocity interpolated on the surface is the prescribed average (v+ + v-)/2
+    vb = cache.zeros_surface()
+    ilm.interpolate(vb, v, cache)
+    assert np.abs(vb.u - 0.5).max() < 1e-8 and np.abs(vb.v).max() < 1e-8
