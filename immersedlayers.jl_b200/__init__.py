@@ -9,7 +9,7 @@ from . import _lib, bodies, lgf  # noqa: F401
 from . import timemarching  # noqa: F401,E402
 from ._lib import DimensionMismatch, IlmError, MethodError  # noqa: F401
 from .api import (  # noqa: F401
-    EdgeGradient, SurfaceVectorCache, TensorData, create_CL2invCT, create_RTHR, create_RTHR_direct, convolve, stokes_flow, create_RTLinvR_direct, neumann_poisson, create_CLinvCT_scalar, create_GLinvD_symm,
+    EdgeGradient, SurfaceVectorCache, TensorData, create_CL2invCT, create_RTHR, create_RTHR_direct, convolve, stokes_flow, convective_derivative, w_cross_v, create_RTLinvR_direct, neumann_poisson, create_CLinvCT_scalar, create_GLinvD_symm,
     normal_dot_interpolate, normal_interpolate_symm, regularize_normal_dot, regularize_normal_symm,
     surface_divergence_symm, surface_grad_symm,
     XEdges, YEdges, Dual, Edges, GridScaling, IndexScaling, LU, Nodes, PhysicalGrid, Primal, ScalarData,

@@ -94,6 +94,9 @@ SIGNATURES = {
     "ilm_mask_product": (_i, [_vp, _i, _i, _i, _dp]),
     "ilm_create_schur_vector": (_i, [_vp, _i, _d, _i, _i, _dp]),
     "ilm_create_nRTRn_vector": (_i, [_vp, _d, _dp]),
+    "ilm_convective_derivative_scalar": (_i, [_vp, _dp, _dp, _dp]),
+    "ilm_convective_derivative_vector": (_i, [_vp, _dp, _dp, _dp]),
+    "ilm_w_cross_v": (_i, [_vp, _dp, _dp, _dp]),
     "ilm_dense_launch_count": (C.c_int64, []),
     "ilm_slab_partition": (_i, [_i, _i, _i, _i, _i, C.POINTER(ilm_slab_info)]),
     "ilm_slab_counts": (_i, [_i, _i, C.POINTER(ilm_slab_info), _i, _vp, _vp]),

@@ -1061,7 +1061,7 @@ def neumann_poisson(cache, vnplus, vnminus=None, S=None):
     vnminus = np.zeros(N) if vnminus is None else np.asarray(vnminus, dtype=np.float64)
     if S is None:
         S = create_CLinvCT(cache)
-    lu = LU(S)
+    lu = S if isinstance(S, LU) else LU(S)                  # an LU object is reused as is
     dvn = cache.zeros_surface().set(vnplus - vnminus)
     vn = 0.5 * (vnplus + vnminus)
     fstar = cache.zeros_grid()
@@ -1231,4 +1231,41 @@ def stokes_flow(cache, vplus, vminus=None, S=None, Ss=None):
     inverse_laplacian(sstar, cache)
     _iadd(s, sstar)
     return v, s, sigma, S, Ss
+
+
+def convective_derivative(out, v, *args):
+    """convective_derivative!(udp, v, p, cache) = v . grad p on Nodes{Primal} (src/grid_operators.jl:258-264);
+    convective_derivative!(vdu, v, u, cache) = (v . grad) u on Edges (:290-299);
+    convective_derivative!(udu, u, cache) = (u . grad) u (:308-316).  Divided by dx for GridScaling.
+    No ConvectiveDerivativeCache argument: the fused kernels need no temporaries."""
+    if len(args) == 1:
+        (cache,), q = args, v
+    elif len(args) == 2:
+        q, cache = args
+    else:
+        raise MethodError("convective_derivative: expected (out, v, cache) or (out, v, q, cache)")
+    _expect(v, Edges, "convective_derivative")
+    if isinstance(q, Nodes):
+        _expect_nodes(q, Primal, "convective_derivative")
+        _expect_nodes(out, Primal, "convective_derivative")
+        L.check(cache._lib.ilm_convective_derivative_scalar(cache._plan, _ptr(v.data), _ptr(q.data), _ptr(out.data)))
+        return out
+    _expect(q, Edges, "convective_derivative")
+    _expect(out, Edges, "convective_derivative")
+    if out is v or out is q:
+        raise MethodError("convective_derivative: the result must not alias an input")
+    L.check(cache._lib.ilm_convective_derivative_vector(cache._plan, _ptr(v.data), _ptr(q.data), _ptr(out.data)))
+    return out
+
+
+def w_cross_v(vw, w, v, cache):
+    """w_cross_v!(vw::Edges, w::Nodes{Dual}, v::Edges, cache) (src/grid_operators.jl:404-434): the
+    rotational form of the convective term; not scaled by the grid spacing."""
+    _expect(vw, Edges, "w_cross_v")
+    _expect_nodes(w, Dual, "w_cross_v")
+    _expect(v, Edges, "w_cross_v")
+    if vw is v:
+        raise MethodError("w_cross_v: the result must not alias the velocity")
+    L.check(cache._lib.ilm_w_cross_v(cache._plan, _ptr(w.data), _ptr(v.data), _ptr(vw.data)))
+    return vw
 

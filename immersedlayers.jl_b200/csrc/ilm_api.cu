@@ -376,6 +376,43 @@ extern "C" int ilm_laplacian(ilm_plan* p, int layout, const double* in, double* 
     return io.finish();
 }
 
+// ---------------------------------------------------------------- convective terms
+// convective_derivative!(udp, u, p, cache, extra) (src/grid_operators.jl:258-264,318-327): out = (u . grad p) / dx
+extern "C" int ilm_convective_derivative_scalar(ilm_plan* p, const double* vel_edges, const double* nodes_primal, double* out) {
+    ILM_CHECK_PLAN(p);
+    Io io(p);
+    const double* dv = io.in(vel_edges, n_layout(p, ILM_EDGES));
+    const double* dp = io.in(nodes_primal, n_layout(p, ILM_NODES_PRIMAL));
+    double* dout = io.out(out, n_layout(p, ILM_NODES_PRIMAL));
+    if (io.status) return io.status;
+    ILM_TRY(launch_convective_scalar(p, dv, dv + n_edges_u(p), dp, dout, deriv_div(p)));
+    return io.finish();
+}
+// convective_derivative!(vdu, v, u, cache, extra) / (udu, u, cache, extra) (:290-316,343-375): out = (v . grad) u / dx
+extern "C" int ilm_convective_derivative_vector(ilm_plan* p, const double* vel_edges, const double* u_edges, double* out_edges) {
+    ILM_CHECK_PLAN(p);
+    Io io(p);
+    const size_t ne = n_layout(p, ILM_EDGES), nu = n_edges_u(p);
+    const double* dc = io.in(vel_edges, ne);
+    const double* du = (u_edges == vel_edges) ? dc : io.in(u_edges, ne);
+    double* dout = io.out(out_edges, ne);
+    if (io.status) return io.status;
+    ILM_TRY(launch_convective_vector(p, dc, dc + nu, du, du + nu, dout, dout + nu, deriv_div(p)));
+    return io.finish();
+}
+// w_cross_v!(vw, w, v, cache, extra) (:404-434): no grid scaling
+extern "C" int ilm_w_cross_v(ilm_plan* p, const double* w_dual, const double* vel_edges, double* out_edges) {
+    ILM_CHECK_PLAN(p);
+    Io io(p);
+    const size_t ne = n_layout(p, ILM_EDGES), nu = n_edges_u(p);
+    const double* dw = io.in(w_dual, n_layout(p, ILM_NODES_DUAL));
+    const double* dv = io.in(vel_edges, ne);
+    double* dout = io.out(out_edges, ne);
+    if (io.status) return io.status;
+    ILM_TRY(launch_w_cross_v(p, dw, dv, dv + nu, dout, dout + nu));
+    return io.finish();
+}
+
 // ---------------------------------------------------------------- convolutions
 extern "C" int ilm_convolve(ilm_plan* p, int kernel_id, int layout, double* w) {
     ILM_CHECK_PLAN(p);

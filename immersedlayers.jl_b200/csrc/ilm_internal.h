@@ -137,6 +137,11 @@ int launch_scale_store_column(ilm_plan* p, const double* src, double* dst, int n
 int launch_scale(ilm_plan* p, double* w, size_t n, double scale);
 // w *= mean of the (complementary) mask m over the nearest entries of its layout (grid_interpolate!)
 int launch_mask_product(ilm_plan* p, double* w, int wlayout, const double* m, int mlayout, int complementary);
+// convective terms, one fused sweep each (src/grid_operators.jl:258-434)
+int launch_convective_scalar(ilm_plan* p, const double* u, const double* v, const double* pn, double* out, double div);
+int launch_w_cross_v(ilm_plan* p, const double* w, const double* u, const double* v, double* ou, double* ov);
+int launch_convective_vector(ilm_plan* p, const double* cu, const double* cv, const double* u, const double* v, double* ou,
+                             double* ov, double div);
 int launch_lgf_prep(ilm_plan* p, const double* table, int ld, int NX, int NY, double c0, double* h);
 int launch_filter_rowsum(ilm_plan* p, DevTable& t);
 int launch_surface_filter(ilm_plan* p, const DevTable& t, double* C);

@@ -783,3 +783,128 @@ int launch_mask_product(ilm_plan* p, double* w, int wlayout, const double* m, in
 }
 
 }  // namespace ilm
+
+// =====================================================================================
+// Convective terms (src/grid_operators.jl:258-434): v.grad(p), v.grad(u), w x v.  The reference
+// composes them from grad! / grid_interpolate! / product! / transpose! over three EdgeGradient-sized
+// temporaries (7-9 sweeps); here each is ONE sweep that evaluates the intermediates on the fly from
+// the (cached) neighbours, in the reference's operation order (no FMA contraction).  Intermediate
+// entries whose stencil leaves the source field are 0, as in the zero-filled temporaries upstream.
+// All indices 0-based; u: NX x (NY-1), v: (NX-1) x NY, primal: (NX-1) x (NY-1), dual: NX x NY.
+// =====================================================================================
+namespace ilm {
+
+struct GridDims { int NX, NY; };
+__device__ __forceinline__ double ld_u(const double* u, GridDims g, int a, int b) { return u[(size_t)b * g.NX + a]; }
+__device__ __forceinline__ double ld_v(const double* v, GridDims g, int a, int b) { return v[(size_t)b * (g.NX - 1) + a]; }
+__device__ __forceinline__ double ld_p(const double* p, GridDims g, int a, int b) { return p[(size_t)b * (g.NX - 1) + a]; }
+__device__ __forceinline__ double ld_d(const double* d, GridDims g, int a, int b) { return d[(size_t)b * g.NX + a]; }
+__device__ __forceinline__ double mean2(double x, double y) { return __dmul_rn(0.5, __dadd_rn(x, y)); }
+
+// ---- v . grad p on Nodes{Primal} (:318-327) ---------------------------------------------------
+__device__ __forceinline__ double cd_tu(const double* u, const double* p, GridDims g, int a, int b) {     // u * (grad p).u at x-edge (a,b)
+    if (a < 1 || a > g.NX - 2) return 0.0;
+    return __dmul_rn(ld_u(u, g, a, b), __dsub_rn(ld_p(p, g, a, b), ld_p(p, g, a - 1, b)));
+}
+__device__ __forceinline__ double cd_tv(const double* v, const double* p, GridDims g, int a, int b) {     // v * (grad p).v at y-edge (a,b)
+    if (b < 1 || b > g.NY - 2) return 0.0;
+    return __dmul_rn(ld_v(v, g, a, b), __dsub_rn(ld_p(p, g, a, b), ld_p(p, g, a, b - 1)));
+}
+__global__ void k_convective_scalar(GridDims g, const double* __restrict__ u, const double* __restrict__ v,
+                                    const double* __restrict__ p, double* __restrict__ out, double div) {
+    const int mx = g.NX - 1, my = g.NY - 1;
+    const size_t n = (size_t)mx * my, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+        const int i = (int)(idx % mx), j = (int)(idx / mx);
+        const double su = mean2(cd_tu(u, p, g, i, j), cd_tu(u, p, g, i + 1, j));
+        const double sv = mean2(cd_tv(v, p, g, i, j), cd_tv(v, p, g, i, j + 1));
+        out[idx] = __ddiv_rn(__dadd_rn(su, sv), div);
+    }
+}
+
+// ---- w x v on Edges (:419-434) ---------------------------------------------------------------
+__device__ __forceinline__ double wv_m1(const double* v, const double* w, GridDims g, int a, int b) {     // (-v at dual node) * w
+    if (a < 1 || a > g.NX - 2) return 0.0;
+    return __dmul_rn(__dmul_rn(-1.0, mean2(ld_v(v, g, a - 1, b), ld_v(v, g, a, b))), ld_d(w, g, a, b));
+}
+__device__ __forceinline__ double wv_m2(const double* u, const double* w, GridDims g, int a, int b) {     // (u at dual node) * w
+    if (b < 1 || b > g.NY - 2) return 0.0;
+    return __dmul_rn(mean2(ld_u(u, g, a, b - 1), ld_u(u, g, a, b)), ld_d(w, g, a, b));
+}
+__global__ void k_w_cross_v(GridDims g, const double* __restrict__ w, const double* __restrict__ u, const double* __restrict__ v,
+                            double* __restrict__ ou, double* __restrict__ ov) {
+    const size_t nu = (size_t)g.NX * (g.NY - 1), nv = (size_t)(g.NX - 1) * g.NY, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nu + nv; idx += stride) {
+        if (idx < nu) {
+            const int i = (int)(idx % g.NX), j = (int)(idx / g.NX);
+            ou[idx] = mean2(wv_m1(v, w, g, i, j), wv_m1(v, w, g, i, j + 1));
+        } else {
+            const size_t k = idx - nu;
+            const int i = (int)(k % (g.NX - 1)), j = (int)(k / (g.NX - 1));
+            ov[k] = mean2(wv_m2(u, w, g, i, j), wv_m2(u, w, g, i + 1, j));
+        }
+    }
+}
+
+// ---- c . grad (u, v) on Edges (:329-375): c = advecting velocity, (u, v) = advected field ------
+__device__ __forceinline__ double cv_p0(const double* cu, const double* u, GridDims g, int a, int b) {    // primal: cu@centre * dudx
+    return __dmul_rn(mean2(ld_u(cu, g, a, b), ld_u(cu, g, a + 1, b)), __dsub_rn(ld_u(u, g, a + 1, b), ld_u(u, g, a, b)));
+}
+__device__ __forceinline__ double cv_p3(const double* cv, const double* v, GridDims g, int a, int b) {    // primal: cv@centre * dvdy
+    return __dmul_rn(mean2(ld_v(cv, g, a, b), ld_v(cv, g, a, b + 1)), __dsub_rn(ld_v(v, g, a, b + 1), ld_v(v, g, a, b)));
+}
+__device__ __forceinline__ double cv_p1(const double* cv, const double* u, GridDims g, int a, int b) {    // dual: cv@node * dudy
+    if (a < 1 || a > g.NX - 2 || b < 1 || b > g.NY - 2) return 0.0;     // cv@node needs a in range, dudy needs both
+    return __dmul_rn(mean2(ld_v(cv, g, a - 1, b), ld_v(cv, g, a, b)), __dsub_rn(ld_u(u, g, a, b), ld_u(u, g, a, b - 1)));
+}
+__device__ __forceinline__ double cv_p2(const double* cu, const double* v, GridDims g, int a, int b) {    // dual: cu@node * dvdx
+    if (a < 1 || a > g.NX - 2 || b < 1 || b > g.NY - 2) return 0.0;
+    return __dmul_rn(mean2(ld_u(cu, g, a, b - 1), ld_u(cu, g, a, b)), __dsub_rn(ld_v(v, g, a, b), ld_v(v, g, a - 1, b)));
+}
+__global__ void k_convective_vector(GridDims g, const double* __restrict__ cu, const double* __restrict__ cv,
+                                    const double* __restrict__ u, const double* __restrict__ v, double* __restrict__ ou,
+                                    double* __restrict__ ov, double div) {
+    const size_t nu = (size_t)g.NX * (g.NY - 1), nv = (size_t)(g.NX - 1) * g.NY, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nu + nv; idx += stride) {
+        if (idx < nu) {
+            const int i = (int)(idx % g.NX), j = (int)(idx / g.NX);
+            const double s0 = (i >= 1 && i <= g.NX - 2) ? mean2(cv_p0(cu, u, g, i - 1, j), cv_p0(cu, u, g, i, j)) : 0.0;
+            const double s1 = mean2(cv_p1(cv, u, g, i, j), cv_p1(cv, u, g, i, j + 1));
+            ou[idx] = __ddiv_rn(__dadd_rn(s0, s1), div);
+        } else {
+            const size_t k = idx - nu;
+            const int i = (int)(k % (g.NX - 1)), j = (int)(k / (g.NX - 1));
+            const double s2 = mean2(cv_p2(cu, v, g, i, j), cv_p2(cu, v, g, i + 1, j));
+            const double s3 = (j >= 1 && j <= g.NY - 2) ? mean2(cv_p3(cv, v, g, i, j - 1), cv_p3(cv, v, g, i, j)) : 0.0;
+            ov[k] = __ddiv_rn(__dadd_rn(s2, s3), div);
+        }
+    }
+}
+
+static unsigned sweep_blocks(const ilm_plan* p, size_t n) {
+    size_t blocks = (n + 255) / 256;
+    const size_t cap = (size_t)p->nsm * 16;
+    return (unsigned)(blocks > cap ? cap : (blocks ? blocks : 1));
+}
+int launch_convective_scalar(ilm_plan* p, const double* u, const double* v, const double* pn, double* out, double div) {
+    const GridDims g{p->g.NX, p->g.NY};
+    k_convective_scalar<<<sweep_blocks(p, (size_t)(g.NX - 1) * (g.NY - 1)), 256, 0, p->stream>>>(g, u, v, pn, out, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+int launch_w_cross_v(ilm_plan* p, const double* w, const double* u, const double* v, double* ou, double* ov) {
+    const GridDims g{p->g.NX, p->g.NY};
+    k_w_cross_v<<<sweep_blocks(p, (size_t)g.NX * (g.NY - 1) + (size_t)(g.NX - 1) * g.NY), 256, 0, p->stream>>>(g, w, u, v, ou, ov);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+int launch_convective_vector(ilm_plan* p, const double* cu, const double* cv, const double* u, const double* v, double* ou,
+                             double* ov, double div) {
+    const GridDims g{p->g.NX, p->g.NY};
+    k_convective_vector<<<sweep_blocks(p, (size_t)g.NX * (g.NY - 1) + (size_t)(g.NX - 1) * g.NY), 256, 0, p->stream>>>(g, cu, cv, u, v, ou, ov, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+}  // namespace ilm
+

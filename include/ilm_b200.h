@@ -215,6 +215,18 @@ int ilm_create_nRTRn_vector(ilm_plan* plan, double scale, double* A);
 /* kernels launched by the three ilm_dense_* entry points since load (bench bookkeeping) */
 int64_t ilm_dense_launch_count(void);
 
+/* ---- convective terms (src/grid_operators.jl:258-434), each one fused sweep --------------------
+ * The reference composes grad! / grid_interpolate! / product! / transpose! over EdgeGradient-sized
+ * temporaries (ConvectiveDerivativeCache, RotConvectiveDerivativeCache); no extra cache is needed here.
+ * Results are divided by dx for GridScaling (_scale_derivative!), except w x v (:404-410).           */
+/* convective_derivative!(udp::Nodes{Primal}, u::Edges, p::Nodes{Primal}, ...) (:258-264, 318-327) */
+int ilm_convective_derivative_scalar(ilm_plan* plan, const double* vel_edges, const double* nodes_primal, double* out_nodes_primal);
+/* convective_derivative!(vdu::Edges, v::Edges, u::Edges, ...) (:290-299, 361-375); u_edges == vel_edges gives
+ * convective_derivative!(udu, u, ...) (:308-316, 343-359)                                            */
+int ilm_convective_derivative_vector(ilm_plan* plan, const double* vel_edges, const double* u_edges, double* out_edges);
+/* w_cross_v!(vw::Edges, w::Nodes{Dual}, v::Edges, ...) (:404-434) */
+int ilm_w_cross_v(ilm_plan* plan, const double* w_nodes_dual, const double* vel_edges, double* out_edges);
+
 /* ---- slab decomposition of one convolution over several GPUs ---------------------------------
  * Multi-GPU form of inverse_laplacian! (src/grid_operators.jl:153-179; the reference itself is
  * single-process) for ONE grid whose rows are spread over `nranks` GPUs, one process per GPU

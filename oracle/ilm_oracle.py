@@ -1010,3 +1010,38 @@ def stokes_solve(cache, vplus, vminus=None):
     s = s + cache.inverse_laplacian(-1.0 * cache.surface_curl_cross_s2n(ds))
     return vu, vv, s, sigma
 
+
+# --------------------------------------------------------------------------
+# convective terms (src/grid_operators.jl:258-434), composed exactly as the reference composes them
+# --------------------------------------------------------------------------
+def convective_derivative_scalar(grid, u, v, p, div=1.0):
+    """_unscaled_convective_derivative!(udp, u, p) (:318-327) then _scale_derivative!:
+    grad!(vt1, p); product!(vt3, u, vt1); grid_interpolate!(udp, vt3) (x- and y-edge parts summed)."""
+    gu, gv = grad_n2e(grid, p)
+    out = grid_interpolate(grid, u * gu, XEDGE, PRIMAL) + grid_interpolate(grid, v * gv, YEDGE, PRIMAL)
+    return out / div
+
+
+def w_cross_v(grid, w, u, v):
+    """_unscaled_w_cross_v! (:419-434)."""
+    t1 = -1.0 * grid_interpolate(grid, v, YEDGE, DUAL)
+    ou = grid_interpolate(grid, t1 * w, DUAL, XEDGE)
+    t1 = grid_interpolate(grid, u, XEDGE, DUAL)
+    ov = grid_interpolate(grid, t1 * w, DUAL, YEDGE)
+    return ou, ov
+
+
+def convective_derivative_vector(grid, cu, cv, u, v, div=1.0):
+    """_unscaled_convective_derivative!(vdu, v, u) (:361-375; (:343-359) when u is v): grid_interpolate!
+    of the advecting velocity to the EdgeGradient positions, transpose!, grad!(u), product!,
+    grid_interpolate! back to the edges (the two contributions of each component summed)."""
+    a0 = grid_interpolate(grid, cu, XEDGE, PRIMAL)      # vt1.dudx
+    a1 = grid_interpolate(grid, cu, XEDGE, DUAL)        # vt1.dudy
+    a2 = grid_interpolate(grid, cv, YEDGE, DUAL)        # vt1.dvdx
+    a3 = grid_interpolate(grid, cv, YEDGE, PRIMAL)      # vt1.dvdy
+    dudx, dudy, dvdx, dvdy = grad_e2t(grid, u, v)
+    p0, p1, p2, p3 = a0 * dudx, a2 * dudy, a1 * dvdx, a3 * dvdy      # transpose! swaps the off-diagonal slots
+    ou = grid_interpolate(grid, p0, PRIMAL, XEDGE) + grid_interpolate(grid, p1, DUAL, XEDGE)
+    ov = grid_interpolate(grid, p2, DUAL, YEDGE) + grid_interpolate(grid, p3, PRIMAL, YEDGE)
+    return ou / div, ov / div
+

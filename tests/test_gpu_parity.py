@@ -502,3 +502,77 @@ def test_implicit_diffusion_kernel(c1):
     ilm.laplacian(lap, u, cache)                       # scaled by L.factor = 1/dx^2
     back = u.array() - a_tab * g.dx ** 2 * lap.array()
     assert np.abs(back - w)[1:-1, 1:-1].max() < 1e-12 * np.abs(w).max()
+
+
+# ---------------------------------------------------------------- convective terms (src/grid_operators.jl:258-434)
+@pytest.mark.parametrize("case", ["c1", "odd"])
+@pytest.mark.parametrize("device", [False, True])
+def test_convective_terms(case, device, request):
+    """The fused sweeps against the oracle's composition of grad! / grid_interpolate! / product! / transpose!
+    (bit-exact: same operation order, no FMA contraction); smoke sequence of test/surface_ops.jl:258-285."""
+    cache0, oc = request.getfixturevalue(case)
+    g = cache0.g
+    cache = (ilm.SurfaceScalarCache((oc.x, oc.y, oc.nx, oc.ny, oc.ds), g, lgf_table=ilm.lgf.lgf_table(max(g.NX, g.NY)), device=True)
+             if device else cache0)
+    rng = np.random.default_rng(23)
+
+    def host(a):
+        return a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
+
+    def edges(u, v):
+        return ilm.Edges(g, device=device).set(np.concatenate([u.ravel(order="F"), v.ravel(order="F")]))
+
+    us, vs = g.layout_shape(L.XEDGES), g.layout_shape(L.YEDGES)
+    u, v = rng.standard_normal(us), rng.standard_normal(vs)
+    u2, v2 = rng.standard_normal(us), rng.standard_normal(vs)
+    p = rng.standard_normal(g.layout_shape(L.NODES_PRIMAL))
+    w = rng.standard_normal(g.layout_shape(L.NODES_DUAL))
+    q, q2 = edges(u, v), edges(u2, v2)
+    dx = g.dx
+    # v . grad p
+    out = ilm.Nodes(ilm.Primal, g, device=device)
+    ilm.convective_derivative(out, q, ilm.Nodes(ilm.Primal, g, device=device).set(p), cache)
+    assert np.array_equal(host(out.data).reshape(p.shape, order="F"), o.convective_derivative_scalar(oc.grid, u, v, p, dx))
+    # (v . grad) v and (v . grad) u
+    nu = us[0] * us[1]
+    for other, (ou_, ov_) in ((q, (u, v)), (q2, (u2, v2))):
+        res = ilm.Edges(g, device=device)
+        if other is q:
+            ilm.convective_derivative(res, q, cache)
+        else:
+            ilm.convective_derivative(res, q, other, cache)
+        ru, rv = o.convective_derivative_vector(oc.grid, u, v, ou_, ov_, dx)
+        r = host(res.data)
+        assert np.array_equal(r[:nu].reshape(us, order="F"), ru) and np.array_equal(r[nu:].reshape(vs, order="F"), rv)
+    # w x v
+    res = ilm.Edges(g, device=device)
+    ilm.w_cross_v(res, ilm.Nodes(ilm.Dual, g, device=device).set(w), q, cache)
+    ru, rv = o.w_cross_v(oc.grid, w, u, v)
+    r = host(res.data)
+    assert np.array_equal(r[:nu].reshape(us, order="F"), ru) and np.array_equal(r[nu:].reshape(vs, order="F"), rv)
+    with pytest.raises(ilm.MethodError):
+        ilm.convective_derivative(q, q, cache)
+
+
+def test_convective_terms_full_size():
+    """4096^2: (u . grad) u of a rigid rotation is the centripetal field -Omega^2 r, w x v likewise."""
+    g = ilm.PhysicalGrid.centered(4096)
+    cache = ilm.SurfaceScalarCache(ilm.bodies.circle(1.0, 1.4 * g.dx), g, device=True)
+    xu, yu = g.coordinates(L.XEDGES)
+    xv, yv = g.coordinates(L.YEDGES)
+    Om = 0.75
+    u = -Om * np.broadcast_to(yu[None, :], g.layout_shape(L.XEDGES))
+    v = Om * np.broadcast_to(xv[:, None], g.layout_shape(L.YEDGES))
+    q = ilm.Edges(g, device=True).set(np.concatenate([u.ravel(order="F"), v.ravel(order="F")]))
+    res = ilm.Edges(g, device=True)
+    ilm.convective_derivative(res, q, cache)
+    r = res.data.cpu().numpy()
+    nu = u.size
+    ru = r[:nu].reshape(u.shape, order="F")
+    rv = r[nu:].reshape(v.shape, order="F")
+    assert np.abs(ru[2:-2, 2:-2] + Om ** 2 * xu[2:-2, None]).max() < 1e-9
+    assert np.abs(rv[2:-2, 2:-2] + Om ** 2 * yv[None, 2:-2]).max() < 1e-9
+    w = ilm.Nodes(ilm.Dual, g, device=True).fill(2 * Om)              # vorticity of the rotation
+    ilm.w_cross_v(res, w, q, cache)
+    r = res.data.cpu().numpy()
+    assert np.abs(r[:nu].reshape(u.shape, order="F")[2:-2, 2:-2] + 2 * Om ** 2 * xu[2:-2, None]).max() < 1e-9

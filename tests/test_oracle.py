@@ -403,3 +403,34 @@ def test_grid_interpolate_is_exact_for_linear_fields():
             ref = 2.0 * xd[:, None] - 3.0 * yd[None, :] + 0.25
             got = o.grid_interpolate(g, m, src, dst)
             assert np.abs(got - ref)[2:-2, 2:-2].max() < 1e-13      # the outer ring may be left at 0
+
+
+def test_convective_terms_on_polynomial_fields():
+    """v . grad p, (v . grad) v and w x v of the oracle (src/grid_operators.jl:258-434 compositions) reproduce
+    the continuous operators on fields for which the second-order staggered scheme is exact."""
+    g = o.Grid(20, 16, 0.25, (5, 4))
+    xu, yu = g.coords(o.XEDGE)
+    xv, yv = g.coords(o.YEDGE)
+    xp, yp = g.coords(o.PRIMAL)
+    xd, yd = g.coords(o.DUAL)
+    # uniform velocity (a, b), linear p: v . grad p = a px + b py exactly
+    a, b, px, py = 0.7, -0.3, 2.0, 1.5
+    u = np.full(o.field_shape(o.XEDGE, g.NX, g.NY), a)
+    v = np.full(o.field_shape(o.YEDGE, g.NX, g.NY), b)
+    p = px * xp[:, None] + py * yp[None, :]
+    out = o.convective_derivative_scalar(g, u, v, p, div=g.dx)
+    assert np.abs(out[2:-2, 2:-2] - (a * px + b * py)).max() < 1e-12
+    # linear velocity field (u, v) = (x + 2y, 3x - y): (v . grad) v is linear, the scheme is exact
+    u = xu[:, None] + 2 * yu[None, :]
+    v = 3 * xv[:, None] - yv[None, :]
+    ou, ov = o.convective_derivative_vector(g, u, v, u, v, div=g.dx)
+    ru = (xu[:, None] + 2 * yu[None, :]) * 1.0 + (3 * xu[:, None] - yu[None, :]) * 2.0
+    rv = (xv[:, None] + 2 * yv[None, :]) * 3.0 + (3 * xv[:, None] - yv[None, :]) * (-1.0)
+    assert np.abs(ou[2:-2, 2:-2] - ru[2:-2, 2:-2]).max() < 1e-12
+    assert np.abs(ov[2:-2, 2:-2] - rv[2:-2, 2:-2]).max() < 1e-12
+    # w x v with uniform w: (w e_z) x (u, v) = (-w v, w u)
+    w = np.full(o.field_shape(o.DUAL, g.NX, g.NY), 1.3)
+    ou, ov = o.w_cross_v(g, w, u, v)
+    assert np.abs(ou[2:-2, 2:-2] - (-1.3 * (3 * xu[:, None] - yu[None, :]))[2:-2, 2:-2]).max() < 1e-12
+    assert np.abs(ov[2:-2, 2:-2] - (1.3 * (xv[:, None] + 2 * yv[None, :]))[2:-2, 2:-2]).max() < 1e-12
+    del xd, yd
