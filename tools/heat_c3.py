@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--grid", type=int, default=2048)
 ap.add_argument("--steps", type=int, default=1000)
 ap.add_argument("--probe", action="store_true", help="build the stage complements column by column (reference's way)")
+ap.add_argument("--breakdown", action="store_true", help="time the pieces of a step separately (20 repetitions each)")
 a = ap.parse_args()
 g = ilm.PhysicalGrid.centered(a.grid)
 dt = tm.timestep_fourier(g, 1.0, 1.0)
@@ -37,6 +38,35 @@ prob = tm.DirichletHeatConduction(g, body_at, kappa=1.0, fourier=1.0, Tplus=0.0,
 for _ in range(3):
     prob.step()
 torch.cuda.synchronize()
+if a.breakdown:
+    import time
+
+    def timed(fn, reps=20):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    c = prob.cache
+    a_half = max(prob.stage_a)
+    S = ilm.create_RTHR_direct(c, prob.table[a_half])
+    w = c.zeros_grid()
+    w.data.normal_()
+    sd = c.zeros_surface()
+    print(json.dumps({"breakdown_ms": {
+        "update_points (table rebuild)": timed(lambda: c.update_points(body_at(prob.t))),
+        "create_RTHR_direct (one stage complement)": timed(lambda: ilm.create_RTHR_direct(c, prob.table[a_half])),
+        "LU factorisation (N = %d)" % c.N: timed(lambda: ilm.LU(S)),
+        "intfact convolution (one field)": timed(lambda: ilm.convolve(w, c, prob.kernel_id[a_half])),
+        "ode_rhs (surface_divergence)": timed(lambda: prob.ode_rhs(0.0)),
+        "interpolate + regularize": timed(lambda: (ilm.interpolate(sd, w, c), ilm.regularize(w, sd, c))),
+        "whole step": timed(prob.step),
+    }, "per_step_counts": {"update_points": 1, "create_RTHR_direct": 2, "LU": 2, "intfact convolution": 7, "ode_rhs": 3,
+                           "interpolate + regularize": 3}}))
+    sys.exit(0)
 l0 = prob.cache.launch_count()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
