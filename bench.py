@@ -348,8 +348,10 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         P = (g.NX - 1) * (g.NY - 1) * 8
-        h2d = N * 8 + P + P + N * N * 8 + (N * N * 8 + N * 4 + N * 8) + N * 8 + P
-        d2h = P + P + N * N * 8 + N * 8 + (N * N * 8 + N * 4) + N * 8 + P + P
+        # per call: surface_divergence (N in, P out), L^-1 (P, P), create_RTLinvR (N^2 out), interpolate (P in, N out),
+        # LU (N^2 in; the factors stay on the device), solve (N, N), regularize (N in, P out), L^-1 (P, P)
+        h2d = N * 8 + P + P + N * N * 8 + N * 8 + N * 8 + P
+        d2h = P + P + N * N * 8 + N * 8 + N * 8 + P + P
         e2e = {"value": g.NX * g.NY * n_solves / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
                "max_abs_diff_vs_device_path": float(np.abs(fh.data - f.numpy()).max())}

@@ -15,6 +15,8 @@ raises `DimensionMismatch` (AssertionError / DimensionMismatch, test/tools.jl:35
 from __future__ import annotations
 
 import ctypes as C
+import sys
+import weakref
 
 import numpy as np
 
@@ -80,18 +82,49 @@ def _ptr(buf):
 _PIN_MIN = 1 << 16          # host buffers of at least this many doubles are page-locked
 
 
+_PIN_POOL = {}              # size (doubles) -> released page-locked buffers, reused instead of re-pinned
+_PIN_IDS = set()            # ids of the page-locked numpy buffers handed out by _host_zeros
+_PIN_POOL_MAX = 1 << 28     # at most this many doubles (2 GiB) parked in the pool
+_pin_pool_size = 0
+
+
 def _host_zeros(n):
     """Host buffer for host mode.  Large buffers are page-locked (through torch) so that the
-    library's H2D/D2H staging runs at DMA speed instead of through the driver's bounce buffer."""
+    library's H2D/D2H staging runs at DMA speed instead of through the driver's bounce buffer.
+    Page-locking 134 MB costs ~30 ms, so released buffers are parked in a pool (see _recycle)
+    and handed out again after a memset."""
+    global _pin_pool_size
     n = int(n)
     if n >= _PIN_MIN:
+        free = _PIN_POOL.get(n)
+        if free:
+            buf = free.pop()
+            _pin_pool_size -= n
+            buf.fill(0.0)
+            return buf
         try:
             import torch
             if torch.cuda.is_available():
-                return torch.zeros(n, dtype=torch.float64).pin_memory().numpy()
+                buf = torch.zeros(n, dtype=torch.float64).pin_memory().numpy()
+                _PIN_IDS.add(id(buf))
+                weakref.finalize(buf, _PIN_IDS.discard, id(buf))     # ids are reused after a free
+                return buf
         except Exception:
             pass
     return np.zeros(n, dtype=np.float64)
+
+
+def _recycle(buf, extra_refs=0):
+    """Park a page-locked buffer for reuse once nothing but the caller refers to it (numpy views keep
+    a reference to their base, so an outstanding view blocks the reuse)."""
+    global _pin_pool_size
+    if not isinstance(buf, np.ndarray) or id(buf) not in _PIN_IDS:
+        return
+    if sys.getrefcount(buf) > 2 + extra_refs or _pin_pool_size + buf.size > _PIN_POOL_MAX:
+        _PIN_IDS.discard(id(buf))
+        return
+    _PIN_POOL.setdefault(buf.size, []).append(buf)
+    _pin_pool_size += buf.size
 
 
 def _alloc(n, device):
@@ -107,6 +140,12 @@ class _Data:
 
     def __init__(self, data):
         self.data = data
+
+    def __del__(self):
+        try:
+            _recycle(self.data, extra_refs=1)          # self.data + the argument
+        except Exception:
+            pass
 
     def __len__(self):
         return int(self.data.shape[0]) if self.data.ndim == 1 else int(np.prod(self.data.shape))
@@ -547,7 +586,10 @@ def _matrix(cache, ncols):
 def _as_matrix(buf, N, ncols):
     if _is_torch(buf):
         return buf.view(ncols, N).t()          # column-major N x ncols view
-    return buf.reshape((N, ncols), order="F")
+    view = buf.reshape((N, ncols), order="F")
+    if id(buf) in _PIN_IDS:
+        weakref.finalize(view, _recycle, buf, 1)       # the finalizer's own reference to buf
+    return view
 
 
 def _schur(which, cache, scale, cols):
@@ -606,31 +648,40 @@ def _colmajor_buffer(A):
 
 
 class LU:
-    """lu(S): dense LU with partial pivoting on the GPU (LAPACK getrf semantics)."""
+    """lu(S): dense LU with partial pivoting on the GPU (LAPACK getrf semantics).  The factors stay on
+    the device also for a host matrix (one H2D of S; `solve` then moves only the right-hand side);
+    `.lu` / `.ipiv` give them back in the memory space of the input."""
 
     def __init__(self, A, stream=None):
+        import torch
         buf, n = _colmajor_buffer(A)
-        if _is_torch(buf):
-            import torch
-            self.lu = buf.clone()
-            self.ipiv = torch.zeros(n, dtype=torch.int32, device="cuda")
-        else:
-            self.lu = _host_zeros(buf.shape[0])
-            self.lu[...] = buf
-            self.ipiv = np.zeros(n, dtype=np.int32)
+        self._host = not _is_torch(buf)
+        self._lu = torch.from_numpy(np.ascontiguousarray(buf)).cuda() if self._host else buf.clone()
+        self._ipiv = torch.zeros(n, dtype=torch.int32, device="cuda")
         self.n = n
         self.stream = stream
-        L.check(L.load().ilm_dense_factor(n, _ptr(self.lu), _ptr(self.ipiv), C.c_void_p(stream or 0)))
+        L.check(L.load().ilm_dense_factor(n, _ptr(self._lu), _ptr(self._ipiv), C.c_void_p(stream or 0)))
+
+    @property
+    def lu(self):
+        return self._lu.cpu().numpy() if self._host else self._lu
+
+    @property
+    def ipiv(self):
+        return self._ipiv.cpu().numpy() if self._host else self._ipiv
 
     def solve(self, b):
         """S \\ b, in place on a copy; b is ScalarData or a flat buffer."""
+        import torch
         data = b.data if isinstance(b, _Data) else b
         if int(np.prod(data.shape)) != self.n:
             raise DimensionMismatch(f"solve: expected length {self.n}")
-        out = data.clone() if _is_torch(data) else np.array(data, dtype=np.float64, copy=True)
-        if _is_torch(out) != _is_torch(self.lu):
+        if _is_torch(data) == self._host:
             raise MethodError("solve: right-hand side and factorisation must live on the same side (host/device)")
-        L.check(L.load().ilm_dense_solve(self.n, _ptr(self.lu), _ptr(self.ipiv), 1, _ptr(out), C.c_void_p(self.stream or 0)))
+        out = torch.from_numpy(np.array(data, dtype=np.float64, copy=True)).cuda() if self._host else data.clone()
+        L.check(L.load().ilm_dense_solve(self.n, _ptr(self._lu), _ptr(self._ipiv), 1, _ptr(out), C.c_void_p(self.stream or 0)))
+        if self._host:
+            out = out.cpu().numpy()
         return ScalarData(self.n, data=out) if isinstance(b, _Data) else out
 
 
