@@ -148,3 +148,62 @@ class SlabLaplacian:
         self._exchange(1)
         L.check(lib.ilm_slab_inverse(plan, info, C.c_void_p(self.recv.data_ptr()), l1, p1, -1 if l2 is None else l2, p2))
         return w1 if w2 is None else (w1, w2)
+
+
+def slab_solve_virtual_ranks(cache, layouts, fields, P, kernel_id=0):
+    """The slab-decomposed solve for P *virtual* ranks on ONE GPU and one plan: the three CUDA stages
+    run rank after rank and the two all-to-alls are done by slicing the packed buffers exactly as
+    all_to_all_single would.  Exercises partition, counts, pack / unpack and the ranged column pass
+    without a multi-GPU box.  fields: full (mx, my) numpy arrays, one per layout; returns the solved
+    full arrays."""
+    import ctypes as C
+    import numpy as np
+    from . import _lib as L
+    import torch
+    g = cache.g
+    lib, plan = cache._lib, cache._plan
+    rows = max(g.layout_shape(l)[1] for l in layouts)
+    infos = [slab_info(g.NX, g.NY, rows, P, r) for r in range(P)]
+    counts = [[slab_counts(g.NX, g.NY, i, ph) for i in infos] for ph in (0, 1)]
+    dev = torch.device("cuda")
+    nbuf = max(int(lib.ilm_slab_buffer_doubles(C.byref(i))) for i in infos)
+    send = [torch.zeros(nbuf, dtype=torch.float64, device=dev) for _ in range(P)]
+    recv = [torch.zeros(nbuf, dtype=torch.float64, device=dev) for _ in range(P)]
+
+    def slab(arr, layout, info):
+        my = g.layout_shape(layout)[1]
+        r0, r1 = min(info.row0, my), min(info.row1, my)
+        return torch.from_numpy(np.ascontiguousarray(arr[:, r0:r1].T).reshape(-1)).to(dev)
+
+    mine = [[slab(f, l, i) for f, l in zip(fields, layouts)] for i in infos]
+    l1 = layouts[0]
+    l2 = layouts[1] if len(layouts) > 1 else -1
+
+    def ptr(t):
+        return C.c_void_p(t.data_ptr())
+
+    def all_to_all(phase):
+        for r in range(P):
+            off = 0
+            for src in range(P):
+                n = counts[phase][r][1][src]
+                soff = sum(counts[phase][src][0][:r])
+                assert counts[phase][src][0][r] == n
+                recv[r][off:off + n] = send[src][soff:soff + n]
+                off += n
+
+    for r, info in enumerate(infos):
+        w2 = ptr(mine[r][1]) if len(layouts) > 1 else None
+        L.check(lib.ilm_slab_forward(plan, C.byref(info), l1, ptr(mine[r][0]), l2, w2, ptr(send[r])))
+    all_to_all(0)
+    for r, info in enumerate(infos):
+        L.check(lib.ilm_slab_columns(plan, C.byref(info), kernel_id, ptr(recv[r]), ptr(send[r])))
+    all_to_all(1)
+    for r, info in enumerate(infos):
+        w2 = ptr(mine[r][1]) if len(layouts) > 1 else None
+        L.check(lib.ilm_slab_inverse(plan, C.byref(info), ptr(recv[r]), l1, ptr(mine[r][0]), l2, w2))
+    out = []
+    for k, l in enumerate(layouts):
+        mx = g.layout_shape(l)[0]
+        out.append(np.concatenate([mine[r][k].cpu().numpy().reshape(-1, mx) for r in range(P)], axis=0).T)
+    return out

@@ -17,3 +17,35 @@ for n in (48, 300):                     # L = 64 (F > 1 path) and L = 512 (TMA p
     vc = ilm.SurfaceVectorCache(body, g)
     B = ilm.create_GLinvD(vc, cols=(0, 4))
 print("done")
+
+# ---- features added later in round 1: mask products, convective terms, slab stages, big lengths, IF-HERK
+import ctypes as C  # noqa: E402
+from ilm_b200 import _lib as L, shard, timemarching as tm  # noqa: E402
+
+g = ilm.PhysicalGrid.centered(48)
+body = ilm.bodies.circle(1.0, 1.4 * g.dx)
+cache = ilm.SurfaceScalarCache(body, g)
+vc = ilm.SurfaceVectorCache(body, g)
+for w in (ilm.Nodes(ilm.Primal, g), ilm.Nodes(ilm.Dual, g), ilm.XEdges(g), ilm.YEdges(g), ilm.Edges(g)):
+    ilm.mask(w.fill(1.0), cache)
+    ilm.complementary_mask(w, cache)
+for w in (ilm.Edges(g), ilm.Nodes(ilm.Primal, g), ilm.Nodes(ilm.Dual, g), ilm.EdgeGradient(g)):
+    ilm.mask(w.fill(1.0), vc)
+q, r = ilm.Edges(g).fill(0.5), ilm.Edges(g)
+ilm.convective_derivative(r, q, cache)
+ilm.convective_derivative(ilm.Nodes(ilm.Primal, g), q, ilm.Nodes(ilm.Primal, g).fill(2.0), cache)
+ilm.w_cross_v(r, ilm.Nodes(ilm.Dual, g).fill(1.0), q, cache)
+v, s, sig, S, Ss = ilm.stokes_flow(vc, np.concatenate([np.ones(vc.N), np.zeros(vc.N)]))
+prob = tm.DirichletHeatConduction(g, lambda t: ilm.bodies.circle(0.7, 1.4 * g.dx, center=(-0.3 + 20 * t, 0.0)), moving=True, device=True)
+prob.run(2)
+prob = tm.DirichletHeatConduction(g, lambda t: body, direct_schur=False, device=False)
+prob.run(1)
+# slab stages for 3 virtual ranks on a device-resident plan (pack / unpack copies, ranged column pass)
+virtual_slab_solve = shard.slab_solve_virtual_ranks
+for NX, NY in ((48, 48), (40, 600), (4200, 24), (24, 4200)):          # the last two: half length 8192 (radix-2Q bodies)
+    gg = ilm.PhysicalGrid(NX, NY, 0.05, (NX // 2, NY // 2))
+    dc = ilm.SurfaceScalarCache(ilm.bodies.circle(0.4, 0.07), gg, lgf_table=ilm.lgf.lgf_table(max(NX, NY)), device=True)
+    wf = np.random.default_rng(0).standard_normal(gg.layout_shape(L.NODES_PRIMAL))
+    virtual_slab_solve(dc, [L.NODES_PRIMAL], [wf], 3)
+    ilm.create_RTLinvR(dc, cols=(0, 4))
+print("done (round-1 additions)")
