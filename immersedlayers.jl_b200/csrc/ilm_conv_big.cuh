@@ -41,42 +41,45 @@ template <int Q> ILM_HD double2 rotq(double2 z, int t) {
 }
 
 // ---------------------------------------------------------------- pass A (rows, forward)
-// work item = row (its Q classes k1 in sequence); group p computes the class c = p + 2 k1
+// work item = row; its 2Q classes c = px + 2 k1 are visited as Q steps (px, k1 pair): group g takes
+// k1 = 2 * pair + g, so that the two groups write the two 16-byte halves (m even / odd) of the same
+// 32-byte spectrum sectors at the same time and L2 merges them into full-sector DRAM writes.
 template <int Q, class Ctx>
 ILM_HD void passA_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, int nblocks) {
     using C = FftCfg<BIG_M>;
     constexpr int T = C::T;
     double2* tw = smem + C::TW_BASE;
     load_twiddles<BIG_M>(ctx, tw, a.twx);
-    const int j = ctx.tid, px = ctx.grp;
+    const int j = ctx.tid;
     double2* xb = smem + ctx.grp * C::GROUP_XBUF;
     const unsigned mask = 2u * (unsigned)a.g.Lx - 1u;
-    // work item = one row, its Q classes back to back on the same CTA: the row is re-read from L1/L2
-    // and the 16-byte halves of a spectrum sector (m even / odd = k1 even / odd) are written within
-    // microseconds of each other, so that L2 merges them into full-sector DRAM writes
-    const int nwork = (a.rhi - a.rlo) * Q;
-    for (int w = block * Q; w < nwork; w = ((w + 1) % Q) ? w + 1 : w + 1 + (nblocks - 1) * Q) {
-        const int row = a.rlo + w / Q, k1 = w % Q;
-        const unsigned cls = (unsigned)(px + 2 * k1);
+    const int nrows = a.rhi - a.rlo;
+    for (int w = block; w < nrows; w += nblocks) {
+        const int row = a.rlo + w;
         const bool r1 = a.f1.p && row < a.f1.my, r2 = a.f2.p && row < a.f2.my;
-        double2 v[16];
+#pragma unroll 1
+        for (int step = 0; step < Q; ++step) {
+            const int px = step / (Q / 2), k1 = 2 * (step % (Q / 2)) + ctx.grp;
+            const unsigned cls = (unsigned)(px + 2 * k1);
+            double2 v[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const int n2 = j + e * T;
-            double2 acc = cmk(0.0, 0.0);
+            for (int e = 0; e < 16; ++e) {
+                const int n2 = j + e * T;
+                double2 acc = cmk(0.0, 0.0);
 #pragma unroll
-            for (int n1 = 0; n1 < Q; ++n1) {
-                const int n = n2 + BIG_M * n1;
-                const double re = (r1 && n < a.f1.mx) ? a.f1.p[(size_t)row * a.f1.mx + n] : 0.0;
-                const double im = (r2 && n < a.f2.mx) ? a.f2.p[(size_t)row * a.f2.mx + n] : 0.0;
-                const double2 x = cmk(re, im);
-                acc = cadd(acc, cls ? cmul(x, a.wl2x[((unsigned)n * cls) & mask]) : x);
+                for (int n1 = 0; n1 < Q; ++n1) {
+                    const int n = n2 + BIG_M * n1;
+                    const double re = (r1 && n < a.f1.mx) ? a.f1.p[(size_t)row * a.f1.mx + n] : 0.0;
+                    const double im = (r2 && n < a.f2.mx) ? a.f2.p[(size_t)row * a.f2.mx + n] : 0.0;
+                    const double2 x = cmk(re, im);
+                    acc = cadd(acc, cls ? cmul(x, a.wl2x[((unsigned)n * cls) & mask]) : x);
+                }
+                v[e] = acc;
             }
-            v[e] = acc;
-        }
-        fft_regs<BIG_M, false>(v, ctx, xb, tw, j);
+            fft_regs<BIG_M, false>(v, ctx, xb, tw, j);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) a.S[s_index(a.g, px, k1 + Q * (j + e * T), row)] = v[e];
+            for (int e = 0; e < 16; ++e) a.S[s_index(a.g, px, k1 + Q * (j + e * T), row)] = v[e];
+        }
     }
 }
 
