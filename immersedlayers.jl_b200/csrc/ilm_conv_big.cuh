@@ -12,11 +12,10 @@
 //             U_{n1}[k2] = conj(w_2L^{n1 k2}) sum_{k1<Q} Z[k2 + 2M k1] exp(+2 pi i n1 k1 / Q)
 //             for the Q output residues n1; the two halves are combined exactly as in ilm_conv.cuh.
 //
-// In the column pass the radix-Q combination that prepares the inverse is thread-local: the 16
-// registers of a thread after the forward class c hold Z[c + 2Q (j + 256 e)], and e = e' + (16/Q) k1
-// are precisely the Q entries k2 + 2M k1 of one U.  The forward classes of a column therefore hand
-// their results to the inverse residues through a per-CTA scratch line in global memory (2L complex
-// per group, L2-resident), the only intermediate that exceeds shared memory.
+// The row passes (A, C) use exactly these two formulas.  The column pass (B) decimates in TIME on the
+// way in instead and spreads a column over a thread-block cluster of Q CTAs (see passB_big_body): the
+// hand-off between the forward sub-transforms and the inverse residues -- the only intermediate that
+// exceeds shared memory -- is one L2-resident line of 2L complex per cluster.
 //
 // Pass A re-reads a row Q times (real input, L2 hits); pass C reads each spectrum entry Q times
 // (once per output residue; the row stays in L2 between the residues of a work group).
@@ -84,101 +83,104 @@ ILM_HD void passA_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block
 }
 
 // ---------------------------------------------------------------- pass B / G (columns)
-// work item = one 2-column tile; group p owns the y-parity p of both the forward classes and the
-// inverse half transforms.  MODE 0: convolution (S -> S2); MODE 1: Ghat = Re(FFT_y(Re S)).
+// One thread-block CLUSTER of Q CTAs per 2-column tile (columns visited one after the other), so that
+// the live data of a column (input, hand-off line, output: ~1.5 MB at L = 16384) exists 148/Q times
+// instead of 148 times and stays L2-resident.  Decimation in time on the way in: CTA `rank` transforms
+// the sub-sequence x[rank + Q n2] (group p with the parity modulation w_2M^{n2 p}, exactly the half
+// transform of ilm_conv.cuh), which reads every spectrum entry once per parity:
+//     A_{n1,p}[kappa] = FFT_M( x[n1 + Q n2] w_2M^{n2 p} )[kappa]            -> hand-off line [p][n1][kappa]
+// After one cluster barrier CTA `rank` = n1' builds, for k2 = 2 kappa + p,
+//     Z[k2 + 2M k1]  = sum_{n1} w_2L^{n1 k2} e^{-2 pi i n1 k1 / Q} A_{n1,p}[kappa]
+//     U_{n1'}[k2]    = conj(w_2L^{n1' k2}) sum_{k1} Ghat[k2 + 2M k1] Z[k2 + 2M k1] e^{+2 pi i n1' k1 / Q}
+// (a Q x Q filter per frequency, thread-local) and inverts it with the usual even/odd pair of 4096-point
+// transforms: z[n1' + Q n2] = Y_0[n2] + conj(w_2M^{n2}) Y_1[n2].  A second cluster barrier frees the line.
+// MODE 0: convolution (S -> S2); MODE 1: Ghat[.., k2 + 2M rank] = Re Z (multiplier construction).
+template <int Q> ILM_HD void radixq_fwd(double2* t) {      // t[k1] <- sum_{n1} t[n1] e^{-2 pi i n1 k1 / Q}
+    if constexpr (Q == 2) {
+        const double2 a = t[0], b = t[1];
+        t[0] = cadd(a, b); t[1] = csub(a, b);
+    } else {
+        const double2 s02 = cadd(t[0], t[2]), d02 = csub(t[0], t[2]);
+        const double2 s13 = cadd(t[1], t[3]), d13 = cmi<false>(csub(t[1], t[3]));      // -i (t1 - t3)
+        t[0] = cadd(s02, s13); t[1] = cadd(d02, d13); t[2] = csub(s02, s13); t[3] = csub(d02, d13);
+    }
+}
+
 template <int Q, int MODE, class Ctx>
-ILM_HD void passB_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, int nblocks) {
+ILM_HD void passB_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int cluster, int nclusters) {
     using C = FftCfg<BIG_M>;
-    constexpr int T = C::T, EQ = 16 / Q;
+    constexpr int T = C::T;
     double2* tw = smem + C::TW_BASE;
     load_twiddles<BIG_M>(ctx, tw, a.twy);
-    const int j = ctx.tid, py = ctx.grp;
+    const int j = ctx.tid, py = ctx.grp, rank = ctx.cluster_rank();
     double2* xb = smem + ctx.grp * C::GROUP_XBUF;
     double2* comb = smem + 2 * C::GROUP_XBUF;
     const int Lb = a.g.Ly;                                        // = Q * BIG_M
     const unsigned mask = 2u * (unsigned)Lb - 1u;
-    double2* scr = a.scratch + ((size_t)block * 2 + ctx.grp) * (size_t)Lb;       // [n1][kappa]
-    const int ncols = 2 * a.g.Lx;
-    const int nwork = ncols / 2;
+    double2* scr = a.scratch + (size_t)cluster * 2 * (size_t)Lb + (size_t)py * Lb;      // this parity: [n1][kappa]
+    const int nwork = a.g.Lx;                                     // 2-column tiles
     const bool ranged = a.whi > 0;
     const int wbeg = ranged ? a.wlo : 0, wend = ranged ? (a.whi < nwork ? a.whi : nwork) : nwork;
     if (MODE == 0 && !py) ctx.arrive(BAR_FREE);
-    for (int w = wbeg + block; w < wend; w += nblocks) {
+    for (int w = wbeg + cluster; w < wend; w += nclusters) {
 #pragma unroll 1
         for (int sub = 0; sub < 2; ++sub) {
             const int c = 2 * w + sub;
             const int px = c / a.g.Lx, m = c % a.g.Lx;
             const size_t gbase = ((size_t)ghat_col(a.g, px, m) * 2 + py) * (size_t)Lb;
             double2 v[16];
-#pragma unroll 1
-            for (int k1 = 0; k1 < Q; ++k1) {
-                const unsigned cls = (unsigned)(py + 2 * k1);
+            // ---- forward: the decimated sub-sequence of this CTA
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int n2 = j + e * T;
-                    double2 acc = cmk(0.0, 0.0);
+            for (int e = 0; e < 16; ++e) {
+                const int n = rank + Q * (j + e * T);
+                double2 x = (n >= a.rlo && n < a.rhi) ? a.S[s_index(a.g, px, m, n)] : cmk(0.0, 0.0);
+                if (MODE == 1) x.y = 0.0;
+                v[e] = py ? cmul(x, mod_fwd<BIG_M>(tw, j, e)) : x;
+            }
+            fft_regs<BIG_M, false>(v, ctx, xb, tw, j);
 #pragma unroll
-                    for (int n1 = 0; n1 < Q; ++n1) {
-                        const int n = n2 + BIG_M * n1;
-                        if (n >= a.rlo && n < a.rhi) {
-                            double2 x = a.S[s_index(a.g, px, m, n)];
-                            if (MODE == 1) x.y = 0.0;
-                            acc = cadd(acc, cls ? cmul(x, a.wl2y[((unsigned)n * cls) & mask]) : x);
-                        }
-                    }
-                    v[e] = acc;
-                }
-                fft_regs<BIG_M, false>(v, ctx, xb, tw, j);
+            for (int e = 0; e < 16; ++e) scr[(size_t)rank * BIG_M + j + e * T] = v[e];
+            ctx.cluster_sync();                               // all Q sub-spectra of this column are in the line
+            // ---- Q x Q filter per frequency, then the inverse half transform of residue `rank`
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int kappa = j + e * T;
+                const unsigned k2 = 2u * (unsigned)kappa + (unsigned)py;
+                double2 t[Q];
+                t[0] = scr[kappa];
+#pragma unroll
+                for (int n1 = 1; n1 < Q; ++n1) t[n1] = cmul(scr[(size_t)n1 * BIG_M + kappa], a.wl2y[((unsigned)n1 * k2) & mask]);
+                radixq_fwd<Q>(t);                             // t[k1] = Z[k2 + 2M k1]
                 if constexpr (MODE == 1) {
-                    if (ghat_is_rep(a.g, px, m)) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) a.GhatOut[gbase + k1 + Q * (j + e * T)] = v[e].x * a.gscale;
-                    }
+                    if (ghat_is_rep(a.g, px, m)) a.GhatOut[gbase + kappa + (size_t)BIG_M * rank] = t[rank].x * a.gscale;
                 } else {
+                    double2 s = cmk(0.0, 0.0);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const double gh = a.Ghat[gbase + k1 + Q * (j + e * T)];
-                        v[e] = cmk(v[e].x * gh, v[e].y * gh);
+                    for (int k1 = 0; k1 < Q; ++k1) {
+                        const double gh = a.Ghat[gbase + kappa + (size_t)BIG_M * k1];
+                        s = cadd(s, rotq<Q>(cmk(t[k1].x * gh, t[k1].y * gh), rank * k1));
                     }
-                    // thread-local radix-Q step towards the inverse: registers e' + EQ k1' hold Z[k2 + 2M k1']
-#pragma unroll
-                    for (int ep = 0; ep < EQ; ++ep) {
-                        const int t = j + ep * T;                                  // < M / Q
-                        const unsigned k2 = cls + 2u * Q * (unsigned)t;            // < 2M
-                        const int kappa = k1 + Q * t;
-#pragma unroll
-                        for (int n1 = 0; n1 < Q; ++n1) {
-                            double2 s = v[ep];
-#pragma unroll
-                            for (int q = 1; q < Q; ++q) s = cadd(s, rotq<Q>(v[ep + EQ * q], n1 * q));
-                            scr[(size_t)n1 * BIG_M + kappa] = n1 ? cmulc(s, a.wl2y[((unsigned)n1 * k2) & mask]) : s;
-                        }
-                    }
+                    v[e] = rank ? cmulc(s, a.wl2y[((unsigned)rank * k2) & mask]) : s;
                 }
             }
             if constexpr (MODE == 0) {
-                ctx.sync();                                   // this group's scratch line is complete
-#pragma unroll 1
-                for (int n1 = 0; n1 < Q; ++n1) {
+                fft_regs<BIG_M, true>(v, ctx, xb, tw, j);
+                if (py) {
+                    ctx.wait(BAR_FREE);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = scr[(size_t)n1 * BIG_M + j + e * T];
-                    fft_regs<BIG_M, true>(v, ctx, xb, tw, j);
-                    if (py) {
-                        ctx.wait(BAR_FREE);
+                    for (int e = 0; e < 16; ++e) comb[j + e * T] = cmulc(v[e], mod_fwd<BIG_M>(tw, j, e));
+                    ctx.arrive(BAR_READY);
+                } else {
+                    ctx.wait(BAR_READY);
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) comb[j + e * T] = cmulc(v[e], mod_fwd<BIG_M>(tw, j, e));
-                        ctx.arrive(BAR_READY);
-                    } else {
-                        ctx.wait(BAR_READY);
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const int n = n1 + Q * (j + e * T);
-                            if (n >= a.olo && n < a.ohi) a.S2[s_index(a.g, px, m, n)] = cadd(v[e], comb[j + e * T]);
-                        }
-                        ctx.arrive(BAR_FREE);
+                    for (int e = 0; e < 16; ++e) {
+                        const int n = rank + Q * (j + e * T);
+                        if (n >= a.olo && n < a.ohi) a.S2[s_index(a.g, px, m, n)] = cadd(v[e], comb[j + e * T]);
                     }
+                    ctx.arrive(BAR_FREE);
                 }
             }
+            ctx.cluster_sync();                               // the line may be overwritten by the next column
         }
     }
 }

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(512, 1) ILM_CAT(ilm_passA_big_Q, ILM_Q)(ConvAr
 __global__ void __launch_bounds__(512, 1) ILM_CAT(ilm_passB_big_Q, ILM_Q)(ConvArgs a) {
     extern __shared__ double2 smem[];
     DevCtx c{(int)(threadIdx.x & 255), (int)(threadIdx.x >> 8), nullptr};
-    passB_big_body<ILM_Q, 0>(c, a, smem, blockIdx.x, gridDim.x);
+    passB_big_body<ILM_Q, 0>(c, a, smem, blockIdx.x / ILM_Q, gridDim.x / ILM_Q);
 }
 __global__ void __launch_bounds__(512, 1) ILM_CAT(ilm_passC_big_Q, ILM_Q)(ConvArgs a) {
     extern __shared__ double2 smem[];
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(512, 1) ILM_CAT(ilm_passC_big_Q, ILM_Q)(ConvAr
 __global__ void __launch_bounds__(512, 1) ILM_CAT(ilm_passG_big_Q, ILM_Q)(ConvArgs a) {
     extern __shared__ double2 smem[];
     DevCtx c{(int)(threadIdx.x & 255), (int)(threadIdx.x >> 8), nullptr};
-    passB_big_body<ILM_Q, 1>(c, a, smem, blockIdx.x, gridDim.x);
+    passB_big_body<ILM_Q, 1>(c, a, smem, blockIdx.x / ILM_Q, gridDim.x / ILM_Q);
 }
 
 int ILM_CAT(conv_launch_big_Q, ILM_Q)(int which, const ConvArgs& a, int nsm, cudaStream_t st, const void*) {
@@ -47,21 +47,35 @@ int ILM_CAT(conv_launch_big_Q, ILM_Q)(int which, const ConvArgs& a, int nsm, cud
         ILM_CUDA(cudaFuncSetAttribute(ILM_CAT(ilm_passG_big_Q, ILM_Q), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         attr_done = true;
     }
-    int nwork;
-    if (which == 0) nwork = a.rhi - a.rlo;              // one row (all of its classes) per work item
-    else if (which == 2) nwork = (a.ohi - a.olo) * ILM_Q;
-    else {
-        nwork = a.g.Lx;                                   // 2-column tiles
-        if (a.whi > 0) nwork = (a.whi < nwork ? a.whi : nwork) - a.wlo;
+    if (which == 0 || which == 2) {
+        const int nwork = which == 0 ? a.rhi - a.rlo : (a.ohi - a.olo) * ILM_Q;
+        int grid = nwork < nsm ? nwork : nsm;
+        if (grid < 1) grid = 1;
+        if (which == 0) ILM_CAT(ilm_passA_big_Q, ILM_Q)<<<grid, 512, C::SMEM_BYTES, st>>>(a);
+        else ILM_CAT(ilm_passC_big_Q, ILM_Q)<<<grid, 512, C::SMEM_BYTES, st>>>(a);
+    } else {
+        // column pass: one cluster of ILM_Q CTAs per 2-column tile, as many clusters as fit the device
         if (!a.scratch) { set_error("big column pass without a scratch buffer"); return ILM_EINVAL; }
-    }
-    int grid = nwork < nsm ? nwork : nsm;
-    if (grid < 1) grid = 1;
-    switch (which) {
-    case 0: ILM_CAT(ilm_passA_big_Q, ILM_Q)<<<grid, 512, C::SMEM_BYTES, st>>>(a); break;
-    case 1: ILM_CAT(ilm_passB_big_Q, ILM_Q)<<<grid, 512, C::SMEM_BYTES, st>>>(a); break;
-    case 2: ILM_CAT(ilm_passC_big_Q, ILM_Q)<<<grid, 512, C::SMEM_BYTES, st>>>(a); break;
-    default: ILM_CAT(ilm_passG_big_Q, ILM_Q)<<<grid, 512, C::SMEM_BYTES, st>>>(a); break;
+        int ntiles = a.g.Lx;
+        if (a.whi > 0) ntiles = (a.whi < ntiles ? a.whi : ntiles) - a.wlo;
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ILM_Q; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        static int max_clusters[64] = {};
+        if (!max_clusters[dev & 63]) {
+            cfg.gridDim = dim3((nsm / ILM_Q) * ILM_Q);
+            int n = 0;
+            ILM_CUDA(cudaOccupancyMaxActiveClusters(&n, ILM_CAT(ilm_passB_big_Q, ILM_Q), &cfg));
+            max_clusters[dev & 63] = n > 0 ? (n < nsm / ILM_Q ? n : nsm / ILM_Q) : 1;
+        }
+        int nclusters = ntiles < max_clusters[dev & 63] ? ntiles : max_clusters[dev & 63];
+        if (nclusters < 1) nclusters = 1;
+        cfg.gridDim = dim3(nclusters * ILM_Q);
+        if (which == 1) ILM_CUDA(cudaLaunchKernelEx(&cfg, ILM_CAT(ilm_passB_big_Q, ILM_Q), a));
+        else ILM_CUDA(cudaLaunchKernelEx(&cfg, ILM_CAT(ilm_passG_big_Q, ILM_Q), a));
     }
     ILM_CUDA(cudaGetLastError());
     return ILM_OK;

@@ -32,6 +32,23 @@ struct DevCtx {
         asm volatile("bar.sync %0, 512;" ::"r"(id) : "memory");
 #endif
     }
+    // thread-block cluster (big column pass): rank of this CTA and a barrier over the whole cluster that
+    // also orders the global-memory hand-off line (release / acquire at cluster scope)
+    ILM_HD int cluster_rank() {
+#ifdef __CUDA_ARCH__
+        unsigned r;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+        return (int)r;
+#else
+        return 0;
+#endif
+    }
+    ILM_HD void cluster_sync() {
+#ifdef __CUDA_ARCH__
+        __threadfence();
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
+    }
     ILM_HD void delay(int ns) {
 #ifdef __CUDA_ARCH__
         if (ns > 0) __nanosleep((unsigned)ns);

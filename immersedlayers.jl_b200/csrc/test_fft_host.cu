@@ -7,6 +7,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <mutex>
 #include <random>
 #include <thread>
@@ -33,6 +34,9 @@ struct Barrier {
 
 struct HostCtx {
     int tid, grp; Barrier* gb; Barrier* cb; Barrier* named;   // named[id] for id = BAR_READY, BAR_FREE
+    int crank = 0; Barrier* clb = nullptr;                    // thread-block cluster: rank and cluster barrier
+    int cluster_rank() const { return crank; }
+    void cluster_sync() { if (clb) clb->wait(); }
     void sync() { gb->wait(); }
     void sync_cta() { cb->wait(); }
     void arrive(int id) { named[id].arrive(); }
@@ -68,6 +72,26 @@ template <class Body> static void run_cta(size_t smem_bytes, Body body) {
             HostCtx c{t & 255, t >> 8, (t >> 8) ? &g1 : &g0, &cb, named};
             body(c, smem.data());
         });
+    for (auto& x : th) x.join();
+}
+
+// a thread-block cluster of Q emulated CTAs (Q x 512 threads, one shared-memory image each)
+template <class Body> static void run_cluster(int Q, size_t smem_bytes, Body body) {
+    struct Cta {
+        std::vector<double2> smem; Barrier g0{256}, g1{256}, cb{512};
+        Barrier named[5] = {Barrier(512), Barrier(512), Barrier(512), Barrier(512), Barrier(512)};
+    };
+    std::vector<std::unique_ptr<Cta>> ctas;
+    for (int q = 0; q < Q; ++q) { ctas.emplace_back(new Cta); ctas.back()->smem.resize(smem_bytes / sizeof(double2) + 1); }
+    Barrier clb(Q * 512);
+    std::vector<std::thread> th;
+    for (int q = 0; q < Q; ++q)
+        for (int t = 0; t < 512; ++t)
+            th.emplace_back([&, q, t] {
+                Cta& c = *ctas[q];
+                HostCtx h{t & 255, t >> 8, (t >> 8) ? &c.g1 : &c.g0, &c.cb, c.named, q, &clb};
+                body(h, c.smem.data());
+            });
     for (auto& x : th) x.join();
 }
 
@@ -130,6 +154,12 @@ template <int L> static void runA(HostCtx& c, const ConvArgs& a, double2* sm, in
 template <int L, int MODE> static void runB(HostCtx& c, const ConvArgs& a, double2* sm, int b, int nb) {
     if constexpr (Len<L>::big) passB_big_body<Len<L>::Q, MODE>(c, a, sm, b, nb); else passB_body<L, MODE>(c, a, sm, b, nb);
 }
+// column pass of one emulated CTA (direct lengths) or one emulated cluster (big lengths)
+template <int L, int MODE> static void launchB(const ConvArgs& a, int b, int nb) {
+    using CY = typename Len<L>::Cfg;
+    if constexpr (Len<L>::big) run_cluster(Len<L>::Q, CY::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runB<L, MODE>(c, a, sm, b, nb); });
+    else run_cta(CY::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runB<L, MODE>(c, a, sm, b, nb); });
+}
 template <int L> static void runC(HostCtx& c, const ConvArgs& a, double2* sm, int b, int nb) {
     if constexpr (Len<L>::big) passC_big_body<Len<L>::Q>(c, a, sm, b, nb); else passC_body<L>(c, a, sm, b, nb);
 }
@@ -174,7 +204,7 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
         nwork = (2 * gg.Lx + Len<LY>::cpw - 1) / Len<LY>::cpw;
         nb = nwork > 3 ? 3 : nwork;
         for (int b = 0; b < nb; ++b)
-            run_cta(CY::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runB<LY, 1>(c, a, sm, b, nb); });
+            launchB<LY, 1>(a, b, nb);
     }
     // ---- fields
     std::mt19937_64 rng(NX * 131 + NY);
@@ -211,7 +241,7 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
         int nworkB = (2 * g2.Lx + Len<LY>::cpw - 1) / Len<LY>::cpw;
         int nbB = nworkB > 3 ? 3 : nworkB;
         for (int b = 0; b < nbB; ++b)
-            run_cta(CY::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runB<LY, 0>(c, a, sm, b, nbB); });
+            launchB<LY, 0>(a, b, nbB);
         for (int b = 0; b < nb; ++b)
             run_cta(CX::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runC<LX>(c, a, sm, b, nb); });
     }
