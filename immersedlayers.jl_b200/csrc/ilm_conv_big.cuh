@@ -129,6 +129,17 @@ ILM_HD void passB_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int clust
             const int px = c / a.g.Lx, m = c % a.g.Lx;
             const size_t gbase = ((size_t)ghat_col(a.g, px, m) * 2 + py) * (size_t)Lb;
             double2 v[16];
+            // L2 prefetch, one cluster-wide share per CTA: the multiplier slice of this column (read after the
+            // forward transform) and, once per tile, the spectrum of the next tile of this cluster
+            if (MODE == 0) {
+                const char* gp = reinterpret_cast<const char*>(a.Ghat + gbase) + (size_t)rank * BIG_M * sizeof(double);
+                for (size_t off = (size_t)j * 128; off < BIG_M * sizeof(double); off += 256 * 128) ctx.prefetch_l2(gp + off);
+            }
+            if (sub == 0 && w + nclusters < wend && a.rhi - a.rlo == a.g.MYp) {
+                const size_t share = (size_t)2 * a.g.MYp * sizeof(double2) / Q;
+                const char* sp = reinterpret_cast<const char*>(a.S + (size_t)(w + nclusters) * 2 * a.g.MYp) + (size_t)rank * share;
+                for (size_t off = (size_t)(ctx.grp * 256 + j) * 128; off < share; off += 512 * 128) ctx.prefetch_l2(sp + off);
+            }
             // ---- forward: the decimated sub-sequence of this CTA
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
