@@ -95,6 +95,16 @@ ILM_HD void passA_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block
 // (a Q x Q filter per frequency, thread-local) and inverts it with the usual even/odd pair of 4096-point
 // transforms: z[n1' + Q n2] = Y_0[n2] + conj(w_2M^{n2}) Y_1[n2].  A second cluster barrier frees the line.
 // MODE 0: convolution (S -> S2); MODE 1: Ghat[.., k2 + 2M rank] = Re Z (multiplier construction).
+// w_2L^{2 T e} with L = Q * 4096, T = 256: exp(-2 pi i e / (16 Q)), e = 0..15 (a 32nd / 64th root of unity)
+template <int Q> ILM_HD double2 wstep(int e) {
+    if constexpr (Q == 2) return w32(e);
+    else {
+        // exp(-2 pi i e / 64) = w32(e / 2) * (e odd ? exp(-2 pi i / 64) : 1)
+        const double2 h = w32(e >> 1);
+        return (e & 1) ? cmul(h, cmk(0.99518472667219688624, -0.09801714032956060199)) : h;
+    }
+}
+
 template <int Q> ILM_HD void radixq_fwd(double2* t) {      // t[k1] <- sum_{n1} t[n1] e^{-2 pi i n1 k1 / Q}
     if constexpr (Q == 2) {
         const double2 a = t[0], b = t[1];
@@ -153,14 +163,19 @@ ILM_HD void passB_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int clust
             for (int e = 0; e < 16; ++e) scr[(size_t)rank * BIG_M + j + e * T] = v[e];
             ctx.cluster_sync();                               // all Q sub-spectra of this column are in the line
             // ---- Q x Q filter per frequency, then the inverse half transform of residue `rank`
+            // twiddles w_2L^{n1 k2}, k2 = 2 (j + e T) + p: one table entry per thread (e = 0), the step
+            // w_2L^{2T} = w_{L/T}... is a compile-time root of unity, the powers n1 = 2, 3 by products
+            const double2 wbase = a.wl2y[(2u * (unsigned)j + (unsigned)py) & mask];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
                 const int kappa = j + e * T;
-                const unsigned k2 = 2u * (unsigned)kappa + (unsigned)py;
+                double2 wp[Q];                                // wp[n1] = w_2L^{n1 k2}
+                wp[1] = e ? cmul(wbase, wstep<Q>(e)) : wbase;
+                if constexpr (Q == 4) { wp[2] = cmul(wp[1], wp[1]); wp[3] = cmul(wp[2], wp[1]); }
                 double2 t[Q];
                 t[0] = scr[kappa];
 #pragma unroll
-                for (int n1 = 1; n1 < Q; ++n1) t[n1] = cmul(scr[(size_t)n1 * BIG_M + kappa], a.wl2y[((unsigned)n1 * k2) & mask]);
+                for (int n1 = 1; n1 < Q; ++n1) t[n1] = cmul(scr[(size_t)n1 * BIG_M + kappa], wp[n1]);
                 radixq_fwd<Q>(t);                             // t[k1] = Z[k2 + 2M k1]
                 if constexpr (MODE == 1) {
                     if (ghat_is_rep(a.g, px, m)) a.GhatOut[gbase + kappa + (size_t)BIG_M * rank] = t[rank].x * a.gscale;
@@ -171,7 +186,7 @@ ILM_HD void passB_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int clust
                         const double gh = a.Ghat[gbase + kappa + (size_t)BIG_M * k1];
                         s = cadd(s, rotq<Q>(cmk(t[k1].x * gh, t[k1].y * gh), rank * k1));
                     }
-                    v[e] = rank ? cmulc(s, a.wl2y[((unsigned)rank * k2) & mask]) : s;
+                    v[e] = rank ? cmulc(s, wp[rank]) : s;
                 }
             }
             if constexpr (MODE == 0) {
