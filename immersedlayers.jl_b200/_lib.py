@@ -95,6 +95,7 @@ SIGNATURES = {
     "ilm_create_schur_vector": (_i, [_vp, _i, _d, _i, _i, _dp]),
     "ilm_create_nRTRn_vector": (_i, [_vp, _d, _dp]),
     "ilm_convective_derivative_scalar": (_i, [_vp, _dp, _dp, _dp]),
+    "ilm_convective_derivative_dual": (_i, [_vp, _dp, _dp, _dp]),
     "ilm_convective_derivative_vector": (_i, [_vp, _dp, _dp, _dp]),
     "ilm_w_cross_v": (_i, [_vp, _dp, _dp, _dp]),
     "ilm_dense_launch_count": (C.c_int64, []),

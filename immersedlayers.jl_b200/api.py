@@ -1285,7 +1285,8 @@ def stokes_flow(cache, vplus, vminus=None, S=None, Ss=None):
 
 
 def convective_derivative(out, v, *args):
-    """convective_derivative!(udp, v, p, cache) = v . grad p on Nodes{Primal} (src/grid_operators.jl:258-264);
+    """convective_derivative!(udp, v, p, cache) = v . grad p on Nodes{Primal} (src/grid_operators.jl:258-264)
+    or on Nodes{Dual} (:272-288);
     convective_derivative!(vdu, v, u, cache) = (v . grad) u on Edges (:290-299);
     convective_derivative!(udu, u, cache) = (u . grad) u (:308-316).  Divided by dx for GridScaling.
     No ConvectiveDerivativeCache argument: the fused kernels need no temporaries."""
@@ -1297,9 +1298,9 @@ def convective_derivative(out, v, *args):
         raise MethodError("convective_derivative: expected (out, v, cache) or (out, v, q, cache)")
     _expect(v, Edges, "convective_derivative")
     if isinstance(q, Nodes):
-        _expect_nodes(q, Primal, "convective_derivative")
-        _expect_nodes(out, Primal, "convective_derivative")
-        L.check(cache._lib.ilm_convective_derivative_scalar(cache._plan, _ptr(v.data), _ptr(q.data), _ptr(out.data)))
+        _expect_nodes(out, q.celltype, "convective_derivative")
+        fn = cache._lib.ilm_convective_derivative_scalar if q.celltype == Primal else cache._lib.ilm_convective_derivative_dual
+        L.check(fn(cache._plan, _ptr(v.data), _ptr(q.data), _ptr(out.data)))
         return out
     _expect(q, Edges, "convective_derivative")
     _expect(out, Edges, "convective_derivative")

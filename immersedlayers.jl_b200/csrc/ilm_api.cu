@@ -388,6 +388,17 @@ extern "C" int ilm_convective_derivative_scalar(ilm_plan* p, const double* vel_e
     ILM_TRY(launch_convective_scalar(p, dv, dv + n_edges_u(p), dp, dout, deriv_div(p)));
     return io.finish();
 }
+// convective_derivative!(vdw, v, w, cache, extra) with w on Nodes{Dual} (:272-288, 329-341): out = (v . grad w) / dx
+extern "C" int ilm_convective_derivative_dual(ilm_plan* p, const double* vel_edges, const double* nodes_dual, double* out) {
+    ILM_CHECK_PLAN(p);
+    Io io(p);
+    const double* dv = io.in(vel_edges, n_layout(p, ILM_EDGES));
+    const double* dw = io.in(nodes_dual, n_layout(p, ILM_NODES_DUAL));
+    double* dout = io.out(out, n_layout(p, ILM_NODES_DUAL));
+    if (io.status) return io.status;
+    ILM_TRY(launch_convective_dual(p, dv, dv + n_edges_u(p), dw, dout, deriv_div(p)));
+    return io.finish();
+}
 // convective_derivative!(vdu, v, u, cache, extra) / (udu, u, cache, extra) (:290-316,343-375): out = (v . grad) u / dx
 extern "C" int ilm_convective_derivative_vector(ilm_plan* p, const double* vel_edges, const double* u_edges, double* out_edges) {
     ILM_CHECK_PLAN(p);

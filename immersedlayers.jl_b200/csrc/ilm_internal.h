@@ -139,6 +139,7 @@ int launch_scale(ilm_plan* p, double* w, size_t n, double scale);
 int launch_mask_product(ilm_plan* p, double* w, int wlayout, const double* m, int mlayout, int complementary);
 // convective terms, one fused sweep each (src/grid_operators.jl:258-434)
 int launch_convective_scalar(ilm_plan* p, const double* u, const double* v, const double* pn, double* out, double div);
+int launch_convective_dual(ilm_plan* p, const double* u, const double* v, const double* w, double* out, double div);
 int launch_w_cross_v(ilm_plan* p, const double* w, const double* u, const double* v, double* ou, double* ov);
 int launch_convective_vector(ilm_plan* p, const double* cu, const double* cv, const double* u, const double* v, double* ou,
                              double* ov, double div);

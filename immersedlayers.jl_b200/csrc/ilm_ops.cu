@@ -881,6 +881,35 @@ __global__ void k_convective_vector(GridDims g, const double* __restrict__ cu, c
     }
 }
 
+// ---- v . grad w on Nodes{Dual} (:272-288, 329-341) -----------------------------------------------
+// Edges{Dual} temporaries: the x-component lives at the primal y-edge positions ((NX-1) x NY), the
+// y-component at the primal x-edge positions (NX x (NY-1)).  grad!(Edges{Dual}, w), the 4-point means of the
+// primal velocity at those positions, the product and the 2-point means back to the dual nodes.
+__device__ __forceinline__ double cdw_tx(const double* u, const double* w, GridDims g, int a, int b) {    // at (a, b) of (NX-1) x NY
+    if (b < 1 || b > g.NY - 2) return 0.0;                       // u (NX x (NY-1)) averaged over rows b-1, b and columns a, a+1
+    const double r0 = __dadd_rn(ld_u(u, g, a, b - 1), ld_u(u, g, a + 1, b - 1));
+    const double r1 = __dadd_rn(ld_u(u, g, a, b), ld_u(u, g, a + 1, b));
+    const double cu = __dmul_rn(0.25, __dadd_rn(r0, r1));
+    return __dmul_rn(cu, __dsub_rn(ld_d(w, g, a + 1, b), ld_d(w, g, a, b)));
+}
+__device__ __forceinline__ double cdw_ty(const double* v, const double* w, GridDims g, int a, int b) {    // at (a, b) of NX x (NY-1)
+    if (a < 1 || a > g.NX - 2) return 0.0;                       // v ((NX-1) x NY) averaged over columns a-1, a and rows b, b+1
+    const double r0 = __dadd_rn(ld_v(v, g, a - 1, b), ld_v(v, g, a, b));
+    const double r1 = __dadd_rn(ld_v(v, g, a - 1, b + 1), ld_v(v, g, a, b + 1));
+    const double cv = __dmul_rn(0.25, __dadd_rn(r0, r1));
+    return __dmul_rn(cv, __dsub_rn(ld_d(w, g, a, b + 1), ld_d(w, g, a, b)));
+}
+__global__ void k_convective_dual(GridDims g, const double* __restrict__ u, const double* __restrict__ v,
+                                  const double* __restrict__ w, double* __restrict__ out, double div) {
+    const size_t n = (size_t)g.NX * g.NY, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+        const int i = (int)(idx % g.NX), j = (int)(idx / g.NX);
+        const double sx = (i >= 1 && i <= g.NX - 2) ? mean2(cdw_tx(u, w, g, i - 1, j), cdw_tx(u, w, g, i, j)) : 0.0;
+        const double sy = (j >= 1 && j <= g.NY - 2) ? mean2(cdw_ty(v, w, g, i, j - 1), cdw_ty(v, w, g, i, j)) : 0.0;
+        out[idx] = __ddiv_rn(__dadd_rn(sx, sy), div);
+    }
+}
+
 static unsigned sweep_blocks(const ilm_plan* p, size_t n) {
     size_t blocks = (n + 255) / 256;
     const size_t cap = (size_t)p->nsm * 16;
@@ -889,6 +918,12 @@ static unsigned sweep_blocks(const ilm_plan* p, size_t n) {
 int launch_convective_scalar(ilm_plan* p, const double* u, const double* v, const double* pn, double* out, double div) {
     const GridDims g{p->g.NX, p->g.NY};
     k_convective_scalar<<<sweep_blocks(p, (size_t)(g.NX - 1) * (g.NY - 1)), 256, 0, p->stream>>>(g, u, v, pn, out, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+int launch_convective_dual(ilm_plan* p, const double* u, const double* v, const double* w, double* out, double div) {
+    const GridDims g{p->g.NX, p->g.NY};
+    k_convective_dual<<<sweep_blocks(p, (size_t)g.NX * g.NY), 256, 0, p->stream>>>(g, u, v, w, out, div);
     ILM_LAUNCHED(p);
     return ILM_OK;
 }

@@ -221,6 +221,8 @@ int64_t ilm_dense_launch_count(void);
  * Results are divided by dx for GridScaling (_scale_derivative!), except w x v (:404-410).           */
 /* convective_derivative!(udp::Nodes{Primal}, u::Edges, p::Nodes{Primal}, ...) (:258-264, 318-327) */
 int ilm_convective_derivative_scalar(ilm_plan* plan, const double* vel_edges, const double* nodes_primal, double* out_nodes_primal);
+/* convective_derivative!(vdw::Nodes{Dual}, v::Edges, w::Nodes{Dual}, ...) (:272-288, 329-341) */
+int ilm_convective_derivative_dual(ilm_plan* plan, const double* vel_edges, const double* nodes_dual, double* out_nodes_dual);
 /* convective_derivative!(vdu::Edges, v::Edges, u::Edges, ...) (:290-299, 361-375); u_edges == vel_edges gives
  * convective_derivative!(udu, u, ...) (:308-316, 343-359)                                            */
 int ilm_convective_derivative_vector(ilm_plan* plan, const double* vel_edges, const double* u_edges, double* out_edges);

@@ -184,6 +184,8 @@ solve_b200!(b::Vector{Float64}, (LU, ipiv)) =
 # ---- convective terms (src/grid_operators.jl:258-434); the extra caches become unused
 convective_derivative!(udp::Nodes{Primal}, u::Edges{Primal}, p::Nodes{Primal}, c::B200Cache, extra=nothing) =
     (check(ccall((:ilm_convective_derivative_scalar, lib), Cint, (Ptr{Cvoid}, PD, PD, PD), c.plan, u.data, p.data, udp.data)); udp)
+convective_derivative!(vdw::Nodes{Dual}, v::Edges{Primal}, w::Nodes{Dual}, c::B200Cache, extra=nothing) =
+    (check(ccall((:ilm_convective_derivative_dual, lib), Cint, (Ptr{Cvoid}, PD, PD, PD), c.plan, v.data, w.data, vdw.data)); vdw)
 convective_derivative!(vdu::Edges{Primal}, v::Edges{Primal}, u::Edges{Primal}, c::B200Cache, extra=nothing) =
     (check(ccall((:ilm_convective_derivative_vector, lib), Cint, (Ptr{Cvoid}, PD, PD, PD), c.plan, v.data, u.data, vdu.data)); vdu)
 convective_derivative!(udu::Edges{Primal}, u::Edges{Primal}, c::B200Cache, extra=nothing) =

@@ -1045,3 +1045,16 @@ def convective_derivative_vector(grid, cu, cv, u, v, div=1.0):
     ov = grid_interpolate(grid, p2, DUAL, YEDGE) + grid_interpolate(grid, p3, PRIMAL, YEDGE)
     return ou / div, ov / div
 
+
+def convective_derivative_dual(grid, u, v, w, div=1.0):
+    """_unscaled_convective_derivative!(udw::Nodes{Dual}, u, w) (:329-341) with Edges{Dual} temporaries (x-component
+    at the primal y-edge positions, y-component at the primal x-edge positions): grad!(vt1, w);
+    grid_interpolate!(vt2, u) (4-point means); product!; grid_interpolate!(udw, vt3).  Parity unpinned like
+    grid_interpolate itself."""
+    gx = w[1:, :] - w[:-1, :]                                  # (NX-1) x NY, at (i, j-1/2)
+    gy = w[:, 1:] - w[:, :-1]                                  # NX x (NY-1), at (i-1/2, j)
+    cu = grid_interpolate(grid, u, XEDGE, YEDGE)
+    cv = grid_interpolate(grid, v, YEDGE, XEDGE)
+    out = grid_interpolate(grid, cu * gx, YEDGE, DUAL) + grid_interpolate(grid, cv * gy, XEDGE, DUAL)
+    return out / div
+

@@ -533,6 +533,10 @@ def test_convective_terms(case, device, request):
     out = ilm.Nodes(ilm.Primal, g, device=device)
     ilm.convective_derivative(out, q, ilm.Nodes(ilm.Primal, g, device=device).set(p), cache)
     assert np.array_equal(host(out.data).reshape(p.shape, order="F"), o.convective_derivative_scalar(oc.grid, u, v, p, dx))
+    # v . grad w on the dual nodes
+    outd = ilm.Nodes(ilm.Dual, g, device=device)
+    ilm.convective_derivative(outd, q, ilm.Nodes(ilm.Dual, g, device=device).set(w), cache)
+    assert np.array_equal(host(outd.data).reshape(w.shape, order="F"), o.convective_derivative_dual(oc.grid, u, v, w, dx))
     # (v . grad) v and (v . grad) u
     nu = us[0] * us[1]
     for other, (ou_, ov_) in ((q, (u, v)), (q2, (u2, v2))):

@@ -433,4 +433,9 @@ def test_convective_terms_on_polynomial_fields():
     ou, ov = o.w_cross_v(g, w, u, v)
     assert np.abs(ou[2:-2, 2:-2] - (-1.3 * (3 * xu[:, None] - yu[None, :]))[2:-2, 2:-2]).max() < 1e-12
     assert np.abs(ov[2:-2, 2:-2] - (1.3 * (xv[:, None] + 2 * yv[None, :]))[2:-2, 2:-2]).max() < 1e-12
-    del xd, yd
+    # v . grad w on the dual nodes: uniform velocity, linear w
+    u = np.full(o.field_shape(o.XEDGE, g.NX, g.NY), a)
+    v = np.full(o.field_shape(o.YEDGE, g.NX, g.NY), b)
+    wd = px * xd[:, None] + py * yd[None, :]
+    out = o.convective_derivative_dual(g, u, v, wd, div=g.dx)
+    assert np.abs(out[2:-2, 2:-2] - (a * px + b * py)).max() < 1e-12
