@@ -528,7 +528,8 @@ extern "C" int ilm_mask(ilm_plan* p, double* nodes) {
 // complement of an IF-HERK stage (src/timemarching.jl:86-107 via ConstrainedSystems)
 // rows of the probed grid field that the post-operator (E, or a stencil followed by E on the edge
 // tables) can read: the union of the points' window rows, widened by the stencil reach
-static void probe_output_rows(const ilm_plan* p, int which, int* olo, int* ohi) {
+namespace ilm {
+void probe_output_rows(const ilm_plan* p, int which, int* olo, int* ohi) {
     int lo = 1 << 30, hi = -1;
     auto span = [&](const DevTable& t, int margin) {
         for (int j : t.h_j0) { lo = std::min(lo, j - margin); hi = std::max(hi, j + t.W + margin); }
@@ -539,6 +540,7 @@ static void probe_output_rows(const ilm_plan* p, int which, int* olo, int* ohi) 
     *ohi = hi;                       // clamped to the field by conv_apply
     if (hi <= *olo) { *olo = -1; *ohi = -1; }
 }
+}  // namespace ilm
 
 extern "C" int ilm_create_schur_kernel(ilm_plan* p, int which, int kernel_id, double scale, int col_begin, int col_end,
                                        double* A) {

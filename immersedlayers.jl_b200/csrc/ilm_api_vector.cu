@@ -323,18 +323,45 @@ extern "C" int ilm_create_schur_vector(ilm_plan* p, int which, double scale, int
     // grid scratch: Nodes{Dual} right-hand sides (curl builders) live in g_a; Edges-valued ones in g_edges,
     // whose u and v components ride one complex transform
     double* fu = p->g_a;
+    if (curl) {
+        // Curl builders: the right-hand side C_s^T e_c is a Nodes{Dual} field, so TWO columns ride one complex
+        // transform (as in the scalar builders).  R_f e_c is a W x W edge patch, its curl reaches one row further:
+        // the first transform gets that row range as sparse input; the last one only inverts the rows that
+        // C_s (curl + edge interpolation) can read.
+        const DevTable& tu = p->tab[ILM_XEDGES];
+        const DevTable& tv = p->tab[ILM_YEDGES];
+        auto rows_of = [&](int c, int* lo, int* hi) {
+            const DevTable& t = c < N ? tu : tv;
+            const int k = c < N ? c : c - N;
+            *lo = std::min(*lo, t.h_j0[k] - 2);
+            *hi = std::max(*hi, t.h_j0[k] + t.W + 2);
+        };
+        int olo, ohi;
+        probe_output_rows(p, ILM_CLINVCT, &olo, &ohi);
+        const int reps = which == ILM_V_CL2INVCT ? 2 : 1;
+        double* fv = p->g_b;
+        for (int c = col_begin; c < col_end; c += 2) {
+            const bool two = c + 1 < col_end;
+            int rlo = 1 << 30, rhi = -1;
+            for (int q = 0; q < (two ? 2 : 1); ++q) rows_of(c + q, &rlo, &rhi);
+            rlo = std::max(rlo, 0); rhi = std::min(rhi, p->g.NY);
+            ILM_TRY(launch_vcurl_probe_pre(p, c, two ? 2 : 1, fu, fv, rlo, rhi, deriv_div(p)));   // C^T R_f e_c / dx on the patch rows
+            const FieldRef f1{fu, p->g.NX, p->g.NY};
+            const FieldRef f2 = two ? FieldRef{fv, p->g.NX, p->g.NY} : FieldRef{nullptr, 0, 0};
+            for (int r = 0; r < reps; ++r) {
+                const bool first = r == 0, last = r == reps - 1;
+                ILM_TRY(conv_apply(p, 0, f1, f2, first ? rlo : -1, first ? rhi : -1, last ? olo : -1, last ? ohi : -1));
+            }
+            ILM_TRY(launch_vcurl_probe_post(p, two ? 2 : 1, fu, fv, deriv_div(p), -scale, dA + (size_t)(c - col_begin) * M,
+                                            dA + (size_t)(c + 1 - col_begin) * M));
+        }
+        return io.finish();
+    }
     for (int c = col_begin; c < col_end; ++c) {
         k_unit2<<<(M + 127) / 128, 128, 0, p->stream>>>(unit, M, c);
         ILM_CUDA(cudaGetLastError());
         p->launches++;
-        if (curl) {
-            // C_s^T v = C^T R_f v / dx -> Nodes{Dual} in g_a
-            ILM_TRY(vsurface_curl_s2n_dev(p, unit, fu));
-            const int reps = which == ILM_V_CL2INVCT ? 2 : 1;
-            for (int r = 0; r < reps; ++r)
-                ILM_TRY(conv_apply(p, 0, FieldRef{fu, p->g.NX, p->g.NY}, FieldRef{nullptr, 0, 0}));
-            ILM_TRY(vsurface_curl_n2s_dev(p, fu, sout));
-        } else {
+        {
             // Edges-valued field: stage through g_edges, then split into (fu, fv) for the pair transform
             if (which == ILM_V_RTLINVR) ILM_TRY(regularize_edges(p, unit, p->g_edges));
             else ILM_TRY(vsurface_divergence_dev(p, mode, unit, p->g_edges));

@@ -150,6 +150,10 @@ int launch_probe_pre(ilm_plan* p, const DevTable& t, int col0, int ncol, double*
 int launch_probe_post(ilm_plan* p, const DevTable& t, int ncol, const double* g0, const double* g1, double coef, double* d0,
                       double* d1);
 // A[:, c] = -scale/factor * E (T - c0) R e_c with T an ng x ng table (leading dimension ldg), zero beyond ng
+// fused pre / post operators of the VectorData curl probes (two columns per launch)
+int launch_vcurl_probe_pre(ilm_plan* p, int col0, int ncol, double* g0, double* g1, int rlo, int rhi, double div);
+int launch_vcurl_probe_post(ilm_plan* p, int ncol, const double* g0, const double* g1, double div, double coef, double* d0,
+                            double* d1);
 int launch_schur_direct(ilm_plan* p, const double* G, int ldg, int ng, double c0, double factor, double scale, int col_begin,
                         int col_end, double* A);
 // vector-cache pieces (TensorData = [dudx; dudy; dvdx; dvdy], EdgeGradient likewise)
@@ -159,6 +163,8 @@ int launch_vec_pointwise(ilm_plan* p, int op, const double* in, double* out);
 int launch_grad_tensor(ilm_plan* p, const double* edges, double* eg, double div);
 int launch_div_tensor(ilm_plan* p, const double* eg, double* edges, double div);
 
+// rows of the probed grid field that the post-operator of Schur builder `which` can read (ilm_api.cu)
+void probe_output_rows(const ilm_plan* p, int which, int* olo, int* ohi);
 // mask = -L^-1 D_s 1 on Nodes{Primal} (scalar cache, ilm_api.cu) / on Edges (vector cache, ilm_api_vector.cu)
 int mask_primal_dev(ilm_plan* p, double* dn);
 int mask_edges_dev(ilm_plan* p, double* de);

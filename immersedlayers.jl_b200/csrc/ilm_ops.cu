@@ -735,6 +735,72 @@ int launch_probe_post(ilm_plan* p, const DevTable& t, int ncol, const double* g0
     return ILM_OK;
 }
 
+// Fused pre/post kernels of the VectorData curl probes (create_CLinvCT / create_CL2invCT on a vector cache,
+// src/matrix_operators.jl:40-61,102-125), two columns per launch:
+//   pre : rows [rlo, rhi) of the Nodes{Dual} right-hand side = C^T R_f e_c / dx: the curl of ONE W x W edge
+//         patch (u patch for c < N, v patch otherwise), zero elsewhere in the rows (other rows never read)
+//   post: A[:, c] = coef * E_f (C s) / dx with the curl formed inside the gather (both edge components)
+// The arithmetic is that of regularize! -> curl! and curl! -> interpolate! -> scale (same operations, same
+// order); they replace 12 + 10 launches per column pair.
+__global__ void k_vcurl_probe_pre(int N, int NX, int NY, TabView tu, TabView tv, const double* __restrict__ wRu,
+                                  const double* __restrict__ wRv, int col0, int ncol, double* __restrict__ g0,
+                                  double* __restrict__ g1, int rlo, int rhi, double div) {
+    const int q = blockIdx.y;
+    if (q >= ncol) return;
+    const int c = col0 + q, comp = c < N ? 0 : 1, k = comp ? c - N : c;
+    const TabView& t = comp ? tv : tu;
+    const double* wR = comp ? wRv : wRu;
+    double* out = q ? g1 : g0;
+    const int ci = t.i0[k], cj = t.j0[k], W = t.W;
+    auto patch = [&](int i, int j) -> double {              // R_f e_c at edge (i, j) of its component
+        const int a = i - ci, b = j - cj;
+        if (a < 0 || a >= W || b < 0 || b >= W || i < 0 || i >= t.mx || j < 0 || j >= t.my) return 0.0;
+        return wR[(size_t)k * W * W + b * W + a];
+    };
+    const size_t n = (size_t)(rhi - rlo) * NX;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % NX), j = rlo + (int)(idx / NX);
+        double val = 0.0;
+        if (i >= 1 && i <= NX - 2 && j >= 1 && j <= NY - 2)
+            val = (comp == 0 ? __dsub_rn(patch(i, j - 1), patch(i, j)) : __dsub_rn(patch(i, j), patch(i - 1, j))) / div;
+        out[(size_t)j * NX + i] = val;
+    }
+}
+int launch_vcurl_probe_pre(ilm_plan* p, int col0, int ncol, double* g0, double* g1, int rlo, int rhi, double div) {
+    const size_t n = (size_t)(rhi - rlo) * p->g.NX;
+    int bx = (int)((n + 255) / 256);
+    if (bx > 2 * p->nsm) bx = 2 * p->nsm;
+    if (bx < 1) bx = 1;
+    k_vcurl_probe_pre<<<dim3(bx, ncol), 256, 0, p->stream>>>(p->N, p->g.NX, p->g.NY, view(p->tab[ILM_XEDGES]), view(p->tab[ILM_YEDGES]),
+                                                          p->tab[ILM_XEDGES].wR, p->tab[ILM_YEDGES].wR, col0, ncol, g0, g1, rlo, rhi, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+__global__ void k_vcurl_probe_post(int N, TabView tu, TabView tv, int NX, int NY, const double* __restrict__ g0,
+                                   const double* __restrict__ g1, double div, double coef, double* __restrict__ d0,
+                                   double* __restrict__ d1) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = gid >> 4, slot = gid & 15;
+    const double* s = blockIdx.y ? g1 : g0;
+    double* dst = blockIdx.y ? d1 : d0;
+    const double su = gather16_edge<1, 0>(tu, s, NX, NY, k, slot, k < N);
+    const double sv = gather16_edge<1, 1>(tv, s, NX, NY, k, slot, k < N);
+    if (slot == 0 && k < N) {
+        dst[k] = __dmul_rn(coef, su / div);
+        dst[N + k] = __dmul_rn(coef, sv / div);
+    }
+}
+int launch_vcurl_probe_post(ilm_plan* p, int ncol, const double* g0, const double* g1, double div, double coef, double* d0,
+                            double* d1) {
+    if (p->N == 0) return ILM_OK;
+    const int threads = p->N * 16;
+    k_vcurl_probe_post<<<dim3((threads + 127) / 128, ncol), 128, 0, p->stream>>>(p->N, view(p->tab[ILM_XEDGES]), view(p->tab[ILM_YEDGES]),
+                                                                                  p->g.NX, p->g.NY, g0, g1, div, coef, d0, d1);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
 // ------------------------------------------------------------------ mask products
 // w *= grid_interpolate(mask -> layout of w), the body of _scalar_mask_product! / _vector_mask_product!
 // (src/surface_operators.jl:880-923): product!(w, mask, w) on the mask's own layout, otherwise the
