@@ -26,7 +26,11 @@ __global__ void __launch_bounds__(512, 1) ILM_CAT(ilm_passB_big_Q, ILM_Q)(ConvAr
 __global__ void __launch_bounds__(512, 1) ILM_CAT(ilm_passC_big_Q, ILM_Q)(ConvArgs a) {
     extern __shared__ double2 smem[];
     DevCtx c{(int)(threadIdx.x & 255), (int)(threadIdx.x >> 8), nullptr};
-    passC_big_body<ILM_Q>(c, a, smem, blockIdx.x, gridDim.x);
+#if ILM_Q == 2
+    passC_big_percta_body<ILM_Q>(c, a, smem, blockIdx.x, gridDim.x);
+#else
+    passC_big_body<ILM_Q>(c, a, smem, blockIdx.x / ILM_Q, gridDim.x / ILM_Q);
+#endif
 }
 __global__ void __launch_bounds__(512, 1) ILM_CAT(ilm_passG_big_Q, ILM_Q)(ConvArgs a) {
     extern __shared__ double2 smem[];
@@ -47,17 +51,18 @@ int ILM_CAT(conv_launch_big_Q, ILM_Q)(int which, const ConvArgs& a, int nsm, cud
         ILM_CUDA(cudaFuncSetAttribute(ILM_CAT(ilm_passG_big_Q, ILM_Q), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         attr_done = true;
     }
-    if (which == 0 || which == 2) {
+    if (which == 0 || (which == 2 && ILM_Q == 2)) {
         const int nwork = which == 0 ? a.rhi - a.rlo : (a.ohi - a.olo) * ILM_Q;
         int grid = nwork < nsm ? nwork : nsm;
         if (grid < 1) grid = 1;
         if (which == 0) ILM_CAT(ilm_passA_big_Q, ILM_Q)<<<grid, 512, C::SMEM_BYTES, st>>>(a);
         else ILM_CAT(ilm_passC_big_Q, ILM_Q)<<<grid, 512, C::SMEM_BYTES, st>>>(a);
     } else {
-        // column pass: one cluster of ILM_Q CTAs per 2-column tile, as many clusters as fit the device
-        if (!a.scratch) { set_error("big column pass without a scratch buffer"); return ILM_EINVAL; }
-        int ntiles = a.g.Lx;
-        if (a.whi > 0) ntiles = (a.whi < ntiles ? a.whi : ntiles) - a.wlo;
+        // column pass / last row pass: one cluster of ILM_Q CTAs per 2-column tile / per row, as many clusters
+        // as fit the device; the cluster's hand-off line lives in a.scratch
+        if (!a.scratch) { set_error("big-length pass without a scratch buffer"); return ILM_EINVAL; }
+        int nitems = which == 2 ? a.ohi - a.olo : a.g.Lx;
+        if (which != 2 && a.whi > 0) nitems = (a.whi < nitems ? a.whi : nitems) - a.wlo;
         cudaLaunchConfig_t cfg{};
         cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -71,10 +76,11 @@ int ILM_CAT(conv_launch_big_Q, ILM_Q)(int which, const ConvArgs& a, int nsm, cud
             ILM_CUDA(cudaOccupancyMaxActiveClusters(&n, ILM_CAT(ilm_passB_big_Q, ILM_Q), &cfg));
             max_clusters[dev & 63] = n > 0 ? (n < nsm / ILM_Q ? n : nsm / ILM_Q) : 1;
         }
-        int nclusters = ntiles < max_clusters[dev & 63] ? ntiles : max_clusters[dev & 63];
+        int nclusters = nitems < max_clusters[dev & 63] ? nitems : max_clusters[dev & 63];
         if (nclusters < 1) nclusters = 1;
         cfg.gridDim = dim3(nclusters * ILM_Q);
         if (which == 1) ILM_CUDA(cudaLaunchKernelEx(&cfg, ILM_CAT(ilm_passB_big_Q, ILM_Q), a));
+        else if (which == 2) ILM_CUDA(cudaLaunchKernelEx(&cfg, ILM_CAT(ilm_passC_big_Q, ILM_Q), a));
         else ILM_CUDA(cudaLaunchKernelEx(&cfg, ILM_CAT(ilm_passG_big_Q, ILM_Q), a));
     }
     ILM_CUDA(cudaGetLastError());

@@ -115,7 +115,10 @@ int conv_setup(ilm_plan* p) {
     };
     ILM_TRY(upload_wl2(p->Ly, &p->wl2y));
     if (p->Lx > 4096) ILM_TRY(upload_wl2(p->Lx, &p->wl2x));
-    if (p->Ly > 4096) ILM_CUDA(cudaMalloc(&p->conv_scratch, (size_t)p->nsm * 2 * p->Ly * sizeof(double2)));
+    if (p->Ly > 4096 || p->Lx > 4096) {     // hand-off lines of the cluster passes: 2L complex per cluster, <= nsm/2 clusters
+        const size_t Lmax = (size_t)(p->Lx > p->Ly ? p->Lx : p->Ly);
+        ILM_CUDA(cudaMalloc(&p->conv_scratch, (size_t)p->nsm * Lmax * sizeof(double2)));
+    }
     ConvGeom g{p->Lx, p->Ly, p->g.NY, (p->g.NY + 1) & ~1};
     p->s_cap = s_elems(g);
     ILM_CUDA(cudaMalloc(&p->S, p->s_cap * sizeof(double2)));

@@ -146,7 +146,7 @@ template <int L> struct Len {
     using Cfg = FftCfg<base>;
     static constexpr int cpw = big ? 2 : (Cfg::F == 1 ? 2 : Cfg::F);        // pass B / C work item width
     static int rowsA(int nrows) { return big ? nrows : (nrows + Cfg::F - 1) / Cfg::F; }
-    static int rowsC(int nrows) { return big ? nrows * Q : (nrows + cpw - 1) / cpw; }
+    static int rowsC(int nrows) { return big ? (Q == 2 ? nrows * Q : nrows) : (nrows + cpw - 1) / cpw; }
 };
 template <int L> static void runA(HostCtx& c, const ConvArgs& a, double2* sm, int b, int nb) {
     if constexpr (Len<L>::big) passA_big_body<Len<L>::Q>(c, a, sm, b, nb); else passA_body<L>(c, a, sm, b, nb);
@@ -161,7 +161,14 @@ template <int L, int MODE> static void launchB(const ConvArgs& a, int b, int nb)
     else run_cta(CY::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runB<L, MODE>(c, a, sm, b, nb); });
 }
 template <int L> static void runC(HostCtx& c, const ConvArgs& a, double2* sm, int b, int nb) {
-    if constexpr (Len<L>::big) passC_big_body<Len<L>::Q>(c, a, sm, b, nb); else passC_body<L>(c, a, sm, b, nb);
+    if constexpr (Len<L>::big && Len<L>::Q == 2) passC_big_percta_body<2>(c, a, sm, b, nb);
+    else if constexpr (Len<L>::big) passC_big_body<Len<L>::Q>(c, a, sm, b, nb);
+    else passC_body<L>(c, a, sm, b, nb);
+}
+template <int L> static void launchC(const ConvArgs& a, int b, int nb) {
+    using CX = typename Len<L>::Cfg;
+    if constexpr (Len<L>::big && Len<L>::Q > 2) run_cluster(Len<L>::Q, CX::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runC<L>(c, a, sm, b, nb); });
+    else run_cta(CX::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runC<L>(c, a, sm, b, nb); });
 }
 
 
@@ -183,7 +190,7 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
     for (int n = 0; n < 2 * LY; ++n) wl2[n] = expm2pii(n, 2LL * LY);
     for (int n = 0; n < 2 * LX; ++n) wl2x[n] = expm2pii(n, 2LL * LX);
     a.wl2y = wl2.data(); a.wl2x = wl2x.data();
-    std::vector<double2> scratch((size_t)3 * 2 * LY, cmk(NAN, NAN));        // up to 3 emulated CTAs
+    std::vector<double2> scratch((size_t)3 * 2 * (LY > LX ? LY : LX), cmk(NAN, NAN));        // up to 3 emulated clusters
     a.scratch = scratch.data();
     // ---- Ghat build: h = eps_i eps_j g
     std::vector<double> h((size_t)NX * NY);
@@ -243,7 +250,7 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
         for (int b = 0; b < nbB; ++b)
             launchB<LY, 0>(a, b, nbB);
         for (int b = 0; b < nb; ++b)
-            run_cta(CX::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runC<LX>(c, a, sm, b, nb); });
+            launchC<LX>(a, b, nb);
     }
     // ---- direct check (sampled)
     double err = 0, nrm = 0;
