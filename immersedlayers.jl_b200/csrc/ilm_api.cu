@@ -556,16 +556,7 @@ extern "C" int ilm_create_schur_kernel(ilm_plan* p, int which, int kernel_id, do
     if (io.status) return io.status;
     const int glayout = (which == ILM_CLINVCT) ? ILM_NODES_DUAL : ILM_NODES_PRIMAL;
     const int mode = (which == ILM_GLINVD_CROSS) ? ILM_CROSS : ILM_NORMAL;
-    double* sout = p->s_a + N;        // N
     double* gf[2] = {p->g_a, p->g_b};
-    auto post = [&](double* g, double* dst) -> int {
-        switch (which) {
-        case ILM_RTLINVR: ILM_TRY(launch_interpolate(p, p->tab[ILM_NODES_PRIMAL], g, sout)); break;
-        case ILM_CLINVCT: ILM_TRY(surface_curl_n2s_dev(p, mode, g, sout)); break;
-        default: ILM_TRY(surface_grad_dev(p, mode, g, sout)); break;
-        }
-        return launch_scale_store_column(p, sout, dst, N, -scale);
-    };
     // two columns per complex transform (src/matrix_operators.jl:16-26 probes one at a time)
     const DevTable& tp = p->tab[ILM_NODES_PRIMAL];
     // The post-operator only reads the rows under the interpolation windows (plus the stencil
@@ -595,21 +586,16 @@ extern "C" int ilm_create_schur_kernel(ilm_plan* p, int which, int kernel_id, do
             const LayoutInfo lg = layout_info(glayout, p->g.NX, p->g.NY);
             rlo = std::max(lo - 1, 0); rhi = std::min(hi + 1, lg.my);
             if (rhi <= rlo) { rlo = 0; rhi = 1; }
-            double* eu = p->g_edges;
-            double* ev = p->g_edges + n_edges_u(p);
-            for (int q = 0; q < (two ? 2 : 1); ++q) {
-                ILM_TRY(launch_regularize_normal_unit(p, mode, c + q, eu, ev, rlo - 1, rhi + 1, true));
-                if (which == ILM_CLINVCT) ILM_TRY(launch_curl_e2n(p, eu, ev, gf[q], deriv_div(p), rlo, rhi));
-                else ILM_TRY(launch_divergence(p, eu, ev, gf[q], deriv_div(p), rlo, rhi));
-            }
+            // curl / divergence of the two edge patches written straight into the patch rows (one launch for both columns)
+            ILM_TRY(launch_sprobe_pre(p, which == ILM_CLINVCT ? 1 : 0, mode, c, two ? 2 : 1, gf[0], gf[1], rlo, rhi, deriv_div(p)));
         }
         ILM_TRY(conv_apply(p, kernel_id, fref(p, glayout, gf[0]), two ? fref(p, glayout, gf[1]) : FieldRef{nullptr, 0, 0}, rlo, rhi, olo, ohi));
         if (which == ILM_RTLINVR && kernel_id >= 0) {
             ILM_TRY(launch_probe_post(p, tp, two ? 2 : 1, gf[0], gf[1], -scale, dA + (size_t)(c - col_begin) * N,
                                       dA + (size_t)(c + 1 - col_begin) * N));
         } else {
-            ILM_TRY(post(gf[0], dA + (size_t)(c - col_begin) * N));
-            if (two) ILM_TRY(post(gf[1], dA + (size_t)(c + 1 - col_begin) * N));
+            ILM_TRY(launch_sprobe_post(p, which == ILM_CLINVCT ? 1 : 0, mode, two ? 2 : 1, gf[0], gf[1], deriv_div(p), -scale,
+                                       dA + (size_t)(c - col_begin) * N, dA + (size_t)(c + 1 - col_begin) * N));
         }
     }
     return io.finish();

@@ -150,6 +150,10 @@ int launch_probe_pre(ilm_plan* p, const DevTable& t, int col0, int ncol, double*
 int launch_probe_post(ilm_plan* p, const DevTable& t, int ncol, const double* g0, const double* g1, double coef, double* d0,
                       double* d1);
 // A[:, c] = -scale/factor * E (T - c0) R e_c with T an ng x ng table (leading dimension ldg), zero beyond ng
+// fused pre / post operators of the ScalarData stencil probes (op 0: divergence / grad, op 1: curl), two columns per launch
+int launch_sprobe_pre(ilm_plan* p, int op, int mode, int col0, int ncol, double* g0, double* g1, int rlo, int rhi, double div);
+int launch_sprobe_post(ilm_plan* p, int op, int mode, int ncol, const double* g0, const double* g1, double div, double coef,
+                       double* d0, double* d1);
 // fused pre / post operators of the VectorData curl probes (two columns per launch)
 int launch_vcurl_probe_pre(ilm_plan* p, int col0, int ncol, double* g0, double* g1, int rlo, int rhi, double div);
 int launch_vcurl_probe_post(ilm_plan* p, int ncol, const double* g0, const double* g1, double div, double coef, double* d0,

@@ -735,6 +735,95 @@ int launch_probe_post(ilm_plan* p, const DevTable& t, int ncol, const double* g0
     return ILM_OK;
 }
 
+// Fused pre/post kernels of the ScalarData stencil probes (create_CLinvCT, create_GLinvD, create_GLinvD_cross on a
+// scalar cache, src/matrix_operators.jl:40-61,135-155,195-215), two columns per launch:
+//   pre : rows [rlo, rhi) of the right-hand side = curl / divergence of the two W x W edge patches
+//         (n_u R_u e_c, n_v R_v e_c) (normal) or (n_v R_u e_c, -n_u R_v e_c) (cross), divided by dx
+//   post: A[:, c] = coef * (n . E_f (stencil field)) / dx  (the fused gather of k_normal_interpolate_fused)
+// Same operations in the same order as regularize_normal! -> stencil and stencil -> normal_interpolate! -> scale.
+template <int OP>       // 0: divergence -> Nodes{Primal} (GLinvD), 1: curl -> Nodes{Dual} (CLinvCT)
+__global__ void k_sprobe_pre(int NX, int NY, TabView tu, TabView tv, const double* __restrict__ wRu, const double* __restrict__ wRv,
+                             const double* __restrict__ nx, const double* __restrict__ ny, int mode, int col0, int ncol,
+                             double* __restrict__ g0, double* __restrict__ g1, int rlo, int rhi, double div) {
+    const int q = blockIdx.y;
+    if (q >= ncol) return;
+    const int c = col0 + q, W = tu.W;
+    double* out = q ? g1 : g0;
+    const double fu = mode == ILM_NORMAL ? nx[c] : ny[c];
+    const double fv = mode == ILM_NORMAL ? ny[c] : -nx[c];
+    const int iu = tu.i0[c], ju = tu.j0[c], iv = tv.i0[c], jv = tv.j0[c];
+    auto U = [&](int i, int j) -> double {
+        const int a = i - iu, b = j - ju;
+        if (a < 0 || a >= W || b < 0 || b >= W || i < 0 || i >= NX || j < 0 || j >= NY - 1) return 0.0;
+        return __dmul_rn(wRu[(size_t)c * W * W + b * W + a], fu);
+    };
+    auto V = [&](int i, int j) -> double {
+        const int a = i - iv, b = j - jv;
+        if (a < 0 || a >= W || b < 0 || b >= W || i < 0 || i >= NX - 1 || j < 0 || j >= NY) return 0.0;
+        return __dmul_rn(wRv[(size_t)c * W * W + b * W + a], fv);
+    };
+    const int mx = OP == 0 ? NX - 1 : NX, my = OP == 0 ? NY - 1 : NY;
+    const int r1 = rhi < my ? rhi : my;
+    if (r1 <= rlo) return;
+    const size_t n = (size_t)(r1 - rlo) * mx;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % mx), j = rlo + (int)(idx / mx);
+        double val;
+        if (OP == 0) val = (((-U(i, j) + U(i + 1, j)) - V(i, j)) + V(i, j + 1)) / div;
+        else val = (i >= 1 && i <= NX - 2 && j >= 1 && j <= NY - 2) ? (((U(i, j - 1) - U(i, j)) - V(i - 1, j)) + V(i, j)) / div : 0.0;
+        out[(size_t)j * mx + i] = val;
+    }
+}
+int launch_sprobe_pre(ilm_plan* p, int op, int mode, int col0, int ncol, double* g0, double* g1, int rlo, int rhi, double div) {
+    const DevTable& tu = p->tab[ILM_XEDGES];
+    const DevTable& tv = p->tab[ILM_YEDGES];
+    const size_t n = (size_t)(rhi - rlo) * p->g.NX;
+    int bx = (int)((n + 255) / 256);
+    if (bx > 2 * p->nsm) bx = 2 * p->nsm;
+    if (bx < 1) bx = 1;
+    if (op == 0)
+        k_sprobe_pre<0><<<dim3(bx, ncol), 256, 0, p->stream>>>(p->g.NX, p->g.NY, view(tu), view(tv), tu.wR, tv.wR, p->nx, p->ny, mode,
+                                                             col0, ncol, g0, g1, rlo, rhi, div);
+    else
+        k_sprobe_pre<1><<<dim3(bx, ncol), 256, 0, p->stream>>>(p->g.NX, p->g.NY, view(tu), view(tv), tu.wR, tv.wR, p->nx, p->ny, mode,
+                                                             col0, ncol, g0, g1, rlo, rhi, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+template <int OP>
+__global__ void k_sprobe_post(int N, TabView tu, TabView tv, int NX, int NY, const double* __restrict__ g0,
+                              const double* __restrict__ g1, const double* __restrict__ nx, const double* __restrict__ ny, int mode,
+                              double div, double coef, double* __restrict__ d0, double* __restrict__ d1) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = gid >> 4, slot = gid & 15;
+    const double* nf = blockIdx.y ? g1 : g0;
+    double* dst = blockIdx.y ? d1 : d0;
+    const double su = gather16_edge<OP, 0>(tu, nf, NX, NY, k, slot, k < N);
+    const double sv = gather16_edge<OP, 1>(tv, nf, NX, NY, k, slot, k < N);
+    if (slot == 0 && k < N) {
+        double r;
+        if (mode == ILM_NORMAL) r = __dadd_rn(__dmul_rn(nx[k], su), __dmul_rn(ny[k], sv));
+        else r = __dsub_rn(__dmul_rn(nx[k], sv), __dmul_rn(ny[k], su));
+        dst[k] = __dmul_rn(coef, r / div);
+    }
+}
+// op 0: grad of Nodes{Primal} (GLinvD), op 1: curl of Nodes{Dual} (CLinvCT)
+int launch_sprobe_post(ilm_plan* p, int op, int mode, int ncol, const double* g0, const double* g1, double div, double coef,
+                       double* d0, double* d1) {
+    if (p->N == 0) return ILM_OK;
+    const int threads = p->N * 16;
+    const dim3 grid((threads + 127) / 128, ncol);
+    if (op == 0)
+        k_sprobe_post<0><<<grid, 128, 0, p->stream>>>(p->N, view(p->tab[ILM_XEDGES]), view(p->tab[ILM_YEDGES]), p->g.NX, p->g.NY, g0, g1,
+                                                      p->nx, p->ny, mode, div, coef, d0, d1);
+    else
+        k_sprobe_post<1><<<grid, 128, 0, p->stream>>>(p->N, view(p->tab[ILM_XEDGES]), view(p->tab[ILM_YEDGES]), p->g.NX, p->g.NY, g0, g1,
+                                                      p->nx, p->ny, mode, div, coef, d0, d1);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
 // Fused pre/post kernels of the VectorData curl probes (create_CLinvCT / create_CL2invCT on a vector cache,
 // src/matrix_operators.jl:40-61,102-125), two columns per launch:
 //   pre : rows [rlo, rhi) of the Nodes{Dual} right-hand side = C^T R_f e_c / dx: the curl of ONE W x W edge
