@@ -282,3 +282,19 @@ def test_slab_exchange_gloo_world2(NX, NY):
         p.join(timeout=60)
     assert [r for r, _ in res] == [0, 1]
     assert all(e < 1e-12 for _, e in res), res
+
+
+def test_julia_shim_binds_only_declared_symbols():
+    """julia/ImmersedLayersB200 (the maintainer-side ccall shim of INTEGRATION.md; not executable here:
+    no Julia toolchain) may only reference entry points that include/ilm_b200.h declares."""
+    import re
+    from ilm_b200 import _lib as L
+    src = open(os.path.join(ROOT, "julia", "ImmersedLayersB200", "src", "ImmersedLayersB200.jl")).read()
+    used = set(re.findall(r"\(:(ilm_[a-z_A-Z0-9]+), lib\)", src)) | set(re.findall(r"_c[23]\(:(ilm_[a-zA-Z_0-9]+)", src))
+    assert len(used) >= 35
+    header = open(os.path.join(ROOT, "include", "ilm_b200.h")).read()
+    for sym in sorted(used):
+        assert sym in L.SIGNATURES, sym
+        assert re.search(r"\b%s\s*\(" % sym, header), sym
+    also = set(re.findall(r"\(:(ilm_[a-z_A-Z0-9]+), lib\)", open(os.path.join(ROOT, "INTEGRATION.md")).read()))
+    assert also and all(s in L.SIGNATURES for s in also)
