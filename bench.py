@@ -327,13 +327,12 @@ def main():
 
         def step_host():
             if world > 1:
-                # host buffers in and out; the shard exchange itself stays on the device
-                dd = hcache.zeros_surface().set(fplus)
-                fstar = hcache.zeros_grid()
-                ilm.surface_divergence(fstar, dd, hcache)
-                ilm.inverse_laplacian(fstar, hcache)
-                S = shard.create_schur_sharded(ilm.create_RTLinvR, cache).t().contiguous().cpu().numpy().T
-                return ilm.dirichlet_poisson(hcache, fplus, S=S)[:2]
+                # host buffers in and out; the shard exchange itself stays on the device, the gathered S comes
+                # back to a page-locked host matrix (what a host caller of create_RTLinvR would hold)
+                Sd = shard.create_schur_sharded(ilm.create_RTLinvR, cache)
+                hb = ilm.api._host_zeros(N * N)
+                torch.from_numpy(hb).copy_(Sd.t().reshape(-1))
+                return ilm.dirichlet_poisson(hcache, fplus, S=hb.reshape((N, N), order="F"))[:2]
             return ilm.dirichlet_poisson(hcache, fplus)[:2]
 
         step_host()

@@ -168,16 +168,15 @@ k_lu_panel_cluster(int n, int k0, int nb, double* __restrict__ A, int* __restric
     cl.sync();                                       // no CTA leaves while a peer may still read its smem
 }
 
-// ---- panel held in shared memory: each CTA of the cluster (1, 2, 4 or 8 CTAs: the smallest cluster whose slices fit
-// shared memory, so the barriers get cheaper as the factorisation proceeds) keeps its slice of the panel
+// ---- panel held in shared memory: each of the 8 CTAs of the cluster keeps its slice of the panel
 // (rows x nb) in its shared memory for all nb column steps; pivot candidates, the pivot row and the
 // row that is swapped out travel through distributed shared memory.  Per column: one block reduction,
 // two cluster barriers, no global memory traffic.
-__global__ void __launch_bounds__(1024)
+__global__ void __cluster_dims__(PANEL_CTAS, 1, 1) __launch_bounds__(1024)
 k_lu_panel_smem(int n, int k0, int nb, int ldp, double* __restrict__ A, int* __restrict__ ipiv) {
     extern __shared__ double P[];                    // [ldp][nb] column-major slice
     cg::cluster_group cl = cg::this_cluster();
-    const int rank = (int)cl.block_rank(), ncta = (int)cl.num_blocks();      // cluster size chosen at launch (1, 2, 4 or 8)
+    const int rank = (int)cl.block_rank();
     __shared__ double s_val[32];
     __shared__ int s_idx[32];
     __shared__ double c_val;
@@ -185,7 +184,7 @@ k_lu_panel_smem(int n, int k0, int nb, int ldp, double* __restrict__ A, int* __r
     __shared__ int s_piv;
     __shared__ double s_row[NB], s_old[NB];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int len = n - k0, chunk = (len + ncta - 1) / ncta;
+    const int len = n - k0, chunk = (len + PANEL_CTAS - 1) / PANEL_CTAS;
     const int sl0 = k0 + rank * chunk, sl1 = min(n, sl0 + chunk);
     const int nrow = max(sl1 - sl0, 0);
     for (int c = 0; c < nb; ++c)
@@ -221,7 +220,7 @@ k_lu_panel_smem(int n, int k0, int nb, int ldp, double* __restrict__ A, int* __r
         cl.sync();                                   // (A) candidates in place, previous updates finished
         if (wid == 0) {
             best = -1.0; bi = n;
-            if (lane < ncta) {
+            if (lane < PANEL_CTAS) {
                 best = *cl.map_shared_rank(&c_val, lane);
                 bi = *cl.map_shared_rank(&c_idx, lane);
             }
@@ -470,20 +469,11 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
     for (int k0 = 0; k0 < n; k0 += NB) {
         const int nb = n - k0 < NB ? n - k0 : NB;
         {
-            // smallest cluster (1, 2, 4, 8 CTAs) whose row slices fit shared memory
-            int ncta = 1;
-            while (ncta < PANEL_CTAS && (size_t)(((n - k0 + ncta - 1) / ncta) | 1) * NB * sizeof(double) > 200 * 1024) ncta *= 2;
-            const int chunk = (n - k0 + ncta - 1) / ncta;
+            const int chunk = (n - k0 + PANEL_CTAS - 1) / PANEL_CTAS;
             const int ldp = chunk | 1;
             const size_t smem = (size_t)ldp * NB * sizeof(double);
             if (smem <= 200 * 1024) {
-                cudaLaunchConfig_t cfg{};
-                cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeClusterDimension;
-                attr[0].val.clusterDim.x = ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-                cfg.attrs = attr; cfg.numAttrs = 1;
-                ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_smem, n, k0, nb, ldp, dA, dP));
+                k_lu_panel_smem<<<PANEL_CTAS, 1024, smem, st>>>(n, k0, nb, ldp, dA, dP);
             } else if (n - k0 >= 2048) {
                 k_lu_panel_cluster<<<PANEL_CTAS, 1024, 0, st>>>(n, k0, nb, dA, dP);
             } else {
