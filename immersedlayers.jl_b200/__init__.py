@@ -7,7 +7,11 @@ builders, surface-point solve) over the C ABI of libilm_b200.so
 """
 from . import _lib, bodies, lgf  # noqa: F401
 from . import timemarching  # noqa: F401,E402
+from . import forcing  # noqa: F401,E402
 from ._lib import DimensionMismatch, IlmError, MethodError  # noqa: F401
+from .forcing import (  # noqa: F401,E402
+    AreaForcingModel, AreaRegionCache, ForcingModelAndRegion, LineForcingModel, LineRegionCache, PointForcingModel,
+    PointRegionCache, RigidTransform, SpatialGaussian, apply_forcing)
 from .api import (  # noqa: F401
     EdgeGradient, SurfaceVectorCache, TensorData, create_CL2invCT, create_RTHR, create_RTHR_direct, convolve, stokes_flow, convective_derivative, w_cross_v, create_RTLinvR_direct, neumann_poisson, create_CLinvCT_scalar, create_GLinvD_symm,
     normal_dot_interpolate, normal_interpolate_symm, regularize_normal_dot, regularize_normal_symm,

@@ -43,6 +43,7 @@ _vp, _dp, _ip, _i, _d = C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double
 # name -> (restype, argtypes); every symbol declared in include/ilm_b200.h
 SIGNATURES = {
     "ilm_plan_create": (_i, [C.POINTER(ilm_grid), _i, _dp, _dp, _dp, _dp, _dp, _i, _i, _dp, _i, _d, _d, _vp, C.POINTER(_vp)]),
+    "ilm_plan_create_shared": (_i, [_vp, _i, _dp, _dp, _dp, _dp, _dp, _i, _i, C.POINTER(_vp)]),
     "ilm_plan_update_points": (_i, [_vp, _i, _dp, _dp, _dp, _dp, _dp]),
     "ilm_plan_destroy": (None, [_vp]),
     "ilm_plan_sync": (_i, [_vp]),
@@ -53,6 +54,8 @@ SIGNATURES = {
     "ilm_get_table": (_i, [_vp, _i, C.POINTER(_i), _vp, _dp, _dp]),
     "ilm_regularize": (_i, [_vp, _i, _dp, _dp]),
     "ilm_interpolate": (_i, [_vp, _i, _dp, _dp]),
+    "ilm_forcing_area_add": (_i, [_vp, _i, _dp, _dp, _dp]),
+    "ilm_forcing_line_add": (_i, [_vp, _i, _dp, _dp]),
     "ilm_regularize_normal": (_i, [_vp, _i, _dp, _dp]),
     "ilm_normal_interpolate": (_i, [_vp, _i, _dp, _dp]),
     "ilm_divergence": (_i, [_vp, _dp, _dp]),

@@ -271,7 +271,9 @@ class SurfaceScalarCache:
     normals and arc weights (`points`, `normals`, `areas`)."""
 
     def __init__(self, body, g, scaling=GridScaling, ddftype="yang3", lgf_table=None, c0=None,
-                 device=False, stream=None):
+                 device=False, stream=None, parent=None):
+        """parent = another cache on the same grid: the Laplacian is shared (`L = L`,
+        src/forcing.jl:201-248) through ilm_plan_create_shared; the parent must outlive this cache."""
         self.g = g
         x, y, nx, ny, ds = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)) for a in body[:5]]
         N = x.shape[0]
@@ -285,6 +287,19 @@ class SurfaceScalarCache:
         self.scaling = scaling
         self.ddftype = ddftype
         self.device = bool(device)
+        if ddftype not in L.DDF:
+            raise MethodError(f"unknown ddftype {ddftype!r}")
+        if parent is not None:
+            if (parent.g.NX, parent.g.NY, parent.g.dx, parent.g.I0) != (g.NX, g.NY, g.dx, g.I0):
+                raise DimensionMismatch("a cache that shares the Laplacian must live on the parent's grid")
+            self.parent = parent                  # keeps the parent plan alive
+            self.lap_factor, self.c0 = parent.lap_factor, parent.c0
+            lib = L.load()
+            plan = C.c_void_p()
+            L.check(lib.ilm_plan_create_shared(parent._plan, N, _ptr(x), _ptr(y), _ptr(nx), _ptr(ny), _ptr(ds), L.DDF[ddftype],
+                                               L.GRID_SCALING if scaling == GridScaling else L.INDEX_SCALING, C.byref(plan)))
+            self._plan, self._lib = plan, lib
+            return
         if lgf_table is None:
             lgf_table = _lgf.lgf_table(max(g.NX, g.NY))
         lgf_table = np.asfortranarray(lgf_table, dtype=np.float64)
@@ -297,8 +312,6 @@ class SurfaceScalarCache:
         lib = L.load()
         gs = L.ilm_grid(g.NX, g.NY, g.dx, g.I0[0], g.I0[1])
         plan = C.c_void_p()
-        if ddftype not in L.DDF:
-            raise MethodError(f"unknown ddftype {ddftype!r}")
         st = lib.ilm_plan_create(C.byref(gs), N, _ptr(x), _ptr(y), _ptr(nx), _ptr(ny), _ptr(ds),
                                  L.DDF[ddftype], L.GRID_SCALING if scaling == GridScaling else L.INDEX_SCALING,
                                  _ptr(lgf_table), lgf_table.shape[0], self.c0, self.lap_factor,

@@ -198,6 +198,32 @@ extern "C" int ilm_plan_create(const ilm_grid* grid, int N, const double* x, con
     return ILM_OK;
 }
 
+// SurfaceScalarCache(shape, g; L = L) as the region caches of src/forcing.jl:201-248 build it: same grid and
+// Laplacian as `parent`, other points.  The child aliases the parent's convolution engine (multipliers, twiddles,
+// spectrum buffers) and grid scratch and owns only its point data and tables.
+extern "C" int ilm_plan_create_shared(ilm_plan* parent, int N, const double* x, const double* y, const double* nx,
+                                      const double* ny, const double* ds, int ddf, int scaling, ilm_plan** out) {
+    ILM_CHECK_PLAN(parent);
+    if (!out || N < 0 || (N > 0 && (!x || !y || !nx || !ny || !ds))) { set_error("ilm_plan_create_shared: null argument"); return ILM_EINVAL; }
+    if (ddf < 0 || ddf > ILM_DDF_WITCHHAT || (scaling != ILM_GRID_SCALING && scaling != ILM_INDEX_SCALING)) {
+        set_error("ilm_plan_create_shared: unknown ddf or scaling");
+        return ILM_EINVAL;
+    }
+    ilm_plan* p = new ilm_plan();
+    p->g = parent->g; p->ddf = ddf; p->scaling = scaling; p->c0 = parent->c0; p->lap_factor = parent->lap_factor;
+    p->stream = parent->stream; p->device = parent->device; p->nsm = parent->nsm;
+    p->shared = true;
+    p->Lx = parent->Lx; p->Ly = parent->Ly;
+    p->twx = parent->twx; p->twy = parent->twy; p->wl2y = parent->wl2y; p->wl2x = parent->wl2x;
+    p->conv_scratch = parent->conv_scratch; p->S = parent->S; p->S2 = parent->S2; p->s_cap = parent->s_cap;
+    p->skew_ns = parent->skew_ns; p->kernels = parent->kernels; p->lgf_dev = parent->lgf_dev; p->lgf_ld = parent->lgf_ld;
+    p->g_edges = parent->g_edges; p->g_a = parent->g_a; p->g_b = parent->g_b;
+    const int st = upload_points(p, N, x, y, nx, ny, ds);
+    if (st != ILM_OK || cudaStreamSynchronize(p->stream) != cudaSuccess) { ilm_plan_destroy(p); return st != ILM_OK ? st : ILM_ECUDA; }
+    *out = p;
+    return ILM_OK;
+}
+
 extern "C" int ilm_plan_update_points(ilm_plan* p, int N, const double* x, const double* y, const double* nx,
                                       const double* ny, const double* ds) {
     ILM_CHECK_PLAN(p);
@@ -210,9 +236,12 @@ extern "C" void ilm_plan_destroy(ilm_plan* p) {
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
     for (auto& t : p->tab) free_table(t);
-    conv_free(p);
+    if (!p->shared) {
+        conv_free(p);
+        cudaFree(p->g_edges); cudaFree(p->g_a); cudaFree(p->g_b);
+    }
     cudaFree(p->x); cudaFree(p->y); cudaFree(p->nx); cudaFree(p->ny); cudaFree(p->ds);
-    cudaFree(p->g_edges); cudaFree(p->g_a); cudaFree(p->g_b); cudaFree(p->s_a); cudaFree(p->s_b); cudaFree(p->g_tensor);
+    cudaFree(p->s_a); cudaFree(p->s_b); cudaFree(p->g_tensor);
     for (void* s : p->staging) cudaFree(s);
     delete p;
 }
@@ -275,6 +304,42 @@ extern "C" int ilm_regularize(ilm_plan* p, int layout, const double* f, double* 
     double* dg = io.out(grid, n_layout(p, layout));
     if (io.status) return io.status;
     ILM_TRY(launch_regularize(p, p->tab[layout], df, nullptr, 1.0, dg, true));
+    return io.finish();
+}
+
+// ---------------------------------------------------------------- forcing (src/forcing.jl:456-515)
+// _apply_forcing! on an AreaRegionCache (:456-465): dy .+= str .* mask(region); mask == NULL is the region that
+// spans the whole domain (AreaForcingModel(fcn), :74).  layout: any of ilm_layout (ILM_EDGES for a vector cache).
+extern "C" int ilm_forcing_area_add(ilm_plan* p, int layout, const double* str, const double* mask, double* dy) {
+    ILM_CHECK_PLAN(p);
+    if (layout != ILM_EDGES && !layout_ok(layout)) { set_error("ilm_forcing_area_add: bad layout"); return ILM_EINVAL; }
+    if (!str || !dy) { set_error("ilm_forcing_area_add: null argument"); return ILM_EINVAL; }
+    const size_t n = n_layout(p, layout);
+    Io io(p);
+    const double* ds = io.in(str, n);
+    const double* dm = mask ? io.in(mask, n) : nullptr;
+    double* dd = io.inout(dy, n);
+    if (io.status) return io.status;
+    ILM_TRY(launch_forcing_area(p, ds, dm, dd, n));
+    return io.finish();
+}
+
+// _apply_forcing! on a LineRegionCache / PointRegionCache (:467-494): dy .+= R str, accumulated on the active
+// cells only.  ILM_EDGES: str is VectorData [u; v] of 2N entries.
+extern "C" int ilm_forcing_line_add(ilm_plan* p, int layout, const double* str, double* dy) {
+    ILM_CHECK_PLAN(p);
+    if (layout != ILM_EDGES && !layout_ok(layout)) { set_error("ilm_forcing_line_add: bad layout"); return ILM_EINVAL; }
+    if ((!str && p->N > 0) || !dy) { set_error("ilm_forcing_line_add: null argument"); return ILM_EINVAL; }
+    Io io(p);
+    const double* df = io.in(str, (layout == ILM_EDGES ? 2 : 1) * (size_t)p->N);
+    double* dd = io.inout(dy, n_layout(p, layout));
+    if (io.status) return io.status;
+    if (layout == ILM_EDGES) {
+        ILM_TRY(launch_regularize_add(p, p->tab[ILM_XEDGES], df, dd));
+        ILM_TRY(launch_regularize_add(p, p->tab[ILM_YEDGES], df + p->N, dd + n_edges_u(p)));
+    } else {
+        ILM_TRY(launch_regularize_add(p, p->tab[layout], df, dd));
+    }
     return io.finish();
 }
 

@@ -67,6 +67,7 @@ struct ilm_plan {
     cudaStream_t stream = nullptr;
     int device = 0, nsm = 0;
     long long launches = 0;
+    bool shared = false;            // ilm_plan_create_shared: the convolution engine and the grid scratch belong to the parent
     // surface points (device)
     double *x = nullptr, *y = nullptr, *nx = nullptr, *ny = nullptr, *ds = nullptr;
     int ncap = 0;
@@ -120,6 +121,10 @@ int launch_fill(ilm_plan* p, double* dst, size_t n, double value);
 // out = sum_k wR[cell,k] * (mul ? mul[k] : 1) * sign * f[k]  on active cells (out pre-zeroed unless !zero)
 int launch_regularize(ilm_plan* p, const DevTable& t, const double* f, const double* mul, double sign, double* out,
                       bool zero);
+// dy[cell] += sum_k wR[cell,k] f[k] on the active cells (line / point forcing: no zero-fill, no full-field add)
+int launch_regularize_add(ilm_plan* p, const DevTable& t, const double* f, double* dy);
+// dy += str .* mask (mask may be null: dy += str)
+int launch_forcing_area(ilm_plan* p, const double* str, const double* mask, double* dy, size_t n);
 int launch_interpolate(ilm_plan* p, const DevTable& t, const double* field, double* f);
 // f = a_u*(E_u u) + a_v*(E_v v) with per-point factors (normal / cross products), then / div
 int launch_normal_interpolate(ilm_plan* p, int mode, const double* u, const double* v, double* f, double div);

@@ -93,6 +93,66 @@ __global__ void k_regularize(int ncell, int W2, const int* __restrict__ cell_idx
     out[cell_idx[c]] = sum;
 }
 
+// forcing (src/forcing.jl:475-478, 487-490): the reference regularizes into a zero-filled scratch field and adds
+// the whole field to dy; only the active cells can change, so the sum of each active cell is added in place
+__global__ void k_regularize_add(int ncell, int W2, const int* __restrict__ cell_idx, const int* __restrict__ cell_off,
+                                 const int* __restrict__ ent, const double* __restrict__ wR,
+                                 const double* __restrict__ f, double* __restrict__ dy) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    double sum = 0.0;
+    const int q1 = cell_off[c + 1];
+    for (int q = cell_off[c]; q < q1; ++q) {
+        const int id = ent[q];
+        sum = __dadd_rn(sum, __dmul_rn(wR[id], f[id / W2]));
+    }
+    const int cell = cell_idx[c];
+    dy[cell] = __dadd_rn(dy[cell], sum);
+}
+
+int launch_regularize_add(ilm_plan* p, const DevTable& t, const double* f, double* dy) {
+    if (t.ncell == 0) return ILM_OK;
+    k_regularize_add<<<(t.ncell + 127) / 128, 128, 0, p->stream>>>(t.ncell, t.W * t.W, t.cell_idx, t.cell_off, t.ent, t.wR, f, dy);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// area forcing (src/forcing.jl:463): dy .+= str .* mask (mask == nullptr: the whole domain, dy .+= str)
+__global__ void k_forcing_area(const double* __restrict__ str, const double* __restrict__ mask, double* __restrict__ dy,
+                               size_t n, int vec2) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec2) {
+        const size_t n2 = n >> 1;
+        const double2* s2 = reinterpret_cast<const double2*>(str);
+        const double2* m2 = reinterpret_cast<const double2*>(mask);
+        double2* d2 = reinterpret_cast<double2*>(dy);
+        for (size_t q = i; q < n2; q += stride) {
+            double2 s = s2[q], d = d2[q];
+            if (mask) { const double2 m = m2[q]; s.x = __dmul_rn(s.x, m.x); s.y = __dmul_rn(s.y, m.y); }
+            d.x = __dadd_rn(d.x, s.x);
+            d.y = __dadd_rn(d.y, s.y);
+            d2[q] = d;
+        }
+        if (i == 0 && (n & 1)) dy[n - 1] = __dadd_rn(dy[n - 1], mask ? __dmul_rn(str[n - 1], mask[n - 1]) : str[n - 1]);
+    } else {
+        for (size_t q = i; q < n; q += stride) dy[q] = __dadd_rn(dy[q], mask ? __dmul_rn(str[q], mask[q]) : str[q]);
+    }
+}
+
+int launch_forcing_area(ilm_plan* p, const double* str, const double* mask, double* dy, size_t n) {
+    if (n == 0) return ILM_OK;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(str) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(dy);
+    const int vec2 = (al & 15) == 0;
+    size_t blocks = ((vec2 ? n / 2 : n) + 255) / 256;
+    const size_t cap = (size_t)p->nsm * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_forcing_area<<<(unsigned)blocks, 256, 0, p->stream>>>(str, mask, dy, n, vec2);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
 int launch_regularize(ilm_plan* p, const DevTable& t, const double* f, const double* mul, double sign, double* out,
                       bool zero) {
     if (zero) ILM_TRY(launch_fill(p, out, (size_t)t.mx * t.my, 0.0));

@@ -80,6 +80,14 @@ typedef struct {
 int ilm_plan_create(const ilm_grid* grid, int N, const double* x, const double* y, const double* nx,
                     const double* ny, const double* ds, int ddf, int scaling, const double* lgf, int nlgf,
                     double c0, double lap_factor, void* stream, ilm_plan** plan);
+/* A second cache on the same grid that shares the Laplacian, as `SurfaceScalarCache(shape, g; L = L, ...)` does
+ * in the region caches of src/forcing.jl:201-248 and `PointCollectionCache` (src/cache.jl:269-292: pass nx = ny = 0,
+ * ds = 1, ILM_GRID_SCALING for its weight-1 Regularize).  The child plan aliases the parent's multipliers, twiddle
+ * tables, spectrum buffers and grid scratch and its stream; it owns only its points and DDF tables.  The parent must
+ * outlive the child, kernels added to the parent afterwards are not seen by the child, and calls on parent and
+ * children are serialised by the caller like calls on one plan.                                                  */
+int ilm_plan_create_shared(ilm_plan* parent, int N, const double* x, const double* y, const double* nx,
+                           const double* ny, const double* ds, int ddf, int scaling, ilm_plan** plan);
 /* update_system (src/system.jl:26-50): new body positions, Ghat is kept */
 int ilm_plan_update_points(ilm_plan* plan, int N, const double* x, const double* y, const double* nx,
                            const double* ny, const double* ds);
@@ -100,6 +108,13 @@ int ilm_get_table(ilm_plan* plan, int layout, int* W, int64_t* idx, double* wR, 
 /* ---- regularize! / interpolate! (src/surface_operators.jl:13-88) ---------- */
 int ilm_regularize(ilm_plan* plan, int layout, const double* f, double* grid);
 int ilm_interpolate(ilm_plan* plan, int layout, const double* grid, double* f);
+/* ---- forcing regions: _apply_forcing! (src/forcing.jl:456-515) --------------
+ * area region (:456-465): dy .+= str .* mask, one fused sweep (32 B per point; mask = NULL: whole domain, 24 B);
+ * line / point region (:467-494): dy .+= R str accumulated on the cells under the DDF windows only (the reference
+ * zero-fills a scratch field, regularizes into it and adds the whole field).  layout: ilm_layout incl. ILM_EDGES
+ * (str = VectorData [u; v]).  dy is updated in place.                                                          */
+int ilm_forcing_area_add(ilm_plan* plan, int layout, const double* str, const double* mask, double* dy);
+int ilm_forcing_line_add(ilm_plan* plan, int layout, const double* str, double* dy);
 /* regularize_normal!, regularize_normal_cross! (:98-103, :150-162) : Edges <- ScalarData */
 int ilm_regularize_normal(ilm_plan* plan, int mode, const double* f, double* edges);
 /* normal_interpolate!, normal_cross_interpolate! (:228-233, :270-291) : ScalarData <- Edges */

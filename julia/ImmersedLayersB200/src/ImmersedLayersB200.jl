@@ -193,4 +193,28 @@ convective_derivative!(udu::Edges{Primal}, u::Edges{Primal}, c::B200Cache, extra
 w_cross_v!(vw::Edges{Primal}, w::Nodes{Dual}, v::Edges{Primal}, c::B200Cache, extra=nothing) =
     (check(ccall((:ilm_w_cross_v, lib), Cint, (Ptr{Cvoid}, PD, PD, PD), c.plan, w.data, v.data, vw.data)); vw)
 
+# ---- forcing regions (src/forcing.jl): region caches share the base cache's Laplacian (`L = L`, :201-248)
+"""
+    B200Cache(region::BasicILMCache, parent::B200Cache; ddftype)
+
+Device plan for a region cache built with the parent's `L` (`AreaRegionCache`, `LineRegionCache`): aliases the
+parent's multipliers and scratch (ilm_plan_create_shared).  The parent must outlive it.
+"""
+function B200Cache(cache::BasicILMCache{N,SCA}, parent::B200Cache; ddftype=CartesianGrids.Yang3) where {N,SCA}
+    pts, nrm, ds = points(cache), normals(cache), areas(cache)
+    plan = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ilm_plan_create_shared, lib), Cint,
+        (Ptr{Cvoid}, Cint, PD, PD, PD, PD, PD, Cint, Cint, Ref{Ptr{Cvoid}}),
+        parent.plan, N, pts.u, pts.v, nrm.u, nrm.v, ds.data, DDF[ddftype], SCA == GridScaling ? 0 : 1, plan))
+    c = B200Cache{N,SCA,typeof(cache)}(cache, plan[], cache.gdata_cache isa Edges)
+    finalizer(x -> ccall((:ilm_plan_destroy, lib), Cvoid, (Ptr{Cvoid},), x.plan), c)
+    return c
+end
+# _apply_forcing! bodies (src/forcing.jl:456-494): dy .+= str .* mask   and   dy .+= R str
+forcing_area_add!(dy::GridData, str::GridData, msk::Union{GridData,Nothing}, c::B200Cache) =
+    (check(ccall((:ilm_forcing_area_add, lib), Cint, (Ptr{Cvoid}, Cint, PD, PD, PD), c.plan, layout(dy), str.data,
+                 msk === nothing ? C_NULL : msk.data, dy.data)); dy)
+forcing_line_add!(dy::GridData, str::PointData, c::B200Cache) =
+    (check(ccall((:ilm_forcing_line_add, lib), Cint, (Ptr{Cvoid}, Cint, PD, PD), c.plan, layout(dy), str.data, dy.data)); dy)
+
 end # module

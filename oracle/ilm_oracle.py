@@ -1058,3 +1058,26 @@ def convective_derivative_dual(grid, u, v, w, div=1.0):
     out = grid_interpolate(grid, cu * gx, YEDGE, DUAL) + grid_interpolate(grid, cv * gy, XEDGE, DUAL)
     return out / div
 
+
+
+# --------------------------------------------------------------------------
+# forcing regions (src/forcing.jl:456-515)
+# --------------------------------------------------------------------------
+def point_collection_table(grid, x, y, kind, ddf="yang3"):
+    """PointCollectionCache's regop (src/cache.jl:269-292, 312-313): Regularize(X, dx, I0 = origin, ddftype) with the
+    default weight 1 and no symmetry, i.e. wR = ddf ddf / dx^2."""
+    x = np.asarray(x, float)
+    return build_table(grid, x, np.asarray(y, float), np.ones_like(x), kind, ddf, GRID_SCALING)
+
+
+def forcing_area(dy, strength, mask=None):
+    """_apply_forcing! on an AreaRegionCache (src/forcing.jl:456-465): dy .+= str .* mask; the whole-domain region
+    has mask = ones (_get_mask! on a cache without points, src/surface_operators.jl:873-876)."""
+    prod = strength if mask is None else strength * mask
+    return dy + prod
+
+
+def forcing_line(dy, tab, strength):
+    """_apply_forcing! on a LineRegionCache / PointRegionCache (src/forcing.jl:467-494): fill!(gdata_cache, 0);
+    regularize!(gdata_cache, str); dy .+= gdata_cache."""
+    return dy + regularize(tab, strength)

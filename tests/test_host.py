@@ -298,3 +298,36 @@ def test_julia_shim_binds_only_declared_symbols():
         assert re.search(r"\b%s\s*\(" % sym, header), sym
     also = set(re.findall(r"\(:(ilm_[a-z_A-Z0-9]+), lib\)", open(os.path.join(ROOT, "INTEGRATION.md")).read()))
     assert also and all(s in L.SIGNATURES for s in also)
+
+
+def test_forcing_host_logic():
+    """RigidTransform algebra, model constructors and the generated field (src/forcing.jl:14-138, 293-325); no GPU."""
+    import ilm_b200 as ilm
+    from ilm_b200 import forcing as F
+    tr = ilm.RigidTransform((1.0, 2.0), 0.3)
+    ident = tr * tr.inv()
+    assert abs(ident.x) < 1e-15 and abs(ident.y) < 1e-15 and ident.angle == 0.0
+    body = ilm.bodies.rectangle(0.5, 0.25, 0.05)
+    moved = ilm.RigidTransform((-1.0, -1.0), np.pi / 4)(body)
+    assert np.abs(moved[2] ** 2 + moved[3] ** 2 - 1).max() < 1e-14 and np.array_equal(moved[4], body[4])
+    assert abs(np.sum(moved[0] * moved[2] * moved[4]) - 0.5) < 1e-12            # area is invariant
+    back = ilm.RigidTransform((-1.0, -1.0), np.pi / 4).inv()(moved)
+    assert np.abs(back[0] - body[0]).max() < 1e-14 and np.abs(back[3] - body[3]).max() < 1e-14
+    x, y = (ilm.RigidTransform((0.5, 0.0), np.pi / 2) * ilm.RigidTransform((1.0, 0.0), 0.0))(np.array([1.0]), np.array([0.0]))
+    assert abs(x[0] - 0.5) < 1e-15 and abs(y[0] - 2.0) < 1e-15                 # b first, then a
+
+    def fcn(*a):
+        pass
+
+    m = ilm.AreaForcingModel(fcn)
+    assert m.shape is None and m.transform is None
+    m = ilm.PointForcingModel((np.zeros(2), np.zeros(2)), fcn, ddftype="m4prime")
+    assert isinstance(m.transform, ilm.RigidTransform) and m.kwargs == {"ddftype": "m4prime"}
+    with pytest.raises(ilm.MethodError):
+        ilm.LineForcingModel(body, tr, 3.0)
+    assert ilm.ForcingModelAndRegion(None, None) == []
+    g = ilm.PhysicalGrid.centered(128)
+    gf = F.GeneratedField(ilm.Nodes(ilm.Primal, g), ilm.SpatialGaussian(0.5, 0.1, 0, 0, 10), g)
+    assert abs(gf().numpy().sum() * g.dx ** 2 - 10.0) < 1e-6
+    gfe = F.GeneratedField(ilm.Edges(g), [ilm.SpatialGaussian(0.3, 0.3, 0.1, 0, 1), ilm.SpatialGaussian(0.2, 0.4, 0, 0.2, 2)], g)
+    assert abs(gfe().u.sum() * g.dx ** 2 - 1.0) < 1e-6 and abs(gfe().v.sum() * g.dx ** 2 - 2.0) < 1e-6

@@ -439,3 +439,28 @@ def test_convective_terms_on_polynomial_fields():
     wd = px * xd[:, None] + py * yd[None, :]
     out = o.convective_derivative_dual(g, u, v, wd, div=g.dx)
     assert np.abs(out[2:-2, 2:-2] - (a * px + b * py)).max() < 1e-12
+
+
+# ---------------------------------------------------------------- forcing regions (src/forcing.jl, test/surface_ops.jl:445-542)
+def test_forcing_region_restatement(small_cache):
+    c = small_cache
+    g = c.grid
+    shp = o.field_shape(o.PRIMAL, g.NX, g.NY)
+    # point forcing with M4': partition of unity -> sum(dT) dx^2 = sum(str); weights are 1/dx^2
+    px, py = np.array([-1.2, 0.5, 0.013]), np.array([0.5, 0.5, -0.777])
+    strength = np.array([1.0, -1.0, 2.5])
+    tab = o.point_collection_table(g, px, py, o.PRIMAL, "m4prime")
+    d = o.forcing_line(np.zeros(shp), tab, strength)
+    assert abs(d.sum() * g.dx ** 2 - strength.sum()) < 1e-12
+    xg, yg = g.coords(o.PRIMAL)
+    assert abs((d * xg[:, None]).sum() * g.dx ** 2 - (strength * px).sum()) < 1e-12      # first moment of M4'
+    # line forcing on the body's own table: flux * perimeter
+    d = o.forcing_line(np.ones(shp), c.tabs[o.PRIMAL], np.full(c.N, -2.0))
+    assert abs((d - 1.0).sum() * g.dx ** 2 + 2.0 * c.ds.sum()) < 1e-10
+    # area forcing: dy + str * mask; whole-domain region = ones
+    m = c.mask()
+    s = np.random.default_rng(1).standard_normal(shp)
+    dy = np.random.default_rng(2).standard_normal(shp)
+    assert np.array_equal(o.forcing_area(dy, s, m), dy + s * m)
+    assert np.array_equal(o.forcing_area(dy, s), o.forcing_area(dy, s, np.ones(shp)))
+    assert abs(o.forcing_area(np.zeros(shp), np.full(shp, 3.0), m).sum() * g.dx ** 2 - 3.0 * np.pi) < 6e-2
