@@ -8,6 +8,13 @@ builders, surface-point solve) over the C ABI of libilm_b200.so
 from . import _lib, bodies, lgf  # noqa: F401
 from . import timemarching  # noqa: F401,E402
 from . import forcing  # noqa: F401,E402
+from . import helmholtz  # noqa: F401,E402
+from .helmholtz import (  # noqa: F401,E402
+    ScalarPotentialCache, VectorFieldCache, VectorPotentialCache, curlv_masked_from_masked_curlv, divv_masked_from_masked_divv,
+    masked_curlv_from_curlv_masked, masked_divv_from_divv_masked, potentials_from_masked_fields, scalarpotential_from_divv,
+    scalarpotential_from_masked_divv, scalarpotential_uniformvecfield, vecfield_from_scalarpotential, vecfield_from_vectorpotential,
+    vecfield_helmholtz, vecfield_uniformvecfield, vectorpotential_from_curlv, vectorpotential_from_masked_curlv,
+    vectorpotential_uniformvecfield)
 from ._lib import DimensionMismatch, IlmError, MethodError  # noqa: F401
 from .forcing import (  # noqa: F401,E402
     AreaForcingModel, AreaRegionCache, ForcingModelAndRegion, LineForcingModel, LineRegionCache, PointForcingModel,

@@ -97,6 +97,10 @@ SIGNATURES = {
     "ilm_mask_product": (_i, [_vp, _i, _i, _i, _dp]),
     "ilm_create_schur_vector": (_i, [_vp, _i, _d, _i, _i, _dp]),
     "ilm_create_nRTRn_vector": (_i, [_vp, _d, _dp]),
+    "ilm_helmholtz_potentials": (_i, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "ilm_vecfield_from_potentials": (_i, [_vp, _dp, _dp, _dp, _dp]),
+    "ilm_vecfield_helmholtz": (_i, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "ilm_helmholtz_jump_add": (_i, [_vp, _i, _i, _dp, _dp, _dp]),
     "ilm_convective_derivative_scalar": (_i, [_vp, _dp, _dp, _dp]),
     "ilm_convective_derivative_dual": (_i, [_vp, _dp, _dp, _dp]),
     "ilm_convective_derivative_vector": (_i, [_vp, _dp, _dp, _dp]),

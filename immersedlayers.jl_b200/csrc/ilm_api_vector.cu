@@ -401,3 +401,97 @@ extern "C" int ilm_create_nRTRn_vector(ilm_plan* p, double scale, double* A) {
     }
     return io.finish();
 }
+
+// ---------------------------------------------------------------- Helmholtz decomposition (src/helmholtz.jl)
+namespace {
+// out = in + sign * R (n x dv) on Nodes{Dual} (op = ILM_VS_CROSS) or in + sign * R (n . dv) on Nodes{Primal}
+// (op = ILM_VS_DOT); `in` may alias `out` or be null (zero field).  The reference zero-fills `out`, regularizes,
+// scales by -1 where needed and adds `in` as whole-field sweeps (:84-96, 149-160, 171-181, 186-201, 240-270).
+int jump_add_dev(ilm_plan* p, int op, bool negate, const double* dv, const double* in, double* out) {
+    const Sizes z(p);
+    const size_t n = op == ILM_VS_CROSS ? z.Pd : z.Pn;
+    if (!in) ILM_TRY(launch_fill(p, out, n, 0.0));
+    else if (in != out) ILM_CUDA(cudaMemcpyAsync(out, in, n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    if (p->N == 0 || !dv) return ILM_OK;           // VectorData{0} methods: the field is passed through
+    ILM_TRY(launch_vec_pointwise(p, op == ILM_VS_CROSS ? 0 : 1, dv, p->s_b));
+    return launch_regularize_add(p, p->tab[op == ILM_VS_CROSS ? ILM_NODES_DUAL : ILM_NODES_PRIMAL], p->s_b, out, negate);
+}
+
+// psi = -L^-1 (masked_curlv + R n x [v]) (:84-96, 121-124), phi = L^-1 (masked_divv + R n . [v]) (:186-201, 216-219);
+// both right-hand sides ride ONE complex transform.  Either output may be null.
+int helmholtz_potentials_dev(ilm_plan* p, const double* curlv, const double* divv, const double* dv, double* psi, double* phi) {
+    const Sizes z(p);
+    const int NX = p->g.NX, NY = p->g.NY;
+    if (psi) ILM_TRY(jump_add_dev(p, ILM_VS_CROSS, false, dv, curlv, psi));
+    if (phi) ILM_TRY(jump_add_dev(p, ILM_VS_DOT, false, dv, divv, phi));
+    const FieldRef fpsi{psi, NX, NY}, fphi{phi, NX - 1, NY - 1}, none{nullptr, 0, 0};
+    if (psi && phi) ILM_TRY(conv_apply(p, 0, fpsi, fphi));
+    else if (psi) ILM_TRY(conv_apply(p, 0, fpsi, none));
+    else if (phi) ILM_TRY(conv_apply(p, 0, fphi, none));
+    if (psi) ILM_TRY(launch_scale(p, psi, z.Pd, -1.0));
+    return ILM_OK;
+}
+}  // namespace
+
+/* masked_curlv_from_curlv_masked! (sign -1), curlv_masked_from_masked_curlv! (+1) on Nodes{Dual} with op = ILM_VS_CROSS;
+ * masked_divv_from_divv_masked! (-1), divv_masked_from_masked_divv! (+1) on Nodes{Primal} with op = ILM_VS_DOT */
+extern "C" int ilm_helmholtz_jump_add(ilm_plan* p, int op, int sign, const double* dv, const double* in, double* out) {
+    ILM_VPLAN(p);
+    if ((op != ILM_VS_CROSS && op != ILM_VS_DOT) || (sign != 1 && sign != -1) || !out) { set_error("ilm_helmholtz_jump_add: bad arguments"); return ILM_EINVAL; }
+    const Sizes z(p);
+    const size_t n = op == ILM_VS_CROSS ? z.Pd : z.Pn;
+    Io io(p);
+    const double* ddv = dv ? io.in(dv, 2 * (size_t)p->N) : nullptr;
+    const double* din = (in && in != out) ? io.in(in, n) : nullptr;
+    double* dout = (in == out) ? io.inout(out, n) : io.out(out, n);
+    if (io.status) return io.status;
+    ILM_TRY(jump_add_dev(p, op, sign < 0, ddv, in == out ? dout : din, dout));
+    return io.finish();
+}
+
+extern "C" int ilm_helmholtz_potentials(ilm_plan* p, const double* masked_curlv, const double* masked_divv, const double* dv,
+                                        double* psi, double* phi) {
+    ILM_VPLAN(p);
+    if (!psi && !phi) { set_error("ilm_helmholtz_potentials: no output"); return ILM_EINVAL; }
+    const Sizes z(p);
+    Io io(p);
+    const double* dc = (psi && masked_curlv) ? io.in(masked_curlv, z.Pd) : nullptr;
+    const double* dd = (phi && masked_divv) ? io.in(masked_divv, z.Pn) : nullptr;
+    const double* ddv = dv ? io.in(dv, 2 * (size_t)p->N) : nullptr;
+    double* dpsi = psi ? io.out(psi, z.Pd) : nullptr;
+    double* dphi = phi ? io.out(phi, z.Pn) : nullptr;
+    if (io.status) return io.status;
+    ILM_TRY(helmholtz_potentials_dev(p, dc, dd, ddv, dpsi, dphi));
+    return io.finish();
+}
+
+extern "C" int ilm_vecfield_from_potentials(ilm_plan* p, const double* psi, const double* phi, const double* vp, double* v) {
+    ILM_VPLAN(p);
+    if (!v) { set_error("ilm_vecfield_from_potentials: null output"); return ILM_EINVAL; }
+    const Sizes z(p);
+    Io io(p);
+    const double* dpsi = psi ? io.in(psi, z.Pd) : nullptr;
+    const double* dphi = phi ? io.in(phi, z.Pn) : nullptr;
+    const double* dvp = vp ? io.in(vp, z.ne) : nullptr;
+    double* dvv = io.out(v, z.ne);
+    if (io.status) return io.status;
+    ILM_TRY(launch_vecfield_from_potentials(p, dpsi, dphi, dvp, dvp ? dvp + z.nu : nullptr, dvv, dvv + z.nu, deriv_div(p)));
+    return io.finish();
+}
+
+extern "C" int ilm_vecfield_helmholtz(ilm_plan* p, const double* masked_curlv, const double* masked_divv, const double* dv,
+                                      const double* vp, double* v) {
+    ILM_VPLAN(p);
+    if (!v) { set_error("ilm_vecfield_helmholtz: null output"); return ILM_EINVAL; }
+    const Sizes z(p);
+    Io io(p);
+    const double* dc = masked_curlv ? io.in(masked_curlv, z.Pd) : nullptr;
+    const double* dd = masked_divv ? io.in(masked_divv, z.Pn) : nullptr;
+    const double* ddv = dv ? io.in(dv, 2 * (size_t)p->N) : nullptr;
+    const double* dvp = vp ? io.in(vp, z.ne) : nullptr;
+    double* dvv = io.out(v, z.ne);
+    if (io.status) return io.status;
+    ILM_TRY(helmholtz_potentials_dev(p, dc, dd, ddv, p->g_a, p->g_b));
+    ILM_TRY(launch_vecfield_from_potentials(p, p->g_a, p->g_b, dvp, dvp ? dvp + z.nu : nullptr, dvv, dvv + z.nu, deriv_div(p)));
+    return io.finish();
+}

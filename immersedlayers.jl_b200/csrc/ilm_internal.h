@@ -121,8 +121,9 @@ int launch_fill(ilm_plan* p, double* dst, size_t n, double value);
 // out = sum_k wR[cell,k] * (mul ? mul[k] : 1) * sign * f[k]  on active cells (out pre-zeroed unless !zero)
 int launch_regularize(ilm_plan* p, const DevTable& t, const double* f, const double* mul, double sign, double* out,
                       bool zero);
-// dy[cell] += sum_k wR[cell,k] f[k] on the active cells (line / point forcing: no zero-fill, no full-field add)
-int launch_regularize_add(ilm_plan* p, const DevTable& t, const double* f, double* dy);
+// dy[cell] += (negate ? -1 : 1) * sum_k wR[cell,k] f[k] on the active cells (line / point forcing, Helmholtz jump
+// terms: no zero-fill, no full-field add)
+int launch_regularize_add(ilm_plan* p, const DevTable& t, const double* f, double* dy, bool negate = false);
 // dy += str .* mask (mask may be null: dy += str)
 int launch_forcing_area(ilm_plan* p, const double* str, const double* mask, double* dy, size_t n);
 int launch_interpolate(ilm_plan* p, const DevTable& t, const double* field, double* f);
@@ -136,6 +137,9 @@ int launch_normal_interpolate_fused(ilm_plan* p, int op, int mode, const double*
 int launch_regularize_normal_unit(ilm_plan* p, int mode, int col, double* u, double* v, int flo, int fhi, bool fill);
 int launch_grad(ilm_plan* p, const double* in, double* u, double* v, double div);
 int launch_curl_n2e(ilm_plan* p, const double* s, double* u, double* v, double div);
+// v = curl(psi) + grad(phi) [+ vp], any of psi / phi / vp may be null (Helmholtz recomposition, one sweep)
+int launch_vecfield_from_potentials(ilm_plan* p, const double* psi, const double* phi, const double* vpu, const double* vpv,
+                                    double* u, double* v, double div);
 int launch_curl_e2n(ilm_plan* p, const double* u, const double* v, double* w, double div, int ybeg = -1, int yend = -1);
 int launch_laplacian(ilm_plan* p, const double* in, double* out, int mx, int my, double factor);
 int launch_scale_store_column(ilm_plan* p, const double* src, double* dst, int n, double scale);

@@ -97,7 +97,7 @@ __global__ void k_regularize(int ncell, int W2, const int* __restrict__ cell_idx
 // the whole field to dy; only the active cells can change, so the sum of each active cell is added in place
 __global__ void k_regularize_add(int ncell, int W2, const int* __restrict__ cell_idx, const int* __restrict__ cell_off,
                                  const int* __restrict__ ent, const double* __restrict__ wR,
-                                 const double* __restrict__ f, double* __restrict__ dy) {
+                                 const double* __restrict__ f, double* __restrict__ dy, int negate) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
     double sum = 0.0;
@@ -107,12 +107,13 @@ __global__ void k_regularize_add(int ncell, int W2, const int* __restrict__ cell
         sum = __dadd_rn(sum, __dmul_rn(wR[id], f[id / W2]));
     }
     const int cell = cell_idx[c];
-    dy[cell] = __dadd_rn(dy[cell], sum);
+    dy[cell] = __dadd_rn(dy[cell], negate ? -sum : sum);
 }
 
-int launch_regularize_add(ilm_plan* p, const DevTable& t, const double* f, double* dy) {
+int launch_regularize_add(ilm_plan* p, const DevTable& t, const double* f, double* dy, bool negate) {
     if (t.ncell == 0) return ILM_OK;
-    k_regularize_add<<<(t.ncell + 127) / 128, 128, 0, p->stream>>>(t.ncell, t.W * t.W, t.cell_idx, t.cell_off, t.ent, t.wR, f, dy);
+    k_regularize_add<<<(t.ncell + 127) / 128, 128, 0, p->stream>>>(t.ncell, t.W * t.W, t.cell_idx, t.cell_off, t.ent, t.wR, f, dy,
+                                                                    negate ? 1 : 0);
     ILM_LAUNCHED(p);
     return ILM_OK;
 }
@@ -475,6 +476,54 @@ __global__ void k_curl_n2e(int NX, int NY, const double* __restrict__ s, double*
 }
 int launch_curl_n2e(ilm_plan* p, const double* s, double* u, double* v, double div) {
     k_curl_n2e<<<st_grid(p->g.NX, p->g.NY), ST_BX, 0, p->stream>>>(p->g.NX, p->g.NY, s, u, v, div);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// Helmholtz recomposition (src/helmholtz.jl:285-307): v = curl(psi) + grad(phi) [+ vp] in one sweep; every term is
+// rounded as in k_curl_n2e / k_grad and the sums are taken in the reference's order (v .= vpsi .+ vphi; v .+= vp)
+__global__ void k_vecfield_from_potentials(int NX, int NY, const double* __restrict__ psi, const double* __restrict__ phi,
+                                           const double* __restrict__ vpu, const double* __restrict__ vpv,
+                                           double* __restrict__ u, double* __restrict__ v, double div) {
+    const int x = blockIdx.x * ST_BX + threadIdx.x;
+    const int y0 = blockIdx.y * ST_ROWS;
+    if (x >= NX) return;
+    const int mp = NX - 1;
+    double sc = (psi && y0 < NY) ? psi[(size_t)y0 * NX + x] : 0.0;
+    double pprev = (phi && y0 >= 1 && y0 - 1 < NY - 1 && x < mp) ? phi[(size_t)(y0 - 1) * mp + x] : 0.0;
+#pragma unroll
+    for (int r = 0; r < ST_ROWS; ++r) {
+        const int y = y0 + r;
+        if (y >= NY) break;
+        const bool prow = y < NY - 1;
+        const double pc = (phi && prow && x < mp) ? phi[(size_t)y * mp + x] : 0.0;
+        if (x < mp) {   // v row
+            const double cv = psi ? (sc - psi[(size_t)y * NX + x + 1]) / div : 0.0;
+            double gv = 0.0;
+            if (phi && y >= 1 && y <= NY - 2) gv = (pc - pprev) / div;
+            double val = __dadd_rn(cv, gv);
+            if (vpv) val = __dadd_rn(val, vpv[(size_t)y * mp + x]);
+            v[(size_t)y * mp + x] = val;
+        }
+        if (prow) {     // u row
+            double cu = 0.0;
+            if (psi) {
+                const double sn = psi[(size_t)(y + 1) * NX + x];
+                cu = (sn - sc) / div;
+                sc = sn;
+            }
+            double gu = 0.0;
+            if (phi && x >= 1 && x <= NX - 2) gu = (pc - phi[(size_t)y * mp + x - 1]) / div;
+            double val = __dadd_rn(cu, gu);
+            if (vpu) val = __dadd_rn(val, vpu[(size_t)y * NX + x]);
+            u[(size_t)y * NX + x] = val;
+        }
+        pprev = pc;
+    }
+}
+int launch_vecfield_from_potentials(ilm_plan* p, const double* psi, const double* phi, const double* vpu, const double* vpv,
+                                    double* u, double* v, double div) {
+    k_vecfield_from_potentials<<<st_grid(p->g.NX, p->g.NY), ST_BX, 0, p->stream>>>(p->g.NX, p->g.NY, psi, phi, vpu, vpv, u, v, div);
     ILM_LAUNCHED(p);
     return ILM_OK;
 }

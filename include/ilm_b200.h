@@ -227,6 +227,26 @@ enum ilm_schur_vector {
 int ilm_create_schur_vector(ilm_plan* plan, int which, double scale, int col_begin, int col_end, double* A);
 int ilm_create_nRTRn_vector(ilm_plan* plan, double scale, double* A);
 
+/* ---- Helmholtz decomposition on the vector cache (src/helmholtz.jl) -------------------------------
+ * v = curl(psi) + grad(phi) + vp with  L psi = -(masked curl v + R n x [v]),  L phi = masked div v + R n . [v].
+ * ilm_helmholtz_potentials = vectorpotential_from_masked_curlv! (:84-96) and scalarpotential_from_masked_divv!
+ * (:186-201) together: the jump terms are accumulated on the cells under the DDF windows and the TWO inverse
+ * Laplacians ride one complex transform.  psi: Nodes{Dual}, phi: Nodes{Primal}; either output may be NULL (then its
+ * right-hand side is ignored); a NULL right-hand side or NULL dv is a zero field (vectorpotential_from_curlv!,
+ * scalarpotential_from_divv!, :114-124, 216-219).
+ * ilm_vecfield_from_potentials = vecfield_from_vectorpotential! + vecfield_from_scalarpotential! + the sum of
+ * vecfield_helmholtz! (:130-134, 228-232, 285-307) as one sweep; psi, phi, vp may be NULL.
+ * ilm_vecfield_helmholtz = vecfield_helmholtz! (:285-307) end to end (potentials stay in plan scratch).
+ * ilm_helmholtz_jump_add: out = in + sign * R (n x dv) (op ILM_VS_CROSS, Nodes{Dual}) or in + sign * R (n . dv)
+ * (op ILM_VS_DOT, Nodes{Primal}): masked_curlv_from_curlv_masked! / masked_divv_from_divv_masked! (sign -1, :149-160,
+ * 240-252) and curlv_masked_from_masked_curlv! / divv_masked_from_masked_divv! (sign +1, :171-181, 263-274).       */
+int ilm_helmholtz_potentials(ilm_plan* plan, const double* masked_curlv, const double* masked_divv, const double* dv,
+                             double* psi, double* phi);
+int ilm_vecfield_from_potentials(ilm_plan* plan, const double* psi, const double* phi, const double* vp_edges, double* v_edges);
+int ilm_vecfield_helmholtz(ilm_plan* plan, const double* masked_curlv, const double* masked_divv, const double* dv,
+                           const double* vp_edges, double* v_edges);
+int ilm_helmholtz_jump_add(ilm_plan* plan, int op, int sign, const double* dv, const double* in, double* out);
+
 /* kernels launched by the three ilm_dense_* entry points since load (bench bookkeeping) */
 int64_t ilm_dense_launch_count(void);
 

@@ -217,4 +217,30 @@ forcing_area_add!(dy::GridData, str::GridData, msk::Union{GridData,Nothing}, c::
 forcing_line_add!(dy::GridData, str::PointData, c::B200Cache) =
     (check(ccall((:ilm_forcing_line_add, lib), Cint, (Ptr{Cvoid}, Cint, PD, PD), c.plan, layout(dy), str.data, dy.data)); dy)
 
+# ---- Helmholtz decomposition (src/helmholtz.jl); the extra caches (wcache, dcache, veccache) become unused
+import ImmersedLayers: vectorpotential_from_masked_curlv!, scalarpotential_from_masked_divv!, vectorpotential_from_curlv!,
+    scalarpotential_from_divv!, vecfield_from_vectorpotential!, vecfield_from_scalarpotential!, vecfield_helmholtz!,
+    masked_curlv_from_curlv_masked!, curlv_masked_from_masked_curlv!, masked_divv_from_divv_masked!, divv_masked_from_masked_divv!
+_pot(c, curlv, divv, dv, psi, phi) = check(ccall((:ilm_helmholtz_potentials, lib), Cint, (Ptr{Cvoid}, PD, PD, PD, PD, PD),
+                                                 c.plan, curlv, divv, dv, psi, phi))
+vectorpotential_from_masked_curlv!(ψ::Nodes{Dual}, curlv::Nodes{Dual}, dv::VectorData, c::B200Cache, wcache=nothing) =
+    (_pot(c, curlv.data, C_NULL, dv.data, ψ.data, C_NULL); ψ)                                   # :84-96
+scalarpotential_from_masked_divv!(ϕ::Nodes{Primal}, divv::Nodes{Primal}, dv::VectorData, c::B200Cache, dcache=nothing) =
+    (_pot(c, C_NULL, divv.data, dv.data, C_NULL, ϕ.data); ϕ)                                    # :186-201
+vectorpotential_from_curlv!(ψ::Nodes{Dual}, curlv::Nodes{Dual}, c::B200Cache) = (_pot(c, curlv.data, C_NULL, C_NULL, ψ.data, C_NULL); ψ)
+scalarpotential_from_divv!(ϕ::Nodes{Primal}, divv::Nodes{Primal}, c::B200Cache) = (_pot(c, C_NULL, divv.data, C_NULL, C_NULL, ϕ.data); ϕ)
+_vfp(c, psi, phi, vp, v) = check(ccall((:ilm_vecfield_from_potentials, lib), Cint, (Ptr{Cvoid}, PD, PD, PD, PD), c.plan, psi, phi, vp, v))
+vecfield_from_vectorpotential!(v::Edges{Primal}, ψ::Nodes{Dual}, c::B200Cache) = (_vfp(c, ψ.data, C_NULL, C_NULL, v.data); v)
+vecfield_from_scalarpotential!(v::Edges{Primal}, ϕ::Nodes{Primal}, c::B200Cache) = (_vfp(c, C_NULL, ϕ.data, C_NULL, v.data); v)
+vecfield_helmholtz!(v::Edges{Primal}, curlv::Nodes{Dual}, divv::Nodes{Primal}, dv::VectorData, vp::Union{Edges{Primal},Nothing},
+                    c::B200Cache, veccache=nothing) =                                             # :285-307
+    (check(ccall((:ilm_vecfield_helmholtz, lib), Cint, (Ptr{Cvoid}, PD, PD, PD, PD, PD), c.plan, curlv.data, divv.data, dv.data,
+                 vp === nothing ? C_NULL : vp.data, v.data)); v)
+_jump(c, op, sign, dv, fin, fout) = check(ccall((:ilm_helmholtz_jump_add, lib), Cint, (Ptr{Cvoid}, Cint, Cint, PD, PD, PD),
+                                                c.plan, op, sign, dv.data, fin.data, fout.data))
+masked_curlv_from_curlv_masked!(mw::Nodes{Dual}, w::Nodes{Dual}, dv::VectorData, c::B200Cache, wcache=nothing) = (_jump(c, 0, -1, dv, w, mw); mw)
+curlv_masked_from_masked_curlv!(w::Nodes{Dual}, mw::Nodes{Dual}, dv::VectorData, c::B200Cache, wcache=nothing) = (_jump(c, 0, 1, dv, mw, w); w)
+masked_divv_from_divv_masked!(md::Nodes{Primal}, d::Nodes{Primal}, dv::VectorData, c::B200Cache, dcache=nothing) = (_jump(c, 1, -1, dv, d, md); md)
+divv_masked_from_masked_divv!(d::Nodes{Primal}, md::Nodes{Primal}, dv::VectorData, c::B200Cache, dcache=nothing) = (_jump(c, 1, 1, dv, md, d); d)
+
 end # module

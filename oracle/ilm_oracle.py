@@ -1081,3 +1081,44 @@ def forcing_line(dy, tab, strength):
     """_apply_forcing! on a LineRegionCache / PointRegionCache (src/forcing.jl:467-494): fill!(gdata_cache, 0);
     regularize!(gdata_cache, str); dy .+= gdata_cache."""
     return dy + regularize(tab, strength)
+
+
+# --------------------------------------------------------------------------
+# Helmholtz decomposition on a VectorCache (src/helmholtz.jl)
+# --------------------------------------------------------------------------
+def helmholtz_jump(vc, op, sign, dvu, dvv, field):
+    """op 'cross' on Nodes{Dual}: field + sign * R (n x dv); op 'dot' on Nodes{Primal}: field + sign * R (n . dv).
+    sign -1: masked_curlv_from_curlv_masked! / masked_divv_from_divv_masked! (src/helmholtz.jl:149-160, 240-252: fill,
+    regularize, .*= -1, .+= field); sign +1: curlv_masked_from_masked_curlv! / divv_masked_from_masked_divv!
+    (:171-181, 263-274).  A cache without points passes the field through (VectorData{0} methods)."""
+    if vc.N == 0:
+        return np.array(field, copy=True)
+    r = vc.regularize_normal_cross_v(dvu, dvv) if op == "cross" else vc.regularize_normal_dot_v(dvu, dvv)
+    if sign < 0:
+        r = r * -1.0
+    return r + field
+
+
+def helmholtz_potentials(vc, curlv, divv, dvu, dvv):
+    """vectorpotential_from_masked_curlv! (src/helmholtz.jl:84-96, 114-124): stemp = R n x dv; stemp .+= curlv;
+    psi = -(L^-1 stemp).  scalarpotential_from_masked_divv! (:186-201, 216-219): phi = L^-1 (R n . dv + divv)."""
+    psi = vc.inverse_laplacian(helmholtz_jump(vc, "cross", +1, dvu, dvv, curlv)) * -1.0
+    phi = vc.inverse_laplacian(helmholtz_jump(vc, "dot", +1, dvu, dvv, divv))
+    return psi, phi
+
+
+def vecfield_from_potentials(vc, psi, phi, vp=None):
+    """vecfield_from_vectorpotential! (curl!, :130-134), vecfield_from_scalarpotential! (grad!, :228-232) and the sum
+    of vecfield_helmholtz! (:300-304): v .= vpsi .+ vphi; v .+= vp."""
+    cu, cv = vc.curl_n2e(psi)
+    gu, gv = vc.grad(phi)
+    u, v = cu + gu, cv + gv
+    if vp is not None:
+        u, v = u + vp[0], v + vp[1]
+    return u, v
+
+
+def vecfield_helmholtz(vc, curlv, divv, dvu, dvv, vp=None):
+    """vecfield_helmholtz! (src/helmholtz.jl:285-307)."""
+    psi, phi = helmholtz_potentials(vc, curlv, divv, dvu, dvv)
+    return vecfield_from_potentials(vc, psi, phi, vp)
