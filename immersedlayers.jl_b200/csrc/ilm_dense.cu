@@ -8,6 +8,7 @@
 // A22 -= A21 * A12 on the FP64 tensor pipe (mma.sync.m8n8k4.f64, "DMMA").
 #include <cooperative_groups.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "ilm_internal.h"
@@ -433,6 +434,125 @@ __global__ void __launch_bounds__(1024) k_getrs(int n, const double* __restrict_
     for (int i = tid; i < n; i += 1024) b[i] = sb[i];
 }
 
+// ---- getrs on a thread-block cluster: the single-CTA kernel above reads the whole factorisation through one SM
+// and fetches every diagonal block with 32 dependent global loads.  Here 8 CTAs own the 32-row blocks of the
+// right-hand side cyclically (block k belongs to CTA k % 8); per block step the owner's first warp solves the 32
+// unknowns from registers (diagonal block loaded one step ahead, coalesced), pushes them into every peer's shared
+// memory (DSMEM), and after ONE cluster barrier all CTAs update their own rows.  Arithmetic order is that of k_getrs.
+constexpr int SOLVE_CTAS = 8, SOLVE_THREADS = 512, SOLVE_WARPS = SOLVE_THREADS / 32;
+// acc = sum_c LU[(k0+c)*n + r] * xk[c] in ascending c, the loads issued 16 at a time ahead of the dependent sum
+__device__ __forceinline__ double getrs_row_dot(const double* __restrict__ LU, int n, int k0, int nb, int r, const double* xk) {
+    double acc = 0.0;
+#pragma unroll
+    for (int h = 0; h < NB; h += 16) {
+        double a[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a[c] = (h + c < nb) ? LU[(size_t)(k0 + h + c) * n + r] : 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+            if (h + c < nb) acc += a[c] * xk[h + c];
+    }
+    return acc;
+}
+__global__ void __cluster_dims__(SOLVE_CTAS, 1, 1) __launch_bounds__(SOLVE_THREADS)
+k_getrs_cluster(int n, const double* __restrict__ LU, const int* __restrict__ ipiv, double* __restrict__ b) {
+    extern __shared__ double sb[];                   // n doubles; only this CTA's own rows are kept current
+    __shared__ double xs[2][NB];                     // solved block of step s in xs[s & 1] (written by its owner)
+    __shared__ double sd[NB][NB + 1];                // diagonal block of this CTA's next step: sd[j][i] = LU[k0+i, k0+j]
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int* sp = reinterpret_cast<int*>(sb + n);         // pivots staged in shared memory (the interchanges are serial)
+    for (int i = tid; i < n; i += SOLVE_THREADS) { sb[i] = b[i]; sp[i] = ipiv[i] - 1; }
+    __syncthreads();
+    if (tid == 0)
+        for (int i = 0; i < n; ++i) {
+            const int pv = sp[i];
+            if (pv != i) { const double t = sb[i]; sb[i] = sb[pv]; sb[pv] = t; }
+        }
+    const int nblk = (n + NB - 1) / NB;
+    // the diagonal block of step k is staged one step ahead by warp 1 of its owner (coalesced column loads)
+    auto stage_diag = [&](int k) {
+        const int k0 = k * NB;
+#pragma unroll
+        for (int h = 0; h < NB; h += 16) {
+            double a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = (k0 + h + j < n && k0 + lane < n) ? LU[(size_t)(k0 + h + j) * n + k0 + lane] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sd[h + j][lane] = a[j];
+        }
+    };
+    auto push = [&](int s, int k0, int nb, double x) {
+        if (lane < nb) {
+            sb[k0 + lane] = x;
+#pragma unroll
+            for (int p = 0; p < SOLVE_CTAS; ++p) cl.map_shared_rank(&xs[s & 1][0], p)[lane] = x;
+        }
+    };
+    int s = 0;
+    // forward: unit lower
+    if (rank == 0 && wid == 1) stage_diag(0);
+    __syncthreads();
+    for (int k = 0; k < nblk; ++k, ++s) {
+        const int k0 = k * NB, nb = min(NB, n - k0);
+        const bool mine = rank == k % SOLVE_CTAS, next_mine = k + 1 < nblk && rank == (k + 1) % SOLVE_CTAS;
+        if (mine && wid == 0) {
+            double x = lane < nb ? sb[k0 + lane] : 0.0;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const double xj = __shfl_sync(0xffffffffu, x, j);
+                if (lane > j && lane < nb) x -= sd[j][lane] * xj;
+            }
+            push(s, k0, nb, x);
+        }
+        cl.sync();
+        if (next_mine && wid == 1) stage_diag(k + 1);           // warp 0 of this CTA is past its use of sd (it is not the owner of k)
+        const double* xk = xs[s & 1];
+        int kb = k + 1 + ((rank - (k + 1)) % SOLVE_CTAS + SOLVE_CTAS) % SOLVE_CTAS;      // first own block after k
+        // the owner of the next step updates that block first, with the warp that does not stage the diagonal
+        for (kb += ((wid + SOLVE_WARPS - 2) % SOLVE_WARPS) * SOLVE_CTAS; kb < nblk; kb += SOLVE_WARPS * SOLVE_CTAS) {
+            const int r = kb * NB + lane;
+            if (r < n) sb[r] -= getrs_row_dot(LU, n, k0, nb, r, xk);
+        }
+        __syncthreads();
+    }
+    // backward: upper
+    if (rank == (nblk - 1) % SOLVE_CTAS && wid == 1) stage_diag(nblk - 1);
+    __syncthreads();
+    for (int k = nblk - 1; k >= 0; --k, ++s) {
+        const int k0 = k * NB, nb = min(NB, n - k0);
+        const bool mine = rank == k % SOLVE_CTAS, next_mine = k >= 1 && rank == (k - 1) % SOLVE_CTAS;
+        if (mine && wid == 0) {
+            double x = lane < nb ? sb[k0 + lane] : 0.0;
+#pragma unroll
+            for (int j = NB - 1; j >= 0; --j) {
+                if (j < nb) {
+                    if (lane == j) x = x / sd[j][lane];
+                    const double xj = __shfl_sync(0xffffffffu, x, j);
+                    if (lane < j) x -= sd[j][lane] * xj;
+                }
+            }
+            push(s, k0, nb, x);
+        }
+        cl.sync();
+        if (next_mine && wid == 1) stage_diag(k - 1);
+        const double* xk = xs[s & 1];
+        // own blocks below k, the highest (the next steps' blocks) first
+        const int nown = k > rank ? (k - rank + SOLVE_CTAS - 1) / SOLVE_CTAS : 0;        // own blocks kb = rank + q*CTAS < k
+        for (int q = nown - 1 - (wid + SOLVE_WARPS - 2) % SOLVE_WARPS; q >= 0; q -= SOLVE_WARPS) {
+            const int kb = rank + q * SOLVE_CTAS;
+            const int r = kb * NB + lane;
+            sb[r] -= getrs_row_dot(LU, n, k0, nb, r, xk);
+        }
+        __syncthreads();
+    }
+    for (int kb = rank; kb < nblk; kb += SOLVE_CTAS)
+        for (int i = tid; i < NB; i += SOLVE_THREADS)
+            if (kb * NB + i < n) b[kb * NB + i] = sb[kb * NB + i];
+    cl.sync();                                       // no CTA leaves while a peer may still write its xs
+}
+
 // ---- y = C x in two deterministic stages
 constexpr int MV_CH = 16;
 __global__ void k_gemv_part(int n, const double* __restrict__ C, const double* __restrict__ x, double* __restrict__ part) {
@@ -498,15 +618,22 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
 extern "C" int ilm_dense_solve(int n, const double* LU, const int* ipiv, int nrhs, double* B, void* stream) {
     if (n < 0 || nrhs < 0 || (n > 0 && nrhs > 0 && (!LU || !ipiv || !B))) { set_error("ilm_dense_solve: bad arguments"); return ILM_EINVAL; }
     if (n == 0 || nrhs == 0) return ILM_OK;
-    if ((size_t)n * sizeof(double) > 200 * 1024) { set_error("ilm_dense_solve: n too large for the shared-memory solve"); return ILM_ESIZE; }
+    if ((size_t)n * (sizeof(double) + sizeof(int)) > 200 * 1024) { set_error("ilm_dense_solve: n too large for the shared-memory solve"); return ILM_ESIZE; }
     DenseIo io(stream);
     double* dLU = nullptr; int* dP = nullptr; double* dB = nullptr;
     ILM_TRY(io.map(const_cast<double*>(LU), (size_t)n * n, true, false, &dLU));
     ILM_TRY(io.map(const_cast<int*>(ipiv), (size_t)n, true, false, &dP));
     ILM_TRY(io.map(B, (size_t)n * nrhs, true, true, &dB));
     const size_t smem = (size_t)n * sizeof(double);
-    ILM_CUDA(cudaFuncSetAttribute(k_getrs, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    for (int r = 0; r < nrhs; ++r) k_getrs<<<1, 1024, smem, io.st>>>(n, dLU, dP, dB + (size_t)r * n);
+    static const bool single_cta = getenv("ILM_GETRS_SINGLE_CTA") != nullptr;      // the first version, kept for comparison
+    if (n < 4 * NB || single_cta) {
+        ILM_CUDA(cudaFuncSetAttribute(k_getrs, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        for (int r = 0; r < nrhs; ++r) k_getrs<<<1, 1024, smem, io.st>>>(n, dLU, dP, dB + (size_t)r * n);
+    } else {
+        ILM_CUDA(cudaFuncSetAttribute(k_getrs_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        for (int r = 0; r < nrhs; ++r)
+            k_getrs_cluster<<<SOLVE_CTAS, SOLVE_THREADS, smem + (size_t)n * sizeof(int), io.st>>>(n, dLU, dP, dB + (size_t)r * n);
+    }
     g_dense_launches += nrhs;
     ILM_CUDA(cudaGetLastError());
     return io.finish();

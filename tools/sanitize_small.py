@@ -49,3 +49,28 @@ for NX, NY in ((48, 48), (40, 600), (4200, 24), (24, 4200)):          # the last
     virtual_slab_solve(dc, [L.NODES_PRIMAL], [wf], 3)
     ilm.create_RTLinvR(dc, cols=(0, 4))
 print("done (round-1 additions)")
+
+# ---- forcing regions and Helmholtz decomposition (shared plans, accumulate-gather, fused recomposition)
+for dev in (False, True):
+    gg = ilm.PhysicalGrid(61, 53, 0.07, (30, 26))
+    bb = ilm.bodies.circle(1.0, 0.1)
+    scc = ilm.SurfaceScalarCache(bb, gg, device=dev)
+    vcc = ilm.SurfaceVectorCache(bb, gg, device=dev, parent=scc)
+    shp = ilm.bodies.rectangle(0.4, 0.3, 0.1, center=(0.2, -0.1))
+    fcs = ilm.ForcingModelAndRegion([ilm.AreaForcingModel(shp, ilm.RigidTransform((0.1, 0.0), 0.3), lambda s, T, t, fr, pp: s.fill(1.0)),
+                                     ilm.LineForcingModel(shp, ilm.RigidTransform(), lambda s, T, t, fr, pp: s.fill(-2.0)),
+                                     ilm.AreaForcingModel(lambda s, T, t, fr, pp: s.fill(0.5)),
+                                     ilm.PointForcingModel((np.array([-1.9, 0.5]), np.array([0.5, 1.7])),
+                                                           lambda s, T, t, fr, pp: s.fill(1.0), ddftype="m4prime")], scc)
+    ilm.apply_forcing(scc.zeros_grid(), scc.zeros_grid(), None, 0.0, fcs, None, None, scc)
+    fcv = ilm.ForcingModelAndRegion([ilm.AreaForcingModel(shp, ilm.RigidTransform(), lambda s, T, t, fr, pp: s.fill(1.0)),
+                                     ilm.LineForcingModel(shp, ilm.RigidTransform(), lambda s, T, t, fr, pp: s.fill(-2.0))], vcc)
+    ilm.apply_forcing(vcc.zeros_grid(), vcc.zeros_grid(), None, 0.0, fcv, None, None, vcc)
+    ww, dd, dvv = vcc.zeros_gridcurl().fill(1.0), vcc.zeros_griddiv().fill(-1.0), vcc.zeros_surface().fill(0.3)
+    vv = vcc.zeros_grid()
+    ilm.vecfield_helmholtz(vv, ww, dd, dvv, (1.0, 0.5), vcc)
+    ilm.masked_curlv_from_curlv_masked(ww, ww, dvv, vcc)
+    ilm.divv_masked_from_masked_divv(vcc.zeros_griddiv(), dd, dvv, vcc)
+    ilm.vectorpotential_from_curlv(vcc.zeros_gridcurl(), ww, vcc)
+    ilm.scalarpotential_from_masked_divv(vcc.zeros_griddiv(), dd, dvv, vcc)
+print("done (forcing, helmholtz)")
