@@ -268,25 +268,150 @@ k_lu_panel_smem(int n, int k0, int nb, int ldp, double* __restrict__ A, int* __r
     cl.sync();                                       // no CTA leaves while a peer may still read its smem
 }
 
-// apply the panel's row interchanges to the columns outside the panel
-__global__ void k_lu_swap(int n, int k0, int nb, double* __restrict__ A, const int* __restrict__ ipiv) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n - nb) return;
-    if (c >= k0) c += nb;
+// ---- panel held in REGISTERS: one thread per row (512 threads x 8 or 16 CTAs of one cluster), the thread keeps
+// its nb <= 32 panel entries in registers for all column steps.  Per column: a warp + CTA arg-max, the CTA's
+// candidate row and the current top row are pushed into every peer's shared memory (DSMEM, double-buffered by
+// column parity), ONE cluster barrier, then every thread picks the winner locally, swaps in registers and
+// updates its row.  (The shared-memory version above needs two cluster barriers and four block barriers per column.)
+constexpr int PR_THREADS = 512, PR_WARPS = PR_THREADS / 32, PR_MAXC = 16;
+struct PanelXchg {
+    double val[2][PR_MAXC];
+    int idx[2][PR_MAXC];
+    double rows[2][PR_MAXC][NB];
+    double old[2][NB];
+};
+__device__ __forceinline__ void argmax_step(double& best, int& bi, int off) {
+    const double ov = __shfl_down_sync(0xffffffffu, best, off);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+}
+__global__ void __launch_bounds__(PR_THREADS) k_lu_panel_regs(int n, int k0, int nb, double* __restrict__ A, int* __restrict__ ipiv) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    __shared__ PanelXchg X;
+    __shared__ double s_val[PR_WARPS];
+    __shared__ int s_idx[PR_WARPS];
+    __shared__ double c_row[NB], o_row[NB];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int row = k0 + rank * PR_THREADS + tid;
+    const bool has = row < n;
+    double a[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) a[c] = (has && c < nb) ? A[(size_t)(k0 + c) * n + row] : 0.0;
+#pragma unroll
+    for (int jj = 0; jj < NB; ++jj) {
+        if (jj < nb) {
+            const int col = k0 + jj, buf = jj & 1;
+            // candidate of this warp, of this CTA (every warp reduces the warp candidates redundantly)
+            const bool active = has && row >= col;
+            double best = active ? fabs(a[jj]) : -1.0;
+            int bi = active ? row : n;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) argmax_step(best, bi, off);
+            if (lane == 0) { s_val[wid] = best; s_idx[wid] = bi; }
+            __syncthreads();
+            best = lane < PR_WARPS ? s_val[lane] : -1.0;
+            bi = lane < PR_WARPS ? s_idx[lane] : n;
+#pragma unroll
+            for (int off = PR_WARPS / 2; off > 0; off >>= 1) argmax_step(best, bi, off);
+            const double cta_val = __shfl_sync(0xffffffffu, best, 0);
+            const int cta_piv = __shfl_sync(0xffffffffu, bi, 0);
+            if (has && row == cta_piv) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) c_row[c] = a[c];
+            }
+            if (has && row == col) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) o_row[c] = a[c];
+            }
+            __syncthreads();
+            if (wid < C) {                               // warp p pushes to peer p
+                PanelXchg* Xp = cl.map_shared_rank(&X, wid);
+                Xp->rows[buf][rank][lane] = c_row[lane];
+                if (lane == 0) { Xp->val[buf][rank] = cta_val; Xp->idx[buf][rank] = cta_piv; }
+                if (rank == (col - k0) / PR_THREADS) Xp->old[buf][lane] = o_row[lane];
+            }
+            cl.sync();
+            double bv = -1.0;
+            int piv = n, pw = 0;
+            for (int p = 0; p < C; ++p) {
+                const double v = X.val[buf][p];
+                const int i = X.idx[buf][p];
+                if (v > bv || (v == bv && i < piv)) { bv = v; piv = i; pw = p; }
+            }
+            const double* prow = X.rows[buf][pw];
+            if (piv != col) {
+                if (has && row == piv) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) a[c] = X.old[buf][c];
+                } else if (has && row == col) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) a[c] = prow[c];
+                }
+            }
+            if (rank == 0 && tid == 0) ipiv[col] = piv + 1;
+            if (has && row > col) {
+                const double l = a[jj] / prow[jj];
+                a[jj] = l;
+#pragma unroll
+                for (int c = jj + 1; c < NB; ++c) a[c] = a[c] - l * prow[c];
+            }
+        }
+    }
+    if (has) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+            if (c < nb) A[(size_t)(k0 + c) * n + row] = a[c];
+    }
+    cl.sync();                                       // no CTA leaves while a peer may still write its shared memory
+}
+
+static int launch_panel_regs(int n, int k0, int nb, double* A, int* ipiv, cudaStream_t st) {
+    const int rows = n - k0;
+    const int C = rows <= 8 * PR_THREADS ? 8 : 16;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C);
+    cfg.blockDim = dim3(PR_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_regs, n, k0, nb, A, ipiv));
+    return ILM_OK;
+}
+
+// apply the row interchanges of pivots [r0, r0+nr) to the columns [cbeg, cend) except [skip0, skip1)
+__global__ void k_lu_swap(int n, int r0, int nr, double* __restrict__ A, const int* __restrict__ ipiv, int cbeg, int cend,
+                          int skip0, int skip1) {
+    int c = cbeg + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= skip0) c += skip1 - skip0;
+    if (c >= cend) return;
     double* col = A + (size_t)c * n;
-    for (int jj = 0; jj < nb; ++jj) {
-        const int r = k0 + jj, pv = ipiv[r] - 1;
+    for (int jj = 0; jj < nr; ++jj) {
+        const int r = r0 + jj, pv = ipiv[r] - 1;
         if (pv != r) { const double t = col[r]; col[r] = col[pv]; col[pv] = t; }
     }
 }
+static int launch_swap(int n, int r0, int nr, double* A, const int* ipiv, int cbeg, int cend, int skip0, int skip1, cudaStream_t st) {
+    if (skip0 < cbeg) skip0 = cbeg;
+    if (skip1 > cend) skip1 = cend;
+    if (skip1 < skip0) skip1 = skip0;
+    const int ncol = (cend - cbeg) - (skip1 - skip0);
+    if (ncol <= 0 || nr <= 0) return ILM_OK;
+    k_lu_swap<<<(ncol + 127) / 128, 128, 0, st>>>(n, r0, nr, A, ipiv, cbeg, cend, skip0, skip1);
+    g_dense_launches++;
+    return ILM_OK;
+}
 
 // block row: A12 <- L11^-1 A12 (unit lower triangular nb x nb)
-__global__ void k_lu_trsm(int n, int k0, int nb, double* __restrict__ A) {
+__global__ void k_lu_trsm(int n, int k0, int nb, double* __restrict__ A, int cbeg, int cend) {
     __shared__ double L11[NB][NB + 1];
     for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) L11[i % nb][i / nb] = A[(size_t)(k0 + i / nb) * n + k0 + i % nb];
     __syncthreads();
-    const int c = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
+    const int c = cbeg + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cend) return;
     double* col = A + (size_t)c * n + k0;
     double x[NB];
 #pragma unroll
@@ -301,7 +426,7 @@ __global__ void k_lu_trsm(int n, int k0, int nb, double* __restrict__ A) {
         if (i < nb) col[i] = x[i];
 }
 
-// trailing update C -= A * B, K = kk (<= 32); 64x64 tile per CTA, 4 warps of 32x32, DMMA m8n8k4
+// trailing update C -= A * B, K = kk; 64x64 tile per CTA, 4 warps of 32x32, DMMA m8n8k4
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -314,15 +439,6 @@ __global__ void __launch_bounds__(128) k_lu_gemm(int M, int Nc, int kk, const do
     __shared__ double Bs[64 * LDB];      // Bs[n][k]
     const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 64 * NB; i += 128) {
-        const int m = i & 63, k = i >> 6;
-        As[k * LDA + m] = (m0 + m < M && k < kk) ? A[(size_t)k * ld + m0 + m] : 0.0;
-    }
-    for (int i = tid; i < 64 * NB; i += 128) {
-        const int k = i & (NB - 1), nn = i >> 5;
-        Bs[nn * LDB + k] = (n0 + nn < Nc && k < kk) ? B[(size_t)(n0 + nn) * ld + k] : 0.0;
-    }
-    __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
     double acc[4][4][2];
@@ -330,17 +446,29 @@ __global__ void __launch_bounds__(128) k_lu_gemm(int M, int Nc, int kk, const do
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kc = 0; kc < kk; kc += NB) {            // K in chunks of 32 (one chunk for the inner updates)
+        if (kc) __syncthreads();
+        for (int i = tid; i < 64 * NB; i += 128) {
+            const int m = i & 63, k = i >> 6;
+            As[k * LDA + m] = (m0 + m < M && kc + k < kk) ? A[(size_t)(kc + k) * ld + m0 + m] : 0.0;
+        }
+        for (int i = tid; i < 64 * NB; i += 128) {
+            const int k = i & (NB - 1), nn = i >> 5;
+            Bs[nn * LDB + k] = (n0 + nn < Nc && kc + k < kk) ? B[(size_t)(n0 + nn) * ld + kc + k] : 0.0;
+        }
+        __syncthreads();
 #pragma unroll
-    for (int k = 0; k < NB; k += 4) {
-        double a[4], b[4];
+        for (int k = 0; k < NB; k += 4) {
+            double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = As[(k + t) * LDA + wm + 8 * i + g];
+            for (int i = 0; i < 4; ++i) a[i] = As[(k + t) * LDA + wm + 8 * i + g];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Bs[(wn + 8 * j + g) * LDB + k + t];
+            for (int j = 0; j < 4; ++j) b[j] = Bs[(wn + 8 * j + g) * LDB + k + t];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -586,9 +714,17 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
     ILM_TRY(io.map(ipiv, (size_t)n, false, true, &dP));
     cudaStream_t st = io.st;
     ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    for (int k0 = 0; k0 < n; k0 += NB) {
-        const int nb = n - k0 < NB ? n - k0 : NB;
-        {
+    static const bool panel_smem_only = getenv("ILM_LU_PANEL_SMEM") != nullptr;     // the shared-memory panel, kept for comparison
+    // outer block (multiple of NB).  Measured on B200: 128 pays from n ~ 4000 on (N = 4593: 30.2 -> 28.9 ms); below, the
+    // extra small launches of the inner updates cost more than the saved sweeps (N = 2295: 9.8 -> 12.2 ms), and
+    // KB = NB is the plain right-looking algorithm.
+    static const int kb_env = getenv("ILM_LU_OUTER") ? atoi(getenv("ILM_LU_OUTER")) : 0;
+    const int KB = kb_env >= NB ? (kb_env / NB) * NB : (n >= 4096 ? 128 : NB);
+    ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_regs, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    auto panel = [&](int k0, int nb) -> int {
+        if (!panel_smem_only && n - k0 <= PR_MAXC * PR_THREADS) {
+            ILM_TRY(launch_panel_regs(n, k0, nb, dA, dP, st));
+        } else {
             const int chunk = (n - k0 + PANEL_CTAS - 1) / PANEL_CTAS;
             const int ldp = chunk | 1;
             const size_t smem = (size_t)ldp * NB * sizeof(double);
@@ -600,16 +736,43 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
                 k_lu_panel<<<1, 1024, 0, st>>>(n, k0, nb, dA, dP);
             }
         }
-        if (n - nb > 0) k_lu_swap<<<(n - nb + 127) / 128, 128, 0, st>>>(n, k0, nb, dA, dP);
-        const int rem = n - k0 - nb;
-        if (rem > 0) {
-            k_lu_trsm<<<(rem + 63) / 64, 64, 0, st>>>(n, k0, nb, dA);
-            dim3 grid((rem + 63) / 64, (rem + 63) / 64);
-            k_lu_gemm<<<grid, 128, 0, st>>>(rem, rem, nb, dA + (size_t)k0 * n + k0 + nb, dA + (size_t)(k0 + nb) * n + k0,
-                                            dA + (size_t)(k0 + nb) * n + k0 + nb, n);
-            g_dense_launches += 2;
+        g_dense_launches++;
+        return ILM_OK;
+    };
+    // C[M x Nc] -= A[M x K] * B[K x Nc], all inside dA (leading dimension n)
+    auto gemm = [&](int M, int Nc, int K, int arow, int acol, int brow, int bcol) {
+        if (M <= 0 || Nc <= 0 || K <= 0) return;
+        dim3 grid((M + 63) / 64, (Nc + 63) / 64);
+        k_lu_gemm<<<grid, 128, 0, st>>>(M, Nc, K, dA + (size_t)acol * n + arow, dA + (size_t)bcol * n + brow,
+                                        dA + (size_t)bcol * n + arow, n);
+        g_dense_launches++;
+    };
+    auto trsm = [&](int k0, int nb, int cbeg, int cend) {
+        if (cend <= cbeg) return;
+        k_lu_trsm<<<(cend - cbeg + 63) / 64, 64, 0, st>>>(n, k0, nb, dA, cbeg, cend);
+        g_dense_launches++;
+    };
+    // Two-level right-looking LU: 32-wide register panels inside an outer block of KB columns; the inner trailing
+    // updates touch only the outer block, the rest of the matrix gets ONE rank-KB update per outer block (the matrix
+    // is read and written n/KB times instead of n/32 times).
+    for (int K0 = 0; K0 < n; K0 += KB) {
+        const int kb = n - K0 < KB ? n - K0 : KB, Kend = K0 + kb;
+        for (int k0 = K0; k0 < Kend; k0 += NB) {
+            const int nb = Kend - k0 < NB ? Kend - k0 : NB;
+            ILM_TRY(panel(k0, nb));
+            ILM_TRY(launch_swap(n, k0, nb, dA, dP, K0, Kend, k0, k0 + nb, st));
+            trsm(k0, nb, k0 + nb, Kend);
+            gemm(n - (k0 + nb), Kend - (k0 + nb), nb, k0 + nb, k0, k0, k0 + nb);
         }
-        g_dense_launches += 2;
+        ILM_TRY(launch_swap(n, K0, kb, dA, dP, 0, n, K0, Kend, st));
+        if (n - Kend > 0) {
+            for (int k0 = K0; k0 < Kend; k0 += NB) {       // block row: A12 <- L11^-1 A12
+                const int nb = Kend - k0 < NB ? Kend - k0 : NB;
+                trsm(k0, nb, Kend, n);
+                gemm(Kend - (k0 + nb), n - Kend, nb, k0 + nb, k0, k0, Kend);
+            }
+            gemm(n - Kend, n - Kend, kb, Kend, K0, K0, Kend);
+        }
     }
     ILM_CUDA(cudaGetLastError());
     return io.finish();
