@@ -325,7 +325,7 @@ def test_schur_reference_physics(c1):
     assert abs(np.linalg.svd(ilm.create_nRTRn(cache), compute_uv=False).max() * dx / 0.04 - 11) < 1.5
 
 
-@pytest.mark.parametrize("n", [1, 7, 32, 33, 141, 500, 2500])
+@pytest.mark.parametrize("n", [1, 7, 32, 33, 141, 500, 2500, 4200])     # 4200: 16-CTA register panels, rank-128 updates
 def test_dense_lu_solve(n):
     import scipy.linalg
     rng = np.random.default_rng(n)
