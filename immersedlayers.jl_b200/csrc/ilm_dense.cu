@@ -298,6 +298,9 @@ __global__ void __launch_bounds__(PR_THREADS) k_lu_panel_regs(int n, int k0, int
     double a[NB];
 #pragma unroll
     for (int c = 0; c < NB; ++c) a[c] = (has && c < nb) ? A[(size_t)(k0 + c) * n + row] : 0.0;
+    // The column loop is fully unrolled so that the register array is addressed statically.  (A rolled loop with
+    // predicated static indices was tried because ncu shows 58 % no_instructions stalls on the ~250 KB of straight-line
+    // code: it spills 400 B per thread at the 128-register cap and is slower, N = 4593: 23.9 -> 31.5 ms.)
 #pragma unroll
     for (int jj = 0; jj < NB; ++jj) {
         if (jj < nb) {
@@ -470,6 +473,18 @@ __global__ void __launch_bounds__(128) k_lu_gemm(int M, int Nc, int kk, const do
                 for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
+    // all 32 loads of C are issued before the first store: a load-subtract-store per element would serialise 32
+    // global round trips (the compiler cannot move a load of C above an earlier store to C)
+    double cv[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = m0 + wm + 8 * i + g;
+            const int c = n0 + wn + 8 * j + 2 * t;
+            cv[i][j][0] = (r < M && c < Nc) ? C[(size_t)c * ld + r] : 0.0;
+            cv[i][j][1] = (r < M && c + 1 < Nc) ? C[(size_t)(c + 1) * ld + r] : 0.0;
+        }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -477,8 +492,8 @@ __global__ void __launch_bounds__(128) k_lu_gemm(int M, int Nc, int kk, const do
             const int r = m0 + wm + 8 * i + g;
             const int c = n0 + wn + 8 * j + 2 * t;
             if (r < M) {
-                if (c < Nc) C[(size_t)c * ld + r] -= acc[i][j][0];
-                if (c + 1 < Nc) C[(size_t)(c + 1) * ld + r] -= acc[i][j][1];
+                if (c < Nc) C[(size_t)c * ld + r] = cv[i][j][0] - acc[i][j][0];
+                if (c + 1 < Nc) C[(size_t)(c + 1) * ld + r] = cv[i][j][1] - acc[i][j][1];
             }
         }
 }
@@ -715,11 +730,12 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
     cudaStream_t st = io.st;
     ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     static const bool panel_smem_only = getenv("ILM_LU_PANEL_SMEM") != nullptr;     // the shared-memory panel, kept for comparison
-    // outer block (multiple of NB).  Measured on B200: 128 pays from n ~ 4000 on (N = 4593: 30.2 -> 28.9 ms); below, the
-    // extra small launches of the inner updates cost more than the saved sweeps (N = 2295: 9.8 -> 12.2 ms), and
-    // KB = NB is the plain right-looking algorithm.
+    // outer block (multiple of NB; ILM_LU_OUTER).  KB = NB is the plain right-looking algorithm and the default:
+    // measured on B200 after the trailing update stopped serialising its read-modify-write of C, rank-32 updates
+    // beat the two-level form at every size tried (N = 4593: 23.9 vs 25.2 ms with KB = 128; N = 2295: 8.6 vs 10.6 ms)
+    // -- the inner trsm / gemm / swap launches on a <= 128-column block cost more than the saved sweeps.
     static const int kb_env = getenv("ILM_LU_OUTER") ? atoi(getenv("ILM_LU_OUTER")) : 0;
-    const int KB = kb_env >= NB ? (kb_env / NB) * NB : (n >= 4096 ? 128 : NB);
+    const int KB = kb_env >= NB ? (kb_env / NB) * NB : NB;
     ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_regs, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     auto panel = [&](int k0, int nb) -> int {
         if (!panel_smem_only && n - k0 <= PR_MAXC * PR_THREADS) {
