@@ -170,3 +170,88 @@ class DirichletHeatConduction:
         for _ in range(nsteps):
             self.step()
         return self.T
+
+
+class UnboundedHeatConduction:
+    """Transient heat conduction in an unbounded domain with area / line / point heating and convection by a
+    prescribed velocity field (test/literate/heatconduction-unbounded.jl):
+
+        dT/dt = kappa L T - N(v, T) + q(T, t)
+
+    with N = convective_derivative! (src/grid_operators.jl:258-264) and q = apply_forcing! (src/forcing.jl:375-396).
+    There is no constraint, so LiskaIFHERK reduces to the integrating-factor Runge-Kutta recursion
+
+        w_j <- H_i w_j (j < i),  q <- H_i q,  w_i = H_i r(U_{i-1}, t_{i-1}),  U_i = q + dt sum_{j<=i} a_ij w_j
+
+    (same tableau and integrating factors H_i = exp(kappa L (c_i - c_{i-1}) dt) as DirichletHeatConduction).
+    forcing_models: list of Area/Line/PointForcingModel; velocity_model(vel, t, cache, phys_params) fills the Edges
+    `vel` (the "convection velocity model" of the reference's forcing Dict, :128-134); dt = min(Fo dx^2/kappa,
+    CFL dx/Umax) as the reference's timestep function (:212-222) when `umax` is given."""
+
+    def __init__(self, g, kappa, forcing_models=None, velocity_model=None, phys_params=None, fourier=1.0, cfl=None, umax=None,
+                 tableau=LISKA_IFHERK, lgf_table=None, device=True, ddftype="yang3"):
+        from . import forcing as F
+        self.g, self.kappa, self.phys_params = g, float(kappa), phys_params
+        self.dt = timestep_fourier(g, kappa, fourier)
+        if cfl is not None and umax:
+            self.dt = min(self.dt, cfl * g.dx / umax)
+        self.tab_a, self.tab_c = tableau["a"], tableau["c"]
+        z = np.zeros(0)
+        self.cache = api.SurfaceScalarCache((z, z, z, z, z), g, ddftype=ddftype, lgf_table=lgf_table, device=device)
+        self.fcache = F.ForcingModelAndRegion(forcing_models, self.cache)
+        self.velocity_model = velocity_model
+        self.vel = self.cache.zeros_gridgrad()
+        self.T = self.cache.zeros_grid()
+        self.t, self.nstep = 0.0, 0
+        self.stage_a, self.kernel_id = [], {}
+        prev = 0.0
+        for c in self.tab_c:
+            self.stage_a.append(self.kappa / g.dx ** 2 * (c - prev) * self.dt)
+            prev = c
+        for a in sorted(set(self.stage_a)):
+            self.kernel_id[a] = self.cache.add_kernel(_lgf.intfact_table(a, max(g.NX, g.NY))) if a > 0.0 else None
+
+    def _apply_H(self, w, a):
+        if self.kernel_id[a] is not None:
+            api.convolve(w, self.cache, self.kernel_id[a])
+        return w
+
+    def ode_rhs(self, T, t):
+        """heatconduction_rhs! (heatconduction-unbounded.jl:143-158): dT = -N(v, T) + forcing."""
+        from . import forcing as F
+        dT = self.cache.zeros_grid()
+        if self.velocity_model is not None:
+            self.velocity_model(self.vel, t, self.cache, self.phys_params)
+            api.convective_derivative(dT, self.vel, T, self.cache)
+            api._iscale(dT, -1.0)
+        tmp = self.cache.zeros_grid()
+        F.apply_forcing(tmp, T, None, t, self.fcache, self.phys_params, None, self.cache)
+        api._iadd(dT, tmp)
+        return dT
+
+    def step(self):
+        dt, t0 = self.dt, self.t
+        q, w, U = self.T, [], self.T
+        c_prev = 0.0
+        for i, c in enumerate(self.tab_c):
+            a_i = self.stage_a[i]
+            r = self.ode_rhs(U, t0 + c_prev * dt)          # before q (= U_0 = T_n at the first stage) is propagated in place
+            for wj in w:
+                self._apply_H(wj, a_i)
+            self._apply_H(q, a_i)
+            w.append(self._apply_H(r, a_i))
+            U = self.cache.zeros_grid()
+            U.data[...] = q.data
+            for j in range(i + 1):
+                if self.tab_a[i][j] != 0.0:
+                    U.data += (dt * self.tab_a[i][j]) * w[j].data
+            c_prev = c
+        self.T = U
+        self.t = t0 + dt
+        self.nstep += 1
+        return self.T
+
+    def run(self, nsteps):
+        for _ in range(nsteps):
+            self.step()
+        return self.T

@@ -1122,3 +1122,28 @@ def vecfield_helmholtz(vc, curlv, divv, dvu, dvv, vp=None):
     """vecfield_helmholtz! (src/helmholtz.jl:285-307)."""
     psi, phi = helmholtz_potentials(vc, curlv, divv, dvu, dvv)
     return vecfield_from_potentials(vc, psi, phi, vp)
+
+
+def heat_unbounded_step(grid, T, t, dt, kappa, tab_a, tab_c, tables, rhs):
+    """One integrating-factor Runge-Kutta step of the unconstrained heat equation dT/dt = kappa L T + rhs(T, t)
+    (test/literate/heatconduction-unbounded.jl: ode_rhs = heatconduction_rhs!, lin_op = heat_L, no constraint), the
+    recursion of heat_ifherk_step without the multiplier.  PARITY UNPINNED (un-vendored integrator)."""
+    def H(wf, a):
+        return wf if a == 0.0 else ConvPlan(tables[a][:grid.NX, :grid.NY]).apply(wf)
+
+    q = T.copy()
+    U = T
+    w = []
+    c_prev = 0.0
+    for i, c in enumerate(tab_c):
+        a = kappa / grid.dx ** 2 * (c - c_prev) * dt
+        r = rhs(U, t + c_prev * dt)
+        w = [H(wj, a) for wj in w]
+        q = H(q, a)
+        w.append(H(r, a))
+        U = q.copy()
+        for j in range(i + 1):
+            if tab_a[i][j] != 0.0:
+                U = U + (dt * tab_a[i][j]) * w[j]
+        c_prev = c
+    return U

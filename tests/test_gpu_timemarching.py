@@ -77,3 +77,66 @@ def test_heat_conduction_reaches_the_prescribed_interior_temperature():
     c = g.I0[0] - 1
     assert abs(T[c, c] - 1.0) < 0.05
     assert abs(T[2, 2]) < 0.05
+
+
+@pytest.mark.parametrize("device", [True, False])
+def test_unbounded_heat_conduction_with_forcing_and_convection(device):
+    """test/literate/heatconduction-unbounded.jl scaled down: a square line heater, an oscillating area heater with
+    heat transfer to the local temperature, a point source, convection by a rigid rotation; IF-RK steps against the
+    oracle's restatement (forcing + convective term + integrating factor through the CUDA path)."""
+    g = ilm.PhysicalGrid.centered(128)
+    G = ilm.lgf.lgf_table(128)
+    og = o.Grid(g.NX, g.NY, g.dx, g.I0)
+    pp = {"diffusivity": 0.005, "angular velocity": 0.5, "lineheater_flux": -2.0, "areaheater_freq": 1.0,
+          "areaheater_temp": 2.0, "areaheater_coeff": 100.0}
+    ds = 1.4 * g.dx
+    square, tr1 = ilm.bodies.rectangle(0.25, 0.25, ds), ilm.RigidTransform((0.0, 1.0), 0.0)
+    disc, tr2 = ilm.bodies.circle(0.2, ds), ilm.RigidTransform((0.0, -0.5), 0.0)
+    pts = (np.array([0.8]), np.array([0.1]))
+
+    def model1(sig, T, t, fr, p):
+        sig.fill(p["lineheater_flux"])
+
+    def model2(sig, T, t, fr, p):
+        sig.set(p["areaheater_coeff"] * (p["areaheater_temp"] * np.cos(2 * np.pi * p["areaheater_freq"] * t) - T.numpy()))
+
+    def model3(sig, T, t, fr, p):
+        sig.fill(5.0)
+
+    xu, yu = g.coordinates(ilm._lib.XEDGES)
+    xv, yv = g.coordinates(ilm._lib.YEDGES)
+    Om = pp["angular velocity"]
+    uu = np.broadcast_to(-Om * yu[None, :], (xu.size, yu.size))
+    vv = np.broadcast_to(Om * xv[:, None], (xv.size, yv.size))
+
+    def velocity(vel, t, cache, p):
+        vel.set(np.concatenate([uu.ravel(order="F"), vv.ravel(order="F")]))
+
+    prob = tm.UnboundedHeatConduction(g, pp["diffusivity"], [ilm.LineForcingModel(square, tr1, model1),
+                                                             ilm.AreaForcingModel(disc, tr2, model2),
+                                                             ilm.PointForcingModel(pts, model3, ddftype="m3")],
+                                      velocity, pp, fourier=1.0, cfl=0.5, umax=Om * 2.0, lgf_table=G, device=device)
+    assert abs(prob.dt - min(g.dx ** 2 / 0.005, 0.5 * g.dx / (Om * 2.0))) < 1e-15
+    # oracle pieces
+    oc1 = o.ScalarCache(og, *tr1(square)[:5], G)
+    oc2 = o.ScalarCache(og, *tr2(disc)[:5], G)
+    m2 = oc2.mask()
+    tabp = o.point_collection_table(og, *pts, o.PRIMAL, "m3")
+
+    def rhs(T, t):
+        dT = o.convective_derivative_scalar(og, uu, vv, T, div=g.dx) * -1.0
+        f = np.zeros_like(T)
+        f = o.forcing_line(f, oc1.tabs[o.PRIMAL], np.full(oc1.N, pp["lineheater_flux"]))
+        f = o.forcing_area(f, pp["areaheater_coeff"] * (pp["areaheater_temp"] * np.cos(2 * np.pi * t) - T), m2)
+        f = o.forcing_line(f, tabp, np.full(1, 5.0))
+        return dT + f
+
+    tables = {a: ilm.lgf.intfact_table(a, g.NX) for a in set(prob.stage_a)}
+    T = np.zeros(o.field_shape(o.PRIMAL, g.NX, g.NY))
+    t = 0.0
+    for n in range(3):
+        T = o.heat_unbounded_step(og, T, t, prob.dt, pp["diffusivity"], prob.tab_a, prob.tab_c, tables, rhs)
+        prob.step()
+        t += prob.dt
+        assert relerr(prob.T.array(), T) < 1e-10, n
+    assert np.abs(T).max() > 1e-3 and prob.nstep == 3

@@ -490,3 +490,23 @@ def test_helmholtz_round_trip(small_vcache):
     xg, yg = g.coords(o.PRIMAL)
     gu, gv = c.grad(1.5 * xg[:, None] - 0.5 * yg[None, :] + 0 * d)
     assert np.abs(gu[1:-1, :] - 1.5).max() < 1e-12 and np.abs(gv[:, 1:-1] + 0.5).max() < 1e-12
+
+
+def test_unbounded_heat_step_conserves_point_heating():
+    """heat_unbounded_step (test/literate/heatconduction-unbounded.jl recursion): with a constant point source of
+    strength q the integral of T grows by q dt per step (the integrating factor and the M3 kernel both sum to one)."""
+    from ilm_b200 import timemarching as tm
+    g = o.Grid(64, 64, 4.0 / 62, (32, 32))
+    kappa, dt = 0.005, 0.02
+    tab = tm.LISKA_IFHERK
+    stage_a, prev = [], 0.0
+    for c in tab["c"]:
+        stage_a.append(kappa / g.dx ** 2 * (c - prev) * dt)
+        prev = c
+    tables = {a: lgfmod.intfact_table(a, g.NX) for a in set(stage_a)}
+    tabp = o.point_collection_table(g, [0.3], [-0.2], o.PRIMAL, "m3")
+    T = np.zeros(o.field_shape(o.PRIMAL, g.NX, g.NY))
+    for n in range(4):
+        T = o.heat_unbounded_step(g, T, n * dt, dt, kappa, tab["a"], tab["c"], tables,
+                                  lambda TT, t: o.forcing_line(np.zeros_like(TT), tabp, np.full(1, 5.0)))
+    assert abs(T.sum() * g.dx ** 2 - 5.0 * 4 * dt) < 1e-12
