@@ -1,4 +1,4 @@
-"""Generates tests/golden/c1_dirichlet_128.npz: the CPU oracle's outputs on BASELINE config C1
+"""Generates tests/golden/c1_dirichlet_128.npz and forcing_helmholtz_64.npz: the CPU oracle's outputs on BASELINE config C1
 (Dirichlet Poisson on a circle, 128x128 grid, Yang3, examples/dirichlet.ipynb setup scaled to the
 (-2,2)^2 synthetic grid of SURVEY.md section 8d), on seeded inputs.
 
@@ -48,7 +48,42 @@ def build():
     return out
 
 
+def build_forcing_helmholtz():
+    """forcing_helmholtz_64.npz: the oracle's forcing-region contributions (src/forcing.jl:456-494) and Helmholtz
+    decomposition (src/helmholtz.jl:84-307) on a 64 x 60 grid with an off-centre ellipse, seeded inputs."""
+    import ilm_b200 as ilm
+    import ilm_oracle as o
+
+    NX, NY, dx, I0 = 64, 60, 0.07, (31, 29)
+    G = ilm.lgf.lgf_table(64)
+    og = o.Grid(NX, NY, dx, I0)
+    body = ilm.bodies.ellipse(0.9, 0.5, 1.4 * dx, center=(0.1, -0.05))
+    shape = ilm.RigidTransform((0.3, 0.2), 0.4)(ilm.bodies.rectangle(0.5, 0.3, 1.4 * dx))
+    oc_shape = o.ScalarCache(og, *shape[:5], G)
+    vc = o.VectorCache(og, *body[:5], G)
+    rng = np.random.default_rng(21)
+    T = rng.standard_normal(o.field_shape(o.PRIMAL, NX, NY))
+    line_str = rng.standard_normal(oc_shape.N)
+    px, py = np.array([-1.2, 0.5, 0.013]), np.array([0.5, 0.5, -0.777])
+    pstr = np.array([1.0, -1.0, 2.5])
+    m = oc_shape.mask()
+    dT = o.forcing_area(np.zeros_like(T), 2.0 * (1.5 - T), m)
+    dT = o.forcing_line(dT, oc_shape.tabs[o.PRIMAL], line_str)
+    dT = o.forcing_line(dT, o.point_collection_table(og, px, py, o.PRIMAL, "m4prime"), pstr)
+    w = rng.standard_normal(o.field_shape(o.DUAL, NX, NY))
+    d = rng.standard_normal(o.field_shape(o.PRIMAL, NX, NY))
+    dvu, dvv = rng.standard_normal(vc.N), rng.standard_normal(vc.N)
+    psi, phi = o.helmholtz_potentials(vc, w, d, dvu, dvv)
+    vu, vv = o.vecfield_from_potentials(vc, psi, phi, None)
+    return dict(NX=NX, NY=NY, dx=dx, I0=np.asarray(I0), lgf=G, body=np.stack(body[:5]), shape=np.stack(shape[:5]),
+                T=T, line_str=line_str, px=px, py=py, pstr=pstr, shape_mask=m, forcing_dT=dT,
+                w=w, d=d, dv=np.concatenate([dvu, dvv]), psi=psi, phi=phi, v_u=vu, v_v=vv,
+                masked_w=o.helmholtz_jump(vc, "cross", -1, dvu, dvv, w), masked_d=o.helmholtz_jump(vc, "dot", -1, dvu, dvv, d))
+
+
 if __name__ == "__main__":
-    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c1_dirichlet_128.npz")
-    np.savez_compressed(dst, **build())
-    print("wrote", dst, os.path.getsize(dst), "bytes")
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name, fn in (("c1_dirichlet_128.npz", build), ("forcing_helmholtz_64.npz", build_forcing_helmholtz)):
+        dst = os.path.join(here, name)
+        np.savez_compressed(dst, **fn())
+        print("wrote", dst, os.path.getsize(dst), "bytes")

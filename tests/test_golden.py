@@ -4,7 +4,9 @@
   (extract_reference_goldens.py); the oracle must reproduce them (CPU).
 * c1_dirichlet_128.npz -- oracle outputs on BASELINE config C1 (make_oracle_fixtures.py); the
   oracle must still reproduce the file (CPU) and the CUDA path must match it (-m gpu): bit-exact
-  for tables / regularization / stencils, 1e-12 norm-wise for everything through the FFT."""
+  for tables / regularization / stencils, 1e-12 norm-wise for everything through the FFT.
+* forcing_helmholtz_64.npz -- oracle outputs of the forcing regions (src/forcing.jl) and the Helmholtz decomposition
+  (src/helmholtz.jl) on a 64 x 60 grid (same script), checked the same two ways."""
 import json
 import os
 
@@ -133,3 +135,68 @@ def test_gpu_matches_c1_fixture(c1file):
     cond = np.linalg.cond(d["S"])
     assert relerr(sm.data, d["dirichlet_s"]) < 50 * cond * np.finfo(float).eps
     assert relerr(f.array(), d["dirichlet_f"]) < 1e-10
+
+
+# ---------------------------------------------------------------- forcing regions / Helmholtz fixture
+@pytest.fixture(scope="module")
+def fhfile():
+    return np.load(os.path.join(HERE, "forcing_helmholtz_64.npz"))
+
+
+def _fh_oracle(d):
+    g = o.Grid(int(d["NX"]), int(d["NY"]), float(d["dx"]), tuple(int(v) for v in d["I0"]))
+    return g, o.ScalarCache(g, *d["shape"], d["lgf"]), o.VectorCache(g, *d["body"], d["lgf"])
+
+
+def test_oracle_reproduces_forcing_helmholtz_fixture(fhfile):
+    d = fhfile
+    g, ocs, vc = _fh_oracle(d)
+    m = ocs.mask()
+    assert relerr(m, d["shape_mask"]) < 1e-13
+    dT = o.forcing_area(np.zeros_like(d["T"]), 2.0 * (1.5 - d["T"]), d["shape_mask"])
+    dT = o.forcing_line(dT, ocs.tabs[o.PRIMAL], d["line_str"])
+    dT = o.forcing_line(dT, o.point_collection_table(g, d["px"], d["py"], o.PRIMAL, "m4prime"), d["pstr"])
+    assert np.array_equal(dT, d["forcing_dT"])
+    n = vc.N
+    psi, phi = o.helmholtz_potentials(vc, d["w"], d["d"], d["dv"][:n], d["dv"][n:])
+    assert relerr(psi, d["psi"]) < 1e-13 and relerr(phi, d["phi"]) < 1e-13
+    vu, vv = o.vecfield_from_potentials(vc, d["psi"], d["phi"], None)
+    assert np.array_equal(vu, d["v_u"]) and np.array_equal(vv, d["v_v"])
+    assert np.array_equal(o.helmholtz_jump(vc, "cross", -1, d["dv"][:n], d["dv"][n:], d["w"]), d["masked_w"])
+
+
+@pytest.mark.gpu
+def test_gpu_matches_forcing_helmholtz_fixture(fhfile):
+    d = fhfile
+    g = ilm.PhysicalGrid(int(d["NX"]), int(d["NY"]), float(d["dx"]), tuple(int(v) for v in d["I0"]))
+    base = ilm.SurfaceScalarCache(tuple(d["body"]), g, lgf_table=d["lgf"])
+    T = base.zeros_grid().set(d["T"])
+
+    def area(sig, TT, t, fr, pp):
+        sig.set(2.0 * (1.5 - TT.numpy()))
+
+    def line(sig, TT, t, fr, pp):
+        sig.set(d["line_str"])
+
+    def point(sig, TT, t, fr, pp):
+        sig.set(d["pstr"])
+
+    shape = tuple(d["shape"])
+    fc = ilm.ForcingModelAndRegion([ilm.AreaForcingModel(shape, ilm.RigidTransform(), area),
+                                    ilm.LineForcingModel(shape, ilm.RigidTransform(), line),
+                                    ilm.PointForcingModel((d["px"], d["py"]), point, ddftype="m4prime")], base)
+    dT = base.zeros_grid()
+    ilm.apply_forcing(dT, T, None, 0.0, fc, None, None, base)
+    assert relerr(fc[0].region_cache.mask.array(), d["shape_mask"]) < RTOL
+    assert relerr(dT.array(), d["forcing_dT"]) < RTOL
+    vc = ilm.SurfaceVectorCache(tuple(d["body"]), g, parent=base)
+    w, dd, dv = vc.zeros_gridcurl().set(d["w"]), vc.zeros_griddiv().set(d["d"]), vc.zeros_surface().set(d["dv"])
+    psi, phi, v = vc.zeros_gridcurl(), vc.zeros_griddiv(), vc.zeros_grid()
+    ilm.potentials_from_masked_fields(psi, phi, w, dd, dv, vc)
+    assert relerr(psi.array(), d["psi"]) < RTOL and relerr(phi.array(), d["phi"]) < RTOL
+    ilm.vecfield_helmholtz(v, w, dd, dv, None, vc)
+    assert relerr(v.u, d["v_u"]) < RTOL and relerr(v.v, d["v_v"]) < RTOL
+    mw, md = vc.zeros_gridcurl(), vc.zeros_griddiv()
+    ilm.masked_curlv_from_curlv_masked(mw, w, dv, vc)
+    ilm.masked_divv_from_divv_masked(md, dd, dv, vc)
+    assert np.array_equal(mw.array(), d["masked_w"]) and np.array_equal(md.array(), d["masked_d"])
