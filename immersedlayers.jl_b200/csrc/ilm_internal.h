@@ -52,6 +52,7 @@ struct DevTable {
     int* ent = nullptr;         // nent    k*W*W + slot, ascending k inside a cell
     double* rowsum = nullptr;   // ncell   sum_k R[cell,k] (surface filter)
     std::vector<int> h_j0;      // host mirror of j0 (row range of each point's window)
+    size_t cap_pts = 0, cap_cells = 0, cap_ents = 0;   // allocated capacities (a moving body refreshes the tables every step)
 };
 
 struct ConvKernel {     // one multiplier (LGF inverse, integrating factor, ...)

@@ -41,64 +41,116 @@ void free_table(DevTable& t) {
     t = DevTable();
 }
 
+// Device buffers of the tables are grow-only: update_points on a moving body (src/system.jl:26-50) rebuilds the tables
+// every step, and a cudaFree / cudaMalloc per buffer and refresh would synchronise the device 64 times.
+
+// stable LSD radix sort of (cell, id) pairs by cell (3 passes of 10 bits cover 2^30 > 16384^2 cells); entries are
+// generated in ascending point order, so ties keep that order -- the order of a CSC column scan, as std::stable_sort gave
+static void sort_by_cell(std::vector<int>& cell, std::vector<int>& id, std::vector<int>& cell_tmp, std::vector<int>& id_tmp) {
+    const size_t n = cell.size();
+    cell_tmp.resize(n);
+    id_tmp.resize(n);
+    int maxc = 0;
+    for (size_t q = 0; q < n; ++q) maxc = std::max(maxc, cell[q]);
+    for (int shift = 0; shift < 30 && (maxc >> shift) > 0; shift += 10) {
+        size_t count[1025] = {0};
+        for (size_t q = 0; q < n; ++q) count[((cell[q] >> shift) & 1023) + 1]++;
+        for (int b = 0; b < 1024; ++b) count[b + 1] += count[b];
+        for (size_t q = 0; q < n; ++q) {
+            const size_t dst = count[(cell[q] >> shift) & 1023]++;
+            cell_tmp[dst] = cell[q];
+            id_tmp[dst] = id[q];
+        }
+        cell.swap(cell_tmp);
+        id.swap(id_tmp);
+    }
+}
+
 int build_tables(ilm_plan* p) {
     const int N = p->N;
     const int W = ddf_width(p->ddf), W2 = W * W;
+    const size_t np = (size_t)(N > 0 ? N : 1);
+    std::vector<int> hi[4], hj[4];
+    // phase 1: the window tables of all four layouts, one synchronisation
     for (int layout = 0; layout < 4; ++layout) {
         DevTable& t = p->tab[layout];
-        free_table(t);
         const LayoutInfo li = layout_info(layout, p->g.NX, p->g.NY);
         t.W = W; t.mx = li.mx; t.my = li.my;
-        const size_t np = (size_t)(N > 0 ? N : 1);
-        ILM_CUDA(cudaMalloc(&t.i0, np * sizeof(int)));
-        ILM_CUDA(cudaMalloc(&t.j0, np * sizeof(int)));
-        ILM_CUDA(cudaMalloc(&t.wR, np * W2 * sizeof(double)));
-        ILM_CUDA(cudaMalloc(&t.wE, np * W2 * sizeof(double)));
-        std::vector<int> hi(N), hj(N);
-        std::vector<double> hw((size_t)N * W2);
+        if (np * W2 > t.cap_pts || !t.i0) {
+            cudaFree(t.i0); cudaFree(t.j0); cudaFree(t.wR); cudaFree(t.wE);
+            t.i0 = t.j0 = nullptr; t.wR = t.wE = nullptr;
+            const size_t cap = np + np / 4 + 16;
+            ILM_CUDA(cudaMalloc(&t.i0, cap * sizeof(int)));
+            ILM_CUDA(cudaMalloc(&t.j0, cap * sizeof(int)));
+            ILM_CUDA(cudaMalloc(&t.wR, cap * W2 * sizeof(double)));
+            ILM_CUDA(cudaMalloc(&t.wE, cap * W2 * sizeof(double)));
+            t.cap_pts = cap * W2;
+        }
+        hi[layout].resize(N);
+        hj[layout].resize(N);
         if (N > 0) {
             k_point_tables<<<(N + 127) / 128, 128, 0, p->stream>>>(N, p->x, p->y, p->ds, p->g.dx, p->g.I0x, p->g.I0y,
                                                                     p->ddf, p->scaling == ILM_INDEX_SCALING, li.sx,
                                                                     li.sy, li.mx, li.my, t.i0, t.j0, t.wR, t.wE);
             ILM_CUDA(cudaGetLastError());
             p->launches++;
-            ILM_CUDA(cudaMemcpyAsync(hi.data(), t.i0, N * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-            ILM_CUDA(cudaMemcpyAsync(hj.data(), t.j0, N * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-            ILM_CUDA(cudaStreamSynchronize(p->stream));
+            ILM_CUDA(cudaMemcpyAsync(hi[layout].data(), t.i0, N * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+            ILM_CUDA(cudaMemcpyAsync(hj[layout].data(), t.j0, N * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
         }
-        t.h_j0 = hj;
-        // gather list: (cell, k, slot) for every in-range window entry, sorted by cell then k
-        struct Ent { int cell, id; };
-        std::vector<Ent> ents;
-        ents.reserve((size_t)N * W2);
+    }
+    ILM_CUDA(cudaStreamSynchronize(p->stream));
+    // phase 2: gather lists (cell, k, slot) for every in-range window entry, sorted by cell then k
+    std::vector<int> cell, id, cell_tmp, id_tmp, cell_idx, cell_off;
+    for (int layout = 0; layout < 4; ++layout) {
+        DevTable& t = p->tab[layout];
+        const LayoutInfo li = layout_info(layout, p->g.NX, p->g.NY);
+        const std::vector<int>& xi = hi[layout];
+        const std::vector<int>& yj = hj[layout];
+        t.h_j0 = yj;
+        cell.clear();
+        id.clear();
+        cell.reserve((size_t)N * W2);
+        id.reserve((size_t)N * W2);
         for (int k = 0; k < N; ++k)
             for (int b = 0; b < W; ++b)
                 for (int a = 0; a < W; ++a) {
-                    const int i = hi[k] + a, j = hj[k] + b;
-                    if (i >= 0 && i < li.mx && j >= 0 && j < li.my) ents.push_back({i + li.mx * j, k * W2 + b * W + a});
+                    const int i = xi[k] + a, j = yj[k] + b;
+                    if (i >= 0 && i < li.mx && j >= 0 && j < li.my) { cell.push_back(i + li.mx * j); id.push_back(k * W2 + b * W + a); }
                 }
-        std::stable_sort(ents.begin(), ents.end(), [](const Ent& u, const Ent& v) { return u.cell < v.cell; });
-        std::vector<int> cell_idx, cell_off, ent(ents.size());
-        for (size_t q = 0; q < ents.size(); ++q) {
-            if (q == 0 || ents[q].cell != ents[q - 1].cell) {
-                cell_idx.push_back(ents[q].cell);
+        sort_by_cell(cell, id, cell_tmp, id_tmp);
+        cell_idx.clear();
+        cell_off.clear();
+        for (size_t q = 0; q < cell.size(); ++q)
+            if (q == 0 || cell[q] != cell[q - 1]) {
+                cell_idx.push_back(cell[q]);
                 cell_off.push_back((int)q);
             }
-            ent[q] = ents[q].id;
-        }
-        cell_off.push_back((int)ents.size());
+        cell_off.push_back((int)cell.size());
         t.ncell = (int)cell_idx.size();
-        t.nent = (int)ents.size();
-        ILM_CUDA(cudaMalloc(&t.cell_idx, (cell_idx.size() + 1) * sizeof(int)));
-        ILM_CUDA(cudaMalloc(&t.cell_off, cell_off.size() * sizeof(int)));
-        ILM_CUDA(cudaMalloc(&t.ent, (ent.size() + 1) * sizeof(int)));
-        ILM_CUDA(cudaMalloc(&t.rowsum, (cell_idx.size() + 1) * sizeof(double)));
+        t.nent = (int)cell.size();
+        if ((size_t)t.ncell + 1 > t.cap_cells || !t.cell_idx) {
+            cudaFree(t.cell_idx); cudaFree(t.cell_off); cudaFree(t.rowsum);
+            t.cell_idx = t.cell_off = nullptr; t.rowsum = nullptr;
+            const size_t cap = (size_t)t.ncell + t.ncell / 4 + 16;
+            ILM_CUDA(cudaMalloc(&t.cell_idx, cap * sizeof(int)));
+            ILM_CUDA(cudaMalloc(&t.cell_off, (cap + 1) * sizeof(int)));
+            ILM_CUDA(cudaMalloc(&t.rowsum, cap * sizeof(double)));
+            t.cap_cells = cap;
+        }
+        if ((size_t)t.nent + 1 > t.cap_ents || !t.ent) {
+            cudaFree(t.ent);
+            t.ent = nullptr;
+            const size_t cap = (size_t)t.nent + t.nent / 4 + 16;
+            ILM_CUDA(cudaMalloc(&t.ent, cap * sizeof(int)));
+            t.cap_ents = cap;
+        }
+        // pageable sources: cudaMemcpyAsync stages them before it returns, so the vectors may be reused at once
         if (t.ncell) ILM_CUDA(cudaMemcpyAsync(t.cell_idx, cell_idx.data(), cell_idx.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         ILM_CUDA(cudaMemcpyAsync(t.cell_off, cell_off.data(), cell_off.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-        if (t.nent) ILM_CUDA(cudaMemcpyAsync(t.ent, ent.data(), ent.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-        ILM_CUDA(cudaStreamSynchronize(p->stream));
+        if (t.nent) ILM_CUDA(cudaMemcpyAsync(t.ent, id.data(), id.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         if (layout == ILM_NODES_PRIMAL) ILM_TRY(launch_filter_rowsum(p, t));
     }
+    ILM_CUDA(cudaStreamSynchronize(p->stream));
     return ILM_OK;
 }
 

@@ -143,12 +143,8 @@ def potentials_from_masked_fields(psi, phi, masked_curlv, masked_divv, dv, base_
 def vecfield_uniformvecfield(v, Vx, Vy, base_cache):
     """vecfield_uniformvecfield!(v, Vx, Vy, base_cache) (:344-348)."""
     A._expect(v, A.Edges, "vecfield_uniformvecfield")
-    if A._is_torch(v.data):
-        v.data[: v.nu] = float(Vx)
-        v.data[v.nu:] = float(Vy)
-    else:
-        v.data[: v.nu] = float(Vx)
-        v.data[v.nu:] = float(Vy)
+    v.data[: v.nu] = float(Vx)              # numpy array or CUDA tensor: same slice assignment
+    v.data[v.nu:] = float(Vy)
     return v
 
 
