@@ -22,9 +22,11 @@ integrating-factor table (`create_RTHR_direct`, milliseconds) or column by colum
 convolution engine (`create_RTHR`, the reference's way).  The operators of a step are those of the
 body position at the start of the step.
 
-PARITY UNPINNED: the integrator lives in ConstrainedSystems.jl (compat 0.3.8, not in the container);
-the tableau and the stage recursion follow the published IF-HERK scheme, the oracle restates the same
-recursion on the CPU (oracle/ilm_oracle.py:heat_ifherk_step) and the GPU path is compared with it."""
+PARITY: the integrator lives in ConstrainedSystems.jl (compat 0.3.8, not in the container); the tableau and
+the stage recursion follow the published IF-HERK scheme, the oracle restates the same recursion on the CPU
+(oracle/ilm_oracle.py:heat_ifherk_step) and reproduces the temperatures printed by the reference's executed
+notebook examples/heatconduction.ipynb (cells 58, 62: 51 and 54 steps) to 2e-14; the GPU path is compared with
+the oracle step by step and with the notebook values directly (tests/test_golden.py)."""
 from __future__ import annotations
 
 import numpy as np

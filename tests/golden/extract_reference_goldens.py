@@ -21,6 +21,14 @@ WANT = [
     ("caches_circle", "caches.ipynb", "body = Circle(RadC", "number of points of Circle(1.0, 1.4dx)"),
     ("layers_dot_x_Rf_n", "Layers.ipynb", "dot(qx,Rf*nrm,g)", "integral of x n_x over the regularized circle ~ pi"),
     ("multbodies_circle", "multbodies.ipynb", "body = Circle(RadC", "number of points of Circle(0.5, 1.4dx)"),
+    # time marching of the constrained heat equation (IF-HERK through ConstrainedSystems): temperature at the grid node
+    # (-0.9, 0) after 51 and 54 steps of dt = 1e-4 on the 408^2 grid (dx = 0.01), circle R = 1, T+ = 0, T- = 1
+    ("heatconduction_dt", "heatconduction.ipynb", "timestep_fourier(u0,sys)", "time step Fo dx^2 / kappa"),
+    ("heatconduction_state_size", "heatconduction.ipynb", "state(u0)", "Nodes{Primal,408,408}: grid size"),
+    ("heatconduction_T_t0051", "heatconduction.ipynb", "Tfcn(-0.9,0)", "T(-0.9, 0) at t = 0.0051"),
+    ("heatconduction_T_t0054", "heatconduction.ipynb", "Tfcn_array[4](-0.9,0)", "T(-0.9, 0) at t = 0.0054"),
+    ("neumann_added_mass", "neumann.ipynb", "M = -integrate(df", "added-mass integral of the Neumann solve"),
+    ("multbodies_volume", "multbodies.ipynb", "V3 = integrate(pointwise_dot(pts,nrm),cache,3)", "area of body 3 by the divergence theorem"),
 ]
 NUM = re.compile(r"[-+]?(?:\d+\.\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?|\d+(?:[eE][-+]?\d+)?)")
 
