@@ -1021,10 +1021,20 @@ def _mask_inplace(w, cache, complementary):
     return w
 
 
-def mask(*args):
+def _mask_cache(w, surface, g, **kwargs):
+    """_mask_cache (src/surface_operators.jl:846-848): a scalar cache for scalar grid data, a vector cache for Edges /
+    EdgeGradient.  kwargs: `parent=` (a cache on the same grid whose Laplacian is shared) or `lgf_table=`."""
+    cls = SurfaceVectorCache if isinstance(w, (Edges, EdgeGradient)) else SurfaceScalarCache
+    return cls(surface, g, device=_is_torch(w.data), **kwargs)
+
+
+def mask(*args, **kwargs):
     """mask(cache) -> new grid data with 1 inside / 0 outside (src/surface_operators.jl:737): Nodes{Primal}
     for a scalar cache, Edges for a vector cache.  mask(w, cache) = mask!(w, cache) (:788-800): w is
-    multiplied in place by the mask, averaged onto w's layout where needed."""
+    multiplied in place by the mask, averaged onto w's layout where needed.
+    mask(w, surface, g) = mask!(w, surface, grid) (:826-829): the same with a temporary cache of the shape."""
+    if len(args) == 3:
+        return _mask_inplace(args[0], _mask_cache(args[0], args[1], args[2], **kwargs), False)
     if len(args) == 2:
         return _mask_inplace(args[0], args[1], False)
     (cache,) = args
@@ -1037,8 +1047,11 @@ def mask(*args):
     return _s_mask(cache)
 
 
-def complementary_mask(*args):
-    """complementary_mask(cache) (:749) / complementary_mask!(w, cache) (:811-823)."""
+def complementary_mask(*args, **kwargs):
+    """complementary_mask(cache) (:749) / complementary_mask!(w, cache) (:811-823) /
+    complementary_mask!(w, surface, grid) (:837-840)."""
+    if len(args) == 3:
+        return _mask_inplace(args[0], _mask_cache(args[0], args[1], args[2], **kwargs), True)
     if len(args) == 2:
         return _mask_inplace(args[0], args[1], True)
     (cache,) = args

@@ -68,3 +68,27 @@ def test_gpu_reproduces_neumann_notebook_added_mass(nbvals):
     ref = nbvals["neumann_added_mass"]["values"]
     assert abs(M[0] - ref[0]) < 1e-8 * abs(ref[0]), (M, ref)
     assert abs(M[1] - ref[1]) < 1e-8
+
+
+def test_mask_of_a_shape_on_a_grid():
+    """test/surface_ops.jl:232-253: mask!(w, Rectangle(0.5, 0.25, ds), g) on every grid-data type integrates to the
+    area 0.5; the temporary cache may share the Laplacian of an existing cache (`parent=`)."""
+    g = ilm.PhysicalGrid.centered(256)
+    G = ilm.lgf.lgf_table(256)
+    base = ilm.SurfaceScalarCache(ilm.bodies.circle(1.0, 1.4 * g.dx), g, lgf_table=G)
+    shape = ilm.bodies.rectangle(0.5, 0.25, 1.4 * g.dx)
+    for w in (ilm.Nodes(ilm.Primal, g), ilm.Nodes(ilm.Dual, g), ilm.Edges(g), ilm.EdgeGradient(g)):
+        w.fill(1.0)
+        ilm.mask(w, shape, g, parent=base)
+        if isinstance(w, ilm.Nodes):
+            parts = [w.numpy()]
+        elif isinstance(w, ilm.Edges):
+            parts = [w.u, w.v]
+        else:
+            parts = [w.component(i) for i in range(4)]
+        for p in parts:
+            assert abs(np.asarray(p).sum() * g.dx ** 2 - 0.5) < 5e-3
+    inner, outer = ilm.Nodes(ilm.Primal, g).fill(1.0), ilm.Nodes(ilm.Primal, g).fill(1.0)
+    ilm.mask(inner, shape, g, parent=base)
+    ilm.complementary_mask(outer, shape, g, lgf_table=G)            # a stand-alone temporary cache
+    assert np.abs(inner.numpy() + outer.numpy() - 1.0).max() < 1e-12
