@@ -8,6 +8,7 @@ builders, surface-point solve) over the C ABI of libilm_b200.so
 from . import _lib, bodies, lgf  # noqa: F401
 from . import timemarching  # noqa: F401,E402
 from . import forcing  # noqa: F401,E402
+from . import tools  # noqa: F401,E402
 from . import helmholtz  # noqa: F401,E402
 from .helmholtz import (  # noqa: F401,E402
     ScalarPotentialCache, VectorFieldCache, VectorPotentialCache, curlv_masked_from_masked_curlv, divv_masked_from_masked_divv,

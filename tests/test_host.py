@@ -331,3 +331,61 @@ def test_forcing_host_logic():
     assert abs(gf().numpy().sum() * g.dx ** 2 - 10.0) < 1e-6
     gfe = F.GeneratedField(ilm.Edges(g), [ilm.SpatialGaussian(0.3, 0.3, 0.1, 0, 1), ilm.SpatialGaussian(0.2, 0.4, 0, 0.2, 2)], g)
     assert abs(gfe().u.sum() * g.dx ** 2 - 1.0) < 1e-6 and abs(gfe().v.sum() * g.dx ** 2 - 2.0) < 1e-6
+
+
+def test_tools_inner_products_and_body_lists():
+    """test/tools.jl "Inner Products" (:27-50) and "Operations on body lists" (:55-98) on the host mirror of
+    src/tools.jl; the grid integrals are pinned by the values printed in examples/caches.ipynb (cells 32, 34)."""
+    import json
+    import ilm_b200 as ilm
+    from ilm_b200 import tools as T
+    g = ilm.PhysicalGrid(406, 406, 0.01, (203, 203))
+    w = ilm.Nodes(ilm.Dual, g).fill(1.0)
+    u = ilm.Nodes(ilm.Dual, g).fill(1.0)
+    assert np.sqrt(T.dot(w, u, g)) == T.norm(w, g)
+    area = ((g.NX - 2) * g.dx) ** 2                       # (xlim[2]-xlim[1]) (ylim[2]-ylim[1])
+    assert abs(T.norm(w, g) - np.sqrt(area)) < 1e-12 and abs(T.integrate(w, g) - area) < 1e-10
+    small = ilm.Nodes(ilm.Dual, ilm.PhysicalGrid(5, 5, 0.01, (2, 2)))
+    with pytest.raises(ilm.MethodError):
+        T.dot(w, small, g)
+    with pytest.raises(ilm.DimensionMismatch):
+        T.dot(small, small, g)
+    nb = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_notebook_values.json")))
+    og = ilm.Nodes(ilm.Primal, g).fill(1.0)
+    assert abs(T.integrate(og, g) - nb["caches_integrate_ones_grid"]["values"][0]) < 1e-10
+    ovg = T.ones(ilm.Edges(g))
+    got = T.integrate(ovg, g)
+    assert np.abs(np.array(got) - np.array(nb["caches_integrate_ones_gridgrad"]["values"])).max() < 1e-10
+    assert T.integrate(T.ones(ilm.Edges(g), 2), g)[0] == 0.0 and len(T.integrate(T.ones(ilm.EdgeGradient(g)), g)) == 4
+    # surface data
+    body = ilm.bodies.circle(1.0, 1.4 * g.dx)
+    n = len(body[0])
+    ds = ilm.ScalarData(n, data=body[4].copy())
+    os_ = T.ones(ilm.ScalarData(n))
+    assert abs(T.dot(os_, os_, ds) - 2 * np.pi) < 1e-3
+    assert abs(T.dot(os_, os_, ds) - nb["caches_dot_ones_surface"]["values"][0]) < 1e-11
+    nrm = ilm.VectorData(n, data=np.concatenate([body[2], body[3]]))
+    assert abs(T.integrate(T.pointwise_dot(nrm, nrm), ds) - 2 * np.pi) < 1e-3
+    # body lists (two copies of the body)
+    bl = ilm.bodies.concat(body, body)
+    X = ilm.VectorData(n, data=np.concatenate([body[0], body[1]]))
+    Xl = ilm.VectorData(2 * n, data=np.concatenate([bl[0], bl[1]]))
+    dsl = ilm.ScalarData(2 * n, data=bl[4].copy())
+    assert T.dot(Xl, Xl, dsl, bl, 1) == T.dot(Xl, Xl, dsl, bl, 2) == T.dot(X, X, ds)
+    assert T.norm(Xl, dsl, bl, 1) == T.norm(Xl, dsl, bl, 2) == T.norm(X, ds)
+    nl = ilm.VectorData(2 * n, data=np.concatenate([bl[2], bl[3]]))
+    assert abs(T.integrate(T.pointwise_dot(nl, nl), dsl, bl, 2) - 2 * np.pi) < 1e-3
+    fl, gl = ilm.ScalarData(2 * n), ilm.ScalarData(2 * n).set(np.random.default_rng(0).random(2 * n))
+    T.copyto(fl, gl, bl, 2)
+    assert not T.view(fl, bl, 1).any() and np.array_equal(T.view(fl, bl, 2), T.view(gl, bl, 2))
+    fl = ilm.ScalarData(2 * n)
+    T.copyto(fl, T.view(gl, bl, 2), bl, 2)
+    assert not T.view(fl, bl, 1).any() and np.array_equal(T.view(fl, bl, 2), T.view(gl, bl, 2))
+    with pytest.raises(ilm.DimensionMismatch):
+        T.copyto(fl, [1.0, 2.0, 3.0], bl, 2)
+    fv, gv = ilm.VectorData(2 * n), ilm.VectorData(2 * n).set(np.random.default_rng(1).random(4 * n))
+    T.copyto(fv, gv, bl, 1)
+    assert not T.view(fv, bl, 2)[0].any() and not T.view(fv, bl, 2)[1].any()
+    assert np.array_equal(T.view(fv, bl, 1)[0], T.view(gv, bl, 1)[0]) and np.array_equal(T.view(fv, bl, 1)[1], T.view(gv, bl, 1)[1])
+    # the added-mass integral of examples/neumann.ipynb cell 37 has this form: -integrate(df o nrm, ds, bl, 2)
+    assert isinstance(T.integrate(nl, dsl, bl, 2), list)
