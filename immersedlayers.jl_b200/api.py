@@ -284,6 +284,8 @@ class SurfaceScalarCache:
         self.nrm = (nx, ny)
         self.areas_ = ds
         self.N = N
+        # offsets of the bodies of a body list (bodies.concat), a single body otherwise (cache.bl of the reference)
+        self.body_first = np.asarray(body[5], dtype=np.int64) if len(body) > 5 else np.array([0, N], dtype=np.int64)
         self.scaling = scaling
         self.ddftype = ddftype
         self.device = bool(device)
@@ -364,6 +366,7 @@ class SurfaceScalarCache:
         x, y, nx, ny, ds = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)) for a in body[:5]]
         L.check(self._lib.ilm_plan_update_points(self._plan, x.shape[0], _ptr(x), _ptr(y), _ptr(nx), _ptr(ny), _ptr(ds)))
         self.pts, self.nrm, self.areas_, self.N = (x, y), (nx, ny), ds, x.shape[0]
+        self.body_first = np.asarray(body[5], dtype=np.int64) if len(body) > 5 else np.array([0, self.N], dtype=np.int64)
 
     def sync(self):
         L.check(self._lib.ilm_plan_sync(self._plan))

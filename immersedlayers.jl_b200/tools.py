@@ -48,10 +48,38 @@ def _same_grid_type(u1, u2, g):
         raise DimensionMismatch("dot: the grid data do not live on this grid")            # @assert (NX,NY) == size(g)
 
 
+def _is_grid_data(u):
+    return isinstance(u, (A.Nodes, A.Edges, A.XEdges, A.YEdges, A.EdgeGradient))
+
+
+def _cache_bl(cache):
+    return (None, None, None, None, None, cache.body_first)
+
+
+def _cache_args(u, w, bl, i, for_integral=False):
+    """The cache methods of src/cache.jl:815-909: GridScaling weighs grid data by dx^2 and surface data by ds,
+    IndexScaling uses plain sums -- except integrate, which always uses the areas.  The body index may come as the
+    fourth positional argument, as in dot(u1, u2, cache, i)."""
+    if not isinstance(w, A.SurfaceScalarCache):
+        return w, bl, i
+    cache = w
+    if i is None and isinstance(bl, (int, np.integer)):
+        i = int(bl)
+    bl = _cache_bl(cache) if i is not None else None
+    if _is_grid_data(u):
+        if cache.scaling == A.GridScaling or for_integral:
+            return cache.g, None, None
+        return A.PhysicalGrid(cache.g.NX, cache.g.NY, 1.0, cache.g.I0), None, None     # plain dot: unit cell area
+    weights = cache.areas() if (cache.scaling == A.GridScaling or for_integral) else np.ones(cache.N)
+    return weights, bl, i
+
+
 def dot(u1, u2, w, bl=None, i=None):
     """dot(u1, u2, g) on grid data (src/tools.jl:101-104); dot(u1, u2, ds) on ScalarData / VectorData (:153-155);
     dot(u1, u2, ds, bl, i) restricted to body i (1-based) of a body list (:163-168); `bl` is the body tuple whose sixth
-    entry holds the offsets of the bodies (bodies.concat)."""
+    entry holds the offsets of the bodies (bodies.concat).  dot(u1, u2, cache[, i]) scales as the cache does
+    (src/cache.jl:826-858)."""
+    w, bl, i = _cache_args(u1, w, bl, i)
     if isinstance(w, A.PhysicalGrid):
         _same_grid_type(u1, u2, w)
         tot = 0.0
@@ -73,7 +101,7 @@ def dot(u1, u2, w, bl=None, i=None):
 
 
 def norm(u, w, bl=None, i=None):
-    """norm(u, g) (:110) / norm(u, ds[, bl, i]) (:175-183)."""
+    """norm(u, g) (:110) / norm(u, ds[, bl, i]) (:175-183) / norm(u, cache[, i]) (src/cache.jl:815-842)."""
     return float(np.sqrt(dot(u, u, w, bl, i)))
 
 
@@ -139,7 +167,9 @@ def _slices(o):
 
 def integrate(u, w, bl=None, i=None):
     """integrate(u, g) (:142-144): a number for scalar grid data, a list per component for Edges / EdgeGradient;
-    integrate(u, ds[, bl, i]) (:192-206): surface integral of ScalarData (number) or VectorData (pair)."""
+    integrate(u, ds[, bl, i]) (:192-206): surface integral of ScalarData (number) or VectorData (pair);
+    integrate(u, cache[, i]) (src/cache.jl:868-899): the same with the cache's grid / areas, whatever its scaling."""
+    w, bl, i = _cache_args(u, w, bl, i, for_integral=True)
     if isinstance(w, A.PhysicalGrid):
         comps = _components(u, w)
         vals = [float(np.sum(_weights(a.shape, lay) * a)) * w.dx ** 2 for a, lay in comps]
@@ -170,7 +200,9 @@ def pointwise_dot(a, b):
 
 # ---- body lists: a body tuple (x, y, nx, ny, ds, first) with the offsets of the bodies (bodies.concat)
 def body_range(bl, i):
-    """Index range of body i (1-based, as in view(v, bl, i), src/tools.jl:57)."""
+    """Index range of body i (1-based, as in view(v, bl, i), src/tools.jl:57); bl: a body tuple or a cache."""
+    if isinstance(bl, A.SurfaceScalarCache):
+        bl = _cache_bl(bl)
     first = np.asarray(bl[5]) if len(bl) > 5 else np.array([0, len(bl[0])])
     if not 1 <= i <= len(first) - 1:
         raise DimensionMismatch(f"body index {i} of a list of {len(first) - 1} bodies")

@@ -389,3 +389,34 @@ def test_tools_inner_products_and_body_lists():
     assert np.array_equal(T.view(fv, bl, 1)[0], T.view(gv, bl, 1)[0]) and np.array_equal(T.view(fv, bl, 1)[1], T.view(gv, bl, 1)[1])
     # the added-mass integral of examples/neumann.ipynb cell 37 has this form: -integrate(df o nrm, ds, bl, 2)
     assert isinstance(T.integrate(nl, dsl, bl, 2), list)
+
+
+def test_tools_cache_forms():
+    """dot / norm / integrate / view with a cache argument (src/cache.jl:815-909): GridScaling weighs by dx^2 / ds,
+    IndexScaling by plain sums, integrate always uses the areas.  The cache is a stand-in without a device plan."""
+    import ilm_b200 as ilm
+    from ilm_b200 import tools as T
+
+    class HostOnlyCache(ilm.SurfaceScalarCache):
+        def __init__(self, body, g, scaling):
+            self.g, self.scaling, self.N, self.device = g, scaling, len(body[0]), False
+            self.areas_ = np.asarray(body[4])
+            self.body_first = np.asarray(body[5])
+
+        def __del__(self):
+            pass
+
+    g = ilm.PhysicalGrid(64, 64, 0.05, (32, 32))
+    body = ilm.bodies.circle(1.0, 0.07)
+    bl = ilm.bodies.concat(body, body)
+    n = len(body[0])
+    cg, ci = HostOnlyCache(bl, g, ilm.GridScaling), HostOnlyCache(bl, g, ilm.IndexScaling)
+    w = ilm.Nodes(ilm.Primal, g).fill(2.0)
+    assert T.dot(w, w, cg) == T.dot(w, w, g) and abs(T.dot(w, w, ci) - T.dot(w, w, g) / g.dx ** 2) < 1e-9
+    assert T.integrate(w, cg) == T.integrate(w, ci) == T.integrate(w, g)
+    f = ilm.ScalarData(2 * n).fill(1.0)
+    ds = ilm.ScalarData(2 * n, data=bl[4].copy())
+    assert T.dot(f, f, cg) == T.dot(f, f, ds) and T.dot(f, f, ci) == 2.0 * n
+    assert T.dot(f, f, cg, 2) == T.dot(f, f, ds, bl, 2) and T.dot(f, f, ci, 2) == float(n)
+    assert T.integrate(f, ci, 1) == T.integrate(f, ds, bl, 1) and T.norm(f, ci, 1) == np.sqrt(n)
+    assert T.view(f, cg, 2).shape == (n,)
