@@ -27,6 +27,7 @@ WANT = [
     ("heatconduction_state_size", "heatconduction.ipynb", "state(u0)", "Nodes{Primal,408,408}: grid size"),
     ("heatconduction_T_t0051", "heatconduction.ipynb", "Tfcn(-0.9,0)", "T(-0.9, 0) at t = 0.0051"),
     ("heatconduction_T_t0054", "heatconduction.ipynb", "Tfcn_array[4](-0.9,0)", "T(-0.9, 0) at t = 0.0054"),
+    ("heatconduction_maxvelocity", "heatconduction.ipynb", "maxvelocity(body,x,m)", "max surface speed of the deforming circle, its point index"),
     ("neumann_added_mass", "neumann.ipynb", "M = -integrate(df", "added-mass integral of the Neumann solve"),
     ("multbodies_volume", "multbodies.ipynb", "V3 = integrate(pointwise_dot(pts,nrm),cache,3)", "area of body 3 by the divergence theorem"),
 ]

@@ -272,3 +272,22 @@ def test_notebook_multbodies_volume(nbvals):
     placed at (-1, 1)."""
     x, y, nx, ny, ds = ilm.bodies.circle(0.5, 1.4 * 0.01, center=(-1.0, 1.0))
     assert abs(np.sum((x * nx + y * ny) * ds) - nbvals["multbodies_volume"]["values"][0]) < 1e-12
+
+
+def test_notebook_circle_endpoints(nbvals):
+    """examples/heatconduction.ipynb cell 69: maxvelocity of Circle(1, 1.4 dx) under the deformation u = xy/4, v = (x^2-y^2)/4
+    is 0.24998770586539437 at point 225.  RigidBodyTools averages the velocities of a segment's END points; with the
+    midpoints ON the circle at theta_k = 2 pi k / N (ilm.bodies.circle) the end points sit at radius 1/cos(pi/N), which
+    gives (1 - tan^2(pi/N))/4 at theta = pi -- the circumscribed-polygon convention that also reproduces sum(ds)."""
+    nums = nbvals["heatconduction_maxvelocity"]["numbers"]
+    x, y, nx, ny, ds = ilm.bodies.circle(1.0, 1.4 * 0.01)
+    n = len(x)
+    th = np.arctan2(y, x)
+    rho, a = 1.0 / np.cos(np.pi / n), np.pi / n
+    xe = rho * np.cos(th[:, None] + np.array([-a, a])[None, :])
+    ye = rho * np.sin(th[:, None] + np.array([-a, a])[None, :])
+    u, v = (0.25 * xe * ye).mean(axis=1), (0.25 * (xe ** 2 - ye ** 2)).mean(axis=1)
+    speed = np.hypot(u, v)
+    k = int(nums[1]) - 1
+    assert abs(speed[k] - nums[0]) < 1e-12 and abs(speed.max() - nums[0]) < 1e-12
+    assert abs(x[k] + 1.0) < 1e-12 and abs(y[k]) < 1e-12
