@@ -665,9 +665,23 @@ class ScalarCache:
             A[:, jc] = sign * scale * post(g)
         return A
 
+    def apply_schur(self, which, x, scale=1.0):
+        """The operator a Schur builder tabulates, applied to a vector: sign*scale*post(L^-1 pre(x)) --
+        one column-probe composition (src/matrix_operators.jl:9-30 with e_c replaced by x; the builders
+        are linear).  `which`: "RTLinvR", "CLinvCT", "GLinvD", "GLinvD_cross"."""
+        pre, post = {"RTLinvR": (self.regularize, self.interpolate),
+                     "CLinvCT": (self.surface_curl_s2n, self.surface_curl_n2s),
+                     "GLinvD": (self.surface_divergence, self.surface_grad),
+                     "GLinvD_cross": (self.surface_divergence_cross, self.surface_grad_cross)}[which]
+        return -scale * post(self.inverse_laplacian(pre(np.asarray(x, float))))
+
     def create_RTLinvR(self, scale=1.0, cols=None):
         """src/matrix_operators.jl:9-30: A[:,c] = -scale*E L^-1 R e_c."""
         return self._probe(self.regularize, self.interpolate, -1.0, scale, cols)
+
+    def create_RTLinvR_table(self, scale=1.0, cols=None):
+        """create_RTLinvR without the FFT: table form with the LGF (table_schur)."""
+        return table_schur(self.tabs[PRIMAL], self.lgf, c0=self.c0, coef=-scale / self.factor, cols=cols)
 
     def create_CLinvCT(self, scale=1.0, cols=None):
         """src/matrix_operators.jl:40-61."""
@@ -703,6 +717,59 @@ class ScalarCache:
         rowsum[rowsum == 0.0] = 1.0
         Ef = E_matrix(tab) @ sp.diags(1.0 / rowsum)
         return np.asarray((Ef @ R).todense(), order="F")
+
+
+def _c_lib():
+    """oracle/direct_conv.c built by oracle/Makefile (test infrastructure)."""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "libilm_oracle_c.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", here])
+    return ctypes.CDLL(so)
+
+
+def table_schur(tab, K, c0=0.0, coef=1.0, cols=None):
+    """A[k,c] = coef * sum_p sum_q wE[k,p] (K(p-q) - c0) wR[c,q]: the regularize -> convolve -> interpolate
+    probe of src/matrix_operators.jl:9-30 with the unit-vector loop written out as a table look-up
+    (long-double accumulation in oracle/direct_conv.c).  The FFT never enters, which
+    makes it the independent full-size check of create_RTLinvR and of the IF-HERK stage complements.
+    `K`: kernel table (G for L^-1, the plan_intfact table for exp(L a)); entries beyond it count as zero."""
+    import ctypes
+    N, W = tab.N, tab.W
+    lo, hi = (0, N) if cols is None else cols
+    a = np.arange(W)
+    ii = np.broadcast_to(tab.i0[:, None, None] + a[None, :, None], (N, W, W))
+    jj = np.broadcast_to(tab.j0[:, None, None] + a[None, None, :], (N, W, W))
+    pi = np.ascontiguousarray(np.where(tab.valid, ii, -1).reshape(N, W * W), dtype=np.int64)
+    pj = np.ascontiguousarray(np.where(tab.valid, jj, -1).reshape(N, W * W), dtype=np.int64)
+    wE = np.ascontiguousarray(tab.wE.reshape(N, W * W))
+    wR = np.ascontiguousarray(tab.wR.reshape(N, W * W))
+    K = np.asfortranarray(K, dtype=np.float64)
+    A = np.zeros((N, hi - lo), order="F")
+    vp = ctypes.c_void_p
+    _c_lib().ilm_oracle_table_schur(vp(K.ctypes.data), K.shape[0], min(K.shape), N, W * W, vp(pi.ctypes.data),
+                                    vp(pj.ctypes.data), vp(wE.ctypes.data), vp(wR.ctypes.data), lo, hi,
+                                    ctypes.c_double(c0), ctypes.c_double(coef), vp(A.ctypes.data))
+    return A
+
+
+def refined_solve(matvec, b, lu_approx, tol=1e-14, maxit=8):
+    """Solve A x = b where A is only available as the ORACLE's operator `matvec` (one probe-like
+    composition pre -> L^-1 -> post per application), by iterative refinement preconditioned with the
+    LU factors of an approximation of A (any matrix close to A: it steers convergence only, the fixed
+    point satisfies the oracle's own equations).  Returns (x, relative residual)."""
+    x = scipy.linalg.lu_solve(lu_approx, b)
+    res = np.inf
+    for _ in range(maxit):
+        r = b - matvec(x)
+        res = np.abs(r).max() / max(np.abs(b).max(), 1e-300)
+        if res < tol:
+            break
+        x = x + scipy.linalg.lu_solve(lu_approx, r)
+    return x, res
 
 
 class VectorCache(ScalarCache):
@@ -839,6 +906,13 @@ class VectorCache(ScalarCache):
             A[:, jc] = sign * scale * np.concatenate(out)
         return A
 
+    def apply_CL2invCT(self, x, scale=1.0):
+        """create_CL2invCT's operator applied to a VectorData x = [u; v] (src/matrix_operators.jl:102-125)."""
+        N = self.N
+        g = self.surface_curl_v2n(x[:N], x[N:])
+        g = self.inverse_laplacian(self.inverse_laplacian(g))
+        return -scale * np.concatenate(self.surface_curl_n2v(g))
+
     def create_RTLinvR_v(self, scale=1.0, cols=None):
         return self._probe_v(self.regularize_edges, self.interpolate_edges, -1.0, scale, cols=cols)
 
@@ -868,41 +942,44 @@ class VectorCache(ScalarCache):
     create_CLinvCT_scalar = ScalarCache.create_CLinvCT
 
 
-def dirichlet_solve(cache, fplus, fminus=None, S=None):
+def dirichlet_solve(cache, fplus, fminus=None, S=None, solve=None):
     """Block-LU Dirichlet Poisson (test/literate/dirichlet.jl:71-107).
-    Returns (f, s, S)."""
+    Returns (f, s, S).  `solve`: optional b -> S^-1 b (e.g. refined_solve on apply_schur) used instead of
+    building and factoring S -- the full-size checks cannot afford N oracle probes."""
     fminus = np.zeros_like(fplus) if fminus is None else fminus
     d = fplus - fminus
     fb = 0.5 * (fplus + fminus)
     fstar = cache.surface_divergence(d)
     fstar = cache.inverse_laplacian(fstar)
-    if S is None:
+    if S is None and solve is None:
         S = cache.create_RTLinvR()
     s = cache.interpolate(fstar)
     s = fb - s
-    s = -scipy.linalg.lu_solve(scipy.linalg.lu_factor(S), s)
+    s = -solve(s) if solve is not None else -scipy.linalg.lu_solve(scipy.linalg.lu_factor(S), s)
     f = cache.regularize(s)
     f = cache.inverse_laplacian(f)
     f = f + fstar
     return f, s, S
 
 
-def neumann_solve(cache, vnplus, vnminus=None, S=None):
+def neumann_solve(cache, vnplus, vnminus=None, S=None, solve=None):
     """Block-LU Neumann Poisson with streamfunction (test/literate/neumann.jl:101-142).
     Returns (f, df, s, ds, S)."""
     vnminus = np.zeros_like(vnplus) if vnminus is None else vnminus
     dvn = vnplus - vnminus
     vn = 0.5 * (vnplus + vnminus)
-    if S is None:
-        S = cache.create_CLinvCT()
-    lu = scipy.linalg.lu_factor(S)
+    if solve is None:
+        if S is None:
+            S = cache.create_CLinvCT()
+        lu = scipy.linalg.lu_factor(S)
+        solve = lambda b: scipy.linalg.lu_solve(lu, b)      # noqa: E731
     fstar = cache.inverse_laplacian(cache.regularize(dvn))
     df = cache.surface_grad(fstar)
     df = vn - df
-    df = -scipy.linalg.lu_solve(lu, df)
+    df = -solve(df)
     f = cache.inverse_laplacian(cache.surface_divergence(df)) + fstar
     sstar = cache.surface_curl_s2n(df)
-    ds = scipy.linalg.lu_solve(lu, cache.surface_grad_cross(fstar))
+    ds = solve(cache.surface_grad_cross(fstar))
     s = cache.surface_curl_cross_s2n(ds)
     s = (s - sstar) * -1.0
     s = cache.inverse_laplacian(s)
@@ -936,7 +1013,7 @@ def dot_surface(a, b, ds):
 # --------------------------------------------------------------------------
 # IF-HERK step of the constrained heat equation (config C3)
 # --------------------------------------------------------------------------
-def heat_ifherk_step(cache, T, t, dt, kappa, tab_a, tab_c, tables, Tplus, Tminus, reuse=None):
+def heat_ifherk_step(cache, T, t, dt, kappa, tab_a, tab_c, tables, Tplus, Tminus, reuse=None, schur="probe"):
     """One step of the half-explicit Runge-Kutta scheme with integrating factor that the reference
     reaches through ConstrainedSystems.jl's LiskaIFHERK (src/timemarching.jl:86-107,254-260;
     problem functions of test/literate/heatconduction.jl:87-129):
@@ -946,7 +1023,9 @@ def heat_ifherk_step(cache, T, t, dt, kappa, tab_a, tab_c, tables, Tplus, Tminus
     examples/heatconduction.ipynb (cells 58, 62): T(-0.9, 0) after 51 and 54 steps is reproduced to 2e-14
     (tests/test_golden.py::test_notebook_heatconduction_time_marching).
     `reuse`: a dict that keeps the convolution plans and the LU factors of the stage complements between steps
-    (static body); None rebuilds them every step (moving body)."""
+    (static body); None rebuilds them every step (moving body).
+    `schur`: "probe" builds S_i column by column as the reference does; "table" uses the FFT-free table form
+    (table_schur), the same matrix up to rounding, affordable at BASELINE sizes (2048^2, N = 2295)."""
     g = cache.grid
     N = cache.N
     tp = cache.tabs[PRIMAL]
@@ -958,7 +1037,7 @@ def heat_ifherk_step(cache, T, t, dt, kappa, tab_a, tab_c, tables, Tplus, Tminus
         if a == 0.0:
             return wf
         if reuse is None:
-            return ConvPlan(tables[a][:g.NX, :g.NY]).apply(wf)
+            return ConvPlan(tables[a][:g.NX, :g.NY], workers=getattr(cache.conv, "workers", 1)).apply(wf)
         if ("plan", a) not in reuse:
             reuse[("plan", a)] = ConvPlan(tables[a][:g.NX, :g.NY], workers=getattr(cache.conv, "workers", 1))
         return reuse[("plan", a)].apply(wf)
@@ -983,11 +1062,14 @@ def heat_ifherk_step(cache, T, t, dt, kappa, tab_a, tab_c, tables, Tplus, Tminus
                 U = U + (dt * tab_a[i][j]) * w[j]
         # S_i = -E H_i R, column by column like create_RTLinvR (src/matrix_operators.jl:9-30)
         if reuse is None or ("lu", a) not in reuse:
-            S = np.zeros((N, N))
-            for col in range(N):
-                e = np.zeros(N)
-                e[col] = 1.0
-                S[:, col] = -interpolate(tp, H(regularize(tp, e), a))
+            if schur == "table":
+                S = table_schur(tp, tables[a][:g.NX, :g.NY] if a != 0.0 else np.ones((1, 1)), coef=-1.0)
+            else:
+                S = np.zeros((N, N))
+                for col in range(N):
+                    e = np.zeros(N)
+                    e[col] = 1.0
+                    S[:, col] = -interpolate(tp, H(regularize(tp, e), a))
             if reuse is not None:
                 reuse[("lu", a)] = scipy.linalg.lu_factor(S)
         b = 0.5 * (sval(Tplus, t + c * dt) + sval(Tminus, t + c * dt))
@@ -1003,7 +1085,7 @@ def heat_ifherk_step(cache, T, t, dt, kappa, tab_a, tab_c, tables, Tplus, Tminus
     return U, sig
 
 
-def stokes_solve(cache, vplus, vminus=None):
+def stokes_solve(cache, vplus, vminus=None, solve_S=None, solve_Ss=None):
     """`solve(prob::StokesFlowProblem, sys)` of test/literate/stokes.jl:98-166 on a VectorCache (without the
     final `C^2 * sigma` traction filter).  vplus / vminus: (2N,) [u; v].  Returns (vu, vv, s, sigma)."""
     N = cache.N
@@ -1021,14 +1103,13 @@ def stokes_solve(cache, vplus, vminus=None):
     cu, cv = cache.curl_n2e(sstar)
     eu, ev = cache.interpolate_edges(cu, cv)
     vprime = vprime - np.concatenate([eu, ev])
-    S = cache.create_CL2invCT()
-    sigma = np.linalg.solve(S, vprime)
+    sigma = solve_S(vprime) if solve_S is not None else np.linalg.solve(cache.create_CL2invCT(), vprime)
     s = -1.0 * cache.surface_curl_v2n(sigma[:N], sigma[N:])
     s = cache.inverse_laplacian(cache.inverse_laplacian(s)) + sstar
     cu, cv = cache.curl_n2e(s)
     vu, vv = cu + pu, cv + pv
     ds = cache.surface_grad_cross(phi)
-    ds = np.linalg.solve(cache.create_CLinvCT(), ds)
+    ds = solve_Ss(ds) if solve_Ss is not None else np.linalg.solve(cache.create_CLinvCT(), ds)
     s = s + cache.inverse_laplacian(-1.0 * cache.surface_curl_cross_s2n(ds))
     return vu, vv, s, sigma
 

@@ -510,3 +510,65 @@ def test_unbounded_heat_step_conserves_point_heating():
         T = o.heat_unbounded_step(g, T, n * dt, dt, kappa, tab["a"], tab["c"], tables,
                                   lambda TT, t: o.forcing_line(np.zeros_like(TT), tabp, np.full(1, 5.0)))
     assert abs(T.sum() * g.dx ** 2 - 5.0 * 4 * dt) < 1e-12
+
+
+# ---------------------------------------------------------------- FFT-free table forms (full-size checks of the GPU tests)
+def test_table_form_schur_matches_probing():
+    """oracle/direct_conv.c:ilm_oracle_table_schur (long double, no FFT) against the column-by-column
+    restatement of create_RTLinvR (src/matrix_operators.jl:9-30), incl. a clipped window and a column range."""
+    g = o.Grid(64, 48, 4.0 / 62, (32, 24))
+    x, y, nx, ny, ds = bodies.circle(1.0, 1.4 * g.dx)
+    x = x + 0.93                                             # windows clipped at the +x boundary
+    G = lgfmod.lgf_table(64)
+    c = o.ScalarCache(g, x, y, nx, ny, ds, G)
+    S = c.create_RTLinvR()
+    St = c.create_RTLinvR_table()
+    assert np.abs(S - St).max() < 1e-13 * np.abs(S).max()
+    blk = c.create_RTLinvR_table(scale=2.0, cols=(5, 9))
+    assert np.abs(blk - 2.0 * S[:, 5:9]).max() < 1e-13 * np.abs(S).max()
+    # integrating-factor table, truncated: entries beyond the table count as zero
+    E = lgfmod.intfact_table(0.5, 64)
+    plan = o.ConvPlan(E[:64, :48])
+    tp = c.tabs[o.PRIMAL]
+    Sp = np.zeros((c.N, c.N))
+    for col in range(c.N):
+        e = np.zeros(c.N); e[col] = 1.0
+        Sp[:, col] = -o.interpolate(tp, plan.apply(o.regularize(tp, e)))
+    assert np.abs(o.table_schur(tp, E[:20, :20], coef=-1.0) - Sp).max() < 1e-13 * np.abs(Sp).max()
+    ER = -(o.E_matrix(tp) @ o.R_matrix(tp)).toarray()
+    assert np.abs(o.table_schur(tp, np.ones((1, 1)), coef=-1.0) - ER).max() < 1e-14 * np.abs(ER).max()
+
+
+def test_refined_solve_converges_to_the_operator_solution():
+    """refined_solve: the fixed point solves the oracle's operator equation whatever (close) matrix preconditions it."""
+    import scipy.linalg
+    g = o.Grid(64, 64, 4.0 / 62, (32, 32))
+    body = bodies.circle(1.0, 1.4 * g.dx)
+    c = o.ScalarCache(g, *body, lgfmod.lgf_table(64))
+    S = c.create_CLinvCT()
+    b = np.random.default_rng(5).standard_normal(c.N)
+    ref = np.linalg.solve(S, b)
+    Sp = S * (1.0 + 1e-6 * np.random.default_rng(6).standard_normal(S.shape))      # a perturbed preconditioner
+    mv = lambda x: -c.surface_curl_n2s(c.inverse_laplacian(c.surface_curl_s2n(x)))  # noqa: E731
+    x, res = o.refined_solve(mv, b, scipy.linalg.lu_factor(Sp), tol=1e-13)
+    assert res < 1e-13
+    assert np.abs(S @ x - b).max() < 1e-11 * np.abs(b).max()
+    assert np.abs(x - ref).max() < 1e-6 * np.abs(ref).max()                          # cond(S)-limited
+
+
+def test_heat_step_table_form_equals_probing():
+    g = o.Grid(48, 48, 4.0 / 46, (24, 24))
+    body = bodies.circle(0.8, 1.4 * g.dx)
+    c = o.ScalarCache(g, *body, lgfmod.lgf_table(48))
+    from ilm_b200 import timemarching as tm
+    tab_a, tab_c = tm.LISKA_IFHERK["a"], tm.LISKA_IFHERK["c"]
+    dt = g.dx ** 2
+    stage_a, prev = [], 0.0
+    for cc in tab_c:
+        stage_a.append(1.0 / g.dx ** 2 * (cc - prev) * dt)
+        prev = cc
+    tables = {a: lgfmod.intfact_table(a, 48) for a in set(stage_a)}
+    T0 = np.zeros(o.field_shape(o.PRIMAL, 48, 48))
+    T1, s1 = o.heat_ifherk_step(c, T0, 0.0, dt, 1.0, tab_a, tab_c, tables, 0.0, 1.0)
+    T2, s2 = o.heat_ifherk_step(c, T0, 0.0, dt, 1.0, tab_a, tab_c, tables, 0.0, 1.0, schur="table")
+    assert np.abs(T1 - T2).max() < 1e-12 * np.abs(T1).max()
