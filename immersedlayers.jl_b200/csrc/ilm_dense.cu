@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(PR_THREADS) k_lu_panel_regs(int n, int k0, int
     double a[NB];
 #pragma unroll
     for (int c = 0; c < NB; ++c) a[c] = (has && c < nb) ? A[(size_t)(k0 + c) * n + row] : 0.0;
+    cl.sync();                                       // every CTA of the cluster is running before the first DSMEM push
     // The column loop is fully unrolled so that the register array is addressed statically.  (A rolled loop with
     // predicated static indices was tried because ncu shows 58 % no_instructions stalls on the ~250 KB of straight-line
     // code: it spills 400 B per thread at the 128-register cap and is slower, N = 4593: 23.9 -> 31.5 ms.)
@@ -637,7 +638,7 @@ k_getrs_cluster(int n, const double* __restrict__ LU, const int* __restrict__ ip
     int s = 0;
     // forward: unit lower
     if (rank == 0 && wid == 1) stage_diag(0);
-    __syncthreads();
+    cl.sync();                                       // every CTA of the cluster is running before the first DSMEM push
     for (int k = 0; k < nblk; ++k, ++s) {
         const int k0 = k * NB, nb = min(NB, n - k0);
         const bool mine = rank == k % SOLVE_CTAS, next_mine = k + 1 < nblk && rank == (k + 1) % SOLVE_CTAS;

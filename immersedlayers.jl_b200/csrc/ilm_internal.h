@@ -57,6 +57,8 @@ struct DevTable {
 
 struct ConvKernel {     // one multiplier (LGF inverse, integrating factor, ...)
     double* ghat = nullptr;
+    double* gxt = nullptr;      // x-transform of the kernel rows, [d][column] (band pass of the Schur probes, ilm_band.cu)
+    int gxt_ld = 0, gxt_rows = 0;
 };
 
 }  // namespace ilm
@@ -85,6 +87,7 @@ struct ilm_plan {
     alignas(64) unsigned char tmap_s2[128] = {};   // CUtensorMap of S2 for the current row count (pass C)
     int tmap_myp = -1;
     int skew_ns = 500;              // ILM_CONV_SKEW_NS: start-up skew between the two groups of a CTA
+    bool band = true;               // ILM_PROBE_BAND=0 sends the Schur probes through the transform column pass instead
     std::vector<ilm::ConvKernel> kernels;
     double* lgf_dev = nullptr;      // device copy of the LGF table (ld = lgf_ld), kept for the direct Schur form
     int lgf_ld = 0;
@@ -203,6 +206,10 @@ extern long long g_dense_launches;
 // per-length launchers, which = 0: pass A, 1: pass B, 2: pass C, 3: pass G
 typedef int (*conv_launch_fn)(int which, const ConvArgs& a, int nsm, cudaStream_t st, const void* tmap);
 conv_launch_fn conv_launcher(int L);
+// band pass (ilm_band.cu): the column step for right-hand sides with <= conv_band_max_rows() non-zero rows
+int conv_build_gxt(ilm_plan* p, const ConvArgs& a, ConvKernel& k, double factor);
+int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k);
+int conv_band_max_rows();
 const double2* conv_twiddles_host(int L, size_t* count);
 
 }  // namespace ilm

@@ -92,6 +92,7 @@ int conv_half_len(int n) {
 
 int conv_setup(ilm_plan* p) {
     if (const char* e = getenv("ILM_CONV_SKEW_NS")) p->skew_ns = atoi(e);
+    if (const char* e = getenv("ILM_PROBE_BAND")) p->band = atoi(e) != 0;
     p->Lx = conv_half_len(p->g.NX);
     p->Ly = conv_half_len(p->g.NY);
     if (p->Lx > 16384 || p->Ly > 16384) {
@@ -129,7 +130,7 @@ int conv_setup(ilm_plan* p) {
 
 void conv_free(ilm_plan* p) {
     cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->wl2y); cudaFree(p->wl2x); cudaFree(p->conv_scratch); cudaFree(p->S); cudaFree(p->S2);
-    for (auto& k : p->kernels) cudaFree(k.ghat);
+    for (auto& k : p->kernels) { cudaFree(k.ghat); cudaFree(k.gxt); }
     cudaFree(p->lgf_dev); p->lgf_dev = nullptr;
     p->kernels.clear();
 }
@@ -173,6 +174,7 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     a.GhatOut = k.ghat;
     a.gscale = 1.0 / (4.0 * (double)p->Lx * (double)p->Ly * factor);
     ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream, nullptr));
+    if (p->band && p->Lx <= 4096) ILM_TRY(conv_build_gxt(p, a, k, factor));   // x-spectrum of the kernel rows (Schur probes)
     ILM_TRY(conv_launcher(p->Ly)(3, a, p->nsm, p->stream, nullptr));
     p->launches += 2;
     ILM_CUDA(cudaStreamSynchronize(p->stream));
@@ -204,7 +206,9 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
     a.Ghat = p->kernels[kernel_id].ghat;
     if (use_tma(p)) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
     ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream, nullptr));
-    ILM_TRY(conv_launcher(p->Ly)(1, a, p->nsm, p->stream, nullptr));
+    const ConvKernel& k = p->kernels[kernel_id];
+    if (k.gxt && p->band && a.rhi - a.rlo <= conv_band_max_rows()) ILM_TRY(conv_launch_band(p, a, k));
+    else ILM_TRY(conv_launcher(p->Ly)(1, a, p->nsm, p->stream, nullptr));
     ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, p->stream, p->tmap_s2));
     p->launches += 3;
     return ILM_OK;
@@ -228,9 +232,12 @@ int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], 
     const int Ls[3] = {p->Lx, p->Ly, p->Lx};
     if (use_tma(p)) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
     for (int which = 0; which < 3; ++which) {
-        ILM_TRY(conv_launcher(Ls[which])(which, a, p->nsm, p->stream, p->tmap_s2));      // warm-up
+        const ConvKernel& k = p->kernels[0];
+        const bool band = which == 1 && k.gxt && p->band && a.rhi - a.rlo <= conv_band_max_rows();
+        auto launch = [&]() { return band ? conv_launch_band(p, a, k) : conv_launcher(Ls[which])(which, a, p->nsm, p->stream, p->tmap_s2); };
+        ILM_TRY(launch());                                                                // warm-up
         ILM_CUDA(cudaEventRecord(e0, p->stream));
-        for (int r = 0; r < reps; ++r) ILM_TRY(conv_launcher(Ls[which])(which, a, p->nsm, p->stream, p->tmap_s2));
+        for (int r = 0; r < reps; ++r) ILM_TRY(launch());
         ILM_CUDA(cudaEventRecord(e1, p->stream));
         ILM_CUDA(cudaEventSynchronize(e1));
         float t = 0;

@@ -31,9 +31,30 @@ WORKERS = os.cpu_count() or 1
 EPS = np.finfo(float).eps
 
 
-def relerr(a, b):
+ACHIEVED = {}
+
+
+def relerr(a, b, name=None):
     a = a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
-    return np.abs(a - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+    e = float(np.abs(a - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+    if name:
+        k, n = name, 1
+        while k in ACHIEVED:
+            n += 1
+            k = f"{name}#{n}"
+        ACHIEVED[k] = e
+    return e
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_achieved():
+    """The achieved errors go to gpurun_out/ (when it exists) so that a GPU run leaves a record for profiles/."""
+    yield
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out) and ACHIEVED:
+        with open(os.path.join(out, "baseline_size_parity_errors.json"), "w") as fh:
+            json.dump(ACHIEVED, fh, indent=1, sort_keys=True)
 
 
 def spread_columns(n, count, extra=()):
@@ -53,15 +74,26 @@ def test_dirichlet_4096_full_solve_against_oracle():
     f, s, S = ilm.dirichlet_poisson(cache, fplus)
     oc = o.ScalarCache(o.Grid(NG, NG, g.dx, g.I0), *body[:5], G, workers=WORKERS)
     Sr = oc.create_RTLinvR_table()                           # every entry of S, no FFT
-    assert relerr(S, Sr) < 1e-12
+    assert relerr(S, Sr, "dirichlet_4096_full_solve_against_oracle:S") < 1e-12
     # a few columns of the oracle's own FFT probe as well (same matrix by two routes)
     cols = [0, 1717, 4592]
-    assert relerr(Sr[:, cols], oc.create_RTLinvR(cols=cols)) < 1e-12
+    assert relerr(Sr[:, cols], oc.create_RTLinvR(cols=cols), "dirichlet_4096_full_solve_against_oracle:Sr") < 1e-12
     fr, sr, _ = o.dirichlet_solve(oc, fplus, S=Sr)
-    assert relerr(f.array(), fr) < 1e-12
+    # The multiplier solves a first-kind (ill-conditioned) system: two backward-stable LU solves of the same
+    # system differ by ~ cond(S) eps in s, and f inherits n eps |S||s| of that.  So: (i) s is judged by the
+    # residual of the ORACLE's system, (ii) the field by the oracle's operators applied to the same multiplier
+    # (1e-12), (iii) the end-to-end numbers at the conditioning-aware tolerances.
+    fstar_r = oc.inverse_laplacian(oc.surface_divergence(fplus))
+    rhs = 0.5 * fplus - oc.interpolate(fstar_r)
+    sg = np.asarray(s.data)
+    res = np.abs(Sr @ (-sg) - rhs).max()
+    assert res < 1e-12 * (np.abs(Sr).sum(axis=1).max() * np.abs(sg).max())          # backward error ~ eps
+    f_from_sg = oc.inverse_laplacian(oc.regularize(sg)) + fstar_r
+    assert relerr(f.array(), f_from_sg, "dirichlet_4096_full_solve_against_oracle:f_array") < 1e-12
     cond = np.linalg.cond(Sr)
-    assert relerr(s.data, sr) < 50 * cond * EPS
-    # the constraint itself: E f = f+ / 2 ... (f- = 0): interpolated field equals the average of the data
+    assert relerr(s.data, sr, "dirichlet_4096_full_solve_against_oracle:s_data") < 50 * cond * EPS
+    assert relerr(f.array(), fr, "dirichlet_4096_full_solve_against_oracle:f_array") < 1e-9
+    # the constraint itself (f- = 0): the interpolated field equals the average of the boundary data
     fb = cache.zeros_surface()
     ilm.interpolate(fb, f, cache)
     assert np.abs(fb.data - 0.5 * fplus).max() < 1e-10
@@ -79,10 +111,10 @@ def test_c2_neumann_1024_against_oracle():
     assert 850 < N < 920
     cols = spread_columns(N, 32)
     S = np.asarray(ilm.create_CLinvCT(cache))
-    assert relerr(S[:, cols], oc.create_CLinvCT(cols=cols)) < 1e-12
+    assert relerr(S[:, cols], oc.create_CLinvCT(cols=cols), "c2_neumann_1024_against_oracle:S") < 1e-12
     A = np.asarray(ilm.create_RTLinvR(cache))
-    assert relerr(A[:, cols], oc.create_RTLinvR(cols=cols)) < 1e-12
-    assert relerr(A, oc.create_RTLinvR_table()) < 1e-12
+    assert relerr(A[:, cols], oc.create_RTLinvR(cols=cols), "c2_neumann_1024_against_oracle:A") < 1e-12
+    assert relerr(A, oc.create_RTLinvR_table(), "c2_neumann_1024_against_oracle:A") < 1e-12
     # the solve, every output
     vnp = cache.normals()[0].copy()                          # v_n+ = n_x (neumann.jl:166-172)
     lu = scipy.linalg.lu_factor(S)
@@ -96,9 +128,22 @@ def test_c2_neumann_1024_against_oracle():
     fr, dfr, sr, dsr, _ = o.neumann_solve(oc, vnp, solve=solve)
     assert max(residuals) < 1e-12
     f, df, s, ds = ilm.neumann_poisson(cache, vnp, S=S)
-    assert relerr(f.array(), fr) < 1e-12 and relerr(s.array(), sr) < 1e-12
     tol = 50 * np.linalg.cond(S) * EPS
-    assert relerr(df.data, dfr) < tol and relerr(ds.data, dsr) < tol
+    assert relerr(df.data, dfr, "c2_neumann_1024_against_oracle:df_data") < tol and relerr(ds.data, dsr, "c2_neumann_1024_against_oracle:ds_data") < tol
+    assert relerr(f.array(), fr, "c2_neumann_1024_against_oracle:f_array") < 1e-9 and relerr(s.array(), sr, "c2_neumann_1024_against_oracle:s_array") < 1e-9
+    # operator parity at 1e-12: the oracle's operators applied to the SAME multipliers (the two solves are
+    # replaced by the GPU's df, ds; their right-hand sides are captured for the residual check)
+    given, seen = [-np.asarray(df.data), np.asarray(ds.data)], []
+
+    def inject(b):
+        seen.append(b)
+        return given[len(seen) - 1]
+
+    f2, _, s2, _, _ = o.neumann_solve(oc, vnp, solve=inject)
+    assert relerr(f.array(), f2, "c2_neumann_1024_against_oracle:f_array") < 1e-12 and relerr(s.array(), s2, "c2_neumann_1024_against_oracle:s_array") < 1e-12
+    Snorm = np.abs(S).sum(axis=1).max()
+    for x, b in zip(given, seen):                            # backward error of the GPU solves in the oracle's system
+        assert np.abs(oc.apply_schur("CLinvCT", x) - b).max() < 1e-12 * Snorm * np.abs(x).max()
 
 
 # ---------------------------------------------------------------- C3: 2048^2, moving circle, IF-HERK
@@ -122,8 +167,8 @@ def test_c3_moving_body_heat_2048_three_steps():
         T, sig = o.heat_ifherk_step(oc, T, t, prob.dt, 1.0, prob.tab_a, prob.tab_c, tables, 0.0, 1.0, schur="table")
         prob.step()
         t += prob.dt
-        assert relerr(prob.T.array(), T) < 1e-11, n
-        assert relerr(prob.sigma, sig) < 1e-5, n
+        assert relerr(prob.T.array(), T, "c3_moving_body_heat_2048_three_steps:prob_T_array") < 1e-11, n
+        assert relerr(prob.sigma, sig, "c3_moving_body_heat_2048_three_steps:prob_sigma") < 1e-5, n
     assert prob.stats["plan_refreshes"] == 2
 
 
@@ -141,11 +186,11 @@ def test_c4_multibody_4096_probe_columns_against_oracle():
     for lo in (b1 - 3, b8 - 3):                              # 2 x 6 columns straddling a body boundary
         blk = np.asarray(ilm.create_RTLinvR(cache, cols=(lo, lo + 6)))
         ref = oc.create_RTLinvR(cols=list(range(lo, lo + 6)))
-        assert relerr(blk, ref) < 1e-12
-        assert relerr(ref, oc.create_RTLinvR_table(cols=(lo, lo + 6))) < 1e-12
+        assert relerr(blk, ref, "c4_multibody_4096_probe_columns_against_oracle:blk") < 1e-12
+        assert relerr(ref, oc.create_RTLinvR_table(cols=(lo, lo + 6)), "c4_multibody_4096_probe_columns_against_oracle:ref") < 1e-12
     # ... and the whole matrix against the table form
     S = np.asarray(ilm.create_RTLinvR(cache))
-    assert relerr(S, oc.create_RTLinvR_table()) < 1e-12
+    assert relerr(S, oc.create_RTLinvR_table(), "c4_multibody_4096_probe_columns_against_oracle:S") < 1e-12
     assert N == S.shape[0]
 
 
@@ -161,10 +206,10 @@ def test_c5a_stokes_1024_against_oracle():
     assert 500 < N < 600
     cols = spread_columns(2 * N, 32, extra=(N - 1, N))
     S = np.asarray(ilm.create_CL2invCT(cache))
-    assert relerr(S[:, cols], oc.create_CL2invCT(cols=cols)) < 1e-12
+    assert relerr(S[:, cols], oc.create_CL2invCT(cols=cols), "c5a_stokes_1024_against_oracle:S") < 1e-12
     Ss = np.asarray(ilm.create_CLinvCT_scalar(cache))
     cs = spread_columns(N, 16)
-    assert relerr(Ss[:, cs], oc.create_CLinvCT_scalar(cols=cs)) < 1e-12
+    assert relerr(Ss[:, cs], oc.create_CLinvCT_scalar(cols=cs), "c5a_stokes_1024_against_oracle:Ss") < 1e-12
     lu, lus = scipy.linalg.lu_factor(S), scipy.linalg.lu_factor(Ss)
     residuals = []
 
@@ -182,6 +227,17 @@ def test_c5a_stokes_1024_against_oracle():
     vu, vv, sr, sigr = o.stokes_solve(oc, vplus, solve_S=solve_S, solve_Ss=solve_Ss)
     assert max(residuals) < 1e-12
     v, s, sigma, _, _ = ilm.stokes_flow(cache, vplus, S=ilm.LU(S), Ss=ilm.LU(Ss))
-    assert relerr(v.u, vu) < 1e-11 and relerr(v.v, vv) < 1e-11
-    assert relerr(s.array(), sr) < 1e-11
-    assert relerr(sigma.data, sigr) < 50 * np.linalg.cond(S) * EPS
+    assert relerr(v.u, vu, "c5a_stokes_1024_against_oracle:v_u") < 1e-9 and relerr(v.v, vv, "c5a_stokes_1024_against_oracle:v_v") < 1e-9 and relerr(s.array(), sr, "c5a_stokes_1024_against_oracle:s_array") < 1e-9
+    assert relerr(sigma.data, sigr, "c5a_stokes_1024_against_oracle:sigma_data") < 50 * np.linalg.cond(S) * EPS
+    # operator parity at 1e-12: the oracle's operators around the GPU's traction (the scalar solve is refined
+    # on the oracle's operator as before: its right-hand side does not depend on sigma)
+    seen = []
+
+    def inject(b):
+        seen.append(b)
+        return np.asarray(sigma.data)
+
+    vu2, vv2, s2, _ = o.stokes_solve(oc, vplus, solve_S=inject, solve_Ss=solve_Ss)
+    assert relerr(v.u, vu2, "c5a_stokes_1024_against_oracle:v_u") < 1e-12 and relerr(v.v, vv2, "c5a_stokes_1024_against_oracle:v_v") < 1e-12 and relerr(s.array(), s2, "c5a_stokes_1024_against_oracle:s_array") < 1e-12
+    Snorm = np.abs(S).sum(axis=1).max()
+    assert np.abs(oc.apply_CL2invCT(np.asarray(sigma.data)) - seen[0]).max() < 1e-12 * Snorm * np.abs(sigma.data).max()

@@ -580,3 +580,31 @@ def test_convective_terms_full_size():
     ilm.w_cross_v(res, w, q, cache)
     r = res.data.cpu().numpy()
     assert np.abs(r[:nu].reshape(u.shape, order="F")[2:-2, 2:-2] + 2 * Om ** 2 * xu[2:-2, None]).max() < 1e-9
+
+
+# ---------------------------------------------------------------- band pass of the Schur probes (ilm_band.cu)
+@pytest.mark.parametrize("ddf", ["yang3", "m4prime", "roma"])
+def test_probe_band_pass_equals_transform_pass(ddf, monkeypatch):
+    """The Schur probes replace the column transform by the direct sum over the patch rows
+    (Y_n = sum_r x_r Gx(|n-r|), csrc/ilm_band.cu).  ILM_PROBE_BAND=0 keeps the transform column pass: both
+    routes give the same matrices, for every builder, on an odd non-square grid with clipped windows,
+    and with another kernel (integrating factor)."""
+    g = ilm.PhysicalGrid(91, 67, 4.0 / 89, (45, 33))
+    x, y, nx, ny, ds = ilm.bodies.circle(1.0, 1.4 * g.dx)
+    body = (x + 0.93, y - 0.4, nx, ny, ds)                   # windows clipped at +x and -y
+    G = ilm.lgf.lgf_table(96)
+    built = {}
+    for band in ("1", "0"):
+        monkeypatch.setenv("ILM_PROBE_BAND", band)
+        cache = ilm.SurfaceScalarCache(body, g, lgf_table=G, ddftype=ddf)
+        vc = ilm.SurfaceVectorCache(body, g, lgf_table=G, ddftype=ddf)
+        kid = cache.add_kernel(ilm.lgf.intfact_table(0.5, 96))
+        built[band] = [ilm.create_RTLinvR(cache), ilm.create_CLinvCT(cache), ilm.create_GLinvD(cache),
+                       ilm.create_GLinvD_cross(cache, cols=(3, 10)), ilm.create_RTHR(cache, kid),
+                       ilm.create_CL2invCT(vc), ilm.create_CLinvCT(vc), ilm.create_RTLinvR(vc), ilm.create_GLinvD(vc, cols=(0, 9))]
+    for a, b in zip(built["1"], built["0"]):
+        assert relerr(a, b) < 1e-13
+    if ddf == "yang3":
+        oc = o.ScalarCache(o.Grid(g.NX, g.NY, g.dx, g.I0), *body, G)
+        assert relerr(built["1"][0], oc.create_RTLinvR()) < RTOL
+        assert relerr(built["1"][0], oc.create_RTLinvR_table()) < RTOL
