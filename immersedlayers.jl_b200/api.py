@@ -1350,3 +1350,65 @@ def w_cross_v(vw, w, v, cache):
     L.check(cache._lib.ilm_w_cross_v(cache._plan, _ptr(w.data), _ptr(v.data), _ptr(vw.data)))
     return vw
 
+
+
+# --------------------------------------------------------------------------
+# Every operator validates its containers against the cache before the C call: the library copies
+# `ilm_layout_size(plan, layout)` doubles through the raw pointers, so a container built on another grid (or
+# point data of another length) would be a host heap overrun / device out-of-bounds access.  The reference gets
+# this from the NX, NY type parameters (MethodError) and the length asserts of src/tools.jl:85,102.
+# --------------------------------------------------------------------------
+def _expected_len(d, cache):
+    g, N = cache.g, cache.N
+    if isinstance(d, (Nodes, _EdgeComponent)):
+        mx, my = g.layout_shape(d.layout)
+        return mx * my
+    if isinstance(d, Edges):
+        (ux, uy), (vx, vy) = g.layout_shape(L.XEDGES), g.layout_shape(L.YEDGES)
+        return ux * uy + vx * vy
+    if isinstance(d, EdgeGradient):
+        (px, py), (dx_, dy_) = g.layout_shape(L.NODES_PRIMAL), g.layout_shape(L.NODES_DUAL)
+        return 2 * px * py + 2 * dx_ * dy_
+    if isinstance(d, TensorData):
+        return 4 * N
+    if isinstance(d, VectorData):
+        return 2 * N
+    if isinstance(d, ScalarData):
+        return N
+    return None
+
+
+def _check_containers(what, args):
+    cache = next((a for a in reversed(args) if isinstance(a, SurfaceScalarCache)), None)
+    if cache is None:
+        return
+    for a in args:
+        if isinstance(a, _Data):
+            n = _expected_len(a, cache)
+            if n is not None and len(a) != n:
+                raise DimensionMismatch(f"{what}: {type(a).__name__} of length {len(a)} does not belong to this cache "
+                                        f"(grid {cache.g.NX} x {cache.g.NY}, {cache.N} points: expected {n})")
+
+
+def _checked(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        _check_containers(fn.__name__, args)
+        return fn(*args, **kwargs)
+    return wrapper
+
+
+def _wrap_operators():
+    import inspect
+    g = globals()
+    for name, fn in list(g.items()):
+        if name.startswith("_") or not inspect.isfunction(fn) or fn.__module__ != __name__:
+            continue
+        params = inspect.signature(fn).parameters
+        if "cache" in params or any(p.kind is inspect.Parameter.VAR_POSITIONAL for p in params.values()):
+            g[name] = _checked(fn)
+
+
+_wrap_operators()

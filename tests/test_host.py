@@ -420,3 +420,39 @@ def test_tools_cache_forms():
     assert T.dot(f, f, cg, 2) == T.dot(f, f, ds, bl, 2) and T.dot(f, f, ci, 2) == float(n)
     assert T.integrate(f, ci, 1) == T.integrate(f, ds, bl, 1) and T.norm(f, ci, 1) == np.sqrt(n)
     assert T.view(f, cg, 2).shape == (n,)
+
+
+def test_operators_reject_containers_of_another_grid():
+    """every operator checks that its grid / point containers belong to the cache's grid before
+    the C call (the library copies ilm_layout_size doubles through the raw pointer).  No GPU needed: the check
+    fires before the plan is touched."""
+    import ilm_b200 as ilm
+    api = ilm.api
+
+    class FakeCache(api.SurfaceScalarCache):
+        def __init__(self, g, N):                      # no plan: only what the checks read
+            self.g, self.N = g, N
+
+        def __del__(self):
+            pass
+
+    g, gs = ilm.PhysicalGrid.centered(32), ilm.PhysicalGrid.centered(16)
+    cache = FakeCache(g, 10)
+    P, D, E = ilm.Nodes(ilm.Primal, gs), ilm.Nodes(ilm.Dual, gs), ilm.Edges(gs)
+    Pg, Dg, Eg = ilm.Nodes(ilm.Primal, g), ilm.Nodes(ilm.Dual, g), ilm.Edges(g)
+    f, fbad = ilm.ScalarData(10), ilm.ScalarData(7)
+    calls = [
+        (api.divergence, (P, Eg, cache)), (api.divergence, (Pg, E, cache)), (api.grad, (E, Pg, cache)),
+        (api.curl, (E, Dg, cache)), (api.curl, (D, Eg, cache)), (api.laplacian, (D, D, cache)),
+        (api.inverse_laplacian, (E, cache)), (api.surface_divergence, (P, f, cache)), (api.surface_grad, (f, P, cache)),
+        (api.surface_curl, (D, f, cache)), (api.surface_curl, (fbad, Dg, cache)), (api.regularize, (Eg, ilm.VectorData(9), cache)),
+        (api.interpolate, (ilm.VectorData(10), E, cache)), (api.regularize_normal, (E, f, cache)),
+        (api.normal_interpolate, (fbad, Eg, cache)), (api.convective_derivative, (E, Eg, cache)),
+        (api.w_cross_v, (Eg, D, Eg, cache)), (api.mask, (ilm.XEdges(gs), cache)), (api.complementary_mask, (P, cache)),
+        (api.regularize_normal, (ilm.EdgeGradient(gs), ilm.VectorData(10), cache)),
+        (api.normal_interpolate, (ilm.VectorData(10), ilm.EdgeGradient(gs), cache)),
+        (api.regularize_normal_dot, (Eg, ilm.TensorData(9), cache)),
+    ]
+    for fn, args in calls:
+        with pytest.raises(ilm.DimensionMismatch):
+            fn(*args)
