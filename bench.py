@@ -2,21 +2,26 @@
 """bench.py -- grid-point*solves/s of the Dirichlet Poisson hot path on B200.
 
 One "step" = one complete Dirichlet Poisson problem with an immersed circle
-(test/literate/dirichlet.jl:71-107): D_s d, L^-1, the Schur build S = -E L^-1 R
-(N column solves), LU, the surface-point solve, R s, L^-1 -- N + 2 inverse
-Laplacians on an NX x NY grid.  Metric (BASELINE.json): NX*NY*(N+2) / seconds.
+(test/literate/dirichlet.jl:71-107): the DDF tables of the body, D_s d, L^-1, the
+Schur build S = -E L^-1 R (N column solves), LU, the surface-point solve, R s,
+L^-1 -- N + 2 inverse Laplacians on an NX x NY grid.
+Metric (BASELINE.json): NX*NY*(N+2) / seconds.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 4096] [--impl reference]
 
-* `value`   : device-resident inputs (torch CUDA tensors), CUDA-event timing.
-* `e2e`     : the same step through the public API with HOST (numpy) buffers:
-              every operator call stages its inputs H2D and its result D2H.
-* `roofline`: the dominant kernel (column pass B of the FFT convolution) timed
-              alone with CUDA events on its own stream (ilm_profile_conv).
+* `value`   : boundary data resident in HBM (torch CUDA tensors), one call of
+              ilm_dirichlet_poisson per step, CUDA-event timing.
+* `e2e`     : the same call with HOST (numpy) buffers: surface points and boundary
+              data go H2D, the field and the multiplier come back D2H, every step.
+* `roofline`: the dominant kernel of the step timed alone with CUDA events on the
+              plan's stream (ilm_profile_conv_probe), beside the other passes, the
+              dense (general right-hand side) inverse Laplacian and the stencil /
+              regularize / interpolate stages (L2 flushed between repetitions).
 * `cpu_baseline` / `--impl reference`: the CPU oracle restatement of the
   reference path (the Julia reference cannot run here) on the host cores.
-N > 1 (torchrun): the N Schur columns are sharded over the ranks and exchanged
-with one NCCL all-gather; everything else is replicated (strong scaling).
+N > 1 (torchrun): the N Schur columns are sharded over the ranks inside the
+library (NCCL communicator bound to the plan, one grouped in-place broadcast);
+LU, the solve and the two remaining L^-1 are replicated (strong scaling).
 """
 import argparse
 import json
@@ -27,6 +32,13 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1, which scipy.fft's worker pool honours: the CPU arm would run on ONE
+    # core under `torch.distributed.run` (round 1: 0.67 s -> 7.5 s per probe).  The reference arm uses every core
+    # the process may run on, however it was launched.
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ.pop(_v, None)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -34,6 +46,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "grid-point-solves/s (Dirichlet Poisson with immersed body, incl. Schur build and solve)"
 UNIT = "grid-point*solves/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures at 4096^2 (profiles/r2_*_ncu_*.txt)
+NCU_TRAFFIC = {"k_passD": 277.2e6}
 
 
 def load_peaks():
@@ -98,11 +112,24 @@ def problem(grid_n):
     return g, body, G
 
 
+def workload_config(args, g, N, world):
+    """The `config` of both arms (same workload, same accounting of solves)."""
+    return {"workload": f"dirichlet_circle_{args.grid}", "grid": [g.NX, g.NY], "surface_points": int(N),
+            "solves_per_step": int(N + 2), "ddf": "yang3"}
+
+
 # ----------------------------------------------------------------------------- reference arm (CPU oracle)
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def oracle_cache(g, body, G):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ilm_oracle as o
-    return o, o.ScalarCache(o.Grid(g.NX, g.NY, g.dx, g.I0), *body[:5], G, workers=os.cpu_count() or 1)
+    return o, o.ScalarCache(o.Grid(g.NX, g.NY, g.dx, g.I0), *body[:5], G, workers=host_threads())
 
 
 def cpu_probe(oc, col):
@@ -113,25 +140,39 @@ def cpu_probe(oc, col):
 
 
 def run_reference(args, rank):
+    """The reference's own algorithm on the host cores: a step is a bounded SAMPLE of the workload -- `cols` column
+    probes (R e_c -> L^-1 -> E, one inverse Laplacian each) of the N + 2 solves of a problem; the rate
+    (grid-point*solves/s) does not depend on how many of the identical solves are timed.  At least 32 columns are
+    timed over the K steps."""
     if rank != 0:
         return
     g, body, G = problem(args.grid)
     o, oc = oracle_cache(g, body, G)
+    steps = max(args.steps, 1)
+    cols = max(1, -(-32 // steps))
+    c = 0
     for w in range(args.warmup):
-        cpu_probe(oc, w)
+        cpu_probe(oc, c % oc.N)
+        c += 1
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        cpu_probe(oc, args.warmup + k)
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    for k in range(steps):
+        for _ in range(cols):
+            cpu_probe(oc, c % oc.N)
+            c += 1
+    dt_step = (time.perf_counter() - t0) / steps
+    dt = dt_step / cols
     val = g.NX * g.NY * 1.0 / dt
-    cores = os.cpu_count() or 1
-    sample = "1 Schur column probe (R e_c -> L^-1 -> E) per step = 1 inverse Laplacian; scipy.fft (2NX-1)^2 pad"
+    cores = host_threads()
+    sample = (f"{cols} Schur column probes (R e_c -> L^-1 -> E = 1 inverse Laplacian each) per step, {cols * steps} in all, "
+              f"{dt:.3f} s each on {cores} threads; scipy.fft on the (2NX-1)^2 pad; value = rate of these solves "
+              f"(a full step is {oc.N + 2} of them: {dt * (oc.N + 2):.0f} s)")
+    cfg = workload_config(args, g, oc.N, 1)
+    cfg["note"] = "CPU oracle restatement of the reference path (Julia reference not runnable here); bounded sample"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"dirichlet_circle_{args.grid}", "grid": [g.NX, g.NY], "surface_points": int(oc.N),
-                   "solves_per_step": 1, "note": "CPU oracle restatement of the reference path (Julia reference not runnable here)"},
+        "warmup": args.warmup, "ms_per_step": dt_step * 1e3, "ms_per_full_problem_extrapolated": dt * (oc.N + 2) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -141,11 +182,12 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the per-stage roofline section")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,7 +205,7 @@ def main():
     import torch
     import torch.distributed as dist
     import ilm_b200 as ilm
-    from ilm_b200 import shard, _lib as L
+    from ilm_b200 import _lib as L
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
@@ -173,42 +215,41 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     g, body, G = problem(args.grid)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     cache = ilm.SurfaceScalarCache(body, g, lgf_table=G, device=True)
+    cache.sync()
+    plan_build_ms = (time.perf_counter() - t0) * 1e3            # once per grid: LGF upload, Ghat, Gx, scratch
+    if world > 1:
+        cache.comm_init()
     N = cache.N
     n_solves = N + 2
     fplus = cache.points()[0].copy()
-    fb_dev = torch.from_numpy(0.5 * fplus).cuda()
-    d = cache.zeros_surface().set(fplus)
-    ranges = shard.column_ranges(N, world)
+    fplus_dev = torch.from_numpy(fplus).cuda()
+    peak, peak_src = load_peaks()
+    lib = cache._lib
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        fstar = cache.zeros_grid()
-        ilm.surface_divergence(fstar, d, cache)
-        ilm.inverse_laplacian(fstar, cache)
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
         if world > 1:
-            S = shard.create_schur_sharded(ilm.create_RTLinvR, cache)
-        else:
-            S = ilm.create_RTLinvR(cache)
-        s = cache.zeros_surface()
-        ilm.interpolate(s, fstar, cache)
-        rhs = fb_dev - s.data
-        sol = ilm.LU(S).solve(rhs)
-        s.data.copy_(-sol)
-        f = cache.zeros_grid()
-        ilm.regularize(f, s, cache)
-        ilm.inverse_laplacian(f, cache)
-        f.data.add_(fstar.data)
-        return f, s
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    lc0 = cache.launch_count() + int(L.load().ilm_dense_launch_count())
+    def launches():
+        return cache.launch_count() + int(lib.ilm_dense_launch_count())
+
+    def step_device():
+        cache.update_points(body)                        # the problem's DDF tables (what a new / moved body costs)
+        return ilm.dirichlet_solve(cache, fplus_dev)
+
     for _ in range(args.warmup):
         step_device()
-    lc1 = cache.launch_count() + int(L.load().ilm_dense_launch_count())
+    lc1 = launches()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -219,18 +260,38 @@ def main():
     e1.record()
     barrier()
     clocks = sampler.stop()
-    lc2 = cache.launch_count() + int(L.load().ilm_dense_launch_count())
-    ms = e0.elapsed_time(e1) / max(args.steps, 1)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    lc2 = launches()
+    ms = max_over_ranks(e0.elapsed_time(e1) / max(args.steps, 1))
     value = g.NX * g.NY * n_solves / (ms * 1e-3)
     checksum = float(f.data.sum().item())
 
-    # ---- roofline of the dominant kernel (pass B), timed alone on its stream
+    def time_dev(fn, reps=3):
+        fn()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record()
+        a1.synchronize()
+        return max_over_ranks(a0.elapsed_time(a1) / reps)
+
+    # ---- where the step goes (each piece timed alone, max over ranks)
+    S_dev = ilm.create_schur_sharded(cache, "RTLinvR")
+    rhs = torch.randn(N, dtype=torch.float64, device="cuda")
+    breakdown = {
+        "table_refresh_ms": time_dev(lambda: (cache.update_points(body), cache.sync())),
+        "schur_build_ms": time_dev(lambda: ilm.create_schur_sharded(cache, "RTLinvR"), reps=2),
+        "lu_factor_ms": time_dev(lambda: ilm.LU(S_dev)),
+        "lu_solve_ms": None, "plan_build_ms_once_per_grid": plan_build_ms}
+    lu = ilm.LU(S_dev)
+    breakdown["lu_solve_ms"] = time_dev(lambda: lu.solve(rhs), reps=5)
+    breakdown["note"] = ("schur_build is the sharded part (N column probes / n_gpus + one in-place broadcast group); "
+                         "table refresh, LU, solve and the two dense L^-1 are replicated on every rank")
+
+    # ---- convolution passes timed alone on the plan's stream (CUDA events inside the library)
     msp = (L.C.c_double * 3)()
-    L.check(cache._lib.ilm_profile_conv(cache._plan, L.NODES_PRIMAL, 10, L.C.byref(msp)))
+    L.check(lib.ilm_profile_conv(cache._plan, L.NODES_PRIMAL, 10, L.C.byref(msp)))
     Lx = Ly = 16
     while 2 * Lx < 2 * g.NX - 1:
         Lx *= 2
@@ -241,149 +302,151 @@ def main():
     bytes_pass = {"A_rows_fwd": 2 * (g.NX - 1) * (g.NY - 1) * 8 + spec,
                   "B_columns": 2 * spec + (Lx + 1) * 2 * Ly * 8,
                   "C_rows_inv": spec + 2 * (g.NX - 1) * (g.NY - 1) * 8}
-    peak, peak_src = load_peaks()
-    passes = {k: {"ms": float(msp[i]), "GBps": b / (float(msp[i]) * 1e-3) / 1e9, "bytes": b}
+    passes = {k: {"ms": float(msp[i]), "GBps": b / (float(msp[i]) * 1e-3) / 1e9, "bytes": b,
+                  "frac_of_hbm_peak": b / (float(msp[i]) * 1e-3) / 1e9 / peak}
               for i, (k, b) in enumerate(bytes_pass.items())}
     conv_ms = sum(float(msp[i]) for i in range(3))
-    # the launches the Schur build actually issues (4593 of the 4595 solves of a step): sparse-row probes.
-    # Pass B then reads no spectrum (the input rows are summed directly) -> Ghat in, S2 out
+    # the launches the Schur build issues (N of the N + 2 solves of a step): the right-hand side R e_c is a W x W
+    # patch.  Pass A transforms its <= 8 rows, the band pass (ilm_band.cu) forms the y-convolution by direct
+    # summation with the x-transformed kernel rows, pass C inverts the rows under the interpolation windows and
+    # interpolates them on the fly.
     msq = (L.C.c_double * 3)()
-    L.check(cache._lib.ilm_profile_conv_probe(cache._plan, N // 3, 10, L.C.byref(msq)))
-    # ... and only for the rows under the interpolation windows (ilm_probe_output_rows)
+    L.check(lib.ilm_profile_conv_probe(cache._plan, N // 3, 20, L.C.byref(msq)))
     r0, r1 = L.C.c_int(), L.C.c_int()
-    L.check(cache._lib.ilm_probe_output_rows(cache._plan, L.RTLINVR, L.C.byref(r0), L.C.byref(r1)))
+    L.check(lib.ilm_probe_output_rows(cache._plan, L.RTLINVR, L.C.byref(r0), L.C.byref(r1)))
     rows_out = r1.value - r0.value
-    bytes_probe_B = 2 * Lx * rows_out * 16 + (Lx + 1) * 2 * Ly * 8
-    achieved = bytes_probe_B / (float(msq[1]) * 1e-3) / 1e9
-    # FP64 pipe: warp instructions per launch (ncu-verified static counts: inverse FFT 782/thread,
-    # sparse forward ~300/thread) x 2 issue cycles / (148 SMs x 4 SMSPs x elapsed cycles at 1.965 GHz)
-    fp64_winst_B = 2 * Lx * 2 * (782 + 300) * 8
-    roofline = {"bound": "hbm",
-                "kernel": f"ilm_passB_L{Ly} in Schur-probe mode (column pass: sparse forward DFT_y * Ghat * IFFT_y, 2 columns of S per launch)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu capture at 4096^2
-                # (profiles/r1_passB_probe_dram_v6.txt: 286.6 MB read + 233.7 MB written); null for other grids
-                "traffic": 520.3e6 if args.grid == 4096 else None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_probe_B,
-                "launch_ms": float(msq[1]),
-                "dense_equivalent_frac": bytes_pass["B_columns"] / (float(msq[1]) * 1e-3) / 1e9 / peak,
-                "fp64_pipe_frac_est": fp64_winst_B * 2 / (148 * 4 * float(msq[1]) * 1e-3 * 1.965e9),
-                "probe_passes_ms": {"A_rows_fwd": float(msq[0]), "B_columns": float(msq[1]), "C_rows_inv": float(msq[2])},
-                "probe_pair_ms": sum(float(msq[i]) for i in range(3)),
-                "probe_output_rows": [r0.value, r1.value],
-                "dense_passes": passes,
-                "dense_solve_pair_ms": conv_ms,
-                "dense_solve_frac_of_hbm": sum(bytes_pass.values()) / (conv_ms * 1e-3) / 1e9 / peak,
-                "frac_of_nominal_8TBps": achieved / 8000.0,
-                "note": "the convolution is FP64-issue / shared-memory bound on B200 (DESIGN.md section 4), not HBM bound"}
-
-    # ---- the other stages of the path (stencils, regularize, interpolate), device resident,
-    #      20 back-to-back launches between CUDA events on the plan's stream (= torch's default stream)
-    def time_op(fn, reps=20):
-        fn()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(reps):
-            fn()
-        a1.record()
-        a1.synchronize()
-        return a0.elapsed_time(a1) / reps
-
-    Pn = (g.NX - 1) * (g.NY - 1)
-    Pd, Pe = g.NX * g.NY, g.NX * (g.NY - 1) + (g.NX - 1) * g.NY
-    gen = torch.Generator(device="cuda").manual_seed(0)
-    qe, pn_, sd = cache.zeros_gridgrad(), cache.zeros_grid(), cache.zeros_gridcurl()
-    qe.data.normal_(generator=gen); pn_.data.normal_(generator=gen); sd.data.normal_(generator=gen)
-    oq, op_, os_ = cache.zeros_gridgrad(), cache.zeros_grid(), cache.zeros_gridcurl()
-    fs, fo = cache.zeros_surface(), cache.zeros_surface()
-    fs.data.normal_(generator=gen)
-    stage_defs = {
-        "divergence": (lambda: ilm.divergence(op_, qe, cache), 8 * (Pe + Pn)),
-        "grad": (lambda: ilm.grad(oq, pn_, cache), 8 * (Pe + Pn)),
-        "curl_nodes_to_edges": (lambda: ilm.curl(oq, sd, cache), 8 * (Pe + Pd)),
-        "curl_edges_to_nodes": (lambda: ilm.curl(os_, qe, cache), 8 * (Pe + Pd)),
-        "laplacian": (lambda: ilm.laplacian(os_, sd, cache), 16 * Pd),
-        "regularize": (lambda: ilm.regularize(op_, fs, cache), 8 * Pn + N * (16 * 12 + 8)),
-        "interpolate": (lambda: ilm.interpolate(fo, pn_, cache), N * (16 * 20 + 8)),
+    nrows_in = 8
+    W = 5
+    kernels = {
+        "k_passD (band pass: Y_n = sum_r x_r Gx(|n-r|), row-major S2 out)": {
+            "ms": float(msq[1]),
+            "bytes": rows_out * 2 * Lx * 16 + (rows_out + nrows_in) * (Lx + 1) * 8 + nrows_in * 2 * Lx * 16,
+            # dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture at 4096^2 (profiles/)
+            "traffic": NCU_TRAFFIC.get("k_passD") if args.grid == 4096 else None},
+        f"ilm_passC_L{Lx} (probe mode: inverse FFT_x of the window rows + fused interpolation)": {
+            "ms": float(msq[2]), "bytes": rows_out * 2 * Lx * 16 + N * W * (16 + 8 * W + 4),
+            "traffic": NCU_TRAFFIC.get("passC_probe") if args.grid == 4096 else None},
+        f"ilm_passA_L{Lx} (probe mode: forward FFT_x of the patch rows)": {
+            "ms": float(msq[0]), "bytes": nrows_in * ((g.NX - 1) * 16 + 2 * Lx * 16), "traffic": None},
     }
-    stages = {}
-    for name, (fn, nbytes) in stage_defs.items():
-        tms = time_op(fn)
-        stages[name] = {"ms": tms, "bytes": nbytes, "GBps": nbytes / (tms * 1e-3) / 1e9,
-                        "frac_of_hbm_peak": nbytes / (tms * 1e-3) / 1e9 / peak}
-    roofline["stages"] = stages
-    # transform-free direct-table Schur builder: reported beside, never part of `value` / `e2e`
-    t_direct = time_op(lambda: ilm.create_RTLinvR_direct(cache), reps=3)
-    S_fft = ilm.create_RTLinvR(cache, cols=(0, 64))
-    S_dir = ilm.create_RTLinvR_direct(cache, cols=(0, 64))
-    roofline["schur_direct_table"] = {
-        "ms": t_direct, "note": "optional O(N^2 W^4) table form of S (SURVEY fact 8); not used by the metric path",
-        "rel_diff_vs_column_solves": float(((S_dir - S_fft).abs().max() / S_fft.abs().max()).item())}
+    for k in kernels.values():
+        k["GBps"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        k["frac"] = k["GBps"] / peak
+    pairs_per_step = (N + 1) // 2 / world
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    dk = kernels[dom]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": dk["GBps"], "peak": peak, "unit": "GB/s", "frac": dk["frac"],
+                "traffic": dk["traffic"], "peak_source": peak_src, "algorithmic_bytes_per_launch": dk["bytes"],
+                "launch_ms": dk["ms"], "launches_per_step": pairs_per_step,
+                "share_of_step": dk["ms"] * pairs_per_step / ms,
+                "frac_of_nominal_8TBps": dk["GBps"] / 8000.0,
+                "probe_kernels": kernels, "probe_pair_ms": sum(float(msq[i]) for i in range(3)),
+                "probe_output_rows": [r0.value, r1.value],
+                "dense_passes": passes, "dense_solve_pair_ms": conv_ms,
+                "dense_solve_frac_of_hbm": sum(bytes_pass.values()) / (conv_ms * 1e-3) / 1e9 / peak,
+                "note": ("probe path: band pass and pass C stream the output rows of the x-spectrum once each; the "
+                         "FFT passes are bound by FP64 issue + shared-memory wavefronts (DESIGN.md section 4), "
+                         "the band pass by HBM")}
 
-    # ---- end to end through the public API with host buffers
-    e2e = None
-    if rank == 0 or world > 1:
-        hcache = ilm.SurfaceScalarCache(body, g, lgf_table=G, device=False)
+    # ---- the other stages of the path (stencils, regularize, interpolate), device resident: one launch per
+    #      repetition between CUDA events on the plan's stream (= torch's default stream), L2 flushed before each
+    if not args.no_stages:
+        flush = torch.empty(64 * 1024 * 1024, dtype=torch.float64, device="cuda")       # 512 MB > 126 MB L2
 
-        def step_host():
-            if world > 1:
-                # host buffers in and out; the shard exchange itself stays on the device, the gathered S comes
-                # back to a page-locked host matrix (what a host caller of create_RTLinvR would hold)
-                Sd = shard.create_schur_sharded(ilm.create_RTLinvR, cache)
-                hb = ilm.api._host_zeros(N * N)
-                torch.from_numpy(hb).copy_(Sd.t().reshape(-1))
-                return ilm.dirichlet_poisson(hcache, fplus, S=hb.reshape((N, N), order="F"))[:2]
-            return ilm.dirichlet_poisson(hcache, fplus)[:2]
+        def time_op(fn, reps=10):
+            fn()
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                fn()
+                a1.record()
+                a1.synchronize()
+                tot += a0.elapsed_time(a1)
+            return tot / reps
 
-        step_host()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            fh, sh = step_host()
-        barrier()
-        dt = (time.perf_counter() - t0) / max(args.steps, 1)
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        P = (g.NX - 1) * (g.NY - 1) * 8
-        # per call: surface_divergence (N in, P out), L^-1 (P, P), create_RTLinvR (N^2 out), interpolate (P in, N out),
-        # LU (N^2 in; the factors stay on the device), solve (N, N), regularize (N in, P out), L^-1 (P, P)
-        h2d = N * 8 + P + P + N * N * 8 + N * 8 + N * 8 + P
-        d2h = P + P + N * N * 8 + N * 8 + N * 8 + P + P
-        e2e = {"value": g.NX * g.NY * n_solves / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
-               "max_abs_diff_vs_device_path": float(np.abs(fh.data - f.numpy()).max())}
-        hcache.close()
+        Pn = (g.NX - 1) * (g.NY - 1)
+        Pd, Pe = g.NX * g.NY, g.NX * (g.NY - 1) + (g.NX - 1) * g.NY
+        gen = torch.Generator(device="cuda").manual_seed(0)
+        qe, pn_, sd = cache.zeros_gridgrad(), cache.zeros_grid(), cache.zeros_gridcurl()
+        qe.data.normal_(generator=gen); pn_.data.normal_(generator=gen); sd.data.normal_(generator=gen)
+        oq, op_, os_ = cache.zeros_gridgrad(), cache.zeros_grid(), cache.zeros_gridcurl()
+        fs, fo = cache.zeros_surface(), cache.zeros_surface()
+        fs.data.normal_(generator=gen)
+        stage_defs = {
+            "divergence": (lambda: ilm.divergence(op_, qe, cache), 8 * (Pe + Pn)),
+            "grad": (lambda: ilm.grad(oq, pn_, cache), 8 * (Pe + Pn)),
+            "curl_nodes_to_edges": (lambda: ilm.curl(oq, sd, cache), 8 * (Pe + Pd)),
+            "curl_edges_to_nodes": (lambda: ilm.curl(os_, qe, cache), 8 * (Pe + Pd)),
+            "laplacian": (lambda: ilm.laplacian(os_, sd, cache), 16 * Pd),
+            "regularize": (lambda: ilm.regularize(op_, fs, cache), 8 * Pn + N * (16 * 12 + 8)),
+            "interpolate": (lambda: ilm.interpolate(fo, pn_, cache), N * (16 * 20 + 8)),
+        }
+        stages = {}
+        for name, (fn, nbytes) in stage_defs.items():
+            tms = time_op(fn)
+            stages[name] = {"ms": tms, "bytes": nbytes, "GBps": nbytes / (tms * 1e-3) / 1e9,
+                            "frac_of_hbm_peak": nbytes / (tms * 1e-3) / 1e9 / peak,
+                            "traffic": NCU_TRAFFIC.get(name) if args.grid == 4096 else None}
+        roofline["stages"] = stages
+        roofline["stages_note"] = "one launch per repetition, 512 MB written between repetitions (L2 flush), CUDA events"
+        del flush
+
+    # ---- end to end: the same call with host buffers (points + boundary data H2D, field + multiplier D2H)
+    hcache = ilm.SurfaceScalarCache(body, g, lgf_table=G, device=False)
+    if world > 1:
+        hcache.comm_init()
+
+    def step_host():
+        hcache.update_points(body)
+        return ilm.dirichlet_solve(hcache, fplus)
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fh, sh = step_host()
+    barrier()
+    dt = max_over_ranks((time.perf_counter() - t0) / max(args.steps, 1))
+    P = (g.NX - 1) * (g.NY - 1) * 8
+    e2e = {"value": g.NX * g.NY * n_solves / dt, "unit": UNIT, "h2d_bytes_per_step": int(5 * N * 8 + N * 8),
+           "d2h_bytes_per_step": int(P + N * 8), "ms_per_step": dt * 1e3,
+           "max_abs_diff_vs_device_path": float(np.abs(fh.data - f.numpy()).max()),
+           "api": "ilm_plan_update_points + ilm_dirichlet_poisson with host pointers (every rank returns the full field)"}
+    hcache.close()
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         o, oc = oracle_cache(g, body, G)
         cpu_probe(oc, 0)
-        ns = 3
         t0 = time.perf_counter()
-        for k in range(ns):
-            cpu_probe(oc, 1 + k)
+        ns = 0
+        while ns < 32 and (ns < 4 or time.perf_counter() - t0 < 12.0):
+            cpu_probe(oc, 1 + ns)
+            ns += 1
         dtc = (time.perf_counter() - t0) / ns
-        cpu = {"value": g.NX * g.NY / dtc, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+        cpu = {"value": g.NX * g.NY / dtc, "unit": UNIT, "cores": host_threads(), "kind": "port",
                "sample": f"{ns} Schur column probes (R e_c -> L^-1 -> E) = {ns} inverse Laplacians of the {N + 2} "
-                         f"in a step, {dtc:.2f} s each; scipy.fft on the (2NX-1)^2 pad with workers=all cores"}
+                         f"in a step, {dtc:.2f} s each; scipy.fft on the (2NX-1)^2 pad with workers = all host threads"}
 
     if rank == 0:
+        cfg = workload_config(args, g, N, world)
+        cfg.update({"parallelism": f"schur-columns/{world}",
+                    "l2": "every column pair streams 2 x %.0f MB of x-spectrum rows (> 126 MB L2)" % (rows_out * 2 * Lx * 16 / 1e6),
+                    "checksum_f": checksum})
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"dirichlet_circle_{args.grid}", "grid": [g.NX, g.NY], "surface_points": int(N),
-                       "solves_per_step": int(n_solves), "ddf": "yang3", "parallelism": f"schur-columns/{world}",
-                       "l2": "spectrum buffers (2 x %.0f MB) exceed the 126 MB L2" % (spec / 1e6),
-                       "checksum_f": checksum},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(lc2 - lc1), "roofline": roofline, "cpu_baseline": cpu,
+            "data": "synthetic", "config": cfg,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(lc2 - lc1), "breakdown": breakdown,
+            "roofline": roofline, "cpu_baseline": cpu,
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
+        cache.comm_destroy()
         dist.destroy_process_group()
 
 

@@ -27,7 +27,7 @@ from .api import (  # noqa: F401
     XEdges, YEdges, Dual, Edges, GridScaling, IndexScaling, LU, Nodes, PhysicalGrid, Primal, ScalarData,
     SurfaceScalarCache, VectorData, complementary_mask, create_CLinvCT, create_GLinvD,
     create_GLinvD_cross, create_RTLinvR, create_nRTRn, create_surface_filter, curl,
-    dirichlet_poisson, divergence, grad, interpolate, inverse_laplacian, laplacian, mask,
+    dirichlet_poisson, dirichlet_solve, create_schur_sharded, divergence, grad, interpolate, inverse_laplacian, laplacian, mask,
     matvec_pow, normal_cross_interpolate, normal_interpolate, regularize, regularize_normal,
     regularize_normal_cross, surface_curl, surface_curl_cross, surface_divergence,
     surface_divergence_cross, surface_grad, surface_grad_cross)

@@ -371,6 +371,31 @@ class SurfaceScalarCache:
     def sync(self):
         L.check(self._lib.ilm_plan_sync(self._plan))
 
+    # -- multi-GPU: the NCCL communicator lives inside the library (ilm_comm_init); the host language only
+    #    distributes the 128-byte unique id (here: torch.distributed, any backend)
+    def comm_init(self, group=None):
+        """Bind an NCCL communicator over the ranks of the torch.distributed `group` to this plan."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            L.check(self._lib.ilm_comm_unique_id(_ptr(uid), 128))
+        box = [uid.tobytes()]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = np.frombuffer(box[0], dtype=np.uint8).copy()
+        L.check(self._lib.ilm_comm_init(self._plan, _ptr(uid), 128, rank, world))
+        del torch
+        return self
+
+    def comm_destroy(self):
+        L.check(self._lib.ilm_comm_destroy(self._plan))
+
+    def comm_info(self):
+        r, n = C.c_int(), C.c_int()
+        L.check(self._lib.ilm_comm_info(self._plan, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
     def launch_count(self):
         return int(self._lib.ilm_plan_launch_count(self._plan))
 
@@ -749,6 +774,48 @@ def dirichlet_poisson(cache, fplus, fminus=None, S=None, filter_passes=0):
         Cm = create_surface_filter(cache)
         matvec_pow(Cm, filter_passes, s)
     return f, s, S
+
+
+def dirichlet_solve(cache, fplus, fminus=None, return_S=False):
+    """`solve(prob::DirichletPoissonProblem, sys)` of test/literate/dirichlet.jl:71-107 as ONE call of the library
+    (ilm_dirichlet_poisson): boundary data in, field and multiplier out; S, its LU factors and the intermediate
+    fields never leave the device, and with a communicator on the plan (cache.comm_init) the Schur columns are
+    sharded over its ranks inside the library.  fplus / fminus: numpy arrays or torch CUDA tensors of length N
+    (the outputs live where the cache says: device=True -> torch).  Returns (f, s) or (f, s, S)."""
+    N = cache.N
+    dev = cache.device
+
+    def surf(v):
+        if v is None:
+            return None
+        if dev and _is_torch(v):
+            return v
+        a = np.ascontiguousarray(np.asarray(v, dtype=np.float64))
+        if dev:
+            import torch
+            return torch.from_numpy(a).cuda()
+        return a
+
+    fp, fm = surf(fplus), surf(fminus)
+    for v in (fp, fm):
+        if v is not None and int(np.prod(v.shape)) != N:
+            raise DimensionMismatch(f"dirichlet_solve: expected {N} surface values")
+    f, s = cache.zeros_grid(), cache.zeros_surface()
+    S = _matrix(cache, N) if return_S else None
+    L.check(cache._lib.ilm_dirichlet_poisson(cache._plan, _ptr(fp), _ptr(fm) if fm is not None else None, _ptr(f.data),
+                                             _ptr(s.data), _ptr(S) if S is not None else None))
+    if return_S:
+        return f, s, _as_matrix(S, N, N)
+    return f, s
+
+
+def create_schur_sharded(cache, which="RTLinvR", scale=1.0, kernel_id=0):
+    """A Schur builder of src/matrix_operators.jl with its column loop sharded over the plan's communicator
+    (ilm_create_schur_sharded): the full N x N matrix on every rank.  which: RTLinvR / CLinvCT / GLinvD / GLinvD_cross."""
+    code = {"RTLinvR": L.RTLINVR, "CLinvCT": L.CLINVCT, "GLinvD": L.GLINVD, "GLinvD_cross": L.GLINVD_CROSS}[which]
+    A = _matrix(cache, cache.N)
+    L.check(cache._lib.ilm_create_schur_sharded(cache._plan, code, int(kernel_id), float(scale), _ptr(A)))
+    return _as_matrix(A, cache.N, cache.N)
 
 
 # ==========================================================================

@@ -10,11 +10,14 @@
 //
 // Thread = one x-frequency (px, m), walking down a run of output rows with the NR multipliers of the current row
 // held in a register ring (one new coalesced load per row: Gx is stored transposed, [d][column], columns
-// mirror-reduced like Ghat); x_r(kx) stays in registers.  Stores go to the 2x2-tile spectrum layout of ilm_conv.cuh
-// (lanes m, m+1 fill one 32-byte sector; consecutive rows complete the 64-byte tile).
+// mirror-reduced like Ghat); x_r(kx) stays in registers.  Stores go to a ROW-MAJOR S2 ([row - olo][px][m],
+// ConvArgs::s2_rowmajor): a warp writes 512 contiguous bytes per row and pass C fetches whole rows with one bulk copy
+// each (first version: the 2x2-tile layout of the transform path, 32-byte pieces 131 KB apart -- 0.115 ms per launch).
 //
 // The result is the same linear convolution as the transform path up to rounding (the sum over <= NR terms is
 // exact arithmetic on the same x-spectrum); tests compare both with the oracle at 1e-12.
+#include <cstdlib>
+
 #include "ilm_internal.h"
 
 namespace ilm {
@@ -31,8 +34,29 @@ __global__ void k_gxt_extract(ConvGeom g, const double2* __restrict__ S, double*
     gxt[(size_t)d * ldc + ghat_col(g, px, m)] = v;
 }
 
-template <int NR>
-__global__ void __launch_bounds__(256) k_passD(ConvGeom g, const double2* __restrict__ S, double2* __restrict__ S2,
+// L2 policies: the multiplier rows (68 MB at 4096^2, the same rows for every column pair of a Schur build) are kept,
+// the spectrum rows (268 MB per launch, read once by pass C) are streamed through
+__device__ __forceinline__ unsigned long long l2_policy_keep() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_stream() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double ld_keep(const double* ptr, unsigned long long pol) {
+    double v;
+    asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(ptr), "l"(pol));      // read-only table: may be hoisted
+    return v;
+}
+__device__ __forceinline__ void st_stream(double2* ptr, double re, double im, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(ptr), "d"(re), "d"(im), "l"(pol) : "memory");
+}
+
+template <int NR, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_passD(ConvGeom g, const double2* __restrict__ S, double2* __restrict__ S2,
                                                const double* __restrict__ gxt, int ldc, int dmax, int rlo, int nrows,
                                                int olo, int ohi, int chunk) {
     const int t = blockIdx.x * 256 + threadIdx.x;            // x-frequency slot
@@ -41,6 +65,7 @@ __global__ void __launch_bounds__(256) k_passD(ConvGeom g, const double2* __rest
     const int n0 = olo + blockIdx.y * chunk;
     const int n1 = min(n0 + chunk, ohi);
     if (n0 >= n1) return;
+    const unsigned long long keep = l2_policy_keep(), stream = l2_policy_stream();
     const size_t base = s_index(g, px, m, 0);
     auto sidx = [&](int row) { return base + ((size_t)(row >> 1) << 2) + (size_t)((row & 1) << 1); };
     double2 x[NR];
@@ -50,22 +75,41 @@ __global__ void __launch_bounds__(256) k_passD(ConvGeom g, const double2* __rest
     auto gload = [&](int e) {                                // multiplier of row distance |e| (clamped: rows past the
         int d = e < 0 ? -e : e;                              // run are computed but never stored)
         d = d < dmax ? d : dmax;
-        return __ldg(gc + (size_t)d * ldc);
+        return ld_keep(gc + (size_t)d * ldc, keep);
     };
     // offsets e = n - rlo; the multiplier of offset o lives in ring slot (o mod NR).  Start at the multiple of NR
     // at or below the first row so that slots are compile-time constants inside the unrolled body.
     const int e0 = n0 - rlo;
     const int es = e0 - (((e0 % NR) + NR) % NR);
-    double ring[NR];
+    constexpr bool PIPE = NR <= 10;                          // wider windows keep the registers for x_r
+    double ring[NR], nxt[PIPE ? NR : 1];
 #pragma unroll
     for (int q = 1; q < NR; ++q) ring[NR - q] = gload(es - q);
     ring[0] = 0.0;
+    if constexpr (PIPE) {
+#pragma unroll
+        for (int s = 0; s < NR; ++s) nxt[s] = gload(es + s);
+    }
     const int eend = n1 - rlo;
-    for (int eb = es; eb < eend; eb += NR) {
+    double2* out = S2 + ((size_t)(es + rlo - olo) * 2 + px) * (size_t)g.Lx + m;      // s2rm_index of row es + rlo
+    const size_t rstride = (size_t)2 * g.Lx;
+    for (int eb = es; eb < eend; eb += NR, out += NR * rstride) {
+        double cur[NR];
+        if constexpr (PIPE) {
+#pragma unroll
+            for (int s = 0; s < NR; ++s) cur[s] = nxt[s];
+            if (eb + NR < eend) {                            // the next block's multipliers travel while this one is summed
+#pragma unroll
+                for (int s = 0; s < NR; ++s) nxt[s] = gload(eb + NR + s);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < NR; ++s) cur[s] = gload(eb + s);
+        }
 #pragma unroll
         for (int s = 0; s < NR; ++s) {
             const int n = eb + s + rlo;
-            ring[s] = gload(eb + s);
+            ring[s] = cur[s];
             double re = 0.0, im = 0.0;
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
@@ -73,7 +117,7 @@ __global__ void __launch_bounds__(256) k_passD(ConvGeom g, const double2* __rest
                 re = fma(x[r].x, gg, re);
                 im = fma(x[r].y, gg, im);
             }
-            if (n >= n0 && n < n1) S2[sidx(n)] = cmk(re, im);
+            if (n >= n0 && n < n1) st_stream(out + s * rstride, re, im, stream);
         }
     }
 }
@@ -107,12 +151,13 @@ int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k) {
     nchunks = (nout + chunk - 1) / chunk;
     const dim3 grid(gx, nchunks);
     const int dmax = k.gxt_rows - 1;
-#define ILM_BAND(NR) k_passD<NR><<<grid, 256, 0, p->stream>>>(a.g, a.S, a.S2, k.gxt, k.gxt_ld, dmax, a.rlo, nrows, a.olo, a.ohi, chunk)
-    if (nrows <= 6) ILM_BAND(6);
-    else if (nrows <= 8) ILM_BAND(8);
-    else if (nrows <= 10) ILM_BAND(10);
-    else if (nrows <= 12) ILM_BAND(12);
-    else ILM_BAND(16);
+#define ILM_BAND(NR, MINB) k_passD<NR, MINB><<<grid, 256, 0, p->stream>>>(a.g, a.S, a.S2, k.gxt, k.gxt_ld, dmax, a.rlo, nrows, a.olo, a.ohi, chunk)
+    static const int minb = getenv("ILM_BAND_MINB") ? atoi(getenv("ILM_BAND_MINB")) : 3;
+    if (nrows <= 6) { if (minb >= 3) ILM_BAND(6, 3); else ILM_BAND(6, 2); }
+    else if (nrows <= 8) { if (minb >= 3) ILM_BAND(8, 3); else ILM_BAND(8, 2); }
+    else if (nrows <= 10) ILM_BAND(10, 2);
+    else if (nrows <= 12) ILM_BAND(12, 2);
+    else ILM_BAND(16, 2);
 #undef ILM_BAND
     ILM_CUDA(cudaGetLastError());
     return ILM_OK;

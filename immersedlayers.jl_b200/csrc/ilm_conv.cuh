@@ -62,6 +62,18 @@ struct FieldRef {          // one real field: column-major, x fastest
     int mx, my;            // extents; leading dimension = mx
 };
 
+// Fused interpolation of the Schur probes (create_RTLinvR: the post-operator is E on one table): pass C hands every
+// inverted row to the points whose windows cross it instead of storing it.  part[k*W + b] = sum_a wE[k][b][a] y[row][i0_k + a]
+// (complex: two probe columns); a small kernel then adds the W row sums of each point.
+struct ProbeGather {
+    const int* rowptr;     // my + 1 offsets into rowent
+    const int* rowent;     // k*W + b of every in-field window row, sorted by row, then point
+    const int* i0;         // first window column of each point
+    const double* w;       // interpolation weights [k][b][a]
+    int W, mx, my;
+    double2* part;         // null = store the rows (every other caller)
+};
+
 struct ConvArgs {
     ConvGeom g;
     FieldRef f1, f2;       // real / imaginary carrier
@@ -83,7 +95,15 @@ struct ConvArgs {
     double2* scratch;      // per-CTA hand-off lines of the big column pass (2 groups x Ly complex per CTA)
     int wlo, whi;          // pass B visits the work items [wlo, whi) only (slab decomposition: the x-frequency
                            // columns this GPU owns); whi <= 0 = all of them
+    ProbeGather eg;        // fused interpolation in pass C (Schur probes)
+    int s2_rowmajor;       // S2 holds the output rows [olo, ohi) row by row, [row - olo][px][m] (written by the band
+                           // pass of the Schur probes, ilm_band.cu): both that pass and pass C then stream whole rows
 };
+
+// row-major S2 of the probe path: one x-spectrum row is 2 Lx contiguous complex numbers (even frequencies, then odd)
+ILM_HD size_t s2rm_index(const ConvArgs& a, int px, int m, int row) {
+    return ((size_t)(row - a.olo) * 2 + px) * (size_t)a.g.Lx + m;
+}
 
 // named barriers 1,2 are the per-group barriers (Ctx::sync); these two carry the
 // producer (odd half, group 1) -> consumer (even half, group 0) hand-off
@@ -334,7 +354,8 @@ ILM_HD void passC_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
         } else {
             const size_t i0 = s_index(a.g, px, j, row);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = live ? a.S2[row_elem<T>(a.g, px, row, j, e, i0)] : cmk(0.0, 0.0);
+            for (int e = 0; e < 16; ++e)
+                v[e] = live ? a.S2[a.s2_rowmajor ? s2rm_index(a, px, j + e * T, row) : row_elem<T>(a.g, px, row, j, e, i0)] : cmk(0.0, 0.0);
         }
         fft_head<L, true>(v, ctx, xb, tw, j);
         if constexpr (C::USE_TMA) {
@@ -349,6 +370,28 @@ ILM_HD void passC_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
 #pragma unroll
             for (int e = 0; e < 16; ++e) comb[j + e * T] = cmulc(v[e], mod_fwd<L>(tw, j, e));
             ctx.arrive(BAR_READY);
+        } else if (a.eg.part) {
+            // probe path: the finished row stays in the combine buffer and is gathered by the points whose
+            // interpolation windows cross it (same term order inside a window row as the oracle: a ascending)
+            ctx.wait(BAR_READY);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { const int n = j + e * T; comb[n] = cadd(v[e], comb[n]); }
+            ctx.sync();
+            if (live && row < a.eg.my) {
+                const int W = a.eg.W;
+                for (int q = a.eg.rowptr[row] + j; q < a.eg.rowptr[row + 1]; q += T) {
+                    const int ent = a.eg.rowent[q];
+                    const int i0 = a.eg.i0[ent / W];
+                    const double* w = a.eg.w + (size_t)ent * W;
+                    double re = 0.0, im = 0.0;
+                    for (int c = 0; c < W; ++c) {
+                        const int i = i0 + c;
+                        if (i >= 0 && i < a.eg.mx) { re += w[c] * comb[i].x; im += w[c] * comb[i].y; }
+                    }
+                    a.eg.part[ent] = cmk(re, im);
+                }
+            }
+            ctx.arrive(BAR_FREE);
         } else {
             ctx.wait(BAR_READY);
 #pragma unroll

@@ -75,6 +75,15 @@ struct DevCtx {
             const unsigned long long tm = reinterpret_cast<unsigned long long>(tmap);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(nrows * L * 16) : "memory");
+            if (a.s2_rowmajor) {                                    // one contiguous bulk copy per row (probe path)
+                for (int r = 0; r < nrows; ++r) {
+                    const unsigned d = (unsigned)__cvta_generic_to_shared(dst + (size_t)r * slot_stride);
+                    const double2* src = a.S2 + s2rm_index(a, px, 0, row0 + r);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(d), "l"(src), "r"(L * 16), "r"(mb) : "memory");
+                }
+                return;
+            }
             const int na = L >> 1;                                 // tile columns per row
             const int box = na < 256 ? na : 256;
             for (int r = 0; r < nrows; ++r) {

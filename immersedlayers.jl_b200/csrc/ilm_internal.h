@@ -52,6 +52,11 @@ struct DevTable {
     int* ent = nullptr;         // nent    k*W*W + slot, ascending k inside a cell
     double* rowsum = nullptr;   // ncell   sum_k R[cell,k] (surface filter)
     std::vector<int> h_j0;      // host mirror of j0 (row range of each point's window)
+    // row buckets of the window rows (primal table only): pass C of the Schur probes interpolates on the fly
+    int* row_ptr = nullptr;     // my + 1
+    int* row_ent = nullptr;     // k*W + b, sorted by row then k
+    double2* part = nullptr;    // N*W row sums of the current column pair
+    size_t cap_rows = 0, cap_rowent = 0;
     size_t cap_pts = 0, cap_cells = 0, cap_ents = 0;   // allocated capacities (a moving body refreshes the tables every step)
 };
 
@@ -88,6 +93,7 @@ struct ilm_plan {
     int tmap_myp = -1;
     int skew_ns = 500;              // ILM_CONV_SKEW_NS: start-up skew between the two groups of a CTA
     bool band = true;               // ILM_PROBE_BAND=0 sends the Schur probes through the transform column pass instead
+    bool fuse_e = true;             // ILM_PROBE_FUSE_E=0: pass C stores the probed rows and a separate kernel interpolates
     std::vector<ilm::ConvKernel> kernels;
     double* lgf_dev = nullptr;      // device copy of the LGF table (ld = lgf_ld), kept for the direct Schur form
     int lgf_ld = 0;
@@ -98,6 +104,12 @@ struct ilm_plan {
     double* s_a = nullptr;          // 4N surface scratch
     double* s_b = nullptr;          // 4N surface scratch (TensorData temporaries)
     double* g_tensor = nullptr;     // EdgeGradient scratch (allocated on first vector-cache use)
+    // NCCL communicator bound to the plan (ilm_comm_init, ilm_comm.cu); null = single GPU
+    void* comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    // scratch of the whole-problem entry points (ilm_dirichlet_poisson): grow-only
+    double* prob_work = nullptr;
+    size_t prob_cap = 0;
     std::vector<void*> staging;     // device staging for host pointers
     std::vector<size_t> staging_cap;
 };
@@ -187,6 +199,12 @@ void probe_output_rows(const ilm_plan* p, int which, int* olo, int* ohi);
 int mask_primal_dev(ilm_plan* p, double* dn);
 int mask_edges_dev(ilm_plan* p, double* de);
 
+// ---- communicator (ilm_comm.cu) ------------------------------------------------------
+void comm_column_range(int n, int nranks, int rank, int* lo, int* hi);
+int comm_allgather_columns(ilm_plan* p, double* dA, int ld, int ncols);
+int comm_alltoallv(ilm_plan* p, const double* send, const int64_t* scount, double* recv, const int64_t* rcount);
+void comm_release(ilm_plan* p);
+
 // ---- tables (ilm_tables.cu, compiled without FMA contraction) -----------------
 int build_tables(ilm_plan* p);
 void free_table(DevTable& t);
@@ -196,12 +214,17 @@ int conv_setup(ilm_plan* p);
 int conv_add_kernel(ilm_plan* p, const double* table_host_or_dev, int n, double c0, double factor, int* id);
 // rows outside [rlo, rhi) of both inputs are known zeros (-1, -1 = dense input); only output rows
 // [olo, ohi) are needed by the caller (-1, -1 = all), the others are left untouched
-int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1);
+int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1,
+               const ProbeGather* eg = nullptr);
+// true when conv_apply would take the band pass for this kernel and input row count (then `eg` may be passed)
+bool conv_band_ok(const ilm_plan* p, int kernel_id, int nrows);
+int launch_probe_post_sum(ilm_plan* p, const DevTable& t, int ncol, double coef, double* d0, double* d1);
 void conv_free(ilm_plan* p);
 ConvArgs conv_base_args(const ilm_plan* p);      // plan-constant kernel arguments (buffers, twiddle tables)
 int conv_half_len(int n);                       // half padded transform length of an n-cell direction
 int make_s2_tensor_map(ilm_plan* p, int MYp);    // bulk-tensor map of S2 for pass C
-int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1);
+int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1,
+                 const ProbeGather* eg = nullptr);
 extern long long g_dense_launches;
 // per-length launchers, which = 0: pass A, 1: pass B, 2: pass C, 3: pass G
 typedef int (*conv_launch_fn)(int which, const ConvArgs& a, int nsm, cudaStream_t st, const void* tmap);

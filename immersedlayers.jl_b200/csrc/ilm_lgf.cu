@@ -93,6 +93,7 @@ int conv_half_len(int n) {
 int conv_setup(ilm_plan* p) {
     if (const char* e = getenv("ILM_CONV_SKEW_NS")) p->skew_ns = atoi(e);
     if (const char* e = getenv("ILM_PROBE_BAND")) p->band = atoi(e) != 0;
+    if (const char* e = getenv("ILM_PROBE_FUSE_E")) p->fuse_e = atoi(e) != 0;
     p->Lx = conv_half_len(p->g.NX);
     p->Ly = conv_half_len(p->g.NY);
     if (p->Lx > 16384 || p->Ly > 16384) {
@@ -187,7 +188,12 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     return ILM_OK;
 }
 
-int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, int rhi, int olo, int ohi) {
+bool conv_band_ok(const ilm_plan* p, int kernel_id, int nrows) {
+    return kernel_id >= 0 && kernel_id < (int)p->kernels.size() && p->kernels[kernel_id].gxt && p->band && nrows >= 1 &&
+           nrows <= conv_band_max_rows();
+}
+
+int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, int rhi, int olo, int ohi, const ProbeGather* eg) {
     if (kernel_id < 0 || kernel_id >= (int)p->kernels.size()) {
         set_error("unknown convolution kernel id");
         return ILM_EINVAL;
@@ -207,15 +213,21 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
     if (use_tma(p)) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
     ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream, nullptr));
     const ConvKernel& k = p->kernels[kernel_id];
-    if (k.gxt && p->band && a.rhi - a.rlo <= conv_band_max_rows()) ILM_TRY(conv_launch_band(p, a, k));
-    else ILM_TRY(conv_launcher(p->Ly)(1, a, p->nsm, p->stream, nullptr));
+    if (eg && !conv_band_ok(p, kernel_id, a.rhi - a.rlo)) { set_error("conv_apply: fused interpolation needs the band pass"); return ILM_EINVAL; }
+    if (eg) a.eg = *eg;
+    if (conv_band_ok(p, kernel_id, a.rhi - a.rlo)) {
+        a.s2_rowmajor = 1;
+        ILM_TRY(conv_launch_band(p, a, k));
+    } else {
+        ILM_TRY(conv_launcher(p->Ly)(1, a, p->nsm, p->stream, nullptr));
+    }
     ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, p->stream, p->tmap_s2));
     p->launches += 3;
     return ILM_OK;
 }
 
 // per-pass timing for the roofline report (ilm_profile_conv)
-int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo, int rhi, int olo, int ohi) {
+int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo, int rhi, int olo, int ohi, const ProbeGather* eg) {
     ConvArgs a = conv_base_args(p);
     int MY = f1.my > f2.my ? f1.my : f2.my;
     a.g = ConvGeom{p->Lx, p->Ly, MY, (MY + 1) & ~1};
@@ -231,9 +243,12 @@ int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], 
     ILM_CUDA(cudaEventCreate(&e1));
     const int Ls[3] = {p->Lx, p->Ly, p->Lx};
     if (use_tma(p)) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
+    const bool band_path = p->kernels[0].gxt && p->band && a.rhi - a.rlo <= conv_band_max_rows();
+    a.s2_rowmajor = band_path ? 1 : 0;
+    if (eg && band_path) a.eg = *eg;
     for (int which = 0; which < 3; ++which) {
         const ConvKernel& k = p->kernels[0];
-        const bool band = which == 1 && k.gxt && p->band && a.rhi - a.rlo <= conv_band_max_rows();
+        const bool band = which == 1 && band_path;
         auto launch = [&]() { return band ? conv_launch_band(p, a, k) : conv_launcher(Ls[which])(which, a, p->nsm, p->stream, p->tmap_s2); };
         ILM_TRY(launch());                                                                // warm-up
         ILM_CUDA(cudaEventRecord(e0, p->stream));

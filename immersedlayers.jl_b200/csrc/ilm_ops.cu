@@ -835,6 +835,25 @@ __global__ void k_probe_post(int N, TabView t, const double* __restrict__ g0, co
     const double v = gather16(t, field, k, slot, k < N);
     if (slot == 0 && k < N) dst[k] = coef * v;
 }
+// column c (and c + 1) of the Schur complement from the window-row sums that pass C left in t.part
+__global__ void k_probe_post_sum(int N, int W, int my, const int* __restrict__ j0, const double2* __restrict__ part, double coef,
+                                 double* __restrict__ d0, double* __restrict__ d1) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    double re = 0.0, im = 0.0;
+    for (int b = 0; b < W; ++b) {
+        const int j = j0[k] + b;
+        if (j >= 0 && j < my) { const double2 v = part[k * W + b]; re += v.x; im += v.y; }
+    }
+    d0[k] = coef * re;
+    if (d1) d1[k] = coef * im;
+}
+int launch_probe_post_sum(ilm_plan* p, const DevTable& t, int ncol, double coef, double* d0, double* d1) {
+    k_probe_post_sum<<<(p->N + 127) / 128, 128, 0, p->stream>>>(p->N, t.W, t.my, t.j0, t.part, coef, d0, ncol > 1 ? d1 : nullptr);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
 int launch_probe_post(ilm_plan* p, const DevTable& t, int ncol, const double* g0, const double* g1, double coef, double* d0,
                       double* d1) {
     if (p->N == 0) return ILM_OK;

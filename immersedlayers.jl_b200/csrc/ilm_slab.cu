@@ -212,3 +212,23 @@ extern "C" int ilm_slab_inverse(ilm_plan* p, const ilm_slab_info* s, const doubl
     p->launches++;
     return ILM_OK;
 }
+
+
+// the three stages with both exchanges issued inside the library (grouped ncclSend / ncclRecv on the plan's stream)
+extern "C" int ilm_slab_solve(ilm_plan* p, const ilm_slab_info* s, int kernel_id, int layout1, double* w1_rows, int layout2,
+                              double* w2_rows, double* sendbuf, double* recvbuf) {
+    ILM_SLAB_PLAN(p);
+    if (!s || !sendbuf || !recvbuf) { set_error("ilm_slab_solve: bad arguments"); return ILM_EINVAL; }
+    if (!p->comm || p->comm_size != s->nranks || p->comm_rank != s->rank) {
+        set_error("ilm_slab_solve: the plan's communicator does not match the slab partition (ilm_comm_init)");
+        return ILM_ENCCL;
+    }
+    std::vector<int64_t> sc(s->nranks), rc(s->nranks);
+    ILM_TRY(ilm_slab_forward(p, s, layout1, w1_rows, layout2, w2_rows, sendbuf));
+    ILM_TRY(ilm_slab_counts(p->g.NX, p->g.NY, s, 0, sc.data(), rc.data()));
+    ILM_TRY(comm_alltoallv(p, sendbuf, sc.data(), recvbuf, rc.data()));
+    ILM_TRY(ilm_slab_columns(p, s, kernel_id, recvbuf, sendbuf));
+    ILM_TRY(ilm_slab_counts(p->g.NX, p->g.NY, s, 1, sc.data(), rc.data()));
+    ILM_TRY(comm_alltoallv(p, sendbuf, sc.data(), recvbuf, rc.data()));
+    return ilm_slab_inverse(p, s, recvbuf, layout1, w1_rows, layout2, w2_rows);
+}

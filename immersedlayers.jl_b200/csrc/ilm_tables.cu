@@ -38,6 +38,7 @@ __global__ void k_point_tables(int N, const double* __restrict__ x, const double
 void free_table(DevTable& t) {
     cudaFree(t.i0); cudaFree(t.j0); cudaFree(t.wR); cudaFree(t.wE);
     cudaFree(t.cell_idx); cudaFree(t.cell_off); cudaFree(t.ent); cudaFree(t.rowsum);
+    cudaFree(t.row_ptr); cudaFree(t.row_ent); cudaFree(t.part);
     t = DevTable();
 }
 
@@ -149,6 +150,33 @@ int build_tables(ilm_plan* p) {
         ILM_CUDA(cudaMemcpyAsync(t.cell_off, cell_off.data(), cell_off.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         if (t.nent) ILM_CUDA(cudaMemcpyAsync(t.ent, id.data(), id.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         if (layout == ILM_NODES_PRIMAL) ILM_TRY(launch_filter_rowsum(p, t));
+        if (layout == ILM_NODES_PRIMAL) {
+            // row buckets of the window rows (k*W + b sorted by grid row, then point) for the fused interpolation
+            // of the Schur probes in pass C (ConvArgs::eg)
+            std::vector<int> rptr((size_t)li.my + 1, 0), rent;
+            for (int k = 0; k < N; ++k)
+                for (int b = 0; b < W; ++b) { const int j = yj[k] + b; if (j >= 0 && j < li.my) ++rptr[j + 1]; }
+            for (int j = 0; j < li.my; ++j) rptr[j + 1] += rptr[j];
+            rent.resize((size_t)rptr[li.my]);
+            std::vector<int> fill(rptr.begin(), rptr.end() - 1);
+            for (int k = 0; k < N; ++k)
+                for (int b = 0; b < W; ++b) { const int j = yj[k] + b; if (j >= 0 && j < li.my) rent[fill[j]++] = k * W + b; }
+            if ((size_t)li.my + 1 > t.cap_rows || !t.row_ptr) {
+                cudaFree(t.row_ptr); t.row_ptr = nullptr;
+                ILM_CUDA(cudaMalloc(&t.row_ptr, ((size_t)li.my + 1) * sizeof(int)));
+                t.cap_rows = (size_t)li.my + 1;
+            }
+            if (np * W > t.cap_rowent || !t.row_ent) {
+                cudaFree(t.row_ent); cudaFree(t.part); t.row_ent = nullptr; t.part = nullptr;
+                const size_t cap = (np + np / 4 + 16) * W;
+                ILM_CUDA(cudaMalloc(&t.row_ent, cap * sizeof(int)));
+                ILM_CUDA(cudaMalloc(&t.part, cap * sizeof(double2)));
+                t.cap_rowent = cap;
+            }
+            ILM_CUDA(cudaMemcpyAsync(t.row_ptr, rptr.data(), rptr.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+            if (!rent.empty()) ILM_CUDA(cudaMemcpyAsync(t.row_ent, rent.data(), rent.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+            ILM_CUDA(cudaStreamSynchronize(p->stream));          // rptr / rent leave scope
+        }
     }
     ILM_CUDA(cudaStreamSynchronize(p->stream));
     return ILM_OK;

@@ -132,9 +132,12 @@ class SlabLaplacian:
         dist.all_to_all_single(self.recv[: sum(recv)], self.send[: sum(send)], output_split_sizes=recv,
                                input_split_sizes=send, group=self.group)
 
-    def inverse_laplacian(self, w1, w2=None, kernel_id=0):
+    def inverse_laplacian(self, w1, w2=None, kernel_id=0, in_library=False):
         """w1 (and w2, the second layout) hold this rank's rows and are overwritten with L^-1 w
-        (kernel_id selects another convolution kernel, e.g. an integrating factor)."""
+        (kernel_id selects another convolution kernel, e.g. an integrating factor).
+        in_library=True: one call of ilm_slab_solve -- both exchanges are grouped ncclSend / ncclRecv issued by
+        the library on the communicator bound to the plan (cache.comm_init); otherwise the three stages with
+        torch.distributed all_to_all_single between them (the cross-check path)."""
         L, C = self._L, self._C
         lib, plan, info = self.cache._lib, self.cache._plan, C.byref(self.info)
         l1, l2 = self.layouts
@@ -142,6 +145,10 @@ class SlabLaplacian:
             raise L.MethodError("SlabLaplacian: second field does not match the configured layouts")
         p1 = C.c_void_p(w1.data_ptr())
         p2 = C.c_void_p(w2.data_ptr()) if w2 is not None else None
+        if in_library:
+            L.check(lib.ilm_slab_solve(plan, info, kernel_id, l1, p1, -1 if l2 is None else l2, p2,
+                                       C.c_void_p(self.send.data_ptr()), C.c_void_p(self.recv.data_ptr())))
+            return w1 if w2 is None else (w1, w2)
         L.check(lib.ilm_slab_forward(plan, info, l1, p1, -1 if l2 is None else l2, p2, C.c_void_p(self.send.data_ptr())))
         self._exchange(0)
         L.check(lib.ilm_slab_columns(plan, info, kernel_id, C.c_void_p(self.recv.data_ptr()), C.c_void_p(self.send.data_ptr())))

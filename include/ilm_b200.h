@@ -297,6 +297,36 @@ int ilm_slab_columns(ilm_plan* plan, const ilm_slab_info* me, int kernel_id, con
 int ilm_slab_inverse(ilm_plan* plan, const ilm_slab_info* me, const double* recvbuf, int layout1, double* w1_rows, int layout2,
                      double* w2_rows /* NULL: one field */);
 
+/* ---- multi-GPU: NCCL behind the ABI (the reference is a single process) -----------------
+ * One process per GPU.  Rank 0 obtains a 128-byte unique id and the host language distributes it (MPI.jl,
+ * torch.distributed store, a file ...); every rank then binds a communicator to its plan.  All collectives of the
+ * sharded entry points run on the plan's stream.  NCCL is resolved at run time (dlopen of libnccl.so.2): a
+ * missing or failing NCCL gives ILM_ENCCL, the single-GPU entry points do not need it.                        */
+int ilm_comm_unique_id(void* id128, int nbytes);
+int ilm_comm_init(ilm_plan* plan, const void* id128, int nbytes, int rank, int nranks);
+int ilm_comm_destroy(ilm_plan* plan);
+int ilm_comm_info(const ilm_plan* plan, int* rank, int* nranks);
+/* columns [lo, hi) of an n-column Schur build owned by `rank`: contiguous, even-sized blocks (column pairs share
+ * one complex transform); pure host arithmetic                                                              */
+int ilm_column_range(int n, int nranks, int rank, int* lo, int* hi);
+/* create_RTLinvR / create_CLinvCT / create_GLinvD[_cross] (src/matrix_operators.jl:9-215) with the column loop
+ * (:16-26) sharded over the plan's communicator: each rank probes its block into its slice of the device matrix,
+ * one grouped in-place broadcast completes it; A (N x N, host or device) is the full matrix on every rank.
+ * Without a communicator: all columns locally.                                                              */
+int ilm_create_schur_sharded(ilm_plan* plan, int which, int kernel_id, double scale, double* A);
+/* The whole Dirichlet Poisson problem `solve(prob, sys)` of test/literate/dirichlet.jl:71-107 in one call:
+ * f* = L^-1 D_s [f], S = -E L^-1 R (sharded when the plan has a communicator), S s~ = (f+ + f-)/2 - E f*,
+ * s = -s~, f = L^-1 R s + f*.  fplus, fminus (NULL = 0): N surface values; f: Nodes{Primal}; s: N; S_out (NULL or
+ * N x N): the Schur complement.  Host or device pointers; S, its LU factors and every intermediate field stay on
+ * the device, so a host caller moves 2N doubles in and one field + N doubles out.                           */
+int ilm_dirichlet_poisson(ilm_plan* plan, const double* fplus, const double* fminus, double* f, double* s, double* S_out);
+/* One inverse Laplacian of row-distributed fields over the plan's communicator: ilm_slab_forward -> exchange ->
+ * ilm_slab_columns -> exchange -> ilm_slab_inverse with both exchanges issued inside the library (grouped
+ * ncclSend / ncclRecv); w*_rows are this rank's rows [row0, row1) (device), sendbuf / recvbuf device scratch of
+ * ilm_slab_buffer_doubles(me) doubles each.                                                                 */
+int ilm_slab_solve(ilm_plan* plan, const ilm_slab_info* me, int kernel_id, int layout1, double* w1_rows, int layout2,
+                   double* w2_rows /* NULL: one field */, double* sendbuf, double* recvbuf);
+
 /* ---- measurement hook ------------------------------------------------------
  * Times each pass of the convolution (A: rows forward, B: columns, C: rows
  * inverse) on the plan's stream with CUDA events: `reps` back-to-back launches

@@ -608,3 +608,30 @@ def test_probe_band_pass_equals_transform_pass(ddf, monkeypatch):
         oc = o.ScalarCache(o.Grid(g.NX, g.NY, g.dx, g.I0), *body, G)
         assert relerr(built["1"][0], oc.create_RTLinvR()) < RTOL
         assert relerr(built["1"][0], oc.create_RTLinvR_table()) < RTOL
+
+
+# ---------------------------------------------------------------- whole-problem entry point (ilm_dirichlet_poisson)
+@pytest.mark.parametrize("device", [False, True])
+def test_dirichlet_solve_single_call(device):
+    """`solve(prob, sys)` of test/literate/dirichlet.jl:71-107 as one library call: same S (bit-equal: the same
+    kernels), field and multiplier as the operator-by-operator composition, and as the oracle."""
+    g = ilm.PhysicalGrid.centered(128)
+    body = ilm.bodies.circle(1.0, 1.4 * g.dx)
+    G = ilm.lgf.lgf_table(128)
+    cache = ilm.SurfaceScalarCache(body, g, lgf_table=G, device=device)
+    oc = o.ScalarCache(o.Grid(g.NX, g.NY, g.dx, g.I0), *body[:5], G)
+    fplus, fminus = cache.points()[0].copy(), 0.3 * cache.points()[1]
+    f, s, S = ilm.dirichlet_solve(cache, fplus, fminus, return_S=True)
+    f1, s1, S1 = ilm.dirichlet_poisson(cache, fplus, fminus)
+    tonp = lambda a: a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)   # noqa: E731
+    assert np.array_equal(tonp(S), tonp(S1))
+    assert relerr(tonp(f.data), tonp(f1.data)) < 1e-13 and relerr(tonp(s.data), tonp(s1.data)) < 1e-9
+    fr, sr, Sr = o.dirichlet_solve(oc, fplus, fminus)
+    assert relerr(tonp(S), Sr) < RTOL
+    assert relerr(f.array(), fr) < 1e-10
+    assert relerr(tonp(s.data), sr) < 50 * np.linalg.cond(Sr) * np.finfo(float).eps
+    f2, s2 = ilm.dirichlet_solve(cache, fplus)                   # fminus = None
+    fr2, _, _ = o.dirichlet_solve(oc, fplus, S=Sr)
+    assert relerr(f2.array(), fr2) < 1e-10
+    assert cache.comm_info() == (0, 1)
+    assert relerr(tonp(ilm.create_schur_sharded(cache, "CLinvCT")), oc.create_CLinvCT()) < RTOL

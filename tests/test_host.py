@@ -456,3 +456,32 @@ def test_operators_reject_containers_of_another_grid():
     for fn, args in calls:
         with pytest.raises(ilm.DimensionMismatch):
             fn(*args)
+
+
+def test_column_range_rule_matches_python_sharding():
+    """ilm_column_range (the partition the library uses for ilm_create_schur_sharded / ilm_dirichlet_poisson) is the
+    rule of shard.column_ranges: contiguous, even-sized blocks that cover [0, n) (no GPU needed)."""
+    import ctypes as C
+    import ilm_b200 as ilm
+    from ilm_b200 import shard
+    lib = ilm._lib.load()
+    for n in (0, 1, 2, 7, 141, 4593, 4594):
+        for world in (1, 2, 3, 4, 8):
+            ref = shard.column_ranges(n, world)
+            got = []
+            for r in range(world):
+                lo, hi = C.c_int(), C.c_int()
+                assert lib.ilm_column_range(n, world, r, C.byref(lo), C.byref(hi)) == 0
+                got.append((lo.value, hi.value))
+            assert got == ref
+            assert got[0][0] == 0 and got[-1][1] == n and all(a[1] == b[0] for a, b in zip(got, got[1:]))
+            assert all(lo % 2 == 0 for lo, _ in got if lo < n)
+    lo, hi = C.c_int(), C.c_int()
+    assert lib.ilm_column_range(10, 2, 2, C.byref(lo), C.byref(hi)) != 0
+
+
+def test_comm_entry_points_fail_cleanly_without_a_plan():
+    import ilm_b200 as ilm
+    lib = ilm._lib.load()
+    assert lib.ilm_comm_init(None, None, 0, 0, 1) == ilm._lib.EINVAL
+    assert lib.ilm_comm_destroy(None) == ilm._lib.EINVAL
