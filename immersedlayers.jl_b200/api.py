@@ -88,8 +88,8 @@ _PIN_POOL_MAX = 1 << 28     # at most this many doubles (2 GiB) parked in the po
 _pin_pool_size = 0
 
 
-def _host_zeros(n):
-    """Host buffer for host mode.  Large buffers are page-locked (through torch) so that the
+def _host_zeros(n, zero=True):
+    """Host buffer for host mode (zero=False: contents undefined, for outputs that are overwritten whole).  Large buffers are page-locked (through torch) so that the
     library's H2D/D2H staging runs at DMA speed instead of through the driver's bounce buffer.
     Page-locking 134 MB costs ~30 ms, so released buffers are parked in a pool (see _recycle)
     and handed out again after a memset."""
@@ -100,12 +100,13 @@ def _host_zeros(n):
         if free:
             buf = free.pop()
             _pin_pool_size -= n
-            buf.fill(0.0)
+            if zero:
+                buf.fill(0.0)
             return buf
         try:
             import torch
             if torch.cuda.is_available():
-                buf = torch.zeros(n, dtype=torch.float64).pin_memory().numpy()
+                buf = (torch.zeros if zero else torch.empty)(n, dtype=torch.float64, pin_memory=True).numpy()
                 _PIN_IDS.add(id(buf))
                 weakref.finalize(buf, _PIN_IDS.discard, id(buf))     # ids are reused after a free
                 return buf
@@ -127,11 +128,11 @@ def _recycle(buf, extra_refs=0):
     _pin_pool_size += buf.size
 
 
-def _alloc(n, device):
+def _alloc(n, device, zero=True):
     if device:
         import torch
-        return torch.zeros(int(n), dtype=torch.float64, device="cuda")
-    return _host_zeros(n)
+        return (torch.zeros if zero else torch.empty)(int(n), dtype=torch.float64, device="cuda")
+    return _host_zeros(n, zero)
 
 
 class _Data:
@@ -800,7 +801,9 @@ def dirichlet_solve(cache, fplus, fminus=None, return_S=False):
     for v in (fp, fm):
         if v is not None and int(np.prod(v.shape)) != N:
             raise DimensionMismatch(f"dirichlet_solve: expected {N} surface values")
-    f, s = cache.zeros_grid(), cache.zeros_surface()
+    mx, my = cache.g.layout_shape(L.NODES_PRIMAL)
+    f = Nodes(Primal, cache.g, data=_alloc(mx * my, dev, zero=False))          # written whole by the library
+    s = ScalarData(N, data=_alloc(N, dev, zero=False))
     S = _matrix(cache, N) if return_S else None
     L.check(cache._lib.ilm_dirichlet_poisson(cache._plan, _ptr(fp), _ptr(fm) if fm is not None else None, _ptr(f.data),
                                              _ptr(s.data), _ptr(S) if S is not None else None))

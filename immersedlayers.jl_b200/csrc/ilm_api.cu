@@ -68,6 +68,9 @@ static int upload_points(ilm_plan* p, int N, const double* x, const double* y, c
                          const double* ds) {
     if (N > p->ncap) {
         cudaFree(p->x); cudaFree(p->y); cudaFree(p->nx); cudaFree(p->ny); cudaFree(p->ds); cudaFree(p->s_a); cudaFree(p->s_b);
+        // a failed allocation below must leave a plan that can still be destroyed (and reports N = 0), not dangling pointers
+        p->x = p->y = p->nx = p->ny = p->ds = p->s_a = p->s_b = nullptr;
+        p->ncap = 0; p->N = 0;
         const size_t b = (size_t)N * sizeof(double);
         ILM_CUDA(cudaMalloc(&p->x, b)); ILM_CUDA(cudaMalloc(&p->y, b)); ILM_CUDA(cudaMalloc(&p->nx, b));
         ILM_CUDA(cudaMalloc(&p->ny, b)); ILM_CUDA(cudaMalloc(&p->ds, b)); ILM_CUDA(cudaMalloc(&p->s_a, 4 * b));

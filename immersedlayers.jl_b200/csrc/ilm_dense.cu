@@ -370,6 +370,104 @@ __global__ void __launch_bounds__(PR_THREADS) k_lu_panel_regs(int n, int k0, int
     cl.sync();                                       // no CTA leaves while a peer may still write its shared memory
 }
 
+__global__ void __launch_bounds__(PR_THREADS) k_lu_panel_rot(int n, int k0, int nb, double* __restrict__ A, int* __restrict__ ipiv) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    __shared__ PanelXchg X;
+    __shared__ double s_val[PR_WARPS];
+    __shared__ int s_idx[PR_WARPS];
+    __shared__ double c_row[NB], o_row[NB];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int row = k0 + rank * PR_THREADS + tid;
+    const bool has = row < n;
+    double a[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) a[c] = (has && c < nb) ? A[(size_t)(k0 + c) * n + row] : 0.0;
+    cl.sync();                                       // every CTA of the cluster is running before the first DSMEM push
+    // ROLLED column loop: the register row is rotated by one position per column, so the current column is always
+    // a[0] and the loop body is the same code for every column (the fully unrolled form, k_lu_panel_regs, is ~250 KB of
+    // straight-line code: ncu showed 58 % no_instructions stalls).  Position p holds logical column (jj + p) mod 32;
+    // positions >= 32 - jj are the finished multipliers of the columns to the left.  All threads rotate alike, so the
+    // row exchanges through shared memory stay position-wise.
+#pragma unroll 1
+    for (int jj = 0; jj < NB; ++jj) {
+        if (jj < nb) {
+            const int col = k0 + jj, buf = jj & 1;
+            // candidate of this warp, of this CTA (every warp reduces the warp candidates redundantly)
+            const bool active = has && row >= col;
+            double best = active ? fabs(a[0]) : -1.0;
+            int bi = active ? row : n;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) argmax_step(best, bi, off);
+            if (lane == 0) { s_val[wid] = best; s_idx[wid] = bi; }
+            __syncthreads();
+            best = lane < PR_WARPS ? s_val[lane] : -1.0;
+            bi = lane < PR_WARPS ? s_idx[lane] : n;
+#pragma unroll
+            for (int off = PR_WARPS / 2; off > 0; off >>= 1) argmax_step(best, bi, off);
+            const double cta_val = __shfl_sync(0xffffffffu, best, 0);
+            const int cta_piv = __shfl_sync(0xffffffffu, bi, 0);
+            if (has && row == cta_piv) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) c_row[c] = a[c];
+            }
+            if (has && row == col) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) o_row[c] = a[c];
+            }
+            __syncthreads();
+            if (wid < C) {                               // warp p pushes to peer p
+                PanelXchg* Xp = cl.map_shared_rank(&X, wid);
+                Xp->rows[buf][rank][lane] = c_row[lane];
+                if (lane == 0) { Xp->val[buf][rank] = cta_val; Xp->idx[buf][rank] = cta_piv; }
+                if (rank == (col - k0) / PR_THREADS) Xp->old[buf][lane] = o_row[lane];
+            }
+            cl.sync();
+            double bv = -1.0;
+            int piv = n, pw = 0;
+            for (int p = 0; p < C; ++p) {
+                const double v = X.val[buf][p];
+                const int i = X.idx[buf][p];
+                if (v > bv || (v == bv && i < piv)) { bv = v; piv = i; pw = p; }
+            }
+            const double* prow = X.rows[buf][pw];
+            if (piv != col) {
+                if (has && row == piv) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) a[c] = X.old[buf][c];
+                } else if (has && row == col) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) a[c] = prow[c];
+                }
+            }
+            if (rank == 0 && tid == 0) ipiv[col] = piv + 1;
+            if (has && row > col) {
+                const double l = a[0] / prow[0];
+                a[0] = l;
+                const int live = NB - jj;                    // positions 1 .. live-1 are the columns still to eliminate
+#pragma unroll
+                for (int c = 1; c < NB; ++c)
+                    if (c < live) a[c] = a[c] - l * prow[c];
+            }
+            {                                                // rotate: the finished column goes to the back
+                const double t0 = a[0];
+#pragma unroll
+                for (int c = 0; c < NB - 1; ++c) a[c] = a[c + 1];
+                a[NB - 1] = t0;
+            }
+        }
+    }
+    if (has) {                                           // after nb rotations position p holds logical column (p + nb) mod 32
+        const int done = nb < NB ? nb : NB;
+#pragma unroll
+        for (int p = 0; p < NB; ++p) {
+            const int c = (p + done) & (NB - 1);
+            if (c < nb) A[(size_t)(k0 + c) * n + row] = a[p];
+        }
+    }
+    cl.sync();                                       // no CTA leaves while a peer may still write its shared memory
+}
+
 static int launch_panel_regs(int n, int k0, int nb, double* A, int* ipiv, cudaStream_t st) {
     const int rows = n - k0;
     const int C = rows <= 8 * PR_THREADS ? 8 : 16;
@@ -382,7 +480,9 @@ static int launch_panel_regs(int n, int k0, int nb, double* A, int* ipiv, cudaSt
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_regs, n, k0, nb, A, ipiv));
+    static const bool unrolled = getenv("ILM_LU_PANEL_UNROLLED") != nullptr;     // the fully unrolled panel, kept for comparison
+    if (unrolled) ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_regs, n, k0, nb, A, ipiv));
+    else ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_rot, n, k0, nb, A, ipiv));
     return ILM_OK;
 }
 
@@ -739,6 +839,7 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
     static const int kb_env = getenv("ILM_LU_OUTER") ? atoi(getenv("ILM_LU_OUTER")) : 0;
     const int KB = kb_env >= NB ? (kb_env / NB) * NB : NB;
     ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_regs, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_rot, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     auto panel = [&](int k0, int nb) -> int {
         if (!panel_smem_only && n - k0 <= PR_MAXC * PR_THREADS) {
             ILM_TRY(launch_panel_regs(n, k0, nb, dA, dP, st));
@@ -770,6 +871,62 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
         k_lu_trsm<<<(cend - cbeg + 63) / 64, 64, 0, st>>>(n, k0, nb, dA, cbeg, cend);
         g_dense_launches++;
     };
+    // Right-looking LU with LOOK-AHEAD (the default, KB == NB): the panel factorisation is latency bound (a cluster of
+    // 8-16 SMs, one cluster barrier per column) and used to leave the other ~130 SMs idle for more than half of the
+    // factorisation.  Two internal streams: `hi` (high priority) carries panel k+1 and the narrow update that feeds it
+    // (interchanges, triangular solve and rank-32 update of the next 32 columns only), `lo` carries the wide update of
+    // step k (all other columns, left and right interchanges) and runs underneath the next panel.
+    static const bool no_lookahead = getenv("ILM_LU_NO_LOOKAHEAD") != nullptr;
+    if (KB == NB && !no_lookahead && n > 2 * NB) {
+        struct Aux { cudaStream_t hi = nullptr, lo = nullptr; cudaEvent_t begin = nullptr, evP = nullptr, evW = nullptr, end = nullptr; };
+        static Aux aux_dev[64];
+        int dev = 0;
+        ILM_CUDA(cudaGetDevice(&dev));
+        Aux& ax = aux_dev[dev & 63];
+        if (!ax.hi) {
+            int lo_p = 0, hi_p = 0;
+            ILM_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+            ILM_CUDA(cudaStreamCreateWithPriority(&ax.hi, cudaStreamNonBlocking, hi_p));
+            ILM_CUDA(cudaStreamCreateWithPriority(&ax.lo, cudaStreamNonBlocking, lo_p));
+            ILM_CUDA(cudaEventCreateWithFlags(&ax.begin, cudaEventDisableTiming));
+            ILM_CUDA(cudaEventCreateWithFlags(&ax.evP, cudaEventDisableTiming));
+            ILM_CUDA(cudaEventCreateWithFlags(&ax.evW, cudaEventDisableTiming));
+            ILM_CUDA(cudaEventCreateWithFlags(&ax.end, cudaEventDisableTiming));
+        }
+        const cudaStream_t user = st;
+        ILM_CUDA(cudaEventRecord(ax.begin, user));
+        ILM_CUDA(cudaStreamWaitEvent(ax.hi, ax.begin, 0));
+        ILM_CUDA(cudaStreamWaitEvent(ax.lo, ax.begin, 0));
+        bool wide_pending = false;
+        for (int k0 = 0; k0 < n; k0 += NB) {
+            const int nb = n - k0 < NB ? n - k0 : NB, k1 = k0 + nb;
+            const int nb1 = n - k1 < NB ? n - k1 : NB, k1e = k1 + nb1;          // the next panel's columns [k1, k1e)
+            st = ax.hi;
+            ILM_TRY(panel(k0, nb));                                             // runs beside the wide update of step k-1
+            ILM_CUDA(cudaEventRecord(ax.evP, ax.hi));
+            ILM_CUDA(cudaStreamWaitEvent(ax.lo, ax.evP, 0));
+            if (wide_pending) ILM_CUDA(cudaStreamWaitEvent(ax.hi, ax.evW, 0)); // the next columns carry every earlier update
+            if (nb1 > 0) {                                                      // narrow update: only what panel k+1 needs
+                ILM_TRY(launch_swap(n, k0, nb, dA, dP, k1, k1e, k1e, k1e, st));
+                trsm(k0, nb, k1, k1e);
+                gemm(n - k1, nb1, nb, k1, k0, k0, k1);
+            }
+            st = ax.lo;                                                         // wide update: everything else
+            ILM_TRY(launch_swap(n, k0, nb, dA, dP, 0, n, k0, k1e, st));
+            if (n - k1e > 0) {
+                trsm(k0, nb, k1e, n);
+                gemm(n - k1, n - k1e, nb, k1, k0, k0, k1e);
+            }
+            ILM_CUDA(cudaEventRecord(ax.evW, ax.lo));
+            wide_pending = true;
+        }
+        ILM_CUDA(cudaStreamWaitEvent(ax.hi, ax.evW, 0));
+        ILM_CUDA(cudaEventRecord(ax.end, ax.hi));
+        ILM_CUDA(cudaStreamWaitEvent(user, ax.end, 0));
+        st = user;
+        ILM_CUDA(cudaGetLastError());
+        return io.finish();
+    }
     // Two-level right-looking LU: 32-wide register panels inside an outer block of KB columns; the inner trailing
     // updates touch only the outer block, the rest of the matrix gets ONE rank-KB update per outer block (the matrix
     // is read and written n/KB times instead of n/32 times).

@@ -156,6 +156,11 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
         return ILM_ESIZE;
     }
     double* dtab = nullptr;
+    ConvKernel k;
+    struct Guard {                                  // an error return below frees what this call allocated
+        double** tab; ConvKernel* k; bool armed = true;
+        ~Guard() { if (armed) { cudaFree(*tab); cudaFree(k->ghat); cudaFree(k->gxt); } }
+    } guard{&dtab, &k};
     const double* src = table;
     if (!is_device_ptr(table)) {
         ILM_CUDA(cudaMalloc(&dtab, (size_t)n * NY * sizeof(double)));
@@ -164,7 +169,6 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     }
     // h = eps_i eps_j (G - c0) into scratch field g_a (NX x NY)
     ILM_TRY(launch_lgf_prep(p, src, n, NX, NY, c0, p->g_a));
-    ConvKernel k;
     ConvArgs a = conv_base_args(p);
     a.g = ConvGeom{p->Lx, p->Ly, NY, (NY + 1) & ~1};
     ILM_CUDA(cudaMalloc(&k.ghat, ghat_elems(a.g) * sizeof(double)));
@@ -179,6 +183,7 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     ILM_TRY(conv_launcher(p->Ly)(3, a, p->nsm, p->stream, nullptr));
     p->launches += 2;
     ILM_CUDA(cudaStreamSynchronize(p->stream));
+    guard.armed = false;
     if (dtab) {
         if (p->kernels.empty() && !p->lgf_dev) { p->lgf_dev = dtab; p->lgf_ld = n; }   // kernel 0 = LGF: keep the table
         else cudaFree(dtab);

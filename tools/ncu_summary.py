@@ -14,7 +14,9 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
         'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum', 'lts__t_sector_hit_rate.pct',
-        'smsp__warps_eligible.avg.per_cycle_active', 'sm__cycles_elapsed.max']
+        'smsp__warps_eligible.avg.per_cycle_active', 'sm__cycles_elapsed.max',
+        'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active',
+        'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed']
 for r in rows[2:]:
     print('-----', r[hdr.index('Kernel Name')], 'grid', r[hdr.index('Grid Size')] if 'Grid Size' in hdr else '')
     for w in want:
