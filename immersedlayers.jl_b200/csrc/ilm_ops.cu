@@ -22,6 +22,27 @@ namespace ilm {
         (p)->launches++;              \
     } while (0)
 
+// a / d, correctly rounded, for the sweeps that divide every output by the grid spacing (_scale_derivative!,
+// src/grid_operators.jl:8-9): with r = RN(1/d) computed once per thread, q0 = RN(a r), e = a - d q0 (exact in one
+// FMA), q = RN(q0 + e r) is RN(a/d) (Markstein's theorem; it needs the significand of d not to be all ones and the
+// quotient to stay in the normal range -- anything else takes the hardware division).  3 FP64 instructions instead of
+// the ~18 of a division; the stencil outputs stay bit-identical to the oracle's `/ dx`.
+struct ExactDiv {
+    double d, r;
+    bool fast;
+    __device__ __forceinline__ explicit ExactDiv(double div) : d(div), r(1.0 / div) {
+        const unsigned long long m = (unsigned long long)__double_as_longlong(div) & 0xFFFFFFFFFFFFFull;
+        fast = m != 0xFFFFFFFFFFFFFull && isfinite(r) && r != 0.0;
+    }
+    __device__ __forceinline__ double operator()(double a) const {
+        const double q0 = __dmul_rn(a, r);
+        const double q1 = __fma_rn(__fma_rn(-d, q0, a), r, q0);
+        const double m = fabs(q1);
+        if (fast && ((m > 1e-290 && m < 1e290) || a == 0.0)) return a == 0.0 ? q0 : q1;
+        return a / d;
+    }
+};
+
 // ------------------------------------------------------------------ fill / scale
 __global__ void k_fill(double* __restrict__ dst, size_t n, double value) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -399,6 +420,7 @@ static dim3 st_grid(int NX, int NY) { return dim3((NX + ST_BX - 1) / ST_BX, (NY 
 // p[x,y] = -u[x,y] + u[x+1,y] - v[x,y] + v[x,y+1]          (A.3)
 __global__ void k_divergence(int NX, int NY, const double* __restrict__ u, const double* __restrict__ v,
                              double* __restrict__ out, double div, int ybeg, int yend) {
+    const ExactDiv dv(div);
     const int x = blockIdx.x * ST_BX + threadIdx.x;
     const int y0 = ybeg + blockIdx.y * ST_ROWS;
     if (x >= NX - 1) return;
@@ -410,7 +432,7 @@ __global__ void k_divergence(int NX, int NY, const double* __restrict__ u, const
         if (y >= NY - 1 || y >= yend) break;
         const double vn = v[(size_t)(y + 1) * mxv + x];
         const double ul = u[(size_t)y * NX + x], ur = u[(size_t)y * NX + x + 1];
-        out[(size_t)y * mxv + x] = (((-ul + ur) - vprev) + vn) / div;
+        out[(size_t)y * mxv + x] = dv(((-ul + ur) - vprev) + vn);
         vprev = vn;
     }
 }
@@ -424,6 +446,7 @@ int launch_divergence(ilm_plan* p, const double* u, const double* v, double* out
 // u[x,y] = p[x,y]-p[x-1,y] (x in 2:NX-1), v[x,y] = p[x,y]-p[x,y-1] (y in 2:NY-1), zero elsewhere
 __global__ void k_grad(int NX, int NY, const double* __restrict__ pn, double* __restrict__ u, double* __restrict__ v,
                        double div) {
+    const ExactDiv dv(div);
     const int x = blockIdx.x * ST_BX + threadIdx.x;
     const int y0 = blockIdx.y * ST_ROWS;
     if (x >= NX) return;
@@ -437,12 +460,12 @@ __global__ void k_grad(int NX, int NY, const double* __restrict__ pn, double* __
         const double pc = (prow && x < mp) ? pn[(size_t)y * mp + x] : 0.0;
         if (prow) {   // u row
             double val = 0.0;
-            if (x >= 1 && x <= NX - 2) val = (pc - pn[(size_t)y * mp + x - 1]) / div;
+            if (x >= 1 && x <= NX - 2) val = dv(pc - pn[(size_t)y * mp + x - 1]);
             u[(size_t)y * NX + x] = val;
         }
         if (x < mp) {  // v row
             double val = 0.0;
-            if (y >= 1 && y <= NY - 2) val = (pc - pprev) / div;
+            if (y >= 1 && y <= NY - 2) val = dv(pc - pprev);
             v[(size_t)y * mp + x] = val;
         }
         pprev = pc;
@@ -457,6 +480,7 @@ int launch_grad(ilm_plan* p, const double* in, double* u, double* v, double div)
 // u[x,y] = s[x,y+1]-s[x,y] ; v[x,y] = s[x,y]-s[x+1,y]
 __global__ void k_curl_n2e(int NX, int NY, const double* __restrict__ s, double* __restrict__ u,
                            double* __restrict__ v, double div) {
+    const ExactDiv dv(div);
     const int x = blockIdx.x * ST_BX + threadIdx.x;
     const int y0 = blockIdx.y * ST_ROWS;
     if (x >= NX) return;
@@ -466,10 +490,10 @@ __global__ void k_curl_n2e(int NX, int NY, const double* __restrict__ s, double*
     for (int r = 0; r < ST_ROWS; ++r) {
         const int y = y0 + r;
         if (y >= NY) break;
-        if (x < mxv) v[(size_t)y * mxv + x] = (sc - s[(size_t)y * NX + x + 1]) / div;
+        if (x < mxv) v[(size_t)y * mxv + x] = dv(sc - s[(size_t)y * NX + x + 1]);
         if (y < NY - 1) {
             const double sn = s[(size_t)(y + 1) * NX + x];
-            u[(size_t)y * NX + x] = (sn - sc) / div;
+            u[(size_t)y * NX + x] = dv(sn - sc);
             sc = sn;
         }
     }
@@ -485,6 +509,7 @@ int launch_curl_n2e(ilm_plan* p, const double* s, double* u, double* v, double d
 __global__ void k_vecfield_from_potentials(int NX, int NY, const double* __restrict__ psi, const double* __restrict__ phi,
                                            const double* __restrict__ vpu, const double* __restrict__ vpv,
                                            double* __restrict__ u, double* __restrict__ v, double div) {
+    const ExactDiv dv(div);
     const int x = blockIdx.x * ST_BX + threadIdx.x;
     const int y0 = blockIdx.y * ST_ROWS;
     if (x >= NX) return;
@@ -498,9 +523,9 @@ __global__ void k_vecfield_from_potentials(int NX, int NY, const double* __restr
         const bool prow = y < NY - 1;
         const double pc = (phi && prow && x < mp) ? phi[(size_t)y * mp + x] : 0.0;
         if (x < mp) {   // v row
-            const double cv = psi ? (sc - psi[(size_t)y * NX + x + 1]) / div : 0.0;
+            const double cv = psi ? dv(sc - psi[(size_t)y * NX + x + 1]) : 0.0;
             double gv = 0.0;
-            if (phi && y >= 1 && y <= NY - 2) gv = (pc - pprev) / div;
+            if (phi && y >= 1 && y <= NY - 2) gv = dv(pc - pprev);
             double val = __dadd_rn(cv, gv);
             if (vpv) val = __dadd_rn(val, vpv[(size_t)y * mp + x]);
             v[(size_t)y * mp + x] = val;
@@ -509,11 +534,11 @@ __global__ void k_vecfield_from_potentials(int NX, int NY, const double* __restr
             double cu = 0.0;
             if (psi) {
                 const double sn = psi[(size_t)(y + 1) * NX + x];
-                cu = (sn - sc) / div;
+                cu = dv(sn - sc);
                 sc = sn;
             }
             double gu = 0.0;
-            if (phi && x >= 1 && x <= NX - 2) gu = (pc - phi[(size_t)y * mp + x - 1]) / div;
+            if (phi && x >= 1 && x <= NX - 2) gu = dv(pc - phi[(size_t)y * mp + x - 1]);
             double val = __dadd_rn(cu, gu);
             if (vpu) val = __dadd_rn(val, vpu[(size_t)y * NX + x]);
             u[(size_t)y * NX + x] = val;
@@ -531,6 +556,7 @@ int launch_vecfield_from_potentials(ilm_plan* p, const double* psi, const double
 // w[x,y] = u[x,y-1]-u[x,y]-v[x-1,y]+v[x,y], x in 2:NX-1, y in 2:NY-1, zero elsewhere
 __global__ void k_curl_e2n(int NX, int NY, const double* __restrict__ u, const double* __restrict__ v,
                            double* __restrict__ w, double div, int ybeg, int yend) {
+    const ExactDiv dv(div);
     const int x = blockIdx.x * ST_BX + threadIdx.x;
     const int y0 = ybeg + blockIdx.y * ST_ROWS;
     if (x >= NX) return;
@@ -543,7 +569,7 @@ __global__ void k_curl_e2n(int NX, int NY, const double* __restrict__ u, const d
         const double uc = (y < NY - 1) ? u[(size_t)y * NX + x] : 0.0;
         double val = 0.0;
         if (x >= 1 && x <= NX - 2 && y >= 1 && y <= NY - 2)
-            val = (((uprev - uc) - v[(size_t)y * mxv + x - 1]) + v[(size_t)y * mxv + x]) / div;
+            val = dv(((uprev - uc) - v[(size_t)y * mxv + x - 1]) + v[(size_t)y * mxv + x]);
         w[(size_t)y * NX + x] = val;
         uprev = uc;
     }
@@ -678,17 +704,18 @@ int launch_vec_pointwise(ilm_plan* p, int op, const double* in, double* out) {
 __global__ void k_grad_tensor(int NX, int NY, const double* __restrict__ u, const double* __restrict__ v,
                               double* __restrict__ dudx, double* __restrict__ dudy, double* __restrict__ dvdx,
                               double* __restrict__ dvdy, double div) {
+    const ExactDiv dv(div);
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= NX || y >= NY) return;
     const int mp = NX - 1;
     if (x < NX - 1 && y < NY - 1) {
-        dudx[(size_t)y * mp + x] = (u[(size_t)y * NX + x + 1] - u[(size_t)y * NX + x]) / div;
-        dvdy[(size_t)y * mp + x] = (v[(size_t)(y + 1) * mp + x] - v[(size_t)y * mp + x]) / div;
+        dudx[(size_t)y * mp + x] = dv(u[(size_t)y * NX + x + 1] - u[(size_t)y * NX + x]);
+        dvdy[(size_t)y * mp + x] = dv(v[(size_t)(y + 1) * mp + x] - v[(size_t)y * mp + x]);
     }
     double a = 0.0, b = 0.0;
     if (x >= 1 && x <= NX - 2 && y >= 1 && y <= NY - 2) {
-        a = (u[(size_t)y * NX + x] - u[(size_t)(y - 1) * NX + x]) / div;
-        b = (v[(size_t)y * mp + x] - v[(size_t)y * mp + x - 1]) / div;
+        a = dv(u[(size_t)y * NX + x] - u[(size_t)(y - 1) * NX + x]);
+        b = dv(v[(size_t)y * mp + x] - v[(size_t)y * mp + x - 1]);
     }
     dudy[(size_t)y * NX + x] = a;
     dvdx[(size_t)y * NX + x] = b;
@@ -706,21 +733,22 @@ int launch_grad_tensor(ilm_plan* p, const double* edges, double* eg, double div)
 __global__ void k_div_tensor(int NX, int NY, const double* __restrict__ dudx, const double* __restrict__ dudy,
                              const double* __restrict__ dvdx, const double* __restrict__ dvdy,
                              double* __restrict__ u, double* __restrict__ v, double div) {
+    const ExactDiv dv(div);
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= NX || y >= NY) return;
     const int mp = NX - 1;
     if (y < NY - 1) {
         double val = 0.0;
         if (x >= 1 && x <= NX - 2)
-            val = (((dudx[(size_t)y * mp + x] - dudx[(size_t)y * mp + x - 1]) + dudy[(size_t)(y + 1) * NX + x]) -
-                   dudy[(size_t)y * NX + x]) / div;
+            val = dv(((dudx[(size_t)y * mp + x] - dudx[(size_t)y * mp + x - 1]) + dudy[(size_t)(y + 1) * NX + x]) -
+                   dudy[(size_t)y * NX + x]);
         u[(size_t)y * NX + x] = val;
     }
     if (x < NX - 1) {
         double val = 0.0;
         if (y >= 1 && y <= NY - 2)
-            val = (((dvdx[(size_t)y * NX + x + 1] - dvdx[(size_t)y * NX + x]) + dvdy[(size_t)y * mp + x]) -
-                   dvdy[(size_t)(y - 1) * mp + x]) / div;
+            val = dv(((dvdx[(size_t)y * NX + x + 1] - dvdx[(size_t)y * NX + x]) + dvdy[(size_t)y * mp + x]) -
+                   dvdy[(size_t)(y - 1) * mp + x]);
         v[(size_t)y * mp + x] = val;
     }
 }
