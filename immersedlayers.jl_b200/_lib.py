@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libilm_b200.so")
+LIB_PATH = os.environ.get("ILM_B200_LIB") or os.path.join(_HERE, "libilm_b200.so")     # ILM_B200_LIB: tuning builds (tools/)
 
 OK, EINVAL, ESIZE, ECUDA, ENCCL, ENOMEM = range(6)
 
@@ -14,7 +14,7 @@ NODES_PRIMAL, NODES_DUAL, XEDGES, YEDGES, EDGES, EDGEGRAD = range(6)
 SCALAR_CACHE, VECTOR_CACHE = 0, 1
 NORMAL, CROSS = 0, 1
 RTLINVR, CLINVCT, GLINVD, GLINVD_CROSS = range(4)
-DDF = {"yang3": 0, "m3": 1, "roma": 2, "m4prime": 3, "witchhat": 4}
+DDF = {"yang3": 0, "m3": 1, "roma": 2, "m4prime": 3, "witchhat": 4, "goza": 5}    # goza: named, answered with ILM_EINVAL
 GRID_SCALING, INDEX_SCALING = 0, 1
 
 

@@ -156,6 +156,14 @@ class _Data:
             return self.data.detach().cpu().numpy()
         return self.data
 
+    @property
+    def is_complex(self):
+        return self.data.is_complex() if _is_torch(self.data) else np.iscomplexobj(self.data)
+
+    @property
+    def eltype(self):
+        return complex if self.is_complex else float
+
     def fill(self, value):
         if _is_torch(self.data):
             self.data.fill_(value)
@@ -164,7 +172,7 @@ class _Data:
         return self
 
     def set(self, arr):
-        arr = np.asarray(arr, dtype=np.float64).ravel(order="F")
+        arr = np.asarray(arr, dtype=np.complex128 if self.is_complex else np.float64).ravel(order="F")
         if arr.shape[0] != len(self):
             raise DimensionMismatch(f"expected {len(self)} values, got {arr.shape[0]}")
         if _is_torch(self.data):
@@ -272,7 +280,7 @@ class SurfaceScalarCache:
     normals and arc weights (`points`, `normals`, `areas`)."""
 
     def __init__(self, body, g, scaling=GridScaling, ddftype="yang3", lgf_table=None, c0=None,
-                 device=False, stream=None, parent=None):
+                 device=False, stream=None, parent=None, dtype=float):
         """parent = another cache on the same grid: the Laplacian is shared (`L = L`,
         src/forcing.jl:201-248) through ilm_plan_create_shared; the parent must outlive this cache."""
         self.g = g
@@ -290,6 +298,11 @@ class SurfaceScalarCache:
         self.scaling = scaling
         self.ddftype = ddftype
         self.device = bool(device)
+        # dtype = ComplexF64 (src/cache.jl:167,187; test/surface_ops.jl:109-119): the similar_* containers are complex
+        # and every (real-linear) operator acts on the real and imaginary parts, two library calls per operator
+        if dtype not in (float, complex, np.float64, np.complex128):
+            raise MethodError(f"dtype must be float or complex, got {dtype!r}")
+        self.dtype = complex if dtype in (complex, np.complex128) else float
         if ddftype not in L.DDF:
             raise MethodError(f"unknown ddftype {ddftype!r}")
         if parent is not None:
@@ -361,6 +374,19 @@ class SurfaceScalarCache:
 
     def zeros_surfacevec(self):
         return VectorData(self.N, device=self.device)
+
+    def _cplx(self, d):
+        """Container of the cache's element type (complex caches: complex zeros of the same length)."""
+        if self.dtype is complex and not d.is_complex:
+            if _is_torch(d.data):
+                import torch
+                d.data = torch.zeros(len(d), dtype=torch.complex128, device=d.data.device)
+            else:
+                d.data = np.zeros(len(d), dtype=np.complex128)
+        return d
+
+    def eltype(self):
+        return self.dtype
 
     def update_points(self, body):
         """update_system (src/system.jl:26-50): new body, same L."""
@@ -1460,12 +1486,50 @@ def _check_containers(what, args):
                                         f"(grid {cache.g.NX} x {cache.g.NY}, {cache.N} points: expected {n})")
 
 
+_NOT_LINEAR = {"convective_derivative", "w_cross_v"}
+
+
+def _complex_call(fn, args, kwargs):
+    """An operator on complex containers (dtype = ComplexF64 caches): the operators of the path are real-linear, so
+    the real and the imaginary parts go through the library one after the other and are merged back."""
+    import copy
+    if fn.__name__ in _NOT_LINEAR:
+        raise MethodError(f"{fn.__name__}: not defined for complex data (the operator is bilinear)")
+    data = [a for a in args if isinstance(a, _Data)]
+    if not all(a.is_complex for a in data):
+        raise MethodError(f"{fn.__name__}: real and complex containers cannot be mixed")
+    parts = []
+    for part in ("real", "imag"):
+        clones = {}
+        for a in data:
+            if id(a) in clones:
+                continue
+            c = copy.copy(a)
+            src = getattr(a.data, part)
+            c.data = src.contiguous().clone() if _is_torch(src) else np.ascontiguousarray(src).copy()
+            clones[id(a)] = c
+        fn(*[clones[id(a)] if isinstance(a, _Data) else a for a in args], **kwargs)
+        parts.append(clones)
+    for a in data:
+        re, im = parts[0][id(a)].data, parts[1][id(a)].data
+        if _is_torch(a.data):
+            import torch
+            a.data.copy_(torch.complex(re, im))
+        else:
+            a.data[...] = re + 1j * im
+        for clone in (parts[0][id(a)], parts[1][id(a)]):
+            clone.data = np.zeros(0)                   # the clones must not recycle the originals' buffers
+    return args[0]
+
+
 def _checked(fn):
     import functools
 
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
         _check_containers(fn.__name__, args)
+        if any(isinstance(a, _Data) and a.is_complex for a in args):
+            return _complex_call(fn, args, kwargs)
         return fn(*args, **kwargs)
     return wrapper
 
@@ -1482,3 +1546,21 @@ def _wrap_operators():
 
 
 _wrap_operators()
+
+
+def _wrap_zeros(cls):
+    """zeros_* honour the cache's element type; similar_* are the reference's names (src/cache.jl:395-440)."""
+    import functools
+    for name, fn in list(vars(cls).items()):
+        if name.startswith("zeros_") and callable(fn):
+            def make(f):
+                @functools.wraps(f)
+                def w(self, *a, **k):
+                    return self._cplx(f(self, *a, **k))
+                return w
+            setattr(cls, name, make(fn))
+            setattr(cls, "similar_" + name[len("zeros_"):], getattr(cls, name))
+
+
+_wrap_zeros(SurfaceScalarCache)
+_wrap_zeros(SurfaceVectorCache)

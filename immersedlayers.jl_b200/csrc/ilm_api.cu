@@ -164,6 +164,10 @@ extern "C" int ilm_plan_create(const ilm_grid* grid, int N, const double* x, con
         set_error("ilm_plan_create: null argument");
         return ILM_EINVAL;
     }
+    if (ddf == ILM_DDF_GOZA) {
+        set_error("ilm_plan_create: Goza DDF not provided (its kernel is defined only in CartesianGrids.jl, which the reference does not vendor)");
+        return ILM_EINVAL;
+    }
     if (ddf < 0 || ddf > ILM_DDF_WITCHHAT || (scaling != ILM_GRID_SCALING && scaling != ILM_INDEX_SCALING)) {
         set_error("ilm_plan_create: unknown ddf or scaling");
         return ILM_EINVAL;

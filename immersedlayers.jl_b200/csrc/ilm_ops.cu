@@ -175,9 +175,57 @@ int launch_forcing_area(ilm_plan* p, const double* str, const double* mask, doub
     return ILM_OK;
 }
 
+// regularize! = fill!(s, 0) + R f (src/surface_operators.jl:38-41) in ONE sweep: a block zero-fills its slice of the
+// field, then (after a block barrier, which orders the two stores of a cell) gathers the active cells of that slice.
+// The cell list is ascending, so the slice's cells are one contiguous run found by a binary search.
+__global__ void __launch_bounds__(256) k_regularize_fused(size_t n, size_t chunk, int ncell, int W2, const int* __restrict__ cell_idx,
+                                                          const int* __restrict__ cell_off, const int* __restrict__ ent,
+                                                          const double* __restrict__ wR, const double* __restrict__ f,
+                                                          const double* __restrict__ mul, double sign, double* __restrict__ out) {
+    const size_t lo = (size_t)blockIdx.x * chunk;
+    const size_t hi = lo + chunk < n ? lo + chunk : n;
+    if (lo >= hi) return;
+    if ((reinterpret_cast<uintptr_t>(out + lo) & 15) == 0) {
+        double2* d2 = reinterpret_cast<double2*>(out + lo);
+        const size_t n2 = (hi - lo) >> 1;
+        for (size_t q = threadIdx.x; q < n2; q += 256) d2[q] = make_double2(0.0, 0.0);
+        if (threadIdx.x == 0 && ((hi - lo) & 1)) out[hi - 1] = 0.0;
+    } else {
+        for (size_t q = lo + threadIdx.x; q < hi; q += 256) out[q] = 0.0;
+    }
+    int a = 0, b = ncell;                                   // first active cell >= lo
+    while (a < b) { const int m = (a + b) >> 1; if ((size_t)cell_idx[m] < lo) a = m + 1; else b = m; }
+    __syncthreads();
+    for (int c = a + threadIdx.x; c < ncell; c += 256) {
+        const size_t cell = (size_t)cell_idx[c];
+        if (cell >= hi) break;
+        double sum = 0.0;
+        const int q1 = cell_off[c + 1];
+        for (int q = cell_off[c]; q < q1; ++q) {
+            const int id = ent[q];
+            double v = f[id / W2];
+            if (mul) v = __dmul_rn(mul[id / W2], v);
+            v = sign < 0 ? -v : v;
+            sum = __dadd_rn(sum, __dmul_rn(wR[id], v));
+        }
+        out[cell] = sum;
+    }
+}
+
 int launch_regularize(ilm_plan* p, const DevTable& t, const double* f, const double* mul, double sign, double* out,
                       bool zero) {
-    if (zero) ILM_TRY(launch_fill(p, out, (size_t)t.mx * t.my, 0.0));
+    if (zero) {
+        const size_t n = (size_t)t.mx * t.my;
+        if (n == 0) return ILM_OK;
+        size_t blocks = (size_t)p->nsm * 8;
+        size_t chunk = ((n + blocks - 1) / blocks + 1) & ~(size_t)1;
+        if (chunk < 512) chunk = 512;
+        blocks = (n + chunk - 1) / chunk;
+        k_regularize_fused<<<(unsigned)blocks, 256, 0, p->stream>>>(n, chunk, t.ncell, t.W * t.W, t.cell_idx, t.cell_off, t.ent,
+                                                                    t.wR, f, mul, sign, out);
+        ILM_LAUNCHED(p);
+        return ILM_OK;
+    }
     if (t.ncell == 0) return ILM_OK;
     k_regularize<<<(t.ncell + 127) / 128, 128, 0, p->stream>>>(t.ncell, t.W * t.W, t.cell_idx, t.cell_off, t.ent,
                                                                t.wR, f, mul, sign, out);
@@ -414,7 +462,16 @@ int launch_normal_interpolate(ilm_plan* p, int mode, const double* u, const doub
 
 // ------------------------------------------------------------------ stencils
 // thread = one x, ROWS consecutive y; grid covers the NX x NY superset.
-constexpr int ST_BX = 128, ST_ROWS = 8;
+// block = ST_BX consecutive x, each thread walks ST_ROWS rows.  Swept under ncu on B200 at 4096^2 (128..1024 x 4..16,
+// profiles/r2_stencil_geometry.txt): 256 x 4 is the best or within noise of it for every sweep; the one-read / two-write
+// sweeps (grad, curl nodes -> edges) stay at 70-75 % of the copy bandwidth for every geometry.
+#ifndef ILM_ST_BX
+#define ILM_ST_BX 256
+#endif
+#ifndef ILM_ST_ROWS
+#define ILM_ST_ROWS 4
+#endif
+constexpr int ST_BX = ILM_ST_BX, ST_ROWS = ILM_ST_ROWS;
 static dim3 st_grid(int NX, int NY) { return dim3((NX + ST_BX - 1) / ST_BX, (NY + ST_ROWS - 1) / ST_ROWS); }
 
 // p[x,y] = -u[x,y] + u[x+1,y] - v[x,y] + v[x,y+1]          (A.3)

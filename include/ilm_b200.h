@@ -32,8 +32,10 @@ typedef struct ilm_plan ilm_plan;
 
 enum ilm_status { ILM_OK = 0, ILM_EINVAL = 1, ILM_ESIZE = 2, ILM_ECUDA = 3, ILM_ENCCL = 4, ILM_ENOMEM = 5 };
 
-/* CartesianGrids DDF types listed at src/cache.jl:305 (Goza is not provided) */
-enum ilm_ddf { ILM_DDF_YANG3 = 0, ILM_DDF_M3 = 1, ILM_DDF_ROMA = 2, ILM_DDF_M4PRIME = 3, ILM_DDF_WITCHHAT = 4 };
+/* CartesianGrids DDF types listed at src/cache.jl:305.  Goza is named so that a caller gets a precise answer:
+ * its kernel is defined only in the un-vendored CartesianGrids source (no formula, value or test of it exists in
+ * ImmersedLayers.jl), so ilm_plan_create returns ILM_EINVAL ("Goza DDF not provided") instead of guessing. */
+enum ilm_ddf { ILM_DDF_YANG3 = 0, ILM_DDF_M3 = 1, ILM_DDF_ROMA = 2, ILM_DDF_M4PRIME = 3, ILM_DDF_WITCHHAT = 4, ILM_DDF_GOZA = 5 };
 /* GridScaling / IndexScaling (src/ImmersedLayers.jl:81, src/cache.jl:305-324) */
 enum ilm_scaling { ILM_GRID_SCALING = 0, ILM_INDEX_SCALING = 1 };
 /* staggered layouts */

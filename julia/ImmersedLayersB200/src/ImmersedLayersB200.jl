@@ -51,6 +51,29 @@ mutable struct B200Cache{N,SCA,BC<:BasicILMCache{N,SCA}}
     base::BC
     plan::Ptr{Cvoid}
     vector::Bool
+    parent::Any       # the cache whose Laplacian a shared plan aliases (ilm_plan_create_shared): finalizers run in
+                      # arbitrary order, so the child keeps its parent reachable for as long as it lives; nothing otherwise
+end
+B200Cache{N,SCA,BC}(base::BC, plan::Ptr{Cvoid}, vector::Bool) where {N,SCA,BC<:BasicILMCache{N,SCA}} =
+    B200Cache{N,SCA,BC}(base, plan, vector, nothing)
+
+# LGF table with at least n x n entries.  CartesianGrids ships LGF_TABLE (1600 x 1600, SURVEY.md fact 7); beyond it the
+# entries come from the two-term far-field expansion (ln r + gamma + ln(8)/2)/2pi - cos(4 theta)/(24 pi r^2), accurate to
+# < 1e-13 for r >= 800 (SURVEY.md section 8c), which is what lets a 4096^2 (or 16384^2) grid be planned at all.
+const DEFAULT_DDF = CartesianGrids.Yang3
+function lgf_table(n::Integer)
+    tbl = CartesianGrids.LGF_TABLE
+    m = size(tbl, 1)
+    n <= m && return tbl
+    G = Matrix{Float64}(undef, n, n)
+    G[1:m, 1:m] .= tbl
+    for j in 1:n, i in 1:n
+        (i <= m && j <= m) && continue
+        x, y = i - 1, j - 1
+        r2 = x^2 + y^2
+        G[i, j] = (log(r2) / 2 + MathConstants.γ + log(8) / 2) / 2π - cos(4 * atan(y, x)) / (24π * r2)
+    end
+    return G
 end
 
 layout(::Nodes{Primal}) = NODES_PRIMAL
@@ -65,7 +88,7 @@ function B200Cache(cache::BasicILMCache{N,SCA}; ddftype=CartesianGrids.Yang3) wh
     NX, NY = size(g); I0 = origin(g); dx = cellsize(g)
     grid = Ref(IlmGrid(NX, NY, dx, I0[1], I0[2]))
     pts, nrm, ds = points(cache), normals(cache), areas(cache)
-    tbl = CartesianGrids.LGF_TABLE
+    tbl = lgf_table(max(NX, NY))                       # ilm_plan_create needs at least max(NX, NY) entries per direction
     factor = SCA == GridScaling ? 1 / dx^2 : 1.0       # src/cache.jl:321-324
     c0 = (MathConstants.γ + log(8) / 2 - log(dx)) / 2π  # far-field constant of L\w (DESIGN.md section 3: unpinned)
     plan = Ref{Ptr{Cvoid}}(C_NULL)
@@ -198,7 +221,8 @@ w_cross_v!(vw::Edges{Primal}, w::Nodes{Dual}, v::Edges{Primal}, c::B200Cache, ex
     B200Cache(region::BasicILMCache, parent::B200Cache; ddftype)
 
 Device plan for a region cache built with the parent's `L` (`AreaRegionCache`, `LineRegionCache`): aliases the
-parent's multipliers and scratch (ilm_plan_create_shared).  The parent must outlive it.
+parent's multipliers and scratch (ilm_plan_create_shared); the child holds a reference to the parent, so the
+parent's finalizer cannot run first.
 """
 function B200Cache(cache::BasicILMCache{N,SCA}, parent::B200Cache; ddftype=CartesianGrids.Yang3) where {N,SCA}
     pts, nrm, ds = points(cache), normals(cache), areas(cache)
@@ -206,7 +230,7 @@ function B200Cache(cache::BasicILMCache{N,SCA}, parent::B200Cache; ddftype=Carte
     check(ccall((:ilm_plan_create_shared, lib), Cint,
         (Ptr{Cvoid}, Cint, PD, PD, PD, PD, PD, Cint, Cint, Ref{Ptr{Cvoid}}),
         parent.plan, N, pts.u, pts.v, nrm.u, nrm.v, ds.data, DDF[ddftype], SCA == GridScaling ? 0 : 1, plan))
-    c = B200Cache{N,SCA,typeof(cache)}(cache, plan[], cache.gdata_cache isa Edges)
+    c = B200Cache{N,SCA,typeof(cache)}(cache, plan[], cache.gdata_cache isa Edges, parent)   # keeps the parent plan alive
     finalizer(x -> ccall((:ilm_plan_destroy, lib), Cvoid, (Ptr{Cvoid},), x.plan), c)
     return c
 end
@@ -242,5 +266,25 @@ masked_curlv_from_curlv_masked!(mw::Nodes{Dual}, w::Nodes{Dual}, dv::VectorData,
 curlv_masked_from_masked_curlv!(w::Nodes{Dual}, mw::Nodes{Dual}, dv::VectorData, c::B200Cache, wcache=nothing) = (_jump(c, 0, 1, dv, mw, w); w)
 masked_divv_from_divv_masked!(md::Nodes{Primal}, d::Nodes{Primal}, dv::VectorData, c::B200Cache, dcache=nothing) = (_jump(c, 1, -1, dv, d, md); md)
 divv_masked_from_masked_divv!(d::Nodes{Primal}, md::Nodes{Primal}, dv::VectorData, c::B200Cache, dcache=nothing) = (_jump(c, 1, 1, dv, md, d); d)
+
+# ---- whole-problem entry point and multi-GPU (include/ilm_b200.h: ilm_dirichlet_poisson, ilm_comm_*, ilm_create_schur_sharded)
+"""
+    dirichlet_solve!(f::Nodes{Primal}, s::ScalarData, fplus::ScalarData, fminus, c::B200Cache)
+
+`solve(prob::DirichletPoissonProblem, sys)` of test/literate/dirichlet.jl:71-107 in one library call; S and its LU
+factors stay on the device.  With a communicator on the plan (`comm_init!`) the Schur columns are sharded.
+"""
+dirichlet_solve!(f::Nodes{Primal}, s::ScalarData, fplus::ScalarData, fminus::Union{ScalarData,Nothing}, c::B200Cache) =
+    (check(ccall((:ilm_dirichlet_poisson, lib), Cint, (Ptr{Cvoid}, PD, PD, PD, PD, PD), c.plan, fplus.data,
+                 fminus === nothing ? C_NULL : fminus.data, f.data, s.data, C_NULL)); (f, s))
+comm_unique_id() = (id = zeros(UInt8, 128); check(ccall((:ilm_comm_unique_id, lib), Cint, (Ptr{UInt8}, Cint), id, 128)); id)
+# `id` from rank 0, distributed by the host program (MPI.Bcast!, a file, ...)
+comm_init!(c::B200Cache, id::Vector{UInt8}, rank::Integer, nranks::Integer) =
+    (check(ccall((:ilm_comm_init, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint, Cint), c.plan, id, 128, rank, nranks)); c)
+comm_destroy!(c::B200Cache) = (check(ccall((:ilm_comm_destroy, lib), Cint, (Ptr{Cvoid},), c.plan)); c)
+function create_schur_sharded(c::B200Cache{N}, which::Integer; scale=1.0, kernel_id=0) where {N}
+    A = Matrix{Float64}(undef, N, N)
+    check(ccall((:ilm_create_schur_sharded, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, PD), c.plan, which, kernel_id, scale, A)); A
+end
 
 end # module

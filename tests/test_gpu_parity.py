@@ -635,3 +635,48 @@ def test_dirichlet_solve_single_call(device):
     assert relerr(f2.array(), fr2) < 1e-10
     assert cache.comm_info() == (0, 1)
     assert relerr(tonp(ilm.create_schur_sharded(cache, "CLinvCT")), oc.create_CLinvCT()) < RTOL
+
+
+def test_goza_ddf_is_named_and_refused():
+    """src/cache.jl:305 lists Goza among the DDF types; its kernel exists only in the un-vendored CartesianGrids, so the
+    library names it and answers ILM_EINVAL rather than guessing a formula."""
+    g = ilm.PhysicalGrid.centered(32)
+    with pytest.raises(ilm.MethodError, match="Goza"):
+        ilm.SurfaceScalarCache(ilm.bodies.circle(0.5, 1.4 * g.dx), g, ddftype="goza")
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_complex_cache(device):
+    """`SurfaceScalarCache(body, g, dtype=ComplexF64)` (src/cache.jl:167,187; test/surface_ops.jl:109-119): the
+    similar_* containers are complex, and the (real-linear) operators act on real and imaginary parts."""
+    g = ilm.PhysicalGrid.centered(64)
+    body = ilm.bodies.circle(1.0, 1.4 * g.dx)
+    G = ilm.lgf.lgf_table(64)
+    cc = ilm.SurfaceScalarCache(body, g, lgf_table=G, dtype=complex, device=device)
+    rc = ilm.SurfaceScalarCache(body, g, lgf_table=G, device=device)
+    for make in (cc.similar_grid, cc.similar_gridcurl, cc.similar_gridgrad, cc.similar_surface):
+        assert make().eltype is complex                       # test/surface_ops.jl:112-116
+    assert rc.similar_grid().eltype is float
+    vc = ilm.SurfaceVectorCache(body, g, lgf_table=G, dtype=complex, device=device)
+    assert vc.similar_grid().eltype is complex and vc.similar_surface().eltype is complex
+    rng = np.random.default_rng(4)
+    fr, fi = rng.standard_normal(cc.N), rng.standard_normal(cc.N)
+    f = cc.similar_surface().set(fr + 1j * fi)
+    s = cc.similar_grid()
+    ilm.regularize(s, f, cc)
+    ilm.inverse_laplacian(s, cc)
+    out = cc.similar_surface()
+    ilm.interpolate(out, s, cc)
+    ref = []
+    for part in (fr, fi):
+        sp = rc.zeros_grid()
+        ilm.regularize(sp, rc.zeros_surface().set(part), rc)
+        ilm.inverse_laplacian(sp, rc)
+        o_ = rc.zeros_surface()
+        ilm.interpolate(o_, sp, rc)
+        ref.append(o_.numpy().copy())
+    assert np.array_equal(out.numpy(), ref[0] + 1j * ref[1])
+    with pytest.raises(ilm.MethodError):
+        ilm.regularize(rc.zeros_grid(), f, cc)                # real and complex containers do not mix
+    with pytest.raises(ilm.MethodError):
+        ilm.convective_derivative(cc.similar_gridgrad(), cc.similar_gridgrad(), cc)
