@@ -112,6 +112,7 @@ SIGNATURES = {
     "ilm_slab_forward": (_i, [_vp, C.POINTER(ilm_slab_info), _i, _dp, _i, _dp, _dp]),
     "ilm_slab_columns": (_i, [_vp, C.POINTER(ilm_slab_info), _i, _dp, _dp]),
     "ilm_slab_inverse": (_i, [_vp, C.POINTER(ilm_slab_info), _dp, _i, _dp, _i, _dp]),
+    "ilm_plan_release_spectrum": (_i, [_vp]),
     "ilm_comm_unique_id": (_i, [_vp, _i]),
     "ilm_comm_init": (_i, [_vp, _vp, _i, _i, _i]),
     "ilm_comm_destroy": (_i, [_vp]),

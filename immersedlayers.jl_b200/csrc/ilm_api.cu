@@ -221,6 +221,7 @@ extern "C" int ilm_plan_create_shared(ilm_plan* parent, int N, const double* x, 
     p->g = parent->g; p->ddf = ddf; p->scaling = scaling; p->c0 = parent->c0; p->lap_factor = parent->lap_factor;
     p->stream = parent->stream; p->device = parent->device; p->nsm = parent->nsm;
     p->shared = true;
+    p->parent = parent->shared && parent->parent ? parent->parent : parent;
     p->Lx = parent->Lx; p->Ly = parent->Ly;
     p->twx = parent->twx; p->twy = parent->twy; p->wl2y = parent->wl2y; p->wl2x = parent->wl2x;
     p->conv_scratch = parent->conv_scratch; p->S = parent->S; p->S2 = parent->S2; p->s_cap = parent->s_cap;
@@ -876,4 +877,17 @@ extern "C" int ilm_dirichlet_poisson(ilm_plan* p, const double* fplus, const dou
     k_negate_add<<<(unsigned)((P + 255) / 256), 256, 0, p->stream>>>(P, nullptr, 0.0, df, fstar);
     ILM_LAUNCHED_API(p);
     return io.finish();
+}
+
+
+// Frees the full-size spectrum buffers (they come back on the next full-grid convolution).  A rank that only runs slab
+// solves on a 16384^2 plan calls this after ilm_plan_create and never holds the 2 x 8.6 GB again.
+extern "C" int ilm_plan_release_spectrum(ilm_plan* p) {
+    ILM_CHECK_PLAN(p);
+    if (p->shared) { set_error("ilm_plan_release_spectrum: the buffers belong to the parent plan"); return ILM_EINVAL; }
+    ILM_CUDA(cudaStreamSynchronize(p->stream));
+    cudaFree(p->S); cudaFree(p->S2);
+    p->S = p->S2 = nullptr;
+    p->tmap_myp = -1;
+    return ILM_OK;
 }

@@ -87,10 +87,14 @@ struct ilm_plan {
     double2* wl2y = nullptr;        // exp(-2 pi i n / (2 Ly)) table for the sparse forward transform
     double2* wl2x = nullptr;        // same for x, only when Lx > 4096 (ilm_conv_big.cuh)
     double2* conv_scratch = nullptr; // per-CTA hand-off lines of the big column pass (Ly > 4096)
-    double2 *S = nullptr, *S2 = nullptr;
-    size_t s_cap = 0;
+    double2 *S = nullptr, *S2 = nullptr;   // full spectrum buffers: allocated on first use (conv_ensure_spectrum), so a plan that
+    size_t s_cap = 0;                      // only runs slab solves never holds them (8.6 GB each at 16384^2)
+    ilm_plan* parent = nullptr;            // shared plans alias the parent's buffers
+    double2 *slab_S = nullptr, *slab_S2 = nullptr;   // slab solve: this rank's x-frequency columns only (1/nranks of the above)
+    size_t slab_cap = 0;
     alignas(64) unsigned char tmap_s2[128] = {};   // CUtensorMap of S2 for the current row count (pass C)
     int tmap_myp = -1;
+    const void* tmap_base = nullptr;
     int skew_ns = 500;              // ILM_CONV_SKEW_NS: start-up skew between the two groups of a CTA
     bool band = true;               // ILM_PROBE_BAND=0 sends the Schur probes through the transform column pass instead
     bool fuse_e = true;             // ILM_PROBE_FUSE_E=0: pass C stores the probed rows and a separate kernel interpolates
@@ -222,7 +226,8 @@ int launch_probe_post_sum(ilm_plan* p, const DevTable& t, int ncol, double coef,
 void conv_free(ilm_plan* p);
 ConvArgs conv_base_args(const ilm_plan* p);      // plan-constant kernel arguments (buffers, twiddle tables)
 int conv_half_len(int n);                       // half padded transform length of an n-cell direction
-int make_s2_tensor_map(ilm_plan* p, int MYp);    // bulk-tensor map of S2 for pass C
+int make_s2_tensor_map(ilm_plan* p, int MYp, const double2* base = nullptr);    // bulk-tensor map of S2 (or `base`) for pass C
+int conv_ensure_spectrum(ilm_plan* p, bool need_s2);
 int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1,
                  const ProbeGather* eg = nullptr);
 extern long long g_dense_launches;

@@ -60,8 +60,9 @@ const double2* conv_twiddles_host(int L, size_t* count) {
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_s2_tensor_map(ilm_plan* p, int MYp) {
-    if (p->tmap_myp == MYp) return ILM_OK;
+int make_s2_tensor_map(ilm_plan* p, int MYp, const double2* base) {
+    if (!base) base = p->S2;
+    if (p->tmap_myp == MYp && p->tmap_base == base) return ILM_OK;
     static encode_tiled_fn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -75,11 +76,12 @@ int make_s2_tensor_map(ilm_plan* p, int MYp) {
     cuuint64_t strides[2] = {64, (cuuint64_t)(MYp >> 1) * 64};             // bytes, dims 1 and 2
     cuuint32_t box[3] = {4, 1, (cuuint32_t)(na < 256 ? na : 256)};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(reinterpret_cast<CUtensorMap*>(p->tmap_s2), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p->S2, dims, strides,
+    CUresult r = encode(reinterpret_cast<CUtensorMap*>(p->tmap_s2), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double2*>(base), dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed"); return ILM_ECUDA; }
     p->tmap_myp = MYp;
+    p->tmap_base = base;
     return ILM_OK;
 }
 
@@ -122,15 +124,26 @@ int conv_setup(ilm_plan* p) {
         ILM_CUDA(cudaMalloc(&p->conv_scratch, (size_t)p->nsm * Lmax * sizeof(double2)));
     }
     ConvGeom g{p->Lx, p->Ly, p->g.NY, (p->g.NY + 1) & ~1};
-    p->s_cap = s_elems(g);
-    ILM_CUDA(cudaMalloc(&p->S, p->s_cap * sizeof(double2)));
-    ILM_CUDA(cudaMalloc(&p->S2, p->s_cap * sizeof(double2)));
+    p->s_cap = s_elems(g);                    // S / S2 themselves: conv_ensure_spectrum, on first use
     ILM_CUDA(cudaStreamSynchronize(p->stream));
+    return ILM_OK;
+}
+
+// the full-size spectrum buffers (2 Lx x MYp complex each), allocated when a full-grid convolution first needs them
+int conv_ensure_spectrum(ilm_plan* p, bool need_s2) {
+    ilm_plan* owner = p->shared && p->parent ? p->parent : p;
+    if (!owner->S) ILM_CUDA(cudaMalloc(&owner->S, owner->s_cap * sizeof(double2)));
+    if (need_s2 && !owner->S2) {
+        ILM_CUDA(cudaMalloc(&owner->S2, owner->s_cap * sizeof(double2)));
+        owner->tmap_myp = -1;
+    }
+    if (owner != p) { p->S = owner->S; p->S2 = owner->S2; }
     return ILM_OK;
 }
 
 void conv_free(ilm_plan* p) {
     cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->wl2y); cudaFree(p->wl2x); cudaFree(p->conv_scratch); cudaFree(p->S); cudaFree(p->S2);
+    cudaFree(p->slab_S); cudaFree(p->slab_S2);
     for (auto& k : p->kernels) { cudaFree(k.ghat); cudaFree(k.gxt); }
     cudaFree(p->lgf_dev); p->lgf_dev = nullptr;
     p->kernels.clear();
@@ -168,6 +181,7 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
         src = dtab;
     }
     // h = eps_i eps_j (G - c0) into scratch field g_a (NX x NY)
+    ILM_TRY(conv_ensure_spectrum(p, false));
     ILM_TRY(launch_lgf_prep(p, src, n, NX, NY, c0, p->g_a));
     ConvArgs a = conv_base_args(p);
     a.g = ConvGeom{p->Lx, p->Ly, NY, (NY + 1) & ~1};
@@ -203,6 +217,7 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
         set_error("unknown convolution kernel id");
         return ILM_EINVAL;
     }
+    ILM_TRY(conv_ensure_spectrum(p, true));
     ConvArgs a = conv_base_args(p);
     int MY = f1.p ? f1.my : 0;
     if (f2.p && f2.my > MY) MY = f2.my;
@@ -233,6 +248,7 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
 
 // per-pass timing for the roofline report (ilm_profile_conv)
 int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo, int rhi, int olo, int ohi, const ProbeGather* eg) {
+    ILM_TRY(conv_ensure_spectrum(p, true));
     ConvArgs a = conv_base_args(p);
     int MY = f1.my > f2.my ? f1.my : f2.my;
     a.g = ConvGeom{p->Lx, p->Ly, MY, (MY + 1) & ~1};

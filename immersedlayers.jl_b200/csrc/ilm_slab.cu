@@ -18,7 +18,14 @@
 //
 // Spectrum layout (ilm_conv.cuh): S[tile column][row pair][2x2 tile]; a tile column (two
 // x-frequency columns) is a contiguous run of 2*MYp complex numbers, and a rank's row range is a
-// contiguous piece of it -- so each (peer, tile column) block is one strided-2D copy.
+// contiguous piece of it.  Two consequences used here:
+//   * with the COMPACT geometry "MYp = this rank's row count" the spectrum of this rank's rows is
+//     [tile column][my row pairs], and the tile columns of peer q are a contiguous block of it: pass A
+//     writes the send buffer of exchange #1 directly and pass C reads the receive buffer of exchange #2
+//     directly (no pack, no unpack, no full-size buffer on either side);
+//   * the column pass needs [my tile columns][all rows]: the only copies left are the unpack of
+//     exchange #1 and the pack of exchange #2 (one strided-2D copy per peer), into / out of buffers that
+//     hold this rank's tile columns only (1/nranks of the full spectrum).
 #include <algorithm>
 
 #include "ilm_internal.h"
@@ -93,11 +100,13 @@ ConvArgs base_args(ilm_plan* p, const ilm_slab_info* s, int kernel_id) {
     return a;
 }
 
-// FieldRef whose row index is the GLOBAL row: the caller's pointer addresses row `row0`
-FieldRef slab_ref(const ilm_plan* p, int layout, double* rows_ptr, int row0) {
+// FieldRef in LOCAL rows: row 0 is the rank's first row; my = how many of the rank's rows exist in this layout
+FieldRef local_ref(const ilm_plan* p, int layout, double* rows_ptr, int row0, int nrows) {
     if (!rows_ptr || layout < 0) return FieldRef{nullptr, 0, 0};
     const LayoutInfo li = layout_info(layout, p->g.NX, p->g.NY);
-    return FieldRef{rows_ptr - (ptrdiff_t)row0 * li.mx, li.mx, li.my};
+    int my = li.my - row0;
+    my = my < 0 ? 0 : (my > nrows ? nrows : my);
+    return FieldRef{rows_ptr, li.mx, my};
 }
 
 int layout_rows(const ilm_plan* p, int layout) { return layout < 0 ? 0 : layout_info(layout, p->g.NX, p->g.NY).my; }
@@ -142,20 +151,17 @@ extern "C" int ilm_slab_forward(ilm_plan* p, const ilm_slab_info* s, int layout1
     if (!is_device_ptr(w1_rows) || !is_device_ptr(sendbuf)) { set_error("ilm_slab_forward: device-resident buffers only"); return ILM_EINVAL; }
     if (!w2_rows) layout2 = -1;
     ILM_TRY(check_info(p, s, layout_rows(p, layout1), layout_rows(p, layout2)));
-    ConvArgs a = base_args(p, s, 0);
-    a.f1 = slab_ref(p, layout1, const_cast<double*>(w1_rows), s->row0);
-    a.f2 = slab_ref(p, layout2, const_cast<double*>(w2_rows), s->row0);
-    a.rlo = s->row0; a.rhi = s->row1;
-    if (s->row1 > s->row0) {
-        ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream, nullptr));
-        p->launches++;
-    }
-    double2* buf = reinterpret_cast<double2*>(sendbuf);
-    for (int r = 0; r < s->nranks; ++r) {
-        const Peer q = peer_of(s, p->g.NX, p->g.NY, r);
-        ILM_TRY(copy_block(p, p->S, s->MYp, q.tc0, q.ntc, s->row0, s->row1 - s->row0, buf, true));
-        buf += (size_t)2 * q.ntc * (s->row1 - s->row0);
-    }
+    // compact geometry: rows are counted from row0, the spectrum of the nrows rows IS the peer-major send buffer
+    const int nrows = s->row1 - s->row0;
+    if (nrows == 0) return ILM_OK;
+    ConvArgs a = conv_base_args(p);
+    a.g = ConvGeom{p->Lx, p->Ly, nrows, nrows};
+    a.f1 = local_ref(p, layout1, const_cast<double*>(w1_rows), s->row0, nrows);
+    a.f2 = local_ref(p, layout2, const_cast<double*>(w2_rows), s->row0, nrows);
+    a.rlo = 0; a.rhi = nrows; a.olo = 0; a.ohi = nrows;
+    a.S = reinterpret_cast<double2*>(sendbuf);
+    ILM_TRY(conv_launcher(p->Lx)(0, a, p->nsm, p->stream, nullptr));
+    p->launches++;
     return ILM_OK;
 }
 
@@ -166,13 +172,25 @@ extern "C" int ilm_slab_columns(ilm_plan* p, const ilm_slab_info* s, int kernel_
     if (kernel_id < 0 || kernel_id >= (int)p->kernels.size()) { set_error("ilm_slab_columns: unknown kernel id"); return ILM_EINVAL; }
     if (s->Lx != p->Lx || s->Ly != p->Ly) { set_error("ilm_slab_columns: slab info of another grid"); return ILM_EINVAL; }
     const int ntc = s->tc1 - s->tc0;
+    // this rank's tile columns only; the kernels index the full layout, so the base pointers are shifted by tc0 columns
+    const size_t need = (size_t)(ntc > 0 ? ntc : 1) * 2 * s->MYp;
+    if (need > p->slab_cap) {
+        cudaFree(p->slab_S); cudaFree(p->slab_S2);
+        p->slab_S = p->slab_S2 = nullptr; p->slab_cap = 0;
+        ILM_CUDA(cudaMalloc(&p->slab_S, need * sizeof(double2)));
+        ILM_CUDA(cudaMalloc(&p->slab_S2, need * sizeof(double2)));
+        p->slab_cap = need;
+    }
+    double2* S = p->slab_S - (ptrdiff_t)s->tc0 * 2 * s->MYp;
+    double2* S2 = p->slab_S2 - (ptrdiff_t)s->tc0 * 2 * s->MYp;
     const double2* in = reinterpret_cast<const double2*>(recvbuf);
     for (int r = 0; r < s->nranks; ++r) {
         const Peer q = peer_of(s, p->g.NX, p->g.NY, r);
-        ILM_TRY(copy_block(p, p->S, s->MYp, s->tc0, ntc, q.row0, q.nrows, const_cast<double2*>(in), false));
+        ILM_TRY(copy_block(p, S, s->MYp, s->tc0, ntc, q.row0, q.nrows, const_cast<double2*>(in), false));
         in += (size_t)2 * ntc * q.nrows;
     }
     ConvArgs a = base_args(p, s, kernel_id);
+    a.S = S; a.S2 = S2;
     a.wlo = s->wlo; a.whi = s->whi;
     if (s->whi > s->wlo) {
         ILM_TRY(conv_launcher(p->Ly)(1, a, p->nsm, p->stream, nullptr));
@@ -181,7 +199,7 @@ extern "C" int ilm_slab_columns(ilm_plan* p, const ilm_slab_info* s, int kernel_
     double2* out = reinterpret_cast<double2*>(sendbuf);
     for (int r = 0; r < s->nranks; ++r) {
         const Peer q = peer_of(s, p->g.NX, p->g.NY, r);
-        ILM_TRY(copy_block(p, p->S2, s->MYp, s->tc0, ntc, q.row0, q.nrows, out, true));
+        ILM_TRY(copy_block(p, S2, s->MYp, s->tc0, ntc, q.row0, q.nrows, out, true));
         out += (size_t)2 * ntc * q.nrows;
     }
     return ILM_OK;
@@ -195,19 +213,17 @@ extern "C" int ilm_slab_inverse(ilm_plan* p, const ilm_slab_info* s, const doubl
     if (!is_device_ptr(w1_rows) || !is_device_ptr(recvbuf)) { set_error("ilm_slab_inverse: device-resident buffers only"); return ILM_EINVAL; }
     if (!w2_rows) layout2 = -1;
     ILM_TRY(check_info(p, s, layout_rows(p, layout1), layout_rows(p, layout2)));
-    const double2* in = reinterpret_cast<const double2*>(recvbuf);
+    // the receive buffer of exchange #2 is [tile column][my row pairs]: the compact spectrum that pass C inverts
     const int nrows = s->row1 - s->row0;
-    for (int r = 0; r < s->nranks; ++r) {
-        const Peer q = peer_of(s, p->g.NX, p->g.NY, r);
-        ILM_TRY(copy_block(p, p->S2, s->MYp, q.tc0, q.ntc, s->row0, nrows, const_cast<double2*>(in), false));
-        in += (size_t)2 * q.ntc * nrows;
-    }
     if (nrows == 0) return ILM_OK;
-    ConvArgs a = base_args(p, s, 0);
-    a.f1 = slab_ref(p, layout1, w1_rows, s->row0);
-    a.f2 = slab_ref(p, layout2, w2_rows, s->row0);
-    a.olo = s->row0; a.ohi = s->row1;
-    if (p->Lx >= 512 && p->Lx <= 4096) ILM_TRY(make_s2_tensor_map(p, s->MYp));
+    ConvArgs a = conv_base_args(p);
+    a.g = ConvGeom{p->Lx, p->Ly, nrows, nrows};
+    a.Ghat = p->kernels[0].ghat;
+    a.f1 = local_ref(p, layout1, w1_rows, s->row0, nrows);
+    a.f2 = local_ref(p, layout2, w2_rows, s->row0, nrows);
+    a.rlo = 0; a.rhi = nrows; a.olo = 0; a.ohi = nrows;
+    a.S2 = const_cast<double2*>(reinterpret_cast<const double2*>(recvbuf));
+    if (p->Lx >= 512 && p->Lx <= 4096) ILM_TRY(make_s2_tensor_map(p, nrows, a.S2));
     ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, p->stream, p->tmap_s2));
     p->launches++;
     return ILM_OK;

@@ -7,6 +7,7 @@
 // cell, then by point index) that makes regularization an atomics-free gather.
 #include <algorithm>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "ilm_ddf.h"
@@ -100,35 +101,58 @@ int build_tables(ilm_plan* p) {
         }
     }
     ILM_CUDA(cudaStreamSynchronize(p->stream));
-    // phase 2: gather lists (cell, k, slot) for every in-range window entry, sorted by cell then k
-    std::vector<int> cell, id, cell_tmp, id_tmp, cell_idx, cell_off;
-    for (int layout = 0; layout < 4; ++layout) {
-        DevTable& t = p->tab[layout];
+    // phase 2: gather lists (cell, k, slot) for every in-range window entry, sorted by cell then k.  Pure host work per
+    // layout (entry generation, radix sort, run detection): the four layouts are built by four host threads, the uploads
+    // follow in layout order.
+    struct HostLists { std::vector<int> id, cell_idx, cell_off, rptr, rent; };
+    HostLists lists[4];
+    auto build_layout = [&](int layout) {
+        HostLists& h = lists[layout];
         const LayoutInfo li = layout_info(layout, p->g.NX, p->g.NY);
         const std::vector<int>& xi = hi[layout];
         const std::vector<int>& yj = hj[layout];
-        t.h_j0 = yj;
-        cell.clear();
-        id.clear();
+        std::vector<int> cell, cell_tmp, id_tmp;
         cell.reserve((size_t)N * W2);
-        id.reserve((size_t)N * W2);
+        h.id.reserve((size_t)N * W2);
         for (int k = 0; k < N; ++k)
             for (int b = 0; b < W; ++b)
                 for (int a = 0; a < W; ++a) {
                     const int i = xi[k] + a, j = yj[k] + b;
-                    if (i >= 0 && i < li.mx && j >= 0 && j < li.my) { cell.push_back(i + li.mx * j); id.push_back(k * W2 + b * W + a); }
+                    if (i >= 0 && i < li.mx && j >= 0 && j < li.my) { cell.push_back(i + li.mx * j); h.id.push_back(k * W2 + b * W + a); }
                 }
-        sort_by_cell(cell, id, cell_tmp, id_tmp);
-        cell_idx.clear();
-        cell_off.clear();
+        sort_by_cell(cell, h.id, cell_tmp, id_tmp);
         for (size_t q = 0; q < cell.size(); ++q)
             if (q == 0 || cell[q] != cell[q - 1]) {
-                cell_idx.push_back(cell[q]);
-                cell_off.push_back((int)q);
+                h.cell_idx.push_back(cell[q]);
+                h.cell_off.push_back((int)q);
             }
-        cell_off.push_back((int)cell.size());
-        t.ncell = (int)cell_idx.size();
-        t.nent = (int)cell.size();
+        h.cell_off.push_back((int)cell.size());
+        if (layout == ILM_NODES_PRIMAL) {
+            // row buckets of the window rows (k*W + b sorted by grid row, then point) for the fused interpolation
+            // of the Schur probes in pass C (ConvArgs::eg)
+            h.rptr.assign((size_t)li.my + 1, 0);
+            for (int k = 0; k < N; ++k)
+                for (int b = 0; b < W; ++b) { const int j = yj[k] + b; if (j >= 0 && j < li.my) ++h.rptr[j + 1]; }
+            for (int j = 0; j < li.my; ++j) h.rptr[j + 1] += h.rptr[j];
+            h.rent.resize((size_t)h.rptr[li.my]);
+            std::vector<int> fill(h.rptr.begin(), h.rptr.end() - 1);
+            for (int k = 0; k < N; ++k)
+                for (int b = 0; b < W; ++b) { const int j = yj[k] + b; if (j >= 0 && j < li.my) h.rent[fill[j]++] = k * W + b; }
+        }
+    };
+    {
+        std::thread workers[3];
+        for (int layout = 1; layout < 4; ++layout) workers[layout - 1] = std::thread(build_layout, layout);
+        build_layout(0);
+        for (auto& w : workers) w.join();
+    }
+    for (int layout = 0; layout < 4; ++layout) {
+        DevTable& t = p->tab[layout];
+        HostLists& h = lists[layout];
+        const LayoutInfo li = layout_info(layout, p->g.NX, p->g.NY);
+        t.h_j0 = hj[layout];
+        t.ncell = (int)h.cell_idx.size();
+        t.nent = (int)h.id.size();
         if ((size_t)t.ncell + 1 > t.cap_cells || !t.cell_idx) {
             cudaFree(t.cell_idx); cudaFree(t.cell_off); cudaFree(t.rowsum);
             t.cell_idx = t.cell_off = nullptr; t.rowsum = nullptr;
@@ -145,22 +169,12 @@ int build_tables(ilm_plan* p) {
             ILM_CUDA(cudaMalloc(&t.ent, cap * sizeof(int)));
             t.cap_ents = cap;
         }
-        // pageable sources: cudaMemcpyAsync stages them before it returns, so the vectors may be reused at once
-        if (t.ncell) ILM_CUDA(cudaMemcpyAsync(t.cell_idx, cell_idx.data(), cell_idx.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-        ILM_CUDA(cudaMemcpyAsync(t.cell_off, cell_off.data(), cell_off.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-        if (t.nent) ILM_CUDA(cudaMemcpyAsync(t.ent, id.data(), id.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-        if (layout == ILM_NODES_PRIMAL) ILM_TRY(launch_filter_rowsum(p, t));
+        // pageable sources: the vectors stay alive until the synchronisation below
+        if (t.ncell) ILM_CUDA(cudaMemcpyAsync(t.cell_idx, h.cell_idx.data(), h.cell_idx.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        ILM_CUDA(cudaMemcpyAsync(t.cell_off, h.cell_off.data(), h.cell_off.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        if (t.nent) ILM_CUDA(cudaMemcpyAsync(t.ent, h.id.data(), h.id.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         if (layout == ILM_NODES_PRIMAL) {
-            // row buckets of the window rows (k*W + b sorted by grid row, then point) for the fused interpolation
-            // of the Schur probes in pass C (ConvArgs::eg)
-            std::vector<int> rptr((size_t)li.my + 1, 0), rent;
-            for (int k = 0; k < N; ++k)
-                for (int b = 0; b < W; ++b) { const int j = yj[k] + b; if (j >= 0 && j < li.my) ++rptr[j + 1]; }
-            for (int j = 0; j < li.my; ++j) rptr[j + 1] += rptr[j];
-            rent.resize((size_t)rptr[li.my]);
-            std::vector<int> fill(rptr.begin(), rptr.end() - 1);
-            for (int k = 0; k < N; ++k)
-                for (int b = 0; b < W; ++b) { const int j = yj[k] + b; if (j >= 0 && j < li.my) rent[fill[j]++] = k * W + b; }
+            ILM_TRY(launch_filter_rowsum(p, t));
             if ((size_t)li.my + 1 > t.cap_rows || !t.row_ptr) {
                 cudaFree(t.row_ptr); t.row_ptr = nullptr;
                 ILM_CUDA(cudaMalloc(&t.row_ptr, ((size_t)li.my + 1) * sizeof(int)));
@@ -173,9 +187,8 @@ int build_tables(ilm_plan* p) {
                 ILM_CUDA(cudaMalloc(&t.part, cap * sizeof(double2)));
                 t.cap_rowent = cap;
             }
-            ILM_CUDA(cudaMemcpyAsync(t.row_ptr, rptr.data(), rptr.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-            if (!rent.empty()) ILM_CUDA(cudaMemcpyAsync(t.row_ent, rent.data(), rent.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-            ILM_CUDA(cudaStreamSynchronize(p->stream));          // rptr / rent leave scope
+            ILM_CUDA(cudaMemcpyAsync(t.row_ptr, h.rptr.data(), h.rptr.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+            if (!h.rent.empty()) ILM_CUDA(cudaMemcpyAsync(t.row_ent, h.rent.data(), h.rent.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         }
     }
     ILM_CUDA(cudaStreamSynchronize(p->stream));

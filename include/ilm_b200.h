@@ -94,6 +94,10 @@ int ilm_plan_create_shared(ilm_plan* parent, int N, const double* x, const doubl
 int ilm_plan_update_points(ilm_plan* plan, int N, const double* x, const double* y, const double* nx,
                            const double* ny, const double* ds);
 void ilm_plan_destroy(ilm_plan* plan);
+/* The two full-size spectrum buffers of the convolution (2 Lx x NY complex each: 537 MB at 4096^2, 8.6 GB at 16384^2) are
+ * allocated on the first full-grid convolution; this frees them again (e.g. after plan creation on a rank that only
+ * runs slab solves, which keep 1/nranks of them). */
+int ilm_plan_release_spectrum(ilm_plan* plan);
 int ilm_plan_sync(ilm_plan* plan);
 const char* ilm_last_error(void);
 int ilm_plan_npoints(const ilm_plan* plan);

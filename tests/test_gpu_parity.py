@@ -680,3 +680,25 @@ def test_complex_cache(device):
         ilm.regularize(rc.zeros_grid(), f, cc)                # real and complex containers do not mix
     with pytest.raises(ilm.MethodError):
         ilm.convective_derivative(cc.similar_gridgrad(), cc.similar_gridgrad(), cc)
+
+
+def test_far_field_constant_is_the_callers_parameter():
+    """c0 of `L\\w` is not pinned by any reference test: it is an explicit argument of ilm_plan_create and
+    the library uses exactly the caller's value -- two plans that differ only in c0 differ by -dc0 sum(w) / factor in
+    L^-1 w, and by the matching rank-one term -dc0/factor (E 1)(1^T R) in S = -E L^-1 R."""
+    g = ilm.PhysicalGrid.centered(64)
+    body = ilm.bodies.circle(1.0, 1.4 * g.dx)
+    G = ilm.lgf.lgf_table(64)
+    ca = ilm.SurfaceScalarCache(body, g, lgf_table=G)                     # default: (gamma + ln(8)/2 - ln dx) / 2 pi
+    cb = ilm.SurfaceScalarCache(body, g, lgf_table=G, c0=0.25)
+    assert abs(ca.c0 - ilm.lgf.lgf_c0(g.dx)) < 1e-15 and cb.c0 == 0.25
+    w = np.random.default_rng(9).standard_normal(g.layout_shape(L.NODES_PRIMAL))
+    wa, wb = ca.zeros_grid().set(w), cb.zeros_grid().set(w)
+    ilm.inverse_laplacian(wa, ca)
+    ilm.inverse_laplacian(wb, cb)
+    shift = -(ca.c0 - cb.c0) * w.sum() / ca.lap_factor
+    assert np.abs((wa.array() - wb.array()) - shift).max() < 1e-12 * max(np.abs(wa.array()).max(), abs(shift))
+    Sa, Sb = ilm.create_RTLinvR(ca), ilm.create_RTLinvR(cb)
+    _, wR, wE = ca.table(L.NODES_PRIMAL)
+    rank1 = (ca.c0 - cb.c0) / ca.lap_factor * np.outer(wE.sum(axis=(1, 2)), wR.sum(axis=(1, 2)))
+    assert np.abs((Sa - Sb) - rank1).max() < 1e-12 * np.abs(Sa).max()

@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--in-library", action="store_true", help="exchanges by ilm_slab_solve (grouped ncclSend/ncclRecv inside the library)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
@@ -30,11 +31,20 @@ def main():
     g = ilm.PhysicalGrid.centered(a.grid)
     cache = ilm.SurfaceScalarCache(ilm.bodies.circle(1.0, 1.4 * g.dx), g, device=True)
     slab = shard.SlabLaplacian(cache, L.NODES_PRIMAL)
+    if a.in_library:
+        cache.comm_init()
+    # a slab-only rank does not need the full-size spectrum buffers of the plan: release them and look at the footprint
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    L.check(cache._lib.ilm_plan_release_spectrum(cache._plan))
+    freed_gb = (torch.cuda.mem_get_info()[0] - free0) / 1e9
     shape = g.layout_shape(L.NODES_PRIMAL)
     w = np.random.default_rng(0).standard_normal(shape)
     mine = slab.scatter(w)
     keep = mine.clone()
-    slab.inverse_laplacian(mine)
+    slab.inverse_laplacian(mine, in_library=a.in_library)
+    torch.cuda.synchronize()
+    slab_only_gb = (free0 + int(freed_gb * 1e9) - torch.cuda.mem_get_info()[0]) / 1e9     # what the slab solve allocated
     full = ilm.Nodes(ilm.Primal, g, device=True).set(w)
     ilm.inverse_laplacian(full, cache)
     r0, r1 = slab.rows(L.NODES_PRIMAL)
@@ -43,12 +53,12 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
         mine.copy_(keep)
-        slab.inverse_laplacian(mine)
+        slab.inverse_laplacian(mine, in_library=a.in_library)
     dist.barrier()
     torch.cuda.synchronize()
     e0.record()
     for _ in range(a.reps):
-        slab.inverse_laplacian(mine)
+        slab.inverse_laplacian(mine, in_library=a.in_library)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / a.reps], device=mine.device)
@@ -66,7 +76,8 @@ def main():
     if rank == 0:
         print(json.dumps({"what": "slab-decomposed inverse Laplacian, one real field", "grid": a.grid, "n_gpus": world,
                           "ms_per_solve_slab": float(ms.item()), "ms_per_solve_single_gpu": single,
-                          "bit_identical_to_single_gpu": bool(ok.item() == 1.0),
+                          "bit_identical_to_single_gpu": bool(ok.item() == 1.0), "exchange": "in-library NCCL" if a.in_library else "torch all_to_all_single",
+                          "full_spectrum_buffers_released_GB": freed_gb, "slab_buffers_allocated_GB": slab_only_gb,
                           "exchange_bytes_per_rank_per_solve": 2 * 8 * sum(slab.counts[0][0])}))
     dist.destroy_process_group()
 
