@@ -310,9 +310,10 @@ def main():
               for i, (k, b) in enumerate(bytes_pass.items())}
     conv_ms = sum(float(msp[i]) for i in range(3))
     # the launches the Schur build issues (N of the N + 2 solves of a step): the right-hand side R e_c is a W x W
-    # patch.  Pass A transforms its <= 8 rows, the band pass (ilm_band.cu) forms the y-convolution by direct
-    # summation with the x-transformed kernel rows, pass C inverts the rows under the interpolation windows and
-    # interpolates them on the fly.
+    # patch.  The band pass (ilm_band.cu) sums the x-spectrum of its <= 8 rows from the DDF windows and forms the
+    # y-convolution by direct summation with the x-transformed kernel rows, pass C inverts the rows under the
+    # interpolation windows and interpolates them on the fly; one post-sum launch per 32 pairs.
+    # (ILM_PROBE_PATCH=0: pre-operator on the grid + pass A on the patch rows, as in the first round-2 builds.)
     msq = (L.C.c_double * 3)()
     L.check(lib.ilm_profile_conv_probe(cache._plan, N // 3, 20, L.C.byref(msq)))
     r0, r1 = L.C.c_int(), L.C.c_int()
@@ -320,18 +321,20 @@ def main():
     rows_out = r1.value - r0.value
     nrows_in = 8
     W = 5
+    patch_mode = float(msq[0]) == 0.0      # the band pass forms the x-spectrum of the DDF windows itself: no pass A
     kernels = {
-        "k_passD (band pass: Y_n = sum_r x_r Gx(|n-r|), row-major S2 out)": {
+        "k_passD (band pass: Y_n = sum_r x_r Gx(|n-r|), row-major S2 out" + ("; x_r summed from the DDF windows)" if patch_mode else ")"): {
             "ms": float(msq[1]),
-            "bytes": rows_out * 2 * Lx * 16 + (rows_out + nrows_in) * (Lx + 1) * 8 + nrows_in * 2 * Lx * 16,
+            "bytes": rows_out * 2 * Lx * 16 + (rows_out + nrows_in) * (Lx + 1) * 8 + (0 if patch_mode else nrows_in * 2 * Lx * 16),
             # dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture at 4096^2 (profiles/)
             "traffic": NCU_TRAFFIC.get("k_passD") if args.grid == 4096 else None},
         f"ilm_passC_L{Lx} (probe mode: inverse FFT_x of the window rows + fused interpolation)": {
             "ms": float(msq[2]), "bytes": rows_out * 2 * Lx * 16 + N * W * (16 + 8 * W + 4),
             "traffic": NCU_TRAFFIC.get("passC_probe") if args.grid == 4096 else None},
-        f"ilm_passA_L{Lx} (probe mode: forward FFT_x of the patch rows)": {
-            "ms": float(msq[0]), "bytes": nrows_in * ((g.NX - 1) * 16 + 2 * Lx * 16), "traffic": None},
     }
+    if not patch_mode:
+        kernels[f"ilm_passA_L{Lx} (probe mode: forward FFT_x of the patch rows)"] = {
+            "ms": float(msq[0]), "bytes": nrows_in * ((g.NX - 1) * 16 + 2 * Lx * 16), "traffic": None}
     for k in kernels.values():
         k["GBps"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9
         k["frac"] = k["GBps"] / peak

@@ -58,7 +58,7 @@ __device__ __forceinline__ void st_stream(double2* ptr, double re, double im, un
 template <int NR, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_passD(ConvGeom g, const double2* __restrict__ S, double2* __restrict__ S2,
                                                const double* __restrict__ gxt, int ldc, int dmax, int rlo, int nrows,
-                                               int olo, int ohi, int chunk) {
+                                               int olo, int ohi, int chunk, PatchSrc ps) {
     const int t = blockIdx.x * 256 + threadIdx.x;            // x-frequency slot
     if (t >= 2 * g.Lx) return;
     const int px = t / g.Lx, m = t - px * g.Lx;
@@ -69,8 +69,40 @@ __global__ void __launch_bounds__(256, MINB) k_passD(ConvGeom g, const double2* 
     const size_t base = s_index(g, px, m, 0);
     auto sidx = [&](int row) { return base + ((size_t)(row >> 1) << 2) + (size_t)((row & 1) << 1); };
     double2 x[NR];
+    if (ps.wR) {
+        // patch mode: x_r(kx) = sum_q i^q w^{kx i0_q} sum_a wR_q[r - (j0_q - rlo)][a] w^{kx a},  w = exp(-2 pi i / PX):
+        // the x-spectrum of the W x W windows summed directly (what pass A computes from the grid rows)
 #pragma unroll
-    for (int r = 0; r < NR; ++r) x[r] = r < nrows ? S[sidx(rlo + r)] : cmk(0.0, 0.0);
+        for (int r = 0; r < NR; ++r) x[r] = cmk(0.0, 0.0);
+        const int kx = 2 * m + px;
+        const unsigned mask = (unsigned)(2 * g.Lx - 1);
+        const double2 gw = ps.wl2x[kx];
+        for (int q = 0; q < ps.ncol; ++q) {
+            const int col = ps.col0 + q;
+            const int ci = ps.i0[col], cj = ps.j0[col];
+            const double* w = ps.wR + (size_t)col * ps.W * ps.W;
+            double2 pw = ps.wl2x[(unsigned)(kx * ci) & mask];          // w^{kx (i0 + a)}, a = 0
+            if (q) pw = cmk(-pw.y, pw.x);                              // second column rides the imaginary part
+            for (int a = 0; a < ps.W; ++a) {
+                const int i = ci + a;
+                if (i >= 0 && i < ps.mx) {
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) {
+                        const int b = rlo + r - cj;
+                        if (r < nrows && b >= 0 && b < ps.W) {
+                            const double wv = w[b * ps.W + a];
+                            x[r].x = fma(wv, pw.x, x[r].x);
+                            x[r].y = fma(wv, pw.y, x[r].y);
+                        }
+                    }
+                }
+                pw = cmul(pw, gw);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) x[r] = r < nrows ? S[sidx(rlo + r)] : cmk(0.0, 0.0);
+    }
     const double* gc = gxt + ghat_col(g, px, m);
     auto gload = [&](int e) {                                // multiplier of row distance |e| (clamped: rows past the
         int d = e < 0 ? -e : e;                              // run are computed but never stored)
@@ -138,7 +170,8 @@ int conv_build_gxt(ilm_plan* p, const ConvArgs& a, ConvKernel& k, double factor)
 int conv_band_max_rows() { return 16; }
 
 // S (rows [rlo, rhi) valid) -> S2 rows [olo, ohi)
-int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k) {
+int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k, const PatchSrc* psrc) {
+    const PatchSrc ps = psrc ? *psrc : PatchSrc{};
     const int nrows = a.rhi - a.rlo;
     const int nout = a.ohi - a.olo;
     if (nrows < 1 || nrows > conv_band_max_rows() || nout < 1) { set_error("conv_launch_band: bad row range"); return ILM_EINVAL; }
@@ -151,7 +184,7 @@ int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k) {
     nchunks = (nout + chunk - 1) / chunk;
     const dim3 grid(gx, nchunks);
     const int dmax = k.gxt_rows - 1;
-#define ILM_BAND(NR, MINB) k_passD<NR, MINB><<<grid, 256, 0, p->stream>>>(a.g, a.S, a.S2, k.gxt, k.gxt_ld, dmax, a.rlo, nrows, a.olo, a.ohi, chunk)
+#define ILM_BAND(NR, MINB) k_passD<NR, MINB><<<grid, 256, 0, p->stream>>>(a.g, a.S, a.S2, k.gxt, k.gxt_ld, dmax, a.rlo, nrows, a.olo, a.ohi, chunk, ps)
     static const int minb = getenv("ILM_BAND_MINB") ? atoi(getenv("ILM_BAND_MINB")) : 3;
     if (nrows <= 6) { if (minb >= 3) ILM_BAND(6, 3); else ILM_BAND(6, 2); }
     else if (nrows <= 8) { if (minb >= 3) ILM_BAND(8, 3); else ILM_BAND(8, 2); }

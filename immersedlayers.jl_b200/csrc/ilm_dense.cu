@@ -470,7 +470,9 @@ __global__ void __launch_bounds__(PR_THREADS) k_lu_panel_rot(int n, int k0, int 
 
 static int launch_panel_regs(int n, int k0, int nb, double* A, int* ipiv, cudaStream_t st) {
     const int rows = n - k0;
-    const int C = rows <= 8 * PR_THREADS ? 8 : 16;
+    int C = rows <= 8 * PR_THREADS ? 8 : 16;
+    static const int adapt = getenv("ILM_LU_PANEL_ADAPT") ? atoi(getenv("ILM_LU_PANEL_ADAPT")) : 0;   // smallest cluster that holds the rows
+    if (adapt > 0) { C = adapt; while (C * PR_THREADS < rows) C *= 2; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C);
     cfg.blockDim = dim3(PR_THREADS);

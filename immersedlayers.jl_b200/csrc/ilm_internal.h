@@ -55,9 +55,24 @@ struct DevTable {
     // row buckets of the window rows (primal table only): pass C of the Schur probes interpolates on the fly
     int* row_ptr = nullptr;     // my + 1
     int* row_ent = nullptr;     // k*W + b, sorted by row then k
-    double2* part = nullptr;    // N*W row sums of the current column pair
+    double2* part = nullptr;    // PART_BATCH x (N*W) row sums: one slice per column pair in flight (the post sum of a
+                                // Schur build runs once per PART_BATCH pairs, not once per pair)
+    size_t part_stride = 0;     // complex entries per slice
     size_t cap_rows = 0, cap_rowent = 0;
     size_t cap_pts = 0, cap_cells = 0, cap_ents = 0;   // allocated capacities (a moving body refreshes the tables every step)
+};
+
+constexpr int PART_BATCH = 32;
+
+// Right-hand side of a create_RTLinvR probe given as DDF patches instead of grid rows: column q of the pair is the
+// W x W window wR[col0 + q] placed at (i0, j0), clipped to the mx x my field.  The band pass forms the x-spectrum of
+// the patch rows itself (W terms per entry), so neither the pre-operator nor pass A is launched.
+struct PatchSrc {
+    const double* wR = nullptr;     // null = read the x-spectrum rows from S (pass A ran)
+    const int* i0 = nullptr;
+    const int* j0 = nullptr;
+    const double2* wl2x = nullptr;  // exp(-2 pi i n / (2 Lx)), n < 2 Lx
+    int W = 0, mx = 0, my = 0, col0 = 0, ncol = 0;
 };
 
 struct ConvKernel {     // one multiplier (LGF inverse, integrating factor, ...)
@@ -85,7 +100,7 @@ struct ilm_plan {
     int Lx = 0, Ly = 0;
     double2 *twx = nullptr, *twy = nullptr;
     double2* wl2y = nullptr;        // exp(-2 pi i n / (2 Ly)) table for the sparse forward transform
-    double2* wl2x = nullptr;        // same for x, only when Lx > 4096 (ilm_conv_big.cuh)
+    double2* wl2x = nullptr;        // same for x (ilm_conv_big.cuh; patch mode of the band pass)
     double2* conv_scratch = nullptr; // per-CTA hand-off lines of the big column pass (Ly > 4096)
     double2 *S = nullptr, *S2 = nullptr;   // full spectrum buffers: allocated on first use (conv_ensure_spectrum), so a plan that
     size_t s_cap = 0;                      // only runs slab solves never holds them (8.6 GB each at 16384^2)
@@ -97,6 +112,7 @@ struct ilm_plan {
     const void* tmap_base = nullptr;
     int skew_ns = 500;              // ILM_CONV_SKEW_NS: start-up skew between the two groups of a CTA
     bool band = true;               // ILM_PROBE_BAND=0 sends the Schur probes through the transform column pass instead
+    bool patch = true;              // ILM_PROBE_PATCH=0: create_RTLinvR probes write R e_c to the grid and run pass A (round-2 first form)
     bool fuse_e = true;             // ILM_PROBE_FUSE_E=0: pass C stores the probed rows and a separate kernel interpolates
     std::vector<ilm::ConvKernel> kernels;
     double* lgf_dev = nullptr;      // device copy of the LGF table (ld = lgf_ld), kept for the direct Schur form
@@ -229,14 +245,17 @@ int conv_half_len(int n);                       // half padded transform length 
 int make_s2_tensor_map(ilm_plan* p, int MYp, const double2* base = nullptr);    // bulk-tensor map of S2 (or `base`) for pass C
 int conv_ensure_spectrum(ilm_plan* p, bool need_s2);
 int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1,
-                 const ProbeGather* eg = nullptr);
+                 const ProbeGather* eg = nullptr, const PatchSrc* ps = nullptr);
 extern long long g_dense_launches;
 // per-length launchers, which = 0: pass A, 1: pass B, 2: pass C, 3: pass G
 typedef int (*conv_launch_fn)(int which, const ConvArgs& a, int nsm, cudaStream_t st, const void* tmap);
 conv_launch_fn conv_launcher(int L);
 // band pass (ilm_band.cu): the column step for right-hand sides with <= conv_band_max_rows() non-zero rows
 int conv_build_gxt(ilm_plan* p, const ConvArgs& a, ConvKernel& k, double factor);
-int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k);
+int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k, const PatchSrc* ps = nullptr);
+// create_RTLinvR probe without pre-operator and pass A: band pass in patch mode, then pass C with the fused interpolation
+int conv_apply_patch(ilm_plan* p, int kernel_id, const PatchSrc& ps, int MY, int rlo, int rhi, int olo, int ohi, const ProbeGather& eg);
+int launch_probe_post_sum_batch(ilm_plan* p, const DevTable& t, int npairs, int ncols, double coef, double* dA0);
 int conv_band_max_rows();
 const double2* conv_twiddles_host(int L, size_t* count);
 

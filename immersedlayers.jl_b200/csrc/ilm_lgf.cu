@@ -96,6 +96,7 @@ int conv_setup(ilm_plan* p) {
     if (const char* e = getenv("ILM_CONV_SKEW_NS")) p->skew_ns = atoi(e);
     if (const char* e = getenv("ILM_PROBE_BAND")) p->band = atoi(e) != 0;
     if (const char* e = getenv("ILM_PROBE_FUSE_E")) p->fuse_e = atoi(e) != 0;
+    if (const char* e = getenv("ILM_PROBE_PATCH")) p->patch = atoi(e) != 0;
     p->Lx = conv_half_len(p->g.NX);
     p->Ly = conv_half_len(p->g.NY);
     if (p->Lx > 16384 || p->Ly > 16384) {
@@ -118,7 +119,7 @@ int conv_setup(ilm_plan* p) {
         return ILM_OK;
     };
     ILM_TRY(upload_wl2(p->Ly, &p->wl2y));
-    if (p->Lx > 4096) ILM_TRY(upload_wl2(p->Lx, &p->wl2x));
+    ILM_TRY(upload_wl2(p->Lx, &p->wl2x));
     if (p->Ly > 4096 || p->Lx > 4096) {     // hand-off lines of the cluster passes: 2L complex per cluster, <= nsm/2 clusters
         const size_t Lmax = (size_t)(p->Lx > p->Ly ? p->Lx : p->Ly);
         ILM_CUDA(cudaMalloc(&p->conv_scratch, (size_t)p->nsm * Lmax * sizeof(double2)));
@@ -246,8 +247,32 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
     return ILM_OK;
 }
 
+// create_RTLinvR probe from the DDF patches: band pass in patch mode (S is not touched), pass C with the fused interpolation
+int conv_apply_patch(ilm_plan* p, int kernel_id, const PatchSrc& ps, int MY, int rlo, int rhi, int olo, int ohi, const ProbeGather& eg) {
+    if (!conv_band_ok(p, kernel_id, rhi - rlo) || !eg.part || !ps.wR || p->Lx > 4096) { set_error("conv_apply_patch: needs the band pass and the fused interpolation"); return ILM_EINVAL; }
+    ILM_TRY(conv_ensure_spectrum(p, true));
+    ConvArgs a = conv_base_args(p);
+    a.g = ConvGeom{p->Lx, p->Ly, MY, (MY + 1) & ~1};
+    a.f1 = FieldRef{nullptr, ps.mx, ps.my};
+    a.f2 = FieldRef{nullptr, ps.mx, ps.my};
+    a.rlo = rlo; a.rhi = rhi;
+    a.olo = olo < 0 ? 0 : (olo & ~1);
+    a.ohi = (ohi < 0 || ohi > a.g.MYp) ? a.g.MYp : ohi;
+    if (a.ohi <= a.olo) { a.olo = 0; a.ohi = a.g.MYp < 2 ? a.g.MYp : 2; }
+    const ConvKernel& k = p->kernels[kernel_id];
+    a.Ghat = k.ghat;
+    a.eg = eg;
+    a.s2_rowmajor = 1;
+    if (use_tma(p)) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
+    ILM_TRY(conv_launch_band(p, a, k, &ps));
+    ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, p->stream, p->tmap_s2));
+    p->launches += 2;
+    return ILM_OK;
+}
+
 // per-pass timing for the roofline report (ilm_profile_conv)
-int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo, int rhi, int olo, int ohi, const ProbeGather* eg) {
+int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo, int rhi, int olo, int ohi, const ProbeGather* eg,
+                 const PatchSrc* ps) {
     ILM_TRY(conv_ensure_spectrum(p, true));
     ConvArgs a = conv_base_args(p);
     int MY = f1.my > f2.my ? f1.my : f2.my;
@@ -270,7 +295,9 @@ int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], 
     for (int which = 0; which < 3; ++which) {
         const ConvKernel& k = p->kernels[0];
         const bool band = which == 1 && band_path;
-        auto launch = [&]() { return band ? conv_launch_band(p, a, k) : conv_launcher(Ls[which])(which, a, p->nsm, p->stream, p->tmap_s2); };
+        const bool patch = band_path && eg && ps && p->patch && p->Lx <= 4096;     // what the create_RTLinvR probes launch
+        if (which == 0 && patch) { ms[0] = 0.0; continue; }                        // pass A is not part of that path
+        auto launch = [&]() { return band ? conv_launch_band(p, a, k, patch ? ps : nullptr) : conv_launcher(Ls[which])(which, a, p->nsm, p->stream, p->tmap_s2); };
         ILM_TRY(launch());                                                                // warm-up
         ILM_CUDA(cudaEventRecord(e0, p->stream));
         for (int r = 0; r < reps; ++r) ILM_TRY(launch());

@@ -933,6 +933,29 @@ __global__ void k_probe_post_sum(int N, int W, int my, const int* __restrict__ j
     d0[k] = coef * re;
     if (d1) d1[k] = coef * im;
 }
+// the same for a batch of column pairs: pair y (blockIdx.y) left its row sums in slice y of t.part and owns the
+// columns 2y, 2y + 1 of dA0 (ncols columns in all; the last pair may be a single column)
+__global__ void k_probe_post_sum_batch(int N, int W, int my, const int* __restrict__ j0, const double2* __restrict__ part,
+                                       size_t stride, double coef, double* __restrict__ dA0, int ncols) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const int pair = blockIdx.y;
+    const double2* pp = part + (size_t)pair * stride;
+    double re = 0.0, im = 0.0;
+    for (int b = 0; b < W; ++b) {
+        const int j = j0[k] + b;
+        if (j >= 0 && j < my) { const double2 v = pp[k * W + b]; re += v.x; im += v.y; }
+    }
+    dA0[(size_t)(2 * pair) * N + k] = coef * re;
+    if (2 * pair + 1 < ncols) dA0[(size_t)(2 * pair + 1) * N + k] = coef * im;
+}
+int launch_probe_post_sum_batch(ilm_plan* p, const DevTable& t, int npairs, int ncols, double coef, double* dA0) {
+    if (npairs <= 0) return ILM_OK;
+    k_probe_post_sum_batch<<<dim3((p->N + 127) / 128, npairs), 128, 0, p->stream>>>(p->N, t.W, t.my, t.j0, t.part, t.part_stride, coef, dA0, ncols);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
 int launch_probe_post_sum(ilm_plan* p, const DevTable& t, int ncol, double coef, double* d0, double* d1) {
     k_probe_post_sum<<<(p->N + 127) / 128, 128, 0, p->stream>>>(p->N, t.W, t.my, t.j0, t.part, coef, d0, ncol > 1 ? d1 : nullptr);
     ILM_LAUNCHED(p);

@@ -184,7 +184,8 @@ int build_tables(ilm_plan* p) {
                 cudaFree(t.row_ent); cudaFree(t.part); t.row_ent = nullptr; t.part = nullptr;
                 const size_t cap = (np + np / 4 + 16) * W;
                 ILM_CUDA(cudaMalloc(&t.row_ent, cap * sizeof(int)));
-                ILM_CUDA(cudaMalloc(&t.part, cap * sizeof(double2)));
+                ILM_CUDA(cudaMalloc(&t.part, cap * PART_BATCH * sizeof(double2)));
+                t.part_stride = cap;
                 t.cap_rowent = cap;
             }
             ILM_CUDA(cudaMemcpyAsync(t.row_ptr, h.rptr.data(), h.rptr.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));

@@ -594,20 +594,47 @@ def test_probe_band_pass_equals_transform_pass(ddf, monkeypatch):
     body = (x + 0.93, y - 0.4, nx, ny, ds)                   # windows clipped at +x and -y
     G = ilm.lgf.lgf_table(96)
     built = {}
-    for band in ("1", "0"):
-        monkeypatch.setenv("ILM_PROBE_BAND", band)
+    for band in ("1", "0", "nopatch"):
+        # "nopatch": band pass fed by pass A on the grid rows (ILM_PROBE_PATCH=0); default: the band pass sums the
+        # x-spectrum of the DDF windows itself (create_RTLinvR probes: no pre-operator, no pass A)
+        monkeypatch.setenv("ILM_PROBE_BAND", "0" if band == "0" else "1")
+        monkeypatch.setenv("ILM_PROBE_PATCH", "0" if band == "nopatch" else "1")
         cache = ilm.SurfaceScalarCache(body, g, lgf_table=G, ddftype=ddf)
         vc = ilm.SurfaceVectorCache(body, g, lgf_table=G, ddftype=ddf)
         kid = cache.add_kernel(ilm.lgf.intfact_table(0.5, 96))
         built[band] = [ilm.create_RTLinvR(cache), ilm.create_CLinvCT(cache), ilm.create_GLinvD(cache),
                        ilm.create_GLinvD_cross(cache, cols=(3, 10)), ilm.create_RTHR(cache, kid),
                        ilm.create_CL2invCT(vc), ilm.create_CLinvCT(vc), ilm.create_RTLinvR(vc), ilm.create_GLinvD(vc, cols=(0, 9))]
-    for a, b in zip(built["1"], built["0"]):
+    for a, b, c in zip(built["1"], built["0"], built["nopatch"]):
         assert relerr(a, b) < 1e-13
+        assert relerr(a, c) < 1e-13
     if ddf == "yang3":
         oc = o.ScalarCache(o.Grid(g.NX, g.NY, g.dx, g.I0), *body, G)
         assert relerr(built["1"][0], oc.create_RTLinvR()) < RTOL
         assert relerr(built["1"][0], oc.create_RTLinvR_table()) < RTOL
+
+
+@pytest.mark.parametrize("cols", [None, (0, 7), (3, 40)])
+def test_probe_pairs_off_the_band_path_inside_a_build(cols):
+    """Two bodies far apart in y: the column pair that straddles the body boundary has patch rows more than
+    16 apart and takes the transform column pass, the pairs around it take the band pass in patch mode with batched
+    post sums.  The mixture (and odd column ranges) must give the same matrix as the oracle."""
+    g = ilm.PhysicalGrid(120, 150, 4.0 / 118, (60, 75))
+    c1_ = ilm.bodies.circle(0.45, 1.4 * g.dx, center=(0.3, -1.2))
+    c2_ = ilm.bodies.circle(0.35, 1.4 * g.dx, center=(-0.5, 1.1))
+    n1 = len(c1_[0])
+    body = ilm.bodies.concat(c1_, c2_)[:5]
+    G = ilm.lgf.lgf_table(160)
+    cache = ilm.SurfaceScalarCache(body, g, lgf_table=G)
+    oc = o.ScalarCache(o.Grid(g.NX, g.NY, g.dx, g.I0), *body, G)
+    if cols is None:
+        # make sure the boundary pair exists: start the build so that (n1 - 1, n1) is a pair
+        lo = (n1 - 1) % 2
+        S = np.asarray(ilm.create_RTLinvR(cache, cols=(lo, cache.N)))
+        assert relerr(S, oc.create_RTLinvR()[:, lo:]) < RTOL
+    else:
+        S = np.asarray(ilm.create_RTLinvR(cache, cols=cols))
+        assert relerr(S, oc.create_RTLinvR(cols=list(range(*cols)))) < RTOL
 
 
 # ---------------------------------------------------------------- whole-problem entry point (ilm_dirichlet_poisson)
