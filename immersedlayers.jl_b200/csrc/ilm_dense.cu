@@ -8,7 +8,9 @@
 // A22 -= A21 * A12 on the FP64 tensor pipe (mma.sync.m8n8k4.f64, "DMMA").
 #include <cooperative_groups.h>
 
+#include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "ilm_internal.h"
@@ -488,6 +490,397 @@ static int launch_panel_regs(int n, int k0, int nb, double* A, int* ipiv, cudaSt
     return ILM_OK;
 }
 
+// =====================================================================================================================
+// Panel, second form (the default): the same register panel (thread per row, cluster of C CTAs x 512 threads) with
+//   * the NARROW UPDATE of the previous panel fused in front: the kernel itself applies panel k-1's interchanges to its
+//     32 columns (each thread loads the row its own row ends up holding), one warp solves the 32 x 32 block row
+//     U12 = L11^-1 A12, the block is pushed to every CTA of the cluster and every thread subtracts L21 U12 from its
+//     row in registers.  Replaces three dependent launches (swap, trsm, rank-32 DMMA update of 32 columns: ~35 us)
+//     on the critical path of the factorisation by ~8 us inside the panel kernel;
+//   * arg-max by three redux.sync on the ordered bit pattern of |a| (max of the high word, max of the low word among
+//     those, min row index among those = first maximum, idamax semantics) instead of five shuffle rounds of
+//     (value, index) pairs;
+//   * every warp's candidate row written to shared memory BEFORE the block barrier (speculatively), so one block
+//     barrier per column instead of two; the final 16-candidate scan is lane-parallel (redux again);
+//   * the reciprocal of the candidate pivot computed by the pushing warp while the row travels (LAPACK's getf2
+//     scales by the reciprocal too).
+// Pivot choices are those of LAPACK (first maximum of |a|); the multipliers l = a * (1/p).
+// =====================================================================================================================
+constexpr int P2_THREADS = 512, P2_WARPS = P2_THREADS / 32, P2_MAXC = 16;
+struct P2Xchg {                        // triple-buffered by column: a peer may be one column ahead while this CTA still
+    double rows[3][P2_MAXC][NB];       // applies the deferred part of the previous column's update
+    double old[3][NB];
+    double rcp[3][P2_MAXC];
+    unsigned khi[3][P2_MAXC], klo[3][P2_MAXC];
+    int idx[3][P2_MAXC];
+};
+constexpr int P2_NOROW = 0x7fffffff;
+// First maximum of the 64-bit keys (hi, lo) over the lanes with `valid`; lanes are in ascending row order, so the lowest
+// matching lane is the first maximum (idamax semantics).  One redux.sync + one ballot unless several lanes share the high
+// word.  Returns the winning lane or -1.
+__device__ __forceinline__ int first_max_lane(unsigned hi, unsigned lo, bool valid) {
+    const unsigned mh = __reduce_max_sync(0xffffffffu, valid ? hi : 0u);
+    unsigned m = __ballot_sync(0xffffffffu, valid && hi == mh);
+    if (__popc(m) > 1) {
+        const bool in = valid && hi == mh;
+        const unsigned ml = __reduce_max_sync(0xffffffffu, in ? lo : 0u);
+        m = __ballot_sync(0xffffffffu, in && lo == ml);
+    }
+    return __ffs(m) - 1;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// per panel: the net row permutation of its interchanges, for the wide update (k_lu_swap_trsm).
+// perm[0] = m, perm[1 + q] = dst row, perm[1 + 64 + q] = src row; the first nb entries are the top block rows in order.
+constexpr int PERM_STRIDE = 132;
+
+#define P2A(p) (((p) & 1) ? a[(p) >> 1].y : a[(p) >> 1].x)
+
+template <bool DEFER>
+__global__ void __launch_bounds__(P2_THREADS) k_lu_panel_v2(int n, int k0, int nb, double* __restrict__ A, int* __restrict__ ipiv,
+                                                            int pk0, int pnb, int* __restrict__ perm, long long* __restrict__ trace) {
+    // trace (ILM_LU_TRACE=1, null otherwise): clock64 sums of the phases of the column loop seen by thread 0 of CTA 0
+    __shared__ long long s_tr[12];
+    long long tlast = 0;
+    auto stamp = [&](int slot) {
+        if (trace && threadIdx.x == 0 && blockIdx.x == 0) {
+            const long long t = clock64();
+            if (slot >= 0) s_tr[slot] += t - tlast; else { for (int i = 0; i < 12; ++i) s_tr[i] = 0; }
+            tlast = clock64();
+        }
+    };
+    stamp(-1);
+    cg::cluster_group cl = cg::this_cluster();
+    const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    __shared__ __align__(16) P2Xchg X;
+    __shared__ __align__(16) double s_rows[P2_WARPS][NB];
+    __shared__ __align__(16) double s_old[NB];
+    __shared__ unsigned s_khi[P2_WARPS], s_klo[P2_WARPS];
+    __shared__ int s_idx[P2_WARPS];
+    __shared__ int s_piv[NB];
+    __shared__ __align__(16) double Ubuf[NB][NB];            // U12 of the fused narrow update, [j][c]
+    __shared__ double Tt[NB][NB + 1], LL[NB][NB + 1];        // rank 0, warp 0: transposition tile and L11
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int row = k0 + rank * P2_THREADS + tid;
+    const bool has = row < n;
+    double2 a[NB / 2];                                       // the row: position p = a[p/2].x / .y (vector shared-memory accesses)
+    if (pnb > 0) {
+        // ---- fused narrow update with panel [pk0, pk0 + pnb), pk0 + pnb == k0
+        if (tid < NB) s_piv[tid] = tid < pnb ? ipiv[pk0 + tid] - 1 : -1;
+        __syncthreads();
+        // the row that ends up in row r after the interchanges jj = 0 .. pnb-1 (applied backwards to the index)
+        auto source_row = [&](int r) {
+            for (int jj = pnb - 1; jj >= 0; --jj) {
+                const int t = pk0 + jj, pv = s_piv[jj];
+                r = (r == t) ? pv : ((r == pv) ? t : r);
+            }
+            return r;
+        };
+        const int src = has ? source_row(row) : 0;
+        if (rank == 0 && wid == 0) {
+            // block row: lane i holds row pk0 + i of the 32 columns; transpose through shared memory so that lane c
+            // solves column c by forward substitution with the unit lower triangle L11
+            const int ur = pk0 + lane;
+            const int usrc = lane < pnb ? source_row(ur) : -1;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) Tt[lane][c] = (usrc >= 0 && c < nb) ? A[(size_t)(k0 + c) * n + usrc] : 0.0;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) LL[lane][j] = (lane < pnb && j < lane) ? A[(size_t)(pk0 + j) * n + ur] : 0.0;
+            __syncwarp();
+            double x[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) x[i] = Tt[i][lane];
+            // column-oriented substitution: for fixed j the updates of x[j+1..] are independent (the row-oriented order
+            // is one dependent chain of 496 FMAs)
+#pragma unroll
+            for (int j = 0; j < NB - 1; ++j) {
+#pragma unroll
+                for (int i = j + 1; i < NB; ++i) x[i] -= LL[i][j] * x[j];
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) Ubuf[i][lane] = x[i];
+        }
+#pragma unroll
+        for (int c = 0; c < NB; ++c) P2A(c) = (has && c < nb) ? A[(size_t)(k0 + c) * n + src] : 0.0;
+        double l[2][8];                                          // multipliers of the previous panel, 8 at a time, one chunk ahead
+#pragma unroll
+        for (int t = 0; t < 8; ++t) l[0][t] = (has && t < pnb) ? A[(size_t)(pk0 + t) * n + row] : 0.0;
+        __syncthreads();
+        if (rank == 0 && wid > 0 && wid < C) {                  // warp p pushes U12 to peer p
+            double2* dst = reinterpret_cast<double2*>(cl.map_shared_rank(&Ubuf[0][0], wid));
+            const double2* s2 = reinterpret_cast<const double2*>(&Ubuf[0][0]);
+#pragma unroll
+            for (int q = 0; q < NB * NB / 2 / 32; ++q) dst[q * 32 + lane] = s2[q * 32 + lane];
+        }
+        cl.sync();                                               // U12 everywhere; every load of the old rows has completed
+        if (rank == 0) {                                         // the block row goes back to the matrix
+            for (int e = tid; e < NB * NB; e += P2_THREADS) {
+                const int j = e & (NB - 1), c = e >> 5;
+                if (j < pnb && c < nb) A[(size_t)(k0 + c) * n + pk0 + j] = Ubuf[j][c];
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < NB / 8; ++ch) {
+            if (ch + 1 < NB / 8) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) l[(ch + 1) & 1][t] = (has && 8 * (ch + 1) + t < pnb) ? A[(size_t)(pk0 + 8 * (ch + 1) + t) * n + row] : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const double2* u = reinterpret_cast<const double2*>(&Ubuf[8 * ch + t][0]);
+                const double lt = l[ch & 1][t];
+#pragma unroll
+                for (int c2 = 0; c2 < NB / 2; ++c2) {
+                    const double2 uu = u[c2];
+                    a[c2].x -= lt * uu.x;
+                    a[c2].y -= lt * uu.y;
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) P2A(c) = (has && c < nb) ? A[(size_t)(k0 + c) * n + row] : 0.0;
+        cl.sync();                                               // every CTA of the cluster is running before the first push
+    }
+    stamp(0);
+    // ---- the columns, in 4 groups of 8: inside a group the sub-step s is a compile-time constant (current column at
+    // position s, static register indices, no moves), after each group the register row is rotated by 8 positions, so the
+    // loop body is the same code for every group and after the 4 rotations position p holds column p again.  In group g
+    // the positions [32 - 8g, 32) hold finished multipliers of earlier groups: the 8-position blocks b >= 4 - g are skipped.
+    //
+    // DEFERRED UPDATE: after the pivot of column jj is known a thread scales its multiplier and updates only the NEXT
+    // column's position; the other positions (up to 30 FMAs) wait until the cluster barrier of column jj + 1 has been
+    // signalled and are applied while that barrier completes.  A thread whose row is about to be published (its warp's
+    // candidate, or the top row) applies its pending part first.
+    bool pend = false;
+    double lprev = 0.0;
+    const double* pprev = nullptr;
+    int buf = 0;
+    // positions > s + 1 of the live blocks: a -= l * prow
+    auto deferred = [&](auto sconst, int liveb) {
+        constexpr int sp = decltype(sconst)::value;              // sub-step whose update is pending
+        const double2* pr = reinterpret_cast<const double2*>(pprev);
+#pragma unroll
+        for (int c2 = 0; c2 < NB / 2; ++c2) {
+            if (2 * c2 + 1 > sp + 1 && (c2 >> 2) < liveb) {
+                const double2 pp = pr[c2];
+                if (2 * c2 > sp + 1) a[c2].x -= lprev * pp.x;
+                a[c2].y -= lprev * pp.y;
+            }
+        }
+    };
+#pragma unroll 1
+    for (int g = 0; g < NB / 8; ++g) {
+        const int liveb = NB / 8 - g;                            // live 8-position blocks
+        auto substep = [&](auto sconst) {
+            constexpr int sidx = decltype(sconst)::value;
+            const int jj = 8 * g + sidx;
+            if (jj < nb) {
+                const int col = k0 + jj;
+                const bool active = has && row >= col;
+                const double av = fabs(P2A(sidx));
+                const unsigned hi = (unsigned)__double2hiint(av), lo = (unsigned)__double2loint(av);
+                const int w = first_max_lane(hi, lo, active);
+                stamp(1);
+                if (DEFER && sidx > 0 && (lane == w || row == col)) {      // rows about to be published apply their pending part first
+                    if (pend) { deferred(std::integral_constant<int, (sidx > 0 ? sidx - 1 : 0)>{}, liveb); pend = false; }
+                }
+                if (lane == w) { s_khi[wid] = hi; s_klo[wid] = lo; s_idx[wid] = row; }
+                if (w < 0 && lane == 0) { s_khi[wid] = 0u; s_klo[wid] = 0u; s_idx[wid] = P2_NOROW; }
+                if (row == col) {                                // the top row (always rank 0, warp 0)
+                    double2* d = reinterpret_cast<double2*>(&s_old[0]);
+#pragma unroll
+                    for (int c = 0; c < NB / 2; ++c) d[c] = a[c];
+                }
+                stamp(2);
+                __syncthreads();
+                stamp(3);
+                // every warp finds the CTA's candidate; its owner alone writes the row to shared memory (16 warps
+                // writing their candidates speculatively cost 16 x 16 single-lane vector stores per column)
+                const bool l16 = lane < P2_WARPS;
+                const int myi = l16 ? s_idx[lane] : P2_NOROW;
+                const unsigned mhi = l16 ? s_khi[lane] : 0u, mlo = l16 ? s_klo[lane] : 0u;
+                const int ww = first_max_lane(mhi, mlo, myi != P2_NOROW);
+                const int crow = ww >= 0 ? s_idx[ww] : P2_NOROW;
+                if (has && row == crow) {
+                    double2* d = reinterpret_cast<double2*>(&s_rows[0][0]);
+#pragma unroll
+                    for (int c = 0; c < NB / 2; ++c) d[c] = a[c];
+                }
+                stamp(4);
+                __syncthreads();
+                if (wid < C) {                                   // warp p pushes the CTA's candidate to peer p
+                    P2Xchg* Xp = cl.map_shared_rank(&X, wid);
+                    if (ww < 0) {                                // no active row in this CTA
+                        if (lane == 0) { Xp->khi[buf][rank] = 0u; Xp->klo[buf][rank] = 0u; Xp->idx[buf][rank] = P2_NOROW; }
+                    } else if (lane == ww) {
+                        Xp->khi[buf][rank] = mhi; Xp->klo[buf][rank] = mlo; Xp->idx[buf][rank] = myi;
+                    }
+                    Xp->rows[buf][rank][lane] = s_rows[0][lane];
+                    if (rank == 0) Xp->old[buf][lane] = s_old[lane];
+                    if (lane == 0) Xp->rcp[buf][rank] = __drcp_rn(s_rows[0][sidx]);
+                }
+                stamp(5);
+                __syncwarp();
+                cluster_arrive();
+                if (sidx > 0) { if (pend) { deferred(std::integral_constant<int, (sidx > 0 ? sidx - 1 : 0)>{}, liveb); pend = false; } }
+                __syncwarp();
+                cluster_wait();
+                stamp(6);
+                const bool lc = lane < C;
+                const int cli = lc ? X.idx[buf][lane] : P2_NOROW;
+                const int pw = first_max_lane(lc ? X.khi[buf][lane] : 0u, lc ? X.klo[buf][lane] : 0u, cli != P2_NOROW);
+                const int piv = X.idx[buf][pw];
+                const double* prow = X.rows[buf][pw];
+                stamp(7);
+                if (piv != col && has && (row == piv || row == col)) {       // the two rows of the interchange
+                    const double2* sp = reinterpret_cast<const double2*>(row == piv ? &X.old[buf][0] : prow);
+#pragma unroll
+                    for (int c = 0; c < NB / 2; ++c) a[c] = sp[c];
+                }
+                if (rank == 0 && tid == 0) { ipiv[col] = piv + 1; s_piv[jj] = piv; }
+                if (has && row > col) {
+                    const double lm = P2A(sidx) * X.rcp[buf][pw];
+                    P2A(sidx) = lm;
+                    if constexpr (DEFER) {
+                        if (((sidx + 1) >> 3) < liveb) P2A(sidx + 1) -= lm * prow[sidx + 1];   // the next column (position 8 = column 0 of the next group; in the last group it holds a finished multiplier)
+                        lprev = lm;
+                        pend = true;
+                    } else {
+                        const double2* pr = reinterpret_cast<const double2*>(prow);
+#pragma unroll
+                        for (int c2 = 0; c2 < NB / 2; ++c2) {
+                            if (2 * c2 + 1 > sidx && (c2 >> 2) < liveb) {
+                                const double2 pp = pr[c2];
+                                if (2 * c2 > sidx) a[c2].x -= lm * pp.x;
+                                a[c2].y -= lm * pp.y;
+                            }
+                        }
+                    }
+                } else {
+                    pend = false;
+                }
+                pprev = prow;
+                buf = buf == 2 ? 0 : buf + 1;
+                stamp(8);
+            }
+        };
+        substep(std::integral_constant<int, 0>{}); substep(std::integral_constant<int, 1>{});
+        substep(std::integral_constant<int, 2>{}); substep(std::integral_constant<int, 3>{});
+        substep(std::integral_constant<int, 4>{}); substep(std::integral_constant<int, 5>{});
+        substep(std::integral_constant<int, 6>{}); substep(std::integral_constant<int, 7>{});
+        {
+            if (pend) { deferred(std::integral_constant<int, 7>{}, liveb); pend = false; }   // the group's last column, before the rotation
+            double2 t[4];                                        // rotate by 8: this group's multipliers go to the back
+#pragma unroll
+            for (int c = 0; c < 4; ++c) t[c] = a[c];
+#pragma unroll
+            for (int c = 0; c < NB / 2 - 4; ++c) a[c] = a[c + 4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a[NB / 2 - 4 + c] = t[c];
+        }
+    }
+    stamp(9);
+    if (has) {                                                   // four rotations by 8: position p holds column p again
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+            if (c < nb) A[(size_t)(k0 + c) * n + row] = P2A(c);
+    }
+    // ---- net permutation of this panel's interchanges for the wide update: rows touched = the top block rows and the
+    // distinct pivot rows below it; each takes the value of the row its index maps back to
+    __syncthreads();                                             // s_piv (thread 0) is complete
+    if (rank == 0 && wid == 1 && perm) {
+        const int pv = lane < nb ? s_piv[lane] : -1;
+        const bool below = pv >= k0 + nb;
+        const unsigned same = __match_any_sync(0xffffffffu, below ? pv : -1 - lane);
+        const bool first = below && (same & ((1u << lane) - 1u)) == 0u;
+        const unsigned fb = __ballot_sync(0xffffffffu, first);
+        const int m = nb + __popc(fb);
+        auto source_of = [&](int r) {
+            for (int jj = nb - 1; jj >= 0; --jj) {
+                const int t = k0 + jj, q = s_piv[jj];
+                r = (r == t) ? q : ((r == q) ? t : r);
+            }
+            return r;
+        };
+        if (lane == 0) perm[0] = m;
+        if (lane < nb) { perm[1 + lane] = k0 + lane; perm[1 + 64 + lane] = source_of(k0 + lane); }
+        if (first) {
+            const int q = nb + __popc(fb & ((1u << lane) - 1u));
+            perm[1 + q] = pv; perm[1 + 64 + q] = source_of(pv);
+        }
+    }
+    stamp(10);
+    if (trace && threadIdx.x == 0 && blockIdx.x == 0) { for (int i = 0; i < 11; ++i) trace[i] += s_tr[i]; }
+    cl.sync();                                                   // no CTA leaves while a peer may still write its shared memory
+}
+#undef P2A
+
+static int launch_panel_v2(int n, int k0, int nb, double* A, int* ipiv, int pk0, int pnb, int* perm, long long* trace, cudaStream_t st) {
+    const int rows = n - k0;
+    int C = 1;
+    while (C * P2_THREADS < rows) C *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C);
+    cfg.blockDim = dim3(P2_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    static const bool defer = getenv("ILM_LU_DEFER") != nullptr;     // deferred row update inside the cluster barrier (measured slower: the
+    if (defer)                                                       // rows about to be published must apply it early, in divergent code)
+        ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<true>, n, k0, nb, A, ipiv, pk0, pnb, perm, trace));
+    else
+        ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<false>, n, k0, nb, A, ipiv, pk0, pnb, perm, trace));
+    return ILM_OK;
+}
+
+// Wide update, first kernel: the interchanges of panel [k0, k0 + nb) applied to the columns [0, k0) and [cright, n) as ONE
+// gather and ONE scatter per column (the net permutation comes from the panel kernel; 32 dependent swaps cost 32 global
+// round trips), and for the right columns the block row U12 = L11^-1 A12 solved in between, in registers.
+__global__ void __launch_bounds__(64) k_lu_swap_trsm(int n, int k0, int nb, double* __restrict__ A, const int* __restrict__ perm,
+                                                     int cright) {
+    __shared__ int s_dst[64], s_src[64];
+    __shared__ int s_m;
+    __shared__ double L11[NB][NB + 1];
+    const int nleft = k0;
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) s_m = perm[0];
+    if (threadIdx.x < 64) { s_dst[threadIdx.x] = perm[1 + threadIdx.x]; s_src[threadIdx.x] = perm[1 + 64 + threadIdx.x]; }
+    const bool right_block = (blockIdx.x + 1) * blockDim.x > nleft;     // some column of this block needs the solve
+    if (right_block)
+        for (int i = threadIdx.x; i < NB * NB; i += blockDim.x) {
+            const int r = i % NB, q = i / NB;
+            L11[r][q] = (r < nb && q < r) ? A[(size_t)(k0 + q) * n + k0 + r] : 0.0;
+        }
+    __syncthreads();
+    const bool right = c >= nleft;
+    if (right) c += cright - nleft;
+    if (c >= n) return;
+    const int m = s_m;
+    double* col = A + (size_t)c * n;
+    double x[NB], y[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) x[i] = i < nb ? col[s_src[i]] : 0.0;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) y[q] = nb + q < m ? col[s_src[nb + q]] : 0.0;
+    if (right) {                                        // column-oriented substitution (independent updates for fixed j)
+#pragma unroll
+        for (int j = 0; j < NB - 1; ++j) {
+#pragma unroll
+            for (int i = j + 1; i < NB; ++i) x[i] -= L11[i][j] * x[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+        if (i < nb) col[k0 + i] = x[i];
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+        if (nb + q < m) col[s_dst[nb + q]] = y[q];
+}
+
 // apply the row interchanges of pivots [r0, r0+nr) to the columns [cbeg, cend) except [skip0, skip1)
 __global__ void k_lu_swap(int n, int r0, int nr, double* __restrict__ A, const int* __restrict__ ipiv, int cbeg, int cend,
                           int skip0, int skip1) {
@@ -880,7 +1273,11 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
     // step k (all other columns, left and right interchanges) and runs underneath the next panel.
     static const bool no_lookahead = getenv("ILM_LU_NO_LOOKAHEAD") != nullptr;
     if (KB == NB && !no_lookahead && n > 2 * NB) {
-        struct Aux { cudaStream_t hi = nullptr, lo = nullptr; cudaEvent_t begin = nullptr, evP = nullptr, evW = nullptr, end = nullptr; };
+        struct Aux {
+            cudaStream_t hi = nullptr, lo = nullptr;
+            cudaEvent_t begin = nullptr, evP = nullptr, evW = nullptr, end = nullptr, evW2[2] = {nullptr, nullptr};
+            int* perm = nullptr; size_t perm_cap = 0;               // net permutations of the panels (k_lu_panel_v2 -> k_lu_swap_trsm)
+        };
         static Aux aux_dev[64];
         int dev = 0;
         ILM_CUDA(cudaGetDevice(&dev));
@@ -894,12 +1291,76 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
             ILM_CUDA(cudaEventCreateWithFlags(&ax.evP, cudaEventDisableTiming));
             ILM_CUDA(cudaEventCreateWithFlags(&ax.evW, cudaEventDisableTiming));
             ILM_CUDA(cudaEventCreateWithFlags(&ax.end, cudaEventDisableTiming));
+            ILM_CUDA(cudaEventCreateWithFlags(&ax.evW2[0], cudaEventDisableTiming));
+            ILM_CUDA(cudaEventCreateWithFlags(&ax.evW2[1], cudaEventDisableTiming));
         }
         const cudaStream_t user = st;
         ILM_CUDA(cudaEventRecord(ax.begin, user));
         ILM_CUDA(cudaStreamWaitEvent(ax.hi, ax.begin, 0));
         ILM_CUDA(cudaStreamWaitEvent(ax.lo, ax.begin, 0));
         bool wide_pending = false;
+        static const bool v1 = getenv("ILM_LU_V1") != nullptr;        // the separate narrow-update launches (first round-2 form)
+        if (!v1 && n <= P2_MAXC * P2_THREADS) {
+            // Second form: the panel kernel applies the previous panel's update to its own 32 columns (k_lu_panel_v2);
+            // the wide update is two launches (net permutation + block row, rank-32 DMMA update) on the low-priority stream.
+            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            const int npan = (n + NB - 1) / NB;
+            if (ax.perm_cap < (size_t)npan * PERM_STRIDE) {
+                ILM_CUDA(cudaStreamSynchronize(ax.hi));
+                ILM_CUDA(cudaStreamSynchronize(ax.lo));
+                cudaFree(ax.perm);
+                ax.perm = nullptr; ax.perm_cap = 0;
+                ILM_CUDA(cudaMalloc(&ax.perm, (size_t)npan * PERM_STRIDE * sizeof(int)));
+                ax.perm_cap = (size_t)npan * PERM_STRIDE;
+            }
+            static const bool want_trace = getenv("ILM_LU_TRACE") != nullptr;
+            long long* trace = nullptr;
+            if (want_trace) { ILM_CUDA(cudaMalloc(&trace, 16 * sizeof(long long))); ILM_CUDA(cudaMemsetAsync(trace, 0, 16 * sizeof(long long), ax.hi)); }
+            int pk0 = 0, pnb = 0;
+            for (int k0 = 0, ip = 0; k0 < n; k0 += NB, ++ip) {
+                const int nb = n - k0 < NB ? n - k0 : NB, k1 = k0 + nb;
+                const int nb1 = n - k1 < NB ? n - k1 : NB, k1e = k1 + nb1;      // the next panel's columns [k1, k1e)
+                int* perm = ax.perm + (size_t)ip * PERM_STRIDE;
+                // this panel's columns were last touched by the wide update of step k-2 (step k-1 excluded them: they get that
+                // update inside the panel kernel), so the panel runs beside the wide update of step k-1
+                if (ip >= 2) ILM_CUDA(cudaStreamWaitEvent(ax.hi, ax.evW2[ip & 1], 0));
+                ILM_TRY(launch_panel_v2(n, k0, nb, dA, dP, pk0, pnb, perm, trace, ax.hi));
+                g_dense_launches++;
+                ILM_CUDA(cudaEventRecord(ax.evP, ax.hi));
+                ILM_CUDA(cudaStreamWaitEvent(ax.lo, ax.evP, 0));
+                const int ncols = k0 + (n - k1e);
+                if (ncols > 0) {
+                    k_lu_swap_trsm<<<(ncols + 63) / 64, 64, 0, ax.lo>>>(n, k0, nb, dA, perm, k1e);
+                    g_dense_launches++;
+                }
+                st = ax.lo;
+                if (n - k1e > 0) gemm(n - k1, n - k1e, nb, k1, k0, k0, k1e);
+                ILM_CUDA(cudaEventRecord(ax.evW2[ip & 1], ax.lo));
+                ILM_CUDA(cudaEventRecord(ax.evW, ax.lo));
+                wide_pending = true;
+                pk0 = k0; pnb = nb;
+            }
+            ILM_CUDA(cudaStreamWaitEvent(ax.hi, ax.evW, 0));
+            ILM_CUDA(cudaEventRecord(ax.end, ax.hi));
+            ILM_CUDA(cudaStreamWaitEvent(user, ax.end, 0));
+            st = user;
+            ILM_CUDA(cudaGetLastError());
+            if (trace) {
+                long long h[16];
+                ILM_CUDA(cudaStreamSynchronize(user));
+                ILM_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+                cudaFree(trace);
+                static const char* nm[11] = {"narrow update (per panel)", "argmax warp", "keys + top row -> smem", "block barrier", "argmax CTA + row -> smem", "barrier + push + rcp",
+                                             "cluster barrier", "argmax cluster", "interchange + update", "rotations (per panel)", "write-back + perm (per panel)"};
+                fprintf(stderr, "ilm LU trace, n = %d, %d panels (clock cycles seen by thread 0 of CTA 0):\n", n, npan);
+                for (int i = 0; i < 11; ++i) {
+                    const bool per_panel = i == 0 || i >= 9;
+                    fprintf(stderr, "  %-32s %10.1f cycles %s\n", nm[i], (double)h[i] / (per_panel ? npan : n), per_panel ? "per panel" : "per column");
+                }
+            }
+            return io.finish();
+        }
         for (int k0 = 0; k0 < n; k0 += NB) {
             const int nb = n - k0 < NB ? n - k0 : NB, k1 = k0 + nb;
             const int nb1 = n - k1 < NB ? n - k1 : NB, k1e = k1 + nb1;          // the next panel's columns [k1, k1e)
