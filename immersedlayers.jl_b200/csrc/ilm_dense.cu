@@ -506,25 +506,26 @@ static int launch_panel_regs(int n, int k0, int nb, double* A, int* ipiv, cudaSt
 //     scales by the reciprocal too).
 // Pivot choices are those of LAPACK (first maximum of |a|); the multipliers l = a * (1/p).
 // =====================================================================================================================
-constexpr int P2_THREADS = 512, P2_WARPS = P2_THREADS / 32, P2_MAXC = 16;
-struct P2Xchg {                        // triple-buffered by column: a peer may be one column ahead while this CTA still
-    double rows[3][P2_MAXC][NB];       // applies the deferred part of the previous column's update
-    double old[3][NB];
-    double rcp[3][P2_MAXC];
-    unsigned khi[3][P2_MAXC], klo[3][P2_MAXC];
-    int idx[3][P2_MAXC];
+constexpr int P2_MAXC = 16;
+struct P2Xchg {                        // double-buffered by column parity
+    double rows[2][P2_MAXC][NB];       // candidate row of every CTA
+    double ext[2][P2_MAXC][4];         // [0] 1 / candidate, [1] key (|a| bit pattern), [2] logical row index (as bits)
 };
 constexpr int P2_NOROW = 0x7fffffff;
-// First maximum of the 64-bit keys (hi, lo) over the lanes with `valid`; lanes are in ascending row order, so the lowest
-// matching lane is the first maximum (idamax semantics).  One redux.sync + one ballot unless several lanes share the high
-// word.  Returns the winning lane or -1.
-__device__ __forceinline__ int first_max_lane(unsigned hi, unsigned lo, bool valid) {
+// Maximum of the 64-bit keys (hi, lo) over the lanes with `valid`, ties to the smallest idx (idamax semantics on the logical
+// row order).  One redux.sync + one ballot unless several lanes share the high word.  Returns the winning lane or -1.
+__device__ __forceinline__ int first_max_lane(unsigned hi, unsigned lo, int idx, bool valid) {
     const unsigned mh = __reduce_max_sync(0xffffffffu, valid ? hi : 0u);
     unsigned m = __ballot_sync(0xffffffffu, valid && hi == mh);
     if (__popc(m) > 1) {
         const bool in = valid && hi == mh;
         const unsigned ml = __reduce_max_sync(0xffffffffu, in ? lo : 0u);
         m = __ballot_sync(0xffffffffu, in && lo == ml);
+        if (__popc(m) > 1) {                                 // equal |a|: the smallest (logical) row index wins
+            const bool in2 = in && lo == ml;
+            const unsigned mi = __reduce_min_sync(0xffffffffu, in2 ? (unsigned)idx : 0xffffffffu);
+            m = __ballot_sync(0xffffffffu, in2 && (unsigned)idx == mi);
+        }
     }
     return __ffs(m) - 1;
 }
@@ -536,32 +537,39 @@ constexpr int PERM_STRIDE = 132;
 
 #define P2A(p) (((p) & 1) ? a[(p) >> 1].y : a[(p) >> 1].x)
 
-template <bool DEFER>
-__global__ void __launch_bounds__(P2_THREADS) k_lu_panel_v2(int n, int k0, int nb, double* __restrict__ A, int* __restrict__ ipiv,
-                                                            int pk0, int pnb, int* __restrict__ perm, long long* __restrict__ trace) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_lu_panel_v2(int n, int k0, int nb, double* __restrict__ A, int* __restrict__ ipiv,
+                                                            int pk0, int pnb, int* __restrict__ perm, double* __restrict__ uscr,
+                                                            long long* __restrict__ trace) {
     // trace (ILM_LU_TRACE=1, null otherwise): clock64 sums of the phases of the column loop seen by thread 0 of CTA 0
-    __shared__ long long s_tr[12];
+    __shared__ long long s_tr[16];
     long long tlast = 0;
     auto stamp = [&](int slot) {
         if (trace && threadIdx.x == 0 && blockIdx.x == 0) {
             const long long t = clock64();
-            if (slot >= 0) s_tr[slot] += t - tlast; else { for (int i = 0; i < 12; ++i) s_tr[i] = 0; }
+            if (slot >= 0) s_tr[slot] += t - tlast; else { for (int i = 0; i < 16; ++i) s_tr[i] = 0; }
             tlast = clock64();
         }
     };
     stamp(-1);
+    if (trace && threadIdx.x == 0 && blockIdx.x == 0) {          // timeline: entry / exit of every panel kernel (ns)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        trace[16 + 2 * (k0 / NB)] = (long long)t;
+    }
+    constexpr int WARPS = THREADS / 32;
     cg::cluster_group cl = cg::this_cluster();
     const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     __shared__ __align__(16) P2Xchg X;
-    __shared__ __align__(16) double s_rows[P2_WARPS][NB];
-    __shared__ __align__(16) double s_old[NB];
-    __shared__ unsigned s_khi[P2_WARPS], s_klo[P2_WARPS];
-    __shared__ int s_idx[P2_WARPS];
+    __shared__ __align__(16) double s_rows[WARPS][NB];
+    __shared__ unsigned s_khi[WARPS], s_klo[WARPS];
+    __shared__ int s_idx[WARPS];
     __shared__ int s_piv[NB];
+    __shared__ double s_ext[4];
     __shared__ __align__(16) double Ubuf[NB][NB];            // U12 of the fused narrow update, [j][c]
     __shared__ double Tt[NB][NB + 1], LL[NB][NB + 1];        // rank 0, warp 0: transposition tile and L11
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int row = k0 + rank * P2_THREADS + tid;
+    const int row = k0 + rank * THREADS + tid;
     const bool has = row < n;
     double2 a[NB / 2];                                       // the row: position p = a[p/2].x / .y (vector shared-memory accesses)
     if (pnb > 0) {
@@ -576,7 +584,12 @@ __global__ void __launch_bounds__(P2_THREADS) k_lu_panel_v2(int n, int k0, int n
             }
             return r;
         };
-        const int src = has ? source_row(row) : 0;
+        // rows >= k0 move only if they were a pivot of the previous panel (independent compares; the dependent
+        // 32-step walk only for those)
+        bool moved = false;
+#pragma unroll 8
+        for (int jj = 0; jj < NB; ++jj) moved |= (row == s_piv[jj]);
+        const int src = (has && moved) ? source_row(row) : (has ? row : 0);
         if (rank == 0 && wid == 0) {
             // block row: lane i holds row pk0 + i of the 32 columns; transpose through shared memory so that lane c
             // solves column c by forward substitution with the unit lower triangle L11
@@ -605,16 +618,27 @@ __global__ void __launch_bounds__(P2_THREADS) k_lu_panel_v2(int n, int k0, int n
         double l[2][8];                                          // multipliers of the previous panel, 8 at a time, one chunk ahead
 #pragma unroll
         for (int t = 0; t < 8; ++t) l[0][t] = (has && t < pnb) ? A[(size_t)(pk0 + t) * n + row] : 0.0;
+        stamp(11);
         __syncthreads();
-        if (rank == 0 && wid > 0 && wid < C) {                  // warp p pushes U12 to peer p
-            double2* dst = reinterpret_cast<double2*>(cl.map_shared_rank(&Ubuf[0][0], wid));
+        stamp(12);
+        // U12 reaches the other CTAs through L2 (a scratch block, not the matrix: rows of the matrix may still be read as
+        // interchange sources): pushing 8 KB to 15 peers through distributed shared memory cost 4.8 k cycles, bound by the
+        // egress of one SM
+        if (rank == 0 && C > 1) {
             const double2* s2 = reinterpret_cast<const double2*>(&Ubuf[0][0]);
-#pragma unroll
-            for (int q = 0; q < NB * NB / 2 / 32; ++q) dst[q * 32 + lane] = s2[q * 32 + lane];
+            double2* g2 = reinterpret_cast<double2*>(uscr);
+            for (int e = tid; e < NB * NB / 2; e += THREADS) g2[e] = s2[e];
         }
-        cl.sync();                                               // U12 everywhere; every load of the old rows has completed
+        cl.sync();                                               // U12 in L2; every load of the old rows has completed
+        if (rank != 0) {
+            double2* d2 = reinterpret_cast<double2*>(&Ubuf[0][0]);
+            const double2* g2 = reinterpret_cast<const double2*>(uscr);
+            for (int e = tid; e < NB * NB / 2; e += THREADS) d2[e] = __ldcg(g2 + e);
+            __syncthreads();
+        }
+        stamp(13);
         if (rank == 0) {                                         // the block row goes back to the matrix
-            for (int e = tid; e < NB * NB; e += P2_THREADS) {
+            for (int e = tid; e < NB * NB; e += THREADS) {
                 const int j = e & (NB - 1), c = e >> 5;
                 if (j < pnb && c < nb) A[(size_t)(k0 + c) * n + pk0 + j] = Ubuf[j][c];
             }
@@ -637,6 +661,7 @@ __global__ void __launch_bounds__(P2_THREADS) k_lu_panel_v2(int n, int k0, int n
                 }
             }
         }
+        stamp(14);
     } else {
 #pragma unroll
         for (int c = 0; c < NB; ++c) P2A(c) = (has && c < nb) ? A[(size_t)(k0 + c) * n + row] : 0.0;
@@ -648,27 +673,13 @@ __global__ void __launch_bounds__(P2_THREADS) k_lu_panel_v2(int n, int k0, int n
     // loop body is the same code for every group and after the 4 rotations position p holds column p again.  In group g
     // the positions [32 - 8g, 32) hold finished multipliers of earlier groups: the 8-position blocks b >= 4 - g are skipped.
     //
-    // DEFERRED UPDATE: after the pivot of column jj is known a thread scales its multiplier and updates only the NEXT
-    // column's position; the other positions (up to 30 FMAs) wait until the cluster barrier of column jj + 1 has been
-    // signalled and are applied while that barrier completes.  A thread whose row is about to be published (its warp's
-    // candidate, or the top row) applies its pending part first.
-    bool pend = false;
-    double lprev = 0.0;
-    const double* pprev = nullptr;
+    // NO ROW MOVES inside the panel: a thread keeps its row for the whole kernel and tracks the LOGICAL row index `pos`
+    // that LAPACK's interchanges would have given it (the top row that is not chosen takes the pivot's index, the pivot
+    // takes the column index and is done: neither searched nor updated any more).  Ties of |a| go to the smallest
+    // logical index (idamax on the interchanged matrix).  At the end every thread writes its row to row `pos`.
+    bool done = !has;
+    int pos = row;
     int buf = 0;
-    // positions > s + 1 of the live blocks: a -= l * prow
-    auto deferred = [&](auto sconst, int liveb) {
-        constexpr int sp = decltype(sconst)::value;              // sub-step whose update is pending
-        const double2* pr = reinterpret_cast<const double2*>(pprev);
-#pragma unroll
-        for (int c2 = 0; c2 < NB / 2; ++c2) {
-            if (2 * c2 + 1 > sp + 1 && (c2 >> 2) < liveb) {
-                const double2 pp = pr[c2];
-                if (2 * c2 > sp + 1) a[c2].x -= lprev * pp.x;
-                a[c2].y -= lprev * pp.y;
-            }
-        }
-    };
 #pragma unroll 1
     for (int g = 0; g < NB / 8; ++g) {
         const int liveb = NB / 8 - g;                            // live 8-position blocks
@@ -677,91 +688,71 @@ __global__ void __launch_bounds__(P2_THREADS) k_lu_panel_v2(int n, int k0, int n
             const int jj = 8 * g + sidx;
             if (jj < nb) {
                 const int col = k0 + jj;
-                const bool active = has && row >= col;
                 const double av = fabs(P2A(sidx));
                 const unsigned hi = (unsigned)__double2hiint(av), lo = (unsigned)__double2loint(av);
-                const int w = first_max_lane(hi, lo, active);
+                const int w = first_max_lane(hi, lo, pos, !done);
                 stamp(1);
-                if (DEFER && sidx > 0 && (lane == w || row == col)) {      // rows about to be published apply their pending part first
-                    if (pend) { deferred(std::integral_constant<int, (sidx > 0 ? sidx - 1 : 0)>{}, liveb); pend = false; }
-                }
-                if (lane == w) { s_khi[wid] = hi; s_klo[wid] = lo; s_idx[wid] = row; }
+                if (lane == w) { s_khi[wid] = hi; s_klo[wid] = lo; s_idx[wid] = pos; }
                 if (w < 0 && lane == 0) { s_khi[wid] = 0u; s_klo[wid] = 0u; s_idx[wid] = P2_NOROW; }
-                if (row == col) {                                // the top row (always rank 0, warp 0)
-                    double2* d = reinterpret_cast<double2*>(&s_old[0]);
-#pragma unroll
-                    for (int c = 0; c < NB / 2; ++c) d[c] = a[c];
-                }
                 stamp(2);
                 __syncthreads();
                 stamp(3);
-                // every warp finds the CTA's candidate; its owner alone writes the row to shared memory (16 warps
-                // writing their candidates speculatively cost 16 x 16 single-lane vector stores per column)
-                const bool l16 = lane < P2_WARPS;
+                // every warp finds the CTA's candidate; its owner alone writes the live part of its row to shared memory
+                const bool l16 = lane < WARPS;
                 const int myi = l16 ? s_idx[lane] : P2_NOROW;
                 const unsigned mhi = l16 ? s_khi[lane] : 0u, mlo = l16 ? s_klo[lane] : 0u;
-                const int ww = first_max_lane(mhi, mlo, myi != P2_NOROW);
-                const int crow = ww >= 0 ? s_idx[ww] : P2_NOROW;
-                if (has && row == crow) {
+                const int ww = first_max_lane(mhi, mlo, myi, myi != P2_NOROW);
+                if (wid == ww && lane == w) {
                     double2* d = reinterpret_cast<double2*>(&s_rows[0][0]);
 #pragma unroll
-                    for (int c = 0; c < NB / 2; ++c) d[c] = a[c];
+                    for (int c2 = 0; c2 < NB / 2; ++c2)
+                        if (2 * c2 + 1 > sidx && (c2 >> 2) < liveb) d[c2] = a[c2];
+                    s_ext[0] = __drcp_rn(P2A(sidx));
+                    s_ext[1] = av;
+                    s_ext[2] = __longlong_as_double((long long)pos);
                 }
+                if (ww < 0 && tid == 0) { s_ext[1] = 0.0; s_ext[2] = __longlong_as_double((long long)P2_NOROW); }   // no row left in this CTA
                 stamp(4);
                 __syncthreads();
-                if (wid < C) {                                   // warp p pushes the CTA's candidate to peer p
-                    P2Xchg* Xp = cl.map_shared_rank(&X, wid);
-                    if (ww < 0) {                                // no active row in this CTA
-                        if (lane == 0) { Xp->khi[buf][rank] = 0u; Xp->klo[buf][rank] = 0u; Xp->idx[buf][rank] = P2_NOROW; }
-                    } else if (lane == ww) {
-                        Xp->khi[buf][rank] = mhi; Xp->klo[buf][rank] = mlo; Xp->idx[buf][rank] = myi;
+                {
+                    const double rv = s_rows[0][lane], ev = s_ext[lane & 3];
+                    for (int peer = wid; peer < C; peer += WARPS) {          // warp p pushes the CTA's candidate to the peers p, p + WARPS, ...
+                        P2Xchg* Xp = cl.map_shared_rank(&X, peer);
+                        Xp->rows[buf][rank][lane] = rv;
+                        if (lane < 3) Xp->ext[buf][rank][lane] = ev;
                     }
-                    Xp->rows[buf][rank][lane] = s_rows[0][lane];
-                    if (rank == 0) Xp->old[buf][lane] = s_old[lane];
-                    if (lane == 0) Xp->rcp[buf][rank] = __drcp_rn(s_rows[0][sidx]);
                 }
                 stamp(5);
                 __syncwarp();
                 cluster_arrive();
-                if (sidx > 0) { if (pend) { deferred(std::integral_constant<int, (sidx > 0 ? sidx - 1 : 0)>{}, liveb); pend = false; } }
-                __syncwarp();
                 cluster_wait();
                 stamp(6);
                 const bool lc = lane < C;
-                const int cli = lc ? X.idx[buf][lane] : P2_NOROW;
-                const int pw = first_max_lane(lc ? X.khi[buf][lane] : 0u, lc ? X.klo[buf][lane] : 0u, cli != P2_NOROW);
-                const int piv = X.idx[buf][pw];
+                const double ck = lc ? X.ext[buf][lane][1] : 0.0;
+                const int cli = lc ? (int)__double_as_longlong(X.ext[buf][lane][2]) : P2_NOROW;
+                const int pw = first_max_lane((unsigned)__double2hiint(ck), (unsigned)__double2loint(ck), cli, cli != P2_NOROW);
+                const int pivpos = (int)__double_as_longlong(X.ext[buf][pw][2]);     // LAPACK's pivot index of this column
                 const double* prow = X.rows[buf][pw];
                 stamp(7);
-                if (piv != col && has && (row == piv || row == col)) {       // the two rows of the interchange
-                    const double2* sp = reinterpret_cast<const double2*>(row == piv ? &X.old[buf][0] : prow);
-#pragma unroll
-                    for (int c = 0; c < NB / 2; ++c) a[c] = sp[c];
+                if (rank == 0 && tid == 0) { ipiv[col] = pivpos + 1; s_piv[jj] = pivpos; }
+                if (!done) {
+                    if (pos == pivpos) { done = true; pos = col; }           // the pivot row: U row `col`, frozen
+                    else if (pos == col) pos = pivpos;                       // the displaced top row
                 }
-                if (rank == 0 && tid == 0) { ipiv[col] = piv + 1; s_piv[jj] = piv; }
-                if (has && row > col) {
-                    const double lm = P2A(sidx) * X.rcp[buf][pw];
+                if (!done) {
+                    const double lm = P2A(sidx) * X.ext[buf][pw][0];
                     P2A(sidx) = lm;
-                    if constexpr (DEFER) {
-                        if (((sidx + 1) >> 3) < liveb) P2A(sidx + 1) -= lm * prow[sidx + 1];   // the next column (position 8 = column 0 of the next group; in the last group it holds a finished multiplier)
-                        lprev = lm;
-                        pend = true;
-                    } else {
-                        const double2* pr = reinterpret_cast<const double2*>(prow);
+                    const double2* pr = reinterpret_cast<const double2*>(prow);
 #pragma unroll
-                        for (int c2 = 0; c2 < NB / 2; ++c2) {
-                            if (2 * c2 + 1 > sidx && (c2 >> 2) < liveb) {
-                                const double2 pp = pr[c2];
-                                if (2 * c2 > sidx) a[c2].x -= lm * pp.x;
-                                a[c2].y -= lm * pp.y;
-                            }
+                    for (int c2 = 0; c2 < NB / 2; ++c2) {
+                        if (2 * c2 + 1 > sidx && (c2 >> 2) < liveb) {
+                            const double2 pp = pr[c2];
+                            if (2 * c2 > sidx) a[c2].x -= lm * pp.x;
+                            a[c2].y -= lm * pp.y;
                         }
                     }
-                } else {
-                    pend = false;
                 }
-                pprev = prow;
-                buf = buf == 2 ? 0 : buf + 1;
+                buf ^= 1;
                 stamp(8);
             }
         };
@@ -770,7 +761,6 @@ __global__ void __launch_bounds__(P2_THREADS) k_lu_panel_v2(int n, int k0, int n
         substep(std::integral_constant<int, 4>{}); substep(std::integral_constant<int, 5>{});
         substep(std::integral_constant<int, 6>{}); substep(std::integral_constant<int, 7>{});
         {
-            if (pend) { deferred(std::integral_constant<int, 7>{}, liveb); pend = false; }   // the group's last column, before the rotation
             double2 t[4];                                        // rotate by 8: this group's multipliers go to the back
 #pragma unroll
             for (int c = 0; c < 4; ++c) t[c] = a[c];
@@ -784,7 +774,7 @@ __global__ void __launch_bounds__(P2_THREADS) k_lu_panel_v2(int n, int k0, int n
     if (has) {                                                   // four rotations by 8: position p holds column p again
 #pragma unroll
         for (int c = 0; c < NB; ++c)
-            if (c < nb) A[(size_t)(k0 + c) * n + row] = P2A(c);
+            if (c < nb) A[(size_t)(k0 + c) * n + pos] = P2A(c);
     }
     // ---- net permutation of this panel's interchanges for the wide update: rows touched = the top block rows and the
     // distinct pivot rows below it; each takes the value of the row its index maps back to
@@ -811,29 +801,35 @@ __global__ void __launch_bounds__(P2_THREADS) k_lu_panel_v2(int n, int k0, int n
         }
     }
     stamp(10);
-    if (trace && threadIdx.x == 0 && blockIdx.x == 0) { for (int i = 0; i < 11; ++i) trace[i] += s_tr[i]; }
+    if (trace && threadIdx.x == 0 && blockIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) trace[i] += s_tr[i];
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        trace[17 + 2 * (k0 / NB)] = (long long)t;
+    }
     cl.sync();                                                   // no CTA leaves while a peer may still write its shared memory
 }
 #undef P2A
 
-static int launch_panel_v2(int n, int k0, int nb, double* A, int* ipiv, int pk0, int pnb, int* perm, long long* trace, cudaStream_t st) {
+static int launch_panel_v2(int n, int k0, int nb, double* A, int* ipiv, int pk0, int pnb, int* perm, double* uscr, long long* trace, cudaStream_t st) {
     const int rows = n - k0;
+    // 256 threads per CTA whenever 16 CTAs hold the rows: twice as many SMs share the per-row work (the rank-32 update
+    // of the fused narrow update is bound by the FP64 pipes of the cluster's SMs) and the block barriers see 8 warps
+    static const int tpb_env = getenv("ILM_LU_PANEL_TPB") ? atoi(getenv("ILM_LU_PANEL_TPB")) : 0;
+    const int tpb = tpb_env == 512 ? 512 : (rows <= P2_MAXC * 256 ? 256 : 512);
     int C = 1;
-    while (C * P2_THREADS < rows) C *= 2;
+    while (C * tpb < rows) C *= 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C);
-    cfg.blockDim = dim3(P2_THREADS);
+    cfg.blockDim = dim3(tpb);
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    static const bool defer = getenv("ILM_LU_DEFER") != nullptr;     // deferred row update inside the cluster barrier (measured slower: the
-    if (defer)                                                       // rows about to be published must apply it early, in divergent code)
-        ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<true>, n, k0, nb, A, ipiv, pk0, pnb, perm, trace));
-    else
-        ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<false>, n, k0, nb, A, ipiv, pk0, pnb, perm, trace));
+    if (tpb == 256) ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<256>, n, k0, nb, A, ipiv, pk0, pnb, perm, uscr, trace));
+    else ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<512>, n, k0, nb, A, ipiv, pk0, pnb, perm, uscr, trace));
     return ILM_OK;
 }
 
@@ -1277,6 +1273,7 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
             cudaStream_t hi = nullptr, lo = nullptr;
             cudaEvent_t begin = nullptr, evP = nullptr, evW = nullptr, end = nullptr, evW2[2] = {nullptr, nullptr};
             int* perm = nullptr; size_t perm_cap = 0;               // net permutations of the panels (k_lu_panel_v2 -> k_lu_swap_trsm)
+            double* uscr = nullptr;                                 // 2 x (32 x 32) block rows in flight inside the panel kernels
         };
         static Aux aux_dev[64];
         int dev = 0;
@@ -1293,6 +1290,7 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
             ILM_CUDA(cudaEventCreateWithFlags(&ax.end, cudaEventDisableTiming));
             ILM_CUDA(cudaEventCreateWithFlags(&ax.evW2[0], cudaEventDisableTiming));
             ILM_CUDA(cudaEventCreateWithFlags(&ax.evW2[1], cudaEventDisableTiming));
+            ILM_CUDA(cudaMalloc(&ax.uscr, 2 * NB * NB * sizeof(double)));
         }
         const cudaStream_t user = st;
         ILM_CUDA(cudaEventRecord(ax.begin, user));
@@ -1300,11 +1298,11 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
         ILM_CUDA(cudaStreamWaitEvent(ax.lo, ax.begin, 0));
         bool wide_pending = false;
         static const bool v1 = getenv("ILM_LU_V1") != nullptr;        // the separate narrow-update launches (first round-2 form)
-        if (!v1 && n <= P2_MAXC * P2_THREADS) {
+        if (!v1 && n <= P2_MAXC * 512) {
             // Second form: the panel kernel applies the previous panel's update to its own 32 columns (k_lu_panel_v2);
             // the wide update is two launches (net permutation + block row, rank-32 DMMA update) on the low-priority stream.
-            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             const int npan = (n + NB - 1) / NB;
             if (ax.perm_cap < (size_t)npan * PERM_STRIDE) {
                 ILM_CUDA(cudaStreamSynchronize(ax.hi));
@@ -1316,7 +1314,8 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
             }
             static const bool want_trace = getenv("ILM_LU_TRACE") != nullptr;
             long long* trace = nullptr;
-            if (want_trace) { ILM_CUDA(cudaMalloc(&trace, 16 * sizeof(long long))); ILM_CUDA(cudaMemsetAsync(trace, 0, 16 * sizeof(long long), ax.hi)); }
+            const size_t ntrace = 16 + 2 * (size_t)npan;
+            if (want_trace) { ILM_CUDA(cudaMalloc(&trace, ntrace * sizeof(long long))); ILM_CUDA(cudaMemsetAsync(trace, 0, ntrace * sizeof(long long), ax.hi)); }
             int pk0 = 0, pnb = 0;
             for (int k0 = 0, ip = 0; k0 < n; k0 += NB, ++ip) {
                 const int nb = n - k0 < NB ? n - k0 : NB, k1 = k0 + nb;
@@ -1325,7 +1324,7 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
                 // this panel's columns were last touched by the wide update of step k-2 (step k-1 excluded them: they get that
                 // update inside the panel kernel), so the panel runs beside the wide update of step k-1
                 if (ip >= 2) ILM_CUDA(cudaStreamWaitEvent(ax.hi, ax.evW2[ip & 1], 0));
-                ILM_TRY(launch_panel_v2(n, k0, nb, dA, dP, pk0, pnb, perm, trace, ax.hi));
+                ILM_TRY(launch_panel_v2(n, k0, nb, dA, dP, pk0, pnb, perm, ax.uscr + (size_t)(ip & 1) * NB * NB, trace, ax.hi));
                 g_dense_launches++;
                 ILM_CUDA(cudaEventRecord(ax.evP, ax.hi));
                 ILM_CUDA(cudaStreamWaitEvent(ax.lo, ax.evP, 0));
@@ -1347,13 +1346,26 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
             st = user;
             ILM_CUDA(cudaGetLastError());
             if (trace) {
-                long long h[16];
+                std::vector<long long> hv(ntrace);
+                long long* h = hv.data();
                 ILM_CUDA(cudaStreamSynchronize(user));
-                ILM_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+                ILM_CUDA(cudaMemcpy(h, trace, ntrace * sizeof(long long), cudaMemcpyDeviceToHost));
                 cudaFree(trace);
-                static const char* nm[11] = {"narrow update (per panel)", "argmax warp", "keys + top row -> smem", "block barrier", "argmax CTA + row -> smem", "barrier + push + rcp",
-                                             "cluster barrier", "argmax cluster", "interchange + update", "rotations (per panel)", "write-back + perm (per panel)"};
+                {
+                    double dur = 0, gap = 0;
+                    for (int i = 0; i < npan; ++i) dur += (double)(h[17 + 2 * i] - h[16 + 2 * i]);
+                    for (int i = 1; i < npan; ++i) gap += (double)(h[16 + 2 * i] - h[15 + 2 * i]);
+                    fprintf(stderr, "ilm LU timeline: panel kernels %.1f us each, gap between panel kernels %.1f us, first entry to last exit %.3f ms\n",
+                            dur / npan * 1e-3, npan > 1 ? gap / (npan - 1) * 1e-3 : 0.0, (double)(h[17 + 2 * (npan - 1)] - h[16]) * 1e-6);
+                    for (int i = 0; i < npan; i += npan / 8 > 0 ? npan / 8 : 1)
+                        fprintf(stderr, "   panel %3d: %.1f us, gap before %.1f us\n", i, (double)(h[17 + 2 * i] - h[16 + 2 * i]) * 1e-3,
+                                i ? (double)(h[16 + 2 * i] - h[15 + 2 * i]) * 1e-3 : 0.0);
+                }
+                static const char* nm[11] = {"(stamp slot 0)", "argmax warp", "keys -> smem", "block barrier", "argmax CTA + row -> smem", "barrier + push",
+                                             "cluster barrier", "argmax cluster", "update", "rotations (per panel)", "write-back + perm (per panel)"};
                 fprintf(stderr, "ilm LU trace, n = %d, %d panels (clock cycles seen by thread 0 of CTA 0):\n", n, npan);
+                fprintf(stderr, "  narrow update: U block row (warp 0) + row loads %.0f, wait for U %.0f, push + cluster barrier %.0f, rank-32 update %.0f cycles per panel\n",
+                        (double)h[11] / npan, (double)h[12] / npan, (double)h[13] / npan, (double)h[14] / npan);
                 for (int i = 0; i < 11; ++i) {
                     const bool per_panel = i == 0 || i >= 9;
                     fprintf(stderr, "  %-32s %10.1f cycles %s\n", nm[i], (double)h[i] / (per_panel ? npan : n), per_panel ? "per panel" : "per column");
