@@ -72,6 +72,8 @@ struct ProbeGather {
     const double* w;       // interpolation weights [k][b][a]
     int W, mx, my;
     double2* part;         // null = store the rows (every other caller)
+    const unsigned short* need;   // my x (Lx/16) column masks: bit e of need[row*T + j] = column j + e*T is read by a window
+                                  // (null = every column); threads / warps without a needed column skip the last pass
 };
 
 struct ConvArgs {
@@ -364,18 +366,39 @@ ILM_HD void passC_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, in
                 ctx.tma_load_rows(a, px, step_row0(s + 1), F, L, C::XBUF, xgrp, mbar);
             }
         }
-        fft_last_pass<L, true>(v, tw, j);
+        // probe path with a column mask: only the columns under the interpolation windows are formed.  A warp none of
+        // whose threads owns such a column skips the last butterfly pass (a third of the transform's FP64 work), and the
+        // odd -> even hand-off touches the needed entries only.
+        unsigned need = 0xffffu;
+        bool skip_last = false;
+        if (a.eg.part && a.eg.need) {
+            need = (live && row < a.eg.my) ? a.eg.need[(size_t)row * T + j] : 0u;
+            skip_last = !ctx.any(need != 0u);
+        }
+        if (!skip_last) fft_last_pass<L, true>(v, tw, j);
         if (px) {
             ctx.wait(BAR_FREE);
+            if (need == 0xffffu) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) comb[j + e * T] = cmulc(v[e], mod_fwd<L>(tw, j, e));
+                for (int e = 0; e < 16; ++e) comb[j + e * T] = cmulc(v[e], mod_fwd<L>(tw, j, e));
+            } else if (need) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if ((need >> e) & 1u) comb[j + e * T] = cmulc(v[e], mod_fwd<L>(tw, j, e));
+            }
             ctx.arrive(BAR_READY);
         } else if (a.eg.part) {
             // probe path: the finished row stays in the combine buffer and is gathered by the points whose
             // interpolation windows cross it (same term order inside a window row as the oracle: a ascending)
             ctx.wait(BAR_READY);
+            if (need == 0xffffu) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { const int n = j + e * T; comb[n] = cadd(v[e], comb[n]); }
+                for (int e = 0; e < 16; ++e) { const int n = j + e * T; comb[n] = cadd(v[e], comb[n]); }
+            } else if (need) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if ((need >> e) & 1u) { const int n = j + e * T; comb[n] = cadd(v[e], comb[n]); }
+            }
             ctx.sync();
             if (live && row < a.eg.my) {
                 const int W = a.eg.W;

@@ -15,6 +15,14 @@ struct DevCtx {
         asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
 #endif
     }
+    // true if the predicate holds for any thread of the calling warp
+    ILM_HD bool any(bool pred) {
+#ifdef __CUDA_ARCH__
+        return __any_sync(0xffffffffu, pred) != 0;
+#else
+        return pred;
+#endif
+    }
     ILM_HD void sync_cta() {
 #ifdef __CUDA_ARCH__
         __syncthreads();

@@ -58,6 +58,9 @@ struct DevTable {
     double2* part = nullptr;    // PART_BATCH x (N*W) row sums: one slice per column pair in flight (the post sum of a
                                 // Schur build runs once per PART_BATCH pairs, not once per pair)
     size_t part_stride = 0;     // complex entries per slice
+    unsigned short* need = nullptr;   // my x need_T words: the columns of each row that some window reads (pass C prunes by it)
+    size_t cap_need = 0;
+    int need_T = 0;
     size_t cap_rows = 0, cap_rowent = 0;
     size_t cap_pts = 0, cap_cells = 0, cap_ents = 0;   // allocated capacities (a moving body refreshes the tables every step)
 };
@@ -112,6 +115,7 @@ struct ilm_plan {
     const void* tmap_base = nullptr;
     int skew_ns = 500;              // ILM_CONV_SKEW_NS: start-up skew between the two groups of a CTA
     bool band = true;               // ILM_PROBE_BAND=0 sends the Schur probes through the transform column pass instead
+    bool prune_c = true;            // ILM_PROBE_PRUNE_C=0: pass C of the probes forms every column of the window rows
     bool patch = true;              // ILM_PROBE_PATCH=0: create_RTLinvR probes write R e_c to the grid and run pass A (round-2 first form)
     bool fuse_e = true;             // ILM_PROBE_FUSE_E=0: pass C stores the probed rows and a separate kernel interpolates
     std::vector<ilm::ConvKernel> kernels;

@@ -6,7 +6,10 @@
 // its <=4x4 window, and the host builds the per-cell gather list (sorted by
 // cell, then by point index) that makes regularization an atomics-free gather.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -39,7 +42,7 @@ __global__ void k_point_tables(int N, const double* __restrict__ x, const double
 void free_table(DevTable& t) {
     cudaFree(t.i0); cudaFree(t.j0); cudaFree(t.wR); cudaFree(t.wE);
     cudaFree(t.cell_idx); cudaFree(t.cell_off); cudaFree(t.ent); cudaFree(t.rowsum);
-    cudaFree(t.row_ptr); cudaFree(t.row_ent); cudaFree(t.part);
+    cudaFree(t.row_ptr); cudaFree(t.row_ent); cudaFree(t.part); cudaFree(t.need);
     t = DevTable();
 }
 
@@ -69,6 +72,10 @@ static void sort_by_cell(std::vector<int>& cell, std::vector<int>& id, std::vect
 }
 
 int build_tables(ilm_plan* p) {
+    static const bool ttrace = getenv("ILM_TABLE_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(now() - t0).count(); };
+    const auto t_begin = now();
     const int N = p->N;
     const int W = ddf_width(p->ddf), W2 = W * W;
     const size_t np = (size_t)(N > 0 ? N : 1);
@@ -101,10 +108,11 @@ int build_tables(ilm_plan* p) {
         }
     }
     ILM_CUDA(cudaStreamSynchronize(p->stream));
+    const double t_phase1 = ms_since(t_begin);
     // phase 2: gather lists (cell, k, slot) for every in-range window entry, sorted by cell then k.  Pure host work per
     // layout (entry generation, radix sort, run detection): the four layouts are built by four host threads, the uploads
     // follow in layout order.
-    struct HostLists { std::vector<int> id, cell_idx, cell_off, rptr, rent; };
+    struct HostLists { std::vector<int> id, cell_idx, cell_off, rptr, rent; std::vector<unsigned short> need; };
     HostLists lists[4];
     auto build_layout = [&](int layout) {
         HostLists& h = lists[layout];
@@ -138,6 +146,20 @@ int build_tables(ilm_plan* p) {
             std::vector<int> fill(h.rptr.begin(), h.rptr.end() - 1);
             for (int k = 0; k < N; ++k)
                 for (int b = 0; b < W; ++b) { const int j = yj[k] + b; if (j >= 0 && j < li.my) h.rent[fill[j]++] = k * W + b; }
+            // columns of every row that some window reads, as one 16-bit word per transform thread: in pass C thread j of a
+            // length-L inverse transform ends up with the columns j + e*T (T = L/16), bit e of need[row*T + j] says whether
+            // column j + e*T is read.  Threads (warps) without a needed column skip the last butterfly pass and the hand-off.
+            const int T = p->Lx / 16;
+            h.need.assign((size_t)li.my * T, 0);
+            for (int k = 0; k < N; ++k)
+                for (int b = 0; b < W; ++b) {
+                    const int j = yj[k] + b;
+                    if (j < 0 || j >= li.my) continue;
+                    for (int a = 0; a < W; ++a) {
+                        const int i = xi[k] + a;
+                        if (i >= 0 && i < li.mx) h.need[(size_t)j * T + i % T] |= (unsigned short)(1u << (i / T));
+                    }
+                }
         }
     };
     {
@@ -146,6 +168,7 @@ int build_tables(ilm_plan* p) {
         build_layout(0);
         for (auto& w : workers) w.join();
     }
+    const double t_phase2 = ms_since(t_begin);
     for (int layout = 0; layout < 4; ++layout) {
         DevTable& t = p->tab[layout];
         HostLists& h = lists[layout];
@@ -188,11 +211,20 @@ int build_tables(ilm_plan* p) {
                 t.part_stride = cap;
                 t.cap_rowent = cap;
             }
+            if (h.need.size() > t.cap_need || !t.need) {
+                cudaFree(t.need); t.need = nullptr;
+                ILM_CUDA(cudaMalloc(&t.need, h.need.size() * sizeof(unsigned short) + 16));
+                t.cap_need = h.need.size();
+            }
+            t.need_T = p->Lx / 16;
+            if (!h.need.empty()) ILM_CUDA(cudaMemcpyAsync(t.need, h.need.data(), h.need.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, p->stream));
             ILM_CUDA(cudaMemcpyAsync(t.row_ptr, h.rptr.data(), h.rptr.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
             if (!h.rent.empty()) ILM_CUDA(cudaMemcpyAsync(t.row_ent, h.rent.data(), h.rent.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         }
     }
     ILM_CUDA(cudaStreamSynchronize(p->stream));
+    if (ttrace) fprintf(stderr, "ilm table refresh, N = %d: window tables + D2H %.3f ms, host lists %.3f ms, uploads %.3f ms\n", N, t_phase1,
+                        t_phase2 - t_phase1, ms_since(t_begin) - t_phase2);
     return ILM_OK;
 }
 

@@ -39,6 +39,7 @@ struct HostCtx {
     void cluster_sync() { if (clb) clb->wait(); }
     void sync() { gb->wait(); }
     void sync_cta() { cb->wait(); }
+    bool any(bool) { return true; }          // a warp never skips in the emulation
     void arrive(int id) { named[id].arrive(); }
     void wait(int id) { named[id].wait(); }
     void delay(int) {}
