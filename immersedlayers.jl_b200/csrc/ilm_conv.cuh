@@ -72,7 +72,7 @@ struct ProbeGather {
     const double* w;       // interpolation weights [k][b][a]
     int W, mx, my;
     double2* part;         // null = store the rows (every other caller)
-    const unsigned short* need;   // my x (Lx/16) column masks: bit e of need[row*T + j] = column j + e*T is read by a window
+    const unsigned* need;         // my x (Lx/16) column masks: bit e of need[row*T + j] = column j + e*T is read by a window
                                   // (null = every column); threads / warps without a needed column skip the last pass
 };
 

@@ -58,9 +58,14 @@ struct DevTable {
     double2* part = nullptr;    // PART_BATCH x (N*W) row sums: one slice per column pair in flight (the post sum of a
                                 // Schur build runs once per PART_BATCH pairs, not once per pair)
     size_t part_stride = 0;     // complex entries per slice
-    unsigned short* need = nullptr;   // my x need_T words: the columns of each row that some window reads (pass C prunes by it)
+    unsigned* need = nullptr;   // my x need_T words: the columns of each row that some window reads (pass C prunes by it)
     size_t cap_need = 0;
     int need_T = 0;
+    // scratch of the device list build (k_build_lists): ping-pong key / value buffers of the cell sort and of the row sort
+    unsigned* skey[2] = {nullptr, nullptr}; int* sval[2] = {nullptr, nullptr};
+    unsigned* rkey[2] = {nullptr, nullptr}; int* rval[2] = {nullptr, nullptr};
+    size_t cap_sort = 0;
+    int* dcounts = nullptr;     // [ncell, nent, row runs, row entries]
     size_t cap_rows = 0, cap_rowent = 0;
     size_t cap_pts = 0, cap_cells = 0, cap_ents = 0;   // allocated capacities (a moving body refreshes the tables every step)
 };

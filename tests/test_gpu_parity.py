@@ -637,6 +637,37 @@ def test_probe_pairs_off_the_band_path_inside_a_build(cols):
         assert relerr(S, oc.create_RTLinvR(cols=list(range(*cols)))) < RTOL
 
 
+@pytest.mark.parametrize("ddf", ["yang3", "m4prime"])
+def test_device_list_build_equals_host_build(ddf, monkeypatch):
+    """The gather lists (cell buckets, row buckets, column mask of pass C) are built by a radix sort on the device;
+    ILM_TABLES_HOST=1 keeps the host build.  Same lists -> bit-equal regularization fields and Schur complements,
+    also for windows clipped at the boundary and after a refresh with moved points."""
+    g = ilm.PhysicalGrid(91, 67, 4.0 / 89, (45, 33))
+    x, y, nx, ny, ds = ilm.bodies.circle(1.0, 1.4 * g.dx)
+    body = (x + 0.93, y - 0.4, nx, ny, ds)
+    G = ilm.lgf.lgf_table(96)
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal(len(x))
+    out = {}
+    for mode in ("device", "host"):
+        if mode == "host":
+            monkeypatch.setenv("ILM_TABLES_HOST", "1")
+        else:
+            monkeypatch.delenv("ILM_TABLES_HOST", raising=False)
+        cache = ilm.SurfaceScalarCache(body, g, lgf_table=G, ddftype=ddf)
+        fs = cache.zeros_surface(); fs.data[:] = f
+        w = cache.zeros_grid(); ilm.regularize(w, fs, cache)
+        q = cache.zeros_gridgrad(); ilm.regularize_normal(q, fs, cache)
+        S = np.asarray(ilm.create_RTLinvR(cache))
+        Cf = np.asarray(ilm.create_surface_filter(cache))
+        cache.update_points((x + 0.5, y - 0.1, nx, ny, ds))
+        w2 = cache.zeros_grid(); ilm.regularize(w2, fs, cache)
+        S2 = np.asarray(ilm.create_RTLinvR(cache, cols=(0, 11)))
+        out[mode] = [np.asarray(w.data).copy(), np.asarray(q.data).copy(), S, Cf, np.asarray(w2.data).copy(), S2]
+    for a, b in zip(out["device"], out["host"]):
+        assert np.array_equal(a, b)
+
+
 # ---------------------------------------------------------------- whole-problem entry point (ilm_dirichlet_poisson)
 @pytest.mark.parametrize("device", [False, True])
 def test_dirichlet_solve_single_call(device):
