@@ -98,6 +98,8 @@ struct ConvArgs {
     int wlo, whi;          // pass B visits the work items [wlo, whi) only (slab decomposition: the x-frequency
                            // columns this GPU owns); whi <= 0 = all of them
     ProbeGather eg;        // fused interpolation in pass C (Schur probes)
+    double2* bigA;         // hand-off block of the split big column pass (ilm_conv_big.cuh): [column - bc0][p][n1][kappa]
+    int bc0, bnc;          // ... for the columns [bc0, bc0 + bnc)
     int s2_rowmajor;       // S2 holds the output rows [olo, ohi) row by row, [row - olo][px][m] (written by the band
                            // pass of the Schur probes, ilm_band.cu): both that pass and pass C then stream whole rows
 };

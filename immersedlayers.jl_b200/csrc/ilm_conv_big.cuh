@@ -214,6 +214,144 @@ ILM_HD void passB_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int clust
     }
 }
 
+// ---------------------------------------------------------------- pass B split in two kernels (the default)
+// The cluster form above couples Q CTAs through two cluster barriers per column and exposes every latency of a column
+// (decimated loads, hand-off line, multiplier) to all of them: at 16384^2 it runs at 17 % issue utilisation, 50 %
+// long-scoreboard stalls.  Here the two halves are separate kernels over independent work items (column, residue):
+//   B1  A_{n1,p}[kappa] = FFT_M( x[n1 + Q n2] w_2M^{n2 p} )[kappa]        -> bigA[col - c0][p][n1][kappa]
+//   B2  the Q x Q filter per frequency and the inverse half transform of residue n1' (as above)  -> S2
+// for a chunk [c0, c0 + nc) of columns at a time, sized so that its hand-off block (nc * 2L complex) stays L2-resident
+// between the two launches.  The 2Q items of a tile run on neighbouring CTAs at the same time, so the 128-byte lines of
+// the tile (16 bytes per item) come from DRAM once.
+template <int Q, class Ctx>
+ILM_HD void passB1_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, int nblocks) {
+    using C = FftCfg<BIG_M>;
+    constexpr int T = C::T;
+    double2* tw = smem + C::TW_BASE;
+    load_twiddles<BIG_M>(ctx, tw, a.twy);
+    const int j = ctx.tid, py = ctx.grp;
+    double2* xb = smem + ctx.grp * C::GROUP_XBUF;
+    const int Lb = a.g.Ly;
+    const int nitems = a.bnc * Q;
+    for (int it = block; it < nitems; it += nblocks) {
+        const int c = a.bc0 + it / Q, rank = it % Q;
+        const int px = c / a.g.Lx, m = c % a.g.Lx;
+        const int itn = it + nblocks;                              // L2 prefetch: this item's eighth of the tile of the next item
+        if (itn < nitems && a.rhi - a.rlo == a.g.MYp) {
+            const int cn = a.bc0 + itn / Q;
+            const size_t share = (size_t)2 * a.g.MYp * sizeof(double2) / (2 * Q);
+            const char* sp = reinterpret_cast<const char*>(a.S + (size_t)(cn >> 1) * 2 * a.g.MYp) + (size_t)((cn & 1) * Q + itn % Q) * share;
+            for (size_t off = (size_t)(ctx.grp * 256 + j) * 128; off < share; off += 512 * 128) ctx.prefetch_l2(sp + off);
+        }
+        double2 v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int n = rank + Q * (j + e * T);
+            const double2 x = (n >= a.rlo && n < a.rhi) ? a.S[s_index(a.g, px, m, n)] : cmk(0.0, 0.0);
+            v[e] = py ? cmul(x, mod_fwd<BIG_M>(tw, j, e)) : x;
+        }
+        fft_regs<BIG_M, false>(v, ctx, xb, tw, j);
+        double2* dst = a.bigA + ((size_t)(c - a.bc0) * 2 + py) * (size_t)Lb + (size_t)rank * BIG_M;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dst[j + e * T] = v[e];
+    }
+}
+
+// FILTERED: the Q x Q filter was applied in place by k_big_filter (a streaming kernel at full occupancy; inside this
+// kernel the 8 dependent loads per frequency are exposed 16 times per item: 72 % long-scoreboard stalls), the hand-off
+// block then holds U_{n1'}[k2] at [p][n1'][kappa] and an item loads its 16 entries per thread like any half transform.
+template <int Q, bool FILTERED, class Ctx>
+ILM_HD void passB2_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block, int nblocks) {
+    using C = FftCfg<BIG_M>;
+    constexpr int T = C::T;
+    double2* tw = smem + C::TW_BASE;
+    load_twiddles<BIG_M>(ctx, tw, a.twy);
+    const int j = ctx.tid, py = ctx.grp;
+    double2* xb = smem + ctx.grp * C::GROUP_XBUF;
+    double2* comb = smem + 2 * C::GROUP_XBUF;
+    const int Lb = a.g.Ly;
+    const unsigned mask = 2u * (unsigned)Lb - 1u;
+    const int nitems = a.bnc * Q;
+    const double2 wbase = a.wl2y[(2u * (unsigned)j + (unsigned)py) & mask];
+    if (!py) ctx.arrive(BAR_FREE);
+    for (int it = block; it < nitems; it += nblocks) {
+        const int c = a.bc0 + it / Q, rank = it % Q;
+        const int px = c / a.g.Lx, m = c % a.g.Lx;
+        const size_t gbase = ((size_t)ghat_col(a.g, px, m) * 2 + py) * (size_t)Lb;
+        const int itn = it + nblocks;                              // L2 prefetch of the next item's multiplier share
+        if (!FILTERED && itn < nitems) {
+            const int cn = a.bc0 + itn / Q;
+            const char* gp = reinterpret_cast<const char*>(a.Ghat + ((size_t)ghat_col(a.g, cn / a.g.Lx, cn % a.g.Lx) * 2 + py) * (size_t)Lb) +
+                             (size_t)(itn % Q) * BIG_M * sizeof(double);
+            for (size_t off = (size_t)j * 128; off < BIG_M * sizeof(double); off += 256 * 128) ctx.prefetch_l2(gp + off);
+        }
+        const double2* scr = a.bigA + ((size_t)(c - a.bc0) * 2 + py) * (size_t)Lb;
+        double2 v[16];
+        if constexpr (FILTERED) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = scr[(size_t)rank * BIG_M + j + e * T];
+        } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int kappa = j + e * T;
+            double2 wp[Q];                                // wp[n1] = w_2L^{n1 k2}, k2 = 2 kappa + py
+            if constexpr (Q == 2) {
+                wp[1] = a.wl2y[(2u * (unsigned)kappa + (unsigned)py) & mask];
+            } else {
+                wp[1] = e ? cmul(wbase, wstep<Q>(e)) : wbase;
+                wp[2] = cmul(wp[1], wp[1]); wp[3] = cmul(wp[2], wp[1]);
+            }
+            double2 t[Q];
+            t[0] = scr[kappa];
+#pragma unroll
+            for (int n1 = 1; n1 < Q; ++n1) t[n1] = cmul(scr[(size_t)n1 * BIG_M + kappa], wp[n1]);
+            radixq_fwd<Q>(t);                             // t[k1] = Z[k2 + 2M k1]
+            double2 s = cmk(0.0, 0.0);
+#pragma unroll
+            for (int k1 = 0; k1 < Q; ++k1) {
+                const double gh = a.Ghat[gbase + kappa + (size_t)BIG_M * k1];
+                s = cadd(s, rotq<Q>(cmk(t[k1].x * gh, t[k1].y * gh), rank * k1));
+            }
+            v[e] = rank ? cmulc(s, wp[rank]) : s;
+        }
+        }
+        fft_regs<BIG_M, true>(v, ctx, xb, tw, j);
+        if (py) {
+            ctx.wait(BAR_FREE);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) comb[j + e * T] = cmulc(v[e], mod_fwd<BIG_M>(tw, j, e));
+            ctx.arrive(BAR_READY);
+        } else {
+            ctx.wait(BAR_READY);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int n = rank + Q * (j + e * T);
+                if (n >= a.olo && n < a.ohi) a.S2[s_index(a.g, px, m, n)] = cadd(v[e], comb[j + e * T]);
+            }
+            ctx.arrive(BAR_FREE);
+        }
+    }
+}
+
+// the Q x Q filter of one frequency, in place: t[n1] = A_{n1,p}[kappa]  ->  t[n1'] = U_{n1'}[k2], k2 = 2 kappa + p
+//     Z[k2 + 2M k1] = sum_{n1} w_2L^{n1 k2} e^{-2 pi i n1 k1 / Q} A_{n1},   U_{n1'} = conj(w_2L^{n1' k2}) sum_{k1} Ghat[k2 + 2M k1] Z[..] e^{+2 pi i n1' k1 / Q}
+// (same operations, same order as the in-kernel filter above: bit-identical results)
+template <int Q> ILM_HD void big_filter_point(double2* t, const double* gh, const double2* wp) {
+#pragma unroll
+    for (int n1 = 1; n1 < Q; ++n1) t[n1] = cmul(t[n1], wp[n1]);
+    radixq_fwd<Q>(t);
+    double2 z[Q];
+#pragma unroll
+    for (int k1 = 0; k1 < Q; ++k1) z[k1] = cmk(t[k1].x * gh[k1], t[k1].y * gh[k1]);
+#pragma unroll
+    for (int r = 0; r < Q; ++r) {
+        double2 s = cmk(0.0, 0.0);
+#pragma unroll
+        for (int k1 = 0; k1 < Q; ++k1) s = cadd(s, rotq<Q>(z[k1], r * k1));
+        t[r] = r ? cmulc(s, wp[r]) : s;
+    }
+}
+
 // ---------------------------------------------------------------- pass C (rows, inverse), one CTA per (row, residue)
 // Used for Q = 2 (measured faster there than the cluster version below: 2.17 vs 2.80 ms at 8192^2).
 // work item = (row, n1); group p inverts the half with k2 = 2 kappa + p; group 0 combines and stores

@@ -110,6 +110,8 @@ struct ilm_plan {
     double2* wl2y = nullptr;        // exp(-2 pi i n / (2 Ly)) table for the sparse forward transform
     double2* wl2x = nullptr;        // same for x (ilm_conv_big.cuh; patch mode of the band pass)
     double2* conv_scratch = nullptr; // per-CTA hand-off lines of the big column pass (Ly > 4096)
+    double2* bigA = nullptr;         // hand-off block of the split big column pass: big_chunk columns x 2 Ly complex
+    int big_chunk = 0;               // columns per chunk (ILM_BIG_CHUNK; 0 = the cluster form of the column pass)
     double2 *S = nullptr, *S2 = nullptr;   // full spectrum buffers: allocated on first use (conv_ensure_spectrum), so a plan that
     size_t s_cap = 0;                      // only runs slab solves never holds them (8.6 GB each at 16384^2)
     ilm_plan* parent = nullptr;            // shared plans alias the parent's buffers

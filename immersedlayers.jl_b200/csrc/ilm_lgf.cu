@@ -121,6 +121,14 @@ int conv_setup(ilm_plan* p) {
     };
     ILM_TRY(upload_wl2(p->Ly, &p->wl2y));
     ILM_TRY(upload_wl2(p->Lx, &p->wl2x));
+    if (p->Ly > 4096) {
+        // split column pass: a chunk of columns whose hand-off block (chunk x 2 Ly complex) stays in L2 between the two launches;
+        // nsm columns = 4 (Q = 4) or 2 (Q = 2) items per CTA, 76 MB at L = 16384
+        p->big_chunk = p->nsm;
+        if (const char* e = getenv("ILM_BIG_CHUNK")) p->big_chunk = atoi(e);
+        if (p->big_chunk > 2 * p->Lx) p->big_chunk = 2 * p->Lx;
+        if (p->big_chunk > 0) ILM_CUDA(cudaMalloc(&p->bigA, (size_t)p->big_chunk * 2 * (size_t)p->Ly * sizeof(double2)));
+    }
     if (p->Ly > 4096 || p->Lx > 4096) {     // hand-off lines of the cluster passes: 2L complex per cluster, <= nsm/2 clusters
         const size_t Lmax = (size_t)(p->Lx > p->Ly ? p->Lx : p->Ly);
         ILM_CUDA(cudaMalloc(&p->conv_scratch, (size_t)p->nsm * Lmax * sizeof(double2)));
@@ -144,7 +152,7 @@ int conv_ensure_spectrum(ilm_plan* p, bool need_s2) {
 }
 
 void conv_free(ilm_plan* p) {
-    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->wl2y); cudaFree(p->wl2x); cudaFree(p->conv_scratch); cudaFree(p->S); cudaFree(p->S2);
+    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->wl2y); cudaFree(p->wl2x); cudaFree(p->conv_scratch); cudaFree(p->bigA); cudaFree(p->S); cudaFree(p->S2);
     cudaFree(p->slab_S); cudaFree(p->slab_S2);
     for (auto& k : p->kernels) { cudaFree(k.ghat); cudaFree(k.gxt); }
     cudaFree(p->lgf_dev); p->lgf_dev = nullptr;
@@ -159,6 +167,7 @@ ConvArgs conv_base_args(const ilm_plan* p) {
     a.skew_ns = p->skew_ns;
     a.wl2y = p->wl2y; a.wl2x = p->wl2x;
     a.scratch = p->conv_scratch;
+    a.bigA = p->bigA; a.bc0 = 0; a.bnc = p->big_chunk;
     return a;
 }
 static bool use_tma(const ilm_plan* p) { return p->Lx >= 512 && p->Lx <= 4096; }
