@@ -66,8 +66,7 @@ __global__ void __launch_bounds__(256, MINB) k_passD(ConvGeom g, const double2* 
     const int n1 = min(n0 + chunk, ohi);
     if (n0 >= n1) return;
     const unsigned long long keep = l2_policy_keep(), stream = l2_policy_stream();
-    const size_t base = s_index(g, px, m, 0);
-    auto sidx = [&](int row) { return base + ((size_t)(row >> 1) << 2) + (size_t)((row & 1) << 1); };
+    auto sidx = [&](int row) { return s_index(g, px, m, row); };
     double2 x[NR];
     if (ps.wR) {
         // patch mode: x_r(kx) = sum_q i^q w^{kx i0_q} sum_a wR_q[r - (j0_q - rlo)][a] w^{kx a},  w = exp(-2 pi i / PX):

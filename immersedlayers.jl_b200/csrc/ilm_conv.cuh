@@ -35,10 +35,16 @@ namespace ilm {
 struct ConvGeom {
     int Lx, Ly;      // half padded lengths (PX = 2Lx, PY = 2Ly)
     int MY;          // number of field rows carried through the spectrum
-    int MYp;         // MY rounded up to even
+    int MYp;         // MY rounded up to even (to a multiple of 2 rq)
+    int rq;          // row interleave (0 / 1 = none): the rows are stored class by class, row n at position
+                     // (n % rq) * (MYp / rq) + n / rq, so that the decimated sub-sequences n1 + Q n2 of the big column
+                     // pass (ilm_conv_big.cuh, rq = Q) are contiguous runs of a column instead of every Q-th row
 };
 
+ILM_HD int s_row(const ConvGeom& g, int row) { return g.rq > 1 ? (row % g.rq) * (g.MYp / g.rq) + row / g.rq : row; }
+
 ILM_HD size_t s_index(const ConvGeom& g, int px, int m, int row) {
+    row = s_row(g, row);
     return ((((size_t)px * (g.Lx >> 1) + (m >> 1)) * (size_t)(g.MYp >> 1) + (row >> 1)) << 2) +
            ((row & 1) << 1) + (m & 1);
 }

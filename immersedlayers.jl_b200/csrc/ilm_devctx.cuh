@@ -95,7 +95,7 @@ struct DevCtx {
             const int na = L >> 1;                                 // tile columns per row
             const int box = na < 256 ? na : 256;
             for (int r = 0; r < nrows; ++r) {
-                const int row = row0 + r;
+                const int row = s_row(a.g, row0 + r);
                 for (int a0 = 0; a0 < na; a0 += box) {
                     const unsigned d = (unsigned)__cvta_generic_to_shared(dst + (size_t)r * slot_stride + 2 * a0);
                     const int c0 = (row & 1) * 4, c1 = row >> 1, c2 = px * na + a0;

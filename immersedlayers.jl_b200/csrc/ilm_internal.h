@@ -253,6 +253,7 @@ int launch_probe_post_sum(ilm_plan* p, const DevTable& t, int ncol, double coef,
 void conv_free(ilm_plan* p);
 ConvArgs conv_base_args(const ilm_plan* p);      // plan-constant kernel arguments (buffers, twiddle tables)
 int conv_half_len(int n);                       // half padded transform length of an n-cell direction
+ConvGeom conv_geom(const ilm_plan* p, int MY);  // spectrum geometry of MY field rows (row interleave for Ly > 4096)
 int make_s2_tensor_map(ilm_plan* p, int MYp, const double2* base = nullptr);    // bulk-tensor map of S2 (or `base`) for pass C
 int conv_ensure_spectrum(ilm_plan* p, bool need_s2);
 int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], int rlo = -1, int rhi = -1, int olo = -1, int ohi = -1,

@@ -133,10 +133,19 @@ int conv_setup(ilm_plan* p) {
         const size_t Lmax = (size_t)(p->Lx > p->Ly ? p->Lx : p->Ly);
         ILM_CUDA(cudaMalloc(&p->conv_scratch, (size_t)p->nsm * Lmax * sizeof(double2)));
     }
-    ConvGeom g{p->Lx, p->Ly, p->g.NY, (p->g.NY + 1) & ~1};
+    const ConvGeom g = conv_geom(p, p->g.NY);
     p->s_cap = s_elems(g);                    // S / S2 themselves: conv_ensure_spectrum, on first use
     ILM_CUDA(cudaStreamSynchronize(p->stream));
     return ILM_OK;
+}
+
+// spectrum geometry of MY field rows: for Ly > 4096 the rows are stored class by class (row interleave Q = Ly / 4096,
+// ConvGeom::rq) and MYp is a multiple of 2 Q
+ConvGeom conv_geom(const ilm_plan* p, int MY) {
+    static const bool no_interleave = getenv("ILM_BIG_NO_INTERLEAVE") != nullptr;
+    const int Q = (p->Ly > 4096 && !no_interleave) ? p->Ly / 4096 : 1;
+    const int unit = 2 * Q;
+    return ConvGeom{p->Lx, p->Ly, MY, (MY + unit - 1) / unit * unit, Q};
 }
 
 // the full-size spectrum buffers (2 Lx x MYp complex each), allocated when a full-grid convolution first needs them
@@ -195,7 +204,7 @@ int conv_add_kernel(ilm_plan* p, const double* table, int n, double c0, double f
     ILM_TRY(conv_ensure_spectrum(p, false));
     ILM_TRY(launch_lgf_prep(p, src, n, NX, NY, c0, p->g_a));
     ConvArgs a = conv_base_args(p);
-    a.g = ConvGeom{p->Lx, p->Ly, NY, (NY + 1) & ~1};
+    a.g = conv_geom(p, NY);
     ILM_CUDA(cudaMalloc(&k.ghat, ghat_elems(a.g) * sizeof(double)));
     a.f1 = FieldRef{p->g_a, NX, NY};
     a.f2 = FieldRef{nullptr, 0, 0};
@@ -233,7 +242,7 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
     int MY = f1.p ? f1.my : 0;
     if (f2.p && f2.my > MY) MY = f2.my;
     if (MY == 0) return ILM_OK;
-    a.g = ConvGeom{p->Lx, p->Ly, MY, (MY + 1) & ~1};
+    a.g = conv_geom(p, MY);
     a.f1 = f1; a.f2 = f2;
     a.rlo = rlo < 0 ? 0 : rlo;
     a.rhi = (rhi < 0 || rhi > a.g.MYp) ? a.g.MYp : rhi;
@@ -262,7 +271,7 @@ int conv_apply_patch(ilm_plan* p, int kernel_id, const PatchSrc& ps, int MY, int
     if (!conv_band_ok(p, kernel_id, rhi - rlo) || !eg.part || !ps.wR || p->Lx > 4096) { set_error("conv_apply_patch: needs the band pass and the fused interpolation"); return ILM_EINVAL; }
     ILM_TRY(conv_ensure_spectrum(p, true));
     ConvArgs a = conv_base_args(p);
-    a.g = ConvGeom{p->Lx, p->Ly, MY, (MY + 1) & ~1};
+    a.g = conv_geom(p, MY);
     a.f1 = FieldRef{nullptr, ps.mx, ps.my};
     a.f2 = FieldRef{nullptr, ps.mx, ps.my};
     a.rlo = rlo; a.rhi = rhi;
@@ -286,7 +295,7 @@ int conv_profile(ilm_plan* p, FieldRef f1, FieldRef f2, int reps, double ms[3], 
     ILM_TRY(conv_ensure_spectrum(p, true));
     ConvArgs a = conv_base_args(p);
     int MY = f1.my > f2.my ? f1.my : f2.my;
-    a.g = ConvGeom{p->Lx, p->Ly, MY, (MY + 1) & ~1};
+    a.g = conv_geom(p, MY);
     a.f1 = f1; a.f2 = f2;
     a.rlo = rlo < 0 ? 0 : rlo;
     a.rhi = (rhi < 0 || rhi > a.g.MYp) ? a.g.MYp : rhi;
