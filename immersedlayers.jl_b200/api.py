@@ -803,12 +803,13 @@ def dirichlet_poisson(cache, fplus, fminus=None, S=None, filter_passes=0):
     return f, s, S
 
 
-def dirichlet_solve(cache, fplus, fminus=None, return_S=False):
+def dirichlet_solve(cache, fplus, fminus=None, return_S=False, want_field=True):
     """`solve(prob::DirichletPoissonProblem, sys)` of test/literate/dirichlet.jl:71-107 as ONE call of the library
     (ilm_dirichlet_poisson): boundary data in, field and multiplier out; S, its LU factors and the intermediate
     fields never leave the device, and with a communicator on the plan (cache.comm_init) the Schur columns are
     sharded over its ranks inside the library.  fplus / fminus: numpy arrays or torch CUDA tensors of length N
-    (the outputs live where the cache says: device=True -> torch).  Returns (f, s) or (f, s, S)."""
+    (the outputs live where the cache says: device=True -> torch).  Returns (f, s) or (f, s, S); want_field=False
+    (a rank of a sharded solve that only needs the multiplier) returns f = None and skips the last L^-1."""
     N = cache.N
     dev = cache.device
 
@@ -828,10 +829,11 @@ def dirichlet_solve(cache, fplus, fminus=None, return_S=False):
         if v is not None and int(np.prod(v.shape)) != N:
             raise DimensionMismatch(f"dirichlet_solve: expected {N} surface values")
     mx, my = cache.g.layout_shape(L.NODES_PRIMAL)
-    f = Nodes(Primal, cache.g, data=_alloc(mx * my, dev, zero=False))          # written whole by the library
+    f = Nodes(Primal, cache.g, data=_alloc(mx * my, dev, zero=False)) if want_field else None   # written whole by the library
     s = ScalarData(N, data=_alloc(N, dev, zero=False))
     S = _matrix(cache, N) if return_S else None
-    L.check(cache._lib.ilm_dirichlet_poisson(cache._plan, _ptr(fp), _ptr(fm) if fm is not None else None, _ptr(f.data),
+    L.check(cache._lib.ilm_dirichlet_poisson(cache._plan, _ptr(fp), _ptr(fm) if fm is not None else None,
+                                             _ptr(f.data) if f is not None else None,
                                              _ptr(s.data), _ptr(S) if S is not None else None))
     if return_S:
         return f, s, _as_matrix(S, N, N)

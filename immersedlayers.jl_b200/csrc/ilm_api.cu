@@ -852,7 +852,7 @@ __global__ void k_negate_add(size_t n, double* __restrict__ s, double sign_s, do
 extern "C" int ilm_dirichlet_poisson(ilm_plan* p, const double* fplus, const double* fminus, double* f, double* s, double* S_out) {
     ILM_CHECK_PLAN(p);
     const int N = p->N;
-    if (!fplus || !f || !s) { set_error("ilm_dirichlet_poisson: null argument"); return ILM_EINVAL; }
+    if (!fplus || !s) { set_error("ilm_dirichlet_poisson: null argument"); return ILM_EINVAL; }
     if (N == 0) { set_error("ilm_dirichlet_poisson: the plan has no surface points"); return ILM_ESIZE; }
     const size_t P = n_layout(p, ILM_NODES_PRIMAL);
     // scratch: fstar (P) | S (N^2) | d, rhs, ef (3N) | ipiv (N ints)
@@ -871,8 +871,8 @@ extern "C" int ilm_dirichlet_poisson(ilm_plan* p, const double* fplus, const dou
     Io io(p);
     const double* dfp = io.in(fplus, N);
     const double* dfm = fminus ? io.in(fminus, N) : nullptr;
-    double* df = io.out(f, P);
-    double* ds = io.out(s, N);
+    double* df = f ? io.out(f, P) : nullptr;         // f == NULL: this rank wants the multiplier only (a sharded solve
+    double* ds = io.out(s, N);                       // returns the field on one rank): the last regularize + L^-1 are skipped
     double* dSo = S_out ? io.out(S_out, (size_t)N * N) : nullptr;
     if (io.status) return io.status;
     const int nb = (N + 127) / 128;
@@ -892,10 +892,12 @@ extern "C" int ilm_dirichlet_poisson(ilm_plan* p, const double* fplus, const dou
     ILM_TRY(ilm_dense_solve(N, dS, ipiv, 1, ds, p->stream));
     k_negate_add<<<nb, 128, 0, p->stream>>>((size_t)N, ds, -1.0, nullptr, nullptr);
     ILM_LAUNCHED_API(p);
-    ILM_TRY(launch_regularize(p, p->tab[ILM_NODES_PRIMAL], ds, nullptr, 1.0, df, true));
-    ILM_TRY(conv_apply(p, 0, fref(p, ILM_NODES_PRIMAL, df), FieldRef{nullptr, 0, 0}));
-    k_negate_add<<<(unsigned)((P + 255) / 256), 256, 0, p->stream>>>(P, nullptr, 0.0, df, fstar);
-    ILM_LAUNCHED_API(p);
+    if (df) {
+        ILM_TRY(launch_regularize(p, p->tab[ILM_NODES_PRIMAL], ds, nullptr, 1.0, df, true));
+        ILM_TRY(conv_apply(p, 0, fref(p, ILM_NODES_PRIMAL, df), FieldRef{nullptr, 0, 0}));
+        k_negate_add<<<(unsigned)((P + 255) / 256), 256, 0, p->stream>>>(P, nullptr, 0.0, df, fstar);
+        ILM_LAUNCHED_API(p);
+    }
     return io.finish();
 }
 

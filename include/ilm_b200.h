@@ -324,7 +324,8 @@ int ilm_create_schur_sharded(ilm_plan* plan, int which, int kernel_id, double sc
  * f* = L^-1 D_s [f], S = -E L^-1 R (sharded when the plan has a communicator), S s~ = (f+ + f-)/2 - E f*,
  * s = -s~, f = L^-1 R s + f*.  fplus, fminus (NULL = 0): N surface values; f: Nodes{Primal}; s: N; S_out (NULL or
  * N x N): the Schur complement.  Host or device pointers; S, its LU factors and every intermediate field stay on
- * the device, so a host caller moves 2N doubles in and one field + N doubles out.                           */
+ * the device, so a host caller moves 2N doubles in and one field + N doubles out.  f may be NULL: the rank wants
+ * the multiplier only (sharded solve with the field returned on one rank); the last regularize + L^-1 are skipped. */
 int ilm_dirichlet_poisson(ilm_plan* plan, const double* fplus, const double* fminus, double* f, double* s, double* S_out);
 /* One inverse Laplacian of row-distributed fields over the plan's communicator: ilm_slab_forward -> exchange ->
  * ilm_slab_columns -> exchange -> ilm_slab_inverse with both exchanges issued inside the library (grouped

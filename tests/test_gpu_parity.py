@@ -691,6 +691,8 @@ def test_dirichlet_solve_single_call(device):
     f2, s2 = ilm.dirichlet_solve(cache, fplus)                   # fminus = None
     fr2, _, _ = o.dirichlet_solve(oc, fplus, S=Sr)
     assert relerr(f2.array(), fr2) < 1e-10
+    f3, s3 = ilm.dirichlet_solve(cache, fplus, want_field=False)  # a rank that only wants the multiplier (f = NULL)
+    assert f3 is None and np.array_equal(tonp(s3.data), tonp(s2.data))
     assert cache.comm_info() == (0, 1)
     assert relerr(tonp(ilm.create_schur_sharded(cache, "CLinvCT")), oc.create_CLinvCT()) < RTOL
 
