@@ -537,7 +537,7 @@ constexpr int PERM_STRIDE = 132;
 
 #define P2A(p) (((p) & 1) ? a[(p) >> 1].y : a[(p) >> 1].x)
 
-template <int THREADS>
+template <int THREADS, int GS>
 __global__ void __launch_bounds__(THREADS) k_lu_panel_v2(int n, int k0, int nb, double* __restrict__ A, int* __restrict__ ipiv,
                                                             int pk0, int pnb, int* __restrict__ perm, double* __restrict__ uscr,
                                                             long long* __restrict__ trace) {
@@ -681,11 +681,11 @@ __global__ void __launch_bounds__(THREADS) k_lu_panel_v2(int n, int k0, int nb, 
     int pos = row;
     int buf = 0;
 #pragma unroll 1
-    for (int g = 0; g < NB / 8; ++g) {
-        const int liveb = NB / 8 - g;                            // live 8-position blocks
+    for (int g = 0; g < NB / GS; ++g) {
+        const int liveb = NB / GS - g;                           // live GS-position blocks
         auto substep = [&](auto sconst) {
             constexpr int sidx = decltype(sconst)::value;
-            const int jj = 8 * g + sidx;
+            const int jj = GS * g + sidx;
             if (jj < nb) {
                 const int col = k0 + jj;
                 const double av = fabs(P2A(sidx));
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(THREADS) k_lu_panel_v2(int n, int k0, int nb, 
                     double2* d = reinterpret_cast<double2*>(&s_rows[0][0]);
 #pragma unroll
                     for (int c2 = 0; c2 < NB / 2; ++c2)
-                        if (2 * c2 + 1 > sidx && (c2 >> 2) < liveb) d[c2] = a[c2];
+                        if (2 * c2 + 1 > sidx && (2 * c2 / GS) < liveb) d[c2] = a[c2];
                     s_ext[0] = __drcp_rn(P2A(sidx));
                     s_ext[1] = av;
                     s_ext[2] = __longlong_as_double((long long)pos);
@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(THREADS) k_lu_panel_v2(int n, int k0, int nb, 
                     const double2* pr = reinterpret_cast<const double2*>(prow);
 #pragma unroll
                     for (int c2 = 0; c2 < NB / 2; ++c2) {
-                        if (2 * c2 + 1 > sidx && (c2 >> 2) < liveb) {
+                        if (2 * c2 + 1 > sidx && (2 * c2 / GS) < liveb) {
                             const double2 pp = pr[c2];
                             if (2 * c2 > sidx) a[c2].x -= lm * pp.x;
                             a[c2].y -= lm * pp.y;
@@ -758,16 +758,18 @@ __global__ void __launch_bounds__(THREADS) k_lu_panel_v2(int n, int k0, int nb, 
         };
         substep(std::integral_constant<int, 0>{}); substep(std::integral_constant<int, 1>{});
         substep(std::integral_constant<int, 2>{}); substep(std::integral_constant<int, 3>{});
-        substep(std::integral_constant<int, 4>{}); substep(std::integral_constant<int, 5>{});
-        substep(std::integral_constant<int, 6>{}); substep(std::integral_constant<int, 7>{});
+        if constexpr (GS == 8) {
+            substep(std::integral_constant<int, 4>{}); substep(std::integral_constant<int, 5>{});
+            substep(std::integral_constant<int, 6>{}); substep(std::integral_constant<int, 7>{});
+        }
         {
-            double2 t[4];                                        // rotate by 8: this group's multipliers go to the back
+            double2 t[GS / 2];                                   // rotate by GS: this group's multipliers go to the back
 #pragma unroll
-            for (int c = 0; c < 4; ++c) t[c] = a[c];
+            for (int c = 0; c < GS / 2; ++c) t[c] = a[c];
 #pragma unroll
-            for (int c = 0; c < NB / 2 - 4; ++c) a[c] = a[c + 4];
+            for (int c = 0; c < NB / 2 - GS / 2; ++c) a[c] = a[c + GS / 2];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) a[NB / 2 - 4 + c] = t[c];
+            for (int c = 0; c < GS / 2; ++c) a[NB / 2 - GS / 2 + c] = t[c];
         }
     }
     stamp(9);
@@ -828,8 +830,16 @@ static int launch_panel_v2(int n, int k0, int nb, double* A, int* ipiv, int pk0,
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if (tpb == 256) ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<256>, n, k0, nb, A, ipiv, pk0, pnb, perm, uscr, trace));
-    else ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<512>, n, k0, nb, A, ipiv, pk0, pnb, perm, uscr, trace));
+    // GS = columns per unrolled group of the column loop (ILM_LU_PANEL_GS): 8 halves the register rotations, 4 halves the code
+    // (ncu: 36 % no_instructions stalls on the 8-column body; measured 10.86 vs 11.08 ms at N = 4593)
+    static const int gs = getenv("ILM_LU_PANEL_GS") ? atoi(getenv("ILM_LU_PANEL_GS")) : 4;
+    if (tpb == 256) {
+        if (gs == 4) ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<256, 4>, n, k0, nb, A, ipiv, pk0, pnb, perm, uscr, trace));
+        else ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<256, 8>, n, k0, nb, A, ipiv, pk0, pnb, perm, uscr, trace));
+    } else {
+        if (gs == 4) ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<512, 4>, n, k0, nb, A, ipiv, pk0, pnb, perm, uscr, trace));
+        else ILM_CUDA(cudaLaunchKernelEx(&cfg, k_lu_panel_v2<512, 8>, n, k0, nb, A, ipiv, pk0, pnb, perm, uscr, trace));
+    }
     return ILM_OK;
 }
 
@@ -1301,8 +1311,10 @@ extern "C" int ilm_dense_factor(int n, double* A, int* ipiv, void* stream) {
         if (!v1 && n <= P2_MAXC * 512) {
             // Second form: the panel kernel applies the previous panel's update to its own 32 columns (k_lu_panel_v2);
             // the wide update is two launches (net permutation + block row, rank-32 DMMA update) on the low-priority stream.
-            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<256, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<512, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<256, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            ILM_CUDA(cudaFuncSetAttribute(k_lu_panel_v2<512, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             const int npan = (n + NB - 1) / NB;
             if (ax.perm_cap < (size_t)npan * PERM_STRIDE) {
                 ILM_CUDA(cudaStreamSynchronize(ax.hi));

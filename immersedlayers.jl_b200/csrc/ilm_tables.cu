@@ -105,7 +105,16 @@ __global__ void __launch_bounds__(LB_THREADS) k_build_lists(const __grid_constan
         unsigned* kout = J.key[src ^ 1]; int* vout = J.val[src ^ 1];
         for (int d = 0; d < 256; ++d) hist[d * LB_THREADS + t] = 0;
         __syncthreads();                                     // the writes of the previous pass (and of the generation) are visible
-        for (int e = e0; e < e1; ++e) hist[((kin[e] >> shift) & 255u) * LB_THREADS + t]++;
+        // the chunk is read in batches of 8 independent loads (a load per loop iteration, each chained to the shared-memory
+        // increment, exposed 600 cycles of L2 latency per element: 2.1 ms per refresh)
+        for (int e = e0; e < e1; e += 8) {
+            unsigned kb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) kb[u] = e + u < e1 ? kin[e + u] : 0u;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (e + u < e1) hist[((kb[u] >> shift) & 255u) * LB_THREADS + t]++;
+        }
         __syncthreads();
         // exclusive scan in (digit, thread) order: thread t scans digits 2t, 2t+1
         int tot = 0;
@@ -113,11 +122,18 @@ __global__ void __launch_bounds__(LB_THREADS) k_build_lists(const __grid_constan
         int base = block_excl_scan_128(tot, s_w, nullptr);
         for (int q = 0; q < 2 * LB_THREADS; ++q) { const unsigned c = hist[(2 * t) * LB_THREADS + q]; hist[(2 * t) * LB_THREADS + q] = base; base += c; }
         __syncthreads();
-        for (int e = e0; e < e1; ++e) {
-            const unsigned key = kin[e];
-            const unsigned dst = hist[((key >> shift) & 255u) * LB_THREADS + t]++;
-            kout[dst] = key;
-            vout[dst] = vin[e];
+        for (int e = e0; e < e1; e += 8) {
+            unsigned kb[8];
+            int vb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { kb[u] = e + u < e1 ? kin[e + u] : 0u; vb[u] = e + u < e1 ? vin[e + u] : 0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (e + u < e1) {
+                    const unsigned dst = hist[((kb[u] >> shift) & 255u) * LB_THREADS + t]++;
+                    kout[dst] = kb[u];
+                    vout[dst] = vb[u];
+                }
         }
         src ^= 1;
         __syncthreads();
