@@ -274,9 +274,9 @@ divv_masked_from_masked_divv!(d::Nodes{Primal}, md::Nodes{Primal}, dv::VectorDat
 `solve(prob::DirichletPoissonProblem, sys)` of test/literate/dirichlet.jl:71-107 in one library call; S and its LU
 factors stay on the device.  With a communicator on the plan (`comm_init!`) the Schur columns are sharded.
 """
-dirichlet_solve!(f::Nodes{Primal}, s::ScalarData, fplus::ScalarData, fminus::Union{ScalarData,Nothing}, c::B200Cache) =
+dirichlet_solve!(f::Union{Nodes{Primal},Nothing}, s::ScalarData, fplus::ScalarData, fminus::Union{ScalarData,Nothing}, c::B200Cache) =
     (check(ccall((:ilm_dirichlet_poisson, lib), Cint, (Ptr{Cvoid}, PD, PD, PD, PD, PD), c.plan, fplus.data,
-                 fminus === nothing ? C_NULL : fminus.data, f.data, s.data, C_NULL)); (f, s))
+                 fminus === nothing ? C_NULL : fminus.data, f === nothing ? C_NULL : f.data, s.data, C_NULL)); (f, s))   # f = nothing: multiplier only (sharded solve, field on one rank)
 comm_unique_id() = (id = zeros(UInt8, 128); check(ccall((:ilm_comm_unique_id, lib), Cint, (Ptr{UInt8}, Cint), id, 128)); id)
 # `id` from rank 0, distributed by the host program (MPI.Bcast!, a file, ...)
 comm_init!(c::B200Cache, id::Vector{UInt8}, rank::Integer, nranks::Integer) =
