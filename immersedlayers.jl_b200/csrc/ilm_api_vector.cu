@@ -345,6 +345,7 @@ extern "C" int ilm_create_schur_vector(ilm_plan* p, int which, double scale, int
             int rlo = 1 << 30, rhi = -1;
             for (int q = 0; q < (two ? 2 : 1); ++q) rows_of(c + q, &rlo, &rhi);
             rlo = std::max(rlo, 0); rhi = std::min(rhi, p->g.NY);
+            if (rhi <= rlo) { rlo = 0; rhi = 1; }          // every window of the pair lies off the grid: an empty (zero) patch row
             ILM_TRY(launch_vcurl_probe_pre(p, c, two ? 2 : 1, fu, fv, rlo, rhi, deriv_div(p)));   // C^T R_f e_c / dx on the patch rows
             const FieldRef f1{fu, p->g.NX, p->g.NY};
             const FieldRef f2 = two ? FieldRef{fv, p->g.NX, p->g.NY} : FieldRef{nullptr, 0, 0};

@@ -49,6 +49,21 @@ def timestep_fourier(g, kappa, fourier):
     return fourier * g.dx ** 2 / kappa
 
 
+
+def _compact_intfact_table(a, nmax):
+    """The plan_intfact table exp(L a) cut where it has decayed to rounding level, for the direct-table form of the stage
+    complements (k_schur_direct treats entries beyond the table as zero).  The support grows with the Fourier number a
+    (31 entries for a <= 5, 64 at a = 30): the table is doubled until its last entry of the first column is below
+    1e-17 of the peak, or the grid size is reached (then nothing is cut)."""
+    n = 64
+    while True:
+        n = min(n, nmax)
+        T = _lgf.intfact_table(a, n)
+        if n >= nmax or abs(T[n - 1, 0]) <= 1e-17 * abs(T[0, 0]):
+            return T
+        n *= 2
+
+
 class DirichletHeatConduction:
     """Unsteady heat conduction with prescribed surface temperatures T+ (outside) / T- (inside) on a
     possibly moving body (test/literate/heatconduction.jl; moving case :386-401).
@@ -77,7 +92,7 @@ class DirichletHeatConduction:
         for a in sorted(set(self.stage_a)):
             if a > 0.0:
                 self.kernel_id[a] = self.cache.add_kernel(_lgf.intfact_table(a, max(g.NX, g.NY)))
-                self.table[a] = _lgf.intfact_table(a, 64)             # compact: support < 31 for a <= 5
+                self.table[a] = _compact_intfact_table(a, max(g.NX, g.NY))
             else:
                 self.table[a] = np.array([[1.0]])
                 self.kernel_id[a] = None                              # H = I

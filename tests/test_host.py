@@ -485,3 +485,16 @@ def test_comm_entry_points_fail_cleanly_without_a_plan():
     lib = ilm._lib.load()
     assert lib.ilm_comm_init(None, None, 0, 0, 1) == ilm._lib.EINVAL
     assert lib.ilm_comm_destroy(None) == ilm._lib.EINVAL
+
+
+def test_compact_intfact_table_grows_with_the_fourier_number():
+    """The direct-table form of the IF-HERK stage complements cuts the plan_intfact table where it has decayed to
+    rounding level; a fixed 64-entry cut truncated it silently for Fourier numbers above ~30 (ADVICE, round 1)."""
+    from ilm_b200 import timemarching as tm
+    small = tm._compact_intfact_table(0.5, 2048)
+    large = tm._compact_intfact_table(50.0, 2048)
+    assert small.shape[0] == 64 and large.shape[0] > 64
+    for T in (small, large):
+        assert abs(T[-1, 0]) <= 1e-17 * abs(T[0, 0])
+    # never larger than the grid: nothing is cut then
+    assert tm._compact_intfact_table(50.0, 80).shape[0] == 80
