@@ -289,7 +289,7 @@ def main():
         "lu_solve_ms": None, "plan_build_ms_once_per_grid": plan_build_ms}
     lu = ilm.LU(S_dev)
     breakdown["lu_solve_ms"] = time_dev(lambda: lu.solve(rhs), reps=5)
-    breakdown["note"] = ("schur_build is the sharded part (N column probes / n_gpus + one in-place broadcast group); "
+    breakdown["note"] = ("schur_build is the sharded part (N column probes / n_gpus in blocks of equal row counts + one in-place broadcast group); "
                          "table refresh, LU, solve and the two dense L^-1 are replicated on every rank")
 
     # ---- convolution passes timed alone on the plan's stream (CUDA events inside the library)
@@ -344,7 +344,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dk["GBps"], "peak": peak, "unit": "GB/s", "frac": dk["frac"],
                 "traffic": dk["traffic"], "peak_source": peak_src, "algorithmic_bytes_per_launch": dk["bytes"],
                 "launch_ms": dk["ms"], "launches_per_step": pairs_per_step,
-                "share_of_step": dk["ms"] * pairs_per_step / ms,
+                # the launch timed here inverts ALL window rows; in the step a pair inverts the rows from its own windows
+                # upwards (symmetric build), about half on average: share = S-build share x the kernel's share of a pair
+                "share_of_step": (breakdown["schur_build_ms"] / ms) * dk["ms"] / sum(k["ms"] for k in kernels.values()),
+                "rows_inverted_per_pair_vs_all_window_rows": breakdown["schur_build_ms"] / (pairs_per_step * sum(k["ms"] for k in kernels.values())),
                 "frac_of_nominal_8TBps": dk["GBps"] / 8000.0,
                 "probe_kernels": kernels, "probe_pair_ms": sum(float(msq[i]) for i in range(3)),
                 "probe_output_rows": [r0.value, r1.value],
@@ -441,7 +444,10 @@ def main():
     if rank == 0:
         cfg = workload_config(args, g, N, world)
         cfg.update({"parallelism": f"schur-columns/{world}",
-                    "l2": "every column pair streams 2 x %.0f MB of x-spectrum rows (> 126 MB L2)" % (rows_out * 2 * Lx * 16 / 1e6),
+                    "l2": "a column pair over all window rows streams 2 x %.0f MB of x-spectrum rows (> 126 MB L2)" % (rows_out * 2 * Lx * 16 / 1e6),
+                    "schur": ("symmetric build: the points are visited by first window row, the probe of a pair inverts the rows from "
+                              "its own windows upwards, S[k,c] below comes from S[c,k] wgt_c/wgt_k (ILM_SCHUR_SYMM=0: every column "
+                              "over all window rows, 347 ms instead of 204 ms)"),
                     "checksum_f": checksum})
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256, MINB) k_passD(ConvGeom g, const double2* 
         const unsigned mask = (unsigned)(2 * g.Lx - 1);
         const double2 gw = ps.wl2x[kx];
         for (int q = 0; q < ps.ncol; ++q) {
-            const int col = ps.col0 + q;
+            const int col = q ? ps.col1 : ps.col0;
             const int ci = ps.i0[col], cj = ps.j0[col];
             const double* w = ps.wR + (size_t)col * ps.W * ps.W;
             double2 pw = ps.wl2x[(unsigned)(kx * ci) & mask];          // w^{kx (i0 + a)}, a = 0

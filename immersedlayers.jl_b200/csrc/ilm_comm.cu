@@ -94,6 +94,22 @@ int comm_allgather_columns(ilm_plan* p, double* dA, int ld, int ncols) {
     return ILM_OK;
 }
 
+// the same with explicit column boundaries: rank r owns the columns [bounds[r], bounds[r + 1])
+int comm_allgather_column_blocks(ilm_plan* p, double* dA, int ld, const int* bounds) {
+    NcclApi* api = nccl();
+    if (!api || !p->comm) { set_error("the plan has no communicator (ilm_comm_init)"); return ILM_ENCCL; }
+    ncclComm_t comm = static_cast<ncclComm_t>(p->comm);
+    ILM_NCCL(api->GroupStart());
+    for (int r = 0; r < p->comm_size; ++r) {
+        if (bounds[r + 1] > bounds[r]) {
+            double* blk = dA + (size_t)bounds[r] * ld;
+            ILM_NCCL(api->Broadcast(blk, blk, (size_t)(bounds[r + 1] - bounds[r]) * ld, ncclDouble, r, comm, p->stream));
+        }
+    }
+    ILM_NCCL(api->GroupEnd());
+    return ILM_OK;
+}
+
 // variable-count all-to-all on device buffers (counts in doubles, peer-major packing): the exchange of the slab solve
 int comm_alltoallv(ilm_plan* p, const double* send, const int64_t* scount, double* recv, const int64_t* rcount) {
     NcclApi* api = nccl();

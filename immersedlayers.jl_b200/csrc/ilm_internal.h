@@ -80,7 +80,7 @@ struct PatchSrc {
     const int* i0 = nullptr;
     const int* j0 = nullptr;
     const double2* wl2x = nullptr;  // exp(-2 pi i n / (2 Lx)), n < 2 Lx
-    int W = 0, mx = 0, my = 0, col0 = 0, ncol = 0;
+    int W = 0, mx = 0, my = 0, col0 = 0, col1 = -1, ncol = 0;   // the points of the pair (need not be neighbours)
 };
 
 struct ConvKernel {     // one multiplier (LGF inverse, integrating factor, ...)
@@ -141,6 +141,11 @@ struct ilm_plan {
     // scratch of the whole-problem entry points (ilm_dirichlet_poisson): grow-only
     double* prob_work = nullptr;
     size_t prob_cap = 0;
+    // symmetric Schur build: the matrix in sorted column order and the index arrays (pos | cololo | pairolo)
+    double* symm_S = nullptr;
+    int* symm_idx = nullptr;
+    size_t symm_cap = 0;
+    bool symm = true;               // ILM_SCHUR_SYMM=0: every column of create_RTLinvR over all window rows
     std::vector<void*> staging;     // device staging for host pointers
     std::vector<size_t> staging_cap;
 };
@@ -267,7 +272,11 @@ int conv_build_gxt(ilm_plan* p, const ConvArgs& a, ConvKernel& k, double factor)
 int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k, const PatchSrc* ps = nullptr);
 // create_RTLinvR probe without pre-operator and pass A: band pass in patch mode, then pass C with the fused interpolation
 int conv_apply_patch(ilm_plan* p, int kernel_id, const PatchSrc& ps, int MY, int rlo, int rhi, int olo, int ohi, const ProbeGather& eg);
-int launch_probe_post_sum_batch(ilm_plan* p, const DevTable& t, int npairs, int ncols, double coef, double* dA0);
+// pairolo (may be null): first inverted row of every pair of the batch; point k is written only if its window rows were inverted
+int launch_probe_post_sum_batch(ilm_plan* p, const DevTable& t, int npairs, int ncols, double coef, double* dA0, const int* pairolo = nullptr);
+// out[k, c] = valid(k, c) ? Ssort[k, pos[c]] : Ssort[c, pos[k]] * ds[c] / ds[k]   (symmetric Schur build, ilm_api.cu)
+int launch_schur_symm_finish(ilm_plan* p, const double* Ssort, const int* pos, const int* cololo, const int* j0, const double* ds, double* out);
+int comm_allgather_column_blocks(ilm_plan* p, double* dA, int ld, const int* bounds);
 int conv_band_max_rows();
 const double2* conv_twiddles_host(int L, size_t* count);
 

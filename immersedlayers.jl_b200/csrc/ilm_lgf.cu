@@ -98,6 +98,7 @@ int conv_setup(ilm_plan* p) {
     if (const char* e = getenv("ILM_PROBE_FUSE_E")) p->fuse_e = atoi(e) != 0;
     if (const char* e = getenv("ILM_PROBE_PATCH")) p->patch = atoi(e) != 0;
     if (const char* e = getenv("ILM_PROBE_PRUNE_C")) p->prune_c = atoi(e) != 0;
+    if (const char* e = getenv("ILM_SCHUR_SYMM")) p->symm = atoi(e) != 0;
     p->Lx = conv_half_len(p->g.NX);
     p->Ly = conv_half_len(p->g.NY);
     if (p->Lx > 16384 || p->Ly > 16384) {

@@ -936,10 +936,11 @@ __global__ void k_probe_post_sum(int N, int W, int my, const int* __restrict__ j
 // the same for a batch of column pairs: pair y (blockIdx.y) left its row sums in slice y of t.part and owns the
 // columns 2y, 2y + 1 of dA0 (ncols columns in all; the last pair may be a single column)
 __global__ void k_probe_post_sum_batch(int N, int W, int my, const int* __restrict__ j0, const double2* __restrict__ part,
-                                       size_t stride, double coef, double* __restrict__ dA0, int ncols) {
+                                       size_t stride, double coef, double* __restrict__ dA0, int ncols, const int* __restrict__ pairolo) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
     const int pair = blockIdx.y;
+    if (pairolo && max(j0[k], 0) < pairolo[pair]) return;        // rows below the pair's first inverted row: filled by symmetry
     const double2* pp = part + (size_t)pair * stride;
     double re = 0.0, im = 0.0;
     for (int b = 0; b < W; ++b) {
@@ -949,9 +950,33 @@ __global__ void k_probe_post_sum_batch(int N, int W, int my, const int* __restri
     dA0[(size_t)(2 * pair) * N + k] = coef * re;
     if (2 * pair + 1 < ncols) dA0[(size_t)(2 * pair + 1) * N + k] = coef * im;
 }
-int launch_probe_post_sum_batch(ilm_plan* p, const DevTable& t, int npairs, int ncols, double coef, double* dA0) {
+int launch_probe_post_sum_batch(ilm_plan* p, const DevTable& t, int npairs, int ncols, double coef, double* dA0, const int* pairolo) {
     if (npairs <= 0) return ILM_OK;
-    k_probe_post_sum_batch<<<dim3((p->N + 127) / 128, npairs), 128, 0, p->stream>>>(p->N, t.W, t.my, t.j0, t.part, t.part_stride, coef, dA0, ncols);
+    k_probe_post_sum_batch<<<dim3((p->N + 127) / 128, npairs), 128, 0, p->stream>>>(p->N, t.W, t.my, t.j0, t.part, t.part_stride, coef, dA0, ncols, pairolo);
+    ILM_LAUNCHED(p);
+    return ILM_OK;
+}
+
+// Symmetric Schur build (create_RTLinvR: S[k,c] = coef wgt_c sum e_k K e_c with the same windows e on both sides): column c was
+// probed over the rows from its own window upwards only, so S[k, c] is there for the points k whose windows start at or above
+// that row; the others come from the mirror entry, S[k, c] = S[c, k] wgt_c / wgt_k.  Ssort holds the columns in sorted order.
+__global__ void k_schur_symm_finish(int N, const double* __restrict__ Ssort, const int* __restrict__ pos, const int* __restrict__ cololo,
+                                    const int* __restrict__ j0, const double* __restrict__ ds, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (k >= N) return;
+    const int olo = cololo[c];
+    const bool valid = olo < 0 || max(j0[k], 0) >= olo;
+    double v;
+    if (valid) v = Ssort[(size_t)pos[c] * N + k];
+    else {
+        v = Ssort[(size_t)pos[k] * N + c];
+        if (ds) v = v * ds[c] / ds[k];
+    }
+    out[(size_t)c * N + k] = v;
+}
+int launch_schur_symm_finish(ilm_plan* p, const double* Ssort, const int* pos, const int* cololo, const int* j0, const double* ds, double* out) {
+    if (p->N == 0) return ILM_OK;
+    k_schur_symm_finish<<<dim3((p->N + 127) / 128, p->N), 128, 0, p->stream>>>(p->N, Ssort, pos, cololo, j0, ds, out);
     ILM_LAUNCHED(p);
     return ILM_OK;
 }

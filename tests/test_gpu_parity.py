@@ -341,6 +341,21 @@ def test_dense_lu_solve(n):
     assert np.abs(A @ x - b).max() < 1e-10 * np.abs(b).max() * n
 
 
+@pytest.mark.parametrize("n", [64, 256, 1024])
+def test_dense_lu_ties_go_to_the_first_row(n):
+    """A Hadamard matrix: every pivot search is a tie of |a| over all remaining rows, and the elimination is exact in
+    fp64 (dyadic entries), so LAPACK's choice -- the first maximum in the interchanged row order -- must be reproduced
+    exactly although the panel kernel never moves rows (it tracks logical row indices), across warps and CTAs."""
+    import scipy.linalg
+    A = scipy.linalg.hadamard(n).astype(np.float64)
+    lu = ilm.LU(A)
+    lu_ref, piv_ref = scipy.linalg.lu_factor(A)
+    assert np.array_equal(lu.ipiv - 1, piv_ref)
+    assert np.array_equal(lu.lu.reshape((n, n), order="F"), lu_ref)
+    b = np.arange(1.0, n + 1.0)
+    assert relerr(lu.solve(b), scipy.linalg.lu_solve((lu_ref, piv_ref), b)) < 1e-13
+
+
 def test_matvec_pow():
     rng = np.random.default_rng(8)
     n = 141
@@ -594,20 +609,23 @@ def test_probe_band_pass_equals_transform_pass(ddf, monkeypatch):
     body = (x + 0.93, y - 0.4, nx, ny, ds)                   # windows clipped at +x and -y
     G = ilm.lgf.lgf_table(96)
     built = {}
-    for band in ("1", "0", "nopatch"):
+    for band in ("1", "0", "nopatch", "nosymm"):
         # "nopatch": band pass fed by pass A on the grid rows (ILM_PROBE_PATCH=0); default: the band pass sums the
-        # x-spectrum of the DDF windows itself (create_RTLinvR probes: no pre-operator, no pass A)
+        # x-spectrum of the DDF windows itself (create_RTLinvR probes: no pre-operator, no pass A) and create_RTLinvR
+        # probes every column from its own window rows upwards only, the rest by symmetry ("nosymm": ILM_SCHUR_SYMM=0)
         monkeypatch.setenv("ILM_PROBE_BAND", "0" if band == "0" else "1")
         monkeypatch.setenv("ILM_PROBE_PATCH", "0" if band == "nopatch" else "1")
+        monkeypatch.setenv("ILM_SCHUR_SYMM", "0" if band == "nosymm" else "1")
         cache = ilm.SurfaceScalarCache(body, g, lgf_table=G, ddftype=ddf)
         vc = ilm.SurfaceVectorCache(body, g, lgf_table=G, ddftype=ddf)
         kid = cache.add_kernel(ilm.lgf.intfact_table(0.5, 96))
         built[band] = [ilm.create_RTLinvR(cache), ilm.create_CLinvCT(cache), ilm.create_GLinvD(cache),
                        ilm.create_GLinvD_cross(cache, cols=(3, 10)), ilm.create_RTHR(cache, kid),
                        ilm.create_CL2invCT(vc), ilm.create_CLinvCT(vc), ilm.create_RTLinvR(vc), ilm.create_GLinvD(vc, cols=(0, 9))]
-    for a, b, c in zip(built["1"], built["0"], built["nopatch"]):
+    for a, b, c, d in zip(built["1"], built["0"], built["nopatch"], built["nosymm"]):
         assert relerr(a, b) < 1e-13
         assert relerr(a, c) < 1e-13
+        assert relerr(a, d) < 1e-13
     if ddf == "yang3":
         oc = o.ScalarCache(o.Grid(g.NX, g.NY, g.dx, g.I0), *body, G)
         assert relerr(built["1"][0], oc.create_RTLinvR()) < RTOL
