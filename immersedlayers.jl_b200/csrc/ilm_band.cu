@@ -169,8 +169,9 @@ int conv_build_gxt(ilm_plan* p, const ConvArgs& a, ConvKernel& k, double factor)
 int conv_band_max_rows() { return 16; }
 
 // S (rows [rlo, rhi) valid) -> S2 rows [olo, ohi)
-int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k, const PatchSrc* psrc) {
+int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k, const PatchSrc* psrc, cudaStream_t st) {
     const PatchSrc ps = psrc ? *psrc : PatchSrc{};
+    if (!st) st = p->stream;
     const int nrows = a.rhi - a.rlo;
     const int nout = a.ohi - a.olo;
     if (nrows < 1 || nrows > conv_band_max_rows() || nout < 1) { set_error("conv_launch_band: bad row range"); return ILM_EINVAL; }
@@ -183,7 +184,7 @@ int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k, const 
     nchunks = (nout + chunk - 1) / chunk;
     const dim3 grid(gx, nchunks);
     const int dmax = k.gxt_rows - 1;
-#define ILM_BAND(NR, MINB) k_passD<NR, MINB><<<grid, 256, 0, p->stream>>>(a.g, a.S, a.S2, k.gxt, k.gxt_ld, dmax, a.rlo, nrows, a.olo, a.ohi, chunk, ps)
+#define ILM_BAND(NR, MINB) k_passD<NR, MINB><<<grid, 256, 0, st>>>(a.g, a.S, a.S2, k.gxt, k.gxt_ld, dmax, a.rlo, nrows, a.olo, a.ohi, chunk, ps)
     static const int minb = getenv("ILM_BAND_MINB") ? atoi(getenv("ILM_BAND_MINB")) : 3;
     if (nrows <= 6) { if (minb >= 3) ILM_BAND(6, 3); else ILM_BAND(6, 2); }
     else if (nrows <= 8) { if (minb >= 3) ILM_BAND(8, 3); else ILM_BAND(8, 2); }

@@ -146,6 +146,11 @@ struct ilm_plan {
     int* symm_idx = nullptr;
     size_t symm_cap = 0;
     bool symm = true;               // ILM_SCHUR_SYMM=0: every column of create_RTLinvR over all window rows
+    // two pairs in flight in the symmetric build: a second stream with its own row-major spectrum buffer
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    double2* S2b = nullptr;
+    bool dual = true;               // ILM_SCHUR_DUAL=0: one pair at a time
     std::vector<void*> staging;     // device staging for host pointers
     std::vector<size_t> staging_cap;
 };
@@ -269,11 +274,14 @@ typedef int (*conv_launch_fn)(int which, const ConvArgs& a, int nsm, cudaStream_
 conv_launch_fn conv_launcher(int L);
 // band pass (ilm_band.cu): the column step for right-hand sides with <= conv_band_max_rows() non-zero rows
 int conv_build_gxt(ilm_plan* p, const ConvArgs& a, ConvKernel& k, double factor);
-int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k, const PatchSrc* ps = nullptr);
+int conv_launch_band(ilm_plan* p, const ConvArgs& a, const ConvKernel& k, const PatchSrc* ps = nullptr, cudaStream_t st = nullptr);
 // create_RTLinvR probe without pre-operator and pass A: band pass in patch mode, then pass C with the fused interpolation
-int conv_apply_patch(ilm_plan* p, int kernel_id, const PatchSrc& ps, int MY, int rlo, int rhi, int olo, int ohi, const ProbeGather& eg);
+// st / S2alt (optional): another stream and spectrum buffer, so that two pairs can be in flight (symmetric Schur build)
+int conv_apply_patch(ilm_plan* p, int kernel_id, const PatchSrc& ps, int MY, int rlo, int rhi, int olo, int ohi, const ProbeGather& eg,
+                     cudaStream_t st = nullptr, double2* S2alt = nullptr);
 // pairolo (may be null): first inverted row of every pair of the batch; point k is written only if its window rows were inverted
-int launch_probe_post_sum_batch(ilm_plan* p, const DevTable& t, int npairs, int ncols, double coef, double* dA0, const int* pairolo = nullptr);
+int launch_probe_post_sum_batch(ilm_plan* p, const DevTable& t, int npairs, int ncols, double coef, double* dA0, const int* pairolo = nullptr,
+                                int slice0 = 0, cudaStream_t st = nullptr);
 // out[k, c] = valid(k, c) ? Ssort[k, pos[c]] : Ssort[c, pos[k]] * ds[c] / ds[k]   (symmetric Schur build, ilm_api.cu)
 int launch_schur_symm_finish(ilm_plan* p, const double* Ssort, const int* pos, const int* cololo, const int* j0, const double* ds, double* out);
 int comm_allgather_column_blocks(ilm_plan* p, double* dA, int ld, const int* bounds);

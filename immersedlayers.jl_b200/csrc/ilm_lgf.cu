@@ -99,6 +99,7 @@ int conv_setup(ilm_plan* p) {
     if (const char* e = getenv("ILM_PROBE_PATCH")) p->patch = atoi(e) != 0;
     if (const char* e = getenv("ILM_PROBE_PRUNE_C")) p->prune_c = atoi(e) != 0;
     if (const char* e = getenv("ILM_SCHUR_SYMM")) p->symm = atoi(e) != 0;
+    if (const char* e = getenv("ILM_SCHUR_DUAL")) p->dual = atoi(e) != 0;
     p->Lx = conv_half_len(p->g.NX);
     p->Ly = conv_half_len(p->g.NY);
     if (p->Lx > 16384 || p->Ly > 16384) {
@@ -162,7 +163,11 @@ int conv_ensure_spectrum(ilm_plan* p, bool need_s2) {
 }
 
 void conv_free(ilm_plan* p) {
-    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->wl2y); cudaFree(p->wl2x); cudaFree(p->conv_scratch); cudaFree(p->bigA); cudaFree(p->S); cudaFree(p->S2);
+    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->wl2y); cudaFree(p->wl2x); cudaFree(p->conv_scratch); cudaFree(p->bigA); cudaFree(p->S); cudaFree(p->S2); cudaFree(p->S2b);
+    if (p->stream2) cudaStreamDestroy(p->stream2);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    p->S2b = nullptr; p->stream2 = nullptr; p->ev_fork = p->ev_join = nullptr;
     cudaFree(p->slab_S); cudaFree(p->slab_S2);
     for (auto& k : p->kernels) { cudaFree(k.ghat); cudaFree(k.gxt); }
     cudaFree(p->lgf_dev); p->lgf_dev = nullptr;
@@ -268,7 +273,9 @@ int conv_apply(ilm_plan* p, int kernel_id, FieldRef f1, FieldRef f2, int rlo, in
 }
 
 // create_RTLinvR probe from the DDF patches: band pass in patch mode (S is not touched), pass C with the fused interpolation
-int conv_apply_patch(ilm_plan* p, int kernel_id, const PatchSrc& ps, int MY, int rlo, int rhi, int olo, int ohi, const ProbeGather& eg) {
+int conv_apply_patch(ilm_plan* p, int kernel_id, const PatchSrc& ps, int MY, int rlo, int rhi, int olo, int ohi, const ProbeGather& eg,
+                     cudaStream_t st, double2* S2alt) {
+    if (!st) st = p->stream;
     if (!conv_band_ok(p, kernel_id, rhi - rlo) || !eg.part || !ps.wR || p->Lx > 4096) { set_error("conv_apply_patch: needs the band pass and the fused interpolation"); return ILM_EINVAL; }
     ILM_TRY(conv_ensure_spectrum(p, true));
     ConvArgs a = conv_base_args(p);
@@ -283,9 +290,10 @@ int conv_apply_patch(ilm_plan* p, int kernel_id, const PatchSrc& ps, int MY, int
     a.Ghat = k.ghat;
     a.eg = eg;
     a.s2_rowmajor = 1;
-    if (use_tma(p)) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));
-    ILM_TRY(conv_launch_band(p, a, k, &ps));
-    ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, p->stream, p->tmap_s2));
+    if (S2alt) a.S2 = S2alt;
+    if (use_tma(p)) ILM_TRY(make_s2_tensor_map(p, a.g.MYp));            // (the row-major path uses plain bulk copies from a.S2)
+    ILM_TRY(conv_launch_band(p, a, k, &ps, st));
+    ILM_TRY(conv_launcher(p->Lx)(2, a, p->nsm, st, p->tmap_s2));
     p->launches += 2;
     return ILM_OK;
 }

@@ -950,9 +950,12 @@ __global__ void k_probe_post_sum_batch(int N, int W, int my, const int* __restri
     dA0[(size_t)(2 * pair) * N + k] = coef * re;
     if (2 * pair + 1 < ncols) dA0[(size_t)(2 * pair + 1) * N + k] = coef * im;
 }
-int launch_probe_post_sum_batch(ilm_plan* p, const DevTable& t, int npairs, int ncols, double coef, double* dA0, const int* pairolo) {
+int launch_probe_post_sum_batch(ilm_plan* p, const DevTable& t, int npairs, int ncols, double coef, double* dA0, const int* pairolo,
+                                int slice0, cudaStream_t st) {
     if (npairs <= 0) return ILM_OK;
-    k_probe_post_sum_batch<<<dim3((p->N + 127) / 128, npairs), 128, 0, p->stream>>>(p->N, t.W, t.my, t.j0, t.part, t.part_stride, coef, dA0, ncols, pairolo);
+    if (!st) st = p->stream;
+    k_probe_post_sum_batch<<<dim3((p->N + 127) / 128, npairs), 128, 0, st>>>(p->N, t.W, t.my, t.j0, t.part + (size_t)slice0 * t.part_stride,
+                                                                             t.part_stride, coef, dA0, ncols, pairolo);
     ILM_LAUNCHED(p);
     return ILM_OK;
 }
