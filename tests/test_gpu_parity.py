@@ -655,6 +655,36 @@ def test_probe_pairs_off_the_band_path_inside_a_build(cols):
         assert relerr(S, oc.create_RTLinvR(cols=list(range(*cols)))) < RTOL
 
 
+@pytest.mark.parametrize("scaling", [ilm.GridScaling, ilm.IndexScaling])
+def test_symmetric_schur_build(scaling):
+    """create_RTLinvR over all columns probes every pair from its own window rows upwards and mirrors the rest
+    (S[k,c] / wgt_c is symmetric; wgt = ds/dx^2 with GridScaling, 1 with IndexScaling).  Two bodies with a gap in y (one
+    pair falls back to full-row probes of single columns), windows clipped at the lower boundary, an odd number of points:
+    the matrix equals the oracle's column-by-column probes and its FFT-free table form."""
+    g = ilm.PhysicalGrid(120, 150, 4.0 / 118, (60, 75))
+    c1_ = ilm.bodies.circle(0.45, 1.4 * g.dx, center=(0.3, -2.15))      # windows clipped at -y
+    c2_ = ilm.bodies.circle(0.35, 1.4 * g.dx, center=(-0.5, 1.1))
+    body = ilm.bodies.concat(c1_, c2_)[:5]
+    if len(body[0]) % 2 == 0:
+        body = tuple(a[:-1] for a in body)
+    G = ilm.lgf.lgf_table(160)
+    cache = ilm.SurfaceScalarCache(body, g, lgf_table=G, scaling=scaling)
+    oc = o.ScalarCache(o.Grid(g.NX, g.NY, g.dx, g.I0), *body, G, scaling=o.GRID_SCALING if scaling == ilm.GridScaling else o.INDEX_SCALING)
+    S = np.asarray(ilm.create_RTLinvR(cache))
+    assert S.shape == (cache.N, cache.N) and cache.N % 2 == 1
+    assert relerr(S, oc.create_RTLinvR()) < RTOL
+    assert relerr(S, oc.create_RTLinvR_table()) < RTOL
+    E = ilm.lgf.intfact_table(0.7, 160)                                # any even kernel: stage complements of IF-HERK
+    kid = cache.add_kernel(E)
+    plan = o.ConvPlan(E[:g.NX, :g.NY])
+    cols = [0, 1, cache.N // 2, cache.N - 1]
+    Sref = np.zeros((cache.N, len(cols)))
+    for q, c in enumerate(cols):
+        e = np.zeros(cache.N); e[c] = 1.0
+        Sref[:, q] = -oc.interpolate(plan.apply(oc.regularize(e)))
+    assert relerr(np.asarray(ilm.create_RTHR(cache, kid))[:, cols], Sref) < RTOL
+
+
 @pytest.mark.parametrize("ddf", ["yang3", "m4prime"])
 def test_device_list_build_equals_host_build(ddf, monkeypatch):
     """The gather lists (cell buckets, row buckets, column mask of pass C) are built by a radix sort on the device;
