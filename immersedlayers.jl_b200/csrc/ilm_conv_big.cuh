@@ -60,9 +60,18 @@ ILM_HD void passA_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block
             const int px = step / (Q / 2), k1 = 2 * (step % (Q / 2)) + ctx.grp;
             const unsigned cls = (unsigned)(px + 2 * k1);
             double2 v[16];
+            // class twiddle w_2L^{n cls}, n = j + e T + M n1: one table entry per thread (w^{j cls}) times warp-uniform
+            // entries (w^{M cls n1}, w^{T cls e}) instead of one scattered table load per element (64 per step)
+            double2 wjm[Q];
+            if (cls) {
+                const double2 wj = a.wl2x[((unsigned)j * cls) & mask];
+#pragma unroll
+                for (int n1 = 0; n1 < Q; ++n1) wjm[n1] = n1 ? cmul(wj, a.wl2x[((unsigned)(BIG_M * n1) * cls) & mask]) : wj;
+            }
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
                 const int n2 = j + e * T;
+                const double2 wte = (cls && e) ? a.wl2x[((unsigned)(e * T) * cls) & mask] : cmk(1.0, 0.0);
                 double2 acc = cmk(0.0, 0.0);
 #pragma unroll
                 for (int n1 = 0; n1 < Q; ++n1) {
@@ -70,7 +79,7 @@ ILM_HD void passA_big_body(Ctx& ctx, const ConvArgs& a, double2* smem, int block
                     const double re = (r1 && n < a.f1.mx) ? a.f1.p[(size_t)row * a.f1.mx + n] : 0.0;
                     const double im = (r2 && n < a.f2.mx) ? a.f2.p[(size_t)row * a.f2.mx + n] : 0.0;
                     const double2 x = cmk(re, im);
-                    acc = cadd(acc, cls ? cmul(x, a.wl2x[((unsigned)n * cls) & mask]) : x);
+                    acc = cadd(acc, cls ? cmul(x, e ? cmul(wjm[n1], wte) : wjm[n1]) : x);
                 }
                 v[e] = acc;
             }
