@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -82,7 +82,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """Start of the timed region: only samples that arrive after this call are kept.  The process is started
+        before the warm-up steps because nvidia-smi's own start-up (NVML initialisation of every GPU of the box) contends
+        for the driver while it lasts: started right before the timed region it cost 22 ms per step on two GPUs."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -94,7 +100,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        rows = [r for t_row, r in self.rows if t_row >= t_mark]
+        if not rows and self.rows:                       # a timed region shorter than the sampling period: the nearest sample
+            rows = [self.rows[-1][1]]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 smax = float(r[1])
@@ -250,12 +260,13 @@ def main():
         cache.update_points(body)                        # the problem's DDF tables (what a new / moved body costs)
         return ilm.dirichlet_solve(cache, fplus_dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     lc1 = launches()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

@@ -666,7 +666,9 @@ static int schur_symm_build(ilm_plan* p, int kernel_id, double scale, double* dS
         if (P.c1 >= 0) cololo[P.c1] = olo;
         // cost of a pair in rows: its inverted rows plus the fixed part of its two launches (measured at 4096^2: 25 us + 0.062 us per
         // row of 8192 frequencies, i.e. 400 rows; the row cost scales with the transform length)
-        const int fixed = (int)(400LL * 4096 / p->Lx);
+        // (with two lanes most of the fixed part overlaps with the other lane's work: ILM_SCHUR_FIXED_ROWS overrides)
+        static const int fixed_env = getenv("ILM_SCHUR_FIXED_ROWS") ? atoi(getenv("ILM_SCHUR_FIXED_ROWS")) : -1;
+        const int fixed = (int)((long long)(fixed_env >= 0 ? fixed_env : (p->dual ? 150 : 400)) * 4096 / p->Lx);
         wsum[q + 1] = wsum[q] + fixed + (P.band ? std::max(ohi_g - olo, 1) : 4 * std::max(ohi_g - olo_g, 1));
     }
     // pair ranges of the ranks: contiguous, equal sums of inverted rows
@@ -1035,10 +1037,17 @@ extern "C" int ilm_dirichlet_poisson(ilm_plan* p, const double* fplus, const dou
     double* dSo = S_out ? io.out(S_out, (size_t)N * N) : nullptr;
     if (io.status) return io.status;
     const int nb = (N + 127) / 128;
+    // ILM_STEP_TRACE=1: CUDA-event times of the phases of this call on stderr (diagnostic)
+    static const bool step_trace = getenv("ILM_STEP_TRACE") != nullptr;
+    cudaEvent_t tev[8] = {};
+    int ntev = 0;
+    auto mark = [&]() { if (step_trace && ntev < 8) { cudaEventCreate(&tev[ntev]); cudaEventRecord(tev[ntev], p->stream); ++ntev; } };
+    mark();
     k_dirichlet_rhs<<<nb, 128, 0, p->stream>>>(N, dfp, dfm, nullptr, d, nullptr);
     ILM_LAUNCHED_API(p);
     ILM_TRY(surface_divergence_dev(p, ILM_NORMAL, d, fstar));
     ILM_TRY(conv_apply(p, 0, fref(p, ILM_NODES_PRIMAL, fstar), FieldRef{nullptr, 0, 0}));
+    mark();
     if (schur_symm_ok(p, ILM_RTLINVR, 0, 0, N)) {
         ILM_TRY(schur_symm_build(p, 0, 1.0, dS, p->comm != nullptr));
     } else {
@@ -1051,8 +1060,11 @@ extern "C" int ilm_dirichlet_poisson(ilm_plan* p, const double* fplus, const dou
     ILM_TRY(launch_interpolate(p, p->tab[ILM_NODES_PRIMAL], fstar, ef));
     k_dirichlet_rhs<<<nb, 128, 0, p->stream>>>(N, dfp, dfm, ef, nullptr, ds);
     ILM_LAUNCHED_API(p);
+    mark();
     ILM_TRY(ilm_dense_factor(N, dS, ipiv, p->stream));
+    mark();
     ILM_TRY(ilm_dense_solve(N, dS, ipiv, 1, ds, p->stream));
+    mark();
     k_negate_add<<<nb, 128, 0, p->stream>>>((size_t)N, ds, -1.0, nullptr, nullptr);
     ILM_LAUNCHED_API(p);
     if (df) {
@@ -1060,6 +1072,15 @@ extern "C" int ilm_dirichlet_poisson(ilm_plan* p, const double* fplus, const dou
         ILM_TRY(conv_apply(p, 0, fref(p, ILM_NODES_PRIMAL, df), FieldRef{nullptr, 0, 0}));
         k_negate_add<<<(unsigned)((P + 255) / 256), 256, 0, p->stream>>>(P, nullptr, 0.0, df, fstar);
         ILM_LAUNCHED_API(p);
+    }
+    mark();
+    if (step_trace && ntev == 6) {
+        cudaEventSynchronize(tev[5]);
+        float t[5];
+        for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
+        fprintf(stderr, "ilm_dirichlet_poisson rank %d: f* %.2f ms, Schur build (+ gather) %.2f, LU %.2f, solve %.2f, field %.2f\n", p->comm_rank, t[0],
+                t[1], t[2], t[3], t[4]);
+        for (int i = 0; i < 6; ++i) cudaEventDestroy(tev[i]);
     }
     return io.finish();
 }
