@@ -1092,8 +1092,9 @@ extern "C" int ilm_plan_release_spectrum(ilm_plan* p) {
     ILM_CHECK_PLAN(p);
     if (p->shared) { set_error("ilm_plan_release_spectrum: the buffers belong to the parent plan"); return ILM_EINVAL; }
     ILM_CUDA(cudaStreamSynchronize(p->stream));
-    cudaFree(p->S); cudaFree(p->S2);
-    p->S = p->S2 = nullptr;
+    if (p->stream2) ILM_CUDA(cudaStreamSynchronize(p->stream2));
+    cudaFree(p->S); cudaFree(p->S2); cudaFree(p->S2b);
+    p->S = p->S2 = p->S2b = nullptr;
     p->tmap_myp = -1;
     return ILM_OK;
 }
