@@ -120,6 +120,7 @@ SIGNATURES = {
     "ilm_column_range": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "ilm_create_schur_sharded": (_i, [_vp, _i, _i, _d, _dp]),
     "ilm_dirichlet_poisson": (_i, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "ilm_dirichlet_poisson_rows": (_i, [_vp, _dp, _dp, _dp, _i, _i, _dp, _dp]),
     "ilm_slab_solve": (_i, [_vp, C.POINTER(ilm_slab_info), _i, _i, _dp, _i, _dp, _dp, _dp]),
     "ilm_profile_conv": (_i, [_vp, _i, _i, C.POINTER(C.c_double * 3)]),
     "ilm_profile_conv_probe": (_i, [_vp, _i, _i, C.POINTER(C.c_double * 3)]),

@@ -803,13 +803,15 @@ def dirichlet_poisson(cache, fplus, fminus=None, S=None, filter_passes=0):
     return f, s, S
 
 
-def dirichlet_solve(cache, fplus, fminus=None, return_S=False, want_field=True):
+def dirichlet_solve(cache, fplus, fminus=None, return_S=False, want_field=True, field_rows=None):
     """`solve(prob::DirichletPoissonProblem, sys)` of test/literate/dirichlet.jl:71-107 as ONE call of the library
     (ilm_dirichlet_poisson): boundary data in, field and multiplier out; S, its LU factors and the intermediate
     fields never leave the device, and with a communicator on the plan (cache.comm_init) the Schur columns are
     sharded over its ranks inside the library.  fplus / fminus: numpy arrays or torch CUDA tensors of length N
     (the outputs live where the cache says: device=True -> torch).  Returns (f, s) or (f, s, S); want_field=False
-    (a rank of a sharded solve that only needs the multiplier) returns f = None and skips the last L^-1."""
+    (a rank of a sharded solve that only needs the multiplier) returns f = None and skips the last L^-1;
+    field_rows=(r0, r1) returns the grid rows [r0, r1) of the field as a flat buffer (ilm_dirichlet_poisson_rows: every rank
+    of a sharded solve keeps a slab of the result)."""
     N = cache.N
     dev = cache.device
 
@@ -829,9 +831,17 @@ def dirichlet_solve(cache, fplus, fminus=None, return_S=False, want_field=True):
         if v is not None and int(np.prod(v.shape)) != N:
             raise DimensionMismatch(f"dirichlet_solve: expected {N} surface values")
     mx, my = cache.g.layout_shape(L.NODES_PRIMAL)
-    f = Nodes(Primal, cache.g, data=_alloc(mx * my, dev, zero=False)) if want_field else None   # written whole by the library
     s = ScalarData(N, data=_alloc(N, dev, zero=False))
     S = _matrix(cache, N) if return_S else None
+    if field_rows is not None:
+        r0, r1 = int(field_rows[0]), int(field_rows[1])
+        if not (0 <= r0 < r1 <= my):
+            raise DimensionMismatch(f"dirichlet_solve: rows [{r0}, {r1}) outside the {my} rows of Nodes{{Primal}}")
+        f = _alloc((r1 - r0) * mx, dev, zero=False)
+        L.check(cache._lib.ilm_dirichlet_poisson_rows(cache._plan, _ptr(fp), _ptr(fm) if fm is not None else None, _ptr(f), r0, r1,
+                                                      _ptr(s.data), _ptr(S) if S is not None else None))
+        return (f, s, _as_matrix(S, N, N)) if return_S else (f, s)
+    f = Nodes(Primal, cache.g, data=_alloc(mx * my, dev, zero=False)) if want_field else None   # written whole by the library
     L.check(cache._lib.ilm_dirichlet_poisson(cache._plan, _ptr(fp), _ptr(fm) if fm is not None else None,
                                              _ptr(f.data) if f is not None else None,
                                              _ptr(s.data), _ptr(S) if S is not None else None))

@@ -49,6 +49,13 @@ double* Io::out(double* user, size_t n) {
     back.push_back({user, d, n * sizeof(double)});
     return (double*)d;
 }
+// the operator writes n doubles into a device scratch buffer; the entries [off, off + m) go to `user` (host or device, m doubles)
+double* Io::out_part(double* user, size_t n, size_t off, size_t m) {
+    void* d = stage(n * sizeof(double));
+    if (!d) return nullptr;
+    back.push_back({user, (double*)d + off, m * sizeof(double)});
+    return (double*)d;
+}
 double* Io::inout(double* user, size_t n) {
     if (n == 0 || is_device_ptr(user)) return user;
     void* d = stage(n * sizeof(double));
@@ -59,7 +66,7 @@ double* Io::inout(double* user, size_t n) {
 }
 int Io::finish() {
     if (status != ILM_OK) return status;
-    for (auto& b : back) ILM_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, p->stream));
+    for (auto& b : back) ILM_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDefault, p->stream));     // (out_part: `host` may be device memory)
     if (!back.empty()) ILM_CUDA(cudaStreamSynchronize(p->stream));
     return ILM_OK;
 }
@@ -1010,7 +1017,23 @@ __global__ void k_negate_add(size_t n, double* __restrict__ s, double sign_s, do
 // on the device.  With a communicator on the plan the Schur columns are sharded over its ranks; every rank returns
 // the full result.
 //   f* = L^-1 D_s (f+ - f-);  S = -E L^-1 R;  S s~ = (f+ + f-)/2 - E f*;  s = -s~;  f = L^-1 R s + f*
+static int dirichlet_poisson_impl(ilm_plan* p, const double* fplus, const double* fminus, double* f, int row0, int row1, double* s,
+                                  double* S_out);
 extern "C" int ilm_dirichlet_poisson(ilm_plan* p, const double* fplus, const double* fminus, double* f, double* s, double* S_out) {
+    return dirichlet_poisson_impl(p, fplus, fminus, f, 0, -1, s, S_out);
+}
+// The same with the field returned for the grid rows [row0, row1) only: `f_rows` holds (row1 - row0) rows of Nodes{Primal}
+// (x fastest).  For a sharded solve whose ranks each keep a slab of the result: every rank copies 1/nranks of the field to its
+// host instead of one rank copying all of it (the 134 MB device -> host copy is the end-to-end cost of a multi-GPU step).
+extern "C" int ilm_dirichlet_poisson_rows(ilm_plan* p, const double* fplus, const double* fminus, double* f_rows, int row0, int row1,
+                                          double* s, double* S_out) {
+    ILM_CHECK_PLAN(p);
+    const LayoutInfo li = layout_info(ILM_NODES_PRIMAL, p->g.NX, p->g.NY);
+    if (!f_rows || row0 < 0 || row1 > li.my || row0 >= row1) { set_error("ilm_dirichlet_poisson_rows: bad row range"); return ILM_ESIZE; }
+    return dirichlet_poisson_impl(p, fplus, fminus, f_rows, row0, row1, s, S_out);
+}
+static int dirichlet_poisson_impl(ilm_plan* p, const double* fplus, const double* fminus, double* f, int row0, int row1, double* s,
+                                  double* S_out) {
     ILM_CHECK_PLAN(p);
     const int N = p->N;
     if (!fplus || !s) { set_error("ilm_dirichlet_poisson: null argument"); return ILM_EINVAL; }
@@ -1032,8 +1055,17 @@ extern "C" int ilm_dirichlet_poisson(ilm_plan* p, const double* fplus, const dou
     Io io(p);
     const double* dfp = io.in(fplus, N);
     const double* dfm = fminus ? io.in(fminus, N) : nullptr;
-    double* df = f ? io.out(f, P) : nullptr;         // f == NULL: this rank wants the multiplier only (a sharded solve
-    double* ds = io.out(s, N);                       // returns the field on one rank): the last regularize + L^-1 are skipped
+    // f == NULL: this rank wants the multiplier only (a sharded solve returns the field on one rank): the last regularize
+    // + L^-1 are skipped.  Row range: the whole field is formed in a scratch buffer, the rows [row0, row1) go to the caller.
+    double* df = nullptr;
+    const bool part = f && row1 >= 0;
+    if (part) {
+        const LayoutInfo li = layout_info(ILM_NODES_PRIMAL, p->g.NX, p->g.NY);
+        df = io.out_part(f, P, (size_t)row0 * li.mx, (size_t)(row1 - row0) * li.mx);
+    } else if (f) {
+        df = io.out(f, P);
+    }
+    double* ds = io.out(s, N);
     double* dSo = S_out ? io.out(S_out, (size_t)N * N) : nullptr;
     if (io.status) return io.status;
     const int nb = (N + 127) / 128;

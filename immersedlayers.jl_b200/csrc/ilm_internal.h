@@ -167,6 +167,7 @@ struct Io {
     explicit Io(ilm_plan* plan) : p(plan) {}
     const double* in(const double* user, size_t n);
     double* out(double* user, size_t n);
+    double* out_part(double* user, size_t n, size_t off, size_t m);
     double* inout(double* user, size_t n);
     int finish();
 private:

@@ -327,6 +327,11 @@ int ilm_create_schur_sharded(ilm_plan* plan, int which, int kernel_id, double sc
  * the device, so a host caller moves 2N doubles in and one field + N doubles out.  f may be NULL: the rank wants
  * the multiplier only (sharded solve with the field returned on one rank); the last regularize + L^-1 are skipped. */
 int ilm_dirichlet_poisson(ilm_plan* plan, const double* fplus, const double* fminus, double* f, double* s, double* S_out);
+/* The same with the field returned for the grid rows [row0, row1) only (f_rows: (row1 - row0) rows of Nodes{Primal}, x fastest;
+ * host or device): in a sharded solve every rank keeps a slab of the result and copies 1/nranks of the field to its host.
+ * The reference has no counterpart (single process); rows of the union equal ilm_dirichlet_poisson's field bit for bit.     */
+int ilm_dirichlet_poisson_rows(ilm_plan* plan, const double* fplus, const double* fminus, double* f_rows, int row0, int row1,
+                               double* s, double* S_out);
 /* One inverse Laplacian of row-distributed fields over the plan's communicator: ilm_slab_forward -> exchange ->
  * ilm_slab_columns -> exchange -> ilm_slab_inverse with both exchanges issued inside the library (grouped
  * ncclSend / ncclRecv); w*_rows are this rank's rows [row0, row1) (device), sendbuf / recvbuf device scratch of

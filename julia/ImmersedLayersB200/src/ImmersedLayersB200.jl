@@ -277,6 +277,11 @@ factors stay on the device.  With a communicator on the plan (`comm_init!`) the 
 dirichlet_solve!(f::Union{Nodes{Primal},Nothing}, s::ScalarData, fplus::ScalarData, fminus::Union{ScalarData,Nothing}, c::B200Cache) =
     (check(ccall((:ilm_dirichlet_poisson, lib), Cint, (Ptr{Cvoid}, PD, PD, PD, PD, PD), c.plan, fplus.data,
                  fminus === nothing ? C_NULL : fminus.data, f === nothing ? C_NULL : f.data, s.data, C_NULL)); (f, s))   # f = nothing: multiplier only (sharded solve, field on one rank)
+# rows [row0, row1) (0-based, half-open) of the field only: every rank of a sharded solve keeps a slab of the result
+dirichlet_solve_rows!(frows::AbstractVector{Float64}, row0::Integer, row1::Integer, s::ScalarData, fplus::ScalarData,
+                      fminus::Union{ScalarData,Nothing}, c::B200Cache) =
+    (check(ccall((:ilm_dirichlet_poisson_rows, lib), Cint, (Ptr{Cvoid}, PD, PD, PD, Cint, Cint, PD, PD), c.plan, fplus.data,
+                 fminus === nothing ? C_NULL : fminus.data, frows, row0, row1, s.data, C_NULL)); (frows, s))
 comm_unique_id() = (id = zeros(UInt8, 128); check(ccall((:ilm_comm_unique_id, lib), Cint, (Ptr{UInt8}, Cint), id, 128)); id)
 # `id` from rank 0, distributed by the host program (MPI.Bcast!, a file, ...)
 comm_init!(c::B200Cache, id::Vector{UInt8}, rank::Integer, nranks::Integer) =

@@ -741,6 +741,11 @@ def test_dirichlet_solve_single_call(device):
     assert relerr(f2.array(), fr2) < 1e-10
     f3, s3 = ilm.dirichlet_solve(cache, fplus, want_field=False)  # a rank that only wants the multiplier (f = NULL)
     assert f3 is None and np.array_equal(tonp(s3.data), tonp(s2.data))
+    mx, my = g.layout_shape(L.NODES_PRIMAL)
+    f4, s4 = ilm.dirichlet_solve(cache, fplus, field_rows=(17, 90))   # a rank that keeps a slab of rows (ilm_dirichlet_poisson_rows)
+    assert np.array_equal(tonp(f4), tonp(f2.data)[17 * mx:90 * mx]) and np.array_equal(tonp(s4.data), tonp(s2.data))
+    with pytest.raises(ilm.DimensionMismatch):
+        ilm.dirichlet_solve(cache, fplus, field_rows=(90, my + 1))
     assert cache.comm_info() == (0, 1)
     assert relerr(tonp(ilm.create_schur_sharded(cache, "CLinvCT")), oc.create_CLinvCT()) < RTOL
 
