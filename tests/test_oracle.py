@@ -572,3 +572,25 @@ def test_heat_step_table_form_equals_probing():
     T1, s1 = o.heat_ifherk_step(c, T0, 0.0, dt, 1.0, tab_a, tab_c, tables, 0.0, 1.0)
     T2, s2 = o.heat_ifherk_step(c, T0, 0.0, dt, 1.0, tab_a, tab_c, tables, 0.0, 1.0, schur="table")
     assert np.abs(T1 - T2).max() < 1e-12 * np.abs(T1).max()
+
+
+@pytest.mark.parametrize("clipped", [False, True])
+@pytest.mark.parametrize("scaling", [o.GRID_SCALING, o.INDEX_SCALING])
+def test_schur_builders_are_symmetric_up_to_the_column_weight(scaling, clipped):
+    """What the symmetric Schur build of the CUDA path rests on (csrc/ilm_api.cu, schur_symm_build): with wR = e * wgt and
+    wE = e (the same DDF window on both sides) create_RTLinvR (src/matrix_operators.jl:9-30) is a symmetric matrix times
+    diag(wgt), wgt = ds/dx^2 (GridScaling) or 1 (IndexScaling): S[k,c] wgt_k = S[c,k] wgt_c to rounding -- also when windows
+    are clipped at the grid boundary (the dropped entries are dropped on both sides).  The stencil builders (create_CLinvCT,
+    create_GLinvD, create_GLinvD_cross) share the property for bodies away from the boundary only (a clipped edge window and
+    the truncated stencil next to it do not commute), which is why the CUDA path mirrors create_RTLinvR alone."""
+    g = ilm_b200.PhysicalGrid(60, 52, 4.0 / 58, (30, 26))
+    x, y, nx, ny, ds = ilm_b200.bodies.ellipse(0.9, 0.5, 1.4 * g.dx, center=(0.1, -0.05))
+    body = (x + 0.95, y, nx, ny, ds) if clipped else (x, y, nx, ny, ds)  # windows clipped at +x
+    G = ilm_b200.lgf.lgf_table(64)
+    oc = o.ScalarCache(o.Grid(g.NX, g.NY, g.dx, g.I0), *body, G, scaling=scaling)
+    w = ds / g.dx ** 2 if scaling == o.GRID_SCALING else np.ones_like(ds)
+    names = ("create_RTLinvR",) if clipped else ("create_RTLinvR", "create_CLinvCT", "create_GLinvD", "create_GLinvD_cross")
+    for name in names:
+        S = getattr(oc, name)()
+        T = S / w[None, :]
+        assert np.abs(T - T.T).max() <= 1e-13 * np.abs(T).max(), name
