@@ -14,6 +14,10 @@
 // ConvArgs::s2_rowmajor): a warp writes 512 contiguous bytes per row and pass C fetches whole rows with one bulk copy
 // each (first version: the 2x2-tile layout of the transform path, 32-byte pieces 131 KB apart -- 0.115 ms per launch).
 //
+// Patch mode (create_RTLinvR, PatchSrc): the non-zero rows are the two W x W DDF windows of the column pair, so the thread
+// sums x_r(kx) = sum_q i^q sum_a wR_q[r][a] w^{kx (i0_q + a)} itself at kernel start -- no pre-operator, no pass A.  The row
+// range [olo, ohi) is free: the symmetric Schur build (ilm_api.cu) asks for the rows from the pair's own windows upwards.
+//
 // The result is the same linear convolution as the transform path up to rounding (the sum over <= NR terms is
 // exact arithmetic on the same x-spectrum); tests compare both with the oracle at 1e-12.
 #include <cstdlib>

@@ -18,6 +18,11 @@
 // exceeds shared memory -- is one L2-resident line of 2L complex per cluster.
 //
 // Pass A re-reads a row Q times (real input, L2 hits); pass C gathers each spectrum row once per cluster.
+//
+// Round 2: the column pass of a convolution runs as THREE independent kernels per chunk of columns (passB1_big_body,
+// k_big_filter_Q*, passB2_big_body<FILTERED>: forward sub-transforms -> L2-resident hand-off block -> streaming Q x Q
+// filter -> inverse half transforms) on a spectrum whose rows are stored class by class (ConvGeom::rq), see below; the
+// cluster form (passB_big_body) still builds the multiplier (MODE 1) and serves ILM_BIG_CHUNK=0.
 #pragma once
 #include "ilm_conv.cuh"
 

@@ -3,9 +3,14 @@
 // and `C^5*s` in the reference's user-level algorithm
 // (test/literate/dirichlet.jl:99,124; neumann.jl:123,133).
 //
-// Right-looking blocked LU (NB = 32): panel factorisation by one CTA, row
-// interchanges, a triangular solve for the block row, and the trailing update
-// A22 -= A21 * A12 on the FP64 tensor pipe (mma.sync.m8n8k4.f64, "DMMA").
+// Right-looking blocked LU (NB = 32) with look-ahead on two prioritised streams.  The critical path is ONE kernel per
+// panel (k_lu_panel_v2): a thread-block cluster holds the panel in registers (thread per row), applies the previous
+// panel's update to its own 32 columns itself, and eliminates column by column with one cluster barrier per column,
+// LAPACK's pivot choices, no row moves (logical row indices).  Beside it, on the low-priority stream, the wide update of
+// the previous step: the panel's net row permutation as one gather + scatter per column with the block-row solve in
+// between (k_lu_swap_trsm), and A22 -= A21 * A12 on the FP64 tensor pipe (k_lu_gemm: mma.sync.m8n8k4.f64, "DMMA").
+// The earlier panel kernels (one CTA, shared-memory cluster, register panel with row moves) stay behind ILM_LU_V1 and
+// for n > 8192; ILM_LU_TRACE prints the phase times of the panel kernel.  Triangular solves: k_getrs_cluster.
 #include <cooperative_groups.h>
 
 #include <cstdio>
