@@ -197,7 +197,10 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
     std::vector<double> h((size_t)NX * NY);
     for (int j = 0; j < NY; ++j)
         for (int i = 0; i < NX; ++i) h[(size_t)j * NX + i] = G[(size_t)j * NX + i] * (i ? 2.0 : 1.0) * (j ? 2.0 : 1.0);
-    ConvGeom gg{LX, LY, NY, (NY + 1) & ~1};
+    // big LY: rows stored class by class (ConvGeom::rq = Q), MYp a multiple of 2 Q -- what conv_geom() builds on the device
+    constexpr int RQ = Len<LY>::big ? Len<LY>::Q : 1;
+    auto geom = [&](int MYrows) { const int unit = 2 * RQ; return ConvGeom{LX, LY, MYrows, (MYrows + unit - 1) / unit * unit, RQ}; };
+    ConvGeom gg = geom(NY);
     std::vector<double2> S(s_elems(gg)), S2;
     std::vector<double> Ghat(ghat_elems(gg), 0.0);
     a.g = gg; a.f1 = FieldRef{h.data(), NX, NY}; a.f2 = FieldRef{nullptr, 0, 0};
@@ -230,7 +233,7 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
         for (int l = 0; l < my2; ++l) if (l < rlo || l >= rhi) for (int k = 0; k < mx2; ++k) o2[(size_t)l * mx2 + k] = NAN;
     }
     int MY = second ? (my1 > my2 ? my1 : my2) : my1;
-    ConvGeom g2{LX, LY, MY, (MY + 1) & ~1};
+    ConvGeom g2 = geom(MY);
     S.assign(s_elems(g2), cmk(NAN, NAN));
     S2.assign(s_elems(g2), cmk(NAN, NAN));
     a.g = g2; a.f1 = FieldRef{o1.data(), mx1, my1};
@@ -248,8 +251,41 @@ static double test_conv(int NX, int NY, int mx1, int my1, int mx2, int my2, bool
             run_cta(CX::SMEM_BYTES, [&](HostCtx& c, double2* sm) { runA<LX>(c, a, sm, b, nbA); });
         int nworkB = (2 * g2.Lx + Len<LY>::cpw - 1) / Len<LY>::cpw;
         int nbB = nworkB > 3 ? 3 : nworkB;
-        for (int b = 0; b < nbB; ++b)
-            launchB<LY, 0>(a, b, nbB);
+        if constexpr (Len<LY>::big) {
+            // the split column pass of the device path: forward sub-transforms -> hand-off block, Q x Q filter in place,
+            // inverse half transforms (passB1_big_body / big_filter_point / passB2_big_body<FILTERED>), in two chunks
+            constexpr int Q = Len<LY>::Q;
+            const int ncols = 2 * g2.Lx, chunk = ncols / 2 + 1;
+            std::vector<double2> bigA((size_t)chunk * 2 * LY);
+            const unsigned mask = 2u * (unsigned)LY - 1u;
+            ConvArgs b2 = a;
+            b2.bigA = bigA.data();
+            for (int c0 = 0; c0 < ncols; c0 += chunk) {
+                b2.bc0 = c0; b2.bnc = std::min(chunk, ncols - c0);
+                const int items = b2.bnc * Q, nbs = items > 3 ? 3 : items;
+                for (int b = 0; b < nbs; ++b)
+                    run_cta(Len<LY>::Cfg::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passB1_big_body<Q>(c, b2, sm, b, nbs); });
+                for (int cc = 0; cc < b2.bnc; ++cc)
+                    for (int py = 0; py < 2; ++py)
+                        for (int kappa = 0; kappa < BIG_M; ++kappa) {
+                            const int col = c0 + cc, px = col / g2.Lx, m = col % g2.Lx;
+                            double2 wp[Q]; wp[0] = cmk(1.0, 0.0);
+                            wp[1] = a.wl2y[(2u * (unsigned)kappa + (unsigned)py) & mask];
+                            if constexpr (Q == 4) { wp[2] = cmul(wp[1], wp[1]); wp[3] = cmul(wp[2], wp[1]); }
+                            double2* scr = bigA.data() + ((size_t)cc * 2 + py) * (size_t)LY + kappa;
+                            const double* gp = a.Ghat + ((size_t)ghat_col(g2, px, m) * 2 + py) * (size_t)LY + kappa;
+                            double2 t[Q]; double gh[Q];
+                            for (int n1 = 0; n1 < Q; ++n1) { t[n1] = scr[(size_t)n1 * BIG_M]; gh[n1] = gp[(size_t)n1 * BIG_M]; }
+                            big_filter_point<Q>(t, gh, wp);
+                            for (int n1 = 0; n1 < Q; ++n1) scr[(size_t)n1 * BIG_M] = t[n1];
+                        }
+                for (int b = 0; b < nbs; ++b)
+                    run_cta(Len<LY>::Cfg::SMEM_BYTES, [&](HostCtx& c, double2* sm) { passB2_big_body<Q, true>(c, b2, sm, b, nbs); });
+            }
+        } else {
+            for (int b = 0; b < nbB; ++b)
+                launchB<LY, 0>(a, b, nbB);
+        }
         for (int b = 0; b < nb; ++b)
             launchC<LX>(a, b, nb);
     }
